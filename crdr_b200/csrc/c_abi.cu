@@ -1,0 +1,134 @@
+// extern "C" surface of libcrdr_sm100.so (declared in include/crdr_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace crdr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return e == cudaErrorNoKernelImageForDevice ? CRDR_ERR_UNSUPPORTED_ARCH : CRDR_ERR_CUDA;
+  }
+  return CRDR_OK;
+}
+
+static std::mutex g_status_mutex;
+static uint32_t* g_status[64] = {nullptr};
+
+uint32_t* device_status_word() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    set_error("cannot query the current CUDA device");
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lk(g_status_mutex);
+  if (!g_status[dev]) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+      set_error("libcrdr_sm100 needs an sm_100 class GPU (found compute %d.%d)", prop.major, prop.minor);
+      return nullptr;
+    }
+    uint32_t* p = nullptr;
+    if (cudaMalloc(&p, 256) != cudaSuccess || cudaMemset(p, 0, 256) != cudaSuccess) {
+      set_error("cannot allocate the device status word: %s", cudaGetErrorString(cudaGetLastError()));
+      return nullptr;
+    }
+    g_status[dev] = p;
+  }
+  return g_status[dev];
+}
+
+int conv2d_launch(const crdr_conv_desc* d, cudaStream_t stream);
+int gauss_launch(const crdr_gauss_desc* d, int mode, cudaStream_t st);
+int eb_launch(const crdr_eb_desc* d, int dequant, cudaStream_t st);
+int nhwc_to_nchw_launch(const float* x, int x_cs, int x_coff, int n, int hw, int c, float* out, cudaStream_t st);
+int affine_to_planes_launch(const float* x, int x_cs, int x_coff, int64_t m, int c, const float* scale,
+                            const float* shift, crdr_planes out, cudaStream_t st);
+int image_to_planes_launch(const float* img, int n, int h, int w, int hp, int wp, crdr_planes out, cudaStream_t st);
+int planes_to_image_launch(const float* x, int x_cs, int n, int hp, int wp, int h, int w, float* img, cudaStream_t st);
+int bits_launch(const float* lik, int n, int64_t per, float* bits, cudaStream_t st);
+int max_abs_launch(const float* x, int64_t count, float* out, cudaStream_t st);
+
+}  // namespace crdr
+
+using namespace crdr;
+
+extern "C" {
+
+int crdr_abi_version(void) { return CRDR_ABI_VERSION; }
+const char* crdr_last_error(void) { return g_err; }
+
+int crdr_status_reset(void* stream) {
+  uint32_t* p = device_status_word();
+  if (!p) return CRDR_ERR_CUDA;
+  cudaError_t e = cudaMemsetAsync(p, 0, 4, (cudaStream_t)stream);
+  if (e != cudaSuccess) { set_error("status_reset: %s", cudaGetErrorString(e)); return CRDR_ERR_CUDA; }
+  return CRDR_OK;
+}
+
+int crdr_status_read(uint32_t* flags, void* stream) {
+  uint32_t* p = device_status_word();
+  if (!p || !flags) return CRDR_ERR_CUDA;
+  cudaError_t e = cudaMemcpyAsync(flags, p, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e != cudaSuccess) { set_error("status_read: %s", cudaGetErrorString(e)); return CRDR_ERR_CUDA; }
+  if (*flags) {
+    set_error("device status flags 0x%x (%s%s)", *flags, (*flags & kFlagOverflow) ? "fp16 overflow " : "",
+              (*flags & kFlagTimeout) ? "pipeline timeout" : "");
+    return CRDR_ERR_DEVICE_FLAG;
+  }
+  return CRDR_OK;
+}
+
+int crdr_conv2d(const crdr_conv_desc* d, void* stream) {
+  if (!d) { set_error("conv2d: null descriptor"); return CRDR_ERR_BAD_SHAPE; }
+  return conv2d_launch(d, (cudaStream_t)stream);
+}
+
+int crdr_affine_to_planes(const float* x, int32_t x_cs, int32_t x_coff, int64_t m, int32_t c, const float* scale,
+                          const float* shift, crdr_planes out, void* stream) {
+  return affine_to_planes_launch(x, x_cs, x_coff, m, c, scale, shift, out, (cudaStream_t)stream);
+}
+
+int crdr_image_to_planes(const float* img, int32_t n, int32_t h, int32_t w, int32_t hp, int32_t wp, crdr_planes out,
+                         void* stream) {
+  return image_to_planes_launch(img, n, h, w, hp, wp, out, (cudaStream_t)stream);
+}
+
+int crdr_planes_to_image(const float* x, int32_t x_cs, int32_t n, int32_t hp, int32_t wp, int32_t h, int32_t w,
+                         float* img, void* stream) {
+  return planes_to_image_launch(x, x_cs, n, hp, wp, h, w, img, (cudaStream_t)stream);
+}
+
+int crdr_nhwc_to_nchw(const float* x, int32_t x_cs, int32_t x_coff, int32_t n, int32_t hw, int32_t c, float* out,
+                      void* stream) {
+  return nhwc_to_nchw_launch(x, x_cs, x_coff, n, hw, c, out, (cudaStream_t)stream);
+}
+
+int crdr_gauss_quantize(const crdr_gauss_desc* d, void* stream) { return gauss_launch(d, 0, (cudaStream_t)stream); }
+int crdr_gauss_indexes(const crdr_gauss_desc* d, void* stream) { return gauss_launch(d, 1, (cudaStream_t)stream); }
+int crdr_gauss_dequantize(const crdr_gauss_desc* d, void* stream) { return gauss_launch(d, 2, (cudaStream_t)stream); }
+int crdr_eb_quantize(const crdr_eb_desc* d, void* stream) { return eb_launch(d, 0, (cudaStream_t)stream); }
+int crdr_eb_dequantize(const crdr_eb_desc* d, void* stream) { return eb_launch(d, 1, (cudaStream_t)stream); }
+
+int crdr_bits_from_likelihood(const float* lik, int32_t n, int64_t per, float* bits, void* stream) {
+  return bits_launch(lik, n, per, bits, (cudaStream_t)stream);
+}
+int crdr_max_abs(const float* x, int64_t count, float* out, void* stream) {
+  return max_abs_launch(x, count, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

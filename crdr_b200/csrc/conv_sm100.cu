@@ -1,0 +1,726 @@
+// Implicit-GEMM convolution for sm_100a: tcgen05.mma (kind::f16) with TMEM accumulators.
+//
+//   out[m, co] = sum_k A[m, k] * W[co, k],   k = tap * Cin + ci,   m = pixel of the base grid
+//
+// * A (im2col of the NHWC fp16 activation planes) is gathered straight into the canonical
+//   K-major / 128B-swizzled UMMA shared-memory layout by 128 producer threads with 16-byte
+//   cp.async (zero-fill outside the image), so any kernel size / stride / transposed phase /
+//   two-range channel concatenation is the same code path.
+// * W tiles ([tile_n][64] fp16, K-major) arrive by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B)
+//   issued by one thread and complete on the same mbarrier as the gather.
+// * One thread issues tcgen05.mma.cta_group::1 (M=128, N=tile_n, K=16); accumulators live in TMEM.
+//   F16X3 precision keeps fp32-class accuracy on fp16 tensor cores: operands are stored as
+//   (hi, lo*2^11) fp16 pairs, D0 += Ahi*Bhi and D1 += Ahi*Blo + Alo*Bhi run as three MMAs per
+//   K step, and the epilogue forms D0 + 2^-11 * D1.
+// * Warps 0-3 gather, then become the epilogue: tcgen05.ld 32x32b.x16 -> fused bias / ReLU /
+//   beta-bias / residual / sigmoid-gate / half-tanh / gain -> fp16 planes (+ optional fp32) NHWC.
+//
+// Deterministic: fixed K order, no atomics on data, no split-K; a given output pixel sees the same
+// arithmetic whatever the batch size or tile position.
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace crdr {
+
+constexpr int kTileM = 128;
+constexpr int kKBlk = 64;                  // fp16 elements per K block = one 128-byte swizzle row
+constexpr uint32_t kAPlaneBytes = kTileM * 128;
+constexpr int kMaxStages = 6;
+constexpr int kThreads = 192;              // warps 0-3 gather/epilogue, warp 4 TMA + TMEM alloc, warp 5 MMA
+constexpr uint32_t kSmemLimit = 227 * 1024;
+
+struct alignas(64) ConvKParams {
+  CUtensorMap tm_hi;
+  CUtensorMap tm_lo;
+  crdr_conv_desc d;
+  int32_t m_total, nkb, cin, k_real, nplanes, stages, tmem_cols, use_tma;
+  int32_t vec_planes_out, vec_f32_out, vec_res_planes, vec_res_f32, vec_trunk;
+  uint32_t* status;
+};
+
+// ----------------------------------------------------------------------------------------------
+// PTX wrappers
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a pipeline bug must end in a trap with the status flag set, never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t* status) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+      atomicOr(status, kFlagTimeout);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"): rows are 128 bytes,
+// groups of 8 rows are 1024 bytes apart (SBO); LBO is unused for swizzled K-major operands.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: fp16 A/B (K-major), fp32 accumulate, M=128, N=n.
+__device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Epilogue for 16 consecutive output channels of one output pixel.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load16_planes(const crdr_planes& pl, int64_t pix, int co, bool vec, float (&o)[16]) {
+  const __half* hi = (const __half*)pl.hi + pix * pl.cs + pl.coff + co;
+  const __half* lo = pl.lo ? (const __half*)pl.lo + pix * pl.cs + pl.coff + co : nullptr;
+  if (vec) {
+    uint4 h[2], l[2];
+    h[0] = __ldg((const uint4*)hi);
+    h[1] = __ldg((const uint4*)hi + 1);
+    const __half* hh = (const __half*)h;
+    if (lo) {
+      l[0] = __ldg((const uint4*)lo);
+      l[1] = __ldg((const uint4*)lo + 1);
+      const __half* ll = (const __half*)l;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) o[e] = join_f16(hh[e], ll[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) o[e] = __half2float(hh[e]);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) o[e] = lo ? join_f16(hi[e], lo[e]) : __half2float(hi[e]);
+  }
+}
+
+__device__ __forceinline__ void epilogue16(const ConvKParams& P, int64_t opix, int co0, float (&acc)[16]) {
+  const crdr_conv_desc& d = P.d;
+  const int nvalid = min(16, d.cout - co0);
+  if (nvalid <= 0) return;
+  const bool full = nvalid == 16;
+  float res[16], trunk[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) { res[e] = 0.f; trunk[e] = 0.f; }
+  if (d.mode != CRDR_EPI_NONE) {
+    if (d.res_f32) {
+      const float* r = d.res_f32 + opix * d.res_f32_cs + d.res_f32_coff + co0;
+      if (full && P.vec_res_f32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 t = __ldg((const float4*)r + q);
+          res[4 * q] = t.x; res[4 * q + 1] = t.y; res[4 * q + 2] = t.z; res[4 * q + 3] = t.w;
+        }
+      } else {
+        for (int e = 0; e < nvalid; ++e) res[e] = r[e];
+      }
+    } else if (full) {
+      load16_planes(d.res, opix, co0, P.vec_res_planes, res);
+    } else {
+      for (int e = 0; e < nvalid; ++e) {
+        const int64_t o = opix * d.res.cs + d.res.coff + co0 + e;
+        res[e] = d.res.lo ? join_f16(((const __half*)d.res.hi)[o], ((const __half*)d.res.lo)[o])
+                          : __half2float(((const __half*)d.res.hi)[o]);
+      }
+    }
+    if (d.mode == CRDR_EPI_GATE) {
+      if (full) {
+        load16_planes(d.trunk, opix, co0, P.vec_trunk, trunk);
+      } else {
+        for (int e = 0; e < nvalid; ++e) {
+          const int64_t o = opix * d.trunk.cs + d.trunk.coff + co0 + e;
+          trunk[e] = d.trunk.lo ? join_f16(((const __half*)d.trunk.hi)[o], ((const __half*)d.trunk.lo)[o])
+                                : __half2float(((const __half*)d.trunk.hi)[o]);
+        }
+      }
+    }
+  }
+  float v[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const int co = co0 + e;
+    const bool ok = e < nvalid;
+    const float b = (ok && d.bias) ? __ldg(d.bias + co) : 0.f;
+    const float a = (ok && d.add_vec) ? __ldg(d.add_vec + co) : 0.f;
+    const float sc = (ok && d.scale) ? __ldg(d.scale + co) : 1.f;
+    const float sh = (ok && d.shift) ? __ldg(d.shift + co) : 0.f;
+    v[e] = epilogue_math(acc[e], b, d.relu, a, d.mode, res[e], trunk[e], sc, sh);
+  }
+  if (d.out_f32) {
+    float* o = d.out_f32 + opix * d.out_f32_cs + d.out_f32_coff + co0;
+    if (full && P.vec_f32_out) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ((float4*)o)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+      for (int e = 0; e < nvalid; ++e) o[e] = v[e];
+    }
+  }
+  if (d.out.hi) {
+    __half hh[16], ll[16];
+    const bool want_lo = d.out.lo != nullptr;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      if (want_lo) {
+        split_f16(v[e], hh[e], ll[e], P.status);
+      } else {
+        float x = v[e];
+        if (fabsf(x) > 65504.0f) { atomicOr(P.status, kFlagOverflow); x = copysignf(65504.0f, x); }
+        hh[e] = __float2half_rn(x);
+      }
+    }
+    const int64_t o = opix * d.out.cs + d.out.coff + co0;
+    __half* ph = (__half*)d.out.hi + o;
+    __half* pl = want_lo ? (__half*)d.out.lo + o : nullptr;
+    if (full && P.vec_planes_out) {
+      ((uint4*)ph)[0] = ((const uint4*)hh)[0];
+      ((uint4*)ph)[1] = ((const uint4*)hh)[1];
+      if (want_lo) {
+        ((uint4*)pl)[0] = ((const uint4*)ll)[0];
+        ((uint4*)pl)[1] = ((const uint4*)ll)[1];
+      }
+    } else {
+      for (int e = 0; e < nvalid; ++e) {
+        ph[e] = hh[e];
+        if (want_lo) pl[e] = ll[e];
+      }
+    }
+  }
+}
+
+// Output pixel (linear NHW index in the output tensor) of GEMM row m; -1 if m is past the end.
+__device__ __forceinline__ int64_t out_pixel_of_row(const crdr_conv_desc& d, int m, int m_total) {
+  if (m >= m_total) return -1;
+  const int bw = m % d.wb;
+  const int t = m / d.wb;
+  const int bh = t % d.hb;
+  const int n = t / d.hb;
+  return ((int64_t)n * d.hout + (bh * d.out_stride + d.out_ph)) * d.wout + (bw * d.out_stride + d.out_pw);
+}
+
+// ----------------------------------------------------------------------------------------------
+// The tcgen05 kernel
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ int s_dh[CRDR_MAX_TAPS + 1], s_dw[CRDR_MAX_TAPS + 1];
+
+  const crdr_conv_desc& d = P.d;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = P.stages;
+  const int nplanes = P.nplanes;
+  const int BN = d.tile_n;
+  const uint32_t b_bytes = (uint32_t)BN * 128u;
+  const uint32_t stage_bytes = (uint32_t)nplanes * (kAPlaneBytes + b_bytes);
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int m0 = blockIdx.x * kTileM;
+  const int n0 = blockIdx.y * BN;
+  const int nkb = P.nkb;
+
+  if (threadIdx.x < d.ntaps) {
+    s_dh[threadIdx.x] = d.dh[threadIdx.x];
+    s_dw[threadIdx.x] = d.dw[threadIdx.x];
+  }
+  if (threadIdx.x == 0) {
+    s_dh[d.ntaps] = 0;  // tap index of the zero-padded K tail
+    s_dw[d.ntaps] = 0;
+    const uint32_t full_count = P.use_tma ? 129u : 128u;
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), full_count);
+      mbar_init(smem_u32(&empty_bar[s]), 1u);
+    }
+    mbar_init(smem_u32(&accum_bar), 1u);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    if (lane == 0 && P.use_tma) {
+      prefetch_tmap(&P.tm_hi);
+      if (nplanes == 2) prefetch_tmap(&P.tm_lo);
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(&tmem_slot), (uint32_t)P.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ gather (im2col) producers
+    const int t = threadIdx.x;
+    const int j = t & 7;        // 16-byte chunk of the 128-byte K row
+    const int rbase = t >> 3;   // rows rbase + 16*i
+    const uint32_t row_off = (uint32_t)(rbase >> 3) * 1024u + (uint32_t)(rbase & 7) * 128u +
+                             (uint32_t)((j ^ (rbase & 7)) << 4);
+    int pix0[8], ih0[8], iw0[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + rbase + 16 * i;
+      if (m < P.m_total) {
+        const int bw = m % d.wb;
+        const int tt = m / d.wb;
+        const int bh = tt % d.hb;
+        const int n = tt / d.hb;
+        ih0[i] = bh * d.in_stride;
+        iw0[i] = bw * d.in_stride;
+        pix0[i] = (n * d.hin + ih0[i]) * d.win + iw0[i];
+      } else {
+        ih0[i] = -(1 << 28);
+        iw0[i] = 0;
+        pix0[i] = 0;
+      }
+    }
+    const __half* in_hi = (const __half*)d.in.hi;
+    const __half* in_lo = (const __half*)d.in.lo;
+    const __half* w_hi = (const __half*)d.w_hi;
+    const __half* w_lo = (const __half*)d.w_lo;
+    const int cin = P.cin;
+    int tap = 0, c = j * 8;  // position of this thread's chunk inside K for the current block
+    while (c >= cin) { c -= cin; ++tap; }
+    const int lookahead = S - 1;
+
+    for (int it = 0; it < nkb + lookahead; ++it) {
+      if (it >= lookahead) {
+        // the block issued `lookahead` iterations ago has landed: publish it to the MMA thread
+        switch (lookahead) {
+          case 1: cp_async_wait<0>(); break;
+          case 2: cp_async_wait<1>(); break;
+          case 3: cp_async_wait<2>(); break;
+          case 4: cp_async_wait<3>(); break;
+          default: cp_async_wait<4>(); break;
+        }
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&full_bar[(it - lookahead) % S]));
+      }
+      if (it < nkb) {
+        const int s = it % S;
+        const uint32_t par = ((uint32_t)(it / S) & 1u) ^ 1u;
+        mbar_wait(smem_u32(&empty_bar[s]), par, P.status);
+        const uint32_t stage = smem_base + (uint32_t)s * stage_bytes;
+        const bool kvalid = (tap < d.ntaps);
+        const int chan = (c < d.seg0_len) ? d.seg0_off + c : d.seg1_off + (c - d.seg0_len);
+        const int dhv = s_dh[min(tap, d.ntaps)], dwv = s_dw[min(tap, d.ntaps)];
+        const int tapoff = dhv * d.win + dwv;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int ih = ih0[i] + dhv, iw = iw0[i] + dwv;
+          const bool ok = kvalid && (unsigned)ih < (unsigned)d.hin && (unsigned)iw < (unsigned)d.win;
+          const int64_t off = ok ? ((int64_t)(pix0[i] + tapoff) * d.in.cs + d.in.coff + chan) : 0;
+          const uint32_t dst = stage + row_off + (uint32_t)i * 2048u;
+          cp_async16(dst, in_hi + off, ok ? 16u : 0u);
+          if (nplanes == 2) cp_async16(dst + kAPlaneBytes, in_lo + off, ok ? 16u : 0u);
+        }
+        if (!P.use_tma) {
+          const uint32_t bst = stage + (uint32_t)nplanes * kAPlaneBytes;
+          for (int i = 0; i < BN / 16; ++i) {
+            const int64_t off = (int64_t)(n0 + rbase + 16 * i) * d.k_pad + (int64_t)it * kKBlk + j * 8;
+            const uint32_t dst = bst + row_off + (uint32_t)i * 2048u;
+            cp_async16(dst, w_hi + off, 16u);
+            if (nplanes == 2) cp_async16(dst + b_bytes, w_lo + off, 16u);
+          }
+        }
+        c += kKBlk;
+        while (c >= cin) { c -= cin; ++tap; }
+      }
+      cp_async_commit();
+    }
+
+    // ------------------------------------------------------------------ epilogue
+    mbar_wait(smem_u32(&accum_bar), 0u, P.status);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    const int64_t opix = out_pixel_of_row(d, m0 + row, P.m_total);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      float acc[16];
+      tmem_ld16(lane_addr + (uint32_t)c0, acc);
+      if (nplanes == 2) {
+        float cross[16];
+        tmem_ld16(lane_addr + 256u + (uint32_t)c0, cross);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] = fmaf(cross[e], kLoInv, acc[e]);
+      }
+      if (opix >= 0) epilogue16(P, opix, n0 + c0, acc);
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ weight tiles by TMA
+    if (lane == 0 && P.use_tma) {
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % S;
+        const uint32_t par = ((uint32_t)(it / S) & 1u) ^ 1u;
+        mbar_wait(smem_u32(&empty_bar[s]), par, P.status);
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        const uint32_t bst = smem_base + (uint32_t)s * stage_bytes + (uint32_t)nplanes * kAPlaneBytes;
+        mbar_arrive_expect_tx(bar, (uint32_t)nplanes * b_bytes);
+        tma_load_2d(bst, &P.tm_hi, it * kKBlk, n0, bar);
+        if (nplanes == 2) tma_load_2d(bst + b_bytes, &P.tm_lo, it * kKBlk, n0, bar);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ MMA issue (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16((uint32_t)BN);
+      const uint32_t d0 = tmem_base;
+      const uint32_t d1 = tmem_base + 256u;
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % S;
+        mbar_wait(smem_u32(&full_bar[s]), (uint32_t)(it / S) & 1u, P.status);
+        tc_fence_after();
+        const uint32_t stage = smem_base + (uint32_t)s * stage_bytes;
+        const uint64_t a_hi = umma_desc_sw128(stage);
+        const uint64_t a_lo = umma_desc_sw128(stage + kAPlaneBytes);
+        const uint64_t b_hi = umma_desc_sw128(stage + (uint32_t)nplanes * kAPlaneBytes);
+        const uint64_t b_lo = umma_desc_sw128(stage + (uint32_t)nplanes * kAPlaneBytes + b_bytes);
+#pragma unroll
+        for (int k = 0; k < kKBlk / 16; ++k) {
+          const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 descriptor units
+          const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+          umma_f16(d0, a_hi + adv, b_hi + adv, idesc, first);
+          if (nplanes == 2) {
+            umma_f16(d1, a_hi + adv, b_lo + adv, idesc, first);
+            umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);
+          }
+        }
+        umma_commit(smem_u32(&empty_bar[s]));
+      }
+      umma_commit(smem_u32(&accum_bar));
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Scalar fp32 cross-check kernel over the same operands and epilogue (one thread per output element).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_simt_kernel(const __grid_constant__ ConvKParams P) {
+  const crdr_conv_desc& d = P.d;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int co = (int)(idx % d.cout);
+  const int64_t m64 = idx / d.cout;
+  if (m64 >= P.m_total) return;
+  const int m = (int)m64;
+  const int bw = m % d.wb;
+  const int tt = m / d.wb;
+  const int bh = tt % d.hb;
+  const int n = tt / d.hb;
+  const __half* in_hi = (const __half*)d.in.hi;
+  const __half* in_lo = (const __half*)d.in.lo;
+  const __half* w_hi = (const __half*)d.w_hi + (int64_t)co * d.k_pad;
+  const __half* w_lo = d.w_lo ? (const __half*)d.w_lo + (int64_t)co * d.k_pad : nullptr;
+  const bool three = P.nplanes == 2;
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int tp = 0; tp < d.ntaps; ++tp) {
+    const int ih = bh * d.in_stride + d.dh[tp], iw = bw * d.in_stride + d.dw[tp];
+    if ((unsigned)ih >= (unsigned)d.hin || (unsigned)iw >= (unsigned)d.win) continue;
+    const int64_t pbase = ((int64_t)(n * d.hin + ih) * d.win + iw) * d.in.cs + d.in.coff;
+    for (int c = 0; c < P.cin; ++c) {
+      const int chan = (c < d.seg0_len) ? d.seg0_off + c : d.seg1_off + (c - d.seg0_len);
+      const int k = tp * P.cin + c;
+      const float ah = __half2float(in_hi[pbase + chan]);
+      const float bhv = __half2float(w_hi[k]);
+      acc0 = fmaf(ah, bhv, acc0);
+      if (three) {
+        const float al = __half2float(in_lo[pbase + chan]);
+        const float bl = __half2float(w_lo[k]);
+        acc1 = fmaf(ah, bl, acc1);
+        acc1 = fmaf(al, bhv, acc1);
+      }
+    }
+  }
+  const float acc = fmaf(acc1, kLoInv, acc0);
+  const int64_t opix = out_pixel_of_row(d, m, P.m_total);
+  float res = 0.f, trunk = 0.f;
+  if (d.mode != CRDR_EPI_NONE) {
+    if (d.res_f32) {
+      res = d.res_f32[opix * d.res_f32_cs + d.res_f32_coff + co];
+    } else {
+      const int64_t o = opix * d.res.cs + d.res.coff + co;
+      res = d.res.lo ? join_f16(((const __half*)d.res.hi)[o], ((const __half*)d.res.lo)[o])
+                     : __half2float(((const __half*)d.res.hi)[o]);
+    }
+    if (d.mode == CRDR_EPI_GATE) {
+      const int64_t o = opix * d.trunk.cs + d.trunk.coff + co;
+      trunk = d.trunk.lo ? join_f16(((const __half*)d.trunk.hi)[o], ((const __half*)d.trunk.lo)[o])
+                         : __half2float(((const __half*)d.trunk.hi)[o]);
+    }
+  }
+  const float v = epilogue_math(acc, d.bias ? d.bias[co] : 0.f, d.relu, d.add_vec ? d.add_vec[co] : 0.f, d.mode, res,
+                                trunk, d.scale ? d.scale[co] : 1.f, d.shift ? d.shift[co] : 0.f);
+  if (d.out_f32) d.out_f32[opix * d.out_f32_cs + d.out_f32_coff + co] = v;
+  if (d.out.hi) {
+    const int64_t o = opix * d.out.cs + d.out.coff + co;
+    if (d.out.lo) {
+      __half h, l;
+      split_f16(v, h, l, P.status);
+      ((__half*)d.out.hi)[o] = h;
+      ((__half*)d.out.lo)[o] = l;
+    } else {
+      float x = v;
+      if (fabsf(x) > 65504.0f) { atomicOr(P.status, kFlagOverflow); x = copysignf(65504.0f, x); }
+      ((__half*)d.out.hi)[o] = __float2half_rn(x);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Host side: descriptor validation, tensor-map cache, launch
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+struct TmKey {
+  const void* ptr;
+  int32_t k_pad, rows, box_rows, dev;
+  bool operator==(const TmKey& o) const {
+    return ptr == o.ptr && k_pad == o.k_pad && rows == o.rows && box_rows == o.box_rows && dev == o.dev;
+  }
+};
+struct TmKeyHash {
+  size_t operator()(const TmKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    h ^= std::hash<int64_t>()(((int64_t)k.k_pad << 32) ^ ((int64_t)k.rows << 12) ^ ((int64_t)k.box_rows << 4) ^ k.dev) +
+         0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+static std::mutex g_tm_mutex;
+static std::unordered_map<TmKey, CUtensorMap, TmKeyHash> g_tm_cache;
+
+static int weight_tensor_map(const void* ptr, int k_pad, int rows, int box_rows, CUtensorMap* out) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  TmKey key{ptr, k_pad, rows, box_rows, dev};
+  {
+    std::lock_guard<std::mutex> lk(g_tm_mutex);
+    auto it = g_tm_cache.find(key);
+    if (it != g_tm_cache.end()) { *out = it->second; return CRDR_OK; }
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return CRDR_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)k_pad * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kKBlk, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap tm;
+  CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return CRDR_ERR_CUDA; }
+  {
+    std::lock_guard<std::mutex> lk(g_tm_mutex);
+    g_tm_cache[key] = tm;
+  }
+  *out = tm;
+  return CRDR_OK;
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+static bool planes_vec_ok(const crdr_planes& p) {
+  return p.hi && aligned16(p.hi) && (!p.lo || aligned16(p.lo)) && p.cs % 8 == 0 && p.coff % 8 == 0;
+}
+
+int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
+  const crdr_conv_desc& d = *dp;
+  const int cin = d.seg0_len + d.seg1_len;
+  if (d.ntaps < 1 || d.ntaps > CRDR_MAX_TAPS || cin <= 0 || d.n <= 0 || d.hb <= 0 || d.wb <= 0 || d.cout <= 0) {
+    set_error("conv2d: bad shape (ntaps=%d cin=%d n=%d hb=%d wb=%d cout=%d)", d.ntaps, cin, d.n, d.hb, d.wb, d.cout);
+    return CRDR_ERR_BAD_SHAPE;
+  }
+  if (d.seg0_len % 8 || d.seg1_len % 8 || d.seg0_off % 8 || d.seg1_off % 8 || d.in.cs % 8 || d.in.coff % 8) {
+    set_error("conv2d: input channel ranges / strides must be multiples of 8");
+    return CRDR_ERR_MISALIGNED;
+  }
+  if (d.k_pad % kKBlk || d.k_pad < d.ntaps * cin || d.tile_n % 16 || d.tile_n < 16 || d.tile_n > 256 ||
+      d.cout_pad % d.tile_n || d.cout > d.cout_pad) {
+    set_error("conv2d: bad packed-weight geometry (k_pad=%d need>=%d, tile_n=%d, cout=%d, cout_pad=%d)", d.k_pad,
+              d.ntaps * cin, d.tile_n, d.cout, d.cout_pad);
+    return CRDR_ERR_BAD_SHAPE;
+  }
+  const bool three = d.precision == CRDR_PREC_F16X3;
+  if (!d.in.hi || !d.w_hi || (three && (!d.in.lo || !d.w_lo))) {
+    set_error("conv2d: missing operand plane for precision %d", d.precision);
+    return CRDR_ERR_BAD_SHAPE;
+  }
+  if (!aligned16(d.in.hi) || !aligned16(d.in.lo) || !aligned16(d.w_hi) || !aligned16(d.w_lo)) {
+    set_error("conv2d: operand pointers must be 16-byte aligned");
+    return CRDR_ERR_MISALIGNED;
+  }
+  if (d.mode != CRDR_EPI_NONE && !d.res_f32 && !d.res.hi) {
+    set_error("conv2d: epilogue mode %d needs a residual tensor", d.mode);
+    return CRDR_ERR_BAD_SHAPE;
+  }
+  if (d.mode == CRDR_EPI_GATE && !d.trunk.hi) {
+    set_error("conv2d: gate epilogue needs a trunk tensor");
+    return CRDR_ERR_BAD_SHAPE;
+  }
+  const int64_t m_total = (int64_t)d.n * d.hb * d.wb;
+  if (m_total > (1LL << 30) || (int64_t)d.n * d.hin * d.win > (1LL << 30)) {
+    set_error("conv2d: pixel count exceeds 2^30");
+    return CRDR_ERR_BAD_SHAPE;
+  }
+
+  ConvKParams P;
+  memset(&P, 0, sizeof(P));
+  P.d = d;
+  P.m_total = (int32_t)m_total;
+  P.cin = cin;
+  P.k_real = d.ntaps * cin;
+  P.nkb = (P.k_real + kKBlk - 1) / kKBlk;
+  P.nplanes = three ? 2 : 1;
+  P.status = device_status_word();
+  if (!P.status) return CRDR_ERR_CUDA;
+  P.vec_planes_out = d.out.hi ? planes_vec_ok(d.out) : 0;
+  P.vec_f32_out = d.out_f32 && aligned16(d.out_f32) && d.out_f32_cs % 4 == 0 && d.out_f32_coff % 4 == 0;
+  P.vec_res_planes = d.res.hi ? planes_vec_ok(d.res) : 0;
+  P.vec_res_f32 = d.res_f32 && aligned16(d.res_f32) && d.res_f32_cs % 4 == 0 && d.res_f32_coff % 4 == 0;
+  P.vec_trunk = d.trunk.hi ? planes_vec_ok(d.trunk) : 0;
+
+  if (d.engine == CRDR_ENGINE_SIMT) {
+    const int64_t total = m_total * d.cout;
+    const int64_t blocks = (total + 255) / 256;
+    if (blocks > 0x7fffffffLL) { set_error("conv2d(simt): problem too large"); return CRDR_ERR_BAD_SHAPE; }
+    conv_simt_kernel<<<(unsigned)blocks, 256, 0, stream>>>(P);
+    return check_launch("conv_simt_kernel");
+  }
+
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit - 2048);
+  });
+  if (attr_err != cudaSuccess) {
+    set_error("conv2d: cannot opt in to large shared memory: %s", cudaGetErrorString(attr_err));
+    return CRDR_ERR_UNSUPPORTED_ARCH;
+  }
+  const uint32_t stage_bytes = (uint32_t)P.nplanes * (kAPlaneBytes + (uint32_t)d.tile_n * 128u);
+  const uint32_t budget = kSmemLimit - 2048 - 1024;
+  int stages = (int)(budget / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > P.nkb + 1) stages = P.nkb + 1;
+  if (stages < 2) { set_error("conv2d: tile_n=%d leaves fewer than 2 pipeline stages", d.tile_n); return CRDR_ERR_BAD_SHAPE; }
+  P.stages = stages;
+  int cols = three ? 512 : 32;
+  while (cols < d.tile_n) cols *= 2;
+  P.tmem_cols = cols;
+  P.use_tma = d.engine == CRDR_ENGINE_TCGEN05;
+  if (P.use_tma) {
+    int rc = weight_tensor_map(d.w_hi, d.k_pad, d.cout_pad, d.tile_n, &P.tm_hi);
+    if (rc) return rc;
+    if (three) {
+      rc = weight_tensor_map(d.w_lo, d.k_pad, d.cout_pad, d.tile_n, &P.tm_lo);
+      if (rc) return rc;
+    }
+  }
+  const uint32_t smem = (uint32_t)stages * stage_bytes + 1024;
+  dim3 grid((unsigned)((m_total + kTileM - 1) / kTileM), (unsigned)(d.cout_pad / d.tile_n));
+  conv_tcgen05_kernel<<<grid, kThreads, smem, stream>>>(P);
+  return check_launch("conv_tcgen05_kernel");
+}
+
+}  // namespace crdr

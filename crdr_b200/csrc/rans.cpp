@@ -1,0 +1,205 @@
+// Host range coder for the CRDR bitstream (see include/crdr_rans.h).
+//
+// Streaming formulation: the encoder walks the symbols back to front and feeds each symbol's
+// sub-symbols (escape nibbles, escape-length run, table symbol) straight into the rANS state, so no
+// per-stream symbol queue is materialised; emitted 32-bit words are collected and reversed once.
+#include "../../include/crdr_rans.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <thread>
+#include <vector>
+
+namespace {
+
+constexpr uint32_t kPrecision = 16;
+constexpr uint32_t kBypassBits = 4;
+constexpr int32_t kBypassMax = (1 << kBypassBits) - 1;
+constexpr uint64_t kRansL = 1ull << 31;
+
+struct Encoder {
+  uint64_t x = kRansL;
+  std::vector<uint32_t> words;  // in emission order (the stream stores them reversed)
+
+  inline void put(uint32_t start, uint32_t freq) {
+    const uint64_t x_max = ((kRansL >> kPrecision) << 32) * (uint64_t)freq;
+    if (x >= x_max) { words.push_back((uint32_t)x); x >>= 32; }
+    x = ((x / freq) << kPrecision) + (x % freq) + start;
+  }
+  inline void put_bits(uint32_t val) {
+    const uint64_t x_max = ((kRansL >> 16) << 32) * (uint64_t)(1u << (16 - kBypassBits));
+    if (x >= x_max) { words.push_back((uint32_t)x); x >>= 32; }
+    x = (x << kBypassBits) | val;
+  }
+};
+
+int64_t encode_one(const int32_t* symbols, const int32_t* indexes, int64_t n, const crdr_cdf_tables* t, uint8_t* out,
+                   int64_t out_cap) {
+  Encoder enc;
+  enc.words.reserve((size_t)(n / 4 + 16));
+  for (int64_t i = n - 1; i >= 0; --i) {
+    const int32_t ci = indexes[i];
+    if (ci < 0 || ci >= t->n_cdf) return std::numeric_limits<int64_t>::min();
+    const int32_t* cdf = t->cdfs + (int64_t)ci * t->cdf_stride;
+    const int32_t max_value = t->cdf_sizes[ci] - 2;
+    int32_t value = symbols[i] - t->offsets[ci];
+    bool escape = false;
+    uint32_t raw = 0;
+    if (value < 0) { raw = (uint32_t)(-2 * value - 1); value = max_value; escape = true; }
+    else if (value >= max_value) { raw = (uint32_t)(2 * (value - max_value)); value = max_value; escape = true; }
+    if (escape) {
+      int32_t nb = 0;
+      while ((raw >> (nb * kBypassBits)) != 0) ++nb;
+      // forward order is: [run of 15s][remainder][nibble 0 .. nibble nb-1]; feed it reversed
+      for (int32_t j = nb - 1; j >= 0; --j) enc.put_bits((raw >> (j * kBypassBits)) & kBypassMax);
+      int32_t full = nb / kBypassMax, rem = nb % kBypassMax;
+      enc.put_bits((uint32_t)rem);
+      for (int32_t r = 0; r < full; ++r) enc.put_bits((uint32_t)kBypassMax);
+    }
+    enc.put((uint32_t)cdf[value], (uint32_t)(cdf[value + 1] - cdf[value]));
+  }
+  const int64_t nbytes = 4 * ((int64_t)enc.words.size() + 2);
+  if (nbytes > out_cap) return -nbytes;
+  uint32_t* o = reinterpret_cast<uint32_t*>(out);
+  uint32_t w0 = (uint32_t)enc.x, w1 = (uint32_t)(enc.x >> 32);
+  std::memcpy(out, &w0, 4);
+  std::memcpy(out + 4, &w1, 4);
+  (void)o;
+  size_t k = 8;
+  for (size_t j = enc.words.size(); j-- > 0; k += 4) std::memcpy(out + k, &enc.words[j], 4);
+  return nbytes;
+}
+
+struct Decoder {
+  std::vector<uint32_t> buf;
+  size_t pos = 0;
+  uint64_t x = 0;
+
+  inline uint32_t next_word() { return pos < buf.size() ? buf[pos++] : 0u; }
+  inline uint32_t get_bits() {
+    uint32_t val = (uint32_t)(x & ((1u << kBypassBits) - 1));
+    x >>= kBypassBits;
+    if (x < kRansL) x = (x << 32) | next_word();
+    return val;
+  }
+};
+
+int decode_some(Decoder* d, const int32_t* indexes, int64_t n, const crdr_cdf_tables* t, int32_t* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    const int32_t ci = indexes[i];
+    if (ci < 0 || ci >= t->n_cdf) return 1;
+    const int32_t* cdf = t->cdfs + (int64_t)ci * t->cdf_stride;
+    const int32_t size = t->cdf_sizes[ci];
+    const int32_t max_value = size - 2;
+    const int32_t cum = (int32_t)(d->x & ((1u << kPrecision) - 1));
+    // first entry strictly greater than cum (the tables are increasing)
+    const int32_t* it = std::upper_bound(cdf, cdf + size, cum);
+    const int32_t s = (int32_t)(it - cdf) - 1;
+    const uint32_t start = (uint32_t)cdf[s], freq = (uint32_t)(cdf[s + 1] - cdf[s]);
+    d->x = (uint64_t)freq * (d->x >> kPrecision) + (d->x & ((1ull << kPrecision) - 1)) - start;
+    if (d->x < kRansL) d->x = (d->x << 32) | d->next_word();
+    int32_t value = s;
+    if (value == max_value) {
+      int32_t val = (int32_t)d->get_bits();
+      int32_t nb = val;
+      while (val == kBypassMax) { val = (int32_t)d->get_bits(); nb += val; }
+      int32_t raw = 0;
+      for (int32_t j = 0; j < nb; ++j) raw |= (int32_t)d->get_bits() << (j * kBypassBits);
+      value = raw >> 1;
+      value = (raw & 1) ? -value - 1 : value + max_value;
+    }
+    out[i] = value + t->offsets[ci];
+  }
+  return 0;
+}
+
+template <class F>
+void parallel_for(int32_t count, int32_t threads, F&& fn) {
+  int32_t nt = threads > 0 ? threads : (int32_t)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min(nt, count));
+  if (nt == 1) { for (int32_t i = 0; i < count; ++i) fn(i); return; }
+  std::atomic<int32_t> next{0};
+  std::vector<std::thread> pool;
+  pool.reserve(nt);
+  for (int32_t w = 0; w < nt; ++w)
+    pool.emplace_back([&] { for (int32_t i; (i = next.fetch_add(1)) < count;) fn(i); });
+  for (auto& th : pool) th.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+int crdr_pmf_to_quantized_cdf(const float* pmf, int64_t n, int32_t precision, uint32_t* cdf) {
+  if (n <= 0 || precision < 1 || precision > 16) return 1;
+  for (int64_t i = 0; i < n; ++i)
+    if (!(pmf[i] >= 0.f) || !std::isfinite(pmf[i])) return 1;
+  const uint32_t one = 1u << precision;
+  cdf[0] = 0;
+  uint32_t total = 0;
+  for (int64_t i = 0; i < n; ++i) { cdf[i + 1] = (uint32_t)std::round(pmf[i] * (float)one); total += cdf[i + 1]; }
+  if (total == 0) return 2;
+  uint32_t run = 0;
+  for (int64_t i = 1; i <= n; ++i) { run += (uint32_t)(((uint64_t)one * cdf[i]) / total); cdf[i] = run; }
+  cdf[n] = one;
+  for (int64_t i = 0; i < n; ++i) {
+    if (cdf[i] != cdf[i + 1]) continue;
+    // empty bin: take one count from the narrowest bin that can spare it
+    uint32_t best_freq = ~0u;
+    int64_t donor = -1;
+    for (int64_t j = 0; j < n; ++j) {
+      const uint32_t f = cdf[j + 1] - cdf[j];
+      if (f > 1 && f < best_freq) { best_freq = f; donor = j; }
+    }
+    if (donor < 0) return 3;
+    if (donor < i) { for (int64_t j = donor + 1; j <= i; ++j) --cdf[j]; }
+    else { for (int64_t j = i + 1; j <= donor; ++j) ++cdf[j]; }
+  }
+  return 0;
+}
+
+int64_t crdr_rans_encode_with_indexes(const int32_t* symbols, const int32_t* indexes, int64_t n,
+                                      const crdr_cdf_tables* t, uint8_t* out, int64_t out_cap) {
+  return encode_one(symbols, indexes, n, t, out, out_cap);
+}
+
+int crdr_rans_encode_batch(int32_t count, const int32_t* const* symbols, const int32_t* const* indexes,
+                           const int64_t* n, const crdr_cdf_tables* t, uint8_t* const* out, const int64_t* out_cap,
+                           int64_t* lengths, int32_t threads) {
+  parallel_for(count, threads, [&](int32_t i) { lengths[i] = encode_one(symbols[i], indexes[i], n[i], t, out[i], out_cap[i]); });
+  for (int32_t i = 0; i < count; ++i)
+    if (lengths[i] < 0) return 1;
+  return 0;
+}
+
+void* crdr_rans_decoder_new(void) { return new Decoder(); }
+void crdr_rans_decoder_free(void* dec) { delete static_cast<Decoder*>(dec); }
+
+int crdr_rans_decoder_set_stream(void* dec, const uint8_t* stream, int64_t nbytes) {
+  Decoder* d = static_cast<Decoder*>(dec);
+  if (!d || nbytes < 8) return 1;
+  d->buf.assign((size_t)((nbytes + 3) / 4), 0u);
+  std::memcpy(d->buf.data(), stream, (size_t)nbytes);
+  d->x = (uint64_t)d->buf[0] | ((uint64_t)d->buf[1] << 32);
+  d->pos = 2;
+  return 0;
+}
+
+int crdr_rans_decoder_decode_stream(void* dec, const int32_t* indexes, int64_t n, const crdr_cdf_tables* t,
+                                    int32_t* out) {
+  return decode_some(static_cast<Decoder*>(dec), indexes, n, t, out);
+}
+
+int crdr_rans_decode_batch(int32_t count, void* const* decoders, const int32_t* const* indexes, const int64_t* n,
+                           const crdr_cdf_tables* t, int32_t* const* out, int32_t threads) {
+  std::atomic<int> bad{0};
+  parallel_for(count, threads, [&](int32_t i) {
+    if (decode_some(static_cast<Decoder*>(decoders[i]), indexes[i], n[i], t, out[i])) bad.store(1);
+  });
+  return bad.load();
+}
+
+}  // extern "C"

@@ -1,0 +1,207 @@
+"""Host-side layer engine: activation planes, weight packing and convolution launches.
+
+Everything here is plumbing above the C ABI (``include/crdr_b200.h``): tensors are allocated with
+torch, the arithmetic happens in ``libcrdr_sm100.so``.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import native as nv
+
+LO_SCALE = 2048.0
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class Act:
+    """NHWC activation stored as fp16 planes: value ~= hi + lo / 2048 (lo is None for single-term tensors)."""
+
+    __slots__ = ("hi", "lo", "n", "h", "w", "c")
+
+    def __init__(self, hi, lo):
+        self.hi, self.lo = hi, lo
+        self.n, self.h, self.w, self.c = hi.shape
+
+    @staticmethod
+    def empty(n, h, w, c, two=True, device="cuda"):
+        hi = torch.empty((n, h, w, c), dtype=torch.float16, device=device)
+        lo = torch.empty((n, h, w, c), dtype=torch.float16, device=device) if two else None
+        return Act(hi, lo)
+
+    @staticmethod
+    def zeros(n, h, w, c, two=True, device="cuda"):
+        hi = torch.zeros((n, h, w, c), dtype=torch.float16, device=device)
+        lo = torch.zeros((n, h, w, c), dtype=torch.float16, device=device) if two else None
+        return Act(hi, lo)
+
+    @staticmethod
+    def from_nchw(x, two=True):
+        """Test helper (torch ops, not a hot-path kernel): fp32 NCHW -> planes."""
+        xh = x.permute(0, 2, 3, 1).contiguous().float()
+        hi = xh.half()
+        lo = ((xh - hi.float()) * LO_SCALE).half() if two else None
+        return Act(hi, lo)
+
+    def to_nchw(self):
+        """Test helper: planes -> fp32 NCHW."""
+        v = self.hi.float()
+        if self.lo is not None:
+            v = v + self.lo.float() / LO_SCALE
+        return v.permute(0, 3, 1, 2).contiguous()
+
+    def planes(self, coff=0):
+        return nv.Planes(self.hi.data_ptr(), self.lo.data_ptr() if self.lo is not None else None, self.c, coff)
+
+    @property
+    def pixels(self):
+        return self.n * self.h * self.w
+
+
+NULL_PLANES = nv.Planes(None, None, 0, 0)
+
+
+def split_weight(w2d, device):
+    """[rows, k] fp32 -> (hi, lo) fp16 with lo = (w - hi) * 2^11."""
+    w2d = w2d.to(device=device, dtype=torch.float32).contiguous()
+    hi = w2d.half()
+    lo = ((w2d - hi.float()) * LO_SCALE).half()
+    return hi.contiguous(), lo.contiguous()
+
+
+class Phase:
+    """One GEMM of a (possibly transposed) convolution: taps, packed weights and output phase."""
+
+    __slots__ = ("dh", "dw", "w_hi", "w_lo", "k_pad", "out_ph", "out_pw")
+
+
+def pick_tile_n(cout_pad, m_tiles, three):
+    """Largest N tile (multiple of 16, divides cout_pad, <= 256) that still yields >= 148 CTAs; tiles below
+    64 columns (shared-memory-bound MMAs) are used only when the layer itself is that narrow."""
+    cands = [t for t in range(16, min(cout_pad, 256) + 1, 16) if cout_pad % t == 0]
+    good = [t for t in cands if t >= min(64, cands[-1])]
+    best = good[0]
+    for t in good:
+        if m_tiles * (cout_pad // t) >= 148:
+            best = t
+    return best
+
+
+class ConvOp:
+    """Conv2d / ConvTranspose2d of the reference lowered to implicit-GEMM launches.
+
+    weight: Conv2d  [Cout, Cin, kh, kw]   (nn.Conv2d, e.g. elic_autoencoder.py:42)
+            Deconv  [Cin, Cout, kh, kw]   (nn.ConvTranspose2d, elic_layers.py:21)
+    """
+
+    def __init__(self, weight, bias, transposed=False, stride=1, padding=0, output_padding=0, cin_pad=None,
+                 device="cuda"):
+        w = weight.detach().to(torch.float32).cpu()
+        self.transposed, self.stride, self.padding, self.output_padding = transposed, stride, padding, output_padding
+        if transposed:
+            cin, cout, kh, kw = w.shape
+        else:
+            cout, cin, kh, kw = w.shape
+        self.cin_real, self.cout, self.kh, self.kw = cin, cout, kh, kw
+        self.cin = cin_pad or cin
+        assert self.cin % 8 == 0, "input channels must be padded to a multiple of 8"
+        self.cout_pad = round_up(cout, 16)
+        self.bias = None if bias is None else bias.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.device = device
+        self.phases = []
+        s, p = stride, padding
+        phase_list = [(0, 0)] if not transposed else [(a, b) for a in range(s) for b in range(s)]
+        for ph, pw in phase_list:
+            taps, cols = [], []
+            for i in range(kh):
+                for j in range(kw):
+                    if transposed:
+                        if (ph + p - i) % s or (pw + p - j) % s:
+                            continue
+                        taps.append(((ph + p - i) // s, (pw + p - j) // s))
+                        blk = w[:, :, i, j].t()  # [Cout, Cin]
+                    else:
+                        taps.append((i - p, j - p))
+                        blk = w[:, :, i, j]  # [Cout, Cin]
+                    if self.cin != cin:
+                        blk = torch.nn.functional.pad(blk, (0, self.cin - cin))
+                    cols.append(blk)
+            assert 0 < len(taps) <= nv.MAX_TAPS
+            k_real = len(taps) * self.cin
+            k_pad = round_up(k_real, 64)
+            w2d = torch.zeros((self.cout_pad, k_pad), dtype=torch.float32)
+            w2d[:cout, :k_real] = torch.cat(cols, dim=1)
+            phs = Phase()
+            phs.dh = [t[0] for t in taps]
+            phs.dw = [t[1] for t in taps]
+            phs.w_hi, phs.w_lo = split_weight(w2d, device)
+            phs.k_pad, phs.out_ph, phs.out_pw = k_pad, ph, pw
+            self.phases.append(phs)
+
+    def out_hw(self, h, w):
+        if self.transposed:
+            f = lambda x, k: (x - 1) * self.stride - 2 * self.padding + k + self.output_padding
+        else:
+            f = lambda x, k: (x + 2 * self.padding - k) // self.stride + 1
+        return f(h, self.kh), f(w, self.kw)
+
+    def __call__(self, x, out=None, out_coff=0, segs=None, relu=False, add_vec=None, mode=nv.EPI_NONE, res=None,
+                 res_coff=0, trunk=None, scale=None, shift=None, out_f32=None, out_f32_coff=0,
+                 precision=nv.PREC_F16X3, engine=nv.ENGINE_TCGEN05, two_out=None, tile_n=None, want_planes=True):
+        """x: Act.  segs: [(channel_offset, length), ...] (<= 2) selecting the input channels (default: all).
+        res: Act or fp32 NHWC tensor.  Returns the output Act (or None when want_planes is False)."""
+        hout, wout = self.out_hw(x.h, x.w)
+        if segs is None:
+            segs = [(0, self.cin)]
+        assert sum(l for _, l in segs) == self.cin, (segs, self.cin)
+        if two_out is None:
+            two_out = precision == nv.PREC_F16X3
+        if out is None and want_planes:
+            out = Act.empty(x.n, hout, wout, self.cout, two=two_out, device=x.hi.device)
+        d = nv.ConvDesc()
+        d.inp = x.planes(0)
+        d.n, d.hin, d.win = x.n, x.h, x.w
+        d.seg0_off, d.seg0_len = segs[0]
+        d.seg1_off, d.seg1_len = segs[1] if len(segs) > 1 else (0, 0)
+        d.cout_pad, d.cout = self.cout_pad, self.cout
+        d.hout, d.wout = hout, wout
+        d.out = out.planes(out_coff) if out is not None else NULL_PLANES
+        if out_f32 is not None:
+            d.out_f32, d.out_f32_cs, d.out_f32_coff = out_f32.data_ptr(), out_f32.shape[-1], out_f32_coff
+        d.bias = self.bias.data_ptr() if self.bias is not None else None
+        d.relu = int(relu)
+        d.add_vec = add_vec.data_ptr() if add_vec is not None else None
+        d.mode = mode
+        if res is not None:
+            if isinstance(res, Act):
+                d.res = res.planes(res_coff)
+            else:
+                d.res_f32, d.res_f32_cs, d.res_f32_coff = res.data_ptr(), res.shape[-1], res_coff
+        if trunk is not None:
+            d.trunk = trunk.planes(0)
+        d.scale = scale.data_ptr() if scale is not None else None
+        d.shift = shift.data_ptr() if shift is not None else None
+        d.precision, d.engine = precision, engine
+        st = nv.stream_handle()
+        L = nv.lib()
+        for phs in self.phases:
+            if self.transposed:
+                hb = -(-(hout - phs.out_ph) // self.stride)
+                wb = -(-(wout - phs.out_pw) // self.stride)
+                d.in_stride, d.out_stride = 1, self.stride
+            else:
+                hb, wb = hout, wout
+                d.in_stride, d.out_stride = self.stride, 1
+            d.hb, d.wb = hb, wb
+            d.out_ph, d.out_pw = phs.out_ph, phs.out_pw
+            d.ntaps = len(phs.dh)
+            for i, (a, b) in enumerate(zip(phs.dh, phs.dw)):
+                d.dh[i], d.dw[i] = a, b
+            d.w_hi, d.w_lo, d.k_pad = phs.w_hi.data_ptr(), phs.w_lo.data_ptr(), phs.k_pad
+            m_tiles = -(-(x.n * hb * wb) // 128)
+            d.tile_n = tile_n or pick_tile_n(self.cout_pad, m_tiles, precision == nv.PREC_F16X3)
+            nv.check(L.crdr_conv2d(C.byref(d), st))
+        return out

@@ -1,0 +1,141 @@
+"""ctypes binding of ``libcrdr_sm100.so`` (the C ABI in ``include/crdr_b200.h``) and ``libcrdr_rans.so``.
+
+PyTorch is only the allocator / stream provider here: every wrapper passes raw device pointers and the
+current stream handle across the C boundary.  There is no CPU fallback: if the library is missing the
+import of a product path fails loudly with build instructions.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SM100_SO = os.path.join(_HERE, "libcrdr_sm100.so")
+RANS_SO = os.path.join(_HERE, "libcrdr_rans.so")
+
+MAX_TAPS = 25
+PREC_F16X3, PREC_F16X1 = 0, 1
+ENGINE_TCGEN05, ENGINE_TCGEN05_NOTMA, ENGINE_SIMT = 0, 1, 2
+EPI_NONE, EPI_RESIDUAL, EPI_GATE, EPI_HALF_TANH = 0, 1, 2, 3
+
+
+class Planes(C.Structure):
+    _fields_ = [("hi", C.c_void_p), ("lo", C.c_void_p), ("cs", C.c_int32), ("coff", C.c_int32)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("inp", Planes),
+        ("n", C.c_int32), ("hin", C.c_int32), ("win", C.c_int32),
+        ("seg0_off", C.c_int32), ("seg0_len", C.c_int32), ("seg1_off", C.c_int32), ("seg1_len", C.c_int32),
+        ("hb", C.c_int32), ("wb", C.c_int32), ("in_stride", C.c_int32),
+        ("ntaps", C.c_int32),
+        ("dh", C.c_int8 * MAX_TAPS), ("dw", C.c_int8 * MAX_TAPS),
+        ("w_hi", C.c_void_p), ("w_lo", C.c_void_p),
+        ("k_pad", C.c_int32), ("cout_pad", C.c_int32), ("cout", C.c_int32),
+        ("tile_n", C.c_int32),
+        ("hout", C.c_int32), ("wout", C.c_int32), ("out_stride", C.c_int32), ("out_ph", C.c_int32), ("out_pw", C.c_int32),
+        ("out", Planes),
+        ("out_f32", C.c_void_p), ("out_f32_cs", C.c_int32), ("out_f32_coff", C.c_int32),
+        ("bias", C.c_void_p),
+        ("relu", C.c_int32),
+        ("add_vec", C.c_void_p),
+        ("mode", C.c_int32),
+        ("res", Planes),
+        ("res_f32", C.c_void_p), ("res_f32_cs", C.c_int32), ("res_f32_coff", C.c_int32),
+        ("trunk", Planes),
+        ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("precision", C.c_int32), ("engine", C.c_int32),
+    ]
+
+
+class GaussDesc(C.Structure):
+    _fields_ = [
+        ("y", C.c_void_p), ("y_cs", C.c_int32), ("y_coff", C.c_int32),
+        ("mu", C.c_void_p), ("sigma", C.c_void_p),
+        ("ms_cs", C.c_int32), ("mu_coff", C.c_int32), ("sigma_coff", C.c_int32),
+        ("n", C.c_int32), ("hw", C.c_int32), ("c", C.c_int32),
+        ("scale_bound", C.c_float),
+        ("scale_table", C.c_void_p), ("ntable", C.c_int32),
+        ("yq_planes", Planes),
+        ("yq_f32", C.c_void_p), ("yq_f32_cs", C.c_int32), ("yq_f32_coff", C.c_int32),
+        ("symbols", C.c_void_p), ("indexes", C.c_void_p), ("likelihood", C.c_void_p),
+        ("c_total", C.c_int32), ("nchw_coff", C.c_int32),
+    ]
+
+
+class EbDesc(C.Structure):
+    _fields_ = [
+        ("z", C.c_void_p), ("z_cs", C.c_int32),
+        ("n", C.c_int32), ("hw", C.c_int32), ("c", C.c_int32),
+        ("params", C.c_void_p), ("medians", C.c_void_p),
+        ("zhat_planes", Planes),
+        ("symbols", C.c_void_p), ("zhat_nchw", C.c_void_p), ("likelihood", C.c_void_p),
+    ]
+
+
+# every symbol include/crdr_b200.h declares (tests check the library exports all of them)
+SM100_SYMBOLS = [
+    "crdr_abi_version", "crdr_last_error", "crdr_status_reset", "crdr_status_read", "crdr_conv2d",
+    "crdr_affine_to_planes", "crdr_image_to_planes", "crdr_planes_to_image", "crdr_nhwc_to_nchw",
+    "crdr_gauss_quantize", "crdr_gauss_indexes", "crdr_gauss_dequantize", "crdr_eb_quantize",
+    "crdr_eb_dequantize", "crdr_bits_from_likelihood", "crdr_max_abs",
+]
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libcrdr_sm100.so (built by ``__graft_entry__.build()`` / ``python -m crdr_b200.build``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SM100_SO):
+            raise NativeError(
+                f"{SM100_SO} is missing: the CUDA extension is the only implementation of the hot path "
+                "(no CPU fallback). Build it with `python -m crdr_b200.build`.")
+        L = C.CDLL(SM100_SO)
+        L.crdr_last_error.restype = C.c_char_p
+        vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+        L.crdr_status_reset.argtypes = [vp]
+        L.crdr_status_read.argtypes = [C.POINTER(C.c_uint32), vp]
+        L.crdr_conv2d.argtypes = [C.POINTER(ConvDesc), vp]
+        L.crdr_affine_to_planes.argtypes = [vp, i32, i32, i64, i32, vp, vp, Planes, vp]
+        L.crdr_image_to_planes.argtypes = [vp, i32, i32, i32, i32, i32, Planes, vp]
+        L.crdr_planes_to_image.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp]
+        L.crdr_nhwc_to_nchw.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
+        for name in ("crdr_gauss_quantize", "crdr_gauss_indexes", "crdr_gauss_dequantize"):
+            getattr(L, name).argtypes = [C.POINTER(GaussDesc), vp]
+        for name in ("crdr_eb_quantize", "crdr_eb_dequantize"):
+            getattr(L, name).argtypes = [C.POINTER(EbDesc), vp]
+        L.crdr_bits_from_likelihood.argtypes = [vp, i32, i64, vp, vp]
+        L.crdr_max_abs.argtypes = [vp, i64, vp, vp]
+        assert L.crdr_abi_version() == 1
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise NativeError(f"crdr status {rc}: {lib().crdr_last_error().decode()}")
+
+
+def stream_handle():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def status_reset():
+    check(lib().crdr_status_reset(stream_handle()))
+
+
+def status_check():
+    """Synchronise the current stream and raise if any kernel flagged fp16 overflow / a pipeline timeout."""
+    flags = C.c_uint32(0)
+    check(lib().crdr_status_read(C.byref(flags), stream_handle()))

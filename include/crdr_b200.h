@@ -1,0 +1,216 @@
+/*
+ * crdr_b200 -- C ABI of the B200-native CRDR codec hot path (libcrdr_sm100.so).
+ *
+ * The reference (iwa-shi/CRDR) is pure PyTorch and has no FFI of its own; every
+ * entry point below replaces a *library call site* of the reference, cited as
+ * file:line relative to the reference tree.  Plain pointers and sizes only; all
+ * device buffers are owned by the caller (the PyTorch caching allocator in the
+ * shipped host code).  Every launch is asynchronous on the given stream.
+ *
+ * Return value: 0 on success, otherwise a crdr_status; a human readable message
+ * for the calling thread is available from crdr_last_error().
+ *
+ * Activation storage inside the path ("planes"): NHWC, fp16.  A tensor is a pair
+ * of planes (hi, lo) with  x ~= hi + lo * 2^-11  (22 significant bits); the lo
+ * plane is NULL for single-term (fp16) tensors.  Pixel stride (`cs`, in
+ * elements) and channel offset (`coff`) let kernels read/write channel ranges of
+ * a wider tensor in place (the ChARM support tensor, SURVEY 2.1 "torch.cat").
+ */
+#ifndef CRDR_B200_H_
+#define CRDR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRDR_ABI_VERSION 1
+#define CRDR_MAX_TAPS 25
+
+typedef enum {
+  CRDR_OK = 0,
+  CRDR_ERR_BAD_SHAPE = 1,
+  CRDR_ERR_MISALIGNED = 2,
+  CRDR_ERR_UNSUPPORTED_ARCH = 3,
+  CRDR_ERR_CUDA = 4,
+  CRDR_ERR_DEVICE_FLAG = 5 /* a kernel raised the device status word (fp16 overflow / pipeline timeout) */
+} crdr_status;
+
+/* Arithmetic of the contraction. */
+typedef enum {
+  CRDR_PREC_F16X3 = 0, /* error-compensated 3-term fp16 split, fp32 accumulate: fp32-class */
+  CRDR_PREC_F16X1 = 1  /* plain fp16 operands, fp32 accumulate */
+} crdr_precision;
+
+/* Which kernel executes the contraction. */
+typedef enum {
+  CRDR_ENGINE_TCGEN05 = 0,       /* tcgen05.mma + TMEM accumulators, weights by TMA (the product path) */
+  CRDR_ENGINE_TCGEN05_NOTMA = 1, /* same, weights staged by cp.async (bring-up / bisect) */
+  CRDR_ENGINE_SIMT = 2           /* scalar fp32 CUDA-core kernel over the same operands (on-device cross-check) */
+} crdr_engine;
+
+typedef enum {
+  CRDR_EPI_NONE = 0,
+  CRDR_EPI_RESIDUAL = 1,  /* v += res                                   (BaseBlock / NLAMResBlock skip) */
+  CRDR_EPI_GATE = 2,      /* v = res + trunk * sigmoid(v)               (ChengNLAM.forward, cheng_nlam.py:23-29) */
+  CRDR_EPI_HALF_TANH = 3  /* v = res + 0.5 * tanh(v)                    (LRP, minnen20_charm_context_model.py:127-131) */
+} crdr_epilogue_mode;
+
+typedef struct {
+  const void* hi; /* fp16 plane, NHWC */
+  const void* lo; /* fp16 plane holding (x - hi) * 2^11, or NULL */
+  int32_t cs;     /* elements per pixel */
+  int32_t coff;   /* first channel */
+} crdr_planes;
+
+/*
+ * One convolution-shaped contraction  out[m, co] = sum_{t, ci} in[pix(m) + tap_t, ci] * W[co, t*Cin + ci]
+ * followed by the fused epilogue
+ *     v = acc + bias[co];  if relu: v = max(v, 0);  v += add_vec[co];
+ *     mode (residual / gate / half-tanh);  v = v * scale[co] + shift[co]
+ * Replaces nn.Conv2d / nn.ConvTranspose2d (+ the element-wise ops that follow) at:
+ *   elic_autoencoder.py:42-52 (g_a convs), elic_layers.py:14-36 (up_conv, BaseBlock),
+ *   elic_interpca_beta_cond_autoencoder.py:42-66 (BetaCondBaseBlock), cheng_nlam.py:5-47,
+ *   minnen20_hyperprior.py:17-19,50-52, minnen20_charm_context_model.py:26-38,
+ *   interp_channel_attention.py:54-73 (gain/bias folded into scale/shift).
+ *
+ * Geometry: the GEMM rows m enumerate a base grid N x Hb x Wb.  Input pixel for tap t is
+ * (b_h * in_stride + dh[t], b_w * in_stride + dw[t]) (zero outside the image); the output pixel is
+ * (b_h * out_stride + out_ph, b_w * out_stride + out_pw).  A stride-2 Conv2d has in_stride 2; a stride-2
+ * ConvTranspose2d is four launches (one per output phase) with out_stride 2.
+ * Input channels are the concatenation of up to two channel ranges of the same NHWC tensor.
+ */
+typedef struct {
+  /* input */
+  crdr_planes in;
+  int32_t n, hin, win;
+  int32_t seg0_off, seg0_len, seg1_off, seg1_len; /* Cin = seg0_len + seg1_len, each a multiple of 8 */
+  /* base grid and taps */
+  int32_t hb, wb, in_stride;
+  int32_t ntaps;
+  int8_t dh[CRDR_MAX_TAPS], dw[CRDR_MAX_TAPS];
+  /* packed weights [cout_pad][k_pad] fp16 (hi, lo*2^11), k = t*Cin + ci, k_pad % 64 == 0 */
+  const void* w_hi;
+  const void* w_lo;
+  int32_t k_pad, cout_pad, cout;
+  int32_t tile_n; /* N tile (multiple of 16, <= 256, divides cout_pad) */
+  /* output */
+  int32_t hout, wout, out_stride, out_ph, out_pw;
+  crdr_planes out;  /* may have hi == NULL */
+  float* out_f32;   /* optional NHWC fp32 output */
+  int32_t out_f32_cs, out_f32_coff;
+  /* epilogue */
+  const float* bias;
+  int32_t relu;
+  const float* add_vec;
+  int32_t mode;
+  crdr_planes res;      /* residual as planes ... */
+  const float* res_f32; /* ... or as NHWC fp32 (takes precedence) */
+  int32_t res_f32_cs, res_f32_coff;
+  crdr_planes trunk;
+  const float* scale;
+  const float* shift;
+  /* arithmetic */
+  int32_t precision; /* crdr_precision */
+  int32_t engine;    /* crdr_engine */
+} crdr_conv_desc;
+
+int crdr_abi_version(void);
+const char* crdr_last_error(void);
+
+/* Device status word (one per device, lives in device memory owned by the library:
+ * bit0 fp16 overflow in an epilogue, bit1 pipeline wait timeout).  `crdr_status_read`
+ * synchronises the stream. */
+int crdr_status_reset(void* stream);
+int crdr_status_read(uint32_t* flags, void* stream);
+
+int crdr_conv2d(const crdr_conv_desc* d, void* stream);
+
+/* fp32 NHWC [m][c] -> planes, v = x*scale[c] + shift[c] (InterpChAtt on a tensor that has no producing
+ * conv: decoder input, elic_interpca_beta_cond_autoencoder.py:153-156).  scale/shift may be NULL. */
+int crdr_affine_to_planes(const float* x, int32_t x_cs, int32_t x_coff, int64_t m, int32_t c,
+                          const float* scale, const float* shift, crdr_planes out, void* stream);
+
+/* Image pre-processing: NCHW fp32 in [-1,1] (n,3,h,w) -> reflect-pad bottom/right to (hp,wp) -> NHWC planes with
+ * 8 channels (3 real + 5 zero).  Replaces BaseModel.data_preprocess/_pad_image (base_model.py:35-43,145-152). */
+int crdr_image_to_planes(const float* img, int32_t n, int32_t h, int32_t w, int32_t hp, int32_t wp,
+                         crdr_planes out, void* stream);
+/* Post-processing: NHWC fp32 (n,hp,wp,cs) first 3 channels -> crop (h,w) -> clamp(-1,1) -> NCHW fp32.
+ * Replaces data_postprocess/_crop_image (base_model.py:45-57,165-167). */
+int crdr_planes_to_image(const float* x, int32_t x_cs, int32_t n, int32_t hp, int32_t wp, int32_t h, int32_t w,
+                         float* img, void* stream);
+
+/* NHWC fp32 [n][hw][cs](coff..coff+c) -> NCHW fp32 [n][c][hw]  (API-facing tensors). */
+int crdr_nhwc_to_nchw(const float* x, int32_t x_cs, int32_t x_coff, int32_t n, int32_t hw, int32_t c,
+                      float* out, void* stream);
+
+/*
+ * GaussianConditional, evaluation mode, one channel slice (CompressAI GaussianConditional.forward /
+ * quantize / _likelihood / build_indexes as called at minnen20_charm_context_model.py:118,123,170,186).
+ *   q = rint(y - mu) (half-to-even);  yq = q + mu;  s = max(sigma, bound)
+ *   L = Phi((.5-|q|)/s) - Phi((-.5-|q|)/s), Phi(x) = .5*erfc(-x/sqrt2);  L = max(L, 1e-9)
+ *   index = (ntable-1) - #{k < ntable-1 : s <= table[k]}
+ * Inputs NHWC fp32: y [m][y_cs] at y_coff; mu, sigma [m][ms_cs] at mu_coff / sigma_coff.  c channels (<= 32 per
+ * call is typical).  Outputs: yq as planes (+ optional NHWC fp32), symbols / indexes int32 and likelihood fp32
+ * in NCHW order [n][c_total][hw] at channel offset nchw_coff.
+ */
+typedef struct {
+  const float* y;
+  int32_t y_cs, y_coff;
+  const float* mu;
+  const float* sigma;
+  int32_t ms_cs, mu_coff, sigma_coff;
+  int32_t n, hw, c;
+  float scale_bound;
+  const float* scale_table;
+  int32_t ntable;
+  crdr_planes yq_planes;
+  float* yq_f32;
+  int32_t yq_f32_cs, yq_f32_coff;
+  int32_t* symbols;   /* NCHW, may be NULL */
+  int32_t* indexes;   /* NCHW, may be NULL */
+  float* likelihood;  /* NCHW, may be NULL */
+  int32_t c_total, nchw_coff;
+} crdr_gauss_desc;
+int crdr_gauss_quantize(const crdr_gauss_desc* d, void* stream);
+
+/* Decoder side of the same slice: indexes from sigma only (build_indexes, :221) ... */
+int crdr_gauss_indexes(const crdr_gauss_desc* d, void* stream);
+/* ... and yq = symbol + mu (GaussianConditional.dequantize, :226); `symbols` is the NCHW int32 input. */
+int crdr_gauss_dequantize(const crdr_gauss_desc* d, void* stream);
+
+/*
+ * EntropyBottleneck, evaluation mode (CompressAI EntropyBottleneck.forward/_likelihood/_logits_cumulative as
+ * called at beta_cond_interpca_hyperprior_charm_model.py:43,58,95).  z: NHWC fp32 [m][c].
+ * params: per channel 58 floats = softplus(matrix0)[3] bias0[3] tanh(factor0)[3] | softplus(matrix1)[9] bias1[3]
+ * tanh(factor1)[3] | (same for 2, 3) | softplus(matrix4)[3] bias4[1];  medians[c].
+ * Outputs: z_hat planes (NHWC), symbols int32 / z_hat fp32 / likelihood fp32 in NCHW.
+ */
+typedef struct {
+  const float* z;
+  int32_t z_cs;
+  int32_t n, hw, c;
+  const float* params;
+  const float* medians;
+  crdr_planes zhat_planes;
+  int32_t* symbols;
+  float* zhat_nchw;
+  float* likelihood;
+} crdr_eb_desc;
+int crdr_eb_quantize(const crdr_eb_desc* d, void* stream);
+/* Decoder: symbols (NCHW int32) -> z_hat planes + NCHW fp32. */
+int crdr_eb_dequantize(const crdr_eb_desc* d, void* stream);
+
+/* bits[i] = -sum_j log2(L[i][j]) over `per` contiguous elements, fixed summation order
+ * (hyperprior_model.py:80-85 likelihood_to_bit). */
+int crdr_bits_from_likelihood(const float* lik, int32_t n, int64_t per, float* bits, void* stream);
+
+/* max |x| over `count` floats -> out[0] (header byte, codec_utils.py:88). */
+int crdr_max_abs(const float* x, int64_t count, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRDR_B200_H_ */

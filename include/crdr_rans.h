@@ -1,0 +1,55 @@
+/*
+ * crdr_rans -- host range coder of the CRDR bitstream (libcrdr_rans.so, plain C ABI).
+ *
+ * The reference reaches its coder through CompressAI 1.2.4's pybind module `compressai.ans`
+ * (RansEncoder.encode_with_indexes inside EntropyModel.compress; RansDecoder.set_stream /
+ * decode_stream at src/models/subnet/context_model/minnen20_charm_context_model.py:201-202,222-224)
+ * and `compressai._CXX.pmf_to_quantized_cdf` (EntropyModel._pmf_to_cdf).  Those calls marshal Python
+ * lists; these entry points take flat int32 arrays instead (zero copy from numpy / pinned torch
+ * buffers) and add batch variants that code independent streams on a thread pool.
+ * The byte format is the reference's: rANS, 64-bit state, 32-bit words, 16-bit precision, 4-bit bypass.
+ */
+#ifndef CRDR_RANS_H_
+#define CRDR_RANS_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* CDF tables: `cdfs` is [n_cdf][cdf_stride] int32, `cdf_sizes[i]` entries of row i are valid,
+ * `offsets[i]` is the symbol value of bin 0. */
+typedef struct {
+  const int32_t* cdfs;
+  int32_t cdf_stride;
+  const int32_t* cdf_sizes;
+  const int32_t* offsets;
+  int32_t n_cdf;
+} crdr_cdf_tables;
+
+/* pmf[n] (float32) -> cdf[n+1] (uint32, cdf[n] == 2^precision, every bin non-empty). 0 on success. */
+int crdr_pmf_to_quantized_cdf(const float* pmf, int64_t n, int32_t precision, uint32_t* cdf);
+
+/* Encode n symbols; returns the stream length in bytes, or -(needed bytes) if out_cap is too small,
+ * or INT64_MIN on invalid input (index out of range). */
+int64_t crdr_rans_encode_with_indexes(const int32_t* symbols, const int32_t* indexes, int64_t n,
+                                      const crdr_cdf_tables* t, uint8_t* out, int64_t out_cap);
+/* `count` independent streams coded concurrently; stream i uses symbols[i]/indexes[i] (n[i] entries) and
+ * writes to out[i] (capacity out_cap[i]); lengths[i] receives the per-stream return value. */
+int crdr_rans_encode_batch(int32_t count, const int32_t* const* symbols, const int32_t* const* indexes,
+                           const int64_t* n, const crdr_cdf_tables* t, uint8_t* const* out, const int64_t* out_cap,
+                           int64_t* lengths, int32_t threads);
+
+void* crdr_rans_decoder_new(void);
+void crdr_rans_decoder_free(void* dec);
+/* Copies the stream; subsequent decode_stream calls continue from the same coder state. */
+int crdr_rans_decoder_set_stream(void* dec, const uint8_t* stream, int64_t nbytes);
+int crdr_rans_decoder_decode_stream(void* dec, const int32_t* indexes, int64_t n, const crdr_cdf_tables* t,
+                                    int32_t* out);
+/* decoders[i] decodes n[i] symbols with indexes[i] into out[i], concurrently. */
+int crdr_rans_decode_batch(int32_t count, void* const* decoders, const int32_t* const* indexes, const int64_t* n,
+                           const crdr_cdf_tables* t, int32_t* const* out, int32_t threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
