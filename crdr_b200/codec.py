@@ -1,0 +1,411 @@
+"""Lowered CRDR codec: the reference's subnets expressed as sequences of C-ABI kernel launches.
+
+Each ``*Engine`` is built from the corresponding slice of the model ``state_dict`` (reference layout,
+fp32 OIHW / IOHW) and owns the packed (hi, lo) fp16 weight matrices.  Activations stay NHWC fp16
+planes between launches; element-wise work (bias, ReLU, InterpChAtt gain, beta bias, skip, NLAM gate,
+LRP tanh) is fused into the producing convolution's epilogue.
+
+Reference call stacks this replaces: SURVEY.md section 3.1-3.3; per-engine citations below.
+"""
+import ctypes as C
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import native as nv
+from .engine import Act, ConvOp, NULL_PLANES
+
+X3, X1 = nv.PREC_F16X3, nv.PREC_F16X1
+
+
+def _sub(sd, prefix):
+    """state_dict entries below ``prefix.`` with the prefix stripped."""
+    p = prefix + "."
+    return {k[len(p):]: v for k, v in sd.items() if k.startswith(p)}
+
+
+class Conv:
+    """ConvOp + the launch-time defaults (precision / engine) shared by a whole sub-network."""
+
+    def __init__(self, sd, name, cfg, **kw):
+        self.op = ConvOp(sd[name + ".weight"], sd[name + ".bias"], device=cfg.device, **kw)
+        self.cfg = cfg
+
+    def __call__(self, x, **kw):
+        kw.setdefault("precision", self.cfg.precision)
+        kw.setdefault("engine", self.cfg.engine)
+        return self.op(x, **kw)
+
+
+class NetCfg:
+    def __init__(self, device, precision, engine=nv.ENGINE_TCGEN05):
+        self.device, self.precision, self.engine = device, precision, engine
+
+
+class Bottleneck:
+    """1x1 -> ReLU -> 3x3 -> ReLU -> 1x1 (+ skip): BaseBlock (elic_layers.py:23-36), NLAMResBlock
+    (cheng_nlam.py:32-47) and BetaCondBaseBlock (elic_interpca_beta_cond_autoencoder.py:42-66)."""
+
+    def __init__(self, sd, names, cfg):
+        self.c1 = Conv(sd, names[0], cfg)
+        self.c2 = Conv(sd, names[1], cfg, padding=1)
+        self.c3 = Conv(sd, names[2], cfg)
+
+    def __call__(self, x, add=(None, None, None), scale=None, shift=None):
+        t = self.c1(x, relu=True, add_vec=add[0])
+        t = self.c2(t, relu=True, add_vec=add[1])
+        return self.c3(t, add_vec=add[2], mode=nv.EPI_RESIDUAL, res=x, scale=scale, shift=shift)
+
+
+class Nlam:
+    """ChengNLAM (cheng_nlam.py:5-29): x + trunk(x) * sigmoid(conv1x1(attn(x)))."""
+
+    def __init__(self, sd, cfg):
+        rb = lambda p: Bottleneck(sd, [p + ".c1", p + ".c2", p + ".c3"], cfg)
+        self.trunk = [rb(f"trunk_block.{i}") for i in range(3)]
+        self.attn = [rb(f"attention_block.{i}") for i in range(3)]
+        self.conv = Conv(sd, "conv", cfg)
+
+    def __call__(self, x, scale=None, shift=None, out_f32=None):
+        t = x
+        for b in self.trunk:
+            t = b(t)
+        a = x
+        for b in self.attn:
+            a = b(a)
+        return self.conv(a, mode=nv.EPI_GATE, res=x, trunk=t, scale=scale, shift=shift, out_f32=out_f32)
+
+
+class InterpGain:
+    """InterpChAtt (interp_channel_attention.py:39-73) reduced to its two per-channel vectors for a
+    given quality index: scale = softplus(lerp(weight)), shift = lerp(bias)."""
+
+    def __init__(self, weight, bias, device):
+        self.w = weight.detach().to(device=device, dtype=torch.float32)  # (L, 1, C, 1, 1)
+        self.b = bias.detach().to(device=device, dtype=torch.float32)
+        self.levels = self.w.shape[0]
+        self._cache = {}
+
+    def vectors(self, q):
+        q = float(q)
+        if q not in self._cache:
+            if not (0.0 <= q <= self.levels - 1):
+                raise AssertionError(f"rate_ind = {q} should be in [0, {self.levels - 1}]")
+            ind = torch.tensor(q, dtype=torch.float32)
+            lo = torch.floor(ind)
+            hi = torch.minimum(lo + 1.0, torch.tensor(float(self.levels - 1)))
+            alpha = (hi - ind).to(self.w.device)
+            l, r = int(lo.item()), int(hi.item())
+            w = self.w[l] * alpha + self.w[r] * (1 - alpha)
+            b = self.b[l] * alpha + self.b[r] * (1 - alpha)
+            self._cache[q] = (F.softplus(w).reshape(-1).contiguous(), b.reshape(-1).contiguous())
+        return self._cache[q]
+
+
+def _gains(sd, count, device):
+    return [InterpGain(sd[f"interp_ca_list.{i}.weight"], sd[f"interp_ca_list.{i}.bias"], device) for i in range(count)]
+
+
+class AnalysisEngine:
+    """g_a: ElicInterpCaEncoder.forward (elic_interpca_autoencoder.py:22-56; layers elic_autoencoder.py:42-56).
+    Every InterpChAtt that follows a layer is folded into that layer's last epilogue."""
+
+    def __init__(self, sd, device, precision=X3, engine=nv.ENGINE_TCGEN05):
+        cfg = NetCfg(device, precision, engine)
+        self.cfg = cfg
+        self.conv1 = Conv(sd, "conv1", cfg, stride=2, padding=2, cin_pad=8)
+        self.conv2 = Conv(sd, "conv2", cfg, stride=2, padding=2)
+        self.conv3 = Conv(sd, "conv3", cfg, stride=2, padding=2)
+        self.conv4 = Conv(sd, "conv4", cfg, stride=2, padding=2)
+        blk = lambda p: [Bottleneck(_sub(sd, f"{p}.block{i}"), ["conv.0", "conv.2", "conv.4"], cfg) for i in range(3)]
+        self.block1, self.block2, self.block3 = blk("block1"), blk("block2"), blk("block3")
+        self.attn2 = Nlam(_sub(sd, "attn2"), cfg)
+        self.attn4 = Nlam(_sub(sd, "attn4"), cfg)
+        self.gains = _gains(sd, 9, device)
+        self.out_ch = sd["conv4.weight"].shape[0]
+
+    @staticmethod
+    def _blocks(blocks, x, g):
+        for i, b in enumerate(blocks):
+            x = b(x, scale=g[0], shift=g[1]) if i == len(blocks) - 1 else b(x)
+        return x
+
+    def run(self, img, q):
+        """img: Act (n, H, W, 8) -> (y planes Act, y fp32 NHWC tensor)."""
+        g = [gn.vectors(q) for gn in self.gains]
+        x = self.conv1(img, scale=g[0][0], shift=g[0][1])
+        x = self._blocks(self.block1, x, g[1])
+        x = self.conv2(x, scale=g[2][0], shift=g[2][1])
+        x = self._blocks(self.block2, x, g[3])
+        x = self.attn2(x, scale=g[4][0], shift=g[4][1])
+        x = self.conv3(x, scale=g[5][0], shift=g[5][1])
+        x = self._blocks(self.block3, x, g[6])
+        x = self.conv4(x, scale=g[7][0], shift=g[7][1])
+        y32 = torch.empty((x.n, x.h, x.w, self.out_ch), dtype=torch.float32, device=x.hi.device)
+        y = self.attn4(x, scale=g[8][0], shift=g[8][1], out_f32=y32)
+        return y, y32
+
+
+class HyperAnalysisEngine:
+    """h_a: Minnen20HyperEncoder.forward (minnen20_hyperprior.py:9-27)."""
+
+    def __init__(self, sd, device, precision=X3, engine=nv.ENGINE_TCGEN05):
+        cfg = NetCfg(device, precision, engine)
+        self.conv1 = Conv(sd, "conv1", cfg, padding=1)
+        self.conv2 = Conv(sd, "conv2", cfg, stride=2, padding=2)
+        self.conv3 = Conv(sd, "conv3", cfg, stride=2, padding=2)
+        self.out_ch = sd["conv3.weight"].shape[0]
+
+    def run(self, y):
+        t = self.conv1(y, relu=True)
+        t = self.conv2(t, relu=True)
+        hz, wz = self.conv3.op.out_hw(t.h, t.w)
+        z32 = torch.empty((t.n, hz, wz, self.out_ch), dtype=torch.float32, device=t.hi.device)
+        self.conv3(t, out_f32=z32, want_planes=False)
+        return z32
+
+
+class HyperSynthesisEngine:
+    """h_s: Minnen20HyperDecoder.forward (minnen20_hyperprior.py:30-58); the two branches write their
+    320 channels straight into the ChARM support tensor (no torch.cat)."""
+
+    def __init__(self, sd, device, precision=X3, engine=nv.ENGINE_TCGEN05):
+        cfg = NetCfg(device, precision, engine)
+        mk = lambda p: [Conv(sd, f"{p}.conv1", cfg, transposed=True, stride=2, padding=2, output_padding=1),
+                        Conv(sd, f"{p}.conv2", cfg, transposed=True, stride=2, padding=2, output_padding=1),
+                        Conv(sd, f"{p}.conv3", cfg, transposed=True, stride=1, padding=1)]
+        self.mu, self.std = mk("hd_mu"), mk("hd_std")
+        self.out_ch = sd["hd_mu.conv3.weight"].shape[1]
+
+    def run(self, zhat, support, mean_coff, scale_coff, hyper32=None):
+        """zhat: Act.  support: Act the outputs are written into.  hyper32: optional fp32 NHWC [.., 2*C]
+        receiving cat[mu, std] (the reference's hyper_out) for API / test use."""
+        for branch, coff, f32off in ((self.mu, mean_coff, 0), (self.std, scale_coff, self.out_ch)):
+            t = branch[0](zhat, relu=True)
+            t = branch[1](t, relu=True)
+            branch[2](t, out=support, out_coff=coff, out_f32=hyper32, out_f32_coff=f32off)
+
+
+class SliceNet:
+    """SliceTransform (minnen20_charm_context_model.py:26-38): conv5x5 -> ReLU -> conv5x5 -> ReLU -> conv3x3."""
+
+    def __init__(self, sd, cfg):
+        self.c1 = Conv(sd, "model.0", cfg, padding=2)
+        self.c2 = Conv(sd, "model.2", cfg, padding=2)
+        self.c3 = Conv(sd, "model.4", cfg, padding=1)
+
+    def __call__(self, x, segs, **last):
+        t = self.c1(x, segs=segs, relu=True)
+        t = self.c2(t, relu=True)
+        return self.c3(t, **last)
+
+
+class GaussianParams:
+    """Constants of the GaussianConditional the kernels need (scale table on device, bound)."""
+
+    def __init__(self, scale_table, scale_bound, device):
+        self.table = scale_table.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.bound = float(scale_bound)
+
+
+class CharmEngine:
+    """Minnen20CharmContextModel.forward / forward_compress / forward_decompress
+    (minnen20_charm_context_model.py:88-240).
+
+    Support tensor layout (one NHWC Act, `cs` channels):  [hyper_scale | hyper_mean | y_hat slices | scratch slice]
+    so that the mean / LRP nets read ``hyper_mean ++ y_hat[:k]`` as ONE contiguous channel range and the
+    scale net reads two ranges; nothing is concatenated or copied.
+    """
+
+    def __init__(self, sd, num_slices, slice_ch, hyper_ch, max_support, device, precision=X3,
+                 engine=nv.ENGINE_TCGEN05):
+        cfg = NetCfg(device, precision, engine)
+        self.cfg = cfg
+        self.S, self.sc, self.hc = num_slices, slice_ch, hyper_ch
+        self.max_support = max_support
+        self.mean = [SliceNet(_sub(sd, f"mean_slice_transforms.{i}"), cfg) for i in range(num_slices)]
+        self.scale = [SliceNet(_sub(sd, f"scale_slice_transforms.{i}"), cfg) for i in range(num_slices)]
+        self.lrp = [SliceNet(_sub(sd, f"lrp_slice_transforms.{i}"), cfg) for i in range(num_slices)]
+        self.off_scale, self.off_mean = 0, hyper_ch
+        self.off_y = 2 * hyper_ch
+        self.off_tmp = self.off_y + num_slices * slice_ch
+        self.cs = self.off_tmp + slice_ch * num_slices  # one scratch slot per slice (slices of a group run together)
+        self.yc = num_slices * slice_ch
+
+    def n_support(self, s):
+        return s if self.max_support < 0 else min(s, self.max_support)
+
+    def new_support(self, n, h, w, device):
+        return Act.empty(n, h, w, self.cs, two=True, device=device)
+
+    def groups(self):
+        """Slices whose (mu, sigma) depend only on already-finished slices can be processed together."""
+        if self.max_support < 0:
+            return [[s] for s in range(self.S)]
+        head = [[s] for s in range(min(self.max_support, self.S))]
+        tail = list(range(self.max_support, self.S))
+        return head + ([tail] if tail else [])
+
+    def _segs_mean(self, s):
+        return [(self.off_mean, self.hc + self.sc * self.n_support(s))]
+
+    def _segs_scale(self, s):
+        k = self.n_support(s)
+        return [(self.off_scale, self.hc)] + ([(self.off_y, self.sc * k)] if k else [])
+
+    def _segs_lrp(self, s):
+        return [(self.off_mean, self.hc + self.sc * self.n_support(s)), (self.off_tmp + s * self.sc, self.sc)]
+
+    def params(self, T, s, ms):
+        """mu_s, sigma_s -> ms[..., 2*s*sc : 2*(s+1)*sc] (fp32 NHWC scratch holding [mu | sigma] per slice)."""
+        self.mean[s](T, self._segs_mean(s), out_f32=ms, out_f32_coff=2 * s * self.sc, want_planes=False)
+        self.scale[s](T, self._segs_scale(s), out_f32=ms, out_f32_coff=(2 * s + 1) * self.sc, want_planes=False)
+
+    def refine(self, T, s, yq32, yhat32):
+        """LRP: y_hat_s = yq_s + 0.5 tanh(lrp(...)) -> support tensor (planes) and yhat32 (fp32 NHWC)."""
+        self.lrp[s](T, self._segs_lrp(s), mode=nv.EPI_HALF_TANH, res=yq32, res_coff=s * self.sc, out=T,
+                    out_coff=self.off_y + s * self.sc, out_f32=yhat32, out_f32_coff=s * self.sc)
+
+    def gauss_desc(self, gp, T, s, cnt, n, hw, ms, y32=None, yq32=None, sym=None, idx=None, lik=None):
+        """Descriptor covering `cnt` consecutive slices starting at s (they share the [mu|sigma] interleave
+        only when cnt == 1, so multi-slice calls are issued per slice by the caller)."""
+        d = nv.GaussDesc()
+        if y32 is not None:
+            d.y, d.y_cs, d.y_coff = y32.data_ptr(), self.yc, s * self.sc
+        d.mu, d.sigma = ms.data_ptr(), ms.data_ptr()
+        d.ms_cs, d.mu_coff, d.sigma_coff = ms.shape[-1], 2 * s * self.sc, (2 * s + 1) * self.sc
+        d.n, d.hw, d.c = n, hw, self.sc * cnt
+        d.scale_bound, d.scale_table, d.ntable = gp.bound, gp.table.data_ptr(), gp.table.numel()
+        d.yq_planes = T.planes(self.off_tmp + s * self.sc)
+        if yq32 is not None:
+            d.yq_f32, d.yq_f32_cs, d.yq_f32_coff = yq32.data_ptr(), self.yc, s * self.sc
+        d.symbols = sym.data_ptr() if sym is not None else None
+        d.indexes = idx.data_ptr() if idx is not None else None
+        d.likelihood = lik.data_ptr() if lik is not None else None
+        d.c_total, d.nchw_coff = self.yc, s * self.sc
+        return d
+
+    def encode(self, T, y32, gp):
+        """Encoder-side pass.  Returns y_hat fp32 NHWC, symbols / indexes int32 NCHW, likelihood fp32 NCHW."""
+        n, h, w = T.n, T.h, T.w
+        dev = T.hi.device
+        ms = torch.empty((n, h, w, 2 * self.yc), dtype=torch.float32, device=dev)
+        yq32 = torch.empty((n, h, w, self.yc), dtype=torch.float32, device=dev)
+        yhat32 = torch.empty((n, h, w, self.yc), dtype=torch.float32, device=dev)
+        sym = torch.empty((n, self.yc, h, w), dtype=torch.int32, device=dev)
+        idx = torch.empty((n, self.yc, h, w), dtype=torch.int32, device=dev)
+        lik = torch.empty((n, self.yc, h, w), dtype=torch.float32, device=dev)
+        st, L = nv.stream_handle(), nv.lib()
+        for grp in self.groups():
+            for s in grp:
+                self.params(T, s, ms)
+            for s in grp:
+                d = self.gauss_desc(gp, T, s, 1, n, h * w, ms, y32=y32, yq32=yq32, sym=sym, idx=idx, lik=lik)
+                nv.check(L.crdr_gauss_quantize(C.byref(d), st))
+            for s in grp:
+                self.refine(T, s, yq32, yhat32)
+        return yhat32, sym, idx, lik
+
+    def decode(self, T, gp, symbol_source):
+        """Decoder-side pass.  ``symbol_source(first_slice, count, idx_nchw)`` returns the int32 NCHW symbols
+        (device tensor, full [n, yc, h, w] buffer with that slice range filled) for the group.
+        Returns y_hat fp32 NHWC."""
+        n, h, w = T.n, T.h, T.w
+        dev = T.hi.device
+        ms = torch.empty((n, h, w, 2 * self.yc), dtype=torch.float32, device=dev)
+        yq32 = torch.empty((n, h, w, self.yc), dtype=torch.float32, device=dev)
+        yhat32 = torch.empty((n, h, w, self.yc), dtype=torch.float32, device=dev)
+        idx = torch.empty((n, self.yc, h, w), dtype=torch.int32, device=dev)
+        st, L = nv.stream_handle(), nv.lib()
+        for grp in self.groups():
+            for s in grp:
+                self.params(T, s, ms)
+                d = self.gauss_desc(gp, T, s, 1, n, h * w, ms, idx=idx)
+                nv.check(L.crdr_gauss_indexes(C.byref(d), st))
+            sym = symbol_source(grp[0], len(grp), idx)
+            for s in grp:
+                d = self.gauss_desc(gp, T, s, 1, n, h * w, ms, yq32=yq32, sym=sym)
+                nv.check(L.crdr_gauss_dequantize(C.byref(d), st))
+            for s in grp:
+                self.refine(T, s, yq32, yhat32)
+        return yhat32
+
+
+class SynthesisEngine:
+    """g_s: ElicInterpCaBetaCondDecoder.forward (elic_interpca_beta_cond_autoencoder.py:88-162).
+    InterpChAtt precedes each layer here, so gain i is folded into the epilogue of layer i-1; gain 0 is
+    applied while converting y_hat to planes.  The beta embedding (fourier_cond.py:21-37), its MLP and
+    the 27 projections are evaluated once per beta and enter as per-channel epilogue vectors."""
+
+    def __init__(self, sd, max_beta, L, use_pi, include_x, use_tanh, device, precision=X1,
+                 engine=nv.ENGINE_TCGEN05):
+        if use_tanh:
+            raise NotImplementedError("use_tanh=True decoders are not lowered (crdr.yaml uses use_tanh: False)")
+        cfg = NetCfg(device, precision, engine)
+        self.cfg, self.device = cfg, device
+        self.two = precision == X3
+        up = lambda name: Conv(sd, name, cfg, transposed=True, stride=2, padding=2, output_padding=1)
+        self.attn1 = Nlam(_sub(sd, "attn1"), cfg)
+        self.conv1, self.conv2, self.conv3, self.conv4 = up("conv1"), up("conv2"), up("conv3"), up("conv4")
+        self.attn2 = Nlam(_sub(sd, "attn2"), cfg)
+        self.blocks, self.proj = {}, {}
+        for b in ("block1", "block2", "block3"):
+            self.blocks[b] = [Bottleneck(_sub(sd, f"{b}.block{i}"), ["conv.0", "conv.2", "conv.4"], cfg) for i in range(3)]
+            self.proj[b] = [[(sd[f"{b}.block{i}.proj_{k}.weight"].detach().to(device=device, dtype=torch.float32).flatten(1),
+                              sd[f"{b}.block{i}.proj_{k}.bias"].detach().to(device=device, dtype=torch.float32))
+                             for k in (1, 2, 3)] for i in range(3)]
+        self.mlp = [(sd[f"mlp.{i}.weight"].detach().to(device=device, dtype=torch.float32),
+                     sd[f"mlp.{i}.bias"].detach().to(device=device, dtype=torch.float32)) for i in (0, 2)]
+        self.gains = _gains(sd, 9, device)
+        self.max_beta, self.L, self.include_x = float(max_beta), int(L), bool(include_x)
+        self.freq = torch.pow(torch.Tensor([2]), torch.arange(L))
+        if use_pi:
+            self.freq = self.freq * math.pi
+        self._beta_cache = {}
+        self.in_ch = sd["conv1.weight"].shape[0]
+
+    def cond_vectors(self, beta):
+        beta = float(beta)
+        if beta not in self._beta_cache:
+            if not (0 <= beta <= self.max_beta):
+                raise AssertionError(f"beta = {beta} should be in [0, {self.max_beta}]")
+            b = torch.Tensor([beta]).float()
+            nb = (b / self.max_beta - 0.5) * 2
+            emb = torch.cat([torch.sin(nb * self.freq), torch.cos(nb * self.freq)], dim=0)
+            if self.include_x:
+                emb = torch.cat([nb, emb], dim=0)
+            c = emb.unsqueeze(0).to(self.device)
+            c = F.linear(torch.relu(F.linear(c, *self.mlp[0])), *self.mlp[1])  # [1, cond_ch]
+            vec = {b_: [[(F.linear(c, w, bb)).reshape(-1).contiguous() for (w, bb) in blk] for blk in pr]
+                   for b_, pr in self.proj.items()}
+            self._beta_cache[beta] = vec
+        return self._beta_cache[beta]
+
+    def _blocks(self, name, x, cond, g):
+        blks = self.blocks[name]
+        for i, b in enumerate(blks):
+            last = i == len(blks) - 1
+            x = b(x, add=cond[name][i], scale=g[0] if last else None, shift=g[1] if last else None)
+        return x
+
+    def run(self, yhat32, q, beta):
+        """yhat32: fp32 NHWC [n, h, w, C] -> fp32 NHWC image [n, 16h, 16w, 4] (3 real channels)."""
+        g = [gn.vectors(q) for gn in self.gains]
+        cond = self.cond_vectors(beta)
+        n, h, w, c = yhat32.shape
+        x = Act.empty(n, h, w, c, two=self.two, device=yhat32.device)
+        nv.check(nv.lib().crdr_affine_to_planes(yhat32.data_ptr(), c, 0, n * h * w, c, g[0][0].data_ptr(),
+                                                g[0][1].data_ptr(), x.planes(0), nv.stream_handle()))
+        x = self.attn1(x, scale=g[1][0], shift=g[1][1])
+        x = self.conv1(x, scale=g[2][0], shift=g[2][1])
+        x = self._blocks("block1", x, cond, g[3])
+        x = self.conv2(x, scale=g[4][0], shift=g[4][1])
+        x = self.attn2(x, scale=g[5][0], shift=g[5][1])
+        x = self._blocks("block2", x, cond, g[6])
+        x = self.conv3(x, scale=g[7][0], shift=g[7][1])
+        x = self._blocks("block3", x, cond, g[8])
+        ho, wo = self.conv4.op.out_hw(x.h, x.w)
+        img = torch.empty((n, ho, wo, 4), dtype=torch.float32, device=yhat32.device)
+        self.conv4(x, out_f32=img, want_planes=False)
+        return img

@@ -12,7 +12,12 @@
 //   F16X3 precision keeps fp32-class accuracy on fp16 tensor cores: operands are stored as
 //   (hi, lo*2^11) fp16 pairs, D0 += Ahi*Bhi and D1 += Ahi*Blo + Alo*Bhi run as three MMAs per
 //   K step, and the epilogue forms D0 + 2^-11 * D1.
-// * Warps 0-3 gather, then become the epilogue: tcgen05.ld 32x32b.x16 -> fused bias / ReLU /
+// * Tensor-core accumulation truncates, and the bias grows with the length of the accumulate chain
+//   (measured: 7e-6 of max|out| at K=8800 vs 2e-6 for fp32 FMA, enough to flip CDF indexes).  F16X3
+//   therefore accumulates D0 in short chunks (kChunkKB K-blocks) that ping-pong between two TMEM
+//   buffers; warps 4-7 drain each finished chunk with tcgen05.ld, add it to a running fp32 total
+//   (round-to-nearest) kept in a fourth TMEM region via tcgen05.st, and hand the buffer back.
+// * The same warps then run the epilogue: tcgen05.ld 32x32b.x16 -> fused bias / ReLU /
 //   beta-bias / residual / sigmoid-gate / half-tanh / gain -> fp16 planes (+ optional fp32) NHWC.
 //
 // Deterministic: fixed K order, no atomics on data, no split-K; a given output pixel sees the same
@@ -28,7 +33,9 @@ constexpr int kTileM = 128;
 constexpr int kKBlk = 64;                  // fp16 elements per K block = one 128-byte swizzle row
 constexpr uint32_t kAPlaneBytes = kTileM * 128;
 constexpr int kMaxStages = 6;
-constexpr int kThreads = 192;              // warps 0-3 gather/epilogue, warp 4 TMA + TMEM alloc, warp 5 MMA
+constexpr int kThreads = 320;              // warps 0-3 gather, 4-7 drain/epilogue, warp 8 TMA + TMEM alloc, warp 9 MMA
+constexpr int kChunkKB = 2;                // F16X3: K blocks per D0 accumulate chain (8 MMAs of K=16)
+constexpr uint32_t kColD0 = 0, kColD1 = 256, kColTotal = 384;  // F16X3 TMEM columns (D0 ping-pong at 0 / 128)
 constexpr uint32_t kSmemLimit = 227 * 1024;
 
 struct alignas(64) ConvKParams {
@@ -122,18 +129,24 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+// 16 consecutive fp32 columns of this thread's TMEM lane; the values are valid after tmem_wait_ld().
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"): rows are 128 bytes,
 // groups of 8 rows are 1024 bytes apart (SBO); LBO is unused for swizzled K-major operands.
@@ -287,7 +300,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t d0_full_bar[2];   // MMA -> drain warps: a D0 chunk is complete
+  __shared__ __align__(8) uint64_t d0_empty_bar[2];  // drain warps -> MMA: the D0 buffer may be overwritten
   __shared__ uint32_t tmem_slot;
   __shared__ int s_dh[CRDR_MAX_TAPS + 1], s_dw[CRDR_MAX_TAPS + 1];
 
@@ -296,6 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
   const int lane = threadIdx.x & 31;
   const int S = P.stages;
   const int nplanes = P.nplanes;
+  const bool three = nplanes == 2;
   const int BN = d.tile_n;
   const uint32_t b_bytes = (uint32_t)BN * 128u;
   const uint32_t stage_bytes = (uint32_t)nplanes * (kAPlaneBytes + b_bytes);
@@ -303,6 +318,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
   const int m0 = blockIdx.x * kTileM;
   const int n0 = blockIdx.y * BN;
   const int nkb = P.nkb;
+  // F16X3: D0 accumulates in chunks of kChunkKB K blocks; F16X1: one chunk spanning all of K
+  const int chunk_kb = three ? kChunkKB : nkb;
+  const int nchunks = (nkb + chunk_kb - 1) / chunk_kb;
 
   if (threadIdx.x < d.ntaps) {
     s_dh[threadIdx.x] = d.dh[threadIdx.x];
@@ -316,13 +334,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
       mbar_init(smem_u32(&full_bar[s]), full_count);
       mbar_init(smem_u32(&empty_bar[s]), 1u);
     }
-    mbar_init(smem_u32(&accum_bar), 1u);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&d0_full_bar[b]), 1u);
+      mbar_init(smem_u32(&d0_empty_bar[b]), 128u);
+    }
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0 && P.use_tma) {
       prefetch_tmap(&P.tm_hi);
-      if (nplanes == 2) prefetch_tmap(&P.tm_lo);
+      if (three) prefetch_tmap(&P.tm_lo);
     }
     __syncwarp();
     tmem_alloc(smem_u32(&tmem_slot), (uint32_t)P.tmem_cols);
@@ -395,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
           const int64_t off = ok ? ((int64_t)(pix0[i] + tapoff) * d.in.cs + d.in.coff + chan) : 0;
           const uint32_t dst = stage + row_off + (uint32_t)i * 2048u;
           cp_async16(dst, in_hi + off, ok ? 16u : 0u);
-          if (nplanes == 2) cp_async16(dst + kAPlaneBytes, in_lo + off, ok ? 16u : 0u);
+          if (three) cp_async16(dst + kAPlaneBytes, in_lo + off, ok ? 16u : 0u);
         }
         if (!P.use_tma) {
           const uint32_t bst = stage + (uint32_t)nplanes * kAPlaneBytes;
@@ -403,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
             const int64_t off = (int64_t)(n0 + rbase + 16 * i) * d.k_pad + (int64_t)it * kKBlk + j * 8;
             const uint32_t dst = bst + row_off + (uint32_t)i * 2048u;
             cp_async16(dst, w_hi + off, 16u);
-            if (nplanes == 2) cp_async16(dst + b_bytes, w_lo + off, 16u);
+            if (three) cp_async16(dst + b_bytes, w_lo + off, 16u);
           }
         }
         c += kKBlk;
@@ -411,26 +432,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
       }
       cp_async_commit();
     }
-
-    // ------------------------------------------------------------------ epilogue
-    mbar_wait(smem_u32(&accum_bar), 0u, P.status);
-    tc_fence_after();
-    const int row = warp * 32 + lane;
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ drain D0 chunks, then the epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t r0[16], r1[16];
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int b = ch & 1;
+      mbar_wait(smem_u32(&d0_full_bar[b]), (uint32_t)(ch >> 1) & 1u, P.status);
+      tc_fence_after();
+      if (!three) break;  // F16X1: the single chunk is consumed directly by the epilogue below
+      const uint32_t src = lane_addr + kColD0 + (uint32_t)b * 128u;
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        tmem_ld16_issue(src + (uint32_t)c0, r0);
+        if (ch > 0) tmem_ld16_issue(lane_addr + kColTotal + (uint32_t)c0, r1);
+        tmem_wait_ld();
+        if (ch > 0) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) r0[e] = __float_as_uint(__uint_as_float(r0[e]) + __uint_as_float(r1[e]));
+        }
+        tmem_st16(lane_addr + kColTotal + (uint32_t)c0, r0);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&d0_empty_bar[b]));
+    }
     const int64_t opix = out_pixel_of_row(d, m0 + row, P.m_total);
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     for (int c0 = 0; c0 < BN; c0 += 16) {
       float acc[16];
-      tmem_ld16(lane_addr + (uint32_t)c0, acc);
-      if (nplanes == 2) {
-        float cross[16];
-        tmem_ld16(lane_addr + 256u + (uint32_t)c0, cross);
+      tmem_ld16_issue(lane_addr + (three ? kColTotal : kColD0) + (uint32_t)c0, r0);
+      if (three) tmem_ld16_issue(lane_addr + kColD1 + (uint32_t)c0, r1);
+      tmem_wait_ld();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) acc[e] = fmaf(cross[e], kLoInv, acc[e]);
-      }
+      for (int e = 0; e < 16; ++e)
+        acc[e] = three ? fmaf(__uint_as_float(r1[e]), kLoInv, __uint_as_float(r0[e])) : __uint_as_float(r0[e]);
       if (opix >= 0) epilogue16(P, opix, n0 + c0, acc);
     }
     tc_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ------------------------------------------------------------------ weight tiles by TMA
     if (lane == 0 && P.use_tma) {
       for (int it = 0; it < nkb; ++it) {
@@ -441,19 +481,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
         const uint32_t bst = smem_base + (uint32_t)s * stage_bytes + (uint32_t)nplanes * kAPlaneBytes;
         mbar_arrive_expect_tx(bar, (uint32_t)nplanes * b_bytes);
         tma_load_2d(bst, &P.tm_hi, it * kKBlk, n0, bar);
-        if (nplanes == 2) tma_load_2d(bst + b_bytes, &P.tm_lo, it * kKBlk, n0, bar);
+        if (three) tma_load_2d(bst + b_bytes, &P.tm_lo, it * kKBlk, n0, bar);
       }
     }
   } else {
     // ------------------------------------------------------------------ MMA issue (one thread)
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16((uint32_t)BN);
-      const uint32_t d0 = tmem_base;
-      const uint32_t d1 = tmem_base + 256u;
+      const uint32_t d1 = tmem_base + kColD1;
       for (int it = 0; it < nkb; ++it) {
         const int s = it % S;
+        const int ch = it / chunk_kb;
+        const int b = ch & 1;
+        const bool chunk_first = (it % chunk_kb) == 0;
+        const bool chunk_last = ((it + 1) % chunk_kb) == 0 || it == nkb - 1;
+        if (chunk_first && ch >= 2) {
+          // the drain warps must have emptied this D0 buffer (chunk ch-2) before it is overwritten
+          mbar_wait(smem_u32(&d0_empty_bar[b]), (uint32_t)((ch - 2) >> 1) & 1u, P.status);
+          tc_fence_after();
+        }
         mbar_wait(smem_u32(&full_bar[s]), (uint32_t)(it / S) & 1u, P.status);
         tc_fence_after();
+        const uint32_t d0 = tmem_base + kColD0 + (three ? (uint32_t)b * 128u : 0u);
         const uint32_t stage = smem_base + (uint32_t)s * stage_bytes;
         const uint64_t a_hi = umma_desc_sw128(stage);
         const uint64_t a_lo = umma_desc_sw128(stage + kAPlaneBytes);
@@ -462,20 +511,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
 #pragma unroll
         for (int k = 0; k < kKBlk / 16; ++k) {
           const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 descriptor units
-          const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
-          umma_f16(d0, a_hi + adv, b_hi + adv, idesc, first);
-          if (nplanes == 2) {
-            umma_f16(d1, a_hi + adv, b_lo + adv, idesc, first);
+          umma_f16(d0, a_hi + adv, b_hi + adv, idesc, (chunk_first && k == 0) ? 0u : 1u);
+          if (three) {
+            umma_f16(d1, a_hi + adv, b_lo + adv, idesc, (it > 0 || k > 0) ? 1u : 0u);
             umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);
           }
         }
         umma_commit(smem_u32(&empty_bar[s]));
+        if (chunk_last) umma_commit(smem_u32(&d0_full_bar[b]));
       }
-      umma_commit(smem_u32(&accum_bar));
     }
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
   }
@@ -705,6 +753,10 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
   if (stages > P.nkb + 1) stages = P.nkb + 1;
   if (stages < 2) { set_error("conv2d: tile_n=%d leaves fewer than 2 pipeline stages", d.tile_n); return CRDR_ERR_BAD_SHAPE; }
   P.stages = stages;
+  if (three && d.tile_n > 128) {
+    set_error("conv2d: F16X3 needs tile_n <= 128 (two D0 buffers, D1 and the fp32 total share 512 TMEM columns)");
+    return CRDR_ERR_BAD_SHAPE;
+  }
   int cols = three ? 512 : 32;
   while (cols < d.tile_n) cols *= 2;
   P.tmem_cols = cols;

@@ -79,9 +79,10 @@ class Phase:
 
 
 def pick_tile_n(cout_pad, m_tiles, three):
-    """Largest N tile (multiple of 16, divides cout_pad, <= 256) that still yields >= 148 CTAs; tiles below
+    """Largest N tile (multiple of 16, divides cout_pad, <= 256 / 128) that still yields >= 148 CTAs; tiles below
     64 columns (shared-memory-bound MMAs) are used only when the layer itself is that narrow."""
-    cands = [t for t in range(16, min(cout_pad, 256) + 1, 16) if cout_pad % t == 0]
+    cap = 128 if three else 256  # F16X3 keeps two D0 buffers, D1 and the fp32 total in 512 TMEM columns
+    cands = [t for t in range(16, min(cout_pad, cap) + 1, 16) if cout_pad % t == 0]
     good = [t for t in cands if t >= min(64, cands[-1])]
     best = good[0]
     for t in good:

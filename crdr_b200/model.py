@@ -1,0 +1,426 @@
+"""Model API of the reference (`src/models/comp_model/*`), driven by the lowered CUDA engines.
+
+`BetaCondInterpCaHyperpriorCharmModel` keeps the reference's public surface -- ``compress`` /
+``decompress`` / ``forward`` / ``run_model`` / ``codec_setup`` / ``load_learned_weight`` /
+``load_state_dict`` / ``separate_aux_parameters`` / ``aux_loss`` / ``validation``
+(beta_cond_interpca_hyperprior_charm_model.py:13-149, beta_cond_interpca_hyperprior_model.py:28-64,
+hyperprior_model.py:60-136, base_model.py:35-167) -- and the 595-key checkpoint layout.  Additions:
+``compress_batch`` / ``decompress_batch`` (the reference asserts N == 1) and the device-only
+``encode_device`` / ``decode_device`` used for device-timed throughput.
+
+There is no PyTorch/CPU fallback: the arithmetic runs in libcrdr_sm100.so or not at all.
+"""
+import ctypes as C
+from collections import OrderedDict
+from copy import deepcopy
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import native as nv
+from . import rans
+from .codec import GaussianParams
+from .codec_utils import MultiRateHeaderHandler
+from .engine import Act
+from .entropy import EntropyBottleneck, GaussianMeanScaleConditional, get_scale_table
+from .logger import get_root_logger
+from .registry import (CONTEXTMODEL_REGISTRY, DECODER_REGISTRY, ENCODER_REGISTRY, ENTROPYMODEL_REGISTRY,
+                       HYPERDECODER_REGISTRY, HYPERENCODER_REGISTRY, MODEL_REGISTRY)
+from . import subnets  # noqa: F401  (registers the sub-network classes)
+
+_REGISTRY_OF = {
+    "encoder": ENCODER_REGISTRY, "decoder": DECODER_REGISTRY, "hyperencoder": HYPERENCODER_REGISTRY,
+    "hyperdecoder": HYPERDECODER_REGISTRY, "context_model": CONTEXTMODEL_REGISTRY,
+    "entropy_model": ENTROPYMODEL_REGISTRY,
+}
+
+
+def build_subnet(subnet_opt, subnet_type):
+    """`type:` selects the class, the remaining keys are its kwargs (subnet/__init__.py:16-43)."""
+    kw = dict(deepcopy(subnet_opt))
+    cls = _REGISTRY_OF[subnet_type].get(kw.pop("type"))
+    return cls(**{k: (dict(v) if isinstance(v, dict) else v) for k, v in kw.items()})
+
+
+def build_comp_model(opt):
+    """models/__init__.py:21-30."""
+    opt = deepcopy(opt)
+    return MODEL_REGISTRY.get(opt["model_type"])(opt)
+
+
+class CodecEngine:
+    """All lowered sub-networks of one model on one device + the launch sequences of the codec."""
+
+    def __init__(self, model, device, precision_main=nv.PREC_F16X3, precision_synthesis=nv.PREC_F16X1,
+                 conv_engine=nv.ENGINE_TCGEN05):
+        kw = dict(engine=conv_engine)
+        self.device = torch.device(device)
+        with torch.cuda.device(self.device):
+            self.ga = model.encoder.lower(device, precision=precision_main, **kw)
+            self.ha = model.hyperencoder.lower(device, precision=precision_main, **kw)
+            self.hs = model.hyperdecoder.lower(device, precision=precision_main, **kw)
+            self.charm = model.context_model.lower(device, precision=precision_main, **kw)
+            self.gs = model.decoder.lower(device, precision=precision_synthesis, **kw)
+            self.eb_params, self.eb_medians = model.entropy_model_z.kernel_params(device)
+            table = model.entropy_model_y.scale_table
+            if table.numel() == 0:
+                table = get_scale_table()
+            self.gp = GaussianParams(table, float(model.entropy_model_y.scale_bound.item()), device)
+        self.zc = model.entropy_model_z.channels
+        self.stride = 64
+
+    # ------------------------------------------------------------------ device-side stages
+    def padded(self, h, w):
+        s = self.stride
+        return -(-h // s) * s, -(-w // s) * s
+
+    def analysis(self, images, q):
+        """images: fp32 NCHW in [-1,1] on the device.  Returns a dict of device tensors (SURVEY 3.1 encode)."""
+        L, st = nv.lib(), nv.stream_handle()
+        n, _, h, w = images.shape
+        hp, wp = self.padded(h, w)
+        dev = images.device
+        img = Act.empty(n, hp, wp, 8, two=True, device=dev)
+        nv.check(L.crdr_image_to_planes(images.data_ptr(), n, h, w, hp, wp, img.planes(0), st))
+        y_act, y32 = self.ga.run(img, q)
+        z32 = self.ha.run(y_act)
+        hz, wz = z32.shape[1:3]
+        zhat = Act.empty(n, hz, wz, self.zc, two=True, device=dev)
+        z_sym = torch.empty((n, self.zc, hz, wz), dtype=torch.int32, device=dev)
+        z_hat = torch.empty((n, self.zc, hz, wz), dtype=torch.float32, device=dev)
+        z_lik = torch.empty((n, self.zc, hz, wz), dtype=torch.float32, device=dev)
+        d = nv.EbDesc()
+        d.z, d.z_cs, d.n, d.hw, d.c = z32.data_ptr(), self.zc, n, hz * wz, self.zc
+        d.params, d.medians = self.eb_params.data_ptr(), self.eb_medians.data_ptr()
+        d.zhat_planes = zhat.planes(0)
+        d.symbols, d.zhat_nchw, d.likelihood = z_sym.data_ptr(), z_hat.data_ptr(), z_lik.data_ptr()
+        nv.check(L.crdr_eb_quantize(C.byref(d), st))
+        T = self.charm.new_support(n, y_act.h, y_act.w, dev)
+        self.hs.run(zhat, T, self.charm.off_mean, self.charm.off_scale)
+        yhat32, y_sym, y_idx, y_lik = self.charm.encode(T, y32, self.gp)
+        return dict(y32=y32, z32=z32, z_sym=z_sym, z_hat=z_hat, z_lik=z_lik, yhat32=yhat32, y_sym=y_sym, y_idx=y_idx,
+                    y_lik=y_lik, size=(h, w))
+
+    def hyper_from_symbols(self, z_sym):
+        """z symbols (int32 NCHW, device) -> (support tensor with h_s output, z_hat NCHW)."""
+        L, st = nv.lib(), nv.stream_handle()
+        n, c, hz, wz = z_sym.shape
+        dev = z_sym.device
+        zhat = Act.empty(n, hz, wz, c, two=True, device=dev)
+        z_hat = torch.empty((n, c, hz, wz), dtype=torch.float32, device=dev)
+        d = nv.EbDesc()
+        d.n, d.hw, d.c = n, hz * wz, c
+        d.params, d.medians = self.eb_params.data_ptr(), self.eb_medians.data_ptr()
+        d.zhat_planes = zhat.planes(0)
+        d.symbols, d.zhat_nchw = z_sym.data_ptr(), z_hat.data_ptr()
+        nv.check(L.crdr_eb_dequantize(C.byref(d), st))
+        T = self.charm.new_support(n, hz * 4, wz * 4, dev)
+        self.hs.run(zhat, T, self.charm.off_mean, self.charm.off_scale)
+        return T, z_hat
+
+    def synthesis(self, yhat32, q, beta, size):
+        """y_hat fp32 NHWC -> cropped, clamped fp32 NCHW image."""
+        img = self.gs.run(yhat32, q, beta)
+        n, hp, wp, cs = img.shape
+        h, w = size
+        out = torch.empty((n, 3, h, w), dtype=torch.float32, device=img.device)
+        nv.check(nv.lib().crdr_planes_to_image(img.data_ptr(), cs, n, hp, wp, h, w, out.data_ptr(), nv.stream_handle()))
+        return out
+
+    def decode_device(self, z_sym, y_sym, q, beta, size):
+        """Decoder arithmetic with the symbols already on the device (the device-timed decode span)."""
+        T, z_hat = self.hyper_from_symbols(z_sym)
+        yhat32 = self.charm.decode(T, self.gp, lambda s0, cnt, idx: y_sym)
+        return self.synthesis(yhat32, q, beta, size), yhat32, z_hat
+
+    # ------------------------------------------------------------------ small reductions / layout
+    def bits(self, lik):
+        n = lik.shape[0]
+        out = torch.empty(n, dtype=torch.float32, device=lik.device)
+        nv.check(nv.lib().crdr_bits_from_likelihood(lik.data_ptr(), n, lik[0].numel(), out.data_ptr(), nv.stream_handle()))
+        return out
+
+    def max_abs(self, x):
+        n = x.shape[0]
+        out = torch.empty(n, dtype=torch.float32, device=x.device)
+        per = x[0].numel()
+        for i in range(n):
+            nv.check(nv.lib().crdr_max_abs(x.data_ptr() + 4 * per * i, per, out.data_ptr() + 4 * i, nv.stream_handle()))
+        return out
+
+    def to_nchw(self, x32):
+        n, h, w, c = x32.shape
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=x32.device)
+        nv.check(nv.lib().crdr_nhwc_to_nchw(x32.data_ptr(), c, 0, n, h * w, c, out.data_ptr(), nv.stream_handle()))
+        return out
+
+
+def _channel_indexes(c, h, w):
+    return np.ascontiguousarray(np.broadcast_to(np.arange(c, dtype=np.int32)[:, None, None], (c, h, w))).reshape(-1)
+
+
+class _CodecModelBase(nn.Module):
+    """Shared plumbing: BaseModel (base_model.py:16-170) + HyperpriorModel bit accounting."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.device = opt.device
+        self.convert_img_range = opt.get("convert_img_range_to_01", False)
+        if self.convert_img_range:
+            raise NotImplementedError("convert_img_range_to_01 is not used by the CRDR configs")
+        self._build_subnets()
+        self.stride = 64
+        self._engine = None
+        self._engine_opts = {}
+
+    # -- engine lifecycle -------------------------------------------------------------------
+    def engine(self):
+        if self._engine is None:
+            dev = torch.device(self.device)
+            if dev.type != "cuda":
+                raise nv.NativeError(
+                    f"device '{self.device}': the codec hot path exists only as sm_100a CUDA kernels; there is no CPU "
+                    "implementation in this package (use the oracle under oracle/ for CPU checks)")
+            nv.lib()  # fail loudly if the extension is missing
+            self._engine = CodecEngine(self, dev, **self._engine_opts)
+        return self._engine
+
+    def set_engine_options(self, **kw):
+        """precision_main / precision_synthesis / conv_engine (see crdr_b200.native)."""
+        self._engine_opts = kw
+        self._engine = None
+
+    def invalidate_engine(self):
+        self._engine = None
+
+    # -- checkpoints ---------------------------------------------------------------------------
+    def load_state_dict(self, state_dict, strict=True):
+        self.entropy_model_z._resize_buffers_from(state_dict, "entropy_model_z.", ["_quantized_cdf", "_offset", "_cdf_length"])
+        self.entropy_model_y._resize_buffers_from(state_dict, "entropy_model_y.",
+                                                  ["_quantized_cdf", "_offset", "_cdf_length", "scale_table"])
+        self.invalidate_engine()
+        return super().load_state_dict(state_dict, strict=strict)
+
+    def load_learned_weight(self, ckpt_path):
+        get_root_logger().info(f"load checkpoint: {ckpt_path}")
+        ckpt = torch.load(ckpt_path, map_location="cpu")
+        incoming = OrderedDict((k[7:] if "module." in k else k, v) for k, v in ckpt["comp_model"].items())
+        merged = self.state_dict()
+        merged.update({k: v for k, v in incoming.items() if k in merged})
+        self.load_state_dict(merged)
+        self.entropy_model_z.update(force=False)
+
+    def separate_aux_parameters(self):
+        named = {n: p for n, p in self.named_parameters() if p.requires_grad}
+        aux = {n: p for n, p in sorted(named.items()) if n.endswith(".quantiles")}
+        main = {n: p for n, p in sorted(named.items()) if not n.endswith(".quantiles")}
+        assert not (main.keys() & aux.keys()) and len(main) + len(aux) == len(named)
+        return main, aux
+
+    def aux_loss(self):
+        return sum(m.loss() for m in self.modules() if isinstance(m, EntropyBottleneck))
+
+    # -- reference helpers ---------------------------------------------------------------------
+    @staticmethod
+    def likelihood_to_bit(likelihood, num_pixel):
+        dims = tuple(range(1, likelihood.ndim))
+        bits = -(torch.log(likelihood).sum(dim=dims)) / np.log(2)
+        return bits, bits / num_pixel
+
+    def codec_setup(self):
+        self.header_handler = MultiRateHeaderHandler(use_non_zero_ind=False)
+        self.entropy_model_z.update(force=True)
+        self.entropy_model_y.update_scale_table(get_scale_table(), force=True)
+        self.yC, self.zC = self.encoder.latent_ch, self.hyperencoder.latent_ch
+        self.y_stride = 2 ** self.encoder.num_downscale
+        self.model_stride = self.y_stride * 2 ** self.hyperencoder.num_downscale
+        self.invalidate_engine()
+
+
+@MODEL_REGISTRY.register()
+class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
+    def _build_subnets(self):
+        sn = self.opt.subnet
+        self.rate_level = sn.encoder.rate_level
+        assert sn.encoder.rate_level == sn.decoder.rate_level
+        self.max_beta = float(sn.decoder.max_beta)
+        self.encoder = build_subnet(sn.encoder, "encoder")
+        self.decoder = build_subnet(sn.decoder, "decoder")
+        self.hyperencoder = build_subnet(sn.hyperencoder, "hyperencoder")
+        self.hyperdecoder = build_subnet(sn.hyperdecoder, "hyperdecoder")
+        self.entropy_model_z = build_subnet(sn.entropy_model_z, "entropy_model")
+        self.entropy_model_y = build_subnet(sn.entropy_model_y, "entropy_model")
+        self.context_model = build_subnet(sn.context_model, "context_model")
+        if not isinstance(self.entropy_model_y, GaussianMeanScaleConditional):
+            raise NotImplementedError("entropy_model_y must be a mean-scale Gaussian conditional")
+
+    # -- sampling helpers of the training API ------------------------------------------------
+    def sample_rate_ind(self, num_sample=1):
+        return torch.randint(self.rate_level, (num_sample,))
+
+    def sample_beta(self):
+        return self.max_beta * (float(np.random.randint(0, 101)) / 100.0)
+
+    @staticmethod
+    def _q(rate_ind):
+        if isinstance(rate_ind, torch.Tensor):
+            assert rate_ind.numel() == 1, "one quality index per batch (batch_rate_ind_sample is unsupported upstream)"
+            return float(rate_ind.reshape(-1)[0].item())
+        return float(rate_ind)
+
+    def _to_device(self, images):
+        return images.to(device=self.device, dtype=torch.float32).contiguous()
+
+    # -- forward / run_model ---------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, real_images, rate_ind, beta, is_train=True):
+        if is_train:
+            raise NotImplementedError(
+                "training-mode forward (uniform-noise likelihoods, STE rounding, autograd) is not lowered yet; "
+                "evaluation (is_train=False), compress and decompress run on the CUDA engines")
+        eng = self.engine()
+        q = self._q(rate_ind)
+        x = self._to_device(real_images)
+        n, _, h, w = x.shape
+        if h % self.stride or w % self.stride:
+            raise ValueError("forward(is_train=False) expects images padded to a multiple of 64 (use run_model)")
+        a = eng.analysis(x, q)
+        fake = eng.synthesis(a["yhat32"], q, beta, (h, w))
+        y, z = eng.to_nchw(a["y32"]), eng.to_nchw(a["z32"])
+        y_hat = eng.to_nchw(a["yhat32"])
+        return {
+            "fake_images": fake,
+            "likelihoods": {"y": a["y_lik"], "z": a["z_lik"]},
+            "latent_code": {"y": y, "z": z},
+            "quantized_code": {"y": y_hat, "z": a["z_hat"]},
+            "q_likelihoods": {"y": a["y_lik"], "z": a["z_lik"]},
+        }
+
+    @torch.no_grad()
+    def run_model(self, real_images, rate_ind=None, beta=None, is_train=True):
+        if is_train:
+            return self.forward(real_images, rate_ind, beta, is_train=True)
+        if rate_ind is None:
+            raise ValueError('"rate_ind" must be specified if is_train=False')
+        if beta is None:
+            raise ValueError('"beta" must be specified if is_train=False')
+        eng = self.engine()
+        q = self._q(rate_ind)
+        x = self._to_device(real_images)
+        n, _, h, w = x.shape
+        a = eng.analysis(x, q)
+        fake = eng.synthesis(a["yhat32"], q, beta, (h, w))
+        num_pixel = h * w
+        y_bpp, z_bpp = eng.bits(a["y_lik"]) / num_pixel, eng.bits(a["z_lik"]) / num_pixel
+        return dict(real_images=x.clamp(-1, 1), fake_images=fake, y_hat=eng.to_nchw(a["yhat32"]), z_hat=a["z_hat"],
+                    rate_ind=rate_ind, beta=beta, y_likelihood=a["y_lik"], z_likelihood=a["z_lik"],
+                    bpp=y_bpp + z_bpp, y_q_likelihood=a["y_lik"], z_q_likelihood=a["z_lik"], qbpp=y_bpp + z_bpp)
+
+    # -- codec -------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def compress_batch(self, real_images, rate_ind, return_tensors=False, coder_threads=0):
+        """N images of one shape -> list of N result dicts (same keys as ``compress``)."""
+        if not hasattr(self, "header_handler"):
+            raise RuntimeError("call codec_setup() before compress()")
+        eng = self.engine()
+        q = self._q(rate_ind)
+        x = self._to_device(real_images)
+        n, _, h, w = x.shape
+        a = eng.analysis(x, q)
+        y_bits, z_bits = eng.bits(a["y_lik"]), eng.bits(a["z_lik"])
+        y_max = eng.max_abs(a["yhat32"])
+        # ---- device -> host boundary (the reference moves y, z here; we move symbols and table indexes)
+        z_sym, y_sym, y_idx = a["z_sym"].cpu().numpy(), a["y_sym"].cpu().numpy(), a["y_idx"].cpu().numpy()
+        y_bits, z_bits, y_max = y_bits.cpu().numpy(), z_bits.cpu().numpy(), y_max.cpu().numpy()
+        nv.status_check()
+        zc, hz, wz = z_sym.shape[1:]
+        zi = _channel_indexes(zc, hz, wz)
+        z_strs = rans.encode_batch([z_sym[i] for i in range(n)], [zi] * n, self.entropy_model_z.coder_tables(), coder_threads)
+        y_strs = rans.encode_batch([y_sym[i] for i in range(n)], [y_idx[i] for i in range(n)],
+                                   self.entropy_model_y.coder_tables(), coder_threads)
+        if return_tensors:
+            y_hat = eng.to_nchw(a["yhat32"])
+        out = []
+        for i in range(n):
+            header = self.header_handler.encode((h, w), rate_ind=q, max_abs=float(y_max[i]))
+            r = {"string_list": [header, z_strs[i], y_strs[i]],
+                 "pred_y_bit": float(y_bits[i]), "pred_y_bpp": float(y_bits[i]) / (h * w),
+                 "pred_z_bit": float(z_bits[i]), "pred_z_bpp": float(z_bits[i]) / (h * w)}
+            if return_tensors:
+                r.update(z_hat=a["z_hat"][i:i + 1], y_hat=y_hat[i:i + 1], z_likelihood=a["z_lik"][i:i + 1],
+                         y_likelihood=a["y_lik"][i:i + 1])
+            out.append(r)
+        return out
+
+    @torch.no_grad()
+    def compress(self, real_images, rate_ind):
+        n = real_images.shape[0]
+        assert n == 1, f"In compress mode, batchsize must be 1, but {n}"
+        return self.compress_batch(real_images, rate_ind, return_tensors=True)[0]
+
+    @torch.no_grad()
+    def decompress_batch(self, string_lists, beta=0.0, coder_threads=0):
+        """Streams of N images with identical size and quality -> (images [N,3,H,W], z_hat, y_hat)."""
+        if not hasattr(self, "header_handler"):
+            raise RuntimeError("call codec_setup() before decompress()")
+        for sl in string_lists:
+            assert len(sl) == 3, f"String list length should be 3 (header, z, and y), but got {len(sl)}"
+        heads = [self.header_handler.decode(sl[0]) for sl in string_lists]
+        if any(hd["img_size"] != heads[0]["img_size"] or hd["rate_ind"] != heads[0]["rate_ind"] for hd in heads):
+            raise ValueError("decompress_batch needs streams of one image size and one quality index")
+        h, w = heads[0]["img_size"]
+        q = heads[0]["rate_ind"]
+        eng = self.engine()
+        n = len(string_lists)
+        hp, wp = eng.padded(h, w)
+        hz, wz = hp // self.model_stride, wp // self.model_stride
+        dev = eng.device
+        with torch.cuda.device(dev):
+            zi = _channel_indexes(self.zC, hz, wz)
+            zt, yt = self.entropy_model_z.coder_tables(), self.entropy_model_y.coder_tables()
+            z_dec = [rans.Decoder(sl[1]) for sl in string_lists]
+            z_np = np.stack(rans.decode_batch(z_dec, [zi] * n, zt, coder_threads)).reshape(n, self.zC, hz, wz)
+            z_sym = torch.from_numpy(z_np).to(dev)
+            T, z_hat = eng.hyper_from_symbols(z_sym)
+            y_dec = [rans.Decoder(sl[2]) for sl in string_lists]
+            hy, wy = T.h, T.w
+            y_sym = torch.empty((n, self.yC, hy, wy), dtype=torch.int32, device=dev)
+            sc = eng.charm.sc
+
+            def source(s0, cnt, idx):
+                c0, c1 = s0 * sc, (s0 + cnt) * sc
+                ix = idx[:, c0:c1].contiguous().cpu().numpy()  # device -> host: table indexes of this group
+                syms = rans.decode_batch(y_dec, [ix[i] for i in range(n)], yt, coder_threads)
+                blk = torch.from_numpy(np.stack(syms).reshape(n, c1 - c0, hy, wy))
+                y_sym[:, c0:c1] = blk.to(dev)  # host -> device: decoded symbols
+                return y_sym
+
+            yhat32 = eng.charm.decode(T, eng.gp, source)
+            img = eng.synthesis(yhat32, q, beta, (h, w))
+            y_hat = eng.to_nchw(yhat32)
+            nv.status_check()
+        return img, z_hat, y_hat
+
+    @torch.no_grad()
+    def decompress(self, string_list, beta=0.0):
+        return self.decompress_batch([string_list], beta=beta)
+
+    # -- validation (beta_cond_interpca_hyperprior_model.py:137-208) -----------------------------------
+    @torch.no_grad()
+    def validation(self, dataloader, max_sample_size, beta=None, save_img=False, save_dir="", use_tqdm=False):
+        import pandas as pd
+        from .img_utils import calc_psnr
+        beta = self.max_beta / 2.0 if beta is None else beta
+        rows = []
+        for idx, data in enumerate(dataloader):
+            row = {"idx": idx + 1}
+            for q in range(self.rate_level):
+                out = self.run_model(**data, rate_ind=float(q), beta=beta, is_train=False)
+                row[f"bpp_{q + 1}"] = out["bpp"].mean().item()
+                row[f"psnr_{q + 1}"] = calc_psnr(out["real_images"], out["fake_images"], 255)
+            rows.append(row)
+            if idx + 1 >= min(len(dataloader), max_sample_size):
+                break
+        return pd.json_normalize(rows)

@@ -1,0 +1,3 @@
+"""Drop-in alias of the reference's top-level ``src`` package: importing it registers the B200-native
+classes under the reference's registry names, so ``scripts/compress.py`` (reference or ours) runs unchanged."""
+import crdr_b200.model  # noqa: F401
