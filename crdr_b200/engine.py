@@ -11,6 +11,9 @@ import torch
 from . import native as nv
 
 LO_SCALE = 2048.0
+LAUNCH_COUNT = nv.LAUNCH_COUNT
+PROFILE_ON = [False]  # bench.py: bracket every conv launch with CUDA events on the launching stream
+PROFILE = []          # (flops, start_event, end_event)
 
 
 def round_up(x, m):
@@ -204,5 +207,12 @@ class ConvOp:
             d.w_hi, d.w_lo, d.k_pad = phs.w_hi.data_ptr(), phs.w_lo.data_ptr(), phs.k_pad
             m_tiles = -(-(x.n * hb * wb) // 128)
             d.tile_n = tile_n or pick_tile_n(self.cout_pad, m_tiles, precision == nv.PREC_F16X3)
-            nv.check(L.crdr_conv2d(C.byref(d), st))
+            if PROFILE_ON[0]:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                nv.check(L.crdr_conv2d(C.byref(d), st))
+                e1.record()
+                PROFILE.append((2.0 * x.n * hb * wb * self.cout * len(phs.dh) * self.cin_real, e0, e1))
+            else:
+                nv.check(L.crdr_conv2d(C.byref(d), st))
         return out

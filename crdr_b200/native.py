@@ -116,9 +116,14 @@ def lib():
     return _lib
 
 
-def check(rc):
+LAUNCH_COUNT = [0]  # kernel-launching C-ABI calls issued by this process (bench.py reports it)
+
+
+def check(rc, counts=True):
     if rc != 0:
         raise NativeError(f"crdr status {rc}: {lib().crdr_last_error().decode()}")
+    if counts:
+        LAUNCH_COUNT[0] += 1
 
 
 def stream_handle():
@@ -132,10 +137,10 @@ def ptr(t):
 
 
 def status_reset():
-    check(lib().crdr_status_reset(stream_handle()))
+    check(lib().crdr_status_reset(stream_handle()), counts=False)
 
 
 def status_check():
     """Synchronise the current stream and raise if any kernel flagged fp16 overflow / a pipeline timeout."""
     flags = C.c_uint32(0)
-    check(lib().crdr_status_read(C.byref(flags), stream_handle()))
+    check(lib().crdr_status_read(C.byref(flags), stream_handle()), counts=False)

@@ -1,0 +1,124 @@
+"""CPU tests: oracle and product range coder / CDF builder against the committed known-answer vectors."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def kat():
+    return np.load(os.path.join(GOLD, "rans_vectors.npz")), np.load(os.path.join(GOLD, "entropy_tables.npz"))
+
+
+@pytest.fixture(scope="module")
+def product_gc():
+    from crdr_b200.entropy import SteGaussianMeanScaleConditional, get_scale_table
+    gc = SteGaussianMeanScaleConditional(scale_bound=0.11)
+    gc.update_scale_table(get_scale_table(), force=True)
+    return gc
+
+
+def test_product_gaussian_tables_match_golden(kat, product_gc):
+    _, tab = kat
+    cdf = product_gc._quantized_cdf.numpy().astype(np.int32)
+    assert cdf.shape == (64, int(tab["gc_lengths"].max()))
+    assert hashlib.sha256(cdf.tobytes()).digest() == tab["gc_cdf_sha256"].tobytes()
+    assert np.array_equal(cdf[[0, 1, 17, 40, 63]], tab["gc_cdf_rows"])
+    assert np.array_equal(product_gc._cdf_length.numpy(), tab["gc_lengths"])
+    assert np.array_equal(product_gc._offset.numpy(), tab["gc_offsets"])
+    # every table is a strictly increasing CDF ending at 2^16
+    for i in range(64):
+        row = cdf[i, : tab["gc_lengths"][i]]
+        assert row[0] == 0 and row[-1] == 65536 and np.all(np.diff(row) > 0)
+
+
+def test_oracle_gaussian_tables_match_golden(kat, oracle):
+    _, tab = kat
+    _, gc = oracle.entropy_models(_tiny_sd(oracle))
+    assert np.array_equal(gc._quantized_cdf.numpy()[[0, 1, 17, 40, 63]], tab["gc_cdf_rows"])
+
+
+def _tiny_sd(oracle):
+    from compressai.entropy_models import EntropyBottleneck
+    eb = EntropyBottleneck(oracle.CFG["zc"])
+    return {"entropy_model_z." + k: v for k, v in eb.state_dict().items()}
+
+
+def test_product_bottleneck_tables_match_golden(kat):
+    _, tab = kat
+    from crdr_b200.entropy import SteEntropyBottleneck
+    eb = SteEntropyBottleneck(channels=8)
+    with torch.no_grad():
+        for k in tab.files:
+            if k.startswith("ebp"):
+                getattr(eb, k[3:]).copy_(torch.from_numpy(tab[k]))
+    eb.update(force=True)
+    assert np.array_equal(eb._quantized_cdf.numpy(), tab["eb_cdf"])
+    assert np.array_equal(eb._cdf_length.numpy(), tab["eb_lengths"])
+    assert np.array_equal(eb._offset.numpy(), tab["eb_offsets"])
+    p, med = eb.kernel_params("cpu")
+    assert p.shape == (8, 58) and med.shape == (8,)
+
+
+def test_rans_known_answer_product_and_oracle(kat, product_gc, oracle):
+    vec, _ = kat
+    from crdr_b200 import rans
+    from compressai import ans
+    sym, idx, want = vec["symbols"], vec["indexes"], vec["stream"].tobytes()
+    T = product_gc.coder_tables()
+    assert rans.encode(sym, idx, T) == want
+    cdf, lens, offs = product_gc._quantized_cdf.numpy(), product_gc._cdf_length.numpy(), product_gc._offset.numpy()
+    assert ans.RansEncoder().encode_with_indexes(sym, idx, cdf, lens, offs) == want
+    # decode in three calls on one coder state (decode_stream semantics of the ChARM slice loop)
+    dec = rans.Decoder(want)
+    got = np.concatenate([dec.decode_stream(idx[:100], T), dec.decode_stream(idx[100:4097], T), dec.decode_stream(idx[4097:], T)])
+    assert np.array_equal(got, sym)
+    od = ans.RansDecoder()
+    od.set_stream(want)
+    assert od.decode_stream(idx, cdf, lens, offs) == sym.tolist()
+
+
+def test_rans_edge_cases(product_gc):
+    from crdr_b200 import rans
+    T = product_gc.coder_tables()
+    # empty input: 8-byte flush only
+    s = rans.encode(np.zeros(0, np.int32), np.zeros(0, np.int32), T)
+    assert len(s) == 8
+    # all-zero symbols with the narrowest table, and extreme escapes in both directions
+    for sym in (np.zeros(5000, np.int32), np.full(300, 2 ** 24, np.int32), np.full(300, -(2 ** 24), np.int32)):
+        idx = np.zeros(sym.size, np.int32)
+        st = rans.encode(sym, idx, T)
+        assert np.array_equal(rans.Decoder(st).decode_stream(idx, T), sym)
+    with pytest.raises(ValueError):
+        rans.encode(np.zeros(4, np.int32), np.full(4, 64, np.int32), T)
+    # batch API == single API, any thread count
+    rng = np.random.default_rng(3)
+    syms = [rng.integers(-20, 20, n).astype(np.int32) for n in (1, 777, 4096)]
+    idxs = [rng.integers(0, 64, s.size).astype(np.int32) for s in syms]
+    for th in (1, 3):
+        outs = rans.encode_batch(syms, idxs, T, threads=th)
+        assert outs == [rans.encode(s, i, T) for s, i in zip(syms, idxs)]
+        decs = [rans.Decoder(o) for o in outs]
+        back = rans.decode_batch(decs, idxs, T, threads=th)
+        assert all(np.array_equal(a, b) for a, b in zip(back, syms))
+
+
+def test_pmf_to_quantized_cdf_properties(oracle):
+    from crdr_b200 import rans
+    from compressai import ans
+    rng = np.random.default_rng(0)
+    for n in (2, 5, 300, 3000):
+        p = np.abs(rng.normal(size=n)).astype(np.float32)
+        p /= p.sum()
+        p[n // 3: n // 2] = 1e-12  # forces the zero-width-bin repair
+        cdf = rans.pmf_to_quantized_cdf(p, 16)
+        assert cdf[0] == 0 and cdf[-1] == 65536 and np.all(np.diff(cdf) > 0)
+        assert np.array_equal(cdf, np.array(ans.pmf_to_quantized_cdf(p, 16)))
+    with pytest.raises(ValueError):
+        rans.pmf_to_quantized_cdf(np.array([0.5, np.nan], np.float32))

@@ -1,0 +1,220 @@
+"""GPU parity of the full codec path (through the model API, i.e. the C ABI) against
+ (1) the committed goldens produced by the UNMODIFIED reference modules, and (2) the CPU oracle on seeded inputs.
+
+Tolerances are BASELINE.json's: symbols >= 99.99 % identical, likelihoods within 1e-3 relative,
+bpp within 0.1 %, PSNR within 0.02 dB (PSNR on truncated uint8 images, img_utils.py:102-132)."""
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+pytestmark = pytest.mark.gpu
+
+SYMBOL_MATCH = 0.9999
+LIK_RTOL = 1e-3
+BPP_RTOL = 1e-3
+PSNR_ATOL = 0.02
+
+
+@pytest.fixture(scope="module")
+def models():
+    import fixtures
+    cache = {}
+
+    def get(calibrated):
+        if calibrated not in cache:
+            cache[calibrated] = fixtures.build_model(seed=0, calibrated=calibrated)
+        return cache[calibrated]
+    return get
+
+
+def _psnr_u8(real, fake_u8):
+    r = ((real + 1.0) / 2.0 * 255.0).numpy().astype(np.uint8).astype(np.float32)
+    return 10.0 * np.log10(255.0 ** 2 / float(np.mean((r - fake_u8.astype(np.float32)) ** 2)))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "codec_*.npz"))),
+                         ids=lambda p: os.path.basename(p)[6:-4])
+def test_against_reference_goldens(path, models):
+    import fixtures
+    from crdr_b200 import native as nv
+    g = np.load(path)
+    model, _ = models(bool(g["calibrated"]))
+    h, w, q, beta = int(g["h"]), int(g["w"]), float(g["q"]), float(g["beta"])
+    x = fixtures.image(1, h, w)
+    eng = model.engine()
+    a = eng.analysis(x.cuda(), q)
+    nv.status_check()
+    y_sym, y_idx, z_sym = a["y_sym"].cpu().numpy(), a["y_idx"].cpu().numpy(), a["z_sym"].cpu().numpy()
+    assert (z_sym == g["z_sym"]).mean() >= SYMBOL_MATCH
+    match = y_sym == g["y_sym"]
+    assert match.mean() >= SYMBOL_MATCH, f"symbol match {match.mean():.6f}"
+    assert (y_idx == g["y_idx"]).mean() >= SYMBOL_MATCH
+    ok = match & (y_idx == g["y_idx"])
+    lik = a["y_lik"].cpu().numpy()
+    assert np.max(np.abs(lik - g["y_lik"])[ok] / g["y_lik"][ok]) <= LIK_RTOL
+    out = model.compress(x, q)
+    ref_bits = float(g["pred_y_bit"]) + float(g["pred_z_bit"])
+    assert abs(out["pred_y_bit"] + out["pred_z_bit"] - ref_bits) <= BPP_RTOL * ref_bits
+    ref_real = 8 * (g["header"].size + g["z_string"].size + g["y_string"].size + 12)
+    my_real = 8 * (sum(len(s) for s in out["string_list"]) + 12)
+    assert abs(my_real - ref_real) <= BPP_RTOL * ref_real
+    assert out["string_list"][0] == g["header"].tobytes()
+    # decode OUR stream with OUR decoder, compare the picture with the reference's reconstruction
+    img, z_hat, y_hat = model.decompress(out["string_list"], beta=beta)
+    assert img.shape == (1, 3, h, w) and float(img.abs().max()) <= 1.0
+    assert torch.equal(y_hat, out["y_hat"]) and torch.equal(z_hat, out["z_hat"])  # scripts/compress.py:126 invariant
+    mine_u8 = ((img.cpu() + 1.0) / 2.0 * 255.0).numpy().astype(np.uint8)
+    assert abs(_psnr_u8(x, mine_u8) - float(g["psnr"])) <= PSNR_ATOL
+    if match.all() and (y_idx == g["y_idx"]).all() and (z_sym == g["z_sym"]).all():
+        # identical symbols and table indexes must give the reference's bytes exactly
+        assert out["string_list"][1] == g["z_string"].tobytes() and out["string_list"][2] == g["y_string"].tobytes()
+
+
+def test_against_oracle_seeded(models, oracle):
+    import fixtures
+    from crdr_b200 import native as nv
+    model, sd = models(True)
+    x = fixtures.image(1, 128, 192, seed=11)
+    q, beta = 2.75, 0.0
+    eb, gc = oracle.entropy_models(sd)
+    o = oracle.compress(sd, x, q, eb, gc)
+    eng = model.engine()
+    a = eng.analysis(x.cuda(), q)
+    nv.status_check()
+    assert (a["y_sym"].cpu() == o["y_sym"]).float().mean() >= SYMBOL_MATCH
+    assert (a["y_idx"].cpu() == o["y_idx"]).float().mean() >= SYMBOL_MATCH
+    assert (a["z_sym"].cpu() == o["z_sym"]).float().mean() >= SYMBOL_MATCH
+    ok = (a["y_sym"].cpu() == o["y_sym"]) & (a["y_idx"].cpu() == o["y_idx"])
+    rel = ((a["y_lik"].cpu() - o["y_lik"]).abs() / o["y_lik"])[ok]
+    assert rel.max() <= LIK_RTOL
+    assert ((a["z_lik"].cpu() - o["z_lik"]).abs() / o["z_lik"]).max() <= LIK_RTOL
+    bits = eng.bits(a["y_lik"]).item() + eng.bits(a["z_lik"]).item()
+    assert abs(bits - o["pred_y_bit"] - o["pred_z_bit"]) <= BPP_RTOL * (o["pred_y_bit"] + o["pred_z_bit"])
+    y = eng.to_nchw(a["y32"]).cpu()
+    assert (y - o["y"]).abs().max() / o["y"].abs().max() < 1e-5
+    # eval-mode forward() / run_model() of the API (validation path)
+    out = model.run_model(x, rate_ind=q, beta=beta, is_train=False)
+    fake_o = oracle.g_s(sd, o["y_hat"], q, beta)[:, :, :128, :192].clamp(-1, 1)
+    assert abs(oracle.psnr_u8(x, out["fake_images"].cpu()) - oracle.psnr_u8(x, fake_o)) <= PSNR_ATOL
+    ref_bpp = (o["pred_y_bit"] + o["pred_z_bit"]) / (128 * 192)
+    assert abs(out["bpp"].item() - ref_bpp) <= BPP_RTOL * ref_bpp
+
+
+def test_kodak_size_roundtrip_determinism_batch_invariance(models):
+    """Size-independent properties at BASELINE's full Kodak shape (no oracle needed)."""
+    import fixtures
+    model, _ = models(True)
+    x = fixtures.image(3, 512, 768, seed=5)
+    q, beta = 1.0, 3.84
+    outs = model.compress_batch(x, q, return_tensors=True)
+    again = model.compress_batch(x, q)
+    single = model.compress_batch(x[1:2], q)
+    for i in range(3):
+        assert outs[i]["string_list"] == again[i]["string_list"]          # run-to-run determinism
+    assert single[0]["string_list"] == outs[1]["string_list"]            # batch-size invariance
+    img, z_hat, y_hat = model.decompress_batch([o["string_list"] for o in outs], beta=beta)
+    assert img.shape == (3, 3, 512, 768)
+    for i in range(3):
+        assert torch.equal(y_hat[i:i + 1], outs[i]["y_hat"]) and torch.equal(z_hat[i:i + 1], outs[i]["z_hat"])
+    one, _, _ = model.decompress(outs[2]["string_list"], beta=beta)
+    assert torch.equal(one, img[2:3])
+    # device-only decode (symbols never leave the GPU) reproduces the host-coder decode bit for bit
+    eng = model.engine()
+    a = eng.analysis(x.cuda(), q)
+    img_d, yhat32_d, _ = eng.decode_device(a["z_sym"], a["y_sym"], q, beta, (512, 768))
+    assert torch.equal(img_d, img)
+
+
+def test_ragged_and_small_sizes(models, oracle):
+    import fixtures
+    model, sd = models(True)
+    for h, w in ((33, 40), (65, 64), (100, 130)):
+        x = fixtures.image(1, h, w, seed=h)
+        out = model.compress(x, 3.0)
+        img, _, y_hat = model.decompress(out["string_list"], beta=1.0)
+        assert img.shape == (1, 3, h, w) and torch.equal(y_hat, out["y_hat"])
+        o = oracle.compress(sd, x, 3.0)
+        assert abs(out["pred_y_bit"] - o["pred_y_bit"]) <= BPP_RTOL * o["pred_y_bit"] + 1.0
+
+
+def test_eltwise_kernels_against_torch():
+    import ctypes as C
+    import torch.nn.functional as F
+    from crdr_b200 import native as nv
+    from crdr_b200.engine import Act
+    L, st = nv.lib(), nv.stream_handle()
+    g = torch.Generator().manual_seed(0)
+    # image -> planes with reflect padding
+    img = (torch.rand(2, 3, 37, 50, generator=g) * 2 - 1).cuda()
+    a = Act.empty(2, 64, 64, 8)
+    nv.check(L.crdr_image_to_planes(img.data_ptr(), 2, 37, 50, 64, 64, a.planes(0), st))
+    ref = F.pad(img, (0, 14, 0, 27), mode="reflect")
+    got = a.to_nchw()
+    assert (got[:, :3] - ref).abs().max() < 2e-7 and got[:, 3:].abs().max() == 0
+    # planes -> image: crop + clamp
+    x = (torch.randn(2, 16, 24, 4, generator=g) * 2).cuda()
+    out = torch.empty(2, 3, 13, 20, device="cuda")
+    nv.check(L.crdr_planes_to_image(x.data_ptr(), 4, 2, 16, 24, 13, 20, out.data_ptr(), st))
+    assert torch.equal(out, x[:, :13, :20, :3].permute(0, 3, 1, 2).clamp(-1, 1))
+    # bits and max-abs reductions
+    lik = (torch.rand(3, 5000, generator=g) * 0.9 + 1e-6).cuda()
+    bits = torch.empty(3, device="cuda")
+    nv.check(L.crdr_bits_from_likelihood(lik.data_ptr(), 3, 5000, bits.data_ptr(), st))
+    assert torch.allclose(bits, -(torch.log(lik.double()).sum(1) / np.log(2)).float(), rtol=1e-5)
+    mx = torch.empty(1, device="cuda")
+    v = torch.randn(100000, generator=g).cuda()
+    nv.check(L.crdr_max_abs(v.data_ptr(), v.numel(), mx.data_ptr(), st))
+    assert mx.item() == v.abs().max().item()
+    # Gaussian conditional slice kernel vs the formulas of CompressAI's GaussianConditional
+    from crdr_b200.entropy import get_scale_table
+    n, hh, ww, c = 2, 5, 7, 32
+    y = (torch.randn(n, hh, ww, c, generator=g) * 6).cuda()
+    ms = torch.randn(n, hh, ww, 2 * c, generator=g).cuda()
+    ms[..., c:] = torch.exp(torch.randn(n, hh, ww, c, generator=g) * 2).cuda() - 0.2
+    table = get_scale_table().cuda()
+    d = nv.GaussDesc()
+    yq = Act.empty(n, hh, ww, c)
+    yq32 = torch.empty(n, hh, ww, c, device="cuda")
+    sym = torch.empty(n, c, hh, ww, dtype=torch.int32, device="cuda")
+    idx = torch.empty_like(sym)
+    lk = torch.empty(n, c, hh, ww, device="cuda")
+    d.y, d.y_cs, d.y_coff = y.data_ptr(), c, 0
+    d.mu = d.sigma = ms.data_ptr()
+    d.ms_cs, d.mu_coff, d.sigma_coff = 2 * c, 0, c
+    d.n, d.hw, d.c = n, hh * ww, c
+    d.scale_bound, d.scale_table, d.ntable = 0.11, table.data_ptr(), 64
+    d.yq_planes = yq.planes(0)
+    d.yq_f32, d.yq_f32_cs, d.yq_f32_coff = yq32.data_ptr(), c, 0
+    d.symbols, d.indexes, d.likelihood = sym.data_ptr(), idx.data_ptr(), lk.data_ptr()
+    d.c_total, d.nchw_coff = c, 0
+    nv.check(L.crdr_gauss_quantize(C.byref(d), st))
+    mu, sg = ms[..., :c], torch.clamp(ms[..., c:], min=0.11)
+    qq = torch.round(y - mu)
+    yh = qq + mu
+    vv = (yh - mu).abs()
+    phi = lambda t: 0.5 * torch.erfc(-(2 ** -0.5) * t)
+    lref = torch.clamp(phi((0.5 - vv) / sg) - phi((-0.5 - vv) / sg), min=1e-9)
+    iref = torch.full_like(sg, 63).int()
+    for s in table[:-1]:
+        iref -= (sg <= s).int()
+    nchw = lambda t: t.permute(0, 3, 1, 2)
+    assert torch.equal(sym, nchw(qq).int()) and torch.equal(idx, nchw(iref)) and torch.equal(yq32, yh)
+    assert ((lk - nchw(lref)).abs() / nchw(lref)).max() < 1e-4
+    assert (yq.to_nchw() - nchw(yh)).abs().max() < 1e-5
+    # decoder-side kernels reproduce the encoder-side values
+    idx2 = torch.zeros_like(idx)
+    d.indexes = idx2.data_ptr()
+    nv.check(L.crdr_gauss_indexes(C.byref(d), st))
+    assert torch.equal(idx2, idx)
+    yq32b = torch.zeros_like(yq32)
+    d.yq_f32 = yq32b.data_ptr()
+    nv.check(L.crdr_gauss_dequantize(C.byref(d), st))
+    assert torch.equal(yq32b, yq32)
+    nv.status_check()

@@ -1,0 +1,95 @@
+"""GPU parity of crdr_conv2d (tcgen05 engine, TMA weights) against float64 torch convolutions, and of the
+tcgen05 engine against the scalar cross-check engine.  Tolerances: F16X3 2e-5 of max|out| (fp32-class),
+F16X1 2e-3 (fp16 operands)."""
+import os
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+pytestmark = pytest.mark.gpu
+
+X3, X1 = 0, 1
+CASES = [
+    ("1x1 64->64 x3", 1, 64, 64, 16, 16, 1, 1, False, X3, "none"),
+    ("1x1 64->64 x1", 1, 64, 64, 16, 16, 1, 1, False, X1, "none"),
+    ("3x3 96->96 x3 relu_affine", 2, 96, 96, 12, 20, 3, 1, False, X3, "relu_affine"),
+    ("5x5s2 192->192 x3", 1, 192, 192, 32, 48, 5, 2, False, X3, "none"),
+    ("5x5s2 8->192 x3 odd dims", 1, 8, 192, 30, 42, 5, 2, False, X3, "none"),
+    ("1x1 96->192 x3 residual", 1, 96, 192, 16, 24, 1, 1, False, X3, "residual"),
+    ("1x1 160->320 x3 gate", 1, 160, 320, 8, 12, 1, 1, False, X3, "gate"),
+    ("3x3 128->32 x3 half_tanh", 1, 128, 32, 8, 12, 3, 1, False, X3, "half_tanh"),
+    ("5x5 352->224 x3", 1, 352, 224, 8, 12, 5, 1, False, X3, "none"),
+    ("deconv5x5s2 192->256 x3", 1, 192, 256, 8, 12, 5, 2, True, X3, "none"),
+    ("deconv3x3s1 256->320 x3", 1, 256, 320, 8, 12, 3, 1, True, X3, "none"),
+    ("deconv5x5s2 256->3 x1", 1, 256, 3, 16, 24, 5, 2, True, X1, "none"),
+    ("3x3 128->128 x1 relu_affine", 2, 128, 128, 16, 24, 3, 1, False, X1, "relu_affine"),
+    ("1x1 128->256 x1 residual", 1, 128, 256, 16, 24, 1, 1, False, X1, "residual"),
+    ("5x5 480->224 x3 charm n=4", 4, 480, 224, 32, 48, 5, 1, False, X3, "none"),
+    ("single pixel 1x1", 1, 64, 32, 1, 1, 1, 1, False, X3, "none"),
+    ("M=129 crosses a tile", 1, 64, 64, 3, 43, 3, 1, False, X3, "none"),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("engine", ["tma", "notma"])
+def test_conv_matches_float64(case, engine):
+    import conv_check
+    assert conv_check.run_case(case[0], conv_check.ENG[engine], *case[1:])
+
+
+def test_simt_cross_check_engine():
+    import conv_check
+    for case in CASES[:6]:
+        assert conv_check.run_case(case[0], conv_check.ENG["simt"], *case[1:])
+
+
+def test_channel_segments_and_in_place_output():
+    """Two input channel ranges of one wide tensor, output written at a channel offset (ChARM support tensor)."""
+    import torch.nn.functional as F
+    from crdr_b200 import native as nv
+    from crdr_b200.engine import Act, ConvOp
+    g = torch.Generator().manual_seed(1)
+    wide = torch.randn(2, 160, 10, 14, generator=g).cuda()
+    T = Act.from_nchw(wide)
+    w = (torch.randn(32, 96, 5, 5, generator=g) / 50).cuda()
+    b = torch.randn(32, generator=g).cuda()
+    op = ConvOp(w, b, padding=2)
+    out = Act.zeros(2, 10, 14, 64)
+    op(T, segs=[(8, 64), (120, 32)], out=out, out_coff=32)
+    torch.cuda.synchronize()
+    xin = torch.cat([T.to_nchw()[:, 8:72], T.to_nchw()[:, 120:152]], dim=1).double()
+    ref = F.conv2d(xin, w.double(), b.double(), padding=2)
+    got = out.to_nchw().double()
+    assert (got[:, 32:] - ref).abs().max() / ref.abs().max() < 2e-5
+    assert got[:, :32].abs().max() == 0
+    nv.status_check()
+
+
+def test_bad_descriptors_raise():
+    from crdr_b200 import native as nv
+    from crdr_b200.engine import Act, ConvOp
+    op = ConvOp(torch.randn(64, 64, 1, 1), torch.zeros(64))
+    x = Act.zeros(1, 4, 4, 64)
+    with pytest.raises(nv.NativeError, match="tile_n"):
+        op(x, tile_n=24)
+    with pytest.raises(nv.NativeError, match="multiples of 8"):
+        op(x, segs=[(4, 64)])
+    with pytest.raises(nv.NativeError, match="residual"):
+        op(x, mode=nv.EPI_RESIDUAL)
+
+
+def test_fp16_overflow_is_flagged_not_silent():
+    from crdr_b200 import native as nv
+    from crdr_b200.engine import Act, ConvOp
+    w = torch.full((64, 64, 1, 1), 100.0)
+    op = ConvOp(w, torch.zeros(64))
+    x = Act.from_nchw(torch.full((1, 64, 4, 4), 50.0).cuda())
+    nv.status_reset()
+    op(x)
+    with pytest.raises(nv.NativeError, match="overflow"):
+        nv.status_check()
+    nv.status_reset()
