@@ -231,7 +231,7 @@ def main():
     device_step(0)
     torch.cuda.synchronize()
     eng_mod.PROFILE_ON[0] = False
-    conv_ms = sum(a.elapsed_time(b) for (_, a, b) in eng_mod.PROFILE)
+    conv_ms = sum(p[1].elapsed_time(p[2]) for p in eng_mod.PROFILE)
     conv_launches = len(eng_mod.PROFILE)
     flops_step = 2.0 * MAC_PER_PX * B * H * W
     tensor_peak, hbm_peak, peak_src = peaks()

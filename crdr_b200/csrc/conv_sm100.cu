@@ -33,10 +33,10 @@ constexpr int kTileM = 128;
 constexpr int kKBlk = 64;                  // fp16 elements per K block = one 128-byte swizzle row
 constexpr uint32_t kAPlaneBytes = kTileM * 128;
 constexpr int kMaxStages = 6;
-constexpr int kThreads = 320;              // warps 0-3 gather, 4-7 drain/epilogue, warp 8 TMA + TMEM alloc, warp 9 MMA
+constexpr int kThreads = 512;              // warps 0-3 gather, 4-11 drain/epilogue, warp 12 TMA + TMEM alloc, warp 13 MMA, 14-15 idle
 constexpr int kChunkKB = 2;                // F16X3: K blocks per D0 accumulate chain (8 MMAs of K=16)
-constexpr uint32_t kColD0 = 0, kColD1 = 256, kColTotal = 384;  // F16X3 TMEM columns (D0 ping-pong at 0 / 128)
 constexpr uint32_t kSmemLimit = 227 * 1024;
+constexpr uint32_t kDynSmemMax = kSmemLimit - 8 * 1024;  // static smem: parameter cache (5 KB) + barriers
 
 struct alignas(64) ConvKParams {
   CUtensorMap tm_hi;
@@ -165,32 +165,91 @@ __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t n) {
 
 // ----------------------------------------------------------------------------------------------
 // Epilogue for 16 consecutive output channels of one output pixel.
+// Split in two so the global loads of a chunk can be issued before its accumulator is read:
+//   epi_load   : residual / trunk operands -> registers (raw fp16 / fp32 vectors)
+//   epi_finish : fused arithmetic + stores
+// Per-channel vectors (bias, beta bias, gain, shift) come from shared memory (loaded once per CTA).
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load16_planes(const crdr_planes& pl, int64_t pix, int co, bool vec, float (&o)[16]) {
-  const __half* hi = (const __half*)pl.hi + pix * pl.cs + pl.coff + co;
-  const __half* lo = pl.lo ? (const __half*)pl.lo + pix * pl.cs + pl.coff + co : nullptr;
-  if (vec) {
-    uint4 h[2], l[2];
-    h[0] = __ldg((const uint4*)hi);
-    h[1] = __ldg((const uint4*)hi + 1);
-    const __half* hh = (const __half*)h;
-    if (lo) {
-      l[0] = __ldg((const uint4*)lo);
-      l[1] = __ldg((const uint4*)lo + 1);
-      const __half* ll = (const __half*)l;
+constexpr int kMaxCout = 320;
+struct EpiRaw {
+  uint4 r[4];  // residual: planes -> r[0..1] = 16 hi halfs, r[2..3] = 16 lo halfs; fp32 -> 16 floats
+  uint4 t[4];  // trunk planes, same packing
+};
+
+// streaming 16-byte load that does not allocate in the (tiny, smem-carved) L1
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) {
+  __half2 h = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(h);
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  __half2 h = __halves2half2(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void epi_load(const ConvKParams& P, int64_t opix, int co0, EpiRaw& r) {
+  const crdr_conv_desc& d = P.d;
+  if (d.mode == CRDR_EPI_NONE || co0 + 16 > d.cout) return;
+  if (d.res_f32) {
+    if (P.vec_res_f32) {
+      const float* p = d.res_f32 + opix * d.res_f32_cs + d.res_f32_coff + co0;
 #pragma unroll
-      for (int e = 0; e < 16; ++e) o[e] = join_f16(hh[e], ll[e]);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 16; ++e) o[e] = __half2float(hh[e]);
+      for (int q = 0; q < 4; ++q) r.r[q] = ld_stream16(p + 4 * q);
     }
-  } else {
-#pragma unroll
-    for (int e = 0; e < 16; ++e) o[e] = lo ? join_f16(hi[e], lo[e]) : __half2float(hi[e]);
+  } else if (P.vec_res_planes) {
+    const int64_t o = opix * d.res.cs + d.res.coff + co0;
+    const __half* ph = (const __half*)d.res.hi + o;
+    r.r[0] = ld_stream16(ph);
+    r.r[1] = ld_stream16(ph + 8);
+    if (d.res.lo) {
+      const __half* pl = (const __half*)d.res.lo + o;
+      r.r[2] = ld_stream16(pl);
+      r.r[3] = ld_stream16(pl + 8);
+    }
+  }
+  if (d.mode == CRDR_EPI_GATE && P.vec_trunk) {
+    const int64_t o = opix * d.trunk.cs + d.trunk.coff + co0;
+    const __half* ph = (const __half*)d.trunk.hi + o;
+    r.t[0] = ld_stream16(ph);
+    r.t[1] = ld_stream16(ph + 8);
+    if (d.trunk.lo) {
+      const __half* pl = (const __half*)d.trunk.lo + o;
+      r.t[2] = ld_stream16(pl);
+      r.t[3] = ld_stream16(pl + 8);
+    }
   }
 }
 
-__device__ __forceinline__ void epilogue16(const ConvKParams& P, int64_t opix, int co0, float (&acc)[16]) {
+__device__ __forceinline__ float plane_at(const crdr_planes& pl, int64_t o) {
+  return pl.lo ? join_f16(((const __half*)pl.hi)[o], ((const __half*)pl.lo)[o]) : __half2float(((const __half*)pl.hi)[o]);
+}
+
+// 16 halfs (two uint4) [+ 16 lo halfs] -> 16 floats; everything stays in registers (static indexing only)
+__device__ __forceinline__ void unpack16(const uint4 (&p)[4], bool has_lo, float (&o)[16]) {
+  const uint32_t hw[8] = {p[0].x, p[0].y, p[0].z, p[0].w, p[1].x, p[1].y, p[1].z, p[1].w};
+  const uint32_t lw[8] = {p[2].x, p[2].y, p[2].z, p[2].w, p[3].x, p[3].y, p[3].z, p[3].w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 a = unpack_h2(hw[i]);
+    o[2 * i] = a.x;
+    o[2 * i + 1] = a.y;
+    if (has_lo) {
+      const float2 b = unpack_h2(lw[i]);
+      o[2 * i] = fmaf(b.x, kLoInv, a.x);
+      o[2 * i + 1] = fmaf(b.y, kLoInv, a.y);
+    }
+  }
+}
+
+// s_par: [4][kMaxCout] = bias | add_vec | scale | shift, indexed by absolute output channel
+__device__ __forceinline__ void epi_finish(const ConvKParams& P, int64_t opix, int co0, const float (&acc)[16],
+                                           const EpiRaw& raw, const float* s_par) {
   const crdr_conv_desc& d = P.d;
   const int nvalid = min(16, d.cout - co0);
   if (nvalid <= 0) return;
@@ -200,47 +259,43 @@ __device__ __forceinline__ void epilogue16(const ConvKParams& P, int64_t opix, i
   for (int e = 0; e < 16; ++e) { res[e] = 0.f; trunk[e] = 0.f; }
   if (d.mode != CRDR_EPI_NONE) {
     if (d.res_f32) {
-      const float* r = d.res_f32 + opix * d.res_f32_cs + d.res_f32_coff + co0;
       if (full && P.vec_res_f32) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          float4 t = __ldg((const float4*)r + q);
-          res[4 * q] = t.x; res[4 * q + 1] = t.y; res[4 * q + 2] = t.z; res[4 * q + 3] = t.w;
+          res[4 * q] = __uint_as_float(raw.r[q].x); res[4 * q + 1] = __uint_as_float(raw.r[q].y);
+          res[4 * q + 2] = __uint_as_float(raw.r[q].z); res[4 * q + 3] = __uint_as_float(raw.r[q].w);
         }
       } else {
-        for (int e = 0; e < nvalid; ++e) res[e] = r[e];
+        const float* r = d.res_f32 + opix * d.res_f32_cs + d.res_f32_coff + co0;
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (e < nvalid) res[e] = r[e];
       }
-    } else if (full) {
-      load16_planes(d.res, opix, co0, P.vec_res_planes, res);
+    } else if (full && P.vec_res_planes) {
+      unpack16(raw.r, d.res.lo != nullptr, res);
     } else {
-      for (int e = 0; e < nvalid; ++e) {
-        const int64_t o = opix * d.res.cs + d.res.coff + co0 + e;
-        res[e] = d.res.lo ? join_f16(((const __half*)d.res.hi)[o], ((const __half*)d.res.lo)[o])
-                          : __half2float(((const __half*)d.res.hi)[o]);
-      }
+      const int64_t o = opix * d.res.cs + d.res.coff + co0;
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (e < nvalid) res[e] = plane_at(d.res, o + e);
     }
     if (d.mode == CRDR_EPI_GATE) {
-      if (full) {
-        load16_planes(d.trunk, opix, co0, P.vec_trunk, trunk);
+      if (full && P.vec_trunk) {
+        unpack16(raw.t, d.trunk.lo != nullptr, trunk);
       } else {
-        for (int e = 0; e < nvalid; ++e) {
-          const int64_t o = opix * d.trunk.cs + d.trunk.coff + co0 + e;
-          trunk[e] = d.trunk.lo ? join_f16(((const __half*)d.trunk.hi)[o], ((const __half*)d.trunk.lo)[o])
-                                : __half2float(((const __half*)d.trunk.hi)[o]);
-        }
+        const int64_t o = opix * d.trunk.cs + d.trunk.coff + co0;
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (e < nvalid) trunk[e] = plane_at(d.trunk, o + e);
       }
     }
   }
   float v[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) {
-    const int co = co0 + e;
-    const bool ok = e < nvalid;
-    const float b = (ok && d.bias) ? __ldg(d.bias + co) : 0.f;
-    const float a = (ok && d.add_vec) ? __ldg(d.add_vec + co) : 0.f;
-    const float sc = (ok && d.scale) ? __ldg(d.scale + co) : 1.f;
-    const float sh = (ok && d.shift) ? __ldg(d.shift + co) : 0.f;
-    v[e] = epilogue_math(acc[e], b, d.relu, a, d.mode, res[e], trunk[e], sc, sh);
+    const int co = min(co0 + e, kMaxCout - 1);
+    v[e] = epilogue_math(acc[e], s_par[co], d.relu, s_par[kMaxCout + co], d.mode, res[e], trunk[e],
+                         s_par[2 * kMaxCout + co], s_par[3 * kMaxCout + co]);
   }
   if (d.out_f32) {
     float* o = d.out_f32 + opix * d.out_f32_cs + d.out_f32_coff + co0;
@@ -248,36 +303,53 @@ __device__ __forceinline__ void epilogue16(const ConvKParams& P, int64_t opix, i
 #pragma unroll
       for (int q = 0; q < 4; ++q) ((float4*)o)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     } else {
-      for (int e = 0; e < nvalid; ++e) o[e] = v[e];
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (e < nvalid) o[e] = v[e];
     }
   }
   if (d.out.hi) {
-    __half hh[16], ll[16];
     const bool want_lo = d.out.lo != nullptr;
+    uint32_t hw[8], lw[8];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
+    for (int i = 0; i < 8; ++i) {
+      __half h0, h1, l0 = __float2half_rn(0.f), l1 = __float2half_rn(0.f);
       if (want_lo) {
-        split_f16(v[e], hh[e], ll[e], P.status);
+        split_f16(v[2 * i], h0, l0, P.status);
+        split_f16(v[2 * i + 1], h1, l1, P.status);
       } else {
-        float x = v[e];
-        if (fabsf(x) > 65504.0f) { atomicOr(P.status, kFlagOverflow); x = copysignf(65504.0f, x); }
-        hh[e] = __float2half_rn(x);
+        float x0 = v[2 * i], x1 = v[2 * i + 1];
+        if (fabsf(x0) > 65504.0f || fabsf(x1) > 65504.0f) {
+          atomicOr(P.status, kFlagOverflow);
+          x0 = fminf(fmaxf(x0, -65504.0f), 65504.0f);
+          x1 = fminf(fmaxf(x1, -65504.0f), 65504.0f);
+        }
+        h0 = __float2half_rn(x0);
+        h1 = __float2half_rn(x1);
       }
+      hw[i] = pack_h2(h0, h1);
+      lw[i] = pack_h2(l0, l1);
     }
     const int64_t o = opix * d.out.cs + d.out.coff + co0;
     __half* ph = (__half*)d.out.hi + o;
     __half* pl = want_lo ? (__half*)d.out.lo + o : nullptr;
     if (full && P.vec_planes_out) {
-      ((uint4*)ph)[0] = ((const uint4*)hh)[0];
-      ((uint4*)ph)[1] = ((const uint4*)hh)[1];
+      ((uint4*)ph)[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      ((uint4*)ph)[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
       if (want_lo) {
-        ((uint4*)pl)[0] = ((const uint4*)ll)[0];
-        ((uint4*)pl)[1] = ((const uint4*)ll)[1];
+        ((uint4*)pl)[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        ((uint4*)pl)[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
       }
     } else {
-      for (int e = 0; e < nvalid; ++e) {
-        ph[e] = hh[e];
-        if (want_lo) pl[e] = ll[e];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        if (e < nvalid) {
+          const uint32_t wsel = hw[e >> 1], lsel = lw[e >> 1];
+          const unsigned short hb = (e & 1) ? (unsigned short)(wsel >> 16) : (unsigned short)(wsel & 0xffffu);
+          const unsigned short lb = (e & 1) ? (unsigned short)(lsel >> 16) : (unsigned short)(lsel & 0xffffu);
+          ((unsigned short*)ph)[e] = hb;
+          if (want_lo) ((unsigned short*)pl)[e] = lb;
+        }
       }
     }
   }
@@ -293,35 +365,53 @@ __device__ __forceinline__ int64_t out_pixel_of_row(const crdr_conv_desc& d, int
   return ((int64_t)n * d.hout + (bh * d.out_stride + d.out_ph)) * d.wout + (bw * d.out_stride + d.out_pw);
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ----------------------------------------------------------------------------------------------
-// The tcgen05 kernel
+// The tcgen05 kernel: persistent CTAs (one per SM), static round-robin tile schedule.
+//   warps 0-3  : im2col gather producers (cp.async), also L2-prefetch the epilogue operands of the tile
+//   warps 4-11 : drain D0 chunks into fp32 register totals (F16X3) and run the epilogue; two warps per
+//                TMEM lane quarter, each owning half of the tile's column chunks
+//   warp 12    : weight tiles by TMA, TMEM alloc / dealloc
+//   warp 13    : MMA issue (one thread)
+// Accumulators are double buffered per tile (F16X1: D0[2]; F16X3: D1[2] + the D0 chunk ping-pong), so the
+// epilogue of tile j overlaps the main loop of tile j+1.
+// MAXCH = column chunks (of 16) per drain warp in F16X3 mode (register totals); 0 selects F16X1.
 // ----------------------------------------------------------------------------------------------
+template <int MAXCH>
 __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
+  constexpr bool three = MAXCH > 0;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t d0_full_bar[2];   // MMA -> drain warps: a D0 chunk is complete
-  __shared__ __align__(8) uint64_t d0_empty_bar[2];  // drain warps -> MMA: the D0 buffer may be overwritten
+  __shared__ __align__(8) uint64_t d0_full_bar[2];    // F16X3: MMA -> drain warps, a D0 chunk is complete
+  __shared__ __align__(8) uint64_t d0_empty_bar[2];   // F16X3: drain warps -> MMA, the D0 buffer may be overwritten
+  __shared__ __align__(8) uint64_t acc_full_bar[2];   // F16X1: MMA -> epilogue, the tile accumulator is complete
+  __shared__ __align__(8) uint64_t acc_empty_bar[2];  // epilogue -> MMA, the tile accumulator (D0 / D1) was consumed
   __shared__ uint32_t tmem_slot;
   __shared__ int s_dh[CRDR_MAX_TAPS + 1], s_dw[CRDR_MAX_TAPS + 1];
+  __shared__ float s_par[4 * kMaxCout];
 
   const crdr_conv_desc& d = P.d;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int S = P.stages;
-  const int nplanes = P.nplanes;
-  const bool three = nplanes == 2;
+  constexpr int nplanes = three ? 2 : 1;
   const int BN = d.tile_n;
   const uint32_t b_bytes = (uint32_t)BN * 128u;
   const uint32_t stage_bytes = (uint32_t)nplanes * (kAPlaneBytes + b_bytes);
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int m0 = blockIdx.x * kTileM;
-  const int n0 = blockIdx.y * BN;
   const int nkb = P.nkb;
-  // F16X3: D0 accumulates in chunks of kChunkKB K blocks; F16X1: one chunk spanning all of K
+  const int n_tiles = d.cout_pad / BN;
+  const int num_tiles = ((P.m_total + kTileM - 1) / kTileM) * n_tiles;
   const int chunk_kb = three ? kChunkKB : nkb;
-  const int nchunks = (nkb + chunk_kb - 1) / chunk_kb;
+  const int nchunks = (nkb + chunk_kb - 1) / chunk_kb;  // D0 chunks per tile
 
+  for (int i = threadIdx.x; i < 4 * kMaxCout; i += kThreads) {
+    const int which = i / kMaxCout, co = i % kMaxCout;
+    const float* src = which == 0 ? d.bias : which == 1 ? d.add_vec : which == 2 ? d.scale : d.shift;
+    s_par[i] = (src && co < d.cout) ? src[co] : (which == 2 ? 1.f : 0.f);
+  }
   if (threadIdx.x < d.ntaps) {
     s_dh[threadIdx.x] = d.dh[threadIdx.x];
     s_dw[threadIdx.x] = d.dw[threadIdx.x];
@@ -336,22 +426,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&d0_full_bar[b]), 1u);
-      mbar_init(smem_u32(&d0_empty_bar[b]), 128u);
+      mbar_init(smem_u32(&d0_empty_bar[b]), 256u);
+      mbar_init(smem_u32(&acc_full_bar[b]), 1u);
+      mbar_init(smem_u32(&acc_empty_bar[b]), 256u);
     }
     fence_barrier_init();
   }
-  if (warp == 8) {
+  if (warp == 12) {
     if (lane == 0 && P.use_tma) {
       prefetch_tmap(&P.tm_hi);
       if (three) prefetch_tmap(&P.tm_lo);
     }
     __syncwarp();
-    tmem_alloc(smem_u32(&tmem_slot), (uint32_t)P.tmem_cols);
+    tmem_alloc(smem_u32(&tmem_slot), 512u);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  // TMEM columns.  F16X3: D0 chunk ping-pong at 0 / 128, D1 per-tile double buffer at 256 / 384.
+  //                F16X1: per-tile accumulator double buffer at 0 / 256.
+  constexpr uint32_t kAccStride = three ? 128u : 256u;
+  constexpr uint32_t kD1Base = 256u;
+
+  // Register re-balancing between the warp groups (512 threads x 128 = the whole register file):
+  // 128 * (80 + 192 + 192 + 48) = 65536.
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+  } else if (warp < 12) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+  }
 
   if (warp < 4) {
     // ------------------------------------------------------------------ gather (im2col) producers
@@ -360,50 +466,69 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
     const int rbase = t >> 3;   // rows rbase + 16*i
     const uint32_t row_off = (uint32_t)(rbase >> 3) * 1024u + (uint32_t)(rbase & 7) * 128u +
                              (uint32_t)((j ^ (rbase & 7)) << 4);
-    int pix0[8], ih0[8], iw0[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int m = m0 + rbase + 16 * i;
-      if (m < P.m_total) {
-        const int bw = m % d.wb;
-        const int tt = m / d.wb;
-        const int bh = tt % d.hb;
-        const int n = tt / d.hb;
-        ih0[i] = bh * d.in_stride;
-        iw0[i] = bw * d.in_stride;
-        pix0[i] = (n * d.hin + ih0[i]) * d.win + iw0[i];
-      } else {
-        ih0[i] = -(1 << 28);
-        iw0[i] = 0;
-        pix0[i] = 0;
-      }
-    }
     const __half* in_hi = (const __half*)d.in.hi;
     const __half* in_lo = (const __half*)d.in.lo;
     const __half* w_hi = (const __half*)d.w_hi;
     const __half* w_lo = (const __half*)d.w_lo;
     const int cin = P.cin;
-    int tap = 0, c = j * 8;  // position of this thread's chunk inside K for the current block
-    while (c >= cin) { c -= cin; ++tap; }
     const int lookahead = S - 1;
-
-    for (int it = 0; it < nkb + lookahead; ++it) {
-      if (it >= lookahead) {
-        // the block issued `lookahead` iterations ago has landed: publish it to the MMA thread
-        switch (lookahead) {
-          case 1: cp_async_wait<0>(); break;
-          case 2: cp_async_wait<1>(); break;
-          case 3: cp_async_wait<2>(); break;
-          case 4: cp_async_wait<3>(); break;
-          default: cp_async_wait<4>(); break;
+    int g = 0;     // K blocks issued so far (all tiles)
+    int gpub = 0;  // K blocks published to the MMA thread
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * kTileM;
+      const int n0 = (tile % n_tiles) * BN;
+      int pix0[8], ih0[8], iw0[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + rbase + 16 * i;
+        if (m < P.m_total) {
+          const int bw = m % d.wb;
+          const int tt = m / d.wb;
+          const int bh = tt % d.hb;
+          const int n = tt / d.hb;
+          ih0[i] = bh * d.in_stride;
+          iw0[i] = bw * d.in_stride;
+          pix0[i] = (n * d.hin + ih0[i]) * d.win + iw0[i];
+          if (d.mode != CRDR_EPI_NONE) {
+            // pull this row's epilogue operands towards L2 while the main loop runs (line j of the row segment)
+            const int64_t opix = ((int64_t)n * d.hout + (bh * d.out_stride + d.out_ph)) * d.wout + (bw * d.out_stride + d.out_pw);
+            if (d.res_f32) {
+              if (j * 32 < BN) prefetch_l2(d.res_f32 + opix * d.res_f32_cs + d.res_f32_coff + n0 + j * 32);
+            } else if (j * 64 < BN) {
+              const int64_t o = opix * d.res.cs + d.res.coff + n0 + j * 64;
+              prefetch_l2((const __half*)d.res.hi + o);
+              if (d.res.lo) prefetch_l2((const __half*)d.res.lo + o);
+            }
+            if (d.mode == CRDR_EPI_GATE && j * 64 < BN) {
+              const int64_t o = opix * d.trunk.cs + d.trunk.coff + n0 + j * 64;
+              prefetch_l2((const __half*)d.trunk.hi + o);
+              if (d.trunk.lo) prefetch_l2((const __half*)d.trunk.lo + o);
+            }
+          }
+        } else {
+          ih0[i] = -(1 << 28);
+          iw0[i] = 0;
+          pix0[i] = 0;
         }
-        fence_proxy_async();
-        mbar_arrive(smem_u32(&full_bar[(it - lookahead) % S]));
       }
-      if (it < nkb) {
-        const int s = it % S;
-        const uint32_t par = ((uint32_t)(it / S) & 1u) ^ 1u;
-        mbar_wait(smem_u32(&empty_bar[s]), par, P.status);
+      int tap = 0, c = j * 8;  // position of this thread's chunk inside K for the current block
+      while (c >= cin) { c -= cin; ++tap; }
+      for (int kb = 0; kb < nkb; ++kb, ++g) {
+        if (g - gpub >= lookahead) {
+          // the block issued `lookahead` iterations ago has landed: publish it to the MMA thread
+          switch (lookahead) {
+            case 1: cp_async_wait<0>(); break;
+            case 2: cp_async_wait<1>(); break;
+            case 3: cp_async_wait<2>(); break;
+            case 4: cp_async_wait<3>(); break;
+            default: cp_async_wait<4>(); break;
+          }
+          fence_proxy_async();
+          mbar_arrive(smem_u32(&full_bar[gpub % S]));
+          ++gpub;
+        }
+        const int s = g % S;
+        mbar_wait(smem_u32(&empty_bar[s]), ((uint32_t)(g / S) & 1u) ^ 1u, P.status);
         const uint32_t stage = smem_base + (uint32_t)s * stage_bytes;
         const bool kvalid = (tap < d.ntaps);
         const int chan = (c < d.seg0_len) ? d.seg0_off + c : d.seg1_off + (c - d.seg0_len);
@@ -421,111 +546,169 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
         if (!P.use_tma) {
           const uint32_t bst = stage + (uint32_t)nplanes * kAPlaneBytes;
           for (int i = 0; i < BN / 16; ++i) {
-            const int64_t off = (int64_t)(n0 + rbase + 16 * i) * d.k_pad + (int64_t)it * kKBlk + j * 8;
+            const int64_t off = (int64_t)(n0 + rbase + 16 * i) * d.k_pad + (int64_t)kb * kKBlk + j * 8;
             const uint32_t dst = bst + row_off + (uint32_t)i * 2048u;
             cp_async16(dst, w_hi + off, 16u);
             if (three) cp_async16(dst + b_bytes, w_lo + off, 16u);
           }
         }
+        cp_async_commit();
         c += kKBlk;
         while (c >= cin) { c -= cin; ++tap; }
       }
-      cp_async_commit();
     }
-  } else if (warp < 8) {
-    // ------------------------------------------------------------------ drain D0 chunks, then the epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // publish what is still in flight
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (; gpub < g; ++gpub) mbar_arrive(smem_u32(&full_bar[gpub % S]));
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ drain D0 chunks + epilogue
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;  // which half of the tile's column chunks
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int nch_tile = BN / 16;
+    const int ch_begin = half == 0 ? 0 : (nch_tile + 1) / 2;
+    const int ch_end = half == 0 ? (nch_tile + 1) / 2 : nch_tile;
+    float total[three ? MAXCH * 16 : 1];
     uint32_t r0[16], r1[16];
-    for (int ch = 0; ch < nchunks; ++ch) {
-      const int b = ch & 1;
-      mbar_wait(smem_u32(&d0_full_bar[b]), (uint32_t)(ch >> 1) & 1u, P.status);
-      tc_fence_after();
-      if (!three) break;  // F16X1: the single chunk is consumed directly by the epilogue below
-      const uint32_t src = lane_addr + kColD0 + (uint32_t)b * 128u;
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        tmem_ld16_issue(src + (uint32_t)c0, r0);
-        if (ch > 0) tmem_ld16_issue(lane_addr + kColTotal + (uint32_t)c0, r1);
-        tmem_wait_ld();
-        if (ch > 0) {
+    int gc = 0;  // D0 chunks seen so far (all tiles)
+    int jt = 0;  // tiles processed by this CTA
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++jt) {
+      const int m0 = (tile / n_tiles) * kTileM;
+      const int n0 = (tile % n_tiles) * BN;
+      const int tb = jt & 1;
+      const int64_t opix = out_pixel_of_row(d, m0 + row, P.m_total);
+      if (three) {
+        for (int ch = 0; ch < nchunks; ++ch, ++gc) {
+          const int b = gc & 1;
+          mbar_wait(smem_u32(&d0_full_bar[b]), (uint32_t)(gc >> 1) & 1u, P.status);
+          tc_fence_after();
+          const uint32_t src = lane_addr + (uint32_t)b * kAccStride;
 #pragma unroll
-          for (int e = 0; e < 16; ++e) r0[e] = __float_as_uint(__uint_as_float(r0[e]) + __uint_as_float(r1[e]));
+          for (int c = 0; c < MAXCH; ++c) {
+            if (ch_begin + c < ch_end) {
+              tmem_ld16_issue(src + (uint32_t)(ch_begin + c) * 16u, r0);
+              tmem_wait_ld();
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                total[c * 16 + e] = (ch == 0) ? __uint_as_float(r0[e]) : total[c * 16 + e] + __uint_as_float(r0[e]);
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(smem_u32(&d0_empty_bar[b]));
         }
-        tmem_st16(lane_addr + kColTotal + (uint32_t)c0, r0);
+      } else {
+        mbar_wait(smem_u32(&acc_full_bar[tb]), (uint32_t)(jt >> 1) & 1u, P.status);
+        tc_fence_after();
       }
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(smem_u32(&d0_empty_bar[b]));
-    }
-    const int64_t opix = out_pixel_of_row(d, m0 + row, P.m_total);
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      float acc[16];
-      tmem_ld16_issue(lane_addr + (three ? kColTotal : kColD0) + (uint32_t)c0, r0);
-      if (three) tmem_ld16_issue(lane_addr + kColD1 + (uint32_t)c0, r1);
-      tmem_wait_ld();
+      // epilogue over this warp's column chunks; loads of the next chunk are issued before finishing the current
+      EpiRaw raw[2];
+      if (opix >= 0 && ch_begin < ch_end) epi_load(P, opix, n0 + ch_begin * 16, raw[0]);
+      if (three) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e)
-        acc[e] = three ? fmaf(__uint_as_float(r1[e]), kLoInv, __uint_as_float(r0[e])) : __uint_as_float(r0[e]);
-      if (opix >= 0) epilogue16(P, opix, n0 + c0, acc);
+        for (int c = 0; c < MAXCH; ++c) {
+          const int chn = ch_begin + c;
+          if (chn < ch_end) {
+            tmem_ld16_issue(lane_addr + kD1Base + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r1);
+            if (opix >= 0 && chn + 1 < ch_end) epi_load(P, opix, n0 + (chn + 1) * 16, raw[(c + 1) & 1]);
+            tmem_wait_ld();
+            float acc[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[e] = fmaf(__uint_as_float(r1[e]), kLoInv, total[c * 16 + e]);
+            if (opix >= 0) epi_finish(P, opix, n0 + chn * 16, acc, raw[c & 1], s_par);
+          }
+        }
+      } else {
+        for (int chn = ch_begin; chn < ch_end; chn += 2) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int cc = chn + u;
+            if (cc < ch_end) {
+              tmem_ld16_issue(lane_addr + (uint32_t)tb * kAccStride + (uint32_t)cc * 16u, r0);
+              if (opix >= 0 && cc + 1 < ch_end) epi_load(P, opix, n0 + (cc + 1) * 16, raw[(u + 1) & 1]);
+              tmem_wait_ld();
+              float acc[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) acc[e] = __uint_as_float(r0[e]);
+              if (opix >= 0) epi_finish(P, opix, n0 + cc * 16, acc, raw[u], s_par);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&acc_empty_bar[tb]));
     }
-    tc_fence_before();
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // ------------------------------------------------------------------ weight tiles by TMA
     if (lane == 0 && P.use_tma) {
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % S;
-        const uint32_t par = ((uint32_t)(it / S) & 1u) ^ 1u;
-        mbar_wait(smem_u32(&empty_bar[s]), par, P.status);
-        const uint32_t bar = smem_u32(&full_bar[s]);
-        const uint32_t bst = smem_base + (uint32_t)s * stage_bytes + (uint32_t)nplanes * kAPlaneBytes;
-        mbar_arrive_expect_tx(bar, (uint32_t)nplanes * b_bytes);
-        tma_load_2d(bst, &P.tm_hi, it * kKBlk, n0, bar);
-        if (three) tma_load_2d(bst + b_bytes, &P.tm_lo, it * kKBlk, n0, bar);
+      int g = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int s = g % S;
+          mbar_wait(smem_u32(&empty_bar[s]), ((uint32_t)(g / S) & 1u) ^ 1u, P.status);
+          const uint32_t bar = smem_u32(&full_bar[s]);
+          const uint32_t bst = smem_base + (uint32_t)s * stage_bytes + (uint32_t)nplanes * kAPlaneBytes;
+          mbar_arrive_expect_tx(bar, (uint32_t)nplanes * b_bytes);
+          tma_load_2d(bst, &P.tm_hi, kb * kKBlk, n0, bar);
+          if (three) tma_load_2d(bst + b_bytes, &P.tm_lo, kb * kKBlk, n0, bar);
+        }
       }
     }
-  } else {
+  } else if (warp == 13) {
     // ------------------------------------------------------------------ MMA issue (one thread)
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16((uint32_t)BN);
-      const uint32_t d1 = tmem_base + kColD1;
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % S;
-        const int ch = it / chunk_kb;
-        const int b = ch & 1;
-        const bool chunk_first = (it % chunk_kb) == 0;
-        const bool chunk_last = ((it + 1) % chunk_kb) == 0 || it == nkb - 1;
-        if (chunk_first && ch >= 2) {
-          // the drain warps must have emptied this D0 buffer (chunk ch-2) before it is overwritten
-          mbar_wait(smem_u32(&d0_empty_bar[b]), (uint32_t)((ch - 2) >> 1) & 1u, P.status);
+      int g = 0, gc = 0, jt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++jt) {
+        const int tb = jt & 1;
+        if (jt >= 2) {
+          // the epilogue of tile jt-2 must have consumed this per-tile accumulator buffer
+          mbar_wait(smem_u32(&acc_empty_bar[tb]), (uint32_t)((jt - 2) >> 1) & 1u, P.status);
           tc_fence_after();
         }
-        mbar_wait(smem_u32(&full_bar[s]), (uint32_t)(it / S) & 1u, P.status);
-        tc_fence_after();
-        const uint32_t d0 = tmem_base + kColD0 + (three ? (uint32_t)b * 128u : 0u);
-        const uint32_t stage = smem_base + (uint32_t)s * stage_bytes;
-        const uint64_t a_hi = umma_desc_sw128(stage);
-        const uint64_t a_lo = umma_desc_sw128(stage + kAPlaneBytes);
-        const uint64_t b_hi = umma_desc_sw128(stage + (uint32_t)nplanes * kAPlaneBytes);
-        const uint64_t b_lo = umma_desc_sw128(stage + (uint32_t)nplanes * kAPlaneBytes + b_bytes);
+        const uint32_t d1 = tmem_base + kD1Base + (uint32_t)tb * kAccStride;
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int s = g % S;
+          const bool chunk_first = (kb % chunk_kb) == 0;
+          const bool chunk_last = ((kb + 1) % chunk_kb) == 0 || kb == nkb - 1;
+          const int b = gc & 1;
+          if (three && chunk_first && gc >= 2) {
+            // the drain warps must have emptied this D0 buffer (chunk gc-2) before it is overwritten
+            mbar_wait(smem_u32(&d0_empty_bar[b]), (uint32_t)((gc - 2) >> 1) & 1u, P.status);
+            tc_fence_after();
+          }
+          mbar_wait(smem_u32(&full_bar[s]), (uint32_t)(g / S) & 1u, P.status);
+          tc_fence_after();
+          const uint32_t d0 = tmem_base + (uint32_t)(three ? b : tb) * kAccStride;
+          const uint32_t stage = smem_base + (uint32_t)s * stage_bytes;
+          const uint64_t a_hi = umma_desc_sw128(stage);
+          const uint64_t a_lo = umma_desc_sw128(stage + kAPlaneBytes);
+          const uint64_t b_hi = umma_desc_sw128(stage + (uint32_t)nplanes * kAPlaneBytes);
+          const uint64_t b_lo = umma_desc_sw128(stage + (uint32_t)nplanes * kAPlaneBytes + b_bytes);
 #pragma unroll
-        for (int k = 0; k < kKBlk / 16; ++k) {
-          const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 descriptor units
-          umma_f16(d0, a_hi + adv, b_hi + adv, idesc, (chunk_first && k == 0) ? 0u : 1u);
-          if (three) {
-            umma_f16(d1, a_hi + adv, b_lo + adv, idesc, (it > 0 || k > 0) ? 1u : 0u);
-            umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);
+          for (int k = 0; k < kKBlk / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 descriptor units
+            umma_f16(d0, a_hi + adv, b_hi + adv, idesc, (chunk_first && k == 0) ? 0u : 1u);
+            if (three) {
+              umma_f16(d1, a_hi + adv, b_lo + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);
+            }
+          }
+          umma_commit(smem_u32(&empty_bar[s]));
+          if (chunk_last) {
+            if (three) { umma_commit(smem_u32(&d0_full_bar[b])); ++gc; }
+            else umma_commit(smem_u32(&acc_full_bar[tb]));
           }
         }
-        umma_commit(smem_u32(&empty_bar[s]));
-        if (chunk_last) umma_commit(smem_u32(&d0_full_bar[b]));
       }
     }
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+    tmem_dealloc(tmem_base, 512u);
   }
 }
 
@@ -737,29 +920,51 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     return check_launch("conv_simt_kernel");
   }
 
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit - 2048);
-  });
-  if (attr_err != cudaSuccess) {
-    set_error("conv2d: cannot opt in to large shared memory: %s", cudaGetErrorString(attr_err));
-    return CRDR_ERR_UNSUPPORTED_ARCH;
-  }
-  const uint32_t stage_bytes = (uint32_t)P.nplanes * (kAPlaneBytes + (uint32_t)d.tile_n * 128u);
-  const uint32_t budget = kSmemLimit - 2048 - 1024;
-  int stages = (int)(budget / stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > P.nkb + 1) stages = P.nkb + 1;
-  if (stages < 2) { set_error("conv2d: tile_n=%d leaves fewer than 2 pipeline stages", d.tile_n); return CRDR_ERR_BAD_SHAPE; }
-  P.stages = stages;
-  if (three && d.tile_n > 128) {
-    set_error("conv2d: F16X3 needs tile_n <= 128 (two D0 buffers, D1 and the fp32 total share 512 TMEM columns)");
+  if (d.cout_pad > kMaxCout) {
+    set_error("conv2d: cout_pad=%d exceeds the per-CTA parameter cache (%d)", d.cout_pad, kMaxCout);
     return CRDR_ERR_BAD_SHAPE;
   }
-  int cols = three ? 512 : 32;
-  while (cols < d.tile_n) cols *= 2;
-  P.tmem_cols = cols;
+  if (three && d.tile_n > 128) {
+    set_error("conv2d: F16X3 needs tile_n <= 128 (D0 ping-pong and double-buffered D1 share 512 TMEM columns)");
+    return CRDR_ERR_BAD_SHAPE;
+  }
+  // template instance: register-total chunks per drain warp (F16X3) or 0 (F16X1)
+  const int maxch = three ? ((d.tile_n / 16 + 1) / 2) : 0;
+  typedef void (*KernelFn)(const ConvKParams);
+  KernelFn fn = nullptr;
+  switch (maxch) {
+    case 0: fn = conv_tcgen05_kernel<0>; break;
+    case 1: fn = conv_tcgen05_kernel<1>; break;
+    case 2: fn = conv_tcgen05_kernel<2>; break;
+    case 3: fn = conv_tcgen05_kernel<3>; break;
+    default: fn = conv_tcgen05_kernel<4>; break;
+  }
+  static std::mutex attr_mutex;
+  static bool attr_done[5] = {false, false, false, false, false};
+  static int num_sms = 0;
+  {
+    std::lock_guard<std::mutex> lk(attr_mutex);
+    if (!attr_done[maxch]) {
+      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemMax);
+      if (e != cudaSuccess) {
+        set_error("conv2d: cannot opt in to large shared memory: %s", cudaGetErrorString(e));
+        return CRDR_ERR_UNSUPPORTED_ARCH;
+      }
+      attr_done[maxch] = true;
+    }
+    if (num_sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+      if (num_sms <= 0) num_sms = 148;
+    }
+  }
+  const uint32_t stage_bytes = (uint32_t)P.nplanes * (kAPlaneBytes + (uint32_t)d.tile_n * 128u);
+  int stages = (int)((kDynSmemMax - 1024) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) { set_error("conv2d: tile_n=%d leaves fewer than 2 pipeline stages", d.tile_n); return CRDR_ERR_BAD_SHAPE; }
+  P.stages = stages;
+  P.tmem_cols = 512;
   P.use_tma = d.engine == CRDR_ENGINE_TCGEN05;
   if (P.use_tma) {
     int rc = weight_tensor_map(d.w_hi, d.k_pad, d.cout_pad, d.tile_n, &P.tm_hi);
@@ -770,8 +975,9 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     }
   }
   const uint32_t smem = (uint32_t)stages * stage_bytes + 1024;
-  dim3 grid((unsigned)((m_total + kTileM - 1) / kTileM), (unsigned)(d.cout_pad / d.tile_n));
-  conv_tcgen05_kernel<<<grid, kThreads, smem, stream>>>(P);
+  const int64_t num_tiles = ((m_total + kTileM - 1) / kTileM) * (d.cout_pad / d.tile_n);
+  const unsigned grid = (unsigned)(num_tiles < num_sms ? num_tiles : num_sms);  // persistent: one CTA per SM
+  fn<<<grid, kThreads, smem, stream>>>(P);
   return check_launch("conv_tcgen05_kernel");
 }
 

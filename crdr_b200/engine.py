@@ -212,7 +212,9 @@ class ConvOp:
                 e0.record()
                 nv.check(L.crdr_conv2d(C.byref(d), st))
                 e1.record()
-                PROFILE.append((2.0 * x.n * hb * wb * self.cout * len(phs.dh) * self.cin_real, e0, e1))
+                PROFILE.append((2.0 * x.n * hb * wb * self.cout * len(phs.dh) * self.cin_real, e0, e1,
+                                dict(m=x.n * hb * wb, n=self.cout, k=len(phs.dh) * self.cin, taps=len(phs.dh), tile_n=d.tile_n,
+                                     prec=precision, transposed=self.transposed, stride=self.stride)))
             else:
                 nv.check(L.crdr_conv2d(C.byref(d), st))
         return out
