@@ -44,6 +44,7 @@ struct alignas(64) ConvKParams {
   crdr_conv_desc d;
   int32_t m_total, nkb, cin, k_real, nplanes, stages, tmem_cols, use_tma;
   int32_t vec_planes_out, vec_f32_out, vec_res_planes, vec_res_f32, vec_trunk;
+  int32_t has_bias, has_add, has_affine;
   uint32_t* status;
 };
 
@@ -61,28 +62,27 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint
+// expires) instead of burning issue slots that the epilogue warps of the same SM sub-partition need.
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(1000000u)
       : "memory");
   return ok;
 }
 // Bounded wait: a pipeline bug must end in a trap with the status flag set, never in a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t* status) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-      atomicOr(status, kFlagTimeout);
-      __threadfence_system();
-      __trap();
-    }
-  }
+#pragma unroll 1
+  for (uint32_t i = 0; i < 4000u; ++i)  // <= 4000 x 1 ms
+    if (mbar_try_wait(bar, parity)) return;
+  atomicOr(status, kFlagTimeout);
+  __threadfence_system();
+  __trap();
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -290,12 +290,47 @@ __device__ __forceinline__ void epi_finish(const ConvKParams& P, int64_t opix, i
       }
     }
   }
+  // uniform (per-launch) switches outside the element loops; per-channel vectors as 128-bit shared loads
   float v[16];
 #pragma unroll
-  for (int e = 0; e < 16; ++e) {
-    const int co = min(co0 + e, kMaxCout - 1);
-    v[e] = epilogue_math(acc[e], s_par[co], d.relu, s_par[kMaxCout + co], d.mode, res[e], trunk[e],
-                         s_par[2 * kMaxCout + co], s_par[3 * kMaxCout + co]);
+  for (int e = 0; e < 16; ++e) v[e] = acc[e];
+  const float4* par = reinterpret_cast<const float4*>(s_par + co0);
+  constexpr int kVecStride = kMaxCout / 4;
+  if (P.has_bias) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 t = par[q];
+      v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+    }
+  }
+  if (d.relu) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.0f);
+  }
+  if (P.has_add) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 t = par[kVecStride + q];
+      v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+    }
+  }
+  if (d.mode == CRDR_EPI_RESIDUAL) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] += res[e];
+  } else if (d.mode == CRDR_EPI_GATE) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = fmaf(trunk[e], sigmoidf_(v[e]), res[e]);
+  } else if (d.mode == CRDR_EPI_HALF_TANH) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = fmaf(0.5f, tanhf(v[e]), res[e]);
+  }
+  if (P.has_affine) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 sc = par[2 * kVecStride + q], sh = par[3 * kVecStride + q];
+      v[4 * q] = fmaf(v[4 * q], sc.x, sh.x); v[4 * q + 1] = fmaf(v[4 * q + 1], sc.y, sh.y);
+      v[4 * q + 2] = fmaf(v[4 * q + 2], sc.z, sh.z); v[4 * q + 3] = fmaf(v[4 * q + 3], sc.w, sh.w);
+    }
   }
   if (d.out_f32) {
     float* o = d.out_f32 + opix * d.out_f32_cs + d.out_f32_coff + co0;
@@ -390,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
   __shared__ __align__(8) uint64_t acc_empty_bar[2];  // epilogue -> MMA, the tile accumulator (D0 / D1) was consumed
   __shared__ uint32_t tmem_slot;
   __shared__ int s_dh[CRDR_MAX_TAPS + 1], s_dw[CRDR_MAX_TAPS + 1];
-  __shared__ float s_par[4 * kMaxCout];
+  __shared__ __align__(16) float s_par[4 * kMaxCout];
 
   const crdr_conv_desc& d = P.d;
   const int warp = threadIdx.x >> 5;
@@ -477,18 +512,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * kTileM;
       const int n0 = (tile % n_tiles) * BN;
-      int pix0[8], ih0[8], iw0[8];
+      int64_t rowoff[8];   // element offset of the row's tap-(0,0) input pixel (channel coff included)
+      uint32_t tapmask[8]; // bit t set <=> tap t of this row lies inside the image
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int m = m0 + rbase + 16 * i;
+        rowoff[i] = 0;
+        tapmask[i] = 0u;
         if (m < P.m_total) {
           const int bw = m % d.wb;
           const int tt = m / d.wb;
           const int bh = tt % d.hb;
           const int n = tt / d.hb;
-          ih0[i] = bh * d.in_stride;
-          iw0[i] = bw * d.in_stride;
-          pix0[i] = (n * d.hin + ih0[i]) * d.win + iw0[i];
+          const int ih0 = bh * d.in_stride, iw0 = bw * d.in_stride;
+          rowoff[i] = ((int64_t)(n * d.hin + ih0) * d.win + iw0) * d.in.cs + d.in.coff;
+          for (int tp = 0; tp < d.ntaps; ++tp) {
+            const int ih = ih0 + s_dh[tp], iw = iw0 + s_dw[tp];
+            if ((unsigned)ih < (unsigned)d.hin && (unsigned)iw < (unsigned)d.win) tapmask[i] |= 1u << tp;
+          }
           if (d.mode != CRDR_EPI_NONE) {
             // pull this row's epilogue operands towards L2 while the main loop runs (line j of the row segment)
             const int64_t opix = ((int64_t)n * d.hout + (bh * d.out_stride + d.out_ph)) * d.wout + (bw * d.out_stride + d.out_pw);
@@ -505,10 +546,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
               if (d.trunk.lo) prefetch_l2((const __half*)d.trunk.lo + o);
             }
           }
-        } else {
-          ih0[i] = -(1 << 28);
-          iw0[i] = 0;
-          pix0[i] = 0;
         }
       }
       int tap = 0, c = j * 8;  // position of this thread's chunk inside K for the current block
@@ -530,15 +567,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
         const int s = g % S;
         mbar_wait(smem_u32(&empty_bar[s]), ((uint32_t)(g / S) & 1u) ^ 1u, P.status);
         const uint32_t stage = smem_base + (uint32_t)s * stage_bytes;
-        const bool kvalid = (tap < d.ntaps);
+        const int tapc = min(tap, d.ntaps);  // == ntaps in the zero-padded K tail: no mask bit is set there
         const int chan = (c < d.seg0_len) ? d.seg0_off + c : d.seg1_off + (c - d.seg0_len);
-        const int dhv = s_dh[min(tap, d.ntaps)], dwv = s_dw[min(tap, d.ntaps)];
-        const int tapoff = dhv * d.win + dwv;
+        const int64_t delta = (int64_t)((s_dh[tapc] * d.win + s_dw[tapc]) * d.in.cs + chan);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int ih = ih0[i] + dhv, iw = iw0[i] + dwv;
-          const bool ok = kvalid && (unsigned)ih < (unsigned)d.hin && (unsigned)iw < (unsigned)d.win;
-          const int64_t off = ok ? ((int64_t)(pix0[i] + tapoff) * d.in.cs + d.in.coff + chan) : 0;
+          const bool ok = (tapmask[i] >> tapc) & 1u;
+          const int64_t off = ok ? rowoff[i] + delta : 0;
           const uint32_t dst = stage + row_off + (uint32_t)i * 2048u;
           cp_async16(dst, in_hi + off, ok ? 16u : 0u);
           if (three) cp_async16(dst + kAPlaneBytes, in_lo + off, ok ? 16u : 0u);
@@ -911,6 +946,9 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
   P.vec_res_planes = d.res.hi ? planes_vec_ok(d.res) : 0;
   P.vec_res_f32 = d.res_f32 && aligned16(d.res_f32) && d.res_f32_cs % 4 == 0 && d.res_f32_coff % 4 == 0;
   P.vec_trunk = d.trunk.hi ? planes_vec_ok(d.trunk) : 0;
+  P.has_bias = d.bias != nullptr;
+  P.has_add = d.add_vec != nullptr;
+  P.has_affine = d.scale != nullptr || d.shift != nullptr;
 
   if (d.engine == CRDR_ENGINE_SIMT) {
     const int64_t total = m_total * d.cout;
