@@ -190,8 +190,8 @@ class HyperSynthesisEngine:
 class SliceNet:
     """SliceTransform (minnen20_charm_context_model.py:26-38): conv5x5 -> ReLU -> conv5x5 -> ReLU -> conv3x3."""
 
-    def __init__(self, sd, cfg):
-        self.c1 = Conv(sd, "model.0", cfg, padding=2)
+    def __init__(self, sd, cfg, seg_lens):
+        self.c1 = Conv(sd, "model.0", cfg, padding=2, seg_lens=seg_lens)
         self.c2 = Conv(sd, "model.2", cfg, padding=2)
         self.c3 = Conv(sd, "model.4", cfg, padding=1)
 
@@ -224,20 +224,23 @@ class CharmEngine:
         self.cfg = cfg
         self.S, self.sc, self.hc = num_slices, slice_ch, hyper_ch
         self.max_support = max_support
-        self.mean = [SliceNet(_sub(sd, f"mean_slice_transforms.{i}"), cfg) for i in range(num_slices)]
-        self.scale = [SliceNet(_sub(sd, f"scale_slice_transforms.{i}"), cfg) for i in range(num_slices)]
-        self.lrp = [SliceNet(_sub(sd, f"lrp_slice_transforms.{i}"), cfg) for i in range(num_slices)]
         self.off_scale, self.off_mean = 0, hyper_ch
         self.off_y = 2 * hyper_ch
         self.off_tmp = self.off_y + num_slices * slice_ch
         self.cs = self.off_tmp + slice_ch * num_slices  # one scratch slot per slice (slices of a group run together)
         self.yc = num_slices * slice_ch
+        lens = lambda segs: [l for _, l in segs]
+        self.mean = [SliceNet(_sub(sd, f"mean_slice_transforms.{i}"), cfg, lens(self._segs_mean(i))) for i in range(num_slices)]
+        self.scale = [SliceNet(_sub(sd, f"scale_slice_transforms.{i}"), cfg, lens(self._segs_scale(i))) for i in range(num_slices)]
+        self.lrp = [SliceNet(_sub(sd, f"lrp_slice_transforms.{i}"), cfg, lens(self._segs_lrp(i))) for i in range(num_slices)]
 
     def n_support(self, s):
         return s if self.max_support < 0 else min(s, self.max_support)
 
     def new_support(self, n, h, w, device):
-        return Act.empty(n, h, w, self.cs, two=True, device=device)
+        # zero-filled: the 64-channel blocks of the patch engine may read channels that are written later
+        # (their weights are zero, but NaN bit patterns of uninitialised memory would still poison the sum)
+        return Act.zeros(n, h, w, self.cs, two=True, device=device)
 
     def groups(self):
         """Slices whose (mu, sigma) depend only on already-finished slices can be processed together."""

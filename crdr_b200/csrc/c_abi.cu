@@ -93,6 +93,14 @@ int crdr_status_read(uint32_t* flags, void* stream) {
   return CRDR_OK;
 }
 
+/* bring-up aid (not part of the documented ABI): MMA-thread cycle counters of CTA 0 of the last traced launch */
+int crdr_debug_counters(unsigned long long* out6) {
+  uint32_t* p = device_status_word();
+  if (!p) return CRDR_ERR_CUDA;
+  cudaDeviceSynchronize();
+  return cudaMemcpy(out6, p + 16, 48, cudaMemcpyDeviceToHost) == cudaSuccess ? CRDR_OK : CRDR_ERR_CUDA;
+}
+
 int crdr_conv2d(const crdr_conv_desc* d, void* stream) {
   if (!d) { set_error("conv2d: null descriptor"); return CRDR_ERR_BAD_SHAPE; }
   return conv2d_launch(d, (cudaStream_t)stream);

@@ -22,6 +22,7 @@
 //
 // Deterministic: fixed K order, no atomics on data, no split-K; a given output pixel sees the same
 // arithmetic whatever the batch size or tile position.
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -38,13 +39,21 @@ constexpr int kChunkKB = 2;                // F16X3: K blocks per D0 accumulate 
 constexpr uint32_t kSmemLimit = 227 * 1024;
 constexpr uint32_t kDynSmemMax = kSmemLimit - 8 * 1024;  // static smem: parameter cache (5 KB) + barriers
 
+constexpr int kMaxCBlocks = 12;            // PATCH mode: 64-channel blocks of the (two-range) input
+constexpr int kPatchTH = 16, kPatchTW = 8; // PATCH mode: the 128 GEMM rows are a 16 x 8 pixel tile of the base grid
+
 struct alignas(64) ConvKParams {
   CUtensorMap tm_hi;
   CUtensorMap tm_lo;
+  CUtensorMap tm_in_hi;  // PATCH mode: 4-D (C, W, H, N) view of the input planes
+  CUtensorMap tm_in_lo;
   crdr_conv_desc d;
+  // PATCH mode geometry
+  int32_t ph, pw, dh_min, dw_min, ncb, tiles_h, tiles_w, patch_stages;
+  int32_t cb_c0[kMaxCBlocks];
   int32_t m_total, nkb, cin, k_real, nplanes, stages, tmem_cols, use_tma;
   int32_t vec_planes_out, vec_f32_out, vec_res_planes, vec_res_f32, vec_trunk;
-  int32_t has_bias, has_add, has_affine;
+  int32_t has_bias, has_add, has_affine, chunk_kb, trace, split, fast_epi;
   uint32_t* status;
 };
 
@@ -101,6 +110,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
@@ -112,6 +128,16 @@ __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// one lane of a fully converged warp (CUTLASS elect_one_sync)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -158,6 +184,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// Same layout for an operand that starts at an arbitrary 128-byte row of a swizzled buffer and whose 8-row
+// groups are `sbo_bytes` apart (PATCH mode: one group per tile row of the halo patch).  Measured on B200: the
+// swizzle XOR is taken from the absolute shared-memory address bits, so as long as the buffer itself (the TMA
+// destination) is 1024-byte aligned the operand may start at any row and use any 128-byte-multiple group stride
+// with base_offset = 0 (setting base_offset to the start row's phase gives wrong results).
+__device__ __forceinline__ uint64_t umma_desc_sw128_rows(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // kind::f16 instruction descriptor: fp16 A/B (K-major), fp32 accumulate, M=128, N=n.
 __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t n) {
   return (1u << 4) | ((n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
@@ -171,10 +210,9 @@ __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t n) {
 // Per-channel vectors (bias, beta bias, gain, shift) come from shared memory (loaded once per CTA).
 // ----------------------------------------------------------------------------------------------
 constexpr int kMaxCout = 320;
-struct EpiRaw {
-  uint4 r[4];  // residual: planes -> r[0..1] = 16 hi halfs, r[2..3] = 16 lo halfs; fp32 -> 16 floats
-  uint4 t[4];  // trunk planes, same packing
-};
+// Raw epilogue operands of one 16-channel chunk, NR 16-byte registers:
+//   NR == 4 (F16X3): planes -> r[0..1] = 16 hi halfs, r[2..3] = 16 lo halfs;  fp32 residual -> 16 floats
+//   NR == 2 (F16X1): hi halfs only (single-term tensors; an fp32 residual is read in epi_finish instead)
 
 // streaming 16-byte load that does not allocate in the (tiny, smem-carved) L1
 __device__ __forceinline__ uint4 ld_stream16(const void* p) {
@@ -193,37 +231,39 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__device__ __forceinline__ void epi_load(const ConvKParams& P, int64_t opix, int co0, EpiRaw& r) {
+template <int NR>
+__device__ __forceinline__ void epi_load_planes(const crdr_planes& pl, int64_t opix, int co0, uint4 (&r)[NR]) {
+  const int64_t o = opix * pl.cs + pl.coff + co0;
+  const __half* ph = (const __half*)pl.hi + o;
+  r[0] = ld_stream16(ph);
+  r[1] = ld_stream16(ph + 8);
+  if (NR == 4 && pl.lo) {
+    const __half* plo = (const __half*)pl.lo + o;
+    r[NR - 2] = ld_stream16(plo);
+    r[NR - 1] = ld_stream16(plo + 8);
+  }
+}
+
+template <int NR>
+__device__ __forceinline__ void epi_load_res(const ConvKParams& P, int64_t opix, int co0, uint4 (&r)[NR]) {
   const crdr_conv_desc& d = P.d;
-  if (d.mode == CRDR_EPI_NONE || co0 + 16 > d.cout) return;
+  if (d.mode == CRDR_EPI_NONE || !P.fast_epi) return;
   if (d.res_f32) {
-    if (P.vec_res_f32) {
+    if (NR == 4) {
       const float* p = d.res_f32 + opix * d.res_f32_cs + d.res_f32_coff + co0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) r.r[q] = ld_stream16(p + 4 * q);
+      for (int q = 0; q < NR; ++q) r[q] = ld_stream16(p + 4 * q);
     }
-  } else if (P.vec_res_planes) {
-    const int64_t o = opix * d.res.cs + d.res.coff + co0;
-    const __half* ph = (const __half*)d.res.hi + o;
-    r.r[0] = ld_stream16(ph);
-    r.r[1] = ld_stream16(ph + 8);
-    if (d.res.lo) {
-      const __half* pl = (const __half*)d.res.lo + o;
-      r.r[2] = ld_stream16(pl);
-      r.r[3] = ld_stream16(pl + 8);
-    }
+  } else {
+    epi_load_planes<NR>(d.res, opix, co0, r);
   }
-  if (d.mode == CRDR_EPI_GATE && P.vec_trunk) {
-    const int64_t o = opix * d.trunk.cs + d.trunk.coff + co0;
-    const __half* ph = (const __half*)d.trunk.hi + o;
-    r.t[0] = ld_stream16(ph);
-    r.t[1] = ld_stream16(ph + 8);
-    if (d.trunk.lo) {
-      const __half* pl = (const __half*)d.trunk.lo + o;
-      r.t[2] = ld_stream16(pl);
-      r.t[3] = ld_stream16(pl + 8);
-    }
-  }
+}
+
+template <int NR>
+__device__ __forceinline__ void epi_load_trunk(const ConvKParams& P, int64_t opix, int co0, uint4 (&t)[NR]) {
+  const crdr_conv_desc& d = P.d;
+  if (d.mode != CRDR_EPI_GATE || !P.fast_epi) return;
+  epi_load_planes<NR>(d.trunk, opix, co0, t);
 }
 
 __device__ __forceinline__ float plane_at(const crdr_planes& pl, int64_t o) {
@@ -231,9 +271,11 @@ __device__ __forceinline__ float plane_at(const crdr_planes& pl, int64_t o) {
 }
 
 // 16 halfs (two uint4) [+ 16 lo halfs] -> 16 floats; everything stays in registers (static indexing only)
-__device__ __forceinline__ void unpack16(const uint4 (&p)[4], bool has_lo, float (&o)[16]) {
+template <int NR>
+__device__ __forceinline__ void unpack16(const uint4 (&p)[NR], bool has_lo, float (&o)[16]) {
   const uint32_t hw[8] = {p[0].x, p[0].y, p[0].z, p[0].w, p[1].x, p[1].y, p[1].z, p[1].w};
-  const uint32_t lw[8] = {p[2].x, p[2].y, p[2].z, p[2].w, p[3].x, p[3].y, p[3].z, p[3].w};
+  const uint32_t lw[8] = {p[NR - 2].x, p[NR - 2].y, p[NR - 2].z, p[NR - 2].w, p[NR - 1].x, p[NR - 1].y, p[NR - 1].z, p[NR - 1].w};
+  has_lo = has_lo && NR == 4;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float2 a = unpack_h2(hw[i]);
@@ -248,47 +290,60 @@ __device__ __forceinline__ void unpack16(const uint4 (&p)[4], bool has_lo, float
 }
 
 // s_par: [4][kMaxCout] = bias | add_vec | scale | shift, indexed by absolute output channel
-__device__ __forceinline__ void epi_finish(const ConvKParams& P, int64_t opix, int co0, const float (&acc)[16],
-                                           const EpiRaw& raw, const float* s_par) {
+// Generic (rare) epilogue: partial channel chunks, unaligned strides, fp32 residual in F16X1 launches.  Kept out of
+// line so the unrolled hot path stays small (instruction-fetch stalls were ~1/3 of the epilogue warps' stall samples).
+__device__ __noinline__ void epi_finish_generic(const ConvKParams* Pp, int64_t opix, int co0, const float* acc,
+                                                const float* s_par) {
+  const ConvKParams& P = *Pp;
   const crdr_conv_desc& d = P.d;
   const int nvalid = min(16, d.cout - co0);
-  if (nvalid <= 0) return;
-  const bool full = nvalid == 16;
+  for (int e = 0; e < nvalid; ++e) {
+    const int co = co0 + e;
+    float res = 0.f, trunk = 0.f;
+    if (d.mode != CRDR_EPI_NONE) {
+      if (d.res_f32) res = d.res_f32[opix * d.res_f32_cs + d.res_f32_coff + co];
+      else res = plane_at(d.res, opix * d.res.cs + d.res.coff + co);
+      if (d.mode == CRDR_EPI_GATE) trunk = plane_at(d.trunk, opix * d.trunk.cs + d.trunk.coff + co);
+    }
+    const float v = epilogue_math(acc[e], s_par[co], d.relu, s_par[kMaxCout + co], d.mode, res, trunk,
+                                  s_par[2 * kMaxCout + co], s_par[3 * kMaxCout + co]);
+    if (d.out_f32) d.out_f32[opix * d.out_f32_cs + d.out_f32_coff + co] = v;
+    if (d.out.hi) {
+      const int64_t o = opix * d.out.cs + d.out.coff + co;
+      if (d.out.lo) {
+        __half h, l;
+        split_f16(v, h, l, P.status);
+        ((__half*)d.out.hi)[o] = h;
+        ((__half*)d.out.lo)[o] = l;
+      } else {
+        float x = v;
+        if (fabsf(x) > 65504.0f) { atomicOr(P.status, kFlagOverflow); x = copysignf(65504.0f, x); }
+        ((__half*)d.out.hi)[o] = __float2half_rn(x);
+      }
+    }
+  }
+}
+
+// Hot path: a full 16-channel chunk with every operand vector-aligned (P.fast_epi); residual / trunk operands were
+// preloaded into registers (rr / rt).
+template <int NR>
+__device__ __forceinline__ void epi_finish(const ConvKParams& P, int64_t opix, int co0, const float (&acc)[16],
+                                           const uint4 (&rr)[NR], const uint4 (&rt)[NR], const float* s_par) {
+  const crdr_conv_desc& d = P.d;
   float res[16], trunk[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) { res[e] = 0.f; trunk[e] = 0.f; }
   if (d.mode != CRDR_EPI_NONE) {
-    if (d.res_f32) {
-      if (full && P.vec_res_f32) {
+    if (NR == 4 && d.res_f32) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          res[4 * q] = __uint_as_float(raw.r[q].x); res[4 * q + 1] = __uint_as_float(raw.r[q].y);
-          res[4 * q + 2] = __uint_as_float(raw.r[q].z); res[4 * q + 3] = __uint_as_float(raw.r[q].w);
-        }
-      } else {
-        const float* r = d.res_f32 + opix * d.res_f32_cs + d.res_f32_coff + co0;
-#pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if (e < nvalid) res[e] = r[e];
+      for (int q = 0; q < NR; ++q) {
+        res[4 * q] = __uint_as_float(rr[q].x); res[4 * q + 1] = __uint_as_float(rr[q].y);
+        res[4 * q + 2] = __uint_as_float(rr[q].z); res[4 * q + 3] = __uint_as_float(rr[q].w);
       }
-    } else if (full && P.vec_res_planes) {
-      unpack16(raw.r, d.res.lo != nullptr, res);
     } else {
-      const int64_t o = opix * d.res.cs + d.res.coff + co0;
-#pragma unroll
-      for (int e = 0; e < 16; ++e)
-        if (e < nvalid) res[e] = plane_at(d.res, o + e);
+      unpack16<NR>(rr, d.res.lo != nullptr, res);
     }
-    if (d.mode == CRDR_EPI_GATE) {
-      if (full && P.vec_trunk) {
-        unpack16(raw.t, d.trunk.lo != nullptr, trunk);
-      } else {
-        const int64_t o = opix * d.trunk.cs + d.trunk.coff + co0;
-#pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if (e < nvalid) trunk[e] = plane_at(d.trunk, o + e);
-      }
-    }
+    if (d.mode == CRDR_EPI_GATE) unpack16<NR>(rt, d.trunk.lo != nullptr, trunk);
   }
   // uniform (per-launch) switches outside the element loops; per-channel vectors as 128-bit shared loads
   float v[16];
@@ -334,14 +389,8 @@ __device__ __forceinline__ void epi_finish(const ConvKParams& P, int64_t opix, i
   }
   if (d.out_f32) {
     float* o = d.out_f32 + opix * d.out_f32_cs + d.out_f32_coff + co0;
-    if (full && P.vec_f32_out) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) ((float4*)o)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 16; ++e)
-        if (e < nvalid) o[e] = v[e];
-    }
+    for (int q = 0; q < 4; ++q) ((float4*)o)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
   if (d.out.hi) {
     const bool want_lo = d.out.lo != nullptr;
@@ -367,25 +416,12 @@ __device__ __forceinline__ void epi_finish(const ConvKParams& P, int64_t opix, i
     }
     const int64_t o = opix * d.out.cs + d.out.coff + co0;
     __half* ph = (__half*)d.out.hi + o;
-    __half* pl = want_lo ? (__half*)d.out.lo + o : nullptr;
-    if (full && P.vec_planes_out) {
-      ((uint4*)ph)[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-      ((uint4*)ph)[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-      if (want_lo) {
-        ((uint4*)pl)[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        ((uint4*)pl)[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        if (e < nvalid) {
-          const uint32_t wsel = hw[e >> 1], lsel = lw[e >> 1];
-          const unsigned short hb = (e & 1) ? (unsigned short)(wsel >> 16) : (unsigned short)(wsel & 0xffffu);
-          const unsigned short lb = (e & 1) ? (unsigned short)(lsel >> 16) : (unsigned short)(lsel & 0xffffu);
-          ((unsigned short*)ph)[e] = hb;
-          if (want_lo) ((unsigned short*)pl)[e] = lb;
-        }
-      }
+    ((uint4*)ph)[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    ((uint4*)ph)[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+    if (want_lo) {
+      __half* pl = (__half*)d.out.lo + o;
+      ((uint4*)pl)[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      ((uint4*)pl)[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
     }
   }
 }
@@ -400,7 +436,47 @@ __device__ __forceinline__ int64_t out_pixel_of_row(const crdr_conv_desc& d, int
   return ((int64_t)n * d.hout + (bh * d.out_stride + d.out_ph)) * d.wout + (bw * d.out_stride + d.out_pw);
 }
 
+// PATCH mode tiling: m-tile index -> (image, top-left base pixel); row r of the tile is pixel (h0 + r/8, w0 + r%8)
+__device__ __forceinline__ void patch_tile_origin(const ConvKParams& P, int mt, int& n, int& h0, int& w0) {
+  const int tw = mt % P.tiles_w;
+  const int t = mt / P.tiles_w;
+  const int th = t % P.tiles_h;
+  n = t / P.tiles_h;
+  h0 = th * kPatchTH;
+  w0 = tw * kPatchTW;
+}
+__device__ __forceinline__ int64_t out_pixel_of_patch_row(const ConvKParams& P, int mt, int row) {
+  int n, h0, w0;
+  patch_tile_origin(P, mt, n, h0, w0);
+  const int bh = h0 + (row >> 3), bw = w0 + (row & 7);
+  const crdr_conv_desc& d = P.d;
+  if (bh >= d.hb || bw >= d.wb) return -1;
+  return ((int64_t)n * d.hout + (bh * d.out_stride + d.out_ph)) * d.wout + (bw * d.out_stride + d.out_pw);
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Pull the residual / trunk operands of one output pixel (channels [c_begin, c_end)) towards L2.
+__device__ __forceinline__ void prefetch_epilogue_operands(const crdr_conv_desc& d, int64_t opix, int c_begin, int c_end) {
+  if (d.mode == CRDR_EPI_NONE || opix < 0) return;
+  if (d.res_f32) {
+    const float* p = d.res_f32 + opix * d.res_f32_cs + d.res_f32_coff;
+    for (int c = c_begin; c < c_end; c += 32) prefetch_l2(p + c);
+  } else {
+    const int64_t o = opix * d.res.cs + d.res.coff;
+    for (int c = c_begin; c < c_end; c += 64) {
+      prefetch_l2((const __half*)d.res.hi + o + c);
+      if (d.res.lo) prefetch_l2((const __half*)d.res.lo + o + c);
+    }
+  }
+  if (d.mode == CRDR_EPI_GATE) {
+    const int64_t o = opix * d.trunk.cs + d.trunk.coff;
+    for (int c = c_begin; c < c_end; c += 64) {
+      prefetch_l2((const __half*)d.trunk.hi + o + c);
+      if (d.trunk.lo) prefetch_l2((const __half*)d.trunk.lo + o + c);
+    }
+  }
+}
 
 // ----------------------------------------------------------------------------------------------
 // The tcgen05 kernel: persistent CTAs (one per SM), static round-robin tile schedule.
@@ -413,7 +489,11 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // epilogue of tile j overlaps the main loop of tile j+1.
 // MAXCH = column chunks (of 16) per drain warp in F16X3 mode (register totals); 0 selects F16X1.
 // ----------------------------------------------------------------------------------------------
-template <int MAXCH>
+// PATCH (stride-1 inputs): instead of gathering one [128 x 64] im2col tile per (tap, channel block) from L2, one
+// TMA box load brings the (16 + span_h) x (8 + span_w) halo patch of a 64-channel block into shared memory
+// (zero fill outside the image) and every tap's A operand is just a different start row of that patch, addressed
+// through the UMMA descriptor (group stride = patch row pitch).  L2 -> SM traffic for A drops by ~ntaps.
+template <int MAXCH, bool PATCH>
 __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
   constexpr bool three = MAXCH > 0;
   extern __shared__ uint8_t smem_raw[];
@@ -423,6 +503,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
   __shared__ __align__(8) uint64_t d0_empty_bar[2];   // F16X3: drain warps -> MMA, the D0 buffer may be overwritten
   __shared__ __align__(8) uint64_t acc_full_bar[2];   // F16X1: MMA -> epilogue, the tile accumulator is complete
   __shared__ __align__(8) uint64_t acc_empty_bar[2];  // epilogue -> MMA, the tile accumulator (D0 / D1) was consumed
+  __shared__ __align__(8) uint64_t patch_full_bar[2];
+  __shared__ __align__(8) uint64_t patch_empty_bar[2];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_dh[CRDR_MAX_TAPS + 1], s_dw[CRDR_MAX_TAPS + 1];
   __shared__ __align__(16) float s_par[4 * kMaxCout];
@@ -434,12 +516,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
   constexpr int nplanes = three ? 2 : 1;
   const int BN = d.tile_n;
   const uint32_t b_bytes = (uint32_t)BN * 128u;
-  const uint32_t stage_bytes = (uint32_t)nplanes * (kAPlaneBytes + b_bytes);
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // shared memory: [patch stages (PATCH only)] [ring of S stages: (A tile, gather mode only) + B tile]
+  const uint32_t patch_plane_bytes = PATCH ? (uint32_t)(P.ph * P.pw) * 128u : 0u;
+  const uint32_t patch_stage_bytes = (patch_plane_bytes * nplanes + 1023u) & ~1023u;
+  const uint32_t a_bytes = PATCH ? 0u : kAPlaneBytes;
+  const uint32_t stage_bytes = (uint32_t)nplanes * (a_bytes + b_bytes);
+  const uint32_t smem_patch = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_base = smem_patch + (PATCH ? (uint32_t)P.patch_stages * patch_stage_bytes : 0u);
   const int nkb = P.nkb;
   const int n_tiles = d.cout_pad / BN;
-  const int num_tiles = ((P.m_total + kTileM - 1) / kTileM) * n_tiles;
-  const int chunk_kb = three ? kChunkKB : nkb;
+  const int num_tiles = (PATCH ? d.n * P.tiles_h * P.tiles_w : (P.m_total + kTileM - 1) / kTileM) * n_tiles;
+  const int chunk_kb = three ? P.chunk_kb : nkb;
   const int nchunks = (nkb + chunk_kb - 1) / chunk_kb;  // D0 chunks per tile
 
   for (int i = threadIdx.x; i < 4 * kMaxCout; i += kThreads) {
@@ -454,7 +541,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
   if (threadIdx.x == 0) {
     s_dh[d.ntaps] = 0;  // tap index of the zero-padded K tail
     s_dw[d.ntaps] = 0;
-    const uint32_t full_count = P.use_tma ? 129u : 128u;
+    const uint32_t full_count = PATCH ? 1u : (P.use_tma ? 129u : 128u);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&patch_full_bar[b]), 1u);
+      mbar_init(smem_u32(&patch_empty_bar[b]), 1u);
+    }
     for (int s = 0; s < S; ++s) {
       mbar_init(smem_u32(&full_bar[s]), full_count);
       mbar_init(smem_u32(&empty_bar[s]), 1u);
@@ -468,9 +559,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
     fence_barrier_init();
   }
   if (warp == 12) {
-    if (lane == 0 && P.use_tma) {
+    if (lane == 0 && (P.use_tma || PATCH)) {
       prefetch_tmap(&P.tm_hi);
       if (three) prefetch_tmap(&P.tm_lo);
+      if (PATCH) {
+        prefetch_tmap(&P.tm_in_hi);
+        if (three) prefetch_tmap(&P.tm_in_lo);
+      }
     }
     __syncwarp();
     tmem_alloc(smem_u32(&tmem_slot), 512u);
@@ -481,20 +576,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
   const uint32_t tmem_base = tmem_slot;
   // TMEM columns.  F16X3: D0 chunk ping-pong at 0 / 128, D1 per-tile double buffer at 256 / 384.
   //                F16X1: per-tile accumulator double buffer at 0 / 256.
+  // Dependent tcgen05.mma on one accumulator issue only every ~207 cycles (measured), longer than a 128 x N x 16
+  // MMA takes, so long-K launches (P.split) trade the per-tile double buffer for independent accumulate chains:
+  //   F16X3 split: D0 ping-pong at 0 / 128, D1a (Ahi*Blo) at 256, D1b (Alo*Bhi) at 384  -> three chains
+  //   F16X1 split: even K steps at 0, odd K steps at 256                                -> two chains
   constexpr uint32_t kAccStride = three ? 128u : 256u;
   constexpr uint32_t kD1Base = 256u;
+  const bool split = P.split != 0;
+  const int TB = split ? 1 : 2;  // per-tile accumulator buffers
 
   // Register re-balancing between the warp groups (512 threads x 128 = the whole register file):
-  // 128 * (80 + 192 + 192 + 48) = 65536.
+  // 128 * (72 + 192 + 192 + 56) = 65536.
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
   } else if (warp < 12) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   }
 
   if (warp < 4) {
+   if (!PATCH) {
     // ------------------------------------------------------------------ gather (im2col) producers
     const int t = threadIdx.x;
     const int j = t & 7;        // 16-byte chunk of the 128-byte K row
@@ -596,6 +698,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
     cp_async_wait<0>();
     fence_proxy_async();
     for (; gpub < g; ++gpub) mbar_arrive(smem_u32(&full_bar[gpub % S]));
+   }
   } else if (warp < 12) {
     // ------------------------------------------------------------------ drain D0 chunks + epilogue
     const int q = warp & 3;            // TMEM lane quarter this warp may access
@@ -605,15 +708,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
     const int nch_tile = BN / 16;
     const int ch_begin = half == 0 ? 0 : (nch_tile + 1) / 2;
     const int ch_end = half == 0 ? (nch_tile + 1) / 2 : nch_tile;
+    constexpr int NR = three ? 4 : 2;         // 16-byte registers per residual chunk
+    constexpr int KCH = three ? MAXCH : 4;    // column chunks handled per epilogue pass (unrolled)
     float total[three ? MAXCH * 16 : 1];
     uint32_t r0[16], r1[16];
     int gc = 0;  // D0 chunks seen so far (all tiles)
     int jt = 0;  // tiles processed by this CTA
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++jt) {
-      const int m0 = (tile / n_tiles) * kTileM;
       const int n0 = (tile % n_tiles) * BN;
-      const int tb = jt & 1;
-      const int64_t opix = out_pixel_of_row(d, m0 + row, P.m_total);
+      const int tb = split ? 0 : (jt & 1);
+      const int64_t opix = PATCH ? out_pixel_of_patch_row(P, tile / n_tiles, row)
+                                 : out_pixel_of_row(d, (tile / n_tiles) * kTileM + row, P.m_total);
+      if (PATCH && d.mode != CRDR_EPI_NONE) {
+        // the epilogue operands of the NEXT tile start their trip to L2 one tile time ahead (gather mode does
+        // this from the producer warps); the very first tile prefetches for itself as well
+        if (jt == 0) prefetch_epilogue_operands(d, opix, n0 + ch_begin * 16, n0 + ch_end * 16);
+        const int nxt = tile + (int)gridDim.x;
+        if (nxt < num_tiles)
+          prefetch_epilogue_operands(d, out_pixel_of_patch_row(P, nxt / n_tiles, row), (nxt % n_tiles) * BN + ch_begin * 16,
+                                     (nxt % n_tiles) * BN + ch_end * 16);
+      }
+      // request the residual operands of the first pass now: their latency overlaps the tile's main loop / drain
+      uint4 rres[KCH][NR];
+#pragma unroll
+      for (int c = 0; c < KCH; ++c)
+        if (opix >= 0 && ch_begin + c < ch_end) epi_load_res<NR>(P, opix, n0 + (ch_begin + c) * 16, rres[c]);
       if (three) {
         for (int ch = 0; ch < nchunks; ++ch, ++gc) {
           const int b = gc & 1;
@@ -634,39 +753,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
           mbar_arrive(smem_u32(&d0_empty_bar[b]));
         }
       } else {
-        mbar_wait(smem_u32(&acc_full_bar[tb]), (uint32_t)(jt >> 1) & 1u, P.status);
+        mbar_wait(smem_u32(&acc_full_bar[tb]), (uint32_t)(jt / TB) & 1u, P.status);
         tc_fence_after();
       }
-      // epilogue over this warp's column chunks; loads of the next chunk are issued before finishing the current
-      EpiRaw raw[2];
-      if (opix >= 0 && ch_begin < ch_end) epi_load(P, opix, n0 + ch_begin * 16, raw[0]);
-      if (three) {
+      // epilogue over this warp's column chunks in passes of KCH (F16X3: one pass)
+      uint4 rtrunk[NR];
+      for (int cb0 = ch_begin; cb0 < ch_end; cb0 += KCH) {
+        if (cb0 != ch_begin) {
 #pragma unroll
-        for (int c = 0; c < MAXCH; ++c) {
-          const int chn = ch_begin + c;
+          for (int c = 0; c < KCH; ++c)
+            if (opix >= 0 && cb0 + c < ch_end) epi_load_res<NR>(P, opix, n0 + (cb0 + c) * 16, rres[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < KCH; ++c) {
+          const int chn = cb0 + c;
           if (chn < ch_end) {
-            tmem_ld16_issue(lane_addr + kD1Base + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r1);
-            if (opix >= 0 && chn + 1 < ch_end) epi_load(P, opix, n0 + (chn + 1) * 16, raw[(c + 1) & 1]);
+            // second chain of a split launch lives one accumulator stride further (D1b / odd K steps)
+            if (three) tmem_ld16_issue(lane_addr + kD1Base + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r1);
+            else tmem_ld16_issue(lane_addr + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r0);
+            if (split) tmem_ld16_issue(lane_addr + (three ? kD1Base : 0u) + kAccStride + (uint32_t)chn * 16u, three ? r0 : r1);
+            if (opix >= 0) epi_load_trunk<NR>(P, opix, n0 + chn * 16, rtrunk);
             tmem_wait_ld();
             float acc[16];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) acc[e] = fmaf(__uint_as_float(r1[e]), kLoInv, total[c * 16 + e]);
-            if (opix >= 0) epi_finish(P, opix, n0 + chn * 16, acc, raw[c & 1], s_par);
-          }
-        }
-      } else {
-        for (int chn = ch_begin; chn < ch_end; chn += 2) {
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int cc = chn + u;
-            if (cc < ch_end) {
-              tmem_ld16_issue(lane_addr + (uint32_t)tb * kAccStride + (uint32_t)cc * 16u, r0);
-              if (opix >= 0 && cc + 1 < ch_end) epi_load(P, opix, n0 + (cc + 1) * 16, raw[(u + 1) & 1]);
-              tmem_wait_ld();
-              float acc[16];
-#pragma unroll
-              for (int e = 0; e < 16; ++e) acc[e] = __uint_as_float(r0[e]);
-              if (opix >= 0) epi_finish(P, opix, n0 + cc * 16, acc, raw[u], s_par);
+            for (int e = 0; e < 16; ++e) {
+              if (three) {
+                const float cross = split ? __uint_as_float(r1[e]) + __uint_as_float(r0[e]) : __uint_as_float(r1[e]);
+                acc[e] = fmaf(cross, kLoInv, total[(three ? c : 0) * 16 + e]);
+              } else {
+                acc[e] = split ? __uint_as_float(r0[e]) + __uint_as_float(r1[e]) : __uint_as_float(r0[e]);
+              }
+            }
+            if (opix >= 0) {
+              if (P.fast_epi) epi_finish<NR>(P, opix, n0 + chn * 16, acc, rres[c], rtrunk, s_par);
+              else epi_finish_generic(&P, opix, n0 + chn * 16, acc, s_par);
             }
           }
         }
@@ -676,7 +796,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
     }
   } else if (warp == 12) {
     // ------------------------------------------------------------------ weight tiles by TMA
-    if (lane == 0 && P.use_tma) {
+    if (lane == 0 && (P.use_tma || PATCH)) {
       int g = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n0 = (tile % n_tiles) * BN;
@@ -684,23 +804,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
           const int s = g % S;
           mbar_wait(smem_u32(&empty_bar[s]), ((uint32_t)(g / S) & 1u) ^ 1u, P.status);
           const uint32_t bar = smem_u32(&full_bar[s]);
-          const uint32_t bst = smem_base + (uint32_t)s * stage_bytes + (uint32_t)nplanes * kAPlaneBytes;
+          const uint32_t bst = smem_base + (uint32_t)s * stage_bytes + (uint32_t)nplanes * a_bytes;
           mbar_arrive_expect_tx(bar, (uint32_t)nplanes * b_bytes);
           tma_load_2d(bst, &P.tm_hi, kb * kKBlk, n0, bar);
           if (three) tma_load_2d(bst + b_bytes, &P.tm_lo, kb * kKBlk, n0, bar);
         }
       }
     }
+  } else if (warp == 14) {
+    // ------------------------------------------------------------------ PATCH: halo patches by TMA (one thread)
+    if (PATCH && lane == 0) {
+      int gp = 0;  // patches issued so far (all tiles)
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int n, h0, w0;
+        patch_tile_origin(P, tile / n_tiles, n, h0, w0);
+        for (int cb = 0; cb < P.ncb; ++cb, ++gp) {
+          const int pb = gp % P.patch_stages;
+          mbar_wait(smem_u32(&patch_empty_bar[pb]), ((uint32_t)(gp / P.patch_stages) & 1u) ^ 1u, P.status);
+          const uint32_t bar = smem_u32(&patch_full_bar[pb]);
+          const uint32_t dst = smem_patch + (uint32_t)pb * patch_stage_bytes;
+          mbar_arrive_expect_tx(bar, (uint32_t)nplanes * patch_plane_bytes);
+          tma_load_4d(dst, &P.tm_in_hi, P.cb_c0[cb], w0 + P.dw_min, h0 + P.dh_min, n, bar);
+          if (three) tma_load_4d(dst + patch_plane_bytes, &P.tm_in_lo, P.cb_c0[cb], w0 + P.dw_min, h0 + P.dh_min, n, bar);
+        }
+      }
+    }
   } else if (warp == 13) {
-    // ------------------------------------------------------------------ MMA issue (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issue (whole warp converged, one lane issues)
+    {
       const uint32_t idesc = umma_idesc_f16((uint32_t)BN);
-      int g = 0, gc = 0, jt = 0;
+      int g = 0, gc = 0, jt = 0, gp = 0;
+      const int ntaps = d.ntaps;
+      const bool tr = P.trace && blockIdx.x == 0 && lane == 0;
+      long long t_full = 0, t_d0 = 0, t_acc = 0, t_patch = 0, t_all0 = tr ? clock64() : 0, t0 = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++jt) {
-        const int tb = jt & 1;
-        if (jt >= 2) {
-          // the epilogue of tile jt-2 must have consumed this per-tile accumulator buffer
-          mbar_wait(smem_u32(&acc_empty_bar[tb]), (uint32_t)((jt - 2) >> 1) & 1u, P.status);
+        const int tb = split ? 0 : (jt & 1);
+        if (jt >= TB) {
+          // the epilogue of tile jt-TB must have consumed this per-tile accumulator buffer
+          if (tr) t0 = clock64();
+          mbar_wait(smem_u32(&acc_empty_bar[tb]), (uint32_t)((jt - TB) / TB) & 1u, P.status);
+          if (tr) t_acc += clock64() - t0;
           tc_fence_after();
         }
         const uint32_t d1 = tmem_base + kD1Base + (uint32_t)tb * kAccStride;
@@ -711,32 +854,74 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
           const int b = gc & 1;
           if (three && chunk_first && gc >= 2) {
             // the drain warps must have emptied this D0 buffer (chunk gc-2) before it is overwritten
+            if (tr) t0 = clock64();
             mbar_wait(smem_u32(&d0_empty_bar[b]), (uint32_t)((gc - 2) >> 1) & 1u, P.status);
+            if (tr) t_d0 += clock64() - t0;
             tc_fence_after();
           }
+          uint64_t a_hi, a_lo;
+          int pb = 0;
+          if (PATCH) {
+            // K block kb = (channel block, tap): the A operand is the patch shifted by the tap offset
+            const int tap = kb % ntaps;
+            pb = gp % P.patch_stages;
+            if (tap == 0) {
+              if (tr) t0 = clock64();
+              mbar_wait(smem_u32(&patch_full_bar[pb]), (uint32_t)(gp / P.patch_stages) & 1u, P.status);
+              if (tr) t_patch += clock64() - t0;
+              tc_fence_after();
+            }
+            const uint32_t prow = (uint32_t)((s_dh[tap] - P.dh_min) * P.pw + (s_dw[tap] - P.dw_min));
+            const uint32_t pa = smem_patch + (uint32_t)pb * patch_stage_bytes + prow * 128u;
+            a_hi = umma_desc_sw128_rows(pa, (uint32_t)P.pw * 128u);
+            a_lo = umma_desc_sw128_rows(pa + patch_plane_bytes, (uint32_t)P.pw * 128u);
+          }
+          if (tr) t0 = clock64();
           mbar_wait(smem_u32(&full_bar[s]), (uint32_t)(g / S) & 1u, P.status);
+          if (tr) t_full += clock64() - t0;
           tc_fence_after();
           const uint32_t d0 = tmem_base + (uint32_t)(three ? b : tb) * kAccStride;
           const uint32_t stage = smem_base + (uint32_t)s * stage_bytes;
-          const uint64_t a_hi = umma_desc_sw128(stage);
-          const uint64_t a_lo = umma_desc_sw128(stage + kAPlaneBytes);
-          const uint64_t b_hi = umma_desc_sw128(stage + (uint32_t)nplanes * kAPlaneBytes);
-          const uint64_t b_lo = umma_desc_sw128(stage + (uint32_t)nplanes * kAPlaneBytes + b_bytes);
+          if (!PATCH) {
+            a_hi = umma_desc_sw128(stage);
+            a_lo = umma_desc_sw128(stage + kAPlaneBytes);
+          }
+          const uint64_t b_hi = umma_desc_sw128(stage + (uint32_t)nplanes * a_bytes);
+          const uint64_t b_lo = umma_desc_sw128(stage + (uint32_t)nplanes * a_bytes + b_bytes);
+          __syncwarp();
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kKBlk / 16; ++k) {
-            const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 descriptor units
-            umma_f16(d0, a_hi + adv, b_hi + adv, idesc, (chunk_first && k == 0) ? 0u : 1u);
-            if (three) {
-              umma_f16(d1, a_hi + adv, b_lo + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              umma_f16(d1, a_lo + adv, b_hi + adv, idesc, 1u);
+            for (int k = 0; k < kKBlk / 16; ++k) {
+              const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 descriptor units
+              if (three) {
+                umma_f16(d0, a_hi + adv, b_hi + adv, idesc, (chunk_first && k == 0) ? 0u : 1u);
+                umma_f16(d1, a_hi + adv, b_lo + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                // split: the second cross term accumulates in its own chain (D1b)
+                umma_f16(split ? d1 + kAccStride : d1, a_lo + adv, b_hi + adv, idesc, (split && kb == 0 && k == 0) ? 0u : 1u);
+              } else if (split) {
+                // even / odd K steps alternate between two accumulators
+                umma_f16(d0 + (uint32_t)(k & 1) * kAccStride, a_hi + adv, b_hi + adv, idesc, (kb == 0 && k < 2) ? 0u : 1u);
+              } else {
+                umma_f16(d0, a_hi + adv, b_hi + adv, idesc, (chunk_first && k == 0) ? 0u : 1u);
+              }
+            }
+            umma_commit(smem_u32(&empty_bar[s]));
+            if (PATCH && (kb % ntaps) == ntaps - 1) umma_commit(smem_u32(&patch_empty_bar[pb]));  // all taps of the block issued
+            if (chunk_last) {
+              if (three) umma_commit(smem_u32(&d0_full_bar[b]));
+              else umma_commit(smem_u32(&acc_full_bar[tb]));
             }
           }
-          umma_commit(smem_u32(&empty_bar[s]));
-          if (chunk_last) {
-            if (three) { umma_commit(smem_u32(&d0_full_bar[b])); ++gc; }
-            else umma_commit(smem_u32(&acc_full_bar[tb]));
-          }
+          __syncwarp();
+          if (PATCH && (kb % ntaps) == ntaps - 1) ++gp;
+          if (three && chunk_last) ++gc;
         }
+      }
+      if (tr) {  // bring-up counters (cycles): total, wait full, wait d0_empty, wait acc_empty, wait patch, k blocks
+        unsigned long long* c = reinterpret_cast<unsigned long long*>(P.status + 16);
+        c[0] = (unsigned long long)(clock64() - t_all0);
+        c[1] = (unsigned long long)t_full; c[2] = (unsigned long long)t_d0; c[3] = (unsigned long long)t_acc;
+        c[4] = (unsigned long long)t_patch; c[5] = (unsigned long long)g;
       }
     }
   }
@@ -773,7 +958,15 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const __grid_constant__ 
     const int64_t pbase = ((int64_t)(n * d.hin + ih) * d.win + iw) * d.in.cs + d.in.coff;
     for (int c = 0; c < P.cin; ++c) {
       const int chan = (c < d.seg0_len) ? d.seg0_off + c : d.seg1_off + (c - d.seg0_len);
-      const int k = tp * P.cin + c;
+      int k;
+      if (d.k_order == 0) {
+        k = tp * P.cin + c;
+      } else {
+        const int in0 = c < d.seg0_len;
+        const int cs_ = in0 ? c : c - d.seg0_len;
+        const int cb = (in0 ? 0 : (d.seg0_len + 63) / 64) + cs_ / 64;
+        k = (cb * d.ntaps + tp) * 64 + (cs_ & 63);
+      }
       const float ah = __half2float(in_hi[pbase + chan]);
       const float bhv = __half2float(w_hi[k]);
       acc0 = fmaf(ah, bhv, acc0);
@@ -886,6 +1079,53 @@ static int weight_tensor_map(const void* ptr, int k_pad, int rows, int box_rows,
   return CRDR_OK;
 }
 
+struct InKey {
+  const void* ptr;
+  int32_t cs, w, h, n, pw, ph, dev;
+  bool operator==(const InKey& o) const {
+    return ptr == o.ptr && cs == o.cs && w == o.w && h == o.h && n == o.n && pw == o.pw && ph == o.ph && dev == o.dev;
+  }
+};
+struct InKeyHash {
+  size_t operator()(const InKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    const int32_t v[7] = {k.cs, k.w, k.h, k.n, k.pw, k.ph, k.dev};
+    for (int i = 0; i < 7; ++i) h = h * 1000003u ^ (size_t)v[i];
+    return h;
+  }
+};
+static std::unordered_map<InKey, CUtensorMap, InKeyHash> g_in_cache;
+
+// 4-D (C, W, H, N) tensor map over NHWC fp16 planes with a (64, pw, ph, 1) box, zero fill out of bounds.
+static int input_tensor_map(const void* ptr, int cs, int w, int h, int n, int pw, int ph, CUtensorMap* out) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  InKey key{ptr, cs, w, h, n, pw, ph, dev};
+  {
+    std::lock_guard<std::mutex> lk(g_tm_mutex);
+    auto it = g_in_cache.find(key);
+    if (it != g_in_cache.end()) { *out = it->second; return CRDR_OK; }
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return CRDR_ERR_CUDA; }
+  cuuint64_t gdim[4] = {(cuuint64_t)cs, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t gstride[3] = {(cuuint64_t)cs * 2, (cuuint64_t)w * cs * 2, (cuuint64_t)h * w * cs * 2};
+  cuuint32_t box[4] = {64u, (cuuint32_t)pw, (cuuint32_t)ph, 1u};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap tm;
+  CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(input) failed (CUresult %d)", (int)r); return CRDR_ERR_CUDA; }
+  {
+    std::lock_guard<std::mutex> lk(g_tm_mutex);
+    if (g_in_cache.size() > 4096) g_in_cache.clear();
+    g_in_cache[key] = tm;
+  }
+  *out = tm;
+  return CRDR_OK;
+}
+
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 static bool planes_vec_ok(const crdr_planes& p) {
   return p.hi && aligned16(p.hi) && (!p.lo || aligned16(p.lo)) && p.cs % 8 == 0 && p.coff % 8 == 0;
@@ -902,7 +1142,23 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     set_error("conv2d: input channel ranges / strides must be multiples of 8");
     return CRDR_ERR_MISALIGNED;
   }
-  if (d.k_pad % kKBlk || d.k_pad < d.ntaps * cin || d.tile_n % 16 || d.tile_n < 16 || d.tile_n > 256 ||
+  const bool patch = d.k_order == 1;
+  int ncb = 0, cb_c0[kMaxCBlocks];
+  if (patch) {
+    for (int sgi = 0; sgi < 2; ++sgi) {
+      const int off = sgi ? d.seg1_off : d.seg0_off, len = sgi ? d.seg1_len : d.seg0_len;
+      for (int b = 0; b * 64 < len; ++b) {
+        if (ncb >= kMaxCBlocks) { set_error("conv2d: more than %d channel blocks", kMaxCBlocks); return CRDR_ERR_BAD_SHAPE; }
+        cb_c0[ncb++] = d.in.coff + off + 64 * b;
+      }
+    }
+    if (d.in_stride != 1 || d.k_pad < ncb * d.ntaps * 64) {
+      set_error("conv2d: k_order=1 needs in_stride == 1 and k_pad >= blocks*taps*64 (in_stride=%d k_pad=%d need %d)",
+                d.in_stride, d.k_pad, ncb * d.ntaps * 64);
+      return CRDR_ERR_BAD_SHAPE;
+    }
+  }
+  if (d.k_pad % kKBlk || (!patch && d.k_pad < d.ntaps * cin) || d.tile_n % 16 || d.tile_n < 16 || d.tile_n > 256 ||
       d.cout_pad % d.tile_n || d.cout > d.cout_pad) {
     set_error("conv2d: bad packed-weight geometry (k_pad=%d need>=%d, tile_n=%d, cout=%d, cout_pad=%d)", d.k_pad,
               d.ntaps * cin, d.tile_n, d.cout, d.cout_pad);
@@ -937,7 +1193,7 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
   P.m_total = (int32_t)m_total;
   P.cin = cin;
   P.k_real = d.ntaps * cin;
-  P.nkb = (P.k_real + kKBlk - 1) / kKBlk;
+  P.nkb = patch ? ncb * d.ntaps : (P.k_real + kKBlk - 1) / kKBlk;
   P.nplanes = three ? 2 : 1;
   P.status = device_status_word();
   if (!P.status) return CRDR_ERR_CUDA;
@@ -946,9 +1202,28 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
   P.vec_res_planes = d.res.hi ? planes_vec_ok(d.res) : 0;
   P.vec_res_f32 = d.res_f32 && aligned16(d.res_f32) && d.res_f32_cs % 4 == 0 && d.res_f32_coff % 4 == 0;
   P.vec_trunk = d.trunk.hi ? planes_vec_ok(d.trunk) : 0;
+  if (!three) {
+    P.d.res.lo = nullptr;    // F16X1 tensors are single-term: the epilogue reads the hi plane only
+    P.d.trunk.lo = nullptr;
+    P.vec_res_f32 = 0;
+  }
+  P.fast_epi = d.cout % 16 == 0 && (!d.out.hi || P.vec_planes_out) && (!d.out_f32 || P.vec_f32_out) &&
+               (d.mode == CRDR_EPI_NONE || (d.res_f32 ? (three && P.vec_res_f32) : P.vec_res_planes)) &&
+               (d.mode != CRDR_EPI_GATE || P.vec_trunk);
   P.has_bias = d.bias != nullptr;
   P.has_add = d.add_vec != nullptr;
   P.has_affine = d.scale != nullptr || d.shift != nullptr;
+  {
+    static int chunk_env = -1;  // tuning knob: K blocks per D0 accumulate chain
+    if (chunk_env < 0) { const char* e = getenv("CRDR_CHUNK_KB"); chunk_env = e ? atoi(e) : kChunkKB; if (chunk_env < 1) chunk_env = 1; }
+    P.chunk_kb = chunk_env;
+    static int trace_env = -1;
+    if (trace_env < 0) { const char* e = getenv("CRDR_CONV_TRACE"); trace_env = e ? atoi(e) : 0; }
+    P.trace = trace_env;
+    static int split_env = -1;  // -1 auto, 0 never, 1 always (tuning knob)
+    if (split_env == -1) { const char* e = getenv("CRDR_CONV_SPLIT"); split_env = e ? atoi(e) : 0; }
+    P.split = split_env == 2 ? -1 : split_env;
+  }
 
   if (d.engine == CRDR_ENGINE_SIMT) {
     const int64_t total = m_total * d.cout;
@@ -966,29 +1241,40 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     set_error("conv2d: F16X3 needs tile_n <= 128 (D0 ping-pong and double-buffered D1 share 512 TMEM columns)");
     return CRDR_ERR_BAD_SHAPE;
   }
-  // template instance: register-total chunks per drain warp (F16X3) or 0 (F16X1)
+  // template instance: register-total chunks per drain warp (F16X3) or 0 (F16X1); PATCH or gather producers
+  const bool use_patch = patch && d.engine != CRDR_ENGINE_TCGEN05_NOTMA;
+  if (patch && !use_patch) {
+    set_error("conv2d: k_order=1 weights need the TMA engine");
+    return CRDR_ERR_BAD_SHAPE;
+  }
   const int maxch = three ? ((d.tile_n / 16 + 1) / 2) : 0;
   typedef void (*KernelFn)(const ConvKParams);
   KernelFn fn = nullptr;
-  switch (maxch) {
-    case 0: fn = conv_tcgen05_kernel<0>; break;
-    case 1: fn = conv_tcgen05_kernel<1>; break;
-    case 2: fn = conv_tcgen05_kernel<2>; break;
-    case 3: fn = conv_tcgen05_kernel<3>; break;
-    default: fn = conv_tcgen05_kernel<4>; break;
+  switch (maxch * 2 + (use_patch ? 1 : 0)) {
+    case 0: fn = conv_tcgen05_kernel<0, false>; break;
+    case 1: fn = conv_tcgen05_kernel<0, true>; break;
+    case 2: fn = conv_tcgen05_kernel<1, false>; break;
+    case 3: fn = conv_tcgen05_kernel<1, true>; break;
+    case 4: fn = conv_tcgen05_kernel<2, false>; break;
+    case 5: fn = conv_tcgen05_kernel<2, true>; break;
+    case 6: fn = conv_tcgen05_kernel<3, false>; break;
+    case 7: fn = conv_tcgen05_kernel<3, true>; break;
+    case 8: fn = conv_tcgen05_kernel<4, false>; break;
+    default: fn = conv_tcgen05_kernel<4, true>; break;
   }
+  const int variant = maxch * 2 + (use_patch ? 1 : 0);
   static std::mutex attr_mutex;
-  static bool attr_done[5] = {false, false, false, false, false};
+  static bool attr_done[10] = {false, false, false, false, false, false, false, false, false, false};
   static int num_sms = 0;
   {
     std::lock_guard<std::mutex> lk(attr_mutex);
-    if (!attr_done[maxch]) {
+    if (!attr_done[variant]) {
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemMax);
       if (e != cudaSuccess) {
         set_error("conv2d: cannot opt in to large shared memory: %s", cudaGetErrorString(e));
         return CRDR_ERR_UNSUPPORTED_ARCH;
       }
-      attr_done[maxch] = true;
+      attr_done[variant] = true;
     }
     if (num_sms == 0) {
       int dev = 0;
@@ -997,12 +1283,47 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
       if (num_sms <= 0) num_sms = 148;
     }
   }
-  const uint32_t stage_bytes = (uint32_t)P.nplanes * (kAPlaneBytes + (uint32_t)d.tile_n * 128u);
-  int stages = (int)((kDynSmemMax - 1024) / stage_bytes);
+  uint32_t patch_total = 0;
+  if (use_patch) {
+    int dh_min = 127, dh_max = -127, dw_min = 127, dw_max = -127;
+    for (int t = 0; t < d.ntaps; ++t) {
+      dh_min = d.dh[t] < dh_min ? d.dh[t] : dh_min; dh_max = d.dh[t] > dh_max ? d.dh[t] : dh_max;
+      dw_min = d.dw[t] < dw_min ? d.dw[t] : dw_min; dw_max = d.dw[t] > dw_max ? d.dw[t] : dw_max;
+    }
+    P.dh_min = dh_min; P.dw_min = dw_min;
+    P.ph = kPatchTH + dh_max - dh_min;
+    P.pw = kPatchTW + dw_max - dw_min;
+    P.ncb = ncb;
+    for (int i = 0; i < ncb; ++i) P.cb_c0[i] = cb_c0[i];
+    P.tiles_h = (d.hb + kPatchTH - 1) / kPatchTH;
+    P.tiles_w = (d.wb + kPatchTW - 1) / kPatchTW;
+    if (P.ph > 64 || P.pw > 64 || d.in.cs < 64) {
+      set_error("conv2d: patch engine needs tap spans <= 48 and >= 64 stored channels (ph=%d pw=%d cs=%d)", P.ph, P.pw, d.in.cs);
+      return CRDR_ERR_BAD_SHAPE;
+    }
+    const uint32_t plane = (uint32_t)(P.ph * P.pw) * 128u;
+    const uint32_t pstage = (plane * (uint32_t)P.nplanes + 1023u) & ~1023u;
+    const uint32_t bstage = (uint32_t)P.nplanes * (uint32_t)d.tile_n * 128u;
+    // two patch buffers when at least three weight stages still fit, else one
+    P.patch_stages = (2 * pstage + 3 * bstage + 1024 <= kDynSmemMax && ncb > 1) ? 2 : 1;
+    patch_total = (uint32_t)P.patch_stages * pstage;
+    int rc = input_tensor_map(d.in.hi, d.in.cs, d.win, d.hin, d.n, P.pw, P.ph, &P.tm_in_hi);
+    if (rc) return rc;
+    if (three) {
+      rc = input_tensor_map(d.in.lo, d.in.cs, d.win, d.hin, d.n, P.pw, P.ph, &P.tm_in_lo);
+      if (rc) return rc;
+    }
+  }
+  const uint32_t stage_bytes = (uint32_t)P.nplanes * ((use_patch ? 0u : kAPlaneBytes) + (uint32_t)d.tile_n * 128u);
+  if (patch_total + 2 * stage_bytes + 1024 > kDynSmemMax) {
+    set_error("conv2d: tile_n=%d does not leave two pipeline stages (patch %u B)", d.tile_n, patch_total);
+    return CRDR_ERR_BAD_SHAPE;
+  }
+  int stages = (int)((kDynSmemMax - 1024 - patch_total) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) { set_error("conv2d: tile_n=%d leaves fewer than 2 pipeline stages", d.tile_n); return CRDR_ERR_BAD_SHAPE; }
   P.stages = stages;
   P.tmem_cols = 512;
+  if (P.split < 0) P.split = P.nkb >= 16;  // long accumulate chains: independent accumulators beat epilogue overlap
   P.use_tma = d.engine == CRDR_ENGINE_TCGEN05;
   if (P.use_tma) {
     int rc = weight_tensor_map(d.w_hi, d.k_pad, d.cout_pad, d.tile_n, &P.tm_hi);
@@ -1012,8 +1333,9 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
       if (rc) return rc;
     }
   }
-  const uint32_t smem = (uint32_t)stages * stage_bytes + 1024;
-  const int64_t num_tiles = ((m_total + kTileM - 1) / kTileM) * (d.cout_pad / d.tile_n);
+  const uint32_t smem = patch_total + (uint32_t)stages * stage_bytes + 1024;
+  const int64_t m_tiles = use_patch ? (int64_t)d.n * P.tiles_h * P.tiles_w : (m_total + kTileM - 1) / kTileM;
+  const int64_t num_tiles = m_tiles * (d.cout_pad / d.tile_n);
   const unsigned grid = (unsigned)(num_tiles < num_sms ? num_tiles : num_sms);  // persistent: one CTA per SM
   fn<<<grid, kThreads, smem, stream>>>(P);
   return check_launch("conv_tcgen05_kernel");

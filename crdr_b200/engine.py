@@ -5,6 +5,7 @@ torch, the arithmetic happens in ``libcrdr_sm100.so``.
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -102,7 +103,7 @@ class ConvOp:
     """
 
     def __init__(self, weight, bias, transposed=False, stride=1, padding=0, output_padding=0, cin_pad=None,
-                 device="cuda"):
+                 device="cuda", seg_lens=None, algo=None):
         w = weight.detach().to(torch.float32).cpu()
         self.transposed, self.stride, self.padding, self.output_padding = transposed, stride, padding, output_padding
         if transposed:
@@ -115,6 +116,15 @@ class ConvOp:
         self.cout_pad = round_up(cout, 16)
         self.bias = None if bias is None else bias.detach().to(device=device, dtype=torch.float32).contiguous()
         self.device = device
+        # channel ranges the input is read from at launch (ChARM: hyper ++ slices); decides the 64-channel blocking
+        self.seg_lens = list(seg_lens) if seg_lens else [self.cin]
+        assert sum(self.seg_lens) == self.cin
+        # "patch": halo-patch engine (input stride 1, >= 64 channels); "gather": per-tap im2col gather (any stride)
+        in_stride = 1 if transposed else stride
+        default = "patch" if (in_stride == 1 and min(self.seg_lens) >= 8 and self.cin >= 64) else "gather"
+        self.algo = algo or os.environ.get("CRDR_CONV_ALGO") or default
+        if in_stride != 1 or self.cin < 64:
+            self.algo = "gather"
         self.phases = []
         s, p = stride, padding
         phase_list = [(0, 0)] if not transposed else [(a, b) for a in range(s) for b in range(s)]
@@ -134,16 +144,35 @@ class ConvOp:
                         blk = torch.nn.functional.pad(blk, (0, self.cin - cin))
                     cols.append(blk)
             assert 0 < len(taps) <= nv.MAX_TAPS
-            k_real = len(taps) * self.cin
-            k_pad = round_up(k_real, 64)
-            w2d = torch.zeros((self.cout_pad, k_pad), dtype=torch.float32)
-            w2d[:cout, :k_real] = torch.cat(cols, dim=1)
             phs = Phase()
             phs.dh = [t[0] for t in taps]
             phs.dw = [t[1] for t in taps]
+            phs.out_ph, phs.out_pw = ph, pw
+            w2d = self._pack(cols)
+            phs.k_pad = w2d.shape[1]
             phs.w_hi, phs.w_lo = split_weight(w2d, device)
-            phs.k_pad, phs.out_ph, phs.out_pw = k_pad, ph, pw
             self.phases.append(phs)
+
+    def _pack(self, cols):
+        """cols: per-tap [Cout, Cin] fp32 blocks -> [cout_pad, k_pad] in the K order of the selected engine."""
+        ntaps = len(cols)
+        if self.algo == "gather":
+            k_real = ntaps * self.cin
+            w2d = torch.zeros((self.cout_pad, round_up(k_real, 64)), dtype=torch.float32)
+            w2d[:self.cout, :k_real] = torch.cat(cols, dim=1)
+            return w2d
+        blocks = []  # (first logical channel, count) of every 64-channel block, per input range
+        start = 0
+        for ln in self.seg_lens:
+            for b in range(0, ln, 64):
+                blocks.append((start + b, min(64, ln - b)))
+            start += ln
+        w2d = torch.zeros((self.cout_pad, len(blocks) * ntaps * 64), dtype=torch.float32)
+        for cb, (c0, cnt) in enumerate(blocks):
+            for t in range(ntaps):
+                k0 = (cb * ntaps + t) * 64
+                w2d[:self.cout, k0:k0 + cnt] = cols[t][:, c0:c0 + cnt]
+        return w2d
 
     def out_hw(self, h, w):
         if self.transposed:
@@ -160,7 +189,7 @@ class ConvOp:
         hout, wout = self.out_hw(x.h, x.w)
         if segs is None:
             segs = [(0, self.cin)]
-        assert sum(l for _, l in segs) == self.cin, (segs, self.cin)
+        assert [l for _, l in segs] == self.seg_lens, (segs, self.seg_lens)
         if two_out is None:
             two_out = precision == nv.PREC_F16X3
         if out is None and want_planes:
@@ -189,6 +218,9 @@ class ConvOp:
         d.scale = scale.data_ptr() if scale is not None else None
         d.shift = shift.data_ptr() if shift is not None else None
         d.precision, d.engine = precision, engine
+        d.k_order = 1 if self.algo == "patch" else 0
+        if self.algo == "patch" and engine == nv.ENGINE_TCGEN05_NOTMA:
+            d.engine = nv.ENGINE_TCGEN05  # the patch engine has no cp.async variant
         st = nv.stream_handle()
         L = nv.lib()
         for phs in self.phases:
@@ -205,7 +237,7 @@ class ConvOp:
             for i, (a, b) in enumerate(zip(phs.dh, phs.dw)):
                 d.dh[i], d.dw[i] = a, b
             d.w_hi, d.w_lo, d.k_pad = phs.w_hi.data_ptr(), phs.w_lo.data_ptr(), phs.k_pad
-            m_tiles = -(-(x.n * hb * wb) // 128)
+            m_tiles = x.n * (-(-hb // 16)) * (-(-wb // 8)) if self.algo == "patch" else -(-(x.n * hb * wb) // 128)
             d.tile_n = tile_n or pick_tile_n(self.cout_pad, m_tiles, precision == nv.PREC_F16X3)
             if PROFILE_ON[0]:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

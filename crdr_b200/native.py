@@ -32,6 +32,7 @@ class ConvDesc(C.Structure):
         ("w_hi", C.c_void_p), ("w_lo", C.c_void_p),
         ("k_pad", C.c_int32), ("cout_pad", C.c_int32), ("cout", C.c_int32),
         ("tile_n", C.c_int32),
+        ("k_order", C.c_int32),
         ("hout", C.c_int32), ("wout", C.c_int32), ("out_stride", C.c_int32), ("out_ph", C.c_int32), ("out_pw", C.c_int32),
         ("out", Planes),
         ("out_f32", C.c_void_p), ("out_f32_cs", C.c_int32), ("out_f32_coff", C.c_int32),

@@ -96,6 +96,10 @@ typedef struct {
   const void* w_lo;
   int32_t k_pad, cout_pad, cout;
   int32_t tile_n; /* N tile (multiple of 16, <= 256, divides cout_pad) */
+  /* K order of the packed weights.  0: k = t*Cin + ci (operands gathered per tap; any stride).
+   * 1: 64-channel blocks cb of each input range, k = (cb*ntaps + t)*64 + ci%64, zero padded -- selects the
+   *    halo-patch engine (one TMA box per channel block serves every tap); needs in_stride == 1. */
+  int32_t k_order;
   /* output */
   int32_t hout, wout, out_stride, out_ph, out_pw;
   crdr_planes out;  /* may have hi == NULL */

@@ -57,7 +57,7 @@ def test_channel_segments_and_in_place_output():
     T = Act.from_nchw(wide)
     w = (torch.randn(32, 96, 5, 5, generator=g) / 50).cuda()
     b = torch.randn(32, generator=g).cuda()
-    op = ConvOp(w, b, padding=2)
+    op = ConvOp(w, b, padding=2, seg_lens=[64, 32])
     out = Act.zeros(2, 10, 14, 64)
     op(T, segs=[(8, 64), (120, 32)], out=out, out_coff=32)
     torch.cuda.synchronize()
