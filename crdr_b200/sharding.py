@@ -1,0 +1,62 @@
+"""Image-level sharding across GPUs: images are independent units, so rank r of W simply takes items
+r, r+W, ... of the sorted list; there is no collective on the data path.  Per-image result rows are merged on
+rank 0 -- through torch.distributed when a process group exists, else through per-rank JSON files."""
+import json
+import os
+import time
+
+
+def rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def shard(items, rank, world):
+    """Round-robin shard of an (already sorted) list; every item lands on exactly one rank."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    return list(items[rank::world])
+
+
+def same_shape_batches(named_images, batch):
+    """Group consecutive (name, tensor[1,3,H,W]) pairs of identical shape into lists of at most `batch`."""
+    group = []
+    for item in named_images:
+        if group and (len(group) >= max(1, batch) or item[1].shape != group[0][1].shape):
+            yield group
+            group = []
+        group.append(item)
+    if group:
+        yield group
+
+
+def gather_rows(rows, rank, world, scratch_dir=None, timeout_s=600.0):
+    """All ranks' row lists concatenated on rank 0 (other ranks get [])."""
+    if world == 1:
+        return list(rows)
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            bucket = [None] * world if rank == 0 else None
+            dist.gather_object(rows, bucket, dst=0)
+            return [r for part in bucket for r in part] if rank == 0 else []
+    except ImportError:
+        pass
+    if scratch_dir is None:
+        raise RuntimeError("gather_rows needs a process group or a scratch directory")
+    mine = os.path.join(scratch_dir, f"_rows_rank{rank}.json")
+    with open(mine + ".tmp", "w") as f:
+        json.dump(rows, f)
+    os.replace(mine + ".tmp", mine)
+    if rank != 0:
+        return []
+    out, deadline = [], time.time() + timeout_s
+    for r in range(world):
+        path = os.path.join(scratch_dir, f"_rows_rank{r}.json")
+        while not os.path.exists(path):
+            if time.time() > deadline:
+                raise TimeoutError(f"rank {r} never delivered its rows")
+            time.sleep(0.05)
+        with open(path) as f:
+            out.extend(json.load(f))
+        os.remove(path)
+    return out

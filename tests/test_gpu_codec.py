@@ -218,3 +218,39 @@ def test_eltwise_kernels_against_torch():
     nv.check(L.crdr_gauss_dequantize(C.byref(d), st))
     assert torch.equal(yq32b, yq32)
     nv.status_check()
+
+
+def test_compress_script_end_to_end(models, tmp_path):
+    """scripts/compress.py (reference CLI) on PNG files with a saved checkpoint: .bin / .png / _bitrates.csv / json."""
+    import json
+    import subprocess
+    import pandas as pd
+    from PIL import Image
+    import fixtures
+    from crdr_b200.codec_utils import load_byte_strings
+    model, sd = models(True)
+    ckpt = tmp_path / "ckpt.pth.tar"
+    torch.save({"iter": 0, "comp_model": sd}, ckpt)
+    img_dir, out_dir = tmp_path / "imgs", tmp_path / "out"
+    img_dir.mkdir()
+    for i, (h, w) in enumerate([(96, 128), (96, 128), (70, 100)]):
+        x = fixtures.image(1, h, w, seed=20 + i)[0]
+        arr = ((x + 1) / 2 * 255).round().clamp(0, 255).byte().permute(1, 2, 0).numpy()
+        Image.fromarray(arr).save(img_dir / f"im{i}.png")
+    cmd = [sys.executable, os.path.join(ROOT, "scripts", "compress.py"), "--config_path", os.path.join(ROOT, "config", "crdr.yaml"),
+           "--model_path", str(ckpt), "--img_dir", str(img_dir), "--save_dir", str(out_dir), "-q", "1.25", "-b", "3.84",
+           "--decompress", "-d", "cuda:0", "--batch", "2"]
+    subprocess.run(cmd, check=True, timeout=600)
+    df = pd.read_csv(out_dir / "_bitrates.csv")
+    assert list(df["img_name"]) == ["im0.png", "im1.png", "im2.png"]
+    for col in ("header_bit", "z_bit", "y_bit", "real_bit", "real_bpp", "pred_z_bit", "pred_y_bit", "pred_bit", "pred_bpp", "num_pixel"):
+        assert col in df.columns
+    assert (df["header_bit"] == 48).all() and (df["real_bit"] == df["header_bit"] + df["z_bit"] + df["y_bit"] + 96).all()
+    assert abs(json.load(open(out_dir / "_avg_bitrate.json"))["avg_bpp"] - df["real_bpp"].mean()) < 1e-9
+    assert ((df["pred_bit"] - df["real_bit"]).abs() / df["real_bit"]).max() < 0.05   # coder within 5 % of the entropy estimate
+    # the written .bin decodes (fresh call) to exactly the written .png
+    strings = load_byte_strings(str(out_dir / "im2.bin"))
+    img, _, _ = model.decompress(strings, beta=3.84)
+    want = np.asarray(Image.open(out_dir / "im2.png").convert("RGB"))
+    got = ((img[0].cpu() + 1) / 2 * 255).numpy().astype(np.uint8).transpose(1, 2, 0)
+    assert got.shape == (70, 100, 3) and np.array_equal(got, want)
