@@ -34,7 +34,9 @@ constexpr int kTileM = 128;
 constexpr int kKBlk = 64;                  // fp16 elements per K block = one 128-byte swizzle row
 constexpr uint32_t kAPlaneBytes = kTileM * 128;
 constexpr int kMaxStages = 6;
-constexpr int kThreads = 512;              // warps 0-3 gather, 4-11 drain/epilogue, warp 12 TMA + TMEM alloc, warp 13 MMA, 14-15 idle
+constexpr int kThreads = 512;              // gather variant: warps 0-3 gather, 4-11 drain/epilogue, 12 TMA + TMEM alloc, 13 MMA, 14-15 idle
+constexpr int kThreadsPatch = 384;         // patch variant: warps 0-7 drain/epilogue, 8 TMA + TMEM alloc, 9 MMA, 10 halo patches, 11 idle
+                                           // setmaxnreg: 128 * (216 + 216 + 56) <= 65536
 constexpr int kChunkKB = 2;                // F16X3: K blocks per D0 accumulate chain (8 MMAs of K=16)
 constexpr uint32_t kSmemLimit = 227 * 1024;
 constexpr uint32_t kDynSmemMax = kSmemLimit - 8 * 1024;  // static smem: parameter cache (5 KB) + barriers
@@ -53,7 +55,7 @@ struct alignas(64) ConvKParams {
   int32_t cb_c0[kMaxCBlocks];
   int32_t m_total, nkb, cin, k_real, nplanes, stages, tmem_cols, use_tma;
   int32_t vec_planes_out, vec_f32_out, vec_res_planes, vec_res_f32, vec_trunk;
-  int32_t has_bias, has_add, has_affine, chunk_kb, trace, split, fast_epi;
+  int32_t has_bias, has_add, has_affine, chunk_kb, trace, split, fast_epi, res_stage_pitch;
   uint32_t* status;
 };
 
@@ -394,25 +396,27 @@ __device__ __forceinline__ void epi_finish(const ConvKParams& P, int64_t opix, i
   }
   if (d.out.hi) {
     const bool want_lo = d.out.lo != nullptr;
+    // one range check per chunk instead of one branch per element
+    float amax = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) amax = fmaxf(amax, fabsf(v[e]));
+    if (!(amax <= 65504.0f)) {  // also true for NaN
+      atomicOr(P.status, kFlagOverflow);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = fminf(fmaxf(v[e], -65504.0f), 65504.0f);
+    }
     uint32_t hw[8], lw[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      __half h0, h1, l0 = __float2half_rn(0.f), l1 = __float2half_rn(0.f);
+      const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);   // one cvt.rn.f16x2.f32
+      hw[i] = *reinterpret_cast<const uint32_t*>(&h);
       if (want_lo) {
-        split_f16(v[2 * i], h0, l0, P.status);
-        split_f16(v[2 * i + 1], h1, l1, P.status);
-      } else {
-        float x0 = v[2 * i], x1 = v[2 * i + 1];
-        if (fabsf(x0) > 65504.0f || fabsf(x1) > 65504.0f) {
-          atomicOr(P.status, kFlagOverflow);
-          x0 = fminf(fmaxf(x0, -65504.0f), 65504.0f);
-          x1 = fminf(fmaxf(x1, -65504.0f), 65504.0f);
-        }
-        h0 = __float2half_rn(x0);
-        h1 = __float2half_rn(x1);
+        const float2 hf = __half22float2(h);
+        // (x - hi) * 2^11 is exact in fp32: fma(x, 2048, -2048*hi) has a single, exact rounding
+        const __half2 l = __floats2half2_rn(fmaf(v[2 * i], kLoScale, -kLoScale * hf.x),
+                                            fmaf(v[2 * i + 1], kLoScale, -kLoScale * hf.y));
+        lw[i] = *reinterpret_cast<const uint32_t*>(&l);
       }
-      hw[i] = pack_h2(h0, h1);
-      lw[i] = pack_h2(l0, l1);
     }
     const int64_t o = opix * d.out.cs + d.out.coff + co0;
     __half* ph = (__half*)d.out.hi + o;
@@ -494,8 +498,13 @@ __device__ __forceinline__ void prefetch_epilogue_operands(const crdr_conv_desc&
 // (zero fill outside the image) and every tap's A operand is just a different start row of that patch, addressed
 // through the UMMA descriptor (group stride = patch row pitch).  L2 -> SM traffic for A drops by ~ntaps.
 template <int MAXCH, bool PATCH>
-__global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
+__global__ void __launch_bounds__(PATCH ? kThreadsPatch : kThreads, 1)
+conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
   constexpr bool three = MAXCH > 0;
+  constexpr int kEpiWarp0 = PATCH ? 0 : 4;      // first of the 8 drain / epilogue warps (a multiple of 4: TMEM lane quarters)
+  constexpr int kTmaWarp = kEpiWarp0 + 8;
+  constexpr int kMmaWarp = kEpiWarp0 + 9;
+  constexpr int kPatchWarp = kEpiWarp0 + 10;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -523,13 +532,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
   const uint32_t stage_bytes = (uint32_t)nplanes * (a_bytes + b_bytes);
   const uint32_t smem_patch = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_base = smem_patch + (PATCH ? (uint32_t)P.patch_stages * patch_stage_bytes : 0u);
+  const uint32_t smem_res = smem_base + (uint32_t)P.stages * stage_bytes;  // residual staging slots (128 rows)
   const int nkb = P.nkb;
   const int n_tiles = d.cout_pad / BN;
   const int num_tiles = (PATCH ? d.n * P.tiles_h * P.tiles_w : (P.m_total + kTileM - 1) / kTileM) * n_tiles;
   const int chunk_kb = three ? P.chunk_kb : nkb;
   const int nchunks = (nkb + chunk_kb - 1) / chunk_kb;  // D0 chunks per tile
 
-  for (int i = threadIdx.x; i < 4 * kMaxCout; i += kThreads) {
+  for (int i = threadIdx.x; i < 4 * kMaxCout; i += (int)blockDim.x) {
     const int which = i / kMaxCout, co = i % kMaxCout;
     const float* src = which == 0 ? d.bias : which == 1 ? d.add_vec : which == 2 ? d.scale : d.shift;
     s_par[i] = (src && co < d.cout) ? src[co] : (which == 2 ? 1.f : 0.f);
@@ -558,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
     }
     fence_barrier_init();
   }
-  if (warp == 12) {
+  if (warp == kTmaWarp) {
     if (lane == 0 && (P.use_tma || PATCH)) {
       prefetch_tmap(&P.tm_hi);
       if (three) prefetch_tmap(&P.tm_lo);
@@ -587,16 +597,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
 
   // Register re-balancing between the warp groups (512 threads x 128 = the whole register file):
   // 128 * (72 + 192 + 192 + 56) = 65536.
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-  } else if (warp < 12) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
-  } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-  }
-
-  if (warp < 4) {
-   if (!PATCH) {
+  // (gather variant only; each setmaxnreg sits at the top of its role branch)
+  if (!PATCH && warp < 4) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+   {
     // ------------------------------------------------------------------ gather (im2col) producers
     const int t = threadIdx.x;
     const int j = t & 7;        // 16-byte chunk of the 128-byte K row
@@ -699,40 +703,85 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
     fence_proxy_async();
     for (; gpub < g; ++gpub) mbar_arrive(smem_u32(&full_bar[gpub % S]));
    }
-  } else if (warp < 12) {
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 8) {
+    if (PATCH) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
     // ------------------------------------------------------------------ drain D0 chunks + epilogue
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;  // which half of the tile's column chunks
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int half = (warp - kEpiWarp0) >> 2;  // which half of the tile's column chunks
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int nch_tile = BN / 16;
     const int ch_begin = half == 0 ? 0 : (nch_tile + 1) / 2;
     const int ch_end = half == 0 ? (nch_tile + 1) / 2 : nch_tile;
     constexpr int NR = three ? 4 : 2;         // 16-byte registers per residual chunk
-    constexpr int KCH = three ? MAXCH : 4;    // column chunks handled per epilogue pass (unrolled)
+    constexpr int KC = three ? MAXCH : 8;     // column chunks per epilogue warp (compile-time bound)
+    // Residual operands are software-pipelined ACROSS tiles without spending registers on it: every thread copies
+    // the residual bytes of its own output row for tile j+1 into a private shared-memory slot with cp.async while
+    // tile j is being finished (a whole tile per SM in flight; the one-chunk-ahead register ring kept only 16 KB
+    // in flight = 0.9 TB/s).  At the start of tile j+1 the slot is read into registers and immediately refilled
+    // for tile j+2.  Each thread only ever touches its own slot, so no barrier is involved.
+    const bool staged = P.res_stage_pitch != 0;
+    const uint32_t my_slot = smem_res + (uint32_t)row * (uint32_t)P.res_stage_pitch + (uint32_t)(ch_begin * NR * 16);
     float total[three ? MAXCH * 16 : 1];
     uint32_t r0[16], r1[16];
+    uint4 rres[KC][NR];
     int gc = 0;  // D0 chunks seen so far (all tiles)
+
+#define CRDR_ROW_PIXEL(TILE) (PATCH ? out_pixel_of_patch_row(P, (TILE) / n_tiles, row) \
+                                    : out_pixel_of_row(d, ((TILE) / n_tiles) * kTileM + row, P.m_total))
+    // cp.async the residual operands of this thread's row / column range of `tile` into its slot
+    auto stage_issue = [&](int tile) {
+      if (staged && tile < num_tiles) {
+        const int64_t op = CRDR_ROW_PIXEL(tile);
+        if (op >= 0) {
+          const int c0 = (tile % n_tiles) * BN + ch_begin * 16;
+          const int nmine = ch_end - ch_begin;
+          if (d.res_f32) {
+            const float* src = d.res_f32 + op * d.res_f32_cs + d.res_f32_coff + c0;
+            for (int i = 0; i < nmine * 4; ++i) cp_async16(my_slot + (uint32_t)i * 16u, src + 4 * i, 16u);
+          } else {
+            const int64_t o = op * d.res.cs + d.res.coff + c0;
+            const __half* hi = (const __half*)d.res.hi + o;
+            const __half* lo = (const __half*)d.res.lo + o;
+            for (int c = 0; c < nmine; ++c) {
+              const uint32_t dst = my_slot + (uint32_t)(c * NR) * 16u;
+              cp_async16(dst, hi + 16 * c, 16u);
+              cp_async16(dst + 16u, hi + 16 * c + 8, 16u);
+              if (NR == 4 && d.res.lo) {
+                cp_async16(dst + 32u, lo + 16 * c, 16u);
+                cp_async16(dst + 48u, lo + 16 * c + 8, 16u);
+              }
+            }
+          }
+        }
+      }
+      cp_async_commit();
+    };
+    if (staged) stage_issue(blockIdx.x);
+
     int jt = 0;  // tiles processed by this CTA
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++jt) {
       const int n0 = (tile % n_tiles) * BN;
       const int tb = split ? 0 : (jt & 1);
-      const int64_t opix = PATCH ? out_pixel_of_patch_row(P, tile / n_tiles, row)
-                                 : out_pixel_of_row(d, (tile / n_tiles) * kTileM + row, P.m_total);
-      if (PATCH && d.mode != CRDR_EPI_NONE) {
-        // the epilogue operands of the NEXT tile start their trip to L2 one tile time ahead (gather mode does
-        // this from the producer warps); the very first tile prefetches for itself as well
-        if (jt == 0) prefetch_epilogue_operands(d, opix, n0 + ch_begin * 16, n0 + ch_end * 16);
-        const int nxt = tile + (int)gridDim.x;
-        if (nxt < num_tiles)
-          prefetch_epilogue_operands(d, out_pixel_of_patch_row(P, nxt / n_tiles, row), (nxt % n_tiles) * BN + ch_begin * 16,
-                                     (nxt % n_tiles) * BN + ch_end * 16);
-      }
-      // request the residual operands of the first pass now: their latency overlaps the tile's main loop / drain
-      uint4 rres[KCH][NR];
+      const int64_t opix = CRDR_ROW_PIXEL(tile);
+      if (staged) {
+        cp_async_wait<0>();  // this thread's own copies for `tile` have landed
 #pragma unroll
-      for (int c = 0; c < KCH; ++c)
-        if (opix >= 0 && ch_begin + c < ch_end) epi_load_res<NR>(P, opix, n0 + (ch_begin + c) * 16, rres[c]);
+        for (int c = 0; c < KC; ++c) {
+          if (ch_begin + c < ch_end) {
+#pragma unroll
+            for (int q = 0; q < NR; ++q) {
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(rres[c][q].x), "=r"(rres[c][q].y), "=r"(rres[c][q].z), "=r"(rres[c][q].w)
+                           : "r"(my_slot + (uint32_t)((c * NR + q) * 16)));
+            }
+          }
+        }
+        stage_issue(tile + (int)gridDim.x);  // refill the slot for the next tile; in flight during this epilogue
+      } else if (opix >= 0 && ch_begin < ch_end) {
+        epi_load_res<NR>(P, opix, n0 + ch_begin * 16, rres[0]);
+      }
       if (three) {
         for (int ch = 0; ch < nchunks; ++ch, ++gc) {
           const int b = gc & 1;
@@ -756,45 +805,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
         mbar_wait(smem_u32(&acc_full_bar[tb]), (uint32_t)(jt / TB) & 1u, P.status);
         tc_fence_after();
       }
-      // epilogue over this warp's column chunks in passes of KCH (F16X3: one pass)
       uint4 rtrunk[NR];
-      for (int cb0 = ch_begin; cb0 < ch_end; cb0 += KCH) {
-        if (cb0 != ch_begin) {
 #pragma unroll
-          for (int c = 0; c < KCH; ++c)
-            if (opix >= 0 && cb0 + c < ch_end) epi_load_res<NR>(P, opix, n0 + (cb0 + c) * 16, rres[c]);
-        }
+      for (int c = 0; c < KC; ++c) {
+        const int chn = ch_begin + c;
+        if (chn < ch_end) {
+          // second chain of a split launch lives one accumulator stride further (D1b / odd K steps)
+          if (three) tmem_ld16_issue(lane_addr + kD1Base + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r1);
+          else tmem_ld16_issue(lane_addr + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r0);
+          if (split) tmem_ld16_issue(lane_addr + (three ? kD1Base : 0u) + kAccStride + (uint32_t)chn * 16u, three ? r0 : r1);
+          if (opix >= 0) {
+            epi_load_trunk<NR>(P, opix, n0 + chn * 16, rtrunk);
+            // unstaged launches (gather variant, unaligned operands): one-chunk-ahead register ring
+            if (!staged && c + 1 < KC && chn + 1 < ch_end) epi_load_res<NR>(P, opix, n0 + (chn + 1) * 16, rres[c + 1 < KC ? c + 1 : c]);
+          }
+          tmem_wait_ld();
+          float acc[16];
 #pragma unroll
-        for (int c = 0; c < KCH; ++c) {
-          const int chn = cb0 + c;
-          if (chn < ch_end) {
-            // second chain of a split launch lives one accumulator stride further (D1b / odd K steps)
-            if (three) tmem_ld16_issue(lane_addr + kD1Base + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r1);
-            else tmem_ld16_issue(lane_addr + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r0);
-            if (split) tmem_ld16_issue(lane_addr + (three ? kD1Base : 0u) + kAccStride + (uint32_t)chn * 16u, three ? r0 : r1);
-            if (opix >= 0) epi_load_trunk<NR>(P, opix, n0 + chn * 16, rtrunk);
-            tmem_wait_ld();
-            float acc[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              if (three) {
-                const float cross = split ? __uint_as_float(r1[e]) + __uint_as_float(r0[e]) : __uint_as_float(r1[e]);
-                acc[e] = fmaf(cross, kLoInv, total[(three ? c : 0) * 16 + e]);
-              } else {
-                acc[e] = split ? __uint_as_float(r0[e]) + __uint_as_float(r1[e]) : __uint_as_float(r0[e]);
-              }
+          for (int e = 0; e < 16; ++e) {
+            if (three) {
+              const float cross = split ? __uint_as_float(r1[e]) + __uint_as_float(r0[e]) : __uint_as_float(r1[e]);
+              acc[e] = fmaf(cross, kLoInv, total[(three ? c : 0) * 16 + e]);
+            } else {
+              acc[e] = split ? __uint_as_float(r0[e]) + __uint_as_float(r1[e]) : __uint_as_float(r0[e]);
             }
-            if (opix >= 0) {
-              if (P.fast_epi) epi_finish<NR>(P, opix, n0 + chn * 16, acc, rres[c], rtrunk, s_par);
-              else epi_finish_generic(&P, opix, n0 + chn * 16, acc, s_par);
-            }
+          }
+          if (opix >= 0) {
+            if (P.fast_epi) epi_finish<NR>(P, opix, n0 + chn * 16, acc, rres[c], rtrunk, s_par);
+            else epi_finish_generic(&P, opix, n0 + chn * 16, acc, s_par);
           }
         }
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&acc_empty_bar[tb]));
     }
-  } else if (warp == 12) {
+#undef CRDR_ROW_PIXEL
+  } else {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+   if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ weight tiles by TMA
     if (lane == 0 && (P.use_tma || PATCH)) {
       int g = 0;
@@ -811,7 +859,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
         }
       }
     }
-  } else if (warp == 14) {
+  } else if (warp == kPatchWarp) {
     // ------------------------------------------------------------------ PATCH: halo patches by TMA (one thread)
     if (PATCH && lane == 0) {
       int gp = 0;  // patches issued so far (all tiles)
@@ -829,7 +877,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
         }
       }
     }
-  } else if (warp == 13) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issue (whole warp converged, one lane issues)
     {
       const uint32_t idesc = umma_idesc_f16((uint32_t)BN);
@@ -924,9 +972,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tcgen05_kernel(const __grid_
         c[4] = (unsigned long long)t_patch; c[5] = (unsigned long long)g;
       }
     }
+   }
   }
   __syncthreads();
-  if (warp == 12) {
+  if (warp == kTmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512u);
   }
@@ -1319,7 +1368,18 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     set_error("conv2d: tile_n=%d does not leave two pipeline stages (patch %u B)", d.tile_n, patch_total);
     return CRDR_ERR_BAD_SHAPE;
   }
-  int stages = (int)((kDynSmemMax - 1024 - patch_total) / stage_bytes);
+  // residual staging: one private slot per output row (pitch padded by 16 B against bank conflicts)
+  uint32_t res_total = 0;
+  P.res_stage_pitch = 0;
+  if (d.mode != CRDR_EPI_NONE && P.fast_epi) {
+    const uint32_t row_bytes = (uint32_t)d.tile_n * (three ? 4u : 2u);
+    const uint32_t pitch = row_bytes + 16u;
+    if (patch_total + 2 * stage_bytes + 1024 + kTileM * pitch <= kDynSmemMax) {
+      P.res_stage_pitch = (int32_t)pitch;
+      res_total = kTileM * pitch;
+    }
+  }
+  int stages = (int)((kDynSmemMax - 1024 - patch_total - res_total) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   P.stages = stages;
   P.tmem_cols = 512;
@@ -1333,11 +1393,11 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
       if (rc) return rc;
     }
   }
-  const uint32_t smem = patch_total + (uint32_t)stages * stage_bytes + 1024;
+  const uint32_t smem = patch_total + (uint32_t)stages * stage_bytes + res_total + 1024;
   const int64_t m_tiles = use_patch ? (int64_t)d.n * P.tiles_h * P.tiles_w : (m_total + kTileM - 1) / kTileM;
   const int64_t num_tiles = m_tiles * (d.cout_pad / d.tile_n);
   const unsigned grid = (unsigned)(num_tiles < num_sms ? num_tiles : num_sms);  // persistent: one CTA per SM
-  fn<<<grid, kThreads, smem, stream>>>(P);
+  fn<<<grid, use_patch ? kThreadsPatch : kThreads, smem, stream>>>(P);
   return check_launch("conv_tcgen05_kernel");
 }
 

@@ -156,6 +156,27 @@ class CodecEngine:
         return out
 
 
+class _PinnedPool:
+    """Reusable page-locked staging buffers for the device<->host boundary of the coder (symbols, CDF indexes)."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, tag, shape, dtype):
+        key = (tag, tuple(shape), dtype)
+        buf = self._bufs.get(key)
+        if buf is None:
+            buf = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+            self._bufs[key] = buf
+        return buf
+
+    def fetch(self, tag, dev_tensor):
+        """Asynchronous device -> pinned host copy on the current stream (caller synchronises)."""
+        buf = self.get(tag, dev_tensor.shape, dev_tensor.dtype)
+        buf.copy_(dev_tensor, non_blocking=True)
+        return buf
+
+
 def _channel_indexes(c, h, w):
     return np.ascontiguousarray(np.broadcast_to(np.arange(c, dtype=np.int32)[:, None, None], (c, h, w))).reshape(-1)
 
@@ -174,6 +195,7 @@ class _CodecModelBase(nn.Module):
         self.stride = 64
         self._engine = None
         self._engine_opts = {}
+        self._pinned = _PinnedPool()
 
     # -- engine lifecycle -------------------------------------------------------------------
     def engine(self):
@@ -332,9 +354,12 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
         y_bits, z_bits = eng.bits(a["y_lik"]), eng.bits(a["z_lik"])
         y_max = eng.max_abs(a["yhat32"])
         # ---- device -> host boundary (the reference moves y, z here; we move symbols and table indexes)
-        z_sym, y_sym, y_idx = a["z_sym"].cpu().numpy(), a["y_sym"].cpu().numpy(), a["y_idx"].cpu().numpy()
-        y_bits, z_bits, y_max = y_bits.cpu().numpy(), z_bits.cpu().numpy(), y_max.cpu().numpy()
-        nv.status_check()
+        pp = self._pinned
+        z_sym, y_sym, y_idx = pp.fetch("z_sym", a["z_sym"]), pp.fetch("y_sym", a["y_sym"]), pp.fetch("y_idx", a["y_idx"])
+        y_bits, z_bits, y_max = pp.fetch("y_bits", y_bits), pp.fetch("z_bits", z_bits), pp.fetch("y_max", y_max)
+        nv.status_check()  # synchronises the stream: the pinned buffers are valid from here
+        z_sym, y_sym, y_idx = z_sym.numpy(), y_sym.numpy(), y_idx.numpy()
+        y_bits, z_bits, y_max = y_bits.numpy().copy(), z_bits.numpy().copy(), y_max.numpy().copy()
         zc, hz, wz = z_sym.shape[1:]
         zi = _channel_indexes(zc, hz, wz)
         z_strs = rans.encode_batch([z_sym[i] for i in range(n)], [zi] * n, self.entropy_model_z.coder_tables(), coder_threads)
@@ -381,8 +406,9 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
             zi = _channel_indexes(self.zC, hz, wz)
             zt, yt = self.entropy_model_z.coder_tables(), self.entropy_model_y.coder_tables()
             z_dec = [rans.Decoder(sl[1]) for sl in string_lists]
-            z_np = np.stack(rans.decode_batch(z_dec, [zi] * n, zt, coder_threads)).reshape(n, self.zC, hz, wz)
-            z_sym = torch.from_numpy(z_np).to(dev)
+            z_host = self._pinned.get("z_dec", (n, self.zC, hz, wz), torch.int32)
+            z_host.numpy().reshape(n, -1)[:] = np.stack(rans.decode_batch(z_dec, [zi] * n, zt, coder_threads))
+            z_sym = z_host.to(dev, non_blocking=True)
             T, z_hat = eng.hyper_from_symbols(z_sym)
             y_dec = [rans.Decoder(sl[2]) for sl in string_lists]
             hy, wy = T.h, T.w
@@ -391,10 +417,14 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
 
             def source(s0, cnt, idx):
                 c0, c1 = s0 * sc, (s0 + cnt) * sc
-                ix = idx[:, c0:c1].contiguous().cpu().numpy()  # device -> host: table indexes of this group
+                # device -> host: table indexes of this group (pinned, one sync)
+                ix_host = self._pinned.fetch(f"y_idx_{cnt}", idx[:, c0:c1].contiguous())
+                torch.cuda.current_stream().synchronize()
+                ix = ix_host.numpy()
                 syms = rans.decode_batch(y_dec, [ix[i] for i in range(n)], yt, coder_threads)
-                blk = torch.from_numpy(np.stack(syms).reshape(n, c1 - c0, hy, wy))
-                y_sym[:, c0:c1] = blk.to(dev)  # host -> device: decoded symbols
+                sym_host = self._pinned.get(f"y_sym_{cnt}", (n, c1 - c0, hy, wy), torch.int32)
+                sym_host.numpy().reshape(n, -1)[:] = np.stack(syms)
+                y_sym[:, c0:c1].copy_(sym_host, non_blocking=True)  # host -> device: decoded symbols
                 return y_sym
 
             yhat32 = eng.charm.decode(T, eng.gp, source)

@@ -6,25 +6,38 @@ from crdr_b200 import native as nv
 from crdr_b200.engine import Act, ConvOp
 
 
-def bench(n, cin, cout, h, w, k, stride, tr, prec, tile_n=None, iters=10):
+def bench(n, cin, cout, h, w, k, stride, tr, prec, tile_n=None, epi=0, iters=10):
     g = torch.Generator().manual_seed(0)
     x = Act.from_nchw(torch.randn(n, cin, h, w, generator=g).cuda(), two=True)
     wt = torch.randn(cin, cout, k, k, generator=g) if tr else torch.randn(cout, cin, k, k, generator=g)
     op = ConvOp(wt / (cin * k * k) ** 0.5, torch.zeros(cout), transposed=bool(tr), stride=stride, padding=k // 2,
                 output_padding=stride - 1 if tr else 0)
-    out = op(x, precision=prec, tile_n=tile_n)
+    kw = {}
+    if epi:  # residual + per-channel gain, like the last 1x1 of a bottleneck block
+        ho, wo = op.out_hw(h, w)
+        r = torch.randn(n, cout, ho, wo, generator=g).cuda()
+        if epi in (1, 3):
+            kw.update(mode=nv.EPI_RESIDUAL, res=Act.from_nchw(r, two=(prec == 0)))
+        if epi == 4:
+            kw.update(mode=nv.EPI_RESIDUAL, res=r.permute(0, 2, 3, 1).contiguous())
+        if epi == 5:
+            kw.update(mode=nv.EPI_RESIDUAL, res=Act.from_nchw(r, two=False))
+        if epi in (1, 2):
+            kw.update(scale=torch.rand(cout).cuda() + 0.5, shift=torch.randn(cout).cuda())
+    tile_n = tile_n or None
+    out = op(x, precision=prec, tile_n=tile_n, **kw)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        op(x, out=out, precision=prec, tile_n=tile_n)
+        op(x, out=out, precision=prec, tile_n=tile_n, **kw)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     ho, wo = op.out_hw(h, w)
     fl = 2.0 * n * ho * wo * cout * cin * k * k / (stride * stride if tr else 1)
     mult = 3 if prec == 0 else 1
-    print(f"n={n} {cin}->{cout} {h}x{w} k{k} s{stride} tr{tr} prec{prec} tile={tile_n}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s alg, {mult*fl/ms/1e9:.1f} MMA")
+    print(f"n={n} {cin}->{cout} {h}x{w} k{k} s{stride} tr{tr} prec{prec} tile={tile_n} epi={epi}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s alg, {mult*fl/ms/1e9:.1f} MMA")
     nv.status_check()
     import os, ctypes
     if os.environ.get("CRDR_CONV_TRACE"):
