@@ -350,8 +350,9 @@ class SynthesisEngine:
         self.two = precision == X3
         up = lambda name: Conv(sd, name, cfg, transposed=True, stride=2, padding=2, output_padding=1)
         self.attn1 = Nlam(_sub(sd, "attn1"), cfg)
-        self.conv1, self.conv2, self.conv3, self.conv4 = up("conv1"), up("conv2"), up("conv3"), up("conv4")
+        self.conv1, self.conv2, self.conv3 = up("conv1"), up("conv2"), up("conv3")
         self.attn2 = Nlam(_sub(sd, "attn2"), cfg)
+        self.conv4p = self._phase_packed(sd["conv4.weight"], sd["conv4.bias"], cfg)
         self.blocks, self.proj = {}, {}
         for b in ("block1", "block2", "block3"):
             self.blocks[b] = [Bottleneck(_sub(sd, f"{b}.block{i}"), ["conv.0", "conv.2", "conv.4"], cfg) for i in range(3)]
@@ -367,6 +368,28 @@ class SynthesisEngine:
             self.freq = self.freq * math.pi
         self._beta_cache = {}
         self.in_ch = sd["conv1.weight"].shape[0]
+
+    @staticmethod
+    def _phase_packed(w, b, cfg):
+        """The last up-convolution (ConvTranspose2d 5x5, stride 2, padding 2, output_padding 1, Cout = 3) as ONE
+        stride-1 3x3 convolution with 4 phases x 3 = 12 (padded to 16) output channels: out[2a+ph, 2b+pw, c] uses the
+        taps kh = ph + 2 - 2*dh, kw = pw + 2 - 2*dw (dh, dw in -1..1).  2.8x fewer (tiny-N) MMAs than four phase
+        launches; exact same products, so results are bit-identical to the phase form up to summation order."""
+        cin, cout, kh, kw = w.shape
+        assert (kh, kw) == (5, 5) and cout * 4 <= 16
+        wc = torch.zeros(16, cin, 3, 3, dtype=torch.float32)
+        bc = torch.zeros(16, dtype=torch.float32)
+        wf, bf = w.detach().float().cpu(), b.detach().float().cpu()
+        for ph in range(2):
+            for pw in range(2):
+                o = (ph * 2 + pw) * cout
+                bc[o:o + cout] = bf
+                for dh in (-1, 0, 1):
+                    for dw in (-1, 0, 1):
+                        i, j = ph + 2 - 2 * dh, pw + 2 - 2 * dw
+                        if 0 <= i < 5 and 0 <= j < 5:
+                            wc[o:o + cout, :, dh + 1, dw + 1] = wf[:, :, i, j].t()
+        return Conv({"w.weight": wc, "w.bias": bc}, "w", cfg, padding=1)
 
     def cond_vectors(self, beta):
         beta = float(beta)
@@ -393,7 +416,7 @@ class SynthesisEngine:
         return x
 
     def run(self, yhat32, q, beta):
-        """yhat32: fp32 NHWC [n, h, w, C] -> fp32 NHWC image [n, 16h, 16w, 4] (3 real channels)."""
+        """yhat32: fp32 NHWC [n, h, w, C] -> phase-packed fp32 image [n, 8h, 8w, 16] (see _phase_packed)."""
         g = [gn.vectors(q) for gn in self.gains]
         cond = self.cond_vectors(beta)
         n, h, w, c = yhat32.shape
@@ -408,7 +431,7 @@ class SynthesisEngine:
         x = self._blocks("block2", x, cond, g[6])
         x = self.conv3(x, scale=g[7][0], shift=g[7][1])
         x = self._blocks("block3", x, cond, g[8])
-        ho, wo = self.conv4.op.out_hw(x.h, x.w)
-        img = torch.empty((n, ho, wo, 4), dtype=torch.float32, device=yhat32.device)
-        self.conv4(x, out_f32=img, want_planes=False)
+        # phase-packed final up-convolution: [n, h/2, w/2, 16] with channel = (phase_y*2 + phase_x)*3 + c
+        img = torch.empty((n, x.h, x.w, 16), dtype=torch.float32, device=yhat32.device)
+        self.conv4p(x, out_f32=img, want_planes=False)
         return img

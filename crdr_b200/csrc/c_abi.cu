@@ -59,6 +59,7 @@ int affine_to_planes_launch(const float* x, int x_cs, int x_coff, int64_t m, int
                             const float* shift, crdr_planes out, cudaStream_t st);
 int image_to_planes_launch(const float* img, int n, int h, int w, int hp, int wp, crdr_planes out, cudaStream_t st);
 int planes_to_image_launch(const float* x, int x_cs, int n, int hp, int wp, int h, int w, float* img, cudaStream_t st);
+int phases_to_image_launch(const float* x, int x_cs, int n, int hb, int wb, int h, int w, float* img, cudaStream_t st);
 int bits_launch(const float* lik, int n, int64_t per, float* bits, cudaStream_t st);
 int max_abs_launch(const float* x, int64_t count, float* out, cudaStream_t st);
 
@@ -119,6 +120,11 @@ int crdr_image_to_planes(const float* img, int32_t n, int32_t h, int32_t w, int3
 int crdr_planes_to_image(const float* x, int32_t x_cs, int32_t n, int32_t hp, int32_t wp, int32_t h, int32_t w,
                          float* img, void* stream) {
   return planes_to_image_launch(x, x_cs, n, hp, wp, h, w, img, (cudaStream_t)stream);
+}
+
+int crdr_phases_to_image(const float* x, int32_t x_cs, int32_t n, int32_t hb, int32_t wb, int32_t h, int32_t w,
+                         float* img, void* stream) {
+  return phases_to_image_launch(x, x_cs, n, hb, wb, h, w, img, (cudaStream_t)stream);
 }
 
 int crdr_nhwc_to_nchw(const float* x, int32_t x_cs, int32_t x_coff, int32_t n, int32_t hw, int32_t c, float* out,

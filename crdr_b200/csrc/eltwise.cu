@@ -261,6 +261,23 @@ __global__ void __launch_bounds__(256) planes_to_image_kernel(const float* __res
   img[idx] = fminf(fmaxf(v, -1.f), 1.f);
 }
 
+// Same, for a stride-2 transposed convolution evaluated as ONE stride-1 launch whose output channels are the four
+// output phases: x[(b, y/2, x/2), ((y%2)*2 + x%2)*3 + c]  (pixel shuffle + crop + clamp in one pass).
+__global__ void __launch_bounds__(256) phases_to_image_kernel(const float* __restrict__ x, int x_cs, int n, int hb,
+                                                              int wb, int h, int w, float* __restrict__ img) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)n * 3 * h * w;
+  if (idx >= total) return;
+  const int xx = (int)(idx % w);
+  int64_t t = idx / w;
+  const int yy = (int)(t % h);
+  t /= h;
+  const int c = (int)(t % 3);
+  const int b = (int)(t / 3);
+  const float v = x[(((int64_t)b * hb + (yy >> 1)) * wb + (xx >> 1)) * x_cs + ((yy & 1) * 2 + (xx & 1)) * 3 + c];
+  img[idx] = fminf(fmaxf(v, -1.f), 1.f);
+}
+
 // one block per image; fixed summation order -> run-to-run and batch-size invariant
 __global__ void __launch_bounds__(1024) bits_kernel(const float* __restrict__ lik, int64_t per, float* __restrict__ bits) {
   __shared__ double s[1024];
@@ -346,6 +363,16 @@ int planes_to_image_launch(const float* x, int x_cs, int n, int hp, int wp, int 
   const int64_t total = (int64_t)n * 3 * h * w;
   planes_to_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, x_cs, n, hp, wp, h, w, img);
   return check_launch("planes_to_image_kernel");
+}
+
+int phases_to_image_launch(const float* x, int x_cs, int n, int hb, int wb, int h, int w, float* img, cudaStream_t st) {
+  if (n <= 0 || h <= 0 || w <= 0 || 2 * hb < h || 2 * wb < w || x_cs < 12) {
+    set_error("phases_to_image: bad shape");
+    return CRDR_ERR_BAD_SHAPE;
+  }
+  const int64_t total = (int64_t)n * 3 * h * w;
+  phases_to_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, x_cs, n, hb, wb, h, w, img);
+  return check_launch("phases_to_image_kernel");
 }
 
 int bits_launch(const float* lik, int n, int64_t per, float* bits, cudaStream_t st) {

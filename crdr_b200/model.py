@@ -121,11 +121,11 @@ class CodecEngine:
 
     def synthesis(self, yhat32, q, beta, size):
         """y_hat fp32 NHWC -> cropped, clamped fp32 NCHW image."""
-        img = self.gs.run(yhat32, q, beta)
-        n, hp, wp, cs = img.shape
+        img = self.gs.run(yhat32, q, beta)  # phase-packed: [n, hp/2, wp/2, 16]
+        n, hb, wb, cs = img.shape
         h, w = size
         out = torch.empty((n, 3, h, w), dtype=torch.float32, device=img.device)
-        nv.check(nv.lib().crdr_planes_to_image(img.data_ptr(), cs, n, hp, wp, h, w, out.data_ptr(), nv.stream_handle()))
+        nv.check(nv.lib().crdr_phases_to_image(img.data_ptr(), cs, n, hb, wb, h, w, out.data_ptr(), nv.stream_handle()))
         return out
 
     def decode_device(self, z_sym, y_sym, q, beta, size):

@@ -146,6 +146,12 @@ int crdr_image_to_planes(const float* img, int32_t n, int32_t h, int32_t w, int3
 int crdr_planes_to_image(const float* x, int32_t x_cs, int32_t n, int32_t hp, int32_t wp, int32_t h, int32_t w,
                          float* img, void* stream);
 
+/* Same post-processing for the final stride-2 ConvTranspose2d (g_s conv4, 256 -> 3) evaluated as ONE stride-1
+ * launch whose 12 output channels are (phase_y*2 + phase_x)*3 + c on the (hb, wb) input grid: pixel shuffle +
+ * crop + clamp -> NCHW fp32 (h <= 2*hb, w <= 2*wb). */
+int crdr_phases_to_image(const float* x, int32_t x_cs, int32_t n, int32_t hb, int32_t wb, int32_t h, int32_t w,
+                         float* img, void* stream);
+
 /* NHWC fp32 [n][hw][cs](coff..coff+c) -> NCHW fp32 [n][c][hw]  (API-facing tensors). */
 int crdr_nhwc_to_nchw(const float* x, int32_t x_cs, int32_t x_coff, int32_t n, int32_t hw, int32_t c,
                       float* out, void* stream);
