@@ -95,11 +95,11 @@ int crdr_status_read(uint32_t* flags, void* stream) {
 }
 
 /* bring-up aid (not part of the documented ABI): MMA-thread cycle counters of CTA 0 of the last traced launch */
-int crdr_debug_counters(unsigned long long* out6) {
+int crdr_debug_counters(unsigned long long* out10) {
   uint32_t* p = device_status_word();
   if (!p) return CRDR_ERR_CUDA;
   cudaDeviceSynchronize();
-  return cudaMemcpy(out6, p + 16, 48, cudaMemcpyDeviceToHost) == cudaSuccess ? CRDR_OK : CRDR_ERR_CUDA;
+  return cudaMemcpy(out10, p + 16, 80, cudaMemcpyDeviceToHost) == cudaSuccess ? CRDR_OK : CRDR_ERR_CUDA;
 }
 
 int crdr_conv2d(const crdr_conv_desc* d, void* stream) {

@@ -33,7 +33,7 @@ namespace crdr {
 constexpr int kTileM = 128;
 constexpr int kKBlk = 64;                  // fp16 elements per K block = one 128-byte swizzle row
 constexpr uint32_t kAPlaneBytes = kTileM * 128;
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 10;
 constexpr int kThreads = 512;              // gather variant: warps 0-3 gather, 4-11 drain/epilogue, 12 TMA + TMEM alloc, 13 MMA, 14-15 idle
 constexpr int kThreadsPatch = 384;         // patch variant: warps 0-7 drain/epilogue, 8 TMA + TMEM alloc, 9 MMA, 10 halo patches, 11 idle
                                            // setmaxnreg: 128 * (216 + 216 + 56) <= 65536
@@ -53,6 +53,7 @@ struct alignas(64) ConvKParams {
   // PATCH mode geometry
   int32_t ph, pw, dh_min, dw_min, ncb, tiles_h, tiles_w, patch_stages;
   int32_t cb_c0[kMaxCBlocks];
+  uint32_t tapoff[CRDR_MAX_TAPS];  // PATCH: byte offset of a tap's start row inside the halo patch
   int32_t m_total, nkb, cin, k_real, nplanes, stages, tmem_cols, use_tma;
   int32_t vec_planes_out, vec_f32_out, vec_res_planes, vec_res_f32, vec_trunk;
   int32_t has_bias, has_add, has_affine, chunk_kb, trace, split, fast_epi, res_stage_pitch;
@@ -87,7 +88,19 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   return ok;
 }
 // Bounded wait: a pipeline bug must end in a trap with the status flag set, never in a hung GPU.
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t* status) {
+  if (mbar_test_wait(bar, parity)) return;  // the common case in a filled pipeline: no suspend machinery
 #pragma unroll 1
   for (uint32_t i = 0; i < 4000u; ++i)  // <= 4000 x 1 ms
     if (mbar_try_wait(bar, parity)) return;
@@ -119,6 +132,41 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: the mbarrier operand lives in the LEADER CTA of the pair ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default (.release.cta) semantics as in CUTLASS' ClusterBarrier::arrive(cta_id): the only thing handed over is
+  // TMEM, ordered by tcgen05.fence::before_thread_sync; ".release.cluster" compiles to MEMBAR.ALL.GPU + ERRBAR and
+  // was 27 % of all stall samples in the drain warps.
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(leader_bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_cg2(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
+                                                uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(leader_bar)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
@@ -130,6 +178,15 @@ __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// CTA pair: one warp of EACH CTA of the pair executes these
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // one lane of a fully converged warp (CUTLASS elect_one_sync)
 __device__ __forceinline__ bool elect_one() {
@@ -156,6 +213,33 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
 // Arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// CTA pair: M = 256 (rows 0-127 from the leader's shared memory / TMEM, 128-255 from the peer's), each CTA supplies
+// half of the N rows of B; issued by the leader only.  The commit arrives on the barrier at this shared-memory
+// offset in BOTH CTAs.
+__device__ __forceinline__ void umma_f16_cg2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+template <bool CG2>
+__device__ __forceinline__ void umma_issue(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (CG2) umma_f16_cg2(d_tmem, adesc, bdesc, idesc, acc);
+  else umma_f16(d_tmem, adesc, bdesc, idesc, acc);
+}
+template <bool CG2>
+__device__ __forceinline__ void umma_done(uint32_t bar) {
+  if (CG2) umma_commit_cg2(bar);
+  else umma_commit(bar);
 }
 // 16 consecutive fp32 columns of this thread's TMEM lane; the values are valid after tmem_wait_ld().
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
@@ -200,8 +284,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_rows(uint32_t saddr, uint32_
   return d;
 }
 // kind::f16 instruction descriptor: fp16 A/B (K-major), fp32 accumulate, M=128, N=n.
-__device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t n) {
-  return (1u << 4) | ((n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+__device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t n, uint32_t m = kTileM) {
+  return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -454,7 +538,7 @@ __device__ __forceinline__ int64_t out_pixel_of_patch_row(const ConvKParams& P, 
   patch_tile_origin(P, mt, n, h0, w0);
   const int bh = h0 + (row >> 3), bw = w0 + (row & 7);
   const crdr_conv_desc& d = P.d;
-  if (bh >= d.hb || bw >= d.wb) return -1;
+  if (bh >= d.hb || bw >= d.wb || n >= d.n) return -1;
   return ((int64_t)n * d.hout + (bh * d.out_stride + d.out_ph)) * d.wout + (bw * d.out_stride + d.out_pw);
 }
 
@@ -497,9 +581,15 @@ __device__ __forceinline__ void prefetch_epilogue_operands(const crdr_conv_desc&
 // TMA box load brings the (16 + span_h) x (8 + span_w) halo patch of a 64-channel block into shared memory
 // (zero fill outside the image) and every tap's A operand is just a different start row of that patch, addressed
 // through the UMMA descriptor (group stride = patch row pitch).  L2 -> SM traffic for A drops by ~ntaps.
-template <int MAXCH, bool PATCH>
+// CG2 (PATCH only): the kernel runs as clusters of two CTAs (a CTA pair on one TPC).  The pair works on two
+// consecutive M tiles and the same N tile; the leader (cluster rank 0) issues
+// tcgen05.mma.cta_group::2 with M = 256 over both CTAs' shared memory / TMEM, each CTA loads its own halo patch and
+// HALF of the weight tile.  One 128 x N x 16 cta_group::1 MMA occupies the tensor pipe for ~N cycles (measured,
+// twice the 4096 MAC/clk rate); the pair form is how sm_100 reaches the full rate.
+template <int MAXCH, bool PATCH, bool CG2 = false>
 __global__ void __launch_bounds__(PATCH ? kThreadsPatch : kThreads, 1)
 conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
+  static_assert(PATCH || !CG2, "the CTA-pair form exists for the patch variant only");
   constexpr bool three = MAXCH > 0;
   constexpr int kEpiWarp0 = PATCH ? 0 : 4;      // first of the 8 drain / epilogue warps (a multiple of 4: TMEM lane quarters)
   constexpr int kTmaWarp = kEpiWarp0 + 8;
@@ -519,12 +609,19 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
   __shared__ __align__(16) float s_par[4 * kMaxCout];
 
   const crdr_conv_desc& d = P.d;
-  const int warp = threadIdx.x >> 5;
+  // warp-uniform values are laundered through a lane-0 broadcast so the compiler keeps everything derived from them
+  // (descriptors, barrier addresses, TMEM addresses) in uniform registers: the MMA issue loop is a serial instruction
+  // stream and every R2UR / waterfall loop in it costs tensor-pipe time.
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int S = P.stages;
   constexpr int nplanes = three ? 2 : 1;
   const int BN = d.tile_n;
-  const uint32_t b_bytes = (uint32_t)BN * 128u;
+  const uint32_t cta_rank = CG2 ? __shfl_sync(0xffffffffu, cluster_ctarank(), 0) : 0u;
+  const int tile0 = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;  // tile schedule of this CTA (pair)
+  const int tstep = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int BNL = CG2 ? BN / 2 : BN;                                 // weight-tile rows held by this CTA
+  const uint32_t b_bytes = (uint32_t)BNL * 128u;
   // shared memory: [patch stages (PATCH only)] [ring of S stages: (A tile, gather mode only) + B tile]
   const uint32_t patch_plane_bytes = PATCH ? (uint32_t)(P.ph * P.pw) * 128u : 0u;
   const uint32_t patch_stage_bytes = (patch_plane_bytes * nplanes + 1023u) & ~1023u;
@@ -535,7 +632,9 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
   const uint32_t smem_res = smem_base + (uint32_t)P.stages * stage_bytes;  // residual staging slots (128 rows)
   const int nkb = P.nkb;
   const int n_tiles = d.cout_pad / BN;
-  const int num_tiles = (PATCH ? d.n * P.tiles_h * P.tiles_w : (P.m_total + kTileM - 1) / kTileM) * n_tiles;
+  const int m_tiles = PATCH ? d.n * P.tiles_h * P.tiles_w : (P.m_total + kTileM - 1) / kTileM;
+  const int num_tiles = (CG2 ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;  // CG2: tiles of the pair (M = 256)
+#define CRDR_MTILE(TILE) (CG2 ? 2 * ((TILE) / n_tiles) + (int)cta_rank : (TILE) / n_tiles)
   const int chunk_kb = three ? P.chunk_kb : nkb;
   const int nchunks = (nkb + chunk_kb - 1) / chunk_kb;  // D0 chunks per tile
 
@@ -562,12 +661,13 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&d0_full_bar[b]), 1u);
-      mbar_init(smem_u32(&d0_empty_bar[b]), 256u);
+      mbar_init(smem_u32(&d0_empty_bar[b]), CG2 ? 16u : 8u);   // one arrive per drain warp (of both CTAs)
       mbar_init(smem_u32(&acc_full_bar[b]), 1u);
-      mbar_init(smem_u32(&acc_empty_bar[b]), 256u);
+      mbar_init(smem_u32(&acc_empty_bar[b]), CG2 ? 16u : 8u);
     }
     fence_barrier_init();
   }
+  if (CG2) cluster_sync_all();  // both CTAs resident, barriers initialised, before any remote arrive / pair alloc
   if (warp == kTmaWarp) {
     if (lane == 0 && (P.use_tma || PATCH)) {
       prefetch_tmap(&P.tm_hi);
@@ -578,12 +678,13 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
       }
     }
     __syncwarp();
-    tmem_alloc(smem_u32(&tmem_slot), 512u);
+    if (CG2) tmem_alloc_cg2(smem_u32(&tmem_slot), 512u);
+    else tmem_alloc(smem_u32(&tmem_slot), 512u);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);
   // TMEM columns.  F16X3: D0 chunk ping-pong at 0 / 128, D1 per-tile double buffer at 256 / 384.
   //                F16X1: per-tile accumulator double buffer at 0 / 256.
   // Dependent tcgen05.mma on one accumulator issue only every ~207 cycles (measured), longer than a 128 x N x 16
@@ -615,7 +716,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
     const int lookahead = S - 1;
     int g = 0;     // K blocks issued so far (all tiles)
     int gpub = 0;  // K blocks published to the MMA thread
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tstep) {
       const int m0 = (tile / n_tiles) * kTileM;
       const int n0 = (tile % n_tiles) * BN;
       int64_t rowoff[8];   // element offset of the row's tap-(0,0) input pixel (channel coff included)
@@ -728,7 +829,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
     uint4 rres[KC][NR];
     int gc = 0;  // D0 chunks seen so far (all tiles)
 
-#define CRDR_ROW_PIXEL(TILE) (PATCH ? out_pixel_of_patch_row(P, (TILE) / n_tiles, row) \
+#define CRDR_ROW_PIXEL(TILE) (PATCH ? out_pixel_of_patch_row(P, CRDR_MTILE(TILE), row) \
                                     : out_pixel_of_row(d, ((TILE) / n_tiles) * kTileM + row, P.m_total))
     // cp.async the residual operands of this thread's row / column range of `tile` into its slot
     auto stage_issue = [&](int tile) {
@@ -758,10 +859,19 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
       }
       cp_async_commit();
     };
-    if (staged) stage_issue(blockIdx.x);
+    if (staged) stage_issue(tile0);
+    // hand a TMEM buffer back to the MMA thread (of the pair's leader): one arrive per warp
+    auto arrive_leader = [&](uint64_t* bar) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG2) mbar_arrive_cluster(mapa_shared(smem_u32(bar), 0u));
+        else mbar_arrive(smem_u32(bar));
+      }
+    };
 
     int jt = 0;  // tiles processed by this CTA
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++jt) {
+    for (int tile = tile0; tile < num_tiles; tile += tstep, ++jt) {
       const int n0 = (tile % n_tiles) * BN;
       const int tb = split ? 0 : (jt & 1);
       const int64_t opix = CRDR_ROW_PIXEL(tile);
@@ -778,7 +888,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
             }
           }
         }
-        stage_issue(tile + (int)gridDim.x);  // refill the slot for the next tile; in flight during this epilogue
+        stage_issue(tile + tstep);  // refill the slot for the next tile; in flight during this epilogue
       } else if (opix >= 0 && ch_begin < ch_end) {
         epi_load_res<NR>(P, opix, n0 + ch_begin * 16, rres[0]);
       }
@@ -798,8 +908,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
                 total[c * 16 + e] = (ch == 0) ? __uint_as_float(r0[e]) : total[c * 16 + e] + __uint_as_float(r0[e]);
             }
           }
-          tc_fence_before();
-          mbar_arrive(smem_u32(&d0_empty_bar[b]));
+          arrive_leader(&d0_empty_bar[b]);
         }
       } else {
         mbar_wait(smem_u32(&acc_full_bar[tb]), (uint32_t)(jt / TB) & 1u, P.status);
@@ -836,8 +945,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(smem_u32(&acc_empty_bar[tb]));
+      arrive_leader(&acc_empty_bar[tb]);
     }
 #undef CRDR_ROW_PIXEL
   } else {
@@ -846,46 +954,88 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
     // ------------------------------------------------------------------ weight tiles by TMA
     if (lane == 0 && (P.use_tma || PATCH)) {
       int g = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const bool trp = P.trace && blockIdx.x == 0;
+      long long tp_wait = 0, tp0 = 0, tp_all0 = trp ? clock64() : 0;
+      int s = 0;
+      uint32_t empty_par = 1u;  // a fresh barrier passes a wait on the previous phase
+      uint32_t bst = smem_base + (uint32_t)nplanes * a_bytes;
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
         const int n0 = (tile % n_tiles) * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++g) {
-          const int s = g % S;
-          mbar_wait(smem_u32(&empty_bar[s]), ((uint32_t)(g / S) & 1u) ^ 1u, P.status);
+        for (int kb = 0; kb < nkb; ++kb, ++g, ++s, bst += stage_bytes) {
+          if (s == S) { s = 0; empty_par ^= 1u; bst = smem_base + (uint32_t)nplanes * a_bytes; }
+          if (trp) tp0 = clock64();
+          mbar_wait(smem_u32(&empty_bar[s]), empty_par, P.status);
+          if (trp) tp_wait += clock64() - tp0;
           const uint32_t bar = smem_u32(&full_bar[s]);
-          const uint32_t bst = smem_base + (uint32_t)s * stage_bytes + (uint32_t)nplanes * a_bytes;
-          mbar_arrive_expect_tx(bar, (uint32_t)nplanes * b_bytes);
-          tma_load_2d(bst, &P.tm_hi, kb * kKBlk, n0, bar);
-          if (three) tma_load_2d(bst + b_bytes, &P.tm_lo, kb * kKBlk, n0, bar);
+          if (CG2) {
+            // both halves of the weight tile complete on the leader's barrier
+            if (cta_rank == 0) mbar_arrive_expect_tx(bar, 2u * (uint32_t)nplanes * b_bytes);
+            const uint32_t lbar = mapa_shared(bar, 0u);
+            const int nrow = n0 + (int)cta_rank * BNL;
+            tma_load_2d_cg2(bst, &P.tm_hi, kb * kKBlk, nrow, lbar);
+            if (three) tma_load_2d_cg2(bst + b_bytes, &P.tm_lo, kb * kKBlk, nrow, lbar);
+          } else {
+            mbar_arrive_expect_tx(bar, (uint32_t)nplanes * b_bytes);
+            tma_load_2d(bst, &P.tm_hi, kb * kKBlk, n0, bar);
+            if (three) tma_load_2d(bst + b_bytes, &P.tm_lo, kb * kKBlk, n0, bar);
+          }
         }
+      }
+      if (trp) {
+        unsigned long long* c = reinterpret_cast<unsigned long long*>(P.status + 16);
+        c[8] = (unsigned long long)(clock64() - tp_all0);
+        c[9] = (unsigned long long)tp_wait;
       }
     }
   } else if (warp == kPatchWarp) {
     // ------------------------------------------------------------------ PATCH: halo patches by TMA (one thread)
     if (PATCH && lane == 0) {
-      int gp = 0;  // patches issued so far (all tiles)
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int pb = 0;
+      uint32_t empty_par = 1u;
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
         int n, h0, w0;
-        patch_tile_origin(P, tile / n_tiles, n, h0, w0);
-        for (int cb = 0; cb < P.ncb; ++cb, ++gp) {
-          const int pb = gp % P.patch_stages;
-          mbar_wait(smem_u32(&patch_empty_bar[pb]), ((uint32_t)(gp / P.patch_stages) & 1u) ^ 1u, P.status);
+        patch_tile_origin(P, CRDR_MTILE(tile), n, h0, w0);  // CG2: a tile past the end has n == d.n -> zero fill
+        for (int cb = 0; cb < P.ncb; ++cb, ++pb) {
+          if (pb == P.patch_stages) { pb = 0; empty_par ^= 1u; }
+          mbar_wait(smem_u32(&patch_empty_bar[pb]), empty_par, P.status);
           const uint32_t bar = smem_u32(&patch_full_bar[pb]);
           const uint32_t dst = smem_patch + (uint32_t)pb * patch_stage_bytes;
-          mbar_arrive_expect_tx(bar, (uint32_t)nplanes * patch_plane_bytes);
-          tma_load_4d(dst, &P.tm_in_hi, P.cb_c0[cb], w0 + P.dw_min, h0 + P.dh_min, n, bar);
-          if (three) tma_load_4d(dst + patch_plane_bytes, &P.tm_in_lo, P.cb_c0[cb], w0 + P.dw_min, h0 + P.dh_min, n, bar);
+          if (CG2) {
+            if (cta_rank == 0) mbar_arrive_expect_tx(bar, 2u * (uint32_t)nplanes * patch_plane_bytes);
+            const uint32_t lbar = mapa_shared(bar, 0u);
+            tma_load_4d_cg2(dst, &P.tm_in_hi, P.cb_c0[cb], w0 + P.dw_min, h0 + P.dh_min, n, lbar);
+            if (three) tma_load_4d_cg2(dst + patch_plane_bytes, &P.tm_in_lo, P.cb_c0[cb], w0 + P.dw_min, h0 + P.dh_min, n, lbar);
+          } else {
+            mbar_arrive_expect_tx(bar, (uint32_t)nplanes * patch_plane_bytes);
+            tma_load_4d(dst, &P.tm_in_hi, P.cb_c0[cb], w0 + P.dw_min, h0 + P.dh_min, n, bar);
+            if (three) tma_load_4d(dst + patch_plane_bytes, &P.tm_in_lo, P.cb_c0[cb], w0 + P.dw_min, h0 + P.dh_min, n, bar);
+          }
         }
       }
     }
   } else if (warp == kMmaWarp) {
-    // ------------------------------------------------------------------ MMA issue (whole warp converged, one lane issues)
-    {
-      const uint32_t idesc = umma_idesc_f16((uint32_t)BN);
-      int g = 0, gc = 0, jt = 0, gp = 0;
+    // ------------------------------------------------------------------ MMA issue (whole warp, one elected lane issues)
+    // The loop is a serial instruction stream that has to sustain one K block per few hundred cycles, so
+    // everything that varies per K block is carried incrementally (ring slot / phase, tap, chunk position), the
+    // descriptors are a constant plus a shifted shared-memory address, and all of it is warp-uniform (uniform
+    // datapath); no division, no shared-memory loads, no warp-level sync.
+    if (!CG2 || cta_rank == 0) {
+      const bool elected = elect_one();
+      const uint32_t idesc = umma_idesc_f16((uint32_t)BN, CG2 ? 256u : (uint32_t)kTileM);
       const int ntaps = d.ntaps;
-      const bool tr = P.trace && blockIdx.x == 0 && lane == 0;
-      long long t_full = 0, t_d0 = 0, t_acc = 0, t_patch = 0, t_all0 = tr ? clock64() : 0, t0 = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++jt) {
+      const bool tr = P.trace && blockIdx.x == 0 && elected;
+      long long t_full = 0, t_d0 = 0, t_acc = 0, t_patch = 0, t_mma = 0, t_commit = 0, t_all0 = tr ? clock64() : 0, t0 = 0;
+      const uint64_t desc_b = umma_desc_sw128(0u);                                            // + (addr >> 4)
+      const uint64_t desc_a = PATCH ? umma_desc_sw128_rows(0u, (uint32_t)P.pw * 128u) : desc_b;
+      const uint32_t a_planes = (uint32_t)nplanes * a_bytes;
+      int g = 0, gc = 0, jt = 0;
+      int s = 0;                 // weight / gather ring slot and its phase
+      uint32_t ring_par = 0;
+      uint32_t stage = smem_base;
+      int pb = 0;                // patch buffer and its phase
+      uint32_t patch_par = 0;
+      uint32_t patch_addr = smem_patch;
+      for (int tile = tile0; tile < num_tiles; tile += tstep, ++jt) {
         const int tb = split ? 0 : (jt & 1);
         if (jt >= TB) {
           // the epilogue of tile jt-TB must have consumed this per-tile accumulator buffer
@@ -895,10 +1045,10 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
           tc_fence_after();
         }
         const uint32_t d1 = tmem_base + kD1Base + (uint32_t)tb * kAccStride;
+        int tap = 0, ck = 0;     // tap of this K block (PATCH), position inside the D0 chunk
         for (int kb = 0; kb < nkb; ++kb, ++g) {
-          const int s = g % S;
-          const bool chunk_first = (kb % chunk_kb) == 0;
-          const bool chunk_last = ((kb + 1) % chunk_kb) == 0 || kb == nkb - 1;
+          const bool chunk_first = ck == 0;
+          const bool chunk_last = ck == chunk_kb - 1 || kb == nkb - 1;
           const int b = gc & 1;
           if (three && chunk_first && gc >= 2) {
             // the drain warps must have emptied this D0 buffer (chunk gc-2) before it is overwritten
@@ -908,61 +1058,65 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
             tc_fence_after();
           }
           uint64_t a_hi, a_lo;
-          int pb = 0;
           if (PATCH) {
             // K block kb = (channel block, tap): the A operand is the patch shifted by the tap offset
-            const int tap = kb % ntaps;
-            pb = gp % P.patch_stages;
             if (tap == 0) {
               if (tr) t0 = clock64();
-              mbar_wait(smem_u32(&patch_full_bar[pb]), (uint32_t)(gp / P.patch_stages) & 1u, P.status);
+              mbar_wait(smem_u32(&patch_full_bar[pb]), patch_par, P.status);
               if (tr) t_patch += clock64() - t0;
-              tc_fence_after();
             }
-            const uint32_t prow = (uint32_t)((s_dh[tap] - P.dh_min) * P.pw + (s_dw[tap] - P.dw_min));
-            const uint32_t pa = smem_patch + (uint32_t)pb * patch_stage_bytes + prow * 128u;
-            a_hi = umma_desc_sw128_rows(pa, (uint32_t)P.pw * 128u);
-            a_lo = umma_desc_sw128_rows(pa + patch_plane_bytes, (uint32_t)P.pw * 128u);
+            const uint32_t pa = patch_addr + P.tapoff[tap];
+            a_hi = desc_a + (uint64_t)(pa >> 4);
+            a_lo = desc_a + (uint64_t)((pa + patch_plane_bytes) >> 4);
+          } else {
+            a_hi = desc_a + (uint64_t)(stage >> 4);
+            a_lo = desc_a + (uint64_t)((stage + kAPlaneBytes) >> 4);
           }
           if (tr) t0 = clock64();
-          mbar_wait(smem_u32(&full_bar[s]), (uint32_t)(g / S) & 1u, P.status);
+          mbar_wait(smem_u32(&full_bar[s]), ring_par, P.status);
           if (tr) t_full += clock64() - t0;
           tc_fence_after();
           const uint32_t d0 = tmem_base + (uint32_t)(three ? b : tb) * kAccStride;
-          const uint32_t stage = smem_base + (uint32_t)s * stage_bytes;
-          if (!PATCH) {
-            a_hi = umma_desc_sw128(stage);
-            a_lo = umma_desc_sw128(stage + kAPlaneBytes);
-          }
-          const uint64_t b_hi = umma_desc_sw128(stage + (uint32_t)nplanes * a_bytes);
-          const uint64_t b_lo = umma_desc_sw128(stage + (uint32_t)nplanes * a_bytes + b_bytes);
-          __syncwarp();
-          if (elect_one()) {
+          const uint64_t b_hi = desc_b + (uint64_t)((stage + a_planes) >> 4);
+          const uint64_t b_lo = desc_b + (uint64_t)((stage + a_planes + b_bytes) >> 4);
+          if (tr) t0 = clock64();
+          if (elected) {
 #pragma unroll
-            for (int k = 0; k < kKBlk / 16; ++k) {
-              const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 descriptor units
-              if (three) {
-                umma_f16(d0, a_hi + adv, b_hi + adv, idesc, (chunk_first && k == 0) ? 0u : 1u);
-                umma_f16(d1, a_hi + adv, b_lo + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                // split: the second cross term accumulates in its own chain (D1b)
-                umma_f16(split ? d1 + kAccStride : d1, a_lo + adv, b_hi + adv, idesc, (split && kb == 0 && k == 0) ? 0u : 1u);
-              } else if (split) {
-                // even / odd K steps alternate between two accumulators
-                umma_f16(d0 + (uint32_t)(k & 1) * kAccStride, a_hi + adv, b_hi + adv, idesc, (kb == 0 && k < 2) ? 0u : 1u);
-              } else {
-                umma_f16(d0, a_hi + adv, b_hi + adv, idesc, (chunk_first && k == 0) ? 0u : 1u);
-              }
-            }
-            umma_commit(smem_u32(&empty_bar[s]));
-            if (PATCH && (kb % ntaps) == ntaps - 1) umma_commit(smem_u32(&patch_empty_bar[pb]));  // all taps of the block issued
-            if (chunk_last) {
-              if (three) umma_commit(smem_u32(&d0_full_bar[b]));
-              else umma_commit(smem_u32(&acc_full_bar[tb]));
+          for (int k = 0; k < kKBlk / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 descriptor units
+            if (three) {
+              umma_issue<CG2>(d0, a_hi + adv, b_hi + adv, idesc, (chunk_first && k == 0) ? 0u : 1u);
+              umma_issue<CG2>(d1, a_hi + adv, b_lo + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              // split: the second cross term accumulates in its own chain (D1b)
+              umma_issue<CG2>(split ? d1 + kAccStride : d1, a_lo + adv, b_hi + adv, idesc, (split && kb == 0 && k == 0) ? 0u : 1u);
+            } else if (split) {
+              // even / odd K steps alternate between two accumulators
+              umma_issue<CG2>(d0 + (uint32_t)(k & 1) * kAccStride, a_hi + adv, b_hi + adv, idesc, (kb == 0 && k < 2) ? 0u : 1u);
+            } else {
+              umma_issue<CG2>(d0, a_hi + adv, b_hi + adv, idesc, (chunk_first && k == 0) ? 0u : 1u);
             }
           }
-          __syncwarp();
-          if (PATCH && (kb % ntaps) == ntaps - 1) ++gp;
-          if (three && chunk_last) ++gc;
+          }
+          if (tr) { const long long t1 = clock64(); t_mma += t1 - t0; t0 = t1; }
+          if (elected) umma_done<CG2>(smem_u32(&empty_bar[s]));
+          if (PATCH) {
+            if (++tap == ntaps) {  // all taps of the channel block issued: the patch buffer may be refilled
+              tap = 0;
+              if (elected) umma_done<CG2>(smem_u32(&patch_empty_bar[pb]));
+              patch_addr += patch_stage_bytes;
+              if (++pb == P.patch_stages) { pb = 0; patch_par ^= 1u; patch_addr = smem_patch; }
+            }
+          }
+          if (chunk_last) {
+            if (elected) umma_done<CG2>(smem_u32(three ? &d0_full_bar[b] : &acc_full_bar[tb]));
+            if (three) ++gc;
+            ck = 0;
+          } else {
+            ++ck;
+          }
+          if (tr) t_commit += clock64() - t0;
+          stage += stage_bytes;
+          if (++s == S) { s = 0; ring_par ^= 1u; stage = smem_base; }
         }
       }
       if (tr) {  // bring-up counters (cycles): total, wait full, wait d0_empty, wait acc_empty, wait patch, k blocks
@@ -970,15 +1124,20 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
         c[0] = (unsigned long long)(clock64() - t_all0);
         c[1] = (unsigned long long)t_full; c[2] = (unsigned long long)t_d0; c[3] = (unsigned long long)t_acc;
         c[4] = (unsigned long long)t_patch; c[5] = (unsigned long long)g;
+        c[6] = (unsigned long long)t_mma; c[7] = (unsigned long long)t_commit;
       }
     }
    }
   }
+  tc_fence_before();
   __syncthreads();
+  if (CG2) cluster_sync_all();  // the peer's TMEM and barriers are in use until both CTAs are done
   if (warp == kTmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512u);
+    if (CG2) tmem_dealloc_cg2(tmem_base, 512u);
+    else tmem_dealloc(tmem_base, 512u);
   }
+#undef CRDR_MTILE
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1299,6 +1458,19 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
   const int maxch = three ? ((d.tile_n / 16 + 1) / 2) : 0;
   typedef void (*KernelFn)(const ConvKParams);
   KernelFn fn = nullptr;
+  // CTA-pair form (cta_group::2, M = 256 per MMA) for the patch variant; CRDR_CONV_CG2=0 falls back to single CTAs
+  static int cg2_env = -1;
+  if (cg2_env < 0) { const char* e = getenv("CRDR_CONV_CG2"); cg2_env = e ? atoi(e) : 1; }
+  const bool cg2 = use_patch && cg2_env != 0;
+  if (cg2) {
+    switch (maxch) {
+      case 0: fn = conv_tcgen05_kernel<0, true, true>; break;
+      case 1: fn = conv_tcgen05_kernel<1, true, true>; break;
+      case 2: fn = conv_tcgen05_kernel<2, true, true>; break;
+      case 3: fn = conv_tcgen05_kernel<3, true, true>; break;
+      default: fn = conv_tcgen05_kernel<4, true, true>; break;
+    }
+  } else
   switch (maxch * 2 + (use_patch ? 1 : 0)) {
     case 0: fn = conv_tcgen05_kernel<0, false>; break;
     case 1: fn = conv_tcgen05_kernel<0, true>; break;
@@ -1311,9 +1483,9 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     case 8: fn = conv_tcgen05_kernel<4, false>; break;
     default: fn = conv_tcgen05_kernel<4, true>; break;
   }
-  const int variant = maxch * 2 + (use_patch ? 1 : 0);
+  const int variant = cg2 ? 10 + maxch : maxch * 2 + (use_patch ? 1 : 0);
   static std::mutex attr_mutex;
-  static bool attr_done[10] = {false, false, false, false, false, false, false, false, false, false};
+  static bool attr_done[16] = {false};
   static int num_sms = 0;
   {
     std::lock_guard<std::mutex> lk(attr_mutex);
@@ -1344,6 +1516,7 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     P.pw = kPatchTW + dw_max - dw_min;
     P.ncb = ncb;
     for (int i = 0; i < ncb; ++i) P.cb_c0[i] = cb_c0[i];
+    for (int t = 0; t < d.ntaps; ++t) P.tapoff[t] = (uint32_t)((d.dh[t] - dh_min) * P.pw + (d.dw[t] - dw_min)) * 128u;
     P.tiles_h = (d.hb + kPatchTH - 1) / kPatchTH;
     P.tiles_w = (d.wb + kPatchTW - 1) / kPatchTW;
     if (P.ph > 64 || P.pw > 64 || d.in.cs < 64) {
@@ -1352,7 +1525,7 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     }
     const uint32_t plane = (uint32_t)(P.ph * P.pw) * 128u;
     const uint32_t pstage = (plane * (uint32_t)P.nplanes + 1023u) & ~1023u;
-    const uint32_t bstage = (uint32_t)P.nplanes * (uint32_t)d.tile_n * 128u;
+    const uint32_t bstage = (uint32_t)P.nplanes * (uint32_t)(cg2 ? d.tile_n / 2 : d.tile_n) * 128u;
     // two patch buffers when at least three weight stages still fit, else one
     P.patch_stages = (2 * pstage + 3 * bstage + 1024 <= kDynSmemMax && ncb > 1) ? 2 : 1;
     patch_total = (uint32_t)P.patch_stages * pstage;
@@ -1363,7 +1536,8 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
       if (rc) return rc;
     }
   }
-  const uint32_t stage_bytes = (uint32_t)P.nplanes * ((use_patch ? 0u : kAPlaneBytes) + (uint32_t)d.tile_n * 128u);
+  const int b_rows = cg2 ? d.tile_n / 2 : d.tile_n;  // weight-tile rows per CTA
+  const uint32_t stage_bytes = (uint32_t)P.nplanes * ((use_patch ? 0u : kAPlaneBytes) + (uint32_t)b_rows * 128u);
   if (patch_total + 2 * stage_bytes + 1024 > kDynSmemMax) {
     set_error("conv2d: tile_n=%d does not leave two pipeline stages (patch %u B)", d.tile_n, patch_total);
     return CRDR_ERR_BAD_SHAPE;
@@ -1386,16 +1560,40 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
   if (P.split < 0) P.split = P.nkb >= 16;  // long accumulate chains: independent accumulators beat epilogue overlap
   P.use_tma = d.engine == CRDR_ENGINE_TCGEN05;
   if (P.use_tma) {
-    int rc = weight_tensor_map(d.w_hi, d.k_pad, d.cout_pad, d.tile_n, &P.tm_hi);
+    int rc = weight_tensor_map(d.w_hi, d.k_pad, d.cout_pad, b_rows, &P.tm_hi);
     if (rc) return rc;
     if (three) {
-      rc = weight_tensor_map(d.w_lo, d.k_pad, d.cout_pad, d.tile_n, &P.tm_lo);
+      rc = weight_tensor_map(d.w_lo, d.k_pad, d.cout_pad, b_rows, &P.tm_lo);
       if (rc) return rc;
     }
   }
   const uint32_t smem = patch_total + (uint32_t)stages * stage_bytes + res_total + 1024;
   const int64_t m_tiles = use_patch ? (int64_t)d.n * P.tiles_h * P.tiles_w : (m_total + kTileM - 1) / kTileM;
   const int64_t num_tiles = m_tiles * (d.cout_pad / d.tile_n);
+  if (cg2) {
+    // persistent CTA pairs: one cluster of two per TPC
+    const int64_t pair_tiles = ((m_tiles + 1) / 2) * (d.cout_pad / d.tile_n);
+    const int64_t pairs = pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(kThreadsPatch);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, P);
+    if (e != cudaSuccess) {
+      set_error("conv2d: cluster launch failed: %s", cudaGetErrorString(e));
+      return CRDR_ERR_CUDA;
+    }
+    return check_launch("conv_tcgen05_kernel(cg2)");
+  }
   const unsigned grid = (unsigned)(num_tiles < num_sms ? num_tiles : num_sms);  // persistent: one CTA per SM
   fn<<<grid, use_patch ? kThreadsPatch : kThreads, smem, stream>>>(P);
   return check_launch("conv_tcgen05_kernel");

@@ -41,10 +41,10 @@ def bench(n, cin, cout, h, w, k, stride, tr, prec, tile_n=None, epi=0, iters=10)
     nv.status_check()
     import os, ctypes
     if os.environ.get("CRDR_CONV_TRACE"):
-        c = (ctypes.c_ulonglong * 6)()
+        c = (ctypes.c_ulonglong * 10)()
         nv.lib().crdr_debug_counters(c)
-        tot, full, d0, acc, patch, kbs = [int(v) for v in c]
-        print(f"   MMA thread (CTA0): {tot} cyc total, {kbs} k-blocks -> {tot/max(kbs,1):.0f} cyc/kb; waits: full {full/tot:.0%} d0_empty {d0/tot:.0%} acc_empty {acc/tot:.0%} patch {patch/tot:.0%}")
+        tot, full, d0, acc, patch, kbs, tmma, tcommit, ptot, pwait = [int(v) for v in c]
+        print(f"   MMA thread (CTA0): {tot} cyc total, {kbs} k-blocks -> {tot/max(kbs,1):.0f} cyc/kb; waits: full {full/tot:.0%} d0_empty {d0/tot:.0%} acc_empty {acc/tot:.0%} patch {patch/tot:.0%}; issue mma {tmma/tot:.0%} commit {tcommit/tot:.0%}; B producer {ptot} cyc, empty wait {pwait/max(ptot,1):.0%}")
 
 
 if __name__ == "__main__":
