@@ -34,6 +34,7 @@ constexpr int kTileM = 128;
 constexpr int kKBlk = 64;                  // fp16 elements per K block = one 128-byte swizzle row
 constexpr uint32_t kAPlaneBytes = kTileM * 128;
 constexpr int kMaxStages = 10;
+constexpr int kMaxPatchStages = 8;         // PATCH mode: halo-patch ring (deep for small-K launches: a patch is a whole tile's A operand)
 constexpr int kThreads = 512;              // gather variant: warps 0-3 gather, 4-11 drain/epilogue, 12 TMA + TMEM alloc, 13 MMA, 14-15 idle
 constexpr int kThreadsPatch = 384;         // patch variant: warps 0-7 drain/epilogue, 8 TMA + TMEM alloc, 9 MMA, 10 halo patches, 11 idle
                                            // setmaxnreg: 128 * (216 + 216 + 56) <= 65536
@@ -602,8 +603,8 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
   __shared__ __align__(8) uint64_t d0_empty_bar[2];   // F16X3: drain warps -> MMA, the D0 buffer may be overwritten
   __shared__ __align__(8) uint64_t acc_full_bar[2];   // F16X1: MMA -> epilogue, the tile accumulator is complete
   __shared__ __align__(8) uint64_t acc_empty_bar[2];  // epilogue -> MMA, the tile accumulator (D0 / D1) was consumed
-  __shared__ __align__(8) uint64_t patch_full_bar[2];
-  __shared__ __align__(8) uint64_t patch_empty_bar[2];
+  __shared__ __align__(8) uint64_t patch_full_bar[kMaxPatchStages];
+  __shared__ __align__(8) uint64_t patch_empty_bar[kMaxPatchStages];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_dh[CRDR_MAX_TAPS + 1], s_dw[CRDR_MAX_TAPS + 1];
   __shared__ __align__(16) float s_par[4 * kMaxCout];
@@ -651,7 +652,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
     s_dh[d.ntaps] = 0;  // tap index of the zero-padded K tail
     s_dw[d.ntaps] = 0;
     const uint32_t full_count = PATCH ? 1u : (P.use_tma ? 129u : 128u);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kMaxPatchStages; ++b) {
       mbar_init(smem_u32(&patch_full_bar[b]), 1u);
       mbar_init(smem_u32(&patch_empty_bar[b]), 1u);
     }
@@ -1504,6 +1505,12 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
       if (num_sms <= 0) num_sms = 148;
     }
   }
+  // residual staging: one private slot per output row (pitch padded by 16 B against bank conflicts)
+  uint32_t res_need = 0, res_pitch = 0;
+  if (d.mode != CRDR_EPI_NONE && P.fast_epi) {
+    res_pitch = (uint32_t)d.tile_n * (three ? 4u : 2u) + 16u;
+    res_need = kTileM * res_pitch;
+  }
   uint32_t patch_total = 0;
   if (use_patch) {
     int dh_min = 127, dh_max = -127, dw_min = 127, dw_max = -127;
@@ -1526,8 +1533,18 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     const uint32_t plane = (uint32_t)(P.ph * P.pw) * 128u;
     const uint32_t pstage = (plane * (uint32_t)P.nplanes + 1023u) & ~1023u;
     const uint32_t bstage = (uint32_t)P.nplanes * (uint32_t)(cg2 ? d.tile_n / 2 : d.tile_n) * 128u;
-    // two patch buffers when at least three weight stages still fit, else one
-    P.patch_stages = (2 * pstage + 3 * bstage + 1024 <= kDynSmemMax && ncb > 1) ? 2 : 1;
+    // Patch ring depth: the patches of about two tiles in flight (small-K launches are bound by the load latency
+    // of the next tile's patch, not by the MMAs), as long as four weight stages still fit; at least one.
+    {
+      const uint32_t budget = kDynSmemMax - 1024 - res_need;
+      int want = 2 * ncb;
+      if (want < 2) want = 2;
+      if (want > kMaxPatchStages) want = kMaxPatchStages;
+      int ps = want;
+      while (ps > 1 && (uint32_t)ps * pstage + 4 * bstage > budget) --ps;
+      if (ps == 1 && pstage + 2 * bstage > budget) ps = 1;
+      P.patch_stages = ps;
+    }
     patch_total = (uint32_t)P.patch_stages * pstage;
     int rc = input_tensor_map(d.in.hi, d.in.cs, d.win, d.hin, d.n, P.pw, P.ph, &P.tm_in_hi);
     if (rc) return rc;
@@ -1542,16 +1559,11 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     set_error("conv2d: tile_n=%d does not leave two pipeline stages (patch %u B)", d.tile_n, patch_total);
     return CRDR_ERR_BAD_SHAPE;
   }
-  // residual staging: one private slot per output row (pitch padded by 16 B against bank conflicts)
   uint32_t res_total = 0;
   P.res_stage_pitch = 0;
-  if (d.mode != CRDR_EPI_NONE && P.fast_epi) {
-    const uint32_t row_bytes = (uint32_t)d.tile_n * (three ? 4u : 2u);
-    const uint32_t pitch = row_bytes + 16u;
-    if (patch_total + 2 * stage_bytes + 1024 + kTileM * pitch <= kDynSmemMax) {
-      P.res_stage_pitch = (int32_t)pitch;
-      res_total = kTileM * pitch;
-    }
+  if (res_need && patch_total + 2 * stage_bytes + 1024 + res_need <= kDynSmemMax) {
+    P.res_stage_pitch = (int32_t)res_pitch;
+    res_total = res_need;
   }
   int stages = (int)((kDynSmemMax - 1024 - patch_total - res_total) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;

@@ -134,6 +134,15 @@ class CodecEngine:
         yhat32 = self.charm.decode(T, self.gp, lambda s0, cnt, idx: y_sym)
         return self.synthesis(yhat32, q, beta, size), yhat32, z_hat
 
+    def prepare(self, q=None, beta=None):
+        """Fill the per-quality / per-beta vector caches on the current stream (before work fans out to side streams)."""
+        if q is not None:
+            for net in (self.ga, self.gs):
+                for gn in net.gains:
+                    gn.vectors(q)
+        if beta is not None:
+            self.gs.cond_vectors(beta)
+
     # ------------------------------------------------------------------ small reductions / layout
     def bits(self, lik):
         n = lik.shape[0]
@@ -341,11 +350,53 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
                     bpp=y_bpp + z_bpp, y_q_likelihood=a["y_lik"], z_q_likelihood=a["z_lik"], qbpp=y_bpp + z_bpp)
 
     # -- codec -------------------------------------------------------------------------------------
-    @torch.no_grad()
-    def compress_batch(self, real_images, rate_ind, return_tensors=False, coder_threads=0):
-        """N images of one shape -> list of N result dicts (same keys as ``compress``)."""
-        if not hasattr(self, "header_handler"):
-            raise RuntimeError("call codec_setup() before compress()")
+    # Host entropy coding and device arithmetic of one call overlap: a batch is cut into `pipeline_chunks` chunks,
+    # each driven by its own host thread on its own CUDA stream.  While one chunk sits in the host coder (ctypes call,
+    # GIL released) or waits for a copy, the device works on the other chunk.  Results are per image and independent of
+    # the chunking (deterministic kernels, one rANS stream per image).
+    pipeline_chunks = 2
+    pipeline_min_images = 8
+
+    def _chunks(self, n):
+        k = self.pipeline_chunks if n >= self.pipeline_min_images else 1
+        k = max(1, min(k, n))
+        edges = [round(i * n / k) for i in range(k + 1)]
+        return [(edges[i], edges[i + 1]) for i in range(k)]
+
+    def _run_chunks(self, chunks, fn):
+        """fn(k, lo, hi) for every chunk, concurrently on side streams; returns the list of results."""
+        if len(chunks) == 1:
+            return [fn(0, *chunks[0])]
+        dev = self.engine().device
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_side_streams") or len(self._side_streams) < len(chunks):
+            self._side_streams = [torch.cuda.Stream(device=dev) for _ in chunks]
+        if not hasattr(self, "_pool") or self._pool._max_workers < len(chunks):
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=len(chunks), thread_name_prefix="crdr-chunk")
+
+        def work(k, lo, hi):
+            torch.cuda.set_device(dev)
+            st = self._side_streams[k]
+            st.wait_stream(main)
+            with torch.cuda.stream(st), torch.no_grad():
+                r = fn(k, lo, hi)
+            return r
+
+        futs = [self._pool.submit(work, k, lo, hi) for k, (lo, hi) in enumerate(chunks)]
+        res = [f.result() for f in futs]
+        for st in self._side_streams[:len(chunks)]:
+            main.wait_stream(st)
+        return res
+
+    @staticmethod
+    def _on_main(t):
+        """A tensor produced on a side stream that the caller will use on the current stream."""
+        if t is not None and t.is_cuda:
+            t.record_stream(torch.cuda.current_stream(t.device))
+        return t
+
+    def _compress_chunk(self, tag, real_images, rate_ind, return_tensors, coder_threads):
         eng = self.engine()
         q = self._q(rate_ind)
         x = self._to_device(real_images)
@@ -355,8 +406,10 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
         y_max = eng.max_abs(a["yhat32"])
         # ---- device -> host boundary (the reference moves y, z here; we move symbols and table indexes)
         pp = self._pinned
-        z_sym, y_sym, y_idx = pp.fetch("z_sym", a["z_sym"]), pp.fetch("y_sym", a["y_sym"]), pp.fetch("y_idx", a["y_idx"])
-        y_bits, z_bits, y_max = pp.fetch("y_bits", y_bits), pp.fetch("z_bits", z_bits), pp.fetch("y_max", y_max)
+        z_sym, y_sym, y_idx = (pp.fetch(tag + "z_sym", a["z_sym"]), pp.fetch(tag + "y_sym", a["y_sym"]),
+                               pp.fetch(tag + "y_idx", a["y_idx"]))
+        y_bits, z_bits, y_max = (pp.fetch(tag + "y_bits", y_bits), pp.fetch(tag + "z_bits", z_bits),
+                                 pp.fetch(tag + "y_max", y_max))
         nv.status_check()  # synchronises the stream: the pinned buffers are valid from here
         z_sym, y_sym, y_idx = z_sym.numpy(), y_sym.numpy(), y_idx.numpy()
         y_bits, z_bits, y_max = y_bits.numpy().copy(), z_bits.numpy().copy(), y_max.numpy().copy()
@@ -374,16 +427,65 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
                  "pred_y_bit": float(y_bits[i]), "pred_y_bpp": float(y_bits[i]) / (h * w),
                  "pred_z_bit": float(z_bits[i]), "pred_z_bpp": float(z_bits[i]) / (h * w)}
             if return_tensors:
-                r.update(z_hat=a["z_hat"][i:i + 1], y_hat=y_hat[i:i + 1], z_likelihood=a["z_lik"][i:i + 1],
-                         y_likelihood=a["y_lik"][i:i + 1])
+                r.update(z_hat=self._on_main(a["z_hat"])[i:i + 1], y_hat=self._on_main(y_hat)[i:i + 1],
+                         z_likelihood=self._on_main(a["z_lik"])[i:i + 1], y_likelihood=self._on_main(a["y_lik"])[i:i + 1])
             out.append(r)
         return out
+
+    @torch.no_grad()
+    def compress_batch(self, real_images, rate_ind, return_tensors=False, coder_threads=0):
+        """N images of one shape -> list of N result dicts (same keys as ``compress``)."""
+        if not hasattr(self, "header_handler"):
+            raise RuntimeError("call codec_setup() before compress()")
+        n = real_images.shape[0]
+        with torch.cuda.device(self.engine().device):
+            self.engine().prepare(q=self._q(rate_ind))
+            res = self._run_chunks(self._chunks(n), lambda k, lo, hi: self._compress_chunk(
+                f"c{k}_", real_images[lo:hi], rate_ind, return_tensors, coder_threads))
+        return [r for chunk in res for r in chunk]
 
     @torch.no_grad()
     def compress(self, real_images, rate_ind):
         n = real_images.shape[0]
         assert n == 1, f"In compress mode, batchsize must be 1, but {n}"
         return self.compress_batch(real_images, rate_ind, return_tensors=True)[0]
+
+    def _decompress_chunk(self, tag, string_lists, h, w, q, beta, coder_threads):
+        eng = self.engine()
+        n = len(string_lists)
+        hp, wp = eng.padded(h, w)
+        hz, wz = hp // self.model_stride, wp // self.model_stride
+        dev = eng.device
+        zi = _channel_indexes(self.zC, hz, wz)
+        zt, yt = self.entropy_model_z.coder_tables(), self.entropy_model_y.coder_tables()
+        z_dec = [rans.Decoder(sl[1]) for sl in string_lists]
+        z_host = self._pinned.get(tag + "z_dec", (n, self.zC, hz, wz), torch.int32)
+        zv = z_host.numpy().reshape(n, -1)
+        rans.decode_batch(z_dec, [zi] * n, zt, coder_threads, outs=[zv[i] for i in range(n)])
+        z_sym = z_host.to(dev, non_blocking=True)
+        T, z_hat = eng.hyper_from_symbols(z_sym)
+        y_dec = [rans.Decoder(sl[2]) for sl in string_lists]
+        hy, wy = T.h, T.w
+        y_sym = torch.empty((n, self.yC, hy, wy), dtype=torch.int32, device=dev)
+        sc = eng.charm.sc
+
+        def source(s0, cnt, idx):
+            c0, c1 = s0 * sc, (s0 + cnt) * sc
+            # device -> host: table indexes of this group (pinned, one sync)
+            ix_host = self._pinned.fetch(f"{tag}y_idx_{cnt}", idx[:, c0:c1].contiguous())
+            torch.cuda.current_stream().synchronize()
+            ix = ix_host.numpy()
+            sym_host = self._pinned.get(f"{tag}y_sym_{cnt}", (n, c1 - c0, hy, wy), torch.int32)
+            sv = sym_host.numpy().reshape(n, -1)
+            rans.decode_batch(y_dec, [ix[i] for i in range(n)], yt, coder_threads, outs=[sv[i] for i in range(n)])
+            y_sym[:, c0:c1].copy_(sym_host, non_blocking=True)  # host -> device: decoded symbols
+            return y_sym
+
+        yhat32 = eng.charm.decode(T, eng.gp, source)
+        img = eng.synthesis(yhat32, q, beta, (h, w))
+        y_hat = eng.to_nchw(yhat32)
+        nv.status_check()
+        return img, z_hat, y_hat
 
     @torch.no_grad()
     def decompress_batch(self, string_lists, beta=0.0, coder_threads=0):
@@ -397,41 +499,14 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
             raise ValueError("decompress_batch needs streams of one image size and one quality index")
         h, w = heads[0]["img_size"]
         q = heads[0]["rate_ind"]
-        eng = self.engine()
         n = len(string_lists)
-        hp, wp = eng.padded(h, w)
-        hz, wz = hp // self.model_stride, wp // self.model_stride
-        dev = eng.device
-        with torch.cuda.device(dev):
-            zi = _channel_indexes(self.zC, hz, wz)
-            zt, yt = self.entropy_model_z.coder_tables(), self.entropy_model_y.coder_tables()
-            z_dec = [rans.Decoder(sl[1]) for sl in string_lists]
-            z_host = self._pinned.get("z_dec", (n, self.zC, hz, wz), torch.int32)
-            z_host.numpy().reshape(n, -1)[:] = np.stack(rans.decode_batch(z_dec, [zi] * n, zt, coder_threads))
-            z_sym = z_host.to(dev, non_blocking=True)
-            T, z_hat = eng.hyper_from_symbols(z_sym)
-            y_dec = [rans.Decoder(sl[2]) for sl in string_lists]
-            hy, wy = T.h, T.w
-            y_sym = torch.empty((n, self.yC, hy, wy), dtype=torch.int32, device=dev)
-            sc = eng.charm.sc
-
-            def source(s0, cnt, idx):
-                c0, c1 = s0 * sc, (s0 + cnt) * sc
-                # device -> host: table indexes of this group (pinned, one sync)
-                ix_host = self._pinned.fetch(f"y_idx_{cnt}", idx[:, c0:c1].contiguous())
-                torch.cuda.current_stream().synchronize()
-                ix = ix_host.numpy()
-                syms = rans.decode_batch(y_dec, [ix[i] for i in range(n)], yt, coder_threads)
-                sym_host = self._pinned.get(f"y_sym_{cnt}", (n, c1 - c0, hy, wy), torch.int32)
-                sym_host.numpy().reshape(n, -1)[:] = np.stack(syms)
-                y_sym[:, c0:c1].copy_(sym_host, non_blocking=True)  # host -> device: decoded symbols
-                return y_sym
-
-            yhat32 = eng.charm.decode(T, eng.gp, source)
-            img = eng.synthesis(yhat32, q, beta, (h, w))
-            y_hat = eng.to_nchw(yhat32)
-            nv.status_check()
-        return img, z_hat, y_hat
+        with torch.cuda.device(self.engine().device):
+            self.engine().prepare(q=q, beta=beta)
+            res = self._run_chunks(self._chunks(n), lambda k, lo, hi: self._decompress_chunk(
+                f"d{k}_", string_lists[lo:hi], h, w, q, beta, coder_threads))
+            if len(res) == 1:
+                return res[0]
+            return tuple(torch.cat([self._on_main(r[j]) for r in res], dim=0) for j in range(3))
 
     @torch.no_grad()
     def decompress(self, string_list, beta=0.0):

@@ -127,10 +127,15 @@ class Decoder:
             pass
 
 
-def decode_batch(decoders, indexes_list, tables, threads=0):
+def decode_batch(decoders, indexes_list, tables, threads=0, outs=None):
+    """``outs``: optional list of writable contiguous int32 arrays (e.g. views of a pinned buffer) to decode into."""
     cnt = len(decoders)
     ii = [_i32(i).reshape(-1) for i in indexes_list]
-    outs = [np.empty(i.size, dtype=np.int32) for i in ii]
+    if outs is None:
+        outs = [np.empty(i.size, dtype=np.int32) for i in ii]
+    else:
+        assert len(outs) == cnt and all(o.dtype == np.int32 and o.flags.c_contiguous and o.size == i.size
+                                        for o, i in zip(outs, ii))
     PP = C.c_void_p * cnt
     n = (C.c_int64 * cnt)(*[i.size for i in ii])
     rc = lib().crdr_rans_decode_batch(cnt, PP(*[d._h for d in decoders]), PP(*[i.ctypes.data for i in ii]), n,
