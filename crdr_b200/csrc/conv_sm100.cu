@@ -57,7 +57,7 @@ struct alignas(64) ConvKParams {
   uint32_t tapoff[CRDR_MAX_TAPS];  // PATCH: byte offset of a tap's start row inside the halo patch
   int32_t m_total, nkb, cin, k_real, nplanes, stages, tmem_cols, use_tma;
   int32_t vec_planes_out, vec_f32_out, vec_res_planes, vec_res_f32, vec_trunk;
-  int32_t has_bias, has_add, has_affine, chunk_kb, trace, split, fast_epi, res_stage_pitch;
+  int32_t has_bias, has_add, has_affine, chunk_kb, trace, split, fast_epi, res_stage_pitch, out_stage_pitch, dbg;
   uint32_t* status;
 };
 
@@ -75,6 +75,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__constant__ uint32_t g_wait_hint_ns = 1000000u;  // CRDR_WAIT_HINT_NS (tuning knob)
 // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint
 // expires) instead of burning issue slots that the epilogue warps of the same SM sub-partition need.
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
@@ -84,7 +85,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(1000000u)
+      : "r"(bar), "r"(parity), "r"(g_wait_hint_ns)
       : "memory");
   return ok;
 }
@@ -413,9 +414,15 @@ __device__ __noinline__ void epi_finish_generic(const ConvKParams* Pp, int64_t o
 
 // Hot path: a full 16-channel chunk with every operand vector-aligned (P.fast_epi); residual / trunk operands were
 // preloaded into registers (rr / rt).
+__device__ __forceinline__ void st_shared16(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// ost != 0: the fp16 planes of this chunk go to the warp's staging tile in shared memory (32 bytes at `ost`, the lo
+// plane `ost_plane` bytes further) and are written to global memory by the warp's coalesced copy-out.
 template <int NR>
 __device__ __forceinline__ void epi_finish(const ConvKParams& P, int64_t opix, int co0, const float (&acc)[16],
-                                           const uint4 (&rr)[NR], const uint4 (&rt)[NR], const float* s_par) {
+                                           const uint4 (&rr)[NR], const uint4 (&rt)[NR], const float* s_par,
+                                           uint32_t ost = 0u, uint32_t ost_plane = 0u) {
   const crdr_conv_desc& d = P.d;
   float res[16], trunk[16];
 #pragma unroll
@@ -503,14 +510,23 @@ __device__ __forceinline__ void epi_finish(const ConvKParams& P, int64_t opix, i
         lw[i] = *reinterpret_cast<const uint32_t*>(&l);
       }
     }
-    const int64_t o = opix * d.out.cs + d.out.coff + co0;
-    __half* ph = (__half*)d.out.hi + o;
-    ((uint4*)ph)[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    ((uint4*)ph)[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-    if (want_lo) {
-      __half* pl = (__half*)d.out.lo + o;
-      ((uint4*)pl)[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-      ((uint4*)pl)[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+    if (ost) {
+      st_shared16(ost, hw[0], hw[1], hw[2], hw[3]);
+      st_shared16(ost + 16u, hw[4], hw[5], hw[6], hw[7]);
+      if (want_lo) {
+        st_shared16(ost + ost_plane, lw[0], lw[1], lw[2], lw[3]);
+        st_shared16(ost + ost_plane + 16u, lw[4], lw[5], lw[6], lw[7]);
+      }
+    } else {
+      const int64_t o = opix * d.out.cs + d.out.coff + co0;
+      __half* ph = (__half*)d.out.hi + o;
+      ((uint4*)ph)[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      ((uint4*)ph)[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+      if (want_lo) {
+        __half* pl = (__half*)d.out.lo + o;
+        ((uint4*)pl)[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        ((uint4*)pl)[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+      }
     }
   }
 }
@@ -631,6 +647,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
   const uint32_t smem_patch = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_base = smem_patch + (PATCH ? (uint32_t)P.patch_stages * patch_stage_bytes : 0u);
   const uint32_t smem_res = smem_base + (uint32_t)P.stages * stage_bytes;  // residual staging slots (128 rows)
+  const uint32_t smem_ost = smem_res + (uint32_t)kTileM * (uint32_t)P.res_stage_pitch;  // output staging (per warp)
   const int nkb = P.nkb;
   const int n_tiles = d.cout_pad / BN;
   const int m_tiles = PATCH ? d.n * P.tiles_h * P.tiles_w : (P.m_total + kTileM - 1) / kTileM;
@@ -827,40 +844,129 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
     const uint32_t my_slot = smem_res + (uint32_t)row * (uint32_t)P.res_stage_pitch + (uint32_t)(ch_begin * NR * 16);
     float total[three ? MAXCH * 16 : 1];
     uint32_t r0[16], r1[16];
-    uint4 rres[KC][NR];
     int gc = 0;  // D0 chunks seen so far (all tiles)
 
-#define CRDR_ROW_PIXEL(TILE) (PATCH ? out_pixel_of_patch_row(P, CRDR_MTILE(TILE), row) \
-                                    : out_pixel_of_row(d, ((TILE) / n_tiles) * kTileM + row, P.m_total))
-    // cp.async the residual operands of this thread's row / column range of `tile` into its slot
-    auto stage_issue = [&](int tile) {
-      if (staged && tile < num_tiles) {
-        const int64_t op = CRDR_ROW_PIXEL(tile);
-        if (op >= 0) {
-          const int c0 = (tile % n_tiles) * BN + ch_begin * 16;
-          const int nmine = ch_end - ch_begin;
-          if (d.res_f32) {
-            const float* src = d.res_f32 + op * d.res_f32_cs + d.res_f32_coff + c0;
-            for (int i = 0; i < nmine * 4; ++i) cp_async16(my_slot + (uint32_t)i * 16u, src + 4 * i, 16u);
-          } else {
-            const int64_t o = op * d.res.cs + d.res.coff + c0;
-            const __half* hi = (const __half*)d.res.hi + o;
-            const __half* lo = (const __half*)d.res.lo + o;
-            for (int c = 0; c < nmine; ++c) {
-              const uint32_t dst = my_slot + (uint32_t)(c * NR) * 16u;
-              cp_async16(dst, hi + 16 * c, 16u);
-              cp_async16(dst + 16u, hi + 16 * c + 8, 16u);
-              if (NR == 4 && d.res.lo) {
-                cp_async16(dst + 32u, lo + 16 * c, 16u);
-                cp_async16(dst + 48u, lo + 16 * c + 8, 16u);
-              }
-            }
+    // Tile cursor: (N tile, image, tile row, tile column) of the current tile, advanced by the persistent schedule's
+    // stride with adds and carries only (the per-tile integer divisions were ~25 % of the epilogue's instructions).
+    struct Cursor { int tile, nt, n, th, tw; };
+    const int m_per = CG2 ? 2 : 1;                                  // M tiles per schedule step in the M direction
+    const int step_nt = tstep % n_tiles;
+    const int step_m = (tstep / n_tiles) * m_per;
+    const int tw_div = PATCH ? P.tiles_w : 1, th_div = PATCH ? P.tiles_h : 1;
+    const int a_tw = step_m % tw_div, a_th = (step_m / tw_div) % th_div, a_n = (step_m / tw_div) / th_div;
+    auto cursor_at = [&](int tile) {
+      Cursor c;
+      c.tile = tile;
+      c.nt = tile % n_tiles;
+      const int mt = CRDR_MTILE(tile);
+      c.tw = mt % tw_div;
+      c.th = (mt / tw_div) % th_div;
+      c.n = (mt / tw_div) / th_div;
+      return c;
+    };
+    auto cursor_advance = [&](Cursor& c) {
+      c.tile += tstep;
+      if (!PATCH) return;
+      c.nt += step_nt;
+      int extra = 0;
+      if (c.nt >= n_tiles) { c.nt -= n_tiles; extra = m_per; }
+      c.tw += a_tw;
+      if (c.tw >= tw_div) { c.tw -= tw_div; ++c.th; }
+      c.th += a_th;
+      if (c.th >= th_div) { c.th -= th_div; ++c.n; }
+      c.n += a_n;
+      for (; extra > 0; --extra)
+        if (++c.tw == tw_div) { c.tw = 0; if (++c.th == th_div) { c.th = 0; ++c.n; } }
+    };
+    // output pixel (linear NHW index) of this thread's row in the cursor's tile; -1 outside the tensor
+    auto cursor_pixel = [&](const Cursor& c) -> int64_t {
+      if (c.tile >= num_tiles) return -1;
+      if (!PATCH) return out_pixel_of_row(d, (c.tile / n_tiles) * kTileM + row, P.m_total);
+      const int bh = c.th * kPatchTH + (row >> 3), bw = c.tw * kPatchTW + (row & 7);
+      if (bh >= d.hb || bw >= d.wb || c.n >= d.n) return -1;
+      return ((int64_t)c.n * d.hout + (bh * d.out_stride + d.out_ph)) * d.wout + (bw * d.out_stride + d.out_pw);
+    };
+    // Global <-> shared traffic of the epilogue is warp-cooperative: a lane that moved only its own row's 16-byte pieces
+    // touched 32 different 128-byte lines per instruction and the LSU (one line per cycle) became the limit of every
+    // memory-bound layer (measured ~1.3 TB/s).  Instead the 16-byte pieces of the warp's 32 rows x column range are
+    // dealt out lane by lane in memory order (consecutive lanes = consecutive pieces of a row), staged in shared memory
+    // in the per-row layout the owning lanes use, and handed over with __syncwarp().
+    const int nmine = ch_end - ch_begin;
+    const uint32_t warp_slot0 = smem_res + (uint32_t)(q * 32) * (uint32_t)P.res_stage_pitch + (uint32_t)(ch_begin * NR * 16);
+    // walker over pieces i = j * 32 + lane of a [32 rows][ppr pieces] block: (row, p) advance without division
+    struct Walk { int row0, p0, drow, dp, ppr; };
+    auto make_walk = [&](int ppr) {
+      Walk w;
+      w.ppr = ppr > 0 ? ppr : 1;
+      w.row0 = lane / w.ppr; w.p0 = lane % w.ppr; w.drow = 32 / w.ppr; w.dp = 32 % w.ppr;
+      return w;
+    };
+    const Walk wk_planes = make_walk(2 * nmine);   // fp16 plane: 32 bytes per chunk
+    // cp.async the residual operands of chunk c (16 channels) of the warp's 32 rows into the rows' slots; consecutive
+    // lanes fetch consecutive 16-byte pieces of a row (2 or 4 pieces per row and plane).  No commit.
+    auto refill_chunk = [&](int c, int opi, int c0) {
+      if (d.res_f32) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int i = it * 32 + lane, row = i >> 2, pp = i & 3;
+          const int orow = __shfl_sync(0xffffffffu, opi, row);
+          if (orow >= 0)
+            cp_async16(warp_slot0 + (uint32_t)row * (uint32_t)P.res_stage_pitch + (uint32_t)((c * NR + pp) * 16),
+                       d.res_f32 + (int64_t)orow * d.res_f32_cs + d.res_f32_coff + c0 + c * 16 + 4 * pp, 16u);
+        }
+      } else {
+        const __half* hi = (const __half*)d.res.hi;
+        const __half* lo = (const __half*)d.res.lo;
+        const bool has_lo = NR == 4 && d.res.lo != nullptr;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int i = it * 32 + lane, row = i >> 1, pp = i & 1;
+          const int orow = __shfl_sync(0xffffffffu, opi, row);
+          if (orow >= 0) {
+            const int64_t o = (int64_t)orow * d.res.cs + d.res.coff + c0 + c * 16 + 8 * pp;
+            const uint32_t dst = warp_slot0 + (uint32_t)row * (uint32_t)P.res_stage_pitch + (uint32_t)((c * NR + pp) * 16);
+            cp_async16(dst, hi + o, 16u);
+            if (has_lo) cp_async16(dst + 32u, lo + o, 16u);
           }
         }
       }
-      cp_async_commit();
     };
-    if (staged) stage_issue(tile0);
+    // coalesced copy-out of the warp's staged fp16 output planes
+    const bool ostaged = P.out_stage_pitch != 0;
+    const uint32_t opitch = (uint32_t)P.out_stage_pitch;
+    const uint32_t ost_plane = 32u * opitch;
+    const uint32_t ost_warp = smem_ost + (uint32_t)(warp - kEpiWarp0) * (d.out.lo ? 2u : 1u) * ost_plane;
+    auto copy_out = [&](int64_t op, int n0) {
+      __syncwarp();  // every lane's chunks are staged
+      const int opi = (int)op;
+      const int c0 = n0 + ch_begin * 16;
+      const bool want_lo = d.out.lo != nullptr;
+      int row = wk_planes.row0, pp = wk_planes.p0;
+      for (int j = 0; j < wk_planes.ppr; ++j) {
+        const int orow = __shfl_sync(0xffffffffu, opi, row);
+        if (orow >= 0 && nmine > 0 && !(P.dbg & 1)) {
+          const uint32_t src = ost_warp + (uint32_t)row * opitch + (uint32_t)pp * 16u;
+          const int64_t o = (int64_t)orow * d.out.cs + d.out.coff + c0 + 8 * pp;
+          uint4 v;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src));
+          *reinterpret_cast<uint4*>((__half*)d.out.hi + o) = v;
+          if (want_lo) {
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src + ost_plane));
+            *reinterpret_cast<uint4*>((__half*)d.out.lo + o) = v;
+          }
+        }
+        pp += wk_planes.dp; row += wk_planes.drow;
+        if (pp >= wk_planes.ppr) { pp -= wk_planes.ppr; ++row; }
+      }
+      __syncwarp();  // staging tile free for the next tile
+    };
+    Cursor cur = cursor_at(tile0);
+    int64_t opix = cursor_pixel(cur);
+    if (staged) {
+      const int c0 = (PATCH ? cur.nt : cur.tile % n_tiles) * BN + ch_begin * 16;
+      for (int c = 0; c < nmine; ++c) refill_chunk(c, (int)opix, c0);
+      cp_async_commit();
+    }
     // hand a TMEM buffer back to the MMA thread (of the pair's leader): one arrive per warp
     auto arrive_leader = [&](uint64_t* bar) {
       tc_fence_before();
@@ -872,26 +978,16 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
     };
 
     int jt = 0;  // tiles processed by this CTA
-    for (int tile = tile0; tile < num_tiles; tile += tstep, ++jt) {
-      const int n0 = (tile % n_tiles) * BN;
+    for (; cur.tile < num_tiles; ++jt) {
+      const int n0 = (PATCH ? cur.nt : cur.tile % n_tiles) * BN;
       const int tb = split ? 0 : (jt & 1);
-      const int64_t opix = CRDR_ROW_PIXEL(tile);
+      Cursor nxt = cur;
+      cursor_advance(nxt);
+      const int64_t opix_next = cursor_pixel(nxt);
+      const int c0_next = (PATCH ? nxt.nt : nxt.tile % n_tiles) * BN + ch_begin * 16;
       if (staged) {
-        cp_async_wait<0>();  // this thread's own copies for `tile` have landed
-#pragma unroll
-        for (int c = 0; c < KC; ++c) {
-          if (ch_begin + c < ch_end) {
-#pragma unroll
-            for (int q = 0; q < NR; ++q) {
-              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                           : "=r"(rres[c][q].x), "=r"(rres[c][q].y), "=r"(rres[c][q].z), "=r"(rres[c][q].w)
-                           : "r"(my_slot + (uint32_t)((c * NR + q) * 16)));
-            }
-          }
-        }
-        stage_issue(tile + tstep);  // refill the slot for the next tile; in flight during this epilogue
-      } else if (opix >= 0 && ch_begin < ch_end) {
-        epi_load_res<NR>(P, opix, n0 + ch_begin * 16, rres[0]);
+        cp_async_wait<0>();  // this lane's copies for `tile` have landed ...
+        __syncwarp();        // ... and so have the other lanes' (they fill this lane's row)
       }
       if (three) {
         for (int ch = 0; ch < nchunks; ++ch, ++gc) {
@@ -915,40 +1011,66 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
         mbar_wait(smem_u32(&acc_full_bar[tb]), (uint32_t)(jt / TB) & 1u, P.status);
         tc_fence_after();
       }
-      uint4 rtrunk[NR];
-#pragma unroll
-      for (int c = 0; c < KC; ++c) {
+      // The chunk loop is deliberately NOT unrolled: one copy of the (large) fused epilogue body instead of up to
+      // eight keeps the tile loop inside the instruction cache (the unrolled form ran at 7-19 cycles per instruction
+      // with every line of the epilogue collecting stall samples).
+      uint4 rtrunk[NR], rr[NR];
+#pragma unroll 1
+      for (int c = 0; c < nmine; ++c) {
         const int chn = ch_begin + c;
-        if (chn < ch_end) {
-          // second chain of a split launch lives one accumulator stride further (D1b / odd K steps)
-          if (three) tmem_ld16_issue(lane_addr + kD1Base + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r1);
-          else tmem_ld16_issue(lane_addr + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r0);
-          if (split) tmem_ld16_issue(lane_addr + (three ? kD1Base : 0u) + kAccStride + (uint32_t)chn * 16u, three ? r0 : r1);
-          if (opix >= 0) {
-            epi_load_trunk<NR>(P, opix, n0 + chn * 16, rtrunk);
-            // unstaged launches (gather variant, unaligned operands): one-chunk-ahead register ring
-            if (!staged && c + 1 < KC && chn + 1 < ch_end) epi_load_res<NR>(P, opix, n0 + (chn + 1) * 16, rres[c + 1 < KC ? c + 1 : c]);
-          }
-          tmem_wait_ld();
-          float acc[16];
+        // second chain of a split launch lives one accumulator stride further (D1b / odd K steps)
+        if (P.dbg & 4) {
+        } else if (three) tmem_ld16_issue(lane_addr + kD1Base + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r1);
+        else tmem_ld16_issue(lane_addr + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r0);
+        if (split) tmem_ld16_issue(lane_addr + (three ? kD1Base : 0u) + kAccStride + (uint32_t)chn * 16u, three ? r0 : r1);
+        if (staged) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            if (three) {
-              const float cross = split ? __uint_as_float(r1[e]) + __uint_as_float(r0[e]) : __uint_as_float(r1[e]);
-              acc[e] = fmaf(cross, kLoInv, total[(three ? c : 0) * 16 + e]);
-            } else {
-              acc[e] = split ? __uint_as_float(r0[e]) + __uint_as_float(r1[e]) : __uint_as_float(r0[e]);
+          for (int q2 = 0; q2 < NR; ++q2) {
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(rr[q2].x), "=r"(rr[q2].y), "=r"(rr[q2].z), "=r"(rr[q2].w)
+                         : "r"(my_slot + (uint32_t)((c * NR + q2) * 16)));
+          }
+          __syncwarp();
+          // chunk c of every row has been read: refill it for the next tile (in flight during the rest of this tile)
+          if (nxt.tile < num_tiles) refill_chunk(c, (int)opix_next, c0_next);
+        } else if (opix >= 0) {
+          epi_load_res<NR>(P, opix, n0 + chn * 16, rr);
+        }
+        if (opix >= 0) epi_load_trunk<NR>(P, opix, n0 + chn * 16, rtrunk);
+        tmem_wait_ld();
+        float acc[16];
+        if (three) {
+          float tsel[16];
+#pragma unroll
+          for (int k = 0; k < (three ? MAXCH : 1); ++k) {
+            if (k == 0 || c == k) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) tsel[e] = total[(three ? k : 0) * 16 + e];
             }
           }
-          if (opix >= 0) {
-            if (P.fast_epi) epi_finish<NR>(P, opix, n0 + chn * 16, acc, rres[c], rtrunk, s_par);
-            else epi_finish_generic(&P, opix, n0 + chn * 16, acc, s_par);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float cross = split ? __uint_as_float(r1[e]) + __uint_as_float(r0[e]) : __uint_as_float(r1[e]);
+            acc[e] = fmaf(cross, kLoInv, tsel[e]);
           }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            acc[e] = split ? __uint_as_float(r0[e]) + __uint_as_float(r1[e]) : __uint_as_float(r0[e]);
+        }
+        if (opix >= 0 && !(P.dbg & 2)) {
+          if (P.fast_epi)
+            epi_finish<NR>(P, opix, n0 + chn * 16, acc, rr, rtrunk, s_par,
+                           ostaged ? ost_warp + (uint32_t)lane * opitch + (uint32_t)c * 32u : 0u, ost_plane);
+          else epi_finish_generic(&P, opix, n0 + chn * 16, acc, s_par);
         }
       }
+      if (staged) cp_async_commit();
       arrive_leader(&acc_empty_bar[tb]);
+      if (ostaged) copy_out(opix, n0);
+      cur = nxt;
+      opix = opix_next;
     }
-#undef CRDR_ROW_PIXEL
   } else {
    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
    if (warp == kTmaWarp) {
@@ -1426,6 +1548,16 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     static int chunk_env = -1;  // tuning knob: K blocks per D0 accumulate chain
     if (chunk_env < 0) { const char* e = getenv("CRDR_CHUNK_KB"); chunk_env = e ? atoi(e) : kChunkKB; if (chunk_env < 1) chunk_env = 1; }
     P.chunk_kb = chunk_env;
+    static int dbg_env = -1;  // bring-up: bit0 skip copy-out stores, bit1 skip the epilogue arithmetic, bit2 skip TMEM loads
+    if (dbg_env < 0) { const char* e = getenv("CRDR_EPI_DEBUG"); dbg_env = e ? atoi(e) : 0; }
+    P.dbg = dbg_env;
+    static int hint_env = -1;
+    if (hint_env < 0) {
+      const char* e = getenv("CRDR_WAIT_HINT_NS");
+      hint_env = e ? atoi(e) : 1000000;
+      const uint32_t h = (uint32_t)hint_env;
+      cudaMemcpyToSymbol(g_wait_hint_ns, &h, sizeof(h));
+    }
     static int trace_env = -1;
     if (trace_env < 0) { const char* e = getenv("CRDR_CONV_TRACE"); trace_env = e ? atoi(e) : 0; }
     P.trace = trace_env;
@@ -1511,6 +1643,16 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     res_pitch = (uint32_t)d.tile_n * (three ? 4u : 2u) + 16u;
     res_need = kTileM * res_pitch;
   }
+  // output staging: per epilogue warp a [32 rows][columns of the warp] tile per fp16 plane (pitch padded by 16 B)
+  uint32_t out_need = 0, out_pitch = 0;
+  {
+    static int ost_env = -1;
+    if (ost_env < 0) { const char* e = getenv("CRDR_CONV_OSTAGE"); ost_env = e ? atoi(e) : 1; }
+    if (ost_env && P.fast_epi && d.out.hi && !d.out_f32) {
+      out_pitch = (uint32_t)((d.tile_n / 16 + 1) / 2) * 32u + 16u;
+      out_need = 8u * 32u * out_pitch * (d.out.lo ? 2u : 1u);
+    }
+  }
   uint32_t patch_total = 0;
   if (use_patch) {
     int dh_min = 127, dh_max = -127, dw_min = 127, dw_max = -127;
@@ -1536,7 +1678,7 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     // Patch ring depth: the patches of about two tiles in flight (small-K launches are bound by the load latency
     // of the next tile's patch, not by the MMAs), as long as four weight stages still fit; at least one.
     {
-      const uint32_t budget = kDynSmemMax - 1024 - res_need;
+      const uint32_t budget = kDynSmemMax - 1024 - res_need - out_need;
       int want = 2 * ncb;
       if (want < 2) want = 2;
       if (want > kMaxPatchStages) want = kMaxPatchStages;
@@ -1561,9 +1703,14 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
   }
   uint32_t res_total = 0;
   P.res_stage_pitch = 0;
+  P.out_stage_pitch = 0;
   if (res_need && patch_total + 2 * stage_bytes + 1024 + res_need <= kDynSmemMax) {
     P.res_stage_pitch = (int32_t)res_pitch;
     res_total = res_need;
+  }
+  if (out_need && patch_total + 3 * stage_bytes + 1024 + res_total + out_need <= kDynSmemMax) {
+    P.out_stage_pitch = (int32_t)out_pitch;
+    res_total += out_need;  // laid out right behind the residual slots
   }
   int stages = (int)((kDynSmemMax - 1024 - patch_total - res_total) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;

@@ -7,6 +7,8 @@ import fixtures
 SWEEP = [0.0, 1.0, 2.0, 3.0, 4.0]
 BETAS = [0.0, 3.84]
 model, _ = fixtures.build_model(seed=0, calibrated=True)
+import os
+model.pipeline_chunks = int(os.environ.get('CHUNKS', '2'))
 x = fixtures.image(24, 512, 768, seed=100).pin_memory()
 host = None
 def T(): torch.cuda.synchronize(); return time.perf_counter()
