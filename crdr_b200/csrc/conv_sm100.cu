@@ -36,8 +36,12 @@ constexpr uint32_t kAPlaneBytes = kTileM * 128;
 constexpr int kMaxStages = 10;
 constexpr int kMaxPatchStages = 8;         // PATCH mode: halo-patch ring (deep for small-K launches: a patch is a whole tile's A operand)
 constexpr int kThreads = 512;              // gather variant: warps 0-3 gather, 4-11 drain/epilogue, 12 TMA + TMEM alloc, 13 MMA, 14-15 idle
-constexpr int kThreadsPatch = 384;         // patch variant: warps 0-7 drain/epilogue, 8 TMA + TMEM alloc, 9 MMA, 10 halo patches, 11 idle
-                                           // setmaxnreg: 128 * (216 + 216 + 56) <= 65536
+constexpr int kThreadsPatch = 512;         // patch variant, F16X1: warps 0-11 drain/epilogue, 12 TMA + TMEM alloc, 13 MMA, 14 halo
+                                           // patches, 15 idle; setmaxnreg 384 * 152 + 128 * 56 == 65536.  F16X3 (register totals)
+                                           // runs 384 threads: warps 0-7 epilogue at 216 registers, 8-10 control, 11 idle.
+// epilogue warps = 4 TMEM lane quarters x column groups (the epilogue is latency bound: 12 warps issue more than 8 do, but
+// the F16X3 drain totals do not fit the 152-register budget of a 12-warp layout)
+__host__ __device__ constexpr int epi_groups(bool patch, bool three) { return (patch && !three) ? 3 : 2; }
 constexpr int kChunkKB = 2;                // F16X3: K blocks per D0 accumulate chain (8 MMAs of K=16)
 constexpr uint32_t kSmemLimit = 227 * 1024;
 constexpr uint32_t kDynSmemMax = kSmemLimit - 8 * 1024;  // static smem: parameter cache (5 KB) + barriers
@@ -604,14 +608,18 @@ __device__ __forceinline__ void prefetch_epilogue_operands(const crdr_conv_desc&
 // HALF of the weight tile.  One 128 x N x 16 cta_group::1 MMA occupies the tensor pipe for ~N cycles (measured,
 // twice the 4096 MAC/clk rate); the pair form is how sm_100 reaches the full rate.
 template <int MAXCH, bool PATCH, bool CG2 = false>
-__global__ void __launch_bounds__(PATCH ? kThreadsPatch : kThreads, 1)
+// (setmaxnreg re-distributes the CTA's LAUNCH allocation: F16X3 patch kernels are bounded at 384 threads so that ptxas
+// gives them 168 registers per thread at launch, enough for 256 x 216 + 128 x 56 afterwards)
+__global__ void __launch_bounds__(PATCH ? (MAXCH > 0 ? 384 : kThreadsPatch) : kThreads, 1)
 conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
   static_assert(PATCH || !CG2, "the CTA-pair form exists for the patch variant only");
   constexpr bool three = MAXCH > 0;
   constexpr int kEpiWarp0 = PATCH ? 0 : 4;      // first of the 8 drain / epilogue warps (a multiple of 4: TMEM lane quarters)
-  constexpr int kTmaWarp = kEpiWarp0 + 8;
-  constexpr int kMmaWarp = kEpiWarp0 + 9;
-  constexpr int kPatchWarp = kEpiWarp0 + 10;
+  constexpr int kEpiGroups = epi_groups(PATCH, three);
+  constexpr int kEpiWarps = 4 * kEpiGroups;
+  constexpr int kTmaWarp = kEpiWarp0 + kEpiWarps;
+  constexpr int kMmaWarp = kTmaWarp + 1;
+  constexpr int kPatchWarp = kTmaWarp + 2;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -679,9 +687,9 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&d0_full_bar[b]), 1u);
-      mbar_init(smem_u32(&d0_empty_bar[b]), CG2 ? 16u : 8u);   // one arrive per drain warp (of both CTAs)
+      mbar_init(smem_u32(&d0_empty_bar[b]), (CG2 ? 2u : 1u) * kEpiWarps);   // one arrive per drain warp (of both CTAs)
       mbar_init(smem_u32(&acc_full_bar[b]), 1u);
-      mbar_init(smem_u32(&acc_empty_bar[b]), CG2 ? 16u : 8u);
+      mbar_init(smem_u32(&acc_empty_bar[b]), (CG2 ? 2u : 1u) * kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -822,17 +830,19 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
     fence_proxy_async();
     for (; gpub < g; ++gpub) mbar_arrive(smem_u32(&full_bar[gpub % S]));
    }
-  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 8) {
-    if (PATCH) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
+    if (PATCH && !three) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    else if (PATCH) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
     // ------------------------------------------------------------------ drain D0 chunks + epilogue
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const int half = (warp - kEpiWarp0) >> 2;  // which half of the tile's column chunks
+    const int cgrp = (warp - kEpiWarp0) >> 2;  // which group of the tile's column chunks
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int nch_tile = BN / 16;
-    const int ch_begin = half == 0 ? 0 : (nch_tile + 1) / 2;
-    const int ch_end = half == 0 ? (nch_tile + 1) / 2 : nch_tile;
+    const int ch_per = (nch_tile + kEpiGroups - 1) / kEpiGroups;
+    const int ch_begin = min(cgrp * ch_per, nch_tile);
+    const int ch_end = min(ch_begin + ch_per, nch_tile);
     constexpr int NR = three ? 4 : 2;         // 16-byte registers per residual chunk
     constexpr int KC = three ? MAXCH : 8;     // column chunks per epilogue warp (compile-time bound)
     // Residual operands are software-pipelined ACROSS tiles without spending registers on it: every thread copies
@@ -1588,7 +1598,9 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     set_error("conv2d: k_order=1 weights need the TMA engine");
     return CRDR_ERR_BAD_SHAPE;
   }
-  const int maxch = three ? ((d.tile_n / 16 + 1) / 2) : 0;
+  const int groups = epi_groups(use_patch, three);
+  const int ch_per_warp = (d.tile_n / 16 + groups - 1) / groups;  // column chunks per epilogue warp
+  const int maxch = three ? ch_per_warp : 0;
   typedef void (*KernelFn)(const ConvKParams);
   KernelFn fn = nullptr;
   // CTA-pair form (cta_group::2, M = 256 per MMA) for the patch variant; CRDR_CONV_CG2=0 falls back to single CTAs
@@ -1649,8 +1661,9 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     static int ost_env = -1;
     if (ost_env < 0) { const char* e = getenv("CRDR_CONV_OSTAGE"); ost_env = e ? atoi(e) : 1; }
     if (ost_env && P.fast_epi && d.out.hi && !d.out_f32) {
-      out_pitch = (uint32_t)((d.tile_n / 16 + 1) / 2) * 32u + 16u;
-      out_need = 8u * 32u * out_pitch * (d.out.lo ? 2u : 1u);
+      const int groups = epi_groups(d.k_order == 1 && d.engine != CRDR_ENGINE_TCGEN05_NOTMA, d.precision == CRDR_PREC_F16X3);
+      out_pitch = (uint32_t)((d.tile_n / 16 + groups - 1) / groups) * 32u + 16u;
+      out_need = (uint32_t)(4 * groups) * 32u * out_pitch * (d.out.lo ? 2u : 1u);
     }
   }
   uint32_t patch_total = 0;
@@ -1736,7 +1749,7 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(2 * pairs));
-    cfg.blockDim = dim3(kThreadsPatch);
+    cfg.blockDim = dim3(32 * (4 * groups + 4));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr;
@@ -1754,7 +1767,7 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     return check_launch("conv_tcgen05_kernel(cg2)");
   }
   const unsigned grid = (unsigned)(num_tiles < num_sms ? num_tiles : num_sms);  // persistent: one CTA per SM
-  fn<<<grid, use_patch ? kThreadsPatch : kThreads, smem, stream>>>(P);
+  fn<<<grid, use_patch ? 32 * (4 * groups + 4) : kThreads, smem, stream>>>(P);
   return check_launch("conv_tcgen05_kernel");
 }
 
