@@ -607,15 +607,19 @@ __device__ __forceinline__ void prefetch_epilogue_operands(const crdr_conv_desc&
 // tcgen05.mma.cta_group::2 with M = 256 over both CTAs' shared memory / TMEM, each CTA loads its own halo patch and
 // HALF of the weight tile.  One 128 x N x 16 cta_group::1 MMA occupies the tensor pipe for ~N cycles (measured,
 // twice the 4096 MAC/clk rate); the pair form is how sm_100 reaches the full rate.
-template <int MAXCH, bool PATCH, bool CG2 = false>
+template <int MAXCH, bool PATCH, bool CG2 = false, bool DIRECT = false>
 // (setmaxnreg re-distributes the CTA's LAUNCH allocation: F16X3 patch kernels are bounded at 384 threads so that ptxas
 // gives them 168 registers per thread at launch, enough for 256 x 216 + 128 x 56 afterwards)
 __global__ void __launch_bounds__(PATCH ? (MAXCH > 0 ? 384 : kThreadsPatch) : kThreads, 1)
 conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
   static_assert(PATCH || !CG2, "the CTA-pair form exists for the patch variant only");
-  constexpr bool three = MAXCH > 0;
+  // DIRECT: F16X3 for short K (<= kDirectMaxKB K blocks): D0 is one accumulate chain per tile like an F16X1 accumulator,
+  // so there is no chunk drain, no register totals, and the launch gets the 12-warp epilogue.
+  static_assert(!DIRECT || (MAXCH == 0 && PATCH), "DIRECT is a patch-variant mode without register totals");
+  constexpr bool three = MAXCH > 0 || DIRECT;
+  constexpr bool drain = MAXCH > 0;
   constexpr int kEpiWarp0 = PATCH ? 0 : 4;      // first of the 8 drain / epilogue warps (a multiple of 4: TMEM lane quarters)
-  constexpr int kEpiGroups = epi_groups(PATCH, three);
+  constexpr int kEpiGroups = epi_groups(PATCH, drain);
   constexpr int kEpiWarps = 4 * kEpiGroups;
   constexpr int kTmaWarp = kEpiWarp0 + kEpiWarps;
   constexpr int kMmaWarp = kTmaWarp + 1;
@@ -661,7 +665,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
   const int m_tiles = PATCH ? d.n * P.tiles_h * P.tiles_w : (P.m_total + kTileM - 1) / kTileM;
   const int num_tiles = (CG2 ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;  // CG2: tiles of the pair (M = 256)
 #define CRDR_MTILE(TILE) (CG2 ? 2 * ((TILE) / n_tiles) + (int)cta_rank : (TILE) / n_tiles)
-  const int chunk_kb = three ? P.chunk_kb : nkb;
+  const int chunk_kb = drain ? P.chunk_kb : nkb;
   const int nchunks = (nkb + chunk_kb - 1) / chunk_kb;  // D0 chunks per tile
 
   for (int i = threadIdx.x; i < 4 * kMaxCout; i += (int)blockDim.x) {
@@ -831,7 +835,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
     for (; gpub < g; ++gpub) mbar_arrive(smem_u32(&full_bar[gpub % S]));
    }
   } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
-    if (PATCH && !three) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    if (PATCH && !drain) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     else if (PATCH) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
     // ------------------------------------------------------------------ drain D0 chunks + epilogue
@@ -852,7 +856,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
     // for tile j+2.  Each thread only ever touches its own slot, so no barrier is involved.
     const bool staged = P.res_stage_pitch != 0;
     const uint32_t my_slot = smem_res + (uint32_t)row * (uint32_t)P.res_stage_pitch + (uint32_t)(ch_begin * NR * 16);
-    float total[three ? MAXCH * 16 : 1];
+    float total[drain ? MAXCH * 16 : 1];
     uint32_t r0[16], r1[16];
     int gc = 0;  // D0 chunks seen so far (all tiles)
 
@@ -999,7 +1003,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
         cp_async_wait<0>();  // this lane's copies for `tile` have landed ...
         __syncwarp();        // ... and so have the other lanes' (they fill this lane's row)
       }
-      if (three) {
+      if (drain) {
         for (int ch = 0; ch < nchunks; ++ch, ++gc) {
           const int b = gc & 1;
           mbar_wait(smem_u32(&d0_full_bar[b]), (uint32_t)(gc >> 1) & 1u, P.status);
@@ -1032,7 +1036,8 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
         if (P.dbg & 4) {
         } else if (three) tmem_ld16_issue(lane_addr + kD1Base + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r1);
         else tmem_ld16_issue(lane_addr + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r0);
-        if (split) tmem_ld16_issue(lane_addr + (three ? kD1Base : 0u) + kAccStride + (uint32_t)chn * 16u, three ? r0 : r1);
+        if (DIRECT) tmem_ld16_issue(lane_addr + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r0);  // D0 of the tile
+        else if (split) tmem_ld16_issue(lane_addr + (three ? kD1Base : 0u) + kAccStride + (uint32_t)chn * 16u, three ? r0 : r1);
         if (staged) {
 #pragma unroll
           for (int q2 = 0; q2 < NR; ++q2) {
@@ -1052,15 +1057,15 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
         if (three) {
           float tsel[16];
 #pragma unroll
-          for (int k = 0; k < (three ? MAXCH : 1); ++k) {
+          for (int k = 0; k < (drain ? MAXCH : 1); ++k) {
             if (k == 0 || c == k) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e) tsel[e] = total[(three ? k : 0) * 16 + e];
+              for (int e = 0; e < 16; ++e) tsel[e] = DIRECT ? __uint_as_float(r0[e]) : total[(drain ? k : 0) * 16 + e];
             }
           }
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const float cross = split ? __uint_as_float(r1[e]) + __uint_as_float(r0[e]) : __uint_as_float(r1[e]);
+            const float cross = (split && !DIRECT) ? __uint_as_float(r1[e]) + __uint_as_float(r0[e]) : __uint_as_float(r1[e]);
             acc[e] = fmaf(cross, kLoInv, tsel[e]);
           }
         } else {
@@ -1183,7 +1188,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
           const bool chunk_first = ck == 0;
           const bool chunk_last = ck == chunk_kb - 1 || kb == nkb - 1;
           const int b = gc & 1;
-          if (three && chunk_first && gc >= 2) {
+          if (drain && chunk_first && gc >= 2) {
             // the drain warps must have emptied this D0 buffer (chunk gc-2) before it is overwritten
             if (tr) t0 = clock64();
             mbar_wait(smem_u32(&d0_empty_bar[b]), (uint32_t)((gc - 2) >> 1) & 1u, P.status);
@@ -1209,7 +1214,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
           mbar_wait(smem_u32(&full_bar[s]), ring_par, P.status);
           if (tr) t_full += clock64() - t0;
           tc_fence_after();
-          const uint32_t d0 = tmem_base + (uint32_t)(three ? b : tb) * kAccStride;
+          const uint32_t d0 = tmem_base + (uint32_t)(drain ? b : tb) * kAccStride;
           const uint64_t b_hi = desc_b + (uint64_t)((stage + a_planes) >> 4);
           const uint64_t b_lo = desc_b + (uint64_t)((stage + a_planes + b_bytes) >> 4);
           if (tr) t0 = clock64();
@@ -1241,8 +1246,8 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
             }
           }
           if (chunk_last) {
-            if (elected) umma_done<CG2>(smem_u32(three ? &d0_full_bar[b] : &acc_full_bar[tb]));
-            if (three) ++gc;
+            if (elected) umma_done<CG2>(smem_u32(drain ? &d0_full_bar[b] : &acc_full_bar[tb]));
+            if (drain) ++gc;
             ck = 0;
           } else {
             ++ck;
@@ -1598,16 +1603,22 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     set_error("conv2d: k_order=1 weights need the TMA engine");
     return CRDR_ERR_BAD_SHAPE;
   }
-  const int groups = epi_groups(use_patch, three);
-  const int ch_per_warp = (d.tile_n / 16 + groups - 1) / groups;  // column chunks per epilogue warp
-  const int maxch = three ? ch_per_warp : 0;
-  typedef void (*KernelFn)(const ConvKParams);
-  KernelFn fn = nullptr;
-  // CTA-pair form (cta_group::2, M = 256 per MMA) for the patch variant; CRDR_CONV_CG2=0 falls back to single CTAs
+  // short-K F16X3 patch launches run without the chunked D0 drain (one accumulate chain of <= kDirectMaxKB K blocks)
+  static int direct_env = -1;
+  if (direct_env < 0) { const char* e = getenv("CRDR_CONV_DIRECT_KB"); direct_env = e ? atoi(e) : 4; }
   static int cg2_env = -1;
   if (cg2_env < 0) { const char* e = getenv("CRDR_CONV_CG2"); cg2_env = e ? atoi(e) : 1; }
   const bool cg2 = use_patch && cg2_env != 0;
-  if (cg2) {
+  const bool direct = three && cg2 && P.nkb <= direct_env && P.split == 0;
+  const int groups = epi_groups(use_patch, three && !direct);
+  const int ch_per_warp = (d.tile_n / 16 + groups - 1) / groups;  // column chunks per epilogue warp
+  const int maxch = (three && !direct) ? ch_per_warp : 0;
+  typedef void (*KernelFn)(const ConvKParams);
+  KernelFn fn = nullptr;
+  // CTA-pair form (cta_group::2, M = 256 per MMA) for the patch variant; CRDR_CONV_CG2=0 falls back to single CTAs
+  if (direct) {
+    fn = conv_tcgen05_kernel<0, true, true, true>;
+  } else if (cg2) {
     switch (maxch) {
       case 0: fn = conv_tcgen05_kernel<0, true, true>; break;
       case 1: fn = conv_tcgen05_kernel<1, true, true>; break;
@@ -1628,7 +1639,7 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     case 8: fn = conv_tcgen05_kernel<4, false>; break;
     default: fn = conv_tcgen05_kernel<4, true>; break;
   }
-  const int variant = cg2 ? 10 + maxch : maxch * 2 + (use_patch ? 1 : 0);
+  const int variant = direct ? 15 : cg2 ? 10 + maxch : maxch * 2 + (use_patch ? 1 : 0);
   static std::mutex attr_mutex;
   static bool attr_done[16] = {false};
   static int num_sms = 0;
@@ -1661,7 +1672,6 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     static int ost_env = -1;
     if (ost_env < 0) { const char* e = getenv("CRDR_CONV_OSTAGE"); ost_env = e ? atoi(e) : 1; }
     if (ost_env && P.fast_epi && d.out.hi && !d.out_f32) {
-      const int groups = epi_groups(d.k_order == 1 && d.engine != CRDR_ENGINE_TCGEN05_NOTMA, d.precision == CRDR_PREC_F16X3);
       out_pitch = (uint32_t)((d.tile_n / 16 + groups - 1) / groups) * 32u + 16u;
       out_need = (uint32_t)(4 * groups) * 32u * out_pitch * (d.out.lo ? 2u : 1u);
     }
