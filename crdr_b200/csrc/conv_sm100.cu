@@ -34,6 +34,7 @@ constexpr int kTileM = 128;
 constexpr int kKBlk = 64;                  // fp16 elements per K block = one 128-byte swizzle row
 constexpr uint32_t kAPlaneBytes = kTileM * 128;
 constexpr int kMaxStages = 10;
+constexpr int kSlotKB = 2;                 // PATCH mode: K blocks of weights per ring slot (one full / empty barrier round per slot)
 constexpr int kMaxPatchStages = 8;         // PATCH mode: halo-patch ring (deep for small-K launches: a patch is a whole tile's A operand)
 constexpr int kThreads = 512;              // gather variant: warps 0-3 gather, 4-11 drain/epilogue, 12 TMA + TMEM alloc, 13 MMA, 14-15 idle
 constexpr int kThreadsPatch = 512;         // patch variant, F16X1: warps 0-11 drain/epilogue, 12 TMA + TMEM alloc, 13 MMA, 14 halo
@@ -655,7 +656,9 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
   const uint32_t patch_plane_bytes = PATCH ? (uint32_t)(P.ph * P.pw) * 128u : 0u;
   const uint32_t patch_stage_bytes = (patch_plane_bytes * nplanes + 1023u) & ~1023u;
   const uint32_t a_bytes = PATCH ? 0u : kAPlaneBytes;
-  const uint32_t stage_bytes = (uint32_t)nplanes * (a_bytes + b_bytes);
+  constexpr int KPS = PATCH ? kSlotKB : 1;   // K blocks per ring slot
+  const uint32_t kb_bytes = (uint32_t)nplanes * (a_bytes + b_bytes);
+  const uint32_t stage_bytes = (uint32_t)KPS * kb_bytes;
   const uint32_t smem_patch = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_base = smem_patch + (PATCH ? (uint32_t)P.patch_stages * patch_stage_bytes : 0u);
   const uint32_t smem_res = smem_base + (uint32_t)P.stages * stage_bytes;  // residual staging slots (128 rows)
@@ -1009,17 +1012,27 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
           mbar_wait(smem_u32(&d0_full_bar[b]), (uint32_t)(gc >> 1) & 1u, P.status);
           tc_fence_after();
           const uint32_t src = lane_addr + (uint32_t)b * kAccStride;
+          // two tcgen05.ld in flight per wait; the buffer goes back to the MMA thread as soon as the last load has
+          // landed in registers, before the adds (the drain round trip bounds short-N F16X3 launches)
 #pragma unroll
-          for (int c = 0; c < MAXCH; ++c) {
-            if (ch_begin + c < ch_end) {
-              tmem_ld16_issue(src + (uint32_t)(ch_begin + c) * 16u, r0);
-              tmem_wait_ld();
+          for (int c = 0; c < MAXCH; c += 2) {
+            const bool has0 = ch_begin + c < ch_end, has1 = c + 1 < MAXCH && ch_begin + c + 1 < ch_end;
+            if (has0) tmem_ld16_issue(src + (uint32_t)(ch_begin + c) * 16u, r0);
+            if (has1) tmem_ld16_issue(src + (uint32_t)(ch_begin + c + 1) * 16u, r1);
+            tmem_wait_ld();
+            if (c + 2 >= MAXCH) arrive_leader(&d0_empty_bar[b]);
+            if (has0) {
 #pragma unroll
               for (int e = 0; e < 16; ++e)
                 total[c * 16 + e] = (ch == 0) ? __uint_as_float(r0[e]) : total[c * 16 + e] + __uint_as_float(r0[e]);
             }
+            if (has1) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                total[(c + 1 < MAXCH ? c + 1 : c) * 16 + e] =
+                    (ch == 0) ? __uint_as_float(r1[e]) : total[(c + 1 < MAXCH ? c + 1 : c) * 16 + e] + __uint_as_float(r1[e]);
+            }
           }
-          arrive_leader(&d0_empty_bar[b]);
         }
       } else {
         mbar_wait(smem_u32(&acc_full_bar[tb]), (uint32_t)(jt / TB) & 1u, P.status);
@@ -1099,23 +1112,31 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
       uint32_t bst = smem_base + (uint32_t)nplanes * a_bytes;
       for (int tile = tile0; tile < num_tiles; tile += tstep) {
         const int n0 = (tile % n_tiles) * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++g, ++s, bst += stage_bytes) {
-          if (s == S) { s = 0; empty_par ^= 1u; bst = smem_base + (uint32_t)nplanes * a_bytes; }
-          if (trp) tp0 = clock64();
-          mbar_wait(smem_u32(&empty_bar[s]), empty_par, P.status);
-          if (trp) tp_wait += clock64() - tp0;
+        int kk = 0;  // K block inside the ring slot
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
           const uint32_t bar = smem_u32(&full_bar[s]);
+          if (kk == 0) {
+            if (trp) tp0 = clock64();
+            mbar_wait(smem_u32(&empty_bar[s]), empty_par, P.status);
+            if (trp) tp_wait += clock64() - tp0;
+            // the slot's K blocks (both halves of the weight tile for a CTA pair) complete on one (the leader's) barrier
+            const uint32_t kcount = (uint32_t)min(KPS, nkb - kb);
+            if (!CG2 || cta_rank == 0) mbar_arrive_expect_tx(bar, (CG2 ? 2u : 1u) * kcount * (uint32_t)nplanes * b_bytes);
+          }
+          const uint32_t dst = bst + (uint32_t)kk * kb_bytes;
           if (CG2) {
-            // both halves of the weight tile complete on the leader's barrier
-            if (cta_rank == 0) mbar_arrive_expect_tx(bar, 2u * (uint32_t)nplanes * b_bytes);
             const uint32_t lbar = mapa_shared(bar, 0u);
             const int nrow = n0 + (int)cta_rank * BNL;
-            tma_load_2d_cg2(bst, &P.tm_hi, kb * kKBlk, nrow, lbar);
-            if (three) tma_load_2d_cg2(bst + b_bytes, &P.tm_lo, kb * kKBlk, nrow, lbar);
+            tma_load_2d_cg2(dst, &P.tm_hi, kb * kKBlk, nrow, lbar);
+            if (three) tma_load_2d_cg2(dst + b_bytes, &P.tm_lo, kb * kKBlk, nrow, lbar);
           } else {
-            mbar_arrive_expect_tx(bar, (uint32_t)nplanes * b_bytes);
-            tma_load_2d(bst, &P.tm_hi, kb * kKBlk, n0, bar);
-            if (three) tma_load_2d(bst + b_bytes, &P.tm_lo, kb * kKBlk, n0, bar);
+            tma_load_2d(dst, &P.tm_hi, kb * kKBlk, n0, bar);
+            if (three) tma_load_2d(dst + b_bytes, &P.tm_lo, kb * kKBlk, n0, bar);
+          }
+          if (++kk == KPS || kb == nkb - 1) {
+            kk = 0;
+            bst += stage_bytes;
+            if (++s == S) { s = 0; empty_par ^= 1u; bst = smem_base + (uint32_t)nplanes * a_bytes; }
           }
         }
       }
@@ -1183,7 +1204,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
           tc_fence_after();
         }
         const uint32_t d1 = tmem_base + kD1Base + (uint32_t)tb * kAccStride;
-        int tap = 0, ck = 0;     // tap of this K block (PATCH), position inside the D0 chunk
+        int tap = 0, ck = 0, kk = 0;  // tap of this K block (PATCH), position inside the D0 chunk / the ring slot
         for (int kb = 0; kb < nkb; ++kb, ++g) {
           const bool chunk_first = ck == 0;
           const bool chunk_last = ck == chunk_kb - 1 || kb == nkb - 1;
@@ -1210,13 +1231,16 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
             a_hi = desc_a + (uint64_t)(stage >> 4);
             a_lo = desc_a + (uint64_t)((stage + kAPlaneBytes) >> 4);
           }
-          if (tr) t0 = clock64();
-          mbar_wait(smem_u32(&full_bar[s]), ring_par, P.status);
-          if (tr) t_full += clock64() - t0;
+          if (kk == 0) {
+            if (tr) t0 = clock64();
+            mbar_wait(smem_u32(&full_bar[s]), ring_par, P.status);
+            if (tr) t_full += clock64() - t0;
+          }
           tc_fence_after();
           const uint32_t d0 = tmem_base + (uint32_t)(drain ? b : tb) * kAccStride;
-          const uint64_t b_hi = desc_b + (uint64_t)((stage + a_planes) >> 4);
-          const uint64_t b_lo = desc_b + (uint64_t)((stage + a_planes + b_bytes) >> 4);
+          const uint32_t bsrc = stage + a_planes + (uint32_t)kk * kb_bytes;
+          const uint64_t b_hi = desc_b + (uint64_t)(bsrc >> 4);
+          const uint64_t b_lo = desc_b + (uint64_t)((bsrc + b_bytes) >> 4);
           if (tr) t0 = clock64();
           if (elected) {
 #pragma unroll
@@ -1236,7 +1260,8 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
           }
           }
           if (tr) { const long long t1 = clock64(); t_mma += t1 - t0; t0 = t1; }
-          if (elected) umma_done<CG2>(smem_u32(&empty_bar[s]));
+          const bool slot_last = ++kk == KPS || kb == nkb - 1;
+          if (slot_last && elected) umma_done<CG2>(smem_u32(&empty_bar[s]));
           if (PATCH) {
             if (++tap == ntaps) {  // all taps of the channel block issued: the patch buffer may be refilled
               tap = 0;
@@ -1253,8 +1278,11 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
             ++ck;
           }
           if (tr) t_commit += clock64() - t0;
-          stage += stage_bytes;
-          if (++s == S) { s = 0; ring_par ^= 1u; stage = smem_base; }
+          if (slot_last) {
+            kk = 0;
+            stage += stage_bytes;
+            if (++s == S) { s = 0; ring_par ^= 1u; stage = smem_base; }
+          }
         }
       }
       if (tr) {  // bring-up counters (cycles): total, wait full, wait d0_empty, wait acc_empty, wait patch, k blocks
@@ -1697,7 +1725,7 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     }
     const uint32_t plane = (uint32_t)(P.ph * P.pw) * 128u;
     const uint32_t pstage = (plane * (uint32_t)P.nplanes + 1023u) & ~1023u;
-    const uint32_t bstage = (uint32_t)P.nplanes * (uint32_t)(cg2 ? d.tile_n / 2 : d.tile_n) * 128u;
+    const uint32_t bstage = (uint32_t)kSlotKB * (uint32_t)P.nplanes * (uint32_t)(cg2 ? d.tile_n / 2 : d.tile_n) * 128u;
     // Patch ring depth: the patches of about two tiles in flight (small-K launches are bound by the load latency
     // of the next tile's patch, not by the MMAs), as long as four weight stages still fit; at least one.
     {
@@ -1706,7 +1734,7 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
       if (want < 2) want = 2;
       if (want > kMaxPatchStages) want = kMaxPatchStages;
       int ps = want;
-      while (ps > 1 && (uint32_t)ps * pstage + 4 * bstage > budget) --ps;
+      while (ps > 1 && (uint32_t)ps * pstage + 3 * bstage > budget) --ps;
       if (ps == 1 && pstage + 2 * bstage > budget) ps = 1;
       P.patch_stages = ps;
     }
@@ -1719,7 +1747,8 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     }
   }
   const int b_rows = cg2 ? d.tile_n / 2 : d.tile_n;  // weight-tile rows per CTA
-  const uint32_t stage_bytes = (uint32_t)P.nplanes * ((use_patch ? 0u : kAPlaneBytes) + (uint32_t)b_rows * 128u);
+  const uint32_t stage_bytes = (uint32_t)P.nplanes * (use_patch ? (uint32_t)kSlotKB * (uint32_t)b_rows * 128u
+                                                                : kAPlaneBytes + (uint32_t)b_rows * 128u);
   if (patch_total + 2 * stage_bytes + 1024 > kDynSmemMax) {
     set_error("conv2d: tile_n=%d does not leave two pipeline stages (patch %u B)", d.tile_n, patch_total);
     return CRDR_ERR_BAD_SHAPE;
