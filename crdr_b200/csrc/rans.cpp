@@ -10,7 +10,10 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <memory>
+#include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -20,14 +23,82 @@ constexpr uint32_t kBypassBits = 4;
 constexpr int32_t kBypassMax = (1 << kBypassBits) - 1;
 constexpr uint64_t kRansL = 1ull << 31;
 
+// Per-table acceleration structures, built once per (table pointer, geometry) and shared by all coder threads:
+//  * encoder: per (row, value) reciprocal of the frequency, so the state update is a multiply-high instead of a 64-bit
+//    division (Alverson; exact for states below 2^63, which the renormalisation bound guarantees) - same words out;
+//  * decoder: per row a 256-bucket index over the 16-bit cumulative range; the slot search starts at the bucket's
+//    first slot and walks forward (Gaussian / logistic tables put a handful of slots in a bucket).
+struct EncSym {
+  uint64_t rcp_freq;
+  uint32_t bias;
+  uint32_t cmpl_freq;   // 2^16 - freq
+  uint32_t rcp_shift;
+  uint32_t freq;
+};
+struct TableAccel {
+  std::vector<EncSym> enc;        // [n_cdf][cdf_stride] (entries past a row's size are unused)
+  std::vector<uint16_t> bucket;   // [n_cdf][256]
+};
+struct AccelKey {
+  const int32_t* cdfs; const int32_t* sizes; int32_t stride, n;
+  bool operator==(const AccelKey& o) const { return cdfs == o.cdfs && sizes == o.sizes && stride == o.stride && n == o.n; }
+};
+struct AccelKeyHash {
+  size_t operator()(const AccelKey& k) const {
+    return std::hash<const void*>()(k.cdfs) ^ (std::hash<const void*>()(k.sizes) << 1) ^ ((size_t)k.stride << 20) ^ (size_t)k.n;
+  }
+};
+std::mutex g_accel_mutex;
+std::unordered_map<AccelKey, std::shared_ptr<const TableAccel>, AccelKeyHash> g_accel;
+
+std::shared_ptr<const TableAccel> table_accel(const crdr_cdf_tables* t) {
+  const AccelKey key{t->cdfs, t->cdf_sizes, t->cdf_stride, t->n_cdf};
+  std::lock_guard<std::mutex> lk(g_accel_mutex);
+  auto it = g_accel.find(key);
+  if (it != g_accel.end()) return it->second;
+  auto a = std::make_shared<TableAccel>();
+  a->enc.assign((size_t)t->n_cdf * (size_t)t->cdf_stride, EncSym{0, 0, 0, 0, 0});
+  a->bucket.assign((size_t)t->n_cdf * 256, 0);
+  for (int32_t r = 0; r < t->n_cdf; ++r) {
+    const int32_t* cdf = t->cdfs + (int64_t)r * t->cdf_stride;
+    const int32_t size = std::min(t->cdf_sizes[r], t->cdf_stride);
+    for (int32_t v = 0; v + 1 < size; ++v) {
+      const uint32_t start = (uint32_t)cdf[v], freq = (uint32_t)(cdf[v + 1] - cdf[v]);
+      EncSym& e = a->enc[(size_t)r * t->cdf_stride + v];
+      e.freq = freq;
+      e.cmpl_freq = (1u << kPrecision) - freq;
+      if (freq < 2) {
+        e.rcp_freq = ~0ull; e.rcp_shift = 0; e.bias = start + (1u << kPrecision) - 1;
+      } else {
+        uint32_t shift = 0;
+        while (freq > (1u << shift)) ++shift;
+        e.rcp_freq = (uint64_t)(((((unsigned __int128)1) << (shift + 63)) + freq - 1) / freq);
+        e.rcp_shift = shift - 1;
+        e.bias = start;
+      }
+    }
+    uint16_t* bk = a->bucket.data() + (size_t)r * 256;
+    int32_t sidx = 0;
+    for (int32_t b = 0; b < 256; ++b) {
+      const int32_t cum = b << 8;
+      while (sidx + 2 < size && cdf[sidx + 1] <= cum) ++sidx;
+      bk[b] = (uint16_t)sidx;
+    }
+  }
+  if (g_accel.size() > 64) g_accel.clear();  // tables are long-lived; this only bounds pathological churn
+  g_accel[key] = a;
+  return a;
+}
+
 struct Encoder {
   uint64_t x = kRansL;
   std::vector<uint32_t> words;  // in emission order (the stream stores them reversed)
 
-  inline void put(uint32_t start, uint32_t freq) {
-    const uint64_t x_max = ((kRansL >> kPrecision) << 32) * (uint64_t)freq;
+  inline void put(const EncSym& e) {
+    const uint64_t x_max = ((kRansL >> kPrecision) << 32) * (uint64_t)e.freq;
     if (x >= x_max) { words.push_back((uint32_t)x); x >>= 32; }
-    x = ((x / freq) << kPrecision) + (x % freq) + start;
+    const uint64_t q = (uint64_t)(((unsigned __int128)x * e.rcp_freq) >> 64) >> e.rcp_shift;   // == x / freq
+    x = x + e.bias + q * e.cmpl_freq;
   }
   inline void put_bits(uint32_t val) {
     const uint64_t x_max = ((kRansL >> 16) << 32) * (uint64_t)(1u << (16 - kBypassBits));
@@ -40,10 +111,11 @@ int64_t encode_one(const int32_t* symbols, const int32_t* indexes, int64_t n, co
                    int64_t out_cap) {
   Encoder enc;
   enc.words.reserve((size_t)(n / 4 + 16));
+  const std::shared_ptr<const TableAccel> accel = table_accel(t);
+  const EncSym* esym = accel->enc.data();
   for (int64_t i = n - 1; i >= 0; --i) {
     const int32_t ci = indexes[i];
     if (ci < 0 || ci >= t->n_cdf) return std::numeric_limits<int64_t>::min();
-    const int32_t* cdf = t->cdfs + (int64_t)ci * t->cdf_stride;
     const int32_t max_value = t->cdf_sizes[ci] - 2;
     int32_t value = symbols[i] - t->offsets[ci];
     bool escape = false;
@@ -59,7 +131,7 @@ int64_t encode_one(const int32_t* symbols, const int32_t* indexes, int64_t n, co
       enc.put_bits((uint32_t)rem);
       for (int32_t r = 0; r < full; ++r) enc.put_bits((uint32_t)kBypassMax);
     }
-    enc.put((uint32_t)cdf[value], (uint32_t)(cdf[value + 1] - cdf[value]));
+    enc.put(esym[(int64_t)ci * t->cdf_stride + value]);
   }
   const int64_t nbytes = 4 * ((int64_t)enc.words.size() + 2);
   if (nbytes > out_cap) return -nbytes;
@@ -88,6 +160,8 @@ struct Decoder {
 };
 
 int decode_some(Decoder* d, const int32_t* indexes, int64_t n, const crdr_cdf_tables* t, int32_t* out) {
+  const std::shared_ptr<const TableAccel> accel = table_accel(t);
+  const uint16_t* bucket = accel->bucket.data();
   for (int64_t i = 0; i < n; ++i) {
     const int32_t ci = indexes[i];
     if (ci < 0 || ci >= t->n_cdf) return 1;
@@ -95,9 +169,9 @@ int decode_some(Decoder* d, const int32_t* indexes, int64_t n, const crdr_cdf_ta
     const int32_t size = t->cdf_sizes[ci];
     const int32_t max_value = size - 2;
     const int32_t cum = (int32_t)(d->x & ((1u << kPrecision) - 1));
-    // first entry strictly greater than cum (the tables are increasing)
-    const int32_t* it = std::upper_bound(cdf, cdf + size, cum);
-    const int32_t s = (int32_t)(it - cdf) - 1;
+    // slot s with cdf[s] <= cum < cdf[s+1] (the tables are increasing): start at the bucket's first slot
+    int32_t s = bucket[(int64_t)ci * 256 + (cum >> 8)];
+    while (s + 2 < size && cdf[s + 1] <= cum) ++s;
     const uint32_t start = (uint32_t)cdf[s], freq = (uint32_t)(cdf[s + 1] - cdf[s]);
     d->x = (uint64_t)freq * (d->x >> kPrecision) + (d->x & ((1ull << kPrecision) - 1)) - start;
     if (d->x < kRansL) d->x = (d->x << 32) | d->next_word();

@@ -109,6 +109,46 @@ def test_rans_edge_cases(product_gc):
         assert all(np.array_equal(a, b) for a, b in zip(back, syms))
 
 
+def test_rans_reciprocal_encoder_and_bucketed_decoder_match_oracle(oracle):
+    """The product coder replaces the 64-bit division by a reciprocal multiply and the CDF binary search by a bucket
+    index: both must reproduce the plain-C oracle coder byte for byte, also for frequency-1 and dominant symbols."""
+    from crdr_b200 import rans
+    from compressai import ans
+    rng = np.random.default_rng(11)
+    rows, width = 9, 40
+    cdfs = np.zeros((rows, width + 2), np.int32)
+    sizes = np.zeros(rows, np.int32)
+    for r in range(rows):
+        n = int(rng.integers(3, width))
+        if r == 0:      # many frequency-1 symbols and one dominant symbol
+            f = np.ones(n, np.int64); f[n // 2] = 65536 - (n - 1)
+        elif r == 1:    # powers of two (reciprocal edge cases)
+            f = np.array([2 ** int(k) for k in rng.integers(0, 11, n)], np.int64); f[0] += 65536 - f.sum()
+            assert f[0] > 0
+        else:
+            f = rng.integers(1, 4000, n).astype(np.int64); f[-1] += 65536 - f.sum()
+            while f[-1] <= 0:
+                f = np.maximum(f // 2, 1); f[-1] = 1; f[-1] += 65536 - f.sum()
+        cdfs[r, 1:n + 1] = np.cumsum(f)
+        assert cdfs[r, n] == 65536
+        sizes[r] = n + 1
+    offs = -(sizes - 1) // 2
+    T = rans.Tables(cdfs, sizes, offs.astype(np.int32))
+    count = 200_000
+    idx = rng.integers(0, rows, count).astype(np.int32)
+    sym = np.empty(count, np.int32)
+    for r in range(rows):
+        m = idx == r
+        lo, hi = int(offs[r]) - 3, int(offs[r]) + int(sizes[r]) + 2     # includes escapes on both sides
+        sym[m] = rng.integers(lo, hi, int(m.sum()))
+    got = rans.encode(sym, idx, T)
+    want = ans.RansEncoder().encode_with_indexes(sym, idx, cdfs, sizes, offs.astype(np.int32))
+    assert got == want
+    dec = rans.Decoder(got)
+    back = np.concatenate([dec.decode_stream(idx[:12345], T), dec.decode_stream(idx[12345:], T)])
+    assert np.array_equal(back, sym)
+
+
 def test_pmf_to_quantized_cdf_properties(oracle):
     from crdr_b200 import rans
     from compressai import ans
