@@ -92,17 +92,22 @@ std::shared_ptr<const TableAccel> table_accel(const crdr_cdf_tables* t) {
 
 struct Encoder {
   uint64_t x = kRansL;
-  std::vector<uint32_t> words;  // in emission order (the stream stores them reversed)
+  uint32_t* wp = nullptr;  // next free word, emission order (the stream stores the words reversed)
 
+  // branch-free renormalisation: the low word is always stored, the pointer only advances when it was due
+  inline void renorm(uint64_t x_max) {
+    const bool emit = x >= x_max;
+    *wp = (uint32_t)x;
+    wp += emit;
+    x = emit ? (x >> 32) : x;
+  }
   inline void put(const EncSym& e) {
-    const uint64_t x_max = ((kRansL >> kPrecision) << 32) * (uint64_t)e.freq;
-    if (x >= x_max) { words.push_back((uint32_t)x); x >>= 32; }
+    renorm(((kRansL >> kPrecision) << 32) * (uint64_t)e.freq);
     const uint64_t q = (uint64_t)(((unsigned __int128)x * e.rcp_freq) >> 64) >> e.rcp_shift;   // == x / freq
     x = x + e.bias + q * e.cmpl_freq;
   }
   inline void put_bits(uint32_t val) {
-    const uint64_t x_max = ((kRansL >> 16) << 32) * (uint64_t)(1u << (16 - kBypassBits));
-    if (x >= x_max) { words.push_back((uint32_t)x); x >>= 32; }
+    renorm(((kRansL >> 16) << 32) * (uint64_t)(1u << (16 - kBypassBits)));
     x = (x << kBypassBits) | val;
   }
 };
@@ -110,38 +115,41 @@ struct Encoder {
 int64_t encode_one(const int32_t* symbols, const int32_t* indexes, int64_t n, const crdr_cdf_tables* t, uint8_t* out,
                    int64_t out_cap) {
   Encoder enc;
-  enc.words.reserve((size_t)(n / 4 + 16));
   const std::shared_ptr<const TableAccel> accel = table_accel(t);
   const EncSym* esym = accel->enc.data();
+  // a table symbol emits at most one word; an escape adds at most 2 + 8 + 1 nibbles (raw < 2^32) = two more words
+  std::unique_ptr<uint32_t[]> words(new uint32_t[(size_t)(3 * n + 8)]);  // uninitialised on purpose
+  enc.wp = words.get();
+  const int32_t n_cdf = t->n_cdf;
+  const int32_t* offsets = t->offsets;
+  const int32_t* sizes = t->cdf_sizes;
+  const int64_t stride = t->cdf_stride;
   for (int64_t i = n - 1; i >= 0; --i) {
     const int32_t ci = indexes[i];
-    if (ci < 0 || ci >= t->n_cdf) return std::numeric_limits<int64_t>::min();
-    const int32_t max_value = t->cdf_sizes[ci] - 2;
-    int32_t value = symbols[i] - t->offsets[ci];
-    bool escape = false;
-    uint32_t raw = 0;
-    if (value < 0) { raw = (uint32_t)(-2 * value - 1); value = max_value; escape = true; }
-    else if (value >= max_value) { raw = (uint32_t)(2 * (value - max_value)); value = max_value; escape = true; }
-    if (escape) {
+    if ((uint32_t)ci >= (uint32_t)n_cdf) return std::numeric_limits<int64_t>::min();
+    const int32_t max_value = sizes[ci] - 2;
+    int32_t value = symbols[i] - offsets[ci];
+    if (value < 0 || value >= max_value) {
+      const uint32_t raw = value < 0 ? (uint32_t)(-2 * (int64_t)value - 1) : (uint32_t)(2 * ((int64_t)value - max_value));
+      value = max_value;
       int32_t nb = 0;
-      while ((raw >> (nb * kBypassBits)) != 0) ++nb;
+      while (nb < 8 && (raw >> (nb * kBypassBits)) != 0) ++nb;
       // forward order is: [run of 15s][remainder][nibble 0 .. nibble nb-1]; feed it reversed
       for (int32_t j = nb - 1; j >= 0; --j) enc.put_bits((raw >> (j * kBypassBits)) & kBypassMax);
       int32_t full = nb / kBypassMax, rem = nb % kBypassMax;
       enc.put_bits((uint32_t)rem);
       for (int32_t r = 0; r < full; ++r) enc.put_bits((uint32_t)kBypassMax);
     }
-    enc.put(esym[(int64_t)ci * t->cdf_stride + value]);
+    enc.put(esym[(int64_t)ci * stride + value]);
   }
-  const int64_t nbytes = 4 * ((int64_t)enc.words.size() + 2);
+  const int64_t nwords = (int64_t)(enc.wp - words.get());
+  const int64_t nbytes = 4 * (nwords + 2);
   if (nbytes > out_cap) return -nbytes;
-  uint32_t* o = reinterpret_cast<uint32_t*>(out);
   uint32_t w0 = (uint32_t)enc.x, w1 = (uint32_t)(enc.x >> 32);
   std::memcpy(out, &w0, 4);
   std::memcpy(out + 4, &w1, 4);
-  (void)o;
   size_t k = 8;
-  for (size_t j = enc.words.size(); j-- > 0; k += 4) std::memcpy(out + k, &enc.words[j], 4);
+  for (int64_t j = nwords; j-- > 0; k += 4) std::memcpy(out + k, &words[(size_t)j], 4);
   return nbytes;
 }
 
