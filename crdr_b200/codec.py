@@ -114,7 +114,12 @@ class AnalysisEngine:
     def __init__(self, sd, device, precision=X3, engine=nv.ENGINE_TCGEN05):
         cfg = NetCfg(device, precision, engine)
         self.cfg = cfg
-        self.conv1 = Conv(sd, "conv1", cfg, stride=2, padding=2, cin_pad=8)
+        # conv1 (5x5, stride 2, 3 -> C; elic_autoencoder.py:42) runs as a 1x1 convolution over the im2col'd image written
+        # by crdr_image_to_patches: patch channel (kh*5+kw)*3+c, 75 real + 53 zero = 128 = two K blocks on the patch engine
+        w1 = sd["conv1.weight"]                                        # (C, 3, 5, 5)
+        wp = torch.zeros(w1.shape[0], 128, 1, 1, dtype=w1.dtype)
+        wp[:, :75, 0, 0] = w1.permute(0, 2, 3, 1).reshape(w1.shape[0], 75)
+        self.conv1 = Conv({"w.weight": wp, "w.bias": sd["conv1.bias"]}, "w", cfg)
         self.conv2 = Conv(sd, "conv2", cfg, stride=2, padding=2)
         self.conv3 = Conv(sd, "conv3", cfg, stride=2, padding=2)
         self.conv4 = Conv(sd, "conv4", cfg, stride=2, padding=2)
@@ -132,7 +137,7 @@ class AnalysisEngine:
         return x
 
     def run(self, img, q):
-        """img: Act (n, H, W, 8) -> (y planes Act, y fp32 NHWC tensor)."""
+        """img: Act (n, H/2, W/2, 128) image patches (crdr_image_to_patches) -> (y planes Act, y fp32 NHWC tensor)."""
         g = [gn.vectors(q) for gn in self.gains]
         x = self.conv1(img, scale=g[0][0], shift=g[0][1])
         x = self._blocks(self.block1, x, g[1])

@@ -58,6 +58,7 @@ int nhwc_to_nchw_launch(const float* x, int x_cs, int x_coff, int n, int hw, int
 int affine_to_planes_launch(const float* x, int x_cs, int x_coff, int64_t m, int c, const float* scale,
                             const float* shift, crdr_planes out, cudaStream_t st);
 int image_to_planes_launch(const float* img, int n, int h, int w, int hp, int wp, crdr_planes out, cudaStream_t st);
+int image_to_patches_launch(const float* img, int n, int h, int w, int hp, int wp, crdr_planes out, cudaStream_t st);
 int planes_to_image_launch(const float* x, int x_cs, int n, int hp, int wp, int h, int w, float* img, cudaStream_t st);
 int phases_to_image_launch(const float* x, int x_cs, int n, int hb, int wb, int h, int w, float* img, cudaStream_t st);
 int bits_launch(const float* lik, int n, int64_t per, float* bits, cudaStream_t st);
@@ -115,6 +116,11 @@ int crdr_affine_to_planes(const float* x, int32_t x_cs, int32_t x_coff, int64_t 
 int crdr_image_to_planes(const float* img, int32_t n, int32_t h, int32_t w, int32_t hp, int32_t wp, crdr_planes out,
                          void* stream) {
   return image_to_planes_launch(img, n, h, w, hp, wp, out, (cudaStream_t)stream);
+}
+
+int crdr_image_to_patches(const float* img, int32_t n, int32_t h, int32_t w, int32_t hp, int32_t wp, crdr_planes out,
+                          void* stream) {
+  return image_to_patches_launch(img, n, h, w, hp, wp, out, (cudaStream_t)stream);
 }
 
 int crdr_planes_to_image(const float* x, int32_t x_cs, int32_t n, int32_t hp, int32_t wp, int32_t h, int32_t w,

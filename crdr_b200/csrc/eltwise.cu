@@ -246,6 +246,43 @@ __global__ void __launch_bounds__(256) image_to_planes_kernel(const float* __res
   if (out.lo) *(uint4*)((__half*)out.lo + o) = *(const uint4*)ll;
 }
 
+// im2col of the first analysis layer (5x5, stride 2, padding 2 on the reflect-padded image): one thread per
+// (output pixel, group of 8 patch channels); patch channel k = (kh * 5 + kw) * 3 + c for k < 75, zero up to 128.
+// The layer then runs as a 1x1 convolution with K = 128 on the patch engine (2 K blocks instead of a 25-tap gather).
+__global__ void __launch_bounds__(256) image_to_patches_kernel(const float* __restrict__ img, int n, int h, int w,
+                                                               int hp, int wp, crdr_planes out, uint32_t* status) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ho = hp / 2, wo = wp / 2;
+  const int64_t total = (int64_t)n * ho * wo * 16;
+  if (idx >= total) return;
+  const int grp = (int)(idx & 15);
+  const int64_t pix = idx >> 4;
+  const int j = (int)(pix % wo);
+  const int64_t t = pix / wo;
+  const int i = (int)(t % ho);
+  const int b = (int)(t / ho);
+  __align__(16) __half hh[8], ll[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = grp * 8 + e;
+    float v = 0.f;
+    if (k < 75) {
+      const int tap = k / 3, c = k - 3 * tap;
+      const int kh = tap / 5, kw = tap - 5 * kh;
+      const int y = 2 * i + kh - 2, x = 2 * j + kw - 2;
+      if (y >= 0 && y < hp && x >= 0 && x < wp) {     // the convolution's own zero padding
+        const int sy = y < h ? y : 2 * (h - 1) - y;   // 'reflect' padding on the bottom / right edges
+        const int sx = x < w ? x : 2 * (w - 1) - x;
+        v = img[(((int64_t)b * 3 + c) * h + sy) * w + sx];
+      }
+    }
+    split_f16(v, hh[e], ll[e], status);
+  }
+  const int64_t o = pix * out.cs + out.coff + grp * 8;
+  *(uint4*)((__half*)out.hi + o) = *(const uint4*)hh;
+  if (out.lo) *(uint4*)((__half*)out.lo + o) = *(const uint4*)ll;
+}
+
 __global__ void __launch_bounds__(256) planes_to_image_kernel(const float* __restrict__ x, int x_cs, int n, int hp,
                                                               int wp, int h, int w, float* __restrict__ img) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -356,6 +393,19 @@ int image_to_planes_launch(const float* img, int n, int h, int w, int hp, int wp
   const int64_t total = (int64_t)n * hp * wp;
   image_to_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(img, n, h, w, hp, wp, out, status);
   return check_launch("image_to_planes_kernel");
+}
+
+int image_to_patches_launch(const float* img, int n, int h, int w, int hp, int wp, crdr_planes out, cudaStream_t st) {
+  if (n <= 0 || h <= 0 || w <= 0 || hp < h || wp < w || hp - h >= h || wp - w >= w || (hp & 1) || (wp & 1) ||
+      out.cs % 8 || out.coff % 8 || out.cs < out.coff + 128 || !out.hi) {
+    set_error("image_to_patches: bad shape (h=%d w=%d hp=%d wp=%d cs=%d)", h, w, hp, wp, out.cs);
+    return CRDR_ERR_BAD_SHAPE;
+  }
+  uint32_t* status = device_status_word();
+  if (!status) return CRDR_ERR_CUDA;
+  const int64_t total = (int64_t)n * (hp / 2) * (wp / 2) * 16;
+  image_to_patches_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(img, n, h, w, hp, wp, out, status);
+  return check_launch("image_to_patches_kernel");
 }
 
 int planes_to_image_launch(const float* x, int x_cs, int n, int hp, int wp, int h, int w, float* img, cudaStream_t st) {

@@ -81,8 +81,8 @@ class CodecEngine:
         n, _, h, w = images.shape
         hp, wp = self.padded(h, w)
         dev = images.device
-        img = Act.empty(n, hp, wp, 8, two=True, device=dev)
-        nv.check(L.crdr_image_to_planes(images.data_ptr(), n, h, w, hp, wp, img.planes(0), st))
+        img = Act.empty(n, hp // 2, wp // 2, 128, two=True, device=dev)   # im2col of g_a conv1 fused with the reflect pad
+        nv.check(L.crdr_image_to_patches(images.data_ptr(), n, h, w, hp, wp, img.planes(0), st))
         y_act, y32 = self.ga.run(img, q)
         z32 = self.ha.run(y_act)
         hz, wz = z32.shape[1:3]

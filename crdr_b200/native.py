@@ -76,7 +76,7 @@ class EbDesc(C.Structure):
 # every symbol include/crdr_b200.h declares (tests check the library exports all of them)
 SM100_SYMBOLS = [
     "crdr_abi_version", "crdr_last_error", "crdr_status_reset", "crdr_status_read", "crdr_conv2d",
-    "crdr_affine_to_planes", "crdr_image_to_planes", "crdr_planes_to_image", "crdr_phases_to_image", "crdr_nhwc_to_nchw",
+    "crdr_affine_to_planes", "crdr_image_to_planes", "crdr_image_to_patches", "crdr_planes_to_image", "crdr_phases_to_image", "crdr_nhwc_to_nchw",
     "crdr_gauss_quantize", "crdr_gauss_indexes", "crdr_gauss_dequantize", "crdr_eb_quantize",
     "crdr_eb_dequantize", "crdr_bits_from_likelihood", "crdr_max_abs",
 ]
@@ -104,6 +104,7 @@ def lib():
         L.crdr_conv2d.argtypes = [C.POINTER(ConvDesc), vp]
         L.crdr_affine_to_planes.argtypes = [vp, i32, i32, i64, i32, vp, vp, Planes, vp]
         L.crdr_image_to_planes.argtypes = [vp, i32, i32, i32, i32, i32, Planes, vp]
+        L.crdr_image_to_patches.argtypes = [vp, i32, i32, i32, i32, i32, Planes, vp]
         L.crdr_planes_to_image.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp]
         L.crdr_phases_to_image.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp]
         L.crdr_nhwc_to_nchw.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]

@@ -141,6 +141,11 @@ int crdr_affine_to_planes(const float* x, int32_t x_cs, int32_t x_coff, int64_t 
  * 8 channels (3 real + 5 zero).  Replaces BaseModel.data_preprocess/_pad_image (base_model.py:35-43,145-152). */
 int crdr_image_to_planes(const float* img, int32_t n, int32_t h, int32_t w, int32_t hp, int32_t wp,
                          crdr_planes out, void* stream);
+/* Same pre-processing fused with the im2col of the first analysis layer (ElicEncoder.conv1: 5x5, stride 2, padding 2,
+ * elic_autoencoder.py:42): output NHWC planes (n, hp/2, wp/2, >=128) whose channel (kh*5+kw)*3+c is the padded image at
+ * (2i+kh-2, 2j+kw-2, c) (zero outside), channels 75..127 zero.  conv1 then runs as a 1x1 convolution with K = 128. */
+int crdr_image_to_patches(const float* img, int32_t n, int32_t h, int32_t w, int32_t hp, int32_t wp,
+                          crdr_planes out, void* stream);
 /* Post-processing: NHWC fp32 (n,hp,wp,cs) first 3 channels -> crop (h,w) -> clamp(-1,1) -> NCHW fp32.
  * Replaces data_postprocess/_crop_image (base_model.py:45-57,165-167). */
 int crdr_planes_to_image(const float* x, int32_t x_cs, int32_t n, int32_t hp, int32_t wp, int32_t h, int32_t w,

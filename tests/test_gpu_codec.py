@@ -132,6 +132,51 @@ def test_kodak_size_roundtrip_determinism_batch_invariance(models):
     assert torch.equal(img_d, img)
 
 
+@pytest.mark.parametrize("h,w", [(1365, 2048), (2160, 3840)], ids=["clic_1365x2048", "uhd_2160x3840"])
+def test_large_shapes_roundtrip(models, h, w):
+    """BASELINE configs[2] / [3] shapes (pad to 1408x2048 / 2176x3840): size-independent properties only."""
+    import fixtures
+    model, _ = models(True)
+    x = fixtures.image(1, h, w, seed=h)
+    q, beta = 2.0, 3.84
+    out = model.compress(x, q)
+    again = model.compress_batch(x, q)[0]
+    assert out["string_list"] == again["string_list"]                     # determinism at this size
+    hp, wp = -(-h // 64) * 64, -(-w // 64) * 64
+    assert out["y_hat"].shape == (1, 320, hp // 16, wp // 16) and out["z_hat"].shape == (1, 192, hp // 64, wp // 64)
+    img, z_hat, y_hat = model.decompress(out["string_list"], beta=beta)
+    assert img.shape == (1, 3, h, w)
+    assert torch.equal(y_hat, out["y_hat"]) and torch.equal(z_hat, out["z_hat"])   # compress.py:126 invariant
+    assert torch.isfinite(img).all() and float(img.abs().max()) <= 1.0
+    # eval forward shares every kernel with the codec: same reconstruction, same rate
+    fwd = model.run_model(x, rate_ind=q, beta=beta, is_train=False)
+    assert torch.equal(fwd["fake_images"], img)
+    bits = out["pred_y_bit"] + out["pred_z_bit"]
+    real_bits = 8 * sum(len(sb) for sb in out["string_list"][1:])
+    assert abs(float(fwd["bpp"]) * h * w - bits) <= 1e-3 * bits
+    assert 0.8 * bits <= real_bits <= 1.25 * bits + 4096                   # coded size tracks the entropy estimate
+
+
+def test_chunk_pipelining_is_transparent(models):
+    """The host/device chunk pipelining of the codec API must not change a byte or a pixel."""
+    import fixtures
+    model, _ = models(True)
+    x = fixtures.image(9, 128, 192, seed=77)
+    ref_chunks = model.pipeline_chunks
+    results = []
+    try:
+        for k in (1, 2, 3):
+            model.pipeline_chunks = k
+            outs = model.compress_batch(x, 1.5)
+            img, z_hat, y_hat = model.decompress_batch([o["string_list"] for o in outs], beta=2.0)
+            results.append(([o["string_list"] for o in outs], [o["pred_y_bit"] for o in outs], img, y_hat))
+    finally:
+        model.pipeline_chunks = ref_chunks
+    for r in results[1:]:
+        assert r[0] == results[0][0] and r[1] == results[0][1]
+        assert torch.equal(r[2], results[0][2]) and torch.equal(r[3], results[0][3])
+
+
 def test_ragged_and_small_sizes(models, oracle):
     import fixtures
     model, sd = models(True)
@@ -158,6 +203,13 @@ def test_eltwise_kernels_against_torch():
     ref = F.pad(img, (0, 14, 0, 27), mode="reflect")
     got = a.to_nchw()
     assert (got[:, :3] - ref).abs().max() < 2e-7 and got[:, 3:].abs().max() == 0
+    # image -> im2col patches of the first 5x5 stride-2 layer: equals unfold of the reflect-padded image (zero conv padding)
+    pa = Act.empty(2, 32, 32, 128)
+    nv.check(L.crdr_image_to_patches(img.data_ptr(), 2, 37, 50, 64, 64, pa.planes(0), st))
+    cols = F.unfold(ref, kernel_size=5, padding=2, stride=2).reshape(2, 3, 25, 32, 32)      # (n, c, tap, i, j)
+    want = cols.permute(0, 2, 1, 3, 4).reshape(2, 75, 32, 32)                                # channel = tap * 3 + c
+    gotp = pa.to_nchw()
+    assert (gotp[:, :75] - want).abs().max() < 2e-7 and gotp[:, 75:].abs().max() == 0
     # planes -> image: crop + clamp
     x = (torch.randn(2, 16, 24, 4, generator=g) * 2).cuda()
     out = torch.empty(2, 3, 13, 20, device="cuda")
