@@ -357,11 +357,17 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
     pipeline_chunks = 2
     pipeline_min_images = 8
 
+    pipeline_weights = None  # optional relative chunk sizes, e.g. (2, 1): the last chunk's host work is the exposed tail
+
     def _chunks(self, n):
         k = self.pipeline_chunks if n >= self.pipeline_min_images else 1
         k = max(1, min(k, n))
-        edges = [round(i * n / k) for i in range(k + 1)]
-        return [(edges[i], edges[i + 1]) for i in range(k)]
+        w = list(self.pipeline_weights) if self.pipeline_weights and len(self.pipeline_weights) == k else [1] * k
+        tot, acc, edges = float(sum(w)), 0.0, [0]
+        for wi in w:
+            acc += wi
+            edges.append(int(round(acc * n / tot)))
+        return [(edges[i], edges[i + 1]) for i in range(k) if edges[i + 1] > edges[i]]
 
     def _run_chunks(self, chunks, fn):
         """fn(k, lo, hi) for every chunk, concurrently on side streams; returns the list of results."""
@@ -370,7 +376,10 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
         dev = self.engine().device
         main = torch.cuda.current_stream(dev)
         if not hasattr(self, "_side_streams") or len(self._side_streams) < len(chunks):
-            self._side_streams = [torch.cuda.Stream(device=dev) for _ in chunks]
+            # earlier chunks get the higher stream priority: with equal priorities the chunks' (full-GPU, persistent)
+            # kernels interleave one for one, every chunk finishes at the end and no host work overlaps anything
+            k = len(chunks)
+            self._side_streams = [torch.cuda.Stream(device=dev, priority=max(i - (k - 1), -5)) for i in range(k)]
         if not hasattr(self, "_pool") or self._pool._max_workers < len(chunks):
             from concurrent.futures import ThreadPoolExecutor
             self._pool = ThreadPoolExecutor(max_workers=len(chunks), thread_name_prefix="crdr-chunk")

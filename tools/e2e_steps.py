@@ -9,6 +9,8 @@ BETAS = [0.0, 3.84]
 model, _ = fixtures.build_model(seed=0, calibrated=True)
 import os
 model.pipeline_chunks = int(os.environ.get('CHUNKS', '2'))
+if os.environ.get('WEIGHTS'):
+    model.pipeline_weights = tuple(float(v) for v in os.environ['WEIGHTS'].split(','))
 x = fixtures.image(24, 512, 768, seed=100).pin_memory()
 host = None
 def T(): torch.cuda.synchronize(); return time.perf_counter()
