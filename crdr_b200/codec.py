@@ -315,29 +315,42 @@ class CharmEngine:
                 self.refine(T, s, yq32, yhat32)
         return yhat32, sym, idx, lik
 
-    def decode(self, T, gp, symbol_source):
-        """Decoder-side pass.  ``symbol_source(first_slice, count, idx_nchw)`` returns the int32 NCHW symbols
-        (device tensor, full [n, yc, h, w] buffer with that slice range filled) for the group.
-        Returns y_hat fp32 NHWC."""
+    def decode_steps(self, T, gp):
+        """Decoder-side pass as a generator: yields ``(first_slice, count, idx_nchw)`` whenever the symbols of a slice group
+        are needed (``idx_nchw`` holds the CDF indexes of that group) and expects the int32 NCHW symbols (device tensor,
+        full [n, yc, h, w] buffer with that slice range filled) to be sent back.  Returns y_hat fp32 NHWC.
+        The generator form lets the caller interleave several independent batches on one stream."""
         n, h, w = T.n, T.h, T.w
         dev = T.hi.device
         ms = torch.empty((n, h, w, 2 * self.yc), dtype=torch.float32, device=dev)
         yq32 = torch.empty((n, h, w, self.yc), dtype=torch.float32, device=dev)
         yhat32 = torch.empty((n, h, w, self.yc), dtype=torch.float32, device=dev)
         idx = torch.empty((n, self.yc, h, w), dtype=torch.int32, device=dev)
-        st, L = nv.stream_handle(), nv.lib()
+        L = nv.lib()
         for grp in self.groups():
             for s in grp:
                 self.params(T, s, ms)
                 d = self.gauss_desc(gp, T, s, 1, n, h * w, ms, idx=idx)
-                nv.check(L.crdr_gauss_indexes(C.byref(d), st))
-            sym = symbol_source(grp[0], len(grp), idx)
+                nv.check(L.crdr_gauss_indexes(C.byref(d), nv.stream_handle()))
+            sym = yield grp[0], len(grp), idx
             for s in grp:
                 d = self.gauss_desc(gp, T, s, 1, n, h * w, ms, yq32=yq32, sym=sym)
-                nv.check(L.crdr_gauss_dequantize(C.byref(d), st))
+                nv.check(L.crdr_gauss_dequantize(C.byref(d), nv.stream_handle()))
             for s in grp:
                 self.refine(T, s, yq32, yhat32)
         return yhat32
+
+    def decode(self, T, gp, symbol_source):
+        """Decoder-side pass.  ``symbol_source(first_slice, count, idx_nchw)`` returns the int32 NCHW symbols
+        (device tensor, full [n, yc, h, w] buffer with that slice range filled) for the group.
+        Returns y_hat fp32 NHWC."""
+        steps = self.decode_steps(T, gp)
+        try:
+            req = next(steps)
+            while True:
+                req = steps.send(symbol_source(*req))
+        except StopIteration as done:
+            return done.value
 
 
 class SynthesisEngine:

@@ -350,14 +350,15 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
                     bpp=y_bpp + z_bpp, y_q_likelihood=a["y_lik"], z_q_likelihood=a["z_lik"], qbpp=y_bpp + z_bpp)
 
     # -- codec -------------------------------------------------------------------------------------
-    # Host entropy coding and device arithmetic of one call overlap: a batch is cut into `pipeline_chunks` chunks,
-    # each driven by its own host thread on its own CUDA stream.  While one chunk sits in the host coder (ctypes call,
-    # GIL released) or waits for a copy, the device works on the other chunk.  Results are per image and independent of
-    # the chunking (deterministic kernels, one rANS stream per image).
+    # Host entropy coding and device arithmetic of one call overlap through a software pipeline on ONE stream and ONE host
+    # thread: the batch is cut into `pipeline_chunks` chunks whose device segments are enqueued in order, and whenever a
+    # chunk needs the host coder (after an event on its device -> host copy) the device already holds the other
+    # chunks' next segments.  (Two host threads on two streams were tried first: the chunks' full-GPU persistent kernels
+    # interleave one for one, both chunks reach the host coder at the same moment and nothing overlaps.)
+    # Results are per image and independent of the chunking (deterministic kernels, one rANS stream per image).
     pipeline_chunks = 2
     pipeline_min_images = 8
-
-    pipeline_weights = None  # optional relative chunk sizes, e.g. (2, 1): the last chunk's host work is the exposed tail
+    pipeline_weights = None  # optional relative chunk sizes, e.g. (2, 1)
 
     def _chunks(self, n):
         k = self.pipeline_chunks if n >= self.pipeline_min_images else 1
@@ -369,43 +370,35 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
             edges.append(int(round(acc * n / tot)))
         return [(edges[i], edges[i + 1]) for i in range(k) if edges[i + 1] > edges[i]]
 
-    def _run_chunks(self, chunks, fn):
-        """fn(k, lo, hi) for every chunk, concurrently on side streams; returns the list of results."""
-        if len(chunks) == 1:
-            return [fn(0, *chunks[0])]
-        dev = self.engine().device
-        main = torch.cuda.current_stream(dev)
-        if not hasattr(self, "_side_streams") or len(self._side_streams) < len(chunks):
-            # earlier chunks get the higher stream priority: with equal priorities the chunks' (full-GPU, persistent)
-            # kernels interleave one for one, every chunk finishes at the end and no host work overlaps anything
-            k = len(chunks)
-            self._side_streams = [torch.cuda.Stream(device=dev, priority=max(i - (k - 1), -5)) for i in range(k)]
-        if not hasattr(self, "_pool") or self._pool._max_workers < len(chunks):
-            from concurrent.futures import ThreadPoolExecutor
-            self._pool = ThreadPoolExecutor(max_workers=len(chunks), thread_name_prefix="crdr-chunk")
-
-        def work(k, lo, hi):
-            torch.cuda.set_device(dev)
-            st = self._side_streams[k]
-            st.wait_stream(main)
-            with torch.cuda.stream(st), torch.no_grad():
-                r = fn(k, lo, hi)
-            return r
-
-        futs = [self._pool.submit(work, k, lo, hi) for k, (lo, hi) in enumerate(chunks)]
-        res = [f.result() for f in futs]
-        for st in self._side_streams[:len(chunks)]:
-            main.wait_stream(st)
-        return res
+    @staticmethod
+    def _drive(gens):
+        """Round-robin scheduler of chunk generators.  A generator yields a recorded CUDA event when it needs the host
+        (its device -> host copy is complete once the event is); it is resumed after the event, runs its host stage,
+        enqueues its next device segment and yields again.  Returns the generators' return values in order."""
+        from collections import deque
+        results = [None] * len(gens)
+        queue = deque()
+        for i, g in enumerate(gens):          # prime: every chunk's first device segment is enqueued, in order
+            try:
+                queue.append((i, g, next(g)))
+            except StopIteration as done:
+                results[i] = done.value
+        while queue:
+            i, g, ev = queue.popleft()
+            ev.synchronize()
+            try:
+                queue.append((i, g, g.send(None)))
+            except StopIteration as done:
+                results[i] = done.value
+        return results
 
     @staticmethod
-    def _on_main(t):
-        """A tensor produced on a side stream that the caller will use on the current stream."""
-        if t is not None and t.is_cuda:
-            t.record_stream(torch.cuda.current_stream(t.device))
-        return t
+    def _event():
+        ev = torch.cuda.Event()
+        ev.record()
+        return ev
 
-    def _compress_chunk(self, tag, real_images, rate_ind, return_tensors, coder_threads):
+    def _compress_gen(self, tag, real_images, rate_ind, return_tensors, coder_threads):
         eng = self.engine()
         q = self._q(rate_ind)
         x = self._to_device(real_images)
@@ -419,7 +412,9 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
                                pp.fetch(tag + "y_idx", a["y_idx"]))
         y_bits, z_bits, y_max = (pp.fetch(tag + "y_bits", y_bits), pp.fetch(tag + "z_bits", z_bits),
                                  pp.fetch(tag + "y_max", y_max))
-        nv.status_check()  # synchronises the stream: the pinned buffers are valid from here
+        if return_tensors:
+            y_hat = eng.to_nchw(a["yhat32"])
+        yield self._event()  # the pinned buffers are valid once this event is
         z_sym, y_sym, y_idx = z_sym.numpy(), y_sym.numpy(), y_idx.numpy()
         y_bits, z_bits, y_max = y_bits.numpy().copy(), z_bits.numpy().copy(), y_max.numpy().copy()
         zc, hz, wz = z_sym.shape[1:]
@@ -427,8 +422,6 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
         z_strs = rans.encode_batch([z_sym[i] for i in range(n)], [zi] * n, self.entropy_model_z.coder_tables(), coder_threads)
         y_strs = rans.encode_batch([y_sym[i] for i in range(n)], [y_idx[i] for i in range(n)],
                                    self.entropy_model_y.coder_tables(), coder_threads)
-        if return_tensors:
-            y_hat = eng.to_nchw(a["yhat32"])
         out = []
         for i in range(n):
             header = self.header_handler.encode((h, w), rate_ind=q, max_abs=float(y_max[i]))
@@ -436,8 +429,8 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
                  "pred_y_bit": float(y_bits[i]), "pred_y_bpp": float(y_bits[i]) / (h * w),
                  "pred_z_bit": float(z_bits[i]), "pred_z_bpp": float(z_bits[i]) / (h * w)}
             if return_tensors:
-                r.update(z_hat=self._on_main(a["z_hat"])[i:i + 1], y_hat=self._on_main(y_hat)[i:i + 1],
-                         z_likelihood=self._on_main(a["z_lik"])[i:i + 1], y_likelihood=self._on_main(a["y_lik"])[i:i + 1])
+                r.update(z_hat=a["z_hat"][i:i + 1], y_hat=y_hat[i:i + 1], z_likelihood=a["z_lik"][i:i + 1],
+                         y_likelihood=a["y_lik"][i:i + 1])
             out.append(r)
         return out
 
@@ -448,9 +441,9 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
             raise RuntimeError("call codec_setup() before compress()")
         n = real_images.shape[0]
         with torch.cuda.device(self.engine().device):
-            self.engine().prepare(q=self._q(rate_ind))
-            res = self._run_chunks(self._chunks(n), lambda k, lo, hi: self._compress_chunk(
-                f"c{k}_", real_images[lo:hi], rate_ind, return_tensors, coder_threads))
+            res = self._drive([self._compress_gen(f"c{k}_", real_images[lo:hi], rate_ind, return_tensors, coder_threads)
+                               for k, (lo, hi) in enumerate(self._chunks(n))])
+            nv.status_check()
         return [r for chunk in res for r in chunk]
 
     @torch.no_grad()
@@ -459,7 +452,7 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
         assert n == 1, f"In compress mode, batchsize must be 1, but {n}"
         return self.compress_batch(real_images, rate_ind, return_tensors=True)[0]
 
-    def _decompress_chunk(self, tag, string_lists, h, w, q, beta, coder_threads):
+    def _decompress_gen(self, tag, string_lists, h, w, q, beta, coder_threads):
         eng = self.engine()
         n = len(string_lists)
         hp, wp = eng.padded(h, w)
@@ -477,23 +470,26 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
         hy, wy = T.h, T.w
         y_sym = torch.empty((n, self.yC, hy, wy), dtype=torch.int32, device=dev)
         sc = eng.charm.sc
-
-        def source(s0, cnt, idx):
-            c0, c1 = s0 * sc, (s0 + cnt) * sc
-            # device -> host: table indexes of this group (pinned, one sync)
-            ix_host = self._pinned.fetch(f"{tag}y_idx_{cnt}", idx[:, c0:c1].contiguous())
-            torch.cuda.current_stream().synchronize()
-            ix = ix_host.numpy()
-            sym_host = self._pinned.get(f"{tag}y_sym_{cnt}", (n, c1 - c0, hy, wy), torch.int32)
-            sv = sym_host.numpy().reshape(n, -1)
-            rans.decode_batch(y_dec, [ix[i] for i in range(n)], yt, coder_threads, outs=[sv[i] for i in range(n)])
-            y_sym[:, c0:c1].copy_(sym_host, non_blocking=True)  # host -> device: decoded symbols
-            return y_sym
-
-        yhat32 = eng.charm.decode(T, eng.gp, source)
+        steps = eng.charm.decode_steps(T, eng.gp)
+        try:
+            req = next(steps)
+            while True:
+                s0, cnt, idx = req
+                c0, c1 = s0 * sc, (s0 + cnt) * sc
+                # device -> host: table indexes of this group (pinned); the event also covers the previous group's
+                # host -> device symbol copy, so the pinned symbol buffer below may be reused
+                ix_host = self._pinned.fetch(f"{tag}y_idx_{cnt}", idx[:, c0:c1].contiguous())
+                yield self._event()
+                ix = ix_host.numpy()
+                sym_host = self._pinned.get(f"{tag}y_sym_{cnt}", (n, c1 - c0, hy, wy), torch.int32)
+                sv = sym_host.numpy().reshape(n, -1)
+                rans.decode_batch(y_dec, [ix[i] for i in range(n)], yt, coder_threads, outs=[sv[i] for i in range(n)])
+                y_sym[:, c0:c1].copy_(sym_host, non_blocking=True)  # host -> device: decoded symbols
+                req = steps.send(y_sym)
+        except StopIteration as done:
+            yhat32 = done.value
         img = eng.synthesis(yhat32, q, beta, (h, w))
         y_hat = eng.to_nchw(yhat32)
-        nv.status_check()
         return img, z_hat, y_hat
 
     @torch.no_grad()
@@ -510,12 +506,12 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
         q = heads[0]["rate_ind"]
         n = len(string_lists)
         with torch.cuda.device(self.engine().device):
-            self.engine().prepare(q=q, beta=beta)
-            res = self._run_chunks(self._chunks(n), lambda k, lo, hi: self._decompress_chunk(
-                f"d{k}_", string_lists[lo:hi], h, w, q, beta, coder_threads))
+            res = self._drive([self._decompress_gen(f"d{k}_", string_lists[lo:hi], h, w, q, beta, coder_threads)
+                               for k, (lo, hi) in enumerate(self._chunks(n))])
+            nv.status_check()
             if len(res) == 1:
                 return res[0]
-            return tuple(torch.cat([self._on_main(r[j]) for r in res], dim=0) for j in range(3))
+            return tuple(torch.cat([r[j] for r in res], dim=0) for j in range(3))
 
     @torch.no_grad()
     def decompress(self, string_list, beta=0.0):
