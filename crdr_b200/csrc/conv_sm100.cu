@@ -61,6 +61,7 @@ struct alignas(64) ConvKParams {
   // PATCH mode geometry
   int32_t ph, pw, dh_min, dw_min, ncb, tiles_h, tiles_w, patch_stages;
   int32_t cb_c0[kMaxCBlocks];
+  int32_t cb_ksteps[kMaxCBlocks];   // PATCH: K steps (of 16 channels) of a channel block that hold real channels (1..4)
   uint32_t tapoff[CRDR_MAX_TAPS];  // PATCH: byte offset of a tap's start row inside the halo patch
   int32_t m_total, nkb, cin, k_real, nplanes, stages, tmem_cols, use_tma;
   int32_t vec_planes_out, vec_f32_out, vec_res_planes, vec_res_f32, vec_trunk;
@@ -1211,6 +1212,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
         }
         const uint32_t d1 = tmem_base + kD1Base + (uint32_t)tb * kAccStride;
         int tap = 0, ck = 0, kk = 0;  // tap of this K block (PATCH), position inside the D0 chunk / the ring slot
+        int cb = 0;                   // channel block of this K block (PATCH)
         for (int kb = 0; kb < nkb; ++kb, ++g) {
           const bool chunk_first = ck == 0;
           const bool chunk_last = ck == chunk_kb - 1 || kb == nkb - 1;
@@ -1248,9 +1250,11 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
           const uint64_t b_hi = desc_b + (uint64_t)(bsrc >> 4);
           const uint64_t b_lo = desc_b + (uint64_t)((bsrc + b_bytes) >> 4);
           if (tr) t0 = clock64();
+          const int nks = PATCH ? P.cb_ksteps[cb] : kKBlk / 16;  // K steps of this block that hold real channels
           if (elected) {
 #pragma unroll
           for (int k = 0; k < kKBlk / 16; ++k) {
+            if (k >= nks) break;
             const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 descriptor units
             if (three) {
               umma_issue<CG2>(d0, a_hi + adv, b_hi + adv, idesc, (chunk_first && k == 0) ? 0u : 1u);
@@ -1271,6 +1275,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
           if (PATCH) {
             if (++tap == ntaps) {  // all taps of the channel block issued: the patch buffer may be refilled
               tap = 0;
+              ++cb;
               if (elected) umma_done<CG2>(smem_u32(&patch_empty_bar[pb]));
               patch_addr += patch_stage_bytes;
               if (++pb == P.patch_stages) { pb = 0; patch_par ^= 1u; patch_addr = smem_patch; }
@@ -1523,12 +1528,14 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     return CRDR_ERR_MISALIGNED;
   }
   const bool patch = d.k_order == 1;
-  int ncb = 0, cb_c0[kMaxCBlocks];
+  int ncb = 0, cb_c0[kMaxCBlocks], cb_ksteps[kMaxCBlocks];
   if (patch) {
     for (int sgi = 0; sgi < 2; ++sgi) {
       const int off = sgi ? d.seg1_off : d.seg0_off, len = sgi ? d.seg1_len : d.seg0_len;
       for (int b = 0; b * 64 < len; ++b) {
         if (ncb >= kMaxCBlocks) { set_error("conv2d: more than %d channel blocks", kMaxCBlocks); return CRDR_ERR_BAD_SHAPE; }
+        const int valid = len - 64 * b < 64 ? len - 64 * b : 64;
+        cb_ksteps[ncb] = (valid + 15) / 16;   // the zero-padded tail of a partial block is never multiplied
         cb_c0[ncb++] = d.in.coff + off + 64 * b;
       }
     }
@@ -1721,7 +1728,7 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     P.ph = kPatchTH + dh_max - dh_min;
     P.pw = kPatchTW + dw_max - dw_min;
     P.ncb = ncb;
-    for (int i = 0; i < ncb; ++i) P.cb_c0[i] = cb_c0[i];
+    for (int i = 0; i < ncb; ++i) { P.cb_c0[i] = cb_c0[i]; P.cb_ksteps[i] = cb_ksteps[i]; }
     for (int t = 0; t < d.ntaps; ++t) P.tapoff[t] = (uint32_t)((d.dh[t] - dh_min) * P.pw + (d.dw[t] - dw_min)) * 128u;
     P.tiles_h = (d.hb + kPatchTH - 1) / kPatchTH;
     P.tiles_w = (d.wb + kPatchTW - 1) / kPatchTW;
