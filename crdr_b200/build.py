@@ -26,7 +26,8 @@ def _stale(target, deps):
 def build_sm100(force=False, verbose=False):
     out = os.path.join(HERE, "libcrdr_sm100.so")
     if force or _stale(out, CU_DEPS):
-        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+        trace = ["-DCRDR_TRACE_EVENTS"] if os.environ.get("CRDR_BUILD_TRACE") else []  # tools/conv_events.py build
+        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", *trace,
                "-shared", "-Xcompiler", "-fPIC", "-o", out] + [os.path.join(CSRC, s) for s in CU_SOURCES] + ["-lcudart"]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

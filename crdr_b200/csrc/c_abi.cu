@@ -42,7 +42,8 @@ uint32_t* device_status_word() {
       return nullptr;
     }
     uint32_t* p = nullptr;
-    if (cudaMalloc(&p, 256) != cudaSuccess || cudaMemset(p, 0, 256) != cudaSuccess) {
+    // 256 bytes of status / cycle counters + a 64 KB event-trace area (bring-up: CRDR_CONV_TRACE=2)
+    if (cudaMalloc(&p, 256 + 65536) != cudaSuccess || cudaMemset(p, 0, 256 + 65536) != cudaSuccess) {
       set_error("cannot allocate the device status word: %s", cudaGetErrorString(cudaGetLastError()));
       return nullptr;
     }
@@ -101,6 +102,18 @@ int crdr_debug_counters(unsigned long long* out10) {
   if (!p) return CRDR_ERR_CUDA;
   cudaDeviceSynchronize();
   return cudaMemcpy(out10, p + 16, 80, cudaMemcpyDeviceToHost) == cudaSuccess ? CRDR_OK : CRDR_ERR_CUDA;
+}
+
+/* bring-up aid: event trace of CTA 0 of the last CRDR_CONV_TRACE=2 launch: three regions of 2600 (tag, clock) records;
+ * unused records are zero */
+int crdr_debug_events(uint32_t* out, int32_t max_words) {
+  uint32_t* p = device_status_word();
+  if (!p) return CRDR_ERR_CUDA;
+  cudaDeviceSynchronize();
+  const size_t bytes = (size_t)(max_words < 16384 ? max_words : 16384) * 4;
+  if (cudaMemcpy(out, p + 64, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return CRDR_ERR_CUDA;
+  cudaMemset(p + 64, 0, 65536);
+  return CRDR_OK;
 }
 
 int crdr_conv2d(const crdr_conv_desc* d, void* stream) {

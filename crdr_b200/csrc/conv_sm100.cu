@@ -591,6 +591,26 @@ __device__ __forceinline__ void prefetch_epilogue_operands(const crdr_conv_desc&
   }
 }
 
+#ifdef CRDR_TRACE_EVENTS
+// bring-up event trace (CRDR_CONV_TRACE=2, CTA 0 only): (tag << 24 | payload, clock) records behind the status words.
+// Three writer threads (epilogue warp 0 lane 0, MMA lane, patch producer) own one region each and count their records
+// in a register, so a record is two fire-and-forget stores (an atomic slot counter cost ~600 cycles per event).
+constexpr uint32_t kTraceRegion = 2600;  // records per region; 3 regions * 2600 * 8 B < 64 KB
+__device__ __forceinline__ void trace_event(uint32_t* status, uint32_t region, uint32_t& count, uint32_t tag, uint32_t payload) {
+  if (count < kTraceRegion) {
+    uint32_t* rec = status + 64 + 2 * (region * kTraceRegion + count);
+    rec[0] = (tag << 24) | (payload & 0xFFFFFFu);
+    rec[1] = (uint32_t)clock64();
+    ++count;
+  }
+}
+#define CRDR_EV(...) __VA_ARGS__
+#else
+// event trace hooks compile to nothing in the product build: present, they cost 4 % of the step (registers and code in
+// the hot loops); build with CRDR_BUILD_TRACE=1 python -m crdr_b200.build to use tools/conv_events.py
+#define CRDR_EV(...)
+#endif
+
 // ----------------------------------------------------------------------------------------------
 // The tcgen05 kernel: persistent CTAs (one per SM), static round-robin tile schedule.
 //   warps 0-3  : im2col gather producers (cp.async), also L2-prefetch the epilogue operands of the tile
@@ -1002,12 +1022,15 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
     };
 
     int jt = 0;  // tiles processed by this CTA
+    CRDR_EV(uint32_t ev_count = 0;)
     for (; cur.tile < num_tiles; ++jt) {
       const int n0 = (PATCH ? cur.nt : cur.tile % n_tiles) * BN;
       const int tb = split ? 0 : (jt & 1);
       Cursor nxt = cur;
       cursor_advance(nxt);
       const int64_t opix_next = cursor_pixel(nxt);
+      CRDR_EV(const bool ev = P.trace == 2 && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0;)
+      CRDR_EV(if (ev) trace_event(P.status, 0u, ev_count, 1u, (uint32_t)jt);)  // epilogue: tile start
       const int c0_next = (PATCH ? nxt.nt : nxt.tile % n_tiles) * BN + ch_begin * 16;
       if (staged) {
         cp_async_wait<0>();  // this lane's copies for `tile` have landed ...
@@ -1044,6 +1067,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
       } else {
         mbar_wait(smem_u32(&acc_full_bar[tb]), (uint32_t)(jt / TB) & 1u, P.status);
         tc_fence_after();
+        CRDR_EV(if (ev) trace_event(P.status, 0u, ev_count, 2u, (uint32_t)jt);)  // epilogue: accumulator full observed
       }
       // The chunk loop is deliberately NOT unrolled: one copy of the (large) fused epilogue body instead of up to
       // eight keeps the tile loop inside the instruction cache (the unrolled form ran at 7-19 cycles per instruction
@@ -1058,6 +1082,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
         else tmem_ld16_issue(lane_addr + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r0);
         if (DIRECT) tmem_ld16_issue(lane_addr + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r0);  // D0 of the tile
         else if (split) tmem_ld16_issue(lane_addr + (three ? kD1Base : 0u) + kAccStride + (uint32_t)chn * 16u, three ? r0 : r1);
+        CRDR_EV(if (ev && c == 0) trace_event(P.status, 0u, ev_count, 16u, (uint32_t)jt);)  // chunk 0: TMEM load issued
         if (staged) {
 #pragma unroll
           for (int q2 = 0; q2 < NR; ++q2) {
@@ -1072,7 +1097,9 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
           epi_load_res<NR>(P, opix, n0 + chn * 16, rr);
         }
         if (opix >= 0) epi_load_trunk<NR>(P, opix, n0 + chn * 16, rtrunk);
+        CRDR_EV(if (ev && c == 0) trace_event(P.status, 0u, ev_count, 17u, (uint32_t)jt);)  // chunk 0: residual read + refill issued
         tmem_wait_ld();
+        CRDR_EV(if (ev && c == 0) trace_event(P.status, 0u, ev_count, 18u, (uint32_t)jt);)  // chunk 0: accumulator in registers
         float acc[16];
         if (three) {
           float tsel[16];
@@ -1099,10 +1126,13 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
                            ostaged ? ost_warp + (uint32_t)lane * opitch + (uint32_t)c * 32u : 0u, ost_plane);
           else epi_finish_generic(&P, opix, n0 + chn * 16, acc, s_par);
         }
+        CRDR_EV(if (ev && c == 0) trace_event(P.status, 0u, ev_count, 19u, (uint32_t)jt);)  // chunk 0: fused epilogue done
       }
       if (staged) cp_async_commit();
+      CRDR_EV(if (ev) trace_event(P.status, 0u, ev_count, 3u, (uint32_t)jt);)  // epilogue: chunks done
       arrive_leader(&acc_empty_bar[tb]);
       if (ostaged) copy_out(opix, n0);
+      CRDR_EV(if (ev) trace_event(P.status, 0u, ev_count, 4u, (uint32_t)jt);)  // epilogue: copy-out done
       cur = nxt;
       opix = opix_next;
     }
@@ -1158,12 +1188,14 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
     if (PATCH && lane == 0) {
       int pb = 0;
       uint32_t empty_par = 1u;
+      CRDR_EV(uint32_t ev_count = 0;)
       for (int tile = tile0; tile < num_tiles; tile += tstep) {
         int n, h0, w0;
         patch_tile_origin(P, CRDR_MTILE(tile), n, h0, w0);  // CG2: a tile past the end has n == d.n -> zero fill
         for (int cb = 0; cb < P.ncb; ++cb, ++pb) {
           if (pb == P.patch_stages) { pb = 0; empty_par ^= 1u; }
           mbar_wait(smem_u32(&patch_empty_bar[pb]), empty_par, P.status);
+          CRDR_EV(if (P.trace == 2 && blockIdx.x == 0) trace_event(P.status, 2u, ev_count, 12u, (uint32_t)cb);)  // patch: slot free, TMA issued
           const uint32_t bar = smem_u32(&patch_full_bar[pb]);
           const uint32_t dst = smem_patch + (uint32_t)pb * patch_stage_bytes;
           if (CG2) {
@@ -1195,6 +1227,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
       const uint64_t desc_a = PATCH ? umma_desc_sw128_rows(0u, (uint32_t)P.pw * 128u) : desc_b;
       const uint32_t a_planes = (uint32_t)nplanes * a_bytes;
       int g = 0, gc = 0, jt = 0;
+      CRDR_EV(uint32_t ev_count = 0;)
       int s = 0;                 // weight / gather ring slot and its phase
       uint32_t ring_par = 0;
       uint32_t stage = smem_base;
@@ -1210,6 +1243,8 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
           if (tr) t_acc += clock64() - t0;
           tc_fence_after();
         }
+        CRDR_EV(const bool ev = P.trace == 2 && blockIdx.x == 0 && elected;)
+        CRDR_EV(if (ev) trace_event(P.status, 1u, ev_count, 8u, (uint32_t)jt);)  // MMA: accumulator buffer free
         const uint32_t d1 = tmem_base + kD1Base + (uint32_t)tb * kAccStride;
         int tap = 0, ck = 0, kk = 0;  // tap of this K block (PATCH), position inside the D0 chunk / the ring slot
         int cb = 0;                   // channel block of this K block (PATCH)
@@ -1231,6 +1266,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
               if (tr) t0 = clock64();
               mbar_wait(smem_u32(&patch_full_bar[pb]), patch_par, P.status);
               if (tr) t_patch += clock64() - t0;
+              CRDR_EV(if (ev) trace_event(P.status, 1u, ev_count, 10u, (uint32_t)jt);)  // MMA: patch landed
             }
             const uint32_t pa = patch_addr + P.tapoff[tap];
             a_hi = desc_a + (uint64_t)(pa >> 4);
@@ -1282,6 +1318,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
             }
           }
           if (chunk_last) {
+            CRDR_EV(if (ev && kb == nkb - 1) trace_event(P.status, 1u, ev_count, 9u, (uint32_t)jt);)  // MMA: last K block of the tile issued
             if (elected) umma_done<CG2>(smem_u32(drain ? &d0_full_bar[b] : &acc_full_bar[tb]));
             if (drain) ++gc;
             ck = 0;
@@ -1743,7 +1780,9 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     // of the next tile's patch, not by the MMAs), as long as four weight stages still fit; at least one.
     {
       const uint32_t budget = kDynSmemMax - 1024 - res_need - out_need;
-      int want = 2 * ncb;
+      static int pmul_env = -1;
+      if (pmul_env < 0) { const char* e = getenv("CRDR_PATCH_TILES"); pmul_env = e ? atoi(e) : 2; }
+      int want = pmul_env * ncb;
       if (want < 2) want = 2;
       if (want > kMaxPatchStages) want = kMaxPatchStages;
       int ps = want;
