@@ -606,8 +606,9 @@ __device__ __forceinline__ void trace_event(uint32_t* status, uint32_t region, u
 }
 #define CRDR_EV(...) __VA_ARGS__
 #else
-// event trace hooks compile to nothing in the product build: present, they cost 4 % of the step (registers and code in
-// the hot loops); build with CRDR_BUILD_TRACE=1 python -m crdr_b200.build to use tools/conv_events.py
+// event-trace hooks and the MMA-thread cycle counters compile to nothing in the product build: present, they cost 4 %
+// of the step (registers, predicated instructions and code in the hot loops); build with
+// CRDR_BUILD_TRACE=1 python -m crdr_b200.build to use tools/conv_events.py and the CRDR_CONV_TRACE=1 counters
 #define CRDR_EV(...)
 #endif
 
@@ -878,7 +879,6 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
     const int ch_begin = min(cgrp * ch_per, nch_tile);
     const int ch_end = min(ch_begin + ch_per, nch_tile);
     constexpr int NR = three ? 4 : 2;         // 16-byte registers per residual chunk
-    constexpr int KC = three ? MAXCH : 8;     // column chunks per epilogue warp (compile-time bound)
     // Residual operands are software-pipelined ACROSS tiles without spending registers on it: every thread copies
     // the residual bytes of its own output row for tile j+1 into a private shared-memory slot with cp.async while
     // tile j is being finished (a whole tile per SM in flight; the one-chunk-ahead register ring kept only 16 KB
@@ -1142,8 +1142,8 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
     // ------------------------------------------------------------------ weight tiles by TMA
     if (lane == 0 && (P.use_tma || PATCH)) {
       int g = 0;
-      const bool trp = P.trace && blockIdx.x == 0;
-      long long tp_wait = 0, tp0 = 0, tp_all0 = trp ? clock64() : 0;
+      CRDR_EV(const bool trp = P.trace && blockIdx.x == 0;)
+      CRDR_EV(long long tp_wait = 0, tp0 = 0, tp_all0 = trp ? clock64() : 0;)
       int s = 0;
       uint32_t empty_par = 1u;  // a fresh barrier passes a wait on the previous phase
       uint32_t bst = smem_base + (uint32_t)nplanes * a_bytes;
@@ -1153,9 +1153,9 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
         for (int kb = 0; kb < nkb; ++kb, ++g) {
           const uint32_t bar = smem_u32(&full_bar[s]);
           if (kk == 0) {
-            if (trp) tp0 = clock64();
+            CRDR_EV(if (trp) tp0 = clock64();)
             mbar_wait(smem_u32(&empty_bar[s]), empty_par, P.status);
-            if (trp) tp_wait += clock64() - tp0;
+            CRDR_EV(if (trp) tp_wait += clock64() - tp0;)
             // the slot's K blocks (both halves of the weight tile for a CTA pair) complete on one (the leader's) barrier
             const uint32_t kcount = (uint32_t)min(KPS, nkb - kb);
             if (!CG2 || cta_rank == 0) mbar_arrive_expect_tx(bar, (CG2 ? 2u : 1u) * kcount * (uint32_t)nplanes * b_bytes);
@@ -1177,11 +1177,13 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
           }
         }
       }
+#ifdef CRDR_TRACE_EVENTS
       if (trp) {
         unsigned long long* c = reinterpret_cast<unsigned long long*>(P.status + 16);
         c[8] = (unsigned long long)(clock64() - tp_all0);
         c[9] = (unsigned long long)tp_wait;
       }
+#endif
     }
   } else if (warp == kPatchWarp) {
     // ------------------------------------------------------------------ PATCH: halo patches by TMA (one thread)
@@ -1221,8 +1223,8 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
       const bool elected = elect_one();
       const uint32_t idesc = umma_idesc_f16((uint32_t)BN, CG2 ? 256u : (uint32_t)kTileM);
       const int ntaps = d.ntaps;
-      const bool tr = P.trace && blockIdx.x == 0 && elected;
-      long long t_full = 0, t_d0 = 0, t_acc = 0, t_patch = 0, t_mma = 0, t_commit = 0, t_all0 = tr ? clock64() : 0, t0 = 0;
+      CRDR_EV(const bool tr = P.trace && blockIdx.x == 0 && elected;)
+      CRDR_EV(long long t_full = 0, t_d0 = 0, t_acc = 0, t_patch = 0, t_mma = 0, t_commit = 0, t_all0 = tr ? clock64() : 0, t0 = 0;)
       const uint64_t desc_b = umma_desc_sw128(0u);                                            // + (addr >> 4)
       const uint64_t desc_a = PATCH ? umma_desc_sw128_rows(0u, (uint32_t)P.pw * 128u) : desc_b;
       const uint32_t a_planes = (uint32_t)nplanes * a_bytes;
@@ -1238,9 +1240,9 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
         const int tb = split ? 0 : (jt & 1);
         if (jt >= TB) {
           // the epilogue of tile jt-TB must have consumed this per-tile accumulator buffer
-          if (tr) t0 = clock64();
+          CRDR_EV(if (tr) t0 = clock64();)
           mbar_wait(smem_u32(&acc_empty_bar[tb]), (uint32_t)((jt - TB) / TB) & 1u, P.status);
-          if (tr) t_acc += clock64() - t0;
+          CRDR_EV(if (tr) t_acc += clock64() - t0;)
           tc_fence_after();
         }
         CRDR_EV(const bool ev = P.trace == 2 && blockIdx.x == 0 && elected;)
@@ -1254,18 +1256,18 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
           const int b = gc & 1;
           if (drain && chunk_first && gc >= 2) {
             // the drain warps must have emptied this D0 buffer (chunk gc-2) before it is overwritten
-            if (tr) t0 = clock64();
+            CRDR_EV(if (tr) t0 = clock64();)
             mbar_wait(smem_u32(&d0_empty_bar[b]), (uint32_t)((gc - 2) >> 1) & 1u, P.status);
-            if (tr) t_d0 += clock64() - t0;
+            CRDR_EV(if (tr) t_d0 += clock64() - t0;)
             tc_fence_after();
           }
           uint64_t a_hi, a_lo;
           if (PATCH) {
             // K block kb = (channel block, tap): the A operand is the patch shifted by the tap offset
             if (tap == 0) {
-              if (tr) t0 = clock64();
+              CRDR_EV(if (tr) t0 = clock64();)
               mbar_wait(smem_u32(&patch_full_bar[pb]), patch_par, P.status);
-              if (tr) t_patch += clock64() - t0;
+              CRDR_EV(if (tr) t_patch += clock64() - t0;)
               CRDR_EV(if (ev) trace_event(P.status, 1u, ev_count, 10u, (uint32_t)jt);)  // MMA: patch landed
             }
             const uint32_t pa = patch_addr + P.tapoff[tap];
@@ -1276,16 +1278,16 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
             a_lo = desc_a + (uint64_t)((stage + kAPlaneBytes) >> 4);
           }
           if (kk == 0) {
-            if (tr) t0 = clock64();
+            CRDR_EV(if (tr) t0 = clock64();)
             mbar_wait(smem_u32(&full_bar[s]), ring_par, P.status);
-            if (tr) t_full += clock64() - t0;
+            CRDR_EV(if (tr) t_full += clock64() - t0;)
           }
           tc_fence_after();
           const uint32_t d0 = tmem_base + (uint32_t)(drain ? b : tb) * kAccStride;
           const uint32_t bsrc = stage + a_planes + (uint32_t)kk * kb_bytes;
           const uint64_t b_hi = desc_b + (uint64_t)(bsrc >> 4);
           const uint64_t b_lo = desc_b + (uint64_t)((bsrc + b_bytes) >> 4);
-          if (tr) t0 = clock64();
+          CRDR_EV(if (tr) t0 = clock64();)
           const int nks = PATCH ? P.cb_ksteps[cb] : kKBlk / 16;  // K steps of this block that hold real channels
           if (elected) {
 #pragma unroll
@@ -1305,7 +1307,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
             }
           }
           }
-          if (tr) { const long long t1 = clock64(); t_mma += t1 - t0; t0 = t1; }
+          CRDR_EV(if (tr) { const long long t1 = clock64(); t_mma += t1 - t0; t0 = t1; })
           const bool slot_last = ++kk == KPS || kb == nkb - 1;
           if (slot_last && elected) umma_done<CG2>(smem_u32(&empty_bar[s]));
           if (PATCH) {
@@ -1325,7 +1327,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
           } else {
             ++ck;
           }
-          if (tr) t_commit += clock64() - t0;
+          CRDR_EV(if (tr) t_commit += clock64() - t0;)
           if (slot_last) {
             kk = 0;
             stage += stage_bytes;
@@ -1333,6 +1335,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
           }
         }
       }
+#ifdef CRDR_TRACE_EVENTS
       if (tr) {  // bring-up counters (cycles): total, wait full, wait d0_empty, wait acc_empty, wait patch, k blocks
         unsigned long long* c = reinterpret_cast<unsigned long long*>(P.status + 16);
         c[0] = (unsigned long long)(clock64() - t_all0);
@@ -1340,6 +1343,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
         c[4] = (unsigned long long)t_patch; c[5] = (unsigned long long)g;
         c[6] = (unsigned long long)t_mma; c[7] = (unsigned long long)t_commit;
       }
+#endif
     }
    }
   }

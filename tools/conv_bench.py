@@ -40,7 +40,7 @@ def bench(n, cin, cout, h, w, k, stride, tr, prec, tile_n=None, epi=0, iters=10)
     print(f"n={n} {cin}->{cout} {h}x{w} k{k} s{stride} tr{tr} prec{prec} tile={tile_n} epi={epi}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s alg, {mult*fl/ms/1e9:.1f} MMA")
     nv.status_check()
     import os, ctypes
-    if os.environ.get("CRDR_CONV_TRACE"):
+    if os.environ.get("CRDR_CONV_TRACE"):  # counters exist only in a CRDR_BUILD_TRACE=1 build of the library
         c = (ctypes.c_ulonglong * 10)()
         nv.lib().crdr_debug_counters(c)
         tot, full, d0, acc, patch, kbs, tmma, tcommit, ptot, pwait = [int(v) for v in c]
