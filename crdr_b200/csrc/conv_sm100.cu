@@ -754,7 +754,13 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
   //   F16X1 split: even K steps at 0, odd K steps at 256                                -> two chains
   constexpr uint32_t kAccStride = three ? 128u : 256u;
   constexpr uint32_t kD1Base = 256u;
-  const bool split = P.split != 0;
+#ifdef CRDR_TRACE_EVENTS
+  const bool split = P.split != 0;   // tuning knobs (CRDR_CONV_SPLIT, CRDR_EPI_DEBUG) exist in the trace build only:
+  const int dbg = P.dbg;             // their per-MMA / per-chunk tests cost issue slots in the product kernel
+#else
+  constexpr bool split = false;
+  constexpr int dbg = 0;
+#endif
   const int TB = split ? 1 : 2;  // per-tile accumulator buffers
 
   // Register re-balancing between the warp groups (512 threads x 128 = the whole register file):
@@ -988,7 +994,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
       int row = wk_planes.row0, pp = wk_planes.p0;
       for (int j = 0; j < wk_planes.ppr; ++j) {
         const int orow = __shfl_sync(0xffffffffu, opi, row);
-        if (orow >= 0 && nmine > 0 && !(P.dbg & 1)) {
+        if (orow >= 0 && nmine > 0 && !(dbg & 1)) {
           const uint32_t src = ost_warp + (uint32_t)row * opitch + (uint32_t)pp * 16u;
           const int64_t o = (int64_t)orow * d.out.cs + d.out.coff + c0 + 8 * pp;
           uint4 v;
@@ -1077,7 +1083,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
       for (int c = 0; c < nmine; ++c) {
         const int chn = ch_begin + c;
         // second chain of a split launch lives one accumulator stride further (D1b / odd K steps)
-        if (P.dbg & 4) {
+        if (dbg & 4) {
         } else if (three) tmem_ld16_issue(lane_addr + kD1Base + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r1);
         else tmem_ld16_issue(lane_addr + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r0);
         if (DIRECT) tmem_ld16_issue(lane_addr + (uint32_t)tb * kAccStride + (uint32_t)chn * 16u, r0);  // D0 of the tile
@@ -1120,7 +1126,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
           for (int e = 0; e < 16; ++e)
             acc[e] = split ? __uint_as_float(r0[e]) + __uint_as_float(r1[e]) : __uint_as_float(r0[e]);
         }
-        if (opix >= 0 && !(P.dbg & 2)) {
+        if (opix >= 0 && !(dbg & 2)) {
           if (P.fast_epi)
             epi_finish<NR>(P, opix, n0 + chn * 16, acc, rr, rtrunk, s_par,
                            ostaged ? ost_warp + (uint32_t)lane * opitch + (uint32_t)c * 32u : 0u, ost_plane);
