@@ -43,9 +43,10 @@ constexpr int kThreadsPatch = 512;         // patch variant, F16X1: warps 0-11 d
 // epilogue warps = 4 TMEM lane quarters x column groups (the epilogue is latency bound: 12 warps issue more than 8 do, but
 // the F16X3 drain totals do not fit the 152-register budget of a 12-warp layout)
 __host__ __device__ constexpr int epi_groups(bool patch, bool three) { return (patch && !three) ? 3 : 2; }
-constexpr int kChunkKB = 4;                // F16X3: K blocks per D0 accumulate chain (16 MMAs of K=16).  Measured conv error vs
-                                           // float64, relative to max|out|: 2 -> 2.3e-7, 4 -> 3.0e-7, 8 -> 4.5e-7, whole K (8800) -> 6.9e-6;
-                                           // all codec parity tests stay byte-identical up to 8; step 88.9 / 85.9 / 84.4 ms for 2 / 4 / 8
+constexpr int kChunkKB = 6;                // F16X3: K blocks per D0 accumulate chain (24 MMAs of K=16).  Measured conv error vs
+                                           // float64, relative to max|out|: 2 -> 2.3e-7, 4 -> 3.0e-7, 6 -> 3.3e-7, 8 -> 4.5e-7, whole K
+                                           // (8800) -> 6.9e-6; all codec parity tests stay byte-identical up to 8; step time on one box
+                                           // 88.9 / 85.9 / 84.8 / 84.4 ms for 2 / 4 / 6 / 8
 constexpr uint32_t kSmemLimit = 227 * 1024;
 constexpr uint32_t kDynSmemMax = kSmemLimit - 8 * 1024;  // static smem: parameter cache (5 KB) + barriers
 
