@@ -428,25 +428,37 @@ __device__ __forceinline__ void st_shared16(uint32_t addr, uint32_t a, uint32_t 
 }
 // ost != 0: the fp16 planes of this chunk go to the warp's staging tile in shared memory (32 bytes at `ost`, the lo
 // plane `ost_plane` bytes further) and are written to global memory by the warp's coalesced copy-out.
+// Per-launch epilogue switches, gathered once per thread into a register bit mask: read from the parameter bank inside the
+// chunk loop, every test was an LDC -> ISETP -> BRA chain whose load latency three warps per scheduler cannot hide.
+constexpr uint32_t kEfBias = 1, kEfRelu = 2, kEfAdd = 4, kEfAffine = 8, kEfOutF32 = 16, kEfOutHi = 32, kEfOutLo = 64,
+                   kEfResF32 = 128, kEfResLo = 256, kEfTrunkLo = 512, kEfModeShift = 12;
+__device__ __forceinline__ uint32_t epi_flags(const ConvKParams& P) {
+  const crdr_conv_desc& d = P.d;
+  return (P.has_bias ? kEfBias : 0u) | (d.relu ? kEfRelu : 0u) | (P.has_add ? kEfAdd : 0u) | (P.has_affine ? kEfAffine : 0u) |
+         (d.out_f32 ? kEfOutF32 : 0u) | (d.out.hi ? kEfOutHi : 0u) | (d.out.lo ? kEfOutLo : 0u) | (d.res_f32 ? kEfResF32 : 0u) |
+         (d.res.lo ? kEfResLo : 0u) | (d.trunk.lo ? kEfTrunkLo : 0u) | ((uint32_t)d.mode << kEfModeShift);
+}
+
 template <int NR>
 __device__ __forceinline__ void epi_finish(const ConvKParams& P, int64_t opix, int co0, const float (&acc)[16],
                                            const uint4 (&rr)[NR], const uint4 (&rt)[NR], const float* s_par,
-                                           uint32_t ost = 0u, uint32_t ost_plane = 0u) {
+                                           uint32_t ost, uint32_t ost_plane, uint32_t ef) {
+  const int mode = (int)(ef >> kEfModeShift);
   const crdr_conv_desc& d = P.d;
   float res[16], trunk[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) { res[e] = 0.f; trunk[e] = 0.f; }
-  if (d.mode != CRDR_EPI_NONE) {
-    if (NR == 4 && d.res_f32) {
+  if (mode != CRDR_EPI_NONE) {
+    if (NR == 4 && (ef & kEfResF32)) {
 #pragma unroll
       for (int q = 0; q < NR; ++q) {
         res[4 * q] = __uint_as_float(rr[q].x); res[4 * q + 1] = __uint_as_float(rr[q].y);
         res[4 * q + 2] = __uint_as_float(rr[q].z); res[4 * q + 3] = __uint_as_float(rr[q].w);
       }
     } else {
-      unpack16<NR>(rr, d.res.lo != nullptr, res);
+      unpack16<NR>(rr, (ef & kEfResLo) != 0, res);
     }
-    if (d.mode == CRDR_EPI_GATE) unpack16<NR>(rt, d.trunk.lo != nullptr, trunk);
+    if (mode == CRDR_EPI_GATE) unpack16<NR>(rt, (ef & kEfTrunkLo) != 0, trunk);
   }
   // uniform (per-launch) switches outside the element loops; per-channel vectors as 128-bit shared loads
   float v[16];
@@ -454,35 +466,35 @@ __device__ __forceinline__ void epi_finish(const ConvKParams& P, int64_t opix, i
   for (int e = 0; e < 16; ++e) v[e] = acc[e];
   const float4* par = reinterpret_cast<const float4*>(s_par + co0);
   constexpr int kVecStride = kMaxCout / 4;
-  if (P.has_bias) {
+  if (ef & kEfBias) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float4 t = par[q];
       v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
     }
   }
-  if (d.relu) {
+  if (ef & kEfRelu) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.0f);
   }
-  if (P.has_add) {
+  if (ef & kEfAdd) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float4 t = par[kVecStride + q];
       v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
     }
   }
-  if (d.mode == CRDR_EPI_RESIDUAL) {
+  if (mode == CRDR_EPI_RESIDUAL) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) v[e] += res[e];
-  } else if (d.mode == CRDR_EPI_GATE) {
+  } else if (mode == CRDR_EPI_GATE) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) v[e] = fmaf(trunk[e], sigmoidf_(v[e]), res[e]);
-  } else if (d.mode == CRDR_EPI_HALF_TANH) {
+  } else if (mode == CRDR_EPI_HALF_TANH) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) v[e] = fmaf(0.5f, tanhf(v[e]), res[e]);
   }
-  if (P.has_affine) {
+  if (ef & kEfAffine) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float4 sc = par[2 * kVecStride + q], sh = par[3 * kVecStride + q];
@@ -490,13 +502,13 @@ __device__ __forceinline__ void epi_finish(const ConvKParams& P, int64_t opix, i
       v[4 * q + 2] = fmaf(v[4 * q + 2], sc.z, sh.z); v[4 * q + 3] = fmaf(v[4 * q + 3], sc.w, sh.w);
     }
   }
-  if (d.out_f32) {
+  if (ef & kEfOutF32) {
     float* o = d.out_f32 + opix * d.out_f32_cs + d.out_f32_coff + co0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) ((float4*)o)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
-  if (d.out.hi) {
-    const bool want_lo = d.out.lo != nullptr;
+  if (ef & kEfOutHi) {
+    const bool want_lo = (ef & kEfOutLo) != 0;
     // one range check per chunk instead of one branch per element
     float amax = 0.f;
 #pragma unroll
@@ -892,6 +904,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
     // in flight = 0.9 TB/s).  At the start of tile j+1 the slot is read into registers and immediately refilled
     // for tile j+2.  Each thread only ever touches its own slot, so no barrier is involved.
     const bool staged = P.res_stage_pitch != 0;
+    const uint32_t ef = epi_flags(P);
     const uint32_t my_slot = smem_res + (uint32_t)row * (uint32_t)P.res_stage_pitch + (uint32_t)(ch_begin * NR * 16);
     float total[drain ? MAXCH * 16 : 1];
     uint32_t r0[16], r1[16];
@@ -1130,7 +1143,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
         if (opix >= 0 && !(dbg & 2)) {
           if (P.fast_epi)
             epi_finish<NR>(P, opix, n0 + chn * 16, acc, rr, rtrunk, s_par,
-                           ostaged ? ost_warp + (uint32_t)lane * opitch + (uint32_t)c * 32u : 0u, ost_plane);
+                           ostaged ? ost_warp + (uint32_t)lane * opitch + (uint32_t)c * 32u : 0u, ost_plane, ef);
           else epi_finish_generic(&P, opix, n0 + chn * 16, acc, s_par);
         }
         CRDR_EV(if (ev && c == 0) trace_event(P.status, 0u, ev_count, 19u, (uint32_t)jt);)  // chunk 0: fused epilogue done
