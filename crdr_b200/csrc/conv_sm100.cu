@@ -968,29 +968,35 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
     const Walk wk_planes = make_walk(2 * nmine);   // fp16 plane: 32 bytes per chunk
     // cp.async the residual operands of chunk c (16 channels) of the warp's 32 rows into the rows' slots; consecutive
     // lanes fetch consecutive 16-byte pieces of a row (2 or 4 pieces per row and plane).  No commit.
+    // loop invariants of the refill / copy-out helpers, held in registers (same reason as the epilogue flag mask)
+    const uint32_t rpitch = (uint32_t)P.res_stage_pitch;
+    const __half* const res_hi = (const __half*)d.res.hi;
+    const __half* const res_lo = (const __half*)d.res.lo;
+    const int res_cs = d.res.cs, res_coff = d.res.coff;
+    __half* const out_hi = (__half*)d.out.hi;
+    __half* const out_lo = (__half*)d.out.lo;
+    const int out_cs = d.out.cs, out_coff = d.out.coff;
     auto refill_chunk = [&](int c, int opi, int c0) {
-      if (d.res_f32) {
+      if (ef & kEfResF32) {
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int i = it * 32 + lane, row = i >> 2, pp = i & 3;
           const int orow = __shfl_sync(0xffffffffu, opi, row);
           if (orow >= 0)
-            cp_async16(warp_slot0 + (uint32_t)row * (uint32_t)P.res_stage_pitch + (uint32_t)((c * NR + pp) * 16),
+            cp_async16(warp_slot0 + (uint32_t)row * rpitch + (uint32_t)((c * NR + pp) * 16),
                        d.res_f32 + (int64_t)orow * d.res_f32_cs + d.res_f32_coff + c0 + c * 16 + 4 * pp, 16u);
         }
       } else {
-        const __half* hi = (const __half*)d.res.hi;
-        const __half* lo = (const __half*)d.res.lo;
-        const bool has_lo = NR == 4 && d.res.lo != nullptr;
+        const bool has_lo = NR == 4 && (ef & kEfResLo);
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
           const int i = it * 32 + lane, row = i >> 1, pp = i & 1;
           const int orow = __shfl_sync(0xffffffffu, opi, row);
           if (orow >= 0) {
-            const int64_t o = (int64_t)orow * d.res.cs + d.res.coff + c0 + c * 16 + 8 * pp;
-            const uint32_t dst = warp_slot0 + (uint32_t)row * (uint32_t)P.res_stage_pitch + (uint32_t)((c * NR + pp) * 16);
-            cp_async16(dst, hi + o, 16u);
-            if (has_lo) cp_async16(dst + 32u, lo + o, 16u);
+            const int64_t o = (int64_t)orow * res_cs + res_coff + c0 + c * 16 + 8 * pp;
+            const uint32_t dst = warp_slot0 + (uint32_t)row * rpitch + (uint32_t)((c * NR + pp) * 16);
+            cp_async16(dst, res_hi + o, 16u);
+            if (has_lo) cp_async16(dst + 32u, res_lo + o, 16u);
           }
         }
       }
@@ -1004,19 +1010,19 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
       __syncwarp();  // every lane's chunks are staged
       const int opi = (int)op;
       const int c0 = n0 + ch_begin * 16;
-      const bool want_lo = d.out.lo != nullptr;
+      const bool want_lo = (ef & kEfOutLo) != 0;
       int row = wk_planes.row0, pp = wk_planes.p0;
       for (int j = 0; j < wk_planes.ppr; ++j) {
         const int orow = __shfl_sync(0xffffffffu, opi, row);
         if (orow >= 0 && nmine > 0 && !(dbg & 1)) {
           const uint32_t src = ost_warp + (uint32_t)row * opitch + (uint32_t)pp * 16u;
-          const int64_t o = (int64_t)orow * d.out.cs + d.out.coff + c0 + 8 * pp;
+          const int64_t o = (int64_t)orow * out_cs + out_coff + c0 + 8 * pp;
           uint4 v;
           asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src));
-          *reinterpret_cast<uint4*>((__half*)d.out.hi + o) = v;
+          *reinterpret_cast<uint4*>(out_hi + o) = v;
           if (want_lo) {
             asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src + ost_plane));
-            *reinterpret_cast<uint4*>((__half*)d.out.lo + o) = v;
+            *reinterpret_cast<uint4*>(out_lo + o) = v;
           }
         }
         pp += wk_planes.dp; row += wk_planes.drow;
