@@ -180,3 +180,48 @@ def test_c_abi_libraries_export_every_declared_symbol():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(td, "s"), os.path.join(td, "s.c")])
         sizes = [int(v) for v in subprocess.check_output([os.path.join(td, "s")]).split()]
     assert sizes == [ctypes.sizeof(native.Planes), ctypes.sizeof(native.ConvDesc), ctypes.sizeof(native.GaussDesc), ctypes.sizeof(native.EbDesc)]
+
+
+def test_chunk_split_and_pipeline_scheduler(model):
+    """Host logic of the codec API's software pipeline (model.py `_chunks` / `_drive`): chunk boundaries cover the batch
+    exactly once, and generators are resumed round-robin, each only after its own event has been synchronised."""
+    cls = type(model)
+    assert model._chunks(3) == [(0, 3)]                                     # below pipeline_min_images: one chunk
+    assert model._chunks(24) == [(0, 12), (12, 24)] and model._chunks(9) == [(0, 4), (4, 9)]
+    model.pipeline_chunks, model.pipeline_weights = 3, (3, 2, 1)
+    try:
+        ch = model._chunks(24)
+        assert ch == [(0, 12), (12, 20), (20, 24)]
+        model.pipeline_weights = None
+        for n in (8, 10, 25):
+            ch = model._chunks(n)
+            assert ch[0][0] == 0 and ch[-1][1] == n and all(a[1] == b[0] for a, b in zip(ch, ch[1:])) and len(ch) == 3
+    finally:
+        model.pipeline_chunks, model.pipeline_weights = 2, None
+
+    log = []
+
+    class Ev:
+        def __init__(self, name):
+            self.name = name
+
+        def synchronize(self):
+            log.append(("sync", self.name))
+
+    def gen(name, stages):
+        for s in range(stages):
+            log.append(("enqueue", name, s))
+            yield Ev(f"{name}{s}")
+            log.append(("host", name, s))
+        return name.upper()
+
+    out = cls._drive([gen("a", 2), gen("b", 3), gen("c", 0)])
+    assert out == ["A", "B", "C"]
+    # both first device segments are enqueued before any host stage runs; afterwards strict round-robin, and a host
+    # stage never runs before its event was synchronised
+    assert log[:2] == [("enqueue", "a", 0), ("enqueue", "b", 0)]
+    for i, rec in enumerate(log):
+        if rec[0] == "host":
+            assert log[i - 1] == ("sync", f"{rec[1]}{rec[2]}")
+    hosts = [r[1:] for r in log if r[0] == "host"]
+    assert hosts == [("a", 0), ("b", 0), ("a", 1), ("b", 1), ("b", 2)]
