@@ -258,7 +258,7 @@ def main():
                          "frac": achieved / tensor_peak,
                          # dram__bytes_read+write per conv launch, averaged over the 369 launches of one step of this
                          # workload (ncu capture: profiles/conv_dram_traffic_r01.txt); only valid for the default batch
-                         "traffic": 294.5e6 if (B == BATCH) else None, "peak_source": peak_src,
+                         "traffic": 289.8e6 if (B == BATCH) else None, "peak_source": peak_src,
                          "kernel": "conv_tcgen05_kernel", "launches_per_step": conv_launches, "kernel_ms_per_step": conv_ms,
                          "flops_per_step": flops_step,
                          "note": "algorithmic FLOPs = 2 x 1,478,360 MAC/px x padded px; the F16X3 layers execute 3 fp16 MMAs "
