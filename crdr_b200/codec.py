@@ -82,8 +82,10 @@ class InterpGain:
     given quality index: scale = softplus(lerp(weight)), shift = lerp(bias)."""
 
     def __init__(self, weight, bias, device):
-        self.w = weight.detach().to(device=device, dtype=torch.float32)  # (L, 1, C, 1, 1)
-        self.b = bias.detach().to(device=device, dtype=torch.float32)
+        # the lerp / softplus run on the host (two C-vectors per quality index, cached) and are uploaded once
+        self.w = weight.detach().to(device="cpu", dtype=torch.float32)  # (L, 1, C, 1, 1)
+        self.b = bias.detach().to(device="cpu", dtype=torch.float32)
+        self.device = device
         self.levels = self.w.shape[0]
         self._cache = {}
 
@@ -95,11 +97,12 @@ class InterpGain:
             ind = torch.tensor(q, dtype=torch.float32)
             lo = torch.floor(ind)
             hi = torch.minimum(lo + 1.0, torch.tensor(float(self.levels - 1)))
-            alpha = (hi - ind).to(self.w.device)
+            alpha = hi - ind
             l, r = int(lo.item()), int(hi.item())
             w = self.w[l] * alpha + self.w[r] * (1 - alpha)
             b = self.b[l] * alpha + self.b[r] * (1 - alpha)
-            self._cache[q] = (F.softplus(w).reshape(-1).contiguous(), b.reshape(-1).contiguous())
+            self._cache[q] = (F.softplus(w).reshape(-1).contiguous().to(self.device),
+                              b.reshape(-1).contiguous().to(self.device))
         return self._cache[q]
 
 
@@ -374,11 +377,12 @@ class SynthesisEngine:
         self.blocks, self.proj = {}, {}
         for b in ("block1", "block2", "block3"):
             self.blocks[b] = [Bottleneck(_sub(sd, f"{b}.block{i}"), ["conv.0", "conv.2", "conv.4"], cfg) for i in range(3)]
-            self.proj[b] = [[(sd[f"{b}.block{i}.proj_{k}.weight"].detach().to(device=device, dtype=torch.float32).flatten(1),
-                              sd[f"{b}.block{i}.proj_{k}.bias"].detach().to(device=device, dtype=torch.float32))
+            # beta embedding MLP and the 27 projections are GEMVs evaluated once per beta: host side, results uploaded
+            self.proj[b] = [[(sd[f"{b}.block{i}.proj_{k}.weight"].detach().to(device="cpu", dtype=torch.float32).flatten(1),
+                              sd[f"{b}.block{i}.proj_{k}.bias"].detach().to(device="cpu", dtype=torch.float32))
                              for k in (1, 2, 3)] for i in range(3)]
-        self.mlp = [(sd[f"mlp.{i}.weight"].detach().to(device=device, dtype=torch.float32),
-                     sd[f"mlp.{i}.bias"].detach().to(device=device, dtype=torch.float32)) for i in (0, 2)]
+        self.mlp = [(sd[f"mlp.{i}.weight"].detach().to(device="cpu", dtype=torch.float32),
+                     sd[f"mlp.{i}.bias"].detach().to(device="cpu", dtype=torch.float32)) for i in (0, 2)]
         self.gains = _gains(sd, 9, device)
         self.max_beta, self.L, self.include_x = float(max_beta), int(L), bool(include_x)
         self.freq = torch.pow(torch.Tensor([2]), torch.arange(L))
@@ -419,9 +423,9 @@ class SynthesisEngine:
             emb = torch.cat([torch.sin(nb * self.freq), torch.cos(nb * self.freq)], dim=0)
             if self.include_x:
                 emb = torch.cat([nb, emb], dim=0)
-            c = emb.unsqueeze(0).to(self.device)
+            c = emb.unsqueeze(0)
             c = F.linear(torch.relu(F.linear(c, *self.mlp[0])), *self.mlp[1])  # [1, cond_ch]
-            vec = {b_: [[(F.linear(c, w, bb)).reshape(-1).contiguous() for (w, bb) in blk] for blk in pr]
+            vec = {b_: [[(F.linear(c, w, bb)).reshape(-1).contiguous().to(self.device) for (w, bb) in blk] for blk in pr]
                    for b_, pr in self.proj.items()}
             self._beta_cache[beta] = vec
         return self._beta_cache[beta]

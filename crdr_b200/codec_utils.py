@@ -19,8 +19,10 @@ class MultiRateHeaderHandler:
             max_abs = float(y_hat.abs().max())
         if hasattr(rate_ind, "item"):
             rate_ind = float(rate_ind.item())
-        m, q = int(max_abs), int(rate_ind * 16)
-        if not (0 <= m <= 255 and 0 <= q <= 255 and 0 <= h <= 65535 and 0 <= w <= 65535):
+        # informational byte (no decoder reads it): the reference's np.array(v, dtype=np.uint8) wraps under numpy 1.x,
+        # so wrap instead of failing an encode whose GPU and rANS work is already done
+        m, q = int(max_abs) & 0xFF, int(rate_ind * 16)
+        if not (0 <= q <= 255 and 0 <= h <= 65535 and 0 <= w <= 65535):
             raise OverflowError(f"header field out of range (H={h}, W={w}, max={m}, q16={q})")
         return struct.pack("<HHBB", h, w, m, q)
 

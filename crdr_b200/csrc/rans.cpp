@@ -11,9 +11,7 @@
 #include <cstring>
 #include <limits>
 #include <memory>
-#include <mutex>
 #include <thread>
-#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -39,23 +37,10 @@ struct TableAccel {
   std::vector<EncSym> enc;        // [n_cdf][cdf_stride] (entries past a row's size are unused)
   std::vector<uint16_t> bucket;   // [n_cdf][256]
 };
-struct AccelKey {
-  const int32_t* cdfs; const int32_t* sizes; int32_t stride, n;
-  bool operator==(const AccelKey& o) const { return cdfs == o.cdfs && sizes == o.sizes && stride == o.stride && n == o.n; }
-};
-struct AccelKeyHash {
-  size_t operator()(const AccelKey& k) const {
-    return std::hash<const void*>()(k.cdfs) ^ (std::hash<const void*>()(k.sizes) << 1) ^ ((size_t)k.stride << 20) ^ (size_t)k.n;
-  }
-};
-std::mutex g_accel_mutex;
-std::unordered_map<AccelKey, std::shared_ptr<const TableAccel>, AccelKeyHash> g_accel;
-
-std::shared_ptr<const TableAccel> table_accel(const crdr_cdf_tables* t) {
-  const AccelKey key{t->cdfs, t->cdf_sizes, t->cdf_stride, t->n_cdf};
-  std::lock_guard<std::mutex> lk(g_accel_mutex);
-  auto it = g_accel.find(key);
-  if (it != g_accel.end()) return it->second;
+// Built by crdr_rans_tables_prepare() and owned by the caller's handle (crdr_cdf_tables::prepared).  There is no
+// cache keyed on table addresses: a rebuilt or reloaded table that lands on a recycled address must never pick up
+// another table's frequencies (the encoder would then disagree with the decoder without any error).
+std::shared_ptr<const TableAccel> build_accel(const crdr_cdf_tables* t) {
   auto a = std::make_shared<TableAccel>();
   a->enc.assign((size_t)t->n_cdf * (size_t)t->cdf_stride, EncSym{0, 0, 0, 0, 0});
   a->bucket.assign((size_t)t->n_cdf * 256, 0);
@@ -85,10 +70,32 @@ std::shared_ptr<const TableAccel> table_accel(const crdr_cdf_tables* t) {
       bk[b] = (uint16_t)sidx;
     }
   }
-  if (g_accel.size() > 64) g_accel.clear();  // tables are long-lived; this only bounds pathological churn
-  g_accel[key] = a;
   return a;
 }
+
+// A prepared table set: private copies of the arrays + the acceleration structures.
+struct Prepared {
+  std::vector<int32_t> cdfs, sizes, offsets;
+  crdr_cdf_tables view;
+  std::shared_ptr<const TableAccel> accel;
+};
+
+// The tables a coder call works on: the prepared copy when the caller made one, otherwise the caller's arrays with
+// acceleration structures built for this call only (correct, just slower).
+struct TableRef {
+  const crdr_cdf_tables* t;
+  std::shared_ptr<const TableAccel> accel;
+  explicit TableRef(const crdr_cdf_tables* in) {
+    if (in->prepared) {
+      const Prepared* p = static_cast<const Prepared*>(in->prepared);
+      t = &p->view;
+      accel = p->accel;
+    } else {
+      t = in;
+      accel = build_accel(in);
+    }
+  }
+};
 
 struct Encoder {
   uint64_t x = kRansL;
@@ -112,11 +119,11 @@ struct Encoder {
   }
 };
 
-int64_t encode_one(const int32_t* symbols, const int32_t* indexes, int64_t n, const crdr_cdf_tables* t, uint8_t* out,
+int64_t encode_one(const int32_t* symbols, const int32_t* indexes, int64_t n, const TableRef& tr, uint8_t* out,
                    int64_t out_cap) {
   Encoder enc;
-  const std::shared_ptr<const TableAccel> accel = table_accel(t);
-  const EncSym* esym = accel->enc.data();
+  const crdr_cdf_tables* t = tr.t;
+  const EncSym* esym = tr.accel->enc.data();
   // a table symbol emits at most one word; an escape adds at most 2 + 8 + 1 nibbles (raw < 2^32) = two more words
   std::unique_ptr<uint32_t[]> words(new uint32_t[(size_t)(3 * n + 8)]);  // uninitialised on purpose
   enc.wp = words.get();
@@ -167,9 +174,9 @@ struct Decoder {
   }
 };
 
-int decode_some(Decoder* d, const int32_t* indexes, int64_t n, const crdr_cdf_tables* t, int32_t* out) {
-  const std::shared_ptr<const TableAccel> accel = table_accel(t);
-  const uint16_t* bucket = accel->bucket.data();
+int decode_some(Decoder* d, const int32_t* indexes, int64_t n, const TableRef& tr, int32_t* out) {
+  const crdr_cdf_tables* t = tr.t;
+  const uint16_t* bucket = tr.accel->bucket.data();
   for (int64_t i = 0; i < n; ++i) {
     const int32_t ci = indexes[i];
     if (ci < 0 || ci >= t->n_cdf) return 1;
@@ -245,13 +252,29 @@ int crdr_pmf_to_quantized_cdf(const float* pmf, int64_t n, int32_t precision, ui
 
 int64_t crdr_rans_encode_with_indexes(const int32_t* symbols, const int32_t* indexes, int64_t n,
                                       const crdr_cdf_tables* t, uint8_t* out, int64_t out_cap) {
-  return encode_one(symbols, indexes, n, t, out, out_cap);
+  if (!t) return std::numeric_limits<int64_t>::min();
+  const TableRef tr(t);
+  return encode_one(symbols, indexes, n, tr, out, out_cap);
 }
+
+void* crdr_rans_tables_prepare(const crdr_cdf_tables* t) {
+  if (!t || !t->cdfs || !t->cdf_sizes || !t->offsets || t->n_cdf <= 0 || t->cdf_stride <= 0) return nullptr;
+  Prepared* p = new Prepared();
+  p->cdfs.assign(t->cdfs, t->cdfs + (size_t)t->n_cdf * (size_t)t->cdf_stride);
+  p->sizes.assign(t->cdf_sizes, t->cdf_sizes + t->n_cdf);
+  p->offsets.assign(t->offsets, t->offsets + t->n_cdf);
+  p->view = crdr_cdf_tables{p->cdfs.data(), t->cdf_stride, p->sizes.data(), p->offsets.data(), t->n_cdf, nullptr};
+  p->accel = build_accel(&p->view);
+  return p;
+}
+
+void crdr_rans_tables_free(void* prepared) { delete static_cast<Prepared*>(prepared); }
 
 int crdr_rans_encode_batch(int32_t count, const int32_t* const* symbols, const int32_t* const* indexes,
                            const int64_t* n, const crdr_cdf_tables* t, uint8_t* const* out, const int64_t* out_cap,
                            int64_t* lengths, int32_t threads) {
-  parallel_for(count, threads, [&](int32_t i) { lengths[i] = encode_one(symbols[i], indexes[i], n[i], t, out[i], out_cap[i]); });
+  const TableRef tr(t);
+  parallel_for(count, threads, [&](int32_t i) { lengths[i] = encode_one(symbols[i], indexes[i], n[i], tr, out[i], out_cap[i]); });
   for (int32_t i = 0; i < count; ++i)
     if (lengths[i] < 0) return 1;
   return 0;
@@ -272,14 +295,16 @@ int crdr_rans_decoder_set_stream(void* dec, const uint8_t* stream, int64_t nbyte
 
 int crdr_rans_decoder_decode_stream(void* dec, const int32_t* indexes, int64_t n, const crdr_cdf_tables* t,
                                     int32_t* out) {
-  return decode_some(static_cast<Decoder*>(dec), indexes, n, t, out);
+  const TableRef tr(t);
+  return decode_some(static_cast<Decoder*>(dec), indexes, n, tr, out);
 }
 
 int crdr_rans_decode_batch(int32_t count, void* const* decoders, const int32_t* const* indexes, const int64_t* n,
                            const crdr_cdf_tables* t, int32_t* const* out, int32_t threads) {
   std::atomic<int> bad{0};
+  const TableRef tr(t);
   parallel_for(count, threads, [&](int32_t i) {
-    if (decode_some(static_cast<Decoder*>(decoders[i]), indexes[i], n[i], t, out[i])) bad.store(1);
+    if (decode_some(static_cast<Decoder*>(decoders[i]), indexes[i], n[i], tr, out[i])) bad.store(1);
   });
   return bad.load();
 }

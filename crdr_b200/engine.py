@@ -69,11 +69,12 @@ NULL_PLANES = nv.Planes(None, None, 0, 0)
 
 
 def split_weight(w2d, device):
-    """[rows, k] fp32 -> (hi, lo) fp16 with lo = (w - hi) * 2^11."""
-    w2d = w2d.to(device=device, dtype=torch.float32).contiguous()
+    """[rows, k] fp32 -> (hi, lo) fp16 with lo = (w - hi) * 2^11.  Packed on the host (one-off, at engine build) and
+    uploaded with plain copies, so building an engine launches no device kernels of its own."""
+    w2d = w2d.detach().to(device="cpu", dtype=torch.float32).contiguous()
     hi = w2d.half()
     lo = ((w2d - hi.float()) * LO_SCALE).half()
-    return hi.contiguous(), lo.contiguous()
+    return hi.contiguous().to(device), lo.contiguous().to(device)
 
 
 class Phase:
@@ -114,7 +115,7 @@ class ConvOp:
         self.cin = cin_pad or cin
         assert self.cin % 8 == 0, "input channels must be padded to a multiple of 8"
         self.cout_pad = round_up(cout, 16)
-        self.bias = None if bias is None else bias.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.bias = None if bias is None else bias.detach().to(device="cpu", dtype=torch.float32).contiguous().to(device)
         self.device = device
         # channel ranges the input is read from at launch (ChARM: hyper ++ slices); decides the 64-channel blocking
         self.seg_lens = list(seg_lens) if seg_lens else [self.cin]

@@ -60,6 +60,11 @@ class _CoderTables(nn.Module):
     def invalidate(self):
         self._tables = None
 
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # an in-place load changes the CDF buffers under a cached rans.Tables: rebuild it on next use
+        self.invalidate()
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
     def _resize_buffers_from(self, state_dict, prefix, names):
         # checkpoints carry filled tables while a fresh module has empty ones (base_model.py:80-96)
         for name in names:

@@ -321,6 +321,7 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
         fake = eng.synthesis(a["yhat32"], q, beta, (h, w))
         y, z = eng.to_nchw(a["y32"]), eng.to_nchw(a["z32"])
         y_hat = eng.to_nchw(a["yhat32"])
+        nv.status_check()  # a clamped fp16 overflow must surface as an error, never as a silent wrong value
         return {
             "fake_images": fake,
             "likelihoods": {"y": a["y_lik"], "z": a["z_lik"]},
@@ -345,6 +346,7 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
         fake = eng.synthesis(a["yhat32"], q, beta, (h, w))
         num_pixel = h * w
         y_bpp, z_bpp = eng.bits(a["y_lik"]) / num_pixel, eng.bits(a["z_lik"]) / num_pixel
+        nv.status_check()
         return dict(real_images=x.clamp(-1, 1), fake_images=fake, y_hat=eng.to_nchw(a["yhat32"]), z_hat=a["z_hat"],
                     rate_ind=rate_ind, beta=beta, y_likelihood=a["y_lik"], z_likelihood=a["z_lik"],
                     bpp=y_bpp + z_bpp, y_q_likelihood=a["y_lik"], z_q_likelihood=a["z_lik"], qbpp=y_bpp + z_bpp)

@@ -144,6 +144,12 @@ def status_reset():
 
 
 def status_check():
-    """Synchronise the current stream and raise if any kernel flagged fp16 overflow / a pipeline timeout."""
+    """Synchronise the current stream and raise if any kernel flagged fp16 overflow / a pipeline timeout.
+    The flag is cleared once it has been reported, so one bad input does not poison later calls."""
     flags = C.c_uint32(0)
-    check(lib().crdr_status_read(C.byref(flags), stream_handle()), counts=False)
+    rc = lib().crdr_status_read(C.byref(flags), stream_handle())
+    if rc != 0:
+        msg = lib().crdr_last_error().decode()
+        if flags.value:
+            lib().crdr_status_reset(stream_handle())
+        raise NativeError(f"crdr status {rc}: {msg}")

@@ -8,10 +8,11 @@ from . import native as nv
 
 class CdfTables(C.Structure):
     _fields_ = [("cdfs", C.c_void_p), ("cdf_stride", C.c_int32), ("cdf_sizes", C.c_void_p),
-                ("offsets", C.c_void_p), ("n_cdf", C.c_int32)]
+                ("offsets", C.c_void_p), ("n_cdf", C.c_int32), ("prepared", C.c_void_p)]
 
 
 RANS_SYMBOLS = [
+    "crdr_rans_tables_prepare", "crdr_rans_tables_free",
     "crdr_pmf_to_quantized_cdf", "crdr_rans_encode_with_indexes", "crdr_rans_encode_batch",
     "crdr_rans_decoder_new", "crdr_rans_decoder_free", "crdr_rans_decoder_set_stream",
     "crdr_rans_decoder_decode_stream", "crdr_rans_decode_batch",
@@ -28,6 +29,9 @@ def lib():
             raise nv.NativeError(f"{nv.RANS_SO} is missing; build it with `python -m crdr_b200.build`")
         L = C.CDLL(nv.RANS_SO)
         vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+        L.crdr_rans_tables_prepare.restype = vp
+        L.crdr_rans_tables_prepare.argtypes = [C.POINTER(CdfTables)]
+        L.crdr_rans_tables_free.argtypes = [vp]
         L.crdr_pmf_to_quantized_cdf.argtypes = [vp, i64, i32, vp]
         L.crdr_rans_encode_with_indexes.restype = i64
         L.crdr_rans_encode_with_indexes.argtypes = [vp, vp, i64, C.POINTER(CdfTables), vp, i64]
@@ -55,13 +59,29 @@ def pmf_to_quantized_cdf(pmf, precision=16):
 
 
 class Tables:
-    """CDF tables held as contiguous int32 arrays for the coder."""
+    """CDF tables for the coder: private int32 copies of the arrays plus a prepared native handle
+    (crdr_rans_tables_prepare) that owns the encoder / decoder acceleration structures.  The copies make the
+    object immune to later in-place changes of the source buffers (load_state_dict, update)."""
 
     def __init__(self, cdfs, cdf_sizes, offsets):
-        self.cdfs, self.sizes, self.offsets = _i32(cdfs), _i32(cdf_sizes).reshape(-1), _i32(offsets).reshape(-1)
+        self.cdfs = np.array(cdfs, dtype=np.int32, order="C", copy=True)
+        self.sizes = np.array(cdf_sizes, dtype=np.int32, copy=True).reshape(-1)
+        self.offsets = np.array(offsets, dtype=np.int32, copy=True).reshape(-1)
         assert self.cdfs.ndim == 2 and self.cdfs.shape[0] == self.sizes.size == self.offsets.size
         self.c = CdfTables(self.cdfs.ctypes.data, self.cdfs.shape[1], self.sizes.ctypes.data,
-                           self.offsets.ctypes.data, self.cdfs.shape[0])
+                           self.offsets.ctypes.data, self.cdfs.shape[0], None)
+        self._h = lib().crdr_rans_tables_prepare(C.byref(self.c))
+        if not self._h:
+            raise ValueError("rans tables: invalid CDF table geometry")
+        self.c.prepared = self._h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().crdr_rans_tables_free(self._h)
+                self._h = None
+        except Exception:
+            pass
 
 
 def encode(symbols, indexes, tables):

@@ -24,7 +24,16 @@ typedef struct {
   const int32_t* cdf_sizes;
   const int32_t* offsets;
   int32_t n_cdf;
+  /* Handle from crdr_rans_tables_prepare() or NULL.  A prepared handle owns private copies of the arrays and the
+   * per-table acceleration structures (reciprocal frequencies, decoder bucket index); with NULL they are rebuilt
+   * for every call.  Nothing is cached by address, so rebuilt or reloaded tables can never be confused. */
+  const void* prepared;
 } crdr_cdf_tables;
+
+/* Copies the tables and builds the coder's acceleration structures once; the arrays of `t` may be freed or
+ * overwritten afterwards.  Returns NULL on invalid input.  Free with crdr_rans_tables_free(). */
+void* crdr_rans_tables_prepare(const crdr_cdf_tables* t);
+void crdr_rans_tables_free(void* prepared);
 
 /* pmf[n] (float32) -> cdf[n+1] (uint32, cdf[n] == 2^precision, every bin non-empty). 0 on success. */
 int crdr_pmf_to_quantized_cdf(const float* pmf, int64_t n, int32_t precision, uint32_t* cdf);

@@ -162,3 +162,26 @@ def test_pmf_to_quantized_cdf_properties(oracle):
         assert np.array_equal(cdf, np.array(ans.pmf_to_quantized_cdf(p, 16)))
     with pytest.raises(ValueError):
         rans.pmf_to_quantized_cdf(np.array([0.5, np.nan], np.float32))
+
+
+def test_rebuilt_tables_never_reuse_stale_frequencies():
+    """tables rebuilt with different pmfs in a loop (the allocator recycles addresses) must each
+    round-trip; the coder holds no address-keyed cache, every rans.Tables owns a prepared native copy."""
+    import gc
+    from crdr_b200 import rans
+    rng = np.random.default_rng(5)
+    for it in range(20):
+        k = 9 + (it % 3)
+        pmf = rng.random(k).astype(np.float32) ** (1 + it % 4)
+        pmf /= pmf.sum()
+        cdf = rans.pmf_to_quantized_cdf(pmf)
+        src = np.ascontiguousarray(cdf[None, :])
+        t = rans.Tables(src, [cdf.size], [-(k // 2)])
+        src[:] = 0  # the source buffers may be overwritten in place (load_state_dict): the tables own copies
+        sym = rng.integers(-(k // 2) - 3, k // 2 + 4, size=4000).astype(np.int32)
+        idx = np.zeros_like(sym)
+        stream = rans.encode(sym, idx, t)
+        out = rans.Decoder(stream).decode_stream(idx, t)
+        assert np.array_equal(out, sym), f"iteration {it}"
+        del t
+        gc.collect()

@@ -91,8 +91,10 @@ def test_header_and_container_bytes(tmp_path):
     hdr = hh.encode((512, 768), rate_ind=1.75, max_abs=21.9)
     assert hdr == bytes([0, 2, 0, 3, 21, 28]) and hh.decode(hdr) == {"img_size": (512, 768), "max_sample": 21, "rate_ind": 1.75}
     assert hh.encode((1, 1), y_hat=torch.tensor([-3.7, 2.0]), rate_ind=torch.tensor([4.0])) == bytes([1, 0, 1, 0, 3, 64])
+    # the informational max-sample byte wraps like the reference's np.uint8 cast (numpy 1.x) instead of failing the encode
+    assert hh.encode((10, 10), rate_ind=0.0, max_abs=300.0) == bytes([10, 0, 10, 0, 300 & 0xFF, 0])
     with pytest.raises(OverflowError):
-        hh.encode((10, 10), rate_ind=0.0, max_abs=300.0)
+        hh.encode((70000, 10), rate_ind=0.0, max_abs=1.0)
     strings = [hdr, b"", b"\x01\x02\x03" * 100]
     p = tmp_path / "x.bin"
     save_byte_strings(str(p), strings)
