@@ -53,6 +53,7 @@ uint32_t* device_status_word() {
 }
 
 int conv2d_launch(const crdr_conv_desc* d, cudaStream_t stream);
+void conv_set_lean(int enabled, int swizzle);
 int gauss_launch(const crdr_gauss_desc* d, int mode, cudaStream_t st);
 int eb_launch(const crdr_eb_desc* d, int dequant, cudaStream_t st);
 int nhwc_to_nchw_launch(const float* x, int x_cs, int x_coff, int n, int hw, int c, float* out, cudaStream_t st);
@@ -115,6 +116,11 @@ int crdr_debug_events(uint32_t* out, int32_t max_words) {
   cudaMemset(p + 64, 0, 65536);
   return CRDR_OK;
 }
+
+/* bring-up / test aid (not part of the documented ABI): select the convolution epilogue at run time.
+ * enabled: 1 = TMA-in / TMA-out LEAN epilogue where eligible (default), 0 = staged epilogue everywhere, -1 = keep;
+ * swizzle: 1 = SWIZZLE_64B staging units (default), 0 = linear, -1 = keep.  Both epilogues produce identical bits. */
+void crdr_debug_conv_epilogue(int32_t enabled, int32_t swizzle) { conv_set_lean(enabled, swizzle); }
 
 int crdr_conv2d(const crdr_conv_desc* d, void* stream) {
   if (!d) { set_error("conv2d: null descriptor"); return CRDR_ERR_BAD_SHAPE; }

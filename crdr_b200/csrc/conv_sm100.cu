@@ -22,6 +22,7 @@
 //
 // Deterministic: fixed K order, no atomics on data, no split-K; a given output pixel sees the same
 // arithmetic whatever the batch size or tile position.
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
@@ -50,6 +51,8 @@ constexpr int kChunkKB = 6;                // F16X3: K blocks per D0 accumulate 
 constexpr uint32_t kSmemLimit = 227 * 1024;
 constexpr uint32_t kDynSmemMax = kSmemLimit - 8 * 1024;  // static smem: parameter cache (5 KB) + barriers
 
+constexpr int kMaxLeanRes = 6;             // LEAN epilogue: residual slots (per warp group a private ring of 1-2 slots)
+constexpr uint32_t kLeanUnitPlane = 128u * 64u;  // LEAN: one unit = [128 rows][32 channels] fp16 per plane
 constexpr int kMaxCBlocks = 12;            // PATCH mode: 64-channel blocks of the (two-range) input
 constexpr int kPatchTH = 16, kPatchTW = 8; // PATCH mode: the 128 GEMM rows are a 16 x 8 pixel tile of the base grid
 
@@ -58,6 +61,10 @@ struct alignas(64) ConvKParams {
   CUtensorMap tm_lo;
   CUtensorMap tm_in_hi;  // PATCH mode: 4-D (C, W, H, N) view of the input planes
   CUtensorMap tm_in_lo;
+  CUtensorMap tm_out_hi; // LEAN epilogue: 4-D (C, W, H, N) views of the output / residual planes, box (32, 8, 16, 1)
+  CUtensorMap tm_out_lo;
+  CUtensorMap tm_res_hi;
+  CUtensorMap tm_res_lo;
   crdr_conv_desc d;
   // PATCH mode geometry
   int32_t ph, pw, dh_min, dw_min, ncb, tiles_h, tiles_w, patch_stages;
@@ -67,6 +74,7 @@ struct alignas(64) ConvKParams {
   int32_t m_total, nkb, cin, k_real, nplanes, stages, tmem_cols, use_tma;
   int32_t vec_planes_out, vec_f32_out, vec_res_planes, vec_res_f32, vec_trunk;
   int32_t has_bias, has_add, has_affine, chunk_kb, trace, split, fast_epi, res_stage_pitch, out_stage_pitch, dbg;
+  int32_t lean_swz, lean_res_slots;   // LEAN epilogue: staging units are SWIZZLE_64B (1) or linear (0); residual ring depth
   uint32_t* status;
 };
 
@@ -261,7 +269,36 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16
       : "r"(taddr)
       : "memory");
 }
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+      "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// ---- LEAN epilogue plumbing: bulk tensor stores from shared memory, named barriers, 128-bit shared accesses ----
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+               ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_named(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
@@ -513,7 +550,7 @@ __device__ __forceinline__ void epi_finish(const ConvKParams& P, int64_t opix, i
     float amax = 0.f;
 #pragma unroll
     for (int e = 0; e < 16; ++e) amax = fmaxf(amax, fabsf(v[e]));
-    if (!(amax <= 65504.0f)) {  // also true for NaN
+    if (!(amax <= 65504.0f)) {
       atomicOr(P.status, kFlagOverflow);
 #pragma unroll
       for (int e = 0; e < 16; ++e) v[e] = fminf(fmaxf(v[e], -65504.0f), 65504.0f);
@@ -548,6 +585,94 @@ __device__ __forceinline__ void epi_finish(const ConvKParams& P, int64_t opix, i
         ((uint4*)pl)[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         ((uint4*)pl)[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
       }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// LEAN epilogue (patch + CTA-pair kernels, F16X1 or DIRECT F16X3).  A unit is 32 output channels of the tile's 128
+// rows ([128][64 B] per fp16 plane in shared memory, the box of a 4-D tensor map over the NHWC planes).  Residual
+// units arrive by TMA in a small ring, results leave through one staging unit per warp group and a TMA store (which
+// also clips partial tiles): no per-thread global addressing, no cp.async bookkeeping, no shuffles, a third of the
+// instructions of the staged epilogue above.  The arithmetic is the same sequence of fp32 operations as epi_finish,
+// so both epilogues produce identical bits.
+// ----------------------------------------------------------------------------------------------
+template <bool THREE>
+__device__ __forceinline__ void lean_unit_math(float (&v)[32], const uint4 (&rh)[4], const uint4 (&rl)[4],
+                                               const float* s_par, int co0, uint32_t ef, uint32_t* status,
+                                               uint32_t (&hw)[16], uint32_t (&lw)[16]) {
+  const int mode = (int)(ef >> kEfModeShift);
+  const float4* par = reinterpret_cast<const float4*>(s_par + co0);
+  constexpr int kVecStride = kMaxCout / 4;
+  if (ef & kEfBias) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 t = par[q];
+      v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+    }
+  }
+  if (ef & kEfRelu) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
+  }
+  if (ef & kEfAdd) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 t = par[kVecStride + q];
+      v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+    }
+  }
+  if (mode == CRDR_EPI_RESIDUAL) {
+    const bool has_lo = THREE && (ef & kEfResLo);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t h4[4] = {rh[j].x, rh[j].y, rh[j].z, rh[j].w};
+      const uint32_t l4[4] = {rl[j].x, rl[j].y, rl[j].z, rl[j].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 a = unpack_h2(h4[i]);
+        if (has_lo) {
+          const float2 b = unpack_h2(l4[i]);
+          a.x = fmaf(b.x, kLoInv, a.x);
+          a.y = fmaf(b.y, kLoInv, a.y);
+        }
+        v[8 * j + 2 * i] += a.x;
+        v[8 * j + 2 * i + 1] += a.y;
+      }
+    }
+  }
+  if (ef & kEfAffine) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 sc = par[2 * kVecStride + q], sh = par[3 * kVecStride + q];
+      v[4 * q] = fmaf(v[4 * q], sc.x, sh.x); v[4 * q + 1] = fmaf(v[4 * q + 1], sc.y, sh.y);
+      v[4 * q + 2] = fmaf(v[4 * q + 2], sc.z, sh.z); v[4 * q + 3] = fmaf(v[4 * q + 3], sc.w, sh.w);
+    }
+  }
+  // one range check per unit (four independent max chains)
+  float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+#pragma unroll
+  for (int e = 0; e < 32; e += 4) {
+    m0 = fmaxf(m0, fabsf(v[e])); m1 = fmaxf(m1, fabsf(v[e + 1]));
+    m2 = fmaxf(m2, fabsf(v[e + 2])); m3 = fmaxf(m3, fabsf(v[e + 3]));
+  }
+  const float amax = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  if (!(amax <= 65504.0f)) {   // inputs are finite fp16 planes, so a NaN can only follow an overflow flagged upstream
+    atomicOr(status, kFlagOverflow);
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = fminf(fmaxf(v[e], -65504.0f), 65504.0f);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    hw[i] = *reinterpret_cast<const uint32_t*>(&h);
+    if (THREE) {
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(fmaf(v[2 * i], kLoScale, -kLoScale * hf.x),
+                                          fmaf(v[2 * i + 1], kLoScale, -kLoScale * hf.y));
+      lw[i] = *reinterpret_cast<const uint32_t*>(&l);
+    } else {
+      lw[i] = 0u;
     }
   }
 }
@@ -645,7 +770,7 @@ __device__ __forceinline__ void trace_event(uint32_t* status, uint32_t region, u
 // tcgen05.mma.cta_group::2 with M = 256 over both CTAs' shared memory / TMEM, each CTA loads its own halo patch and
 // HALF of the weight tile.  One 128 x N x 16 cta_group::1 MMA occupies the tensor pipe for ~N cycles (measured,
 // twice the 4096 MAC/clk rate); the pair form is how sm_100 reaches the full rate.
-template <int MAXCH, bool PATCH, bool CG2 = false, bool DIRECT = false>
+template <int MAXCH, bool PATCH, bool CG2 = false, bool DIRECT = false, bool LEAN = false>
 // (setmaxnreg re-distributes the CTA's LAUNCH allocation: F16X3 patch kernels are bounded at 384 threads so that ptxas
 // gives them 168 registers per thread at launch, enough for 256 x 216 + 128 x 56 afterwards)
 __global__ void __launch_bounds__(PATCH ? (MAXCH > 0 ? 384 : kThreadsPatch) : kThreads, 1)
@@ -654,6 +779,8 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
   // DIRECT: F16X3 for short K (<= kDirectMaxKB K blocks): D0 is one accumulate chain per tile like an F16X1 accumulator,
   // so there is no chunk drain, no register totals, and the launch gets the 12-warp epilogue.
   static_assert(!DIRECT || (MAXCH == 0 && PATCH), "DIRECT is a patch-variant mode without register totals");
+  // LEAN: TMA-in / TMA-out epilogue (see lean_unit_math) for the CTA-pair patch kernels without a chunk drain
+  static_assert(!LEAN || (MAXCH == 0 && PATCH && CG2), "LEAN needs the CTA-pair patch variant without register totals");
   constexpr bool three = MAXCH > 0 || DIRECT;
   constexpr bool drain = MAXCH > 0;
   constexpr int kEpiWarp0 = PATCH ? 0 : 4;      // first of the 8 drain / epilogue warps (a multiple of 4: TMEM lane quarters)
@@ -671,6 +798,8 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
   __shared__ __align__(8) uint64_t acc_empty_bar[2];  // epilogue -> MMA, the tile accumulator (D0 / D1) was consumed
   __shared__ __align__(8) uint64_t patch_full_bar[kMaxPatchStages];
   __shared__ __align__(8) uint64_t patch_empty_bar[kMaxPatchStages];
+  __shared__ __align__(8) uint64_t lean_res_full[kMaxLeanRes];   // LEAN: residual unit landed (TMA)
+  __shared__ __align__(8) uint64_t lean_res_empty[kMaxLeanRes];  // LEAN: the unit's four consumer warps have read it
   __shared__ uint32_t tmem_slot;
   __shared__ int s_dh[CRDR_MAX_TAPS + 1], s_dw[CRDR_MAX_TAPS + 1];
   __shared__ __align__(16) float s_par[4 * kMaxCout];
@@ -730,6 +859,10 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
       mbar_init(smem_u32(&full_bar[s]), full_count);
       mbar_init(smem_u32(&empty_bar[s]), 1u);
     }
+    for (int b = 0; b < kMaxLeanRes; ++b) {
+      mbar_init(smem_u32(&lean_res_full[b]), 1u);
+      mbar_init(smem_u32(&lean_res_empty[b]), 4u);
+    }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&d0_full_bar[b]), 1u);
       mbar_init(smem_u32(&d0_empty_bar[b]), (CG2 ? 2u : 1u) * kEpiWarps);   // one arrive per drain warp (of both CTAs)
@@ -746,6 +879,14 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
       if (PATCH) {
         prefetch_tmap(&P.tm_in_hi);
         if (three) prefetch_tmap(&P.tm_in_lo);
+      }
+      if (LEAN) {
+        prefetch_tmap(&P.tm_out_hi);
+        if (three) prefetch_tmap(&P.tm_out_lo);
+        if (d.mode == CRDR_EPI_RESIDUAL) {
+          prefetch_tmap(&P.tm_res_hi);
+          if (three) prefetch_tmap(&P.tm_res_lo);
+        }
       }
     }
     __syncwarp();
@@ -888,6 +1029,102 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
     if (PATCH && !drain) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     else if (PATCH) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+    if constexpr (LEAN) {
+    // ------------------------------------------------------------------ LEAN epilogue: 32-channel units, TMA in / out
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int cgrp = (warp - kEpiWarp0) >> 2;  // warp group: units cgrp, cgrp + kEpiGroups, ... of every tile
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int units = BN >> 5;
+    const uint32_t unit_bytes = (uint32_t)nplanes * kLeanUnitPlane;
+    // Residual units: every warp group owns a private ring of D slots, filled in the group's own unit order.  (A ring
+    // shared by the groups races: a fast group can run two phases ahead of a slot's mbarrier, and a parity wait cannot
+    // tell phase k from phase k-2.)
+    const int D = P.lean_res_slots;
+    const uint32_t res_ring = smem_res + (uint32_t)(cgrp * D) * unit_bytes;
+    const uint32_t stage_unit = smem_res + (uint32_t)(kEpiGroups * D) * unit_bytes + (uint32_t)cgrp * unit_bytes;
+    int rslot = 0;            // this group's next residual slot and its phase
+    uint32_t rpar = 0u;
+    // the row's four 16-byte pieces inside a unit (SWIZZLE_64B: piece index ^ address bits 7-8)
+    const uint32_t sx = P.lean_swz ? (uint32_t)((row >> 1) & 3) : 0u;
+    uint32_t choff[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) choff[j] = (uint32_t)row * 64u + (((uint32_t)j ^ sx) << 4);
+    const uint32_t ef = epi_flags(P);
+    const bool has_res = (int)(ef >> kEfModeShift) == CRDR_EPI_RESIDUAL;
+    const bool issuer = q == 0 && lane == 0;   // issues the group's TMA stores
+    auto arrive_leader = [&](uint64_t* bar) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(bar), 0u));
+    };
+    int jt = 0;
+    for (int tile = tile0; tile < num_tiles; tile += tstep, ++jt) {
+      const int n0 = (tile % n_tiles) * BN;
+      const int tb = jt & 1;
+      mbar_wait(smem_u32(&acc_full_bar[tb]), (uint32_t)(jt >> 1) & 1u, P.status);
+      tc_fence_after();
+      if (cgrp >= units) {   // narrow tile: this group has no unit, but every epilogue warp hands the buffer back
+        arrive_leader(&acc_empty_bar[tb]);
+        continue;
+      }
+#pragma unroll 1
+      for (int u = cgrp; u < units; u += kEpiGroups) {
+        uint32_t r0[32], r1[32];
+        const uint32_t col = (uint32_t)tb * kAccStride + (uint32_t)u * 32u;
+        tmem_ld32_issue(lane_addr + col, r0);
+        if (three) tmem_ld32_issue(lane_addr + kD1Base + col, r1);
+        uint4 rh[4], rl[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { rh[j] = make_uint4(0u, 0u, 0u, 0u); rl[j] = rh[j]; }
+        if (has_res) {
+          const int slot = cgrp * D + rslot;
+          mbar_wait(smem_u32(&lean_res_full[slot]), rpar, P.status);
+          const uint32_t rbase = res_ring + (uint32_t)rslot * unit_bytes;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            rh[j] = lds128(rbase + choff[j]);
+            if (three) rl[j] = lds128(rbase + kLeanUnitPlane + choff[j]);
+          }
+          // The slot goes back to the TMA (async proxy) while these generic-proxy loads may still be queued behind bank
+          // conflicts: without the proxy fence the refill of a slot the producer is already waiting for overtook them
+          // (measured: wrong residual rows in the first unit of a tile, linear staging layout only).
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&lean_res_empty[slot]));
+          if (++rslot == D) { rslot = 0; rpar ^= 1u; }
+        }
+        tmem_wait_ld();
+        if (u + kEpiGroups >= units) arrive_leader(&acc_empty_bar[tb]);   // this warp's last read of the tile's accumulators
+        float v[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          v[e] = three ? fmaf(__uint_as_float(r1[e]), kLoInv, __uint_as_float(r0[e])) : __uint_as_float(r0[e]);
+        uint32_t hw[16], lw[16];
+        lean_unit_math<three>(v, rh, rl, s_par, n0 + u * 32, ef, P.status, hw, lw);
+        if (issuer) bulk_wait_read0();              // the previous store of this group has left the staging unit
+        bar_sync_named(1u + (uint32_t)cgrp, 128u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          st_shared16(stage_unit + choff[j], hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
+          if (three) st_shared16(stage_unit + kLeanUnitPlane + choff[j], lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
+        }
+        fence_proxy_async();                        // generic-proxy writes -> visible to the TMA (async proxy)
+        bar_sync_named(1u + (uint32_t)cgrp, 128u);
+        if (issuer) {
+          int n, h0, w0;
+          patch_tile_origin(P, CRDR_MTILE(tile), n, h0, w0);
+          if (n < d.n) {   // a CTA pair's odd tail tile lies past the end: nothing to store
+            const int c = d.out.coff + n0 + u * 32;
+            tma_store_4d(&P.tm_out_hi, stage_unit, c, w0, h0, n);
+            if (three) tma_store_4d(&P.tm_out_lo, stage_unit + kLeanUnitPlane, c, w0, h0, n);
+          }
+          bulk_commit();
+        }
+      }
+    }
+    if (issuer) bulk_wait0();
+    } else {
     // ------------------------------------------------------------------ drain D0 chunks + epilogue
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int cgrp = (warp - kEpiWarp0) >> 2;  // which group of the tile's column chunks
@@ -1162,6 +1399,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
       cur = nxt;
       opix = opix_next;
     }
+    }  // !LEAN
   } else {
    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
    if (warp == kTmaWarp) {
@@ -1236,6 +1474,37 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
             tma_load_4d(dst, &P.tm_in_hi, P.cb_c0[cb], w0 + P.dw_min, h0 + P.dh_min, n, bar);
             if (three) tma_load_4d(dst + patch_plane_bytes, &P.tm_in_lo, P.cb_c0[cb], w0 + P.dw_min, h0 + P.dh_min, n, bar);
           }
+        }
+      }
+    }
+  } else if (LEAN && warp == kPatchWarp + 1) {
+    // ------------------------------------------------------------------ LEAN: residual units by TMA (one thread)
+    if (lane == 0 && d.mode == CRDR_EPI_RESIDUAL) {
+      const int units = BN >> 5;
+      const uint32_t unit_bytes = (uint32_t)nplanes * kLeanUnitPlane;
+      const int D = P.lean_res_slots;
+      int gslot[kEpiGroups];        // per warp group: next slot of its private ring and the ring's phase
+      uint32_t gpar[kEpiGroups];
+#pragma unroll
+      for (int g = 0; g < kEpiGroups; ++g) { gslot[g] = 0; gpar[g] = 1u; }
+      for (int tile = tile0; tile < num_tiles; tile += tstep) {
+        int n, h0, w0;
+        patch_tile_origin(P, CRDR_MTILE(tile), n, h0, w0);   // a tile past the end has n == d.n -> zero fill
+        const int c0 = d.res.coff + (tile % n_tiles) * BN;
+        int g = 0;
+        for (int u = 0; u < units; ++u) {
+          int slot = 0;
+          uint32_t par = 0u;
+#pragma unroll
+          for (int k = 0; k < kEpiGroups; ++k)   // static indexing keeps the cursors in registers
+            if (k == g) { slot = g * D + gslot[k]; par = gpar[k]; if (++gslot[k] == D) { gslot[k] = 0; gpar[k] ^= 1u; } }
+          mbar_wait(smem_u32(&lean_res_empty[slot]), par, P.status);
+          const uint32_t bar = smem_u32(&lean_res_full[slot]);
+          const uint32_t dst = smem_res + (uint32_t)slot * unit_bytes;
+          mbar_arrive_expect_tx(bar, unit_bytes);
+          tma_load_4d(dst, &P.tm_res_hi, c0 + u * 32, w0, h0, n, bar);
+          if (three) tma_load_4d(dst + kLeanUnitPlane, &P.tm_res_lo, c0 + u * 32, w0, h0, n, bar);
+          if (++g == kEpiGroups) g = 0;
         }
       }
     }
@@ -1533,26 +1802,29 @@ static int weight_tensor_map(const void* ptr, int k_pad, int rows, int box_rows,
 
 struct InKey {
   const void* ptr;
-  int32_t cs, w, h, n, pw, ph, dev;
+  int32_t cs, w, h, n, pw, ph, dev, box_c, swz;
   bool operator==(const InKey& o) const {
-    return ptr == o.ptr && cs == o.cs && w == o.w && h == o.h && n == o.n && pw == o.pw && ph == o.ph && dev == o.dev;
+    return ptr == o.ptr && cs == o.cs && w == o.w && h == o.h && n == o.n && pw == o.pw && ph == o.ph && dev == o.dev &&
+           box_c == o.box_c && swz == o.swz;
   }
 };
 struct InKeyHash {
   size_t operator()(const InKey& k) const {
     size_t h = std::hash<const void*>()(k.ptr);
-    const int32_t v[7] = {k.cs, k.w, k.h, k.n, k.pw, k.ph, k.dev};
-    for (int i = 0; i < 7; ++i) h = h * 1000003u ^ (size_t)v[i];
+    const int32_t v[9] = {k.cs, k.w, k.h, k.n, k.pw, k.ph, k.dev, k.box_c, k.swz};
+    for (int i = 0; i < 9; ++i) h = h * 1000003u ^ (size_t)v[i];
     return h;
   }
 };
 static std::unordered_map<InKey, CUtensorMap, InKeyHash> g_in_cache;
 
-// 4-D (C, W, H, N) tensor map over NHWC fp16 planes with a (64, pw, ph, 1) box, zero fill out of bounds.
-static int input_tensor_map(const void* ptr, int cs, int w, int h, int n, int pw, int ph, CUtensorMap* out) {
+// 4-D (C, W, H, N) tensor map over NHWC fp16 planes with a (box_c, pw, ph, 1) box, zero fill out of bounds (loads) /
+// clipping (stores).  swz: 128 (halo patches, 64-channel boxes), 64 (LEAN units, 32-channel boxes) or 0 (linear).
+static int input_tensor_map(const void* ptr, int cs, int w, int h, int n, int pw, int ph, CUtensorMap* out,
+                            int box_c = 64, int swz = 128) {
   int dev = 0;
   cudaGetDevice(&dev);
-  InKey key{ptr, cs, w, h, n, pw, ph, dev};
+  InKey key{ptr, cs, w, h, n, pw, ph, dev, box_c, swz};
   {
     std::lock_guard<std::mutex> lk(g_tm_mutex);
     auto it = g_in_cache.find(key);
@@ -1562,11 +1834,13 @@ static int input_tensor_map(const void* ptr, int cs, int w, int h, int n, int pw
   if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return CRDR_ERR_CUDA; }
   cuuint64_t gdim[4] = {(cuuint64_t)cs, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t gstride[3] = {(cuuint64_t)cs * 2, (cuuint64_t)w * cs * 2, (cuuint64_t)h * w * cs * 2};
-  cuuint32_t box[4] = {64u, (cuuint32_t)pw, (cuuint32_t)ph, 1u};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)pw, (cuuint32_t)ph, 1u};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUtensorMap tm;
+  const CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                                    : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(input) failed (CUresult %d)", (int)r); return CRDR_ERR_CUDA; }
   {
@@ -1581,6 +1855,16 @@ static int input_tensor_map(const void* ptr, int cs, int w, int h, int n, int pw
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 static bool planes_vec_ok(const crdr_planes& p) {
   return p.hi && aligned16(p.hi) && (!p.lo || aligned16(p.lo)) && p.cs % 8 == 0 && p.coff % 8 == 0;
+}
+
+// runtime switches of the LEAN epilogue (defaults from CRDR_CONV_LEAN / CRDR_LEAN_SWZ; tests flip them to compare the
+// two epilogues bit for bit inside one process)
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+static std::atomic<int> g_lean_enabled{env_int("CRDR_CONV_LEAN", 1)};
+static std::atomic<int> g_lean_swizzle{env_int("CRDR_LEAN_SWZ", 1)};
+void conv_set_lean(int enabled, int swizzle) {
+  if (enabled >= 0) g_lean_enabled.store(enabled);
+  if (swizzle >= 0) g_lean_swizzle.store(swizzle);
 }
 
 int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
@@ -1721,10 +2005,22 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
   const int groups = epi_groups(use_patch, three && !direct);
   const int ch_per_warp = (d.tile_n / 16 + groups - 1) / groups;  // column chunks per epilogue warp
   const int maxch = (three && !direct) ? ch_per_warp : 0;
+  // LEAN epilogue (TMA-in / TMA-out, see lean_unit_math): CTA-pair patch launches without a chunk drain whose output is
+  // a stride-1 set of fp16 planes in 32-channel units; residual (planes) and per-channel vectors supported.
+  bool lean = g_lean_enabled.load() != 0 && cg2 && (!three || direct) && P.fast_epi && d.out.hi && !d.out_f32 &&
+              d.out_stride == 1 && d.out_ph == 0 && d.out_pw == 0 && d.hb == d.hout && d.wb == d.wout &&
+              (d.mode == CRDR_EPI_NONE || (d.mode == CRDR_EPI_RESIDUAL && !d.res_f32)) && d.tile_n % 32 == 0 &&
+              d.cout % 32 == 0 && (three ? d.out.lo != nullptr : d.out.lo == nullptr) &&
+              (d.mode == CRDR_EPI_NONE || !three || d.res.lo != nullptr);
+  // residual slots per warp group: two for single-plane tensors, one for the (twice as large) two-plane units
+  const int lean_res_slots = (lean && d.mode == CRDR_EPI_RESIDUAL) ? (three ? 1 : 2) : 0;
+  const uint32_t lean_bytes = lean ? (uint32_t)(lean_res_slots * groups + groups) * (uint32_t)(three ? 2 : 1) * kLeanUnitPlane : 0u;
   typedef void (*KernelFn)(const ConvKParams);
   KernelFn fn = nullptr;
   // CTA-pair form (cta_group::2, M = 256 per MMA) for the patch variant; CRDR_CONV_CG2=0 falls back to single CTAs
-  if (direct) {
+  if (lean) {
+    fn = direct ? conv_tcgen05_kernel<0, true, true, true, true> : conv_tcgen05_kernel<0, true, true, false, true>;
+  } else if (direct) {
     fn = conv_tcgen05_kernel<0, true, true, true>;
   } else if (cg2) {
     switch (maxch) {
@@ -1747,9 +2043,9 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
     case 8: fn = conv_tcgen05_kernel<4, false>; break;
     default: fn = conv_tcgen05_kernel<4, true>; break;
   }
-  const int variant = direct ? 15 : cg2 ? 10 + maxch : maxch * 2 + (use_patch ? 1 : 0);
+  const int variant = lean ? (direct ? 17 : 16) : direct ? 15 : cg2 ? 10 + maxch : maxch * 2 + (use_patch ? 1 : 0);
   static std::mutex attr_mutex;
-  static bool attr_done[16] = {false};
+  static bool attr_done[18] = {false};
   static int num_sms = 0;
   {
     std::lock_guard<std::mutex> lk(attr_mutex);
@@ -1770,7 +2066,9 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
   }
   // residual staging: one private slot per output row (pitch padded by 16 B against bank conflicts)
   uint32_t res_need = 0, res_pitch = 0;
-  if (d.mode != CRDR_EPI_NONE && P.fast_epi) {
+  if (lean) {
+    res_need = lean_bytes;   // residual ring + staging units (mandatory for this variant)
+  } else if (d.mode != CRDR_EPI_NONE && P.fast_epi) {
     res_pitch = (uint32_t)d.tile_n * (three ? 4u : 2u) + 16u;
     res_need = kTileM * res_pitch;
   }
@@ -1779,7 +2077,7 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
   {
     static int ost_env = -1;
     if (ost_env < 0) { const char* e = getenv("CRDR_CONV_OSTAGE"); ost_env = e ? atoi(e) : 1; }
-    if (ost_env && P.fast_epi && d.out.hi && !d.out_f32) {
+    if (!lean && ost_env && P.fast_epi && d.out.hi && !d.out_f32) {
       out_pitch = (uint32_t)((d.tile_n / 16 + groups - 1) / groups) * 32u + 16u;
       out_need = (uint32_t)(4 * groups) * 32u * out_pitch * (d.out.lo ? 2u : 1u);
     }
@@ -1838,7 +2136,23 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
   uint32_t res_total = 0;
   P.res_stage_pitch = 0;
   P.out_stage_pitch = 0;
-  if (res_need && patch_total + 2 * stage_bytes + 1024 + res_need <= kDynSmemMax) {
+  if (lean) {
+    if (patch_total + 2 * stage_bytes + 1024 + res_need > kDynSmemMax) {
+      set_error("conv2d: the LEAN epilogue does not fit (patch %u B, stage %u B, units %u B)", patch_total, stage_bytes, res_need);
+      return CRDR_ERR_BAD_SHAPE;
+    }
+    res_total = res_need;
+    P.lean_res_slots = lean_res_slots;
+    P.lean_swz = g_lean_swizzle.load();
+    const int swz = P.lean_swz ? 64 : 0;
+    int rc = input_tensor_map(d.out.hi, d.out.cs, d.wout, d.hout, d.n, kPatchTW, kPatchTH, &P.tm_out_hi, 32, swz);
+    if (!rc && three) rc = input_tensor_map(d.out.lo, d.out.cs, d.wout, d.hout, d.n, kPatchTW, kPatchTH, &P.tm_out_lo, 32, swz);
+    if (!rc && d.mode == CRDR_EPI_RESIDUAL) {
+      rc = input_tensor_map(d.res.hi, d.res.cs, d.wout, d.hout, d.n, kPatchTW, kPatchTH, &P.tm_res_hi, 32, swz);
+      if (!rc && three) rc = input_tensor_map(d.res.lo, d.res.cs, d.wout, d.hout, d.n, kPatchTW, kPatchTH, &P.tm_res_lo, 32, swz);
+    }
+    if (rc) return rc;
+  } else if (res_need && patch_total + 2 * stage_bytes + 1024 + res_need <= kDynSmemMax) {
     P.res_stage_pitch = (int32_t)res_pitch;
     res_total = res_need;
   }

@@ -139,6 +139,11 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def set_conv_epilogue(enabled=-1, swizzle=-1):
+    """Test / bring-up aid: choose between the LEAN (TMA-in / TMA-out) and the staged convolution epilogue."""
+    lib().crdr_debug_conv_epilogue(int(enabled), int(swizzle))
+
+
 def status_reset():
     check(lib().crdr_status_reset(stream_handle()), counts=False)
 
