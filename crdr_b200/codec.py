@@ -269,23 +269,24 @@ class CharmEngine:
         return [(self.off_mean, self.hc + self.sc * self.n_support(s)), (self.off_tmp + s * self.sc, self.sc)]
 
     def params(self, T, s, ms):
-        """mu_s, sigma_s -> ms[..., 2*s*sc : 2*(s+1)*sc] (fp32 NHWC scratch holding [mu | sigma] per slice)."""
-        self.mean[s](T, self._segs_mean(s), out_f32=ms, out_f32_coff=2 * s * self.sc, want_planes=False)
-        self.scale[s](T, self._segs_scale(s), out_f32=ms, out_f32_coff=(2 * s + 1) * self.sc, want_planes=False)
+        """mu_s, sigma_s -> fp32 NHWC scratch `ms` laid out [mu of all slices | sigma of all slices], so that the
+        element-wise kernels cover a whole dependency group (consecutive slices) in one launch."""
+        self.mean[s](T, self._segs_mean(s), out_f32=ms, out_f32_coff=s * self.sc, want_planes=False)
+        self.scale[s](T, self._segs_scale(s), out_f32=ms, out_f32_coff=self.yc + s * self.sc, want_planes=False)
 
     def refine(self, T, s, yq32, yhat32):
         """LRP: y_hat_s = yq_s + 0.5 tanh(lrp(...)) -> support tensor (planes) and yhat32 (fp32 NHWC)."""
         self.lrp[s](T, self._segs_lrp(s), mode=nv.EPI_HALF_TANH, res=yq32, res_coff=s * self.sc, out=T,
                     out_coff=self.off_y + s * self.sc, out_f32=yhat32, out_f32_coff=s * self.sc)
 
-    def gauss_desc(self, gp, T, s, cnt, n, hw, ms, y32=None, yq32=None, sym=None, idx=None, lik=None):
-        """Descriptor covering `cnt` consecutive slices starting at s (they share the [mu|sigma] interleave
-        only when cnt == 1, so multi-slice calls are issued per slice by the caller)."""
+    def gauss_desc(self, gp, T, s, cnt, n, hw, ms, y32=None, yq32=None, sym=None, idx=None, lik=None, sym16=None,
+                   idx8=None):
+        """Descriptor covering `cnt` consecutive slices starting at slice s."""
         d = nv.GaussDesc()
         if y32 is not None:
             d.y, d.y_cs, d.y_coff = y32.data_ptr(), self.yc, s * self.sc
         d.mu, d.sigma = ms.data_ptr(), ms.data_ptr()
-        d.ms_cs, d.mu_coff, d.sigma_coff = ms.shape[-1], 2 * s * self.sc, (2 * s + 1) * self.sc
+        d.ms_cs, d.mu_coff, d.sigma_coff = ms.shape[-1], s * self.sc, self.yc + s * self.sc
         d.n, d.hw, d.c = n, hw, self.sc * cnt
         d.scale_bound, d.scale_table, d.ntable = gp.bound, gp.table.data_ptr(), gp.table.numel()
         d.yq_planes = T.planes(self.off_tmp + s * self.sc)
@@ -294,11 +295,14 @@ class CharmEngine:
         d.symbols = sym.data_ptr() if sym is not None else None
         d.indexes = idx.data_ptr() if idx is not None else None
         d.likelihood = lik.data_ptr() if lik is not None else None
+        d.symbols16 = sym16.data_ptr() if sym16 is not None else None
+        d.indexes8 = idx8.data_ptr() if idx8 is not None else None
         d.c_total, d.nchw_coff = self.yc, s * self.sc
         return d
 
-    def encode(self, T, y32, gp):
-        """Encoder-side pass.  Returns y_hat fp32 NHWC, symbols / indexes int32 NCHW, likelihood fp32 NCHW."""
+    def encode(self, T, y32, gp, compact=False):
+        """Encoder-side pass.  Returns y_hat fp32 NHWC, symbols / indexes int32 NCHW, likelihood fp32 NCHW and, with
+        ``compact``, the int16 symbols / uint8 indexes copies the host range coder reads."""
         n, h, w = T.n, T.h, T.w
         dev = T.hi.device
         ms = torch.empty((n, h, w, 2 * self.yc), dtype=torch.float32, device=dev)
@@ -307,38 +311,41 @@ class CharmEngine:
         sym = torch.empty((n, self.yc, h, w), dtype=torch.int32, device=dev)
         idx = torch.empty((n, self.yc, h, w), dtype=torch.int32, device=dev)
         lik = torch.empty((n, self.yc, h, w), dtype=torch.float32, device=dev)
+        sym16 = torch.empty((n, self.yc, h, w), dtype=torch.int16, device=dev) if compact else None
+        idx8 = torch.empty((n, self.yc, h, w), dtype=torch.uint8, device=dev) if compact else None
         st, L = nv.stream_handle(), nv.lib()
         for grp in self.groups():
             for s in grp:
                 self.params(T, s, ms)
-            for s in grp:
-                d = self.gauss_desc(gp, T, s, 1, n, h * w, ms, y32=y32, yq32=yq32, sym=sym, idx=idx, lik=lik)
-                nv.check(L.crdr_gauss_quantize(C.byref(d), st))
+            d = self.gauss_desc(gp, T, grp[0], len(grp), n, h * w, ms, y32=y32, yq32=yq32, sym=sym, idx=idx, lik=lik,
+                                sym16=sym16, idx8=idx8)
+            nv.check(L.crdr_gauss_quantize(C.byref(d), st))
             for s in grp:
                 self.refine(T, s, yq32, yhat32)
+        if compact:
+            return yhat32, sym, idx, lik, sym16, idx8
         return yhat32, sym, idx, lik
 
-    def decode_steps(self, T, gp):
+    def decode_steps(self, T, gp, compact=False):
         """Decoder-side pass as a generator: yields ``(first_slice, count, idx_nchw)`` whenever the symbols of a slice group
-        are needed (``idx_nchw`` holds the CDF indexes of that group) and expects the int32 NCHW symbols (device tensor,
-        full [n, yc, h, w] buffer with that slice range filled) to be sent back.  Returns y_hat fp32 NHWC.
-        The generator form lets the caller interleave several independent batches on one stream."""
+        are needed (``idx_nchw`` holds the CDF indexes of that group: int32, or uint8 with ``compact``) and expects the
+        int32 NCHW symbols (device tensor, full [n, yc, h, w] buffer with that slice range filled) to be sent back.
+        Returns y_hat fp32 NHWC.  The generator form lets the caller interleave several independent batches on one stream."""
         n, h, w = T.n, T.h, T.w
         dev = T.hi.device
         ms = torch.empty((n, h, w, 2 * self.yc), dtype=torch.float32, device=dev)
         yq32 = torch.empty((n, h, w, self.yc), dtype=torch.float32, device=dev)
         yhat32 = torch.empty((n, h, w, self.yc), dtype=torch.float32, device=dev)
-        idx = torch.empty((n, self.yc, h, w), dtype=torch.int32, device=dev)
+        idx = torch.empty((n, self.yc, h, w), dtype=torch.uint8 if compact else torch.int32, device=dev)
         L = nv.lib()
         for grp in self.groups():
             for s in grp:
                 self.params(T, s, ms)
-                d = self.gauss_desc(gp, T, s, 1, n, h * w, ms, idx=idx)
-                nv.check(L.crdr_gauss_indexes(C.byref(d), nv.stream_handle()))
+            d = self.gauss_desc(gp, T, grp[0], len(grp), n, h * w, ms, **({"idx8": idx} if compact else {"idx": idx}))
+            nv.check(L.crdr_gauss_indexes(C.byref(d), nv.stream_handle()))
             sym = yield grp[0], len(grp), idx
-            for s in grp:
-                d = self.gauss_desc(gp, T, s, 1, n, h * w, ms, yq32=yq32, sym=sym)
-                nv.check(L.crdr_gauss_dequantize(C.byref(d), nv.stream_handle()))
+            d = self.gauss_desc(gp, T, grp[0], len(grp), n, h * w, ms, yq32=yq32, sym=sym)
+            nv.check(L.crdr_gauss_dequantize(C.byref(d), nv.stream_handle()))
             for s in grp:
                 self.refine(T, s, yq32, yhat32)
         return yhat32

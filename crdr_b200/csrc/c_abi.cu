@@ -63,7 +63,11 @@ int image_to_planes_launch(const float* img, int n, int h, int w, int hp, int wp
 int image_to_patches_launch(const float* img, int n, int h, int w, int hp, int wp, crdr_planes out, cudaStream_t st);
 int planes_to_image_launch(const float* x, int x_cs, int n, int hp, int wp, int h, int w, float* img, cudaStream_t st);
 int phases_to_image_launch(const float* x, int x_cs, int n, int hb, int wb, int h, int w, float* img, cudaStream_t st);
+int image_u8_to_patches_launch(const uint8_t* img, int n, int h, int w, int hp, int wp, crdr_planes out, cudaStream_t st);
+int phases_to_image_u8_launch(const float* x, int x_cs, int n, int hb, int wb, int h, int w, uint8_t* img, cudaStream_t st);
+int max_abs_batch_launch(const float* x, int n, int64_t per, float* out, cudaStream_t st);
 int bits_launch(const float* lik, int n, int64_t per, float* bits, cudaStream_t st);
+int status_clear_bits_launch(uint32_t* status, uint32_t bits, cudaStream_t st);
 int max_abs_launch(const float* x, int64_t count, float* out, cudaStream_t st);
 
 }  // namespace crdr
@@ -90,11 +94,25 @@ int crdr_status_read(uint32_t* flags, void* stream) {
   if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
   if (e != cudaSuccess) { set_error("status_read: %s", cudaGetErrorString(e)); return CRDR_ERR_CUDA; }
   if (*flags) {
-    set_error("device status flags 0x%x (%s%s)", *flags, (*flags & kFlagOverflow) ? "fp16 overflow " : "",
-              (*flags & kFlagTimeout) ? "pipeline timeout" : "");
+    set_error("device status flags 0x%x (%s%s%s)", *flags, (*flags & kFlagOverflow) ? "fp16 overflow " : "",
+              (*flags & kFlagTimeout) ? "pipeline timeout " : "", (*flags & kFlagSymRange) ? "int16 symbol range" : "");
     return CRDR_ERR_DEVICE_FLAG;
   }
   return CRDR_OK;
+}
+
+int crdr_status_peek_async(uint32_t* host_flags, void* stream) {
+  uint32_t* p = device_status_word();
+  if (!p || !host_flags) return CRDR_ERR_CUDA;
+  cudaError_t e = cudaMemcpyAsync(host_flags, p, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (e != cudaSuccess) { set_error("status_peek: %s", cudaGetErrorString(e)); return CRDR_ERR_CUDA; }
+  return CRDR_OK;
+}
+
+int crdr_status_clear_bits(uint32_t bits, void* stream) {
+  uint32_t* p = device_status_word();
+  if (!p) return CRDR_ERR_CUDA;
+  return status_clear_bits_launch(p, bits, (cudaStream_t)stream);
 }
 
 /* bring-up aid (not part of the documented ABI): MMA-thread cycle counters of CTA 0 of the last traced launch */
@@ -150,6 +168,20 @@ int crdr_planes_to_image(const float* x, int32_t x_cs, int32_t n, int32_t hp, in
 int crdr_phases_to_image(const float* x, int32_t x_cs, int32_t n, int32_t hb, int32_t wb, int32_t h, int32_t w,
                          float* img, void* stream) {
   return phases_to_image_launch(x, x_cs, n, hb, wb, h, w, img, (cudaStream_t)stream);
+}
+
+int crdr_image_u8_to_patches(const uint8_t* img, int32_t n, int32_t h, int32_t w, int32_t hp, int32_t wp, crdr_planes out,
+                             void* stream) {
+  return image_u8_to_patches_launch(img, n, h, w, hp, wp, out, (cudaStream_t)stream);
+}
+
+int crdr_phases_to_image_u8(const float* x, int32_t x_cs, int32_t n, int32_t hb, int32_t wb, int32_t h, int32_t w,
+                            uint8_t* img, void* stream) {
+  return phases_to_image_u8_launch(x, x_cs, n, hb, wb, h, w, img, (cudaStream_t)stream);
+}
+
+int crdr_max_abs_batch(const float* x, int32_t n, int64_t per, float* out, void* stream) {
+  return max_abs_batch_launch(x, n, per, out, (cudaStream_t)stream);
 }
 
 int crdr_nhwc_to_nchw(const float* x, int32_t x_cs, int32_t x_coff, int32_t n, int32_t hw, int32_t c, float* out,

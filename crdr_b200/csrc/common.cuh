@@ -13,6 +13,7 @@ constexpr float kLoScale = 2048.0f;          // lo plane stores (x - hi) * 2^11
 constexpr float kLoInv = 1.0f / 2048.0f;
 constexpr uint32_t kFlagOverflow = 1u;       // fp16 overflow in an epilogue
 constexpr uint32_t kFlagTimeout = 2u;        // mbarrier wait timed out (pipeline bug guard)
+constexpr uint32_t kFlagSymRange = 4u;       // a quantised symbol did not fit the compact int16 copy
 
 void set_error(const char* fmt, ...);
 uint32_t* device_status_word();              // per-device, lazily allocated

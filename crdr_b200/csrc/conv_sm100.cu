@@ -68,6 +68,11 @@ struct alignas(64) ConvKParams {
   crdr_conv_desc d;
   // PATCH mode geometry
   int32_t ph, pw, dh_min, dw_min, ncb, tiles_h, tiles_w, patch_stages;
+  // PATCH mode with an input stride s (1 or 2): the taps are grouped into s*s parity classes; class c owns one halo patch
+  // per channel block, loaded through a tensor map that steps s pixels (elementStrides), from pixel
+  // (s*h0 + cls_h0[c], s*w0 + cls_w0[c]); its taps are tapoff[cls_end[c-1] .. cls_end[c]).
+  int32_t ncls, in_mul;
+  int32_t cls_end[4], cls_h0[4], cls_w0[4];
   int32_t cb_c0[kMaxCBlocks];
   int32_t cb_ksteps[kMaxCBlocks];   // PATCH: K steps (of 16 channels) of a channel block that hold real channels (1..4)
   uint32_t tapoff[CRDR_MAX_TAPS];  // PATCH: byte offset of a tap's start row inside the halo patch
@@ -1458,22 +1463,25 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
       for (int tile = tile0; tile < num_tiles; tile += tstep) {
         int n, h0, w0;
         patch_tile_origin(P, CRDR_MTILE(tile), n, h0, w0);  // CG2: a tile past the end has n == d.n -> zero fill
-        for (int cb = 0; cb < P.ncb; ++cb, ++pb) {
+        for (int cb = 0; cb < P.ncb; ++cb) {
+         for (int cls = 0; cls < P.ncls; ++cls, ++pb) {
           if (pb == P.patch_stages) { pb = 0; empty_par ^= 1u; }
           mbar_wait(smem_u32(&patch_empty_bar[pb]), empty_par, P.status);
           CRDR_EV(if (P.trace == 2 && blockIdx.x == 0) trace_event(P.status, 2u, ev_count, 12u, (uint32_t)cb);)  // patch: slot free, TMA issued
           const uint32_t bar = smem_u32(&patch_full_bar[pb]);
           const uint32_t dst = smem_patch + (uint32_t)pb * patch_stage_bytes;
+          const int pw0 = w0 * P.in_mul + P.cls_w0[cls], ph0 = h0 * P.in_mul + P.cls_h0[cls];
           if (CG2) {
             if (cta_rank == 0) mbar_arrive_expect_tx(bar, 2u * (uint32_t)nplanes * patch_plane_bytes);
             const uint32_t lbar = mapa_shared(bar, 0u);
-            tma_load_4d_cg2(dst, &P.tm_in_hi, P.cb_c0[cb], w0 + P.dw_min, h0 + P.dh_min, n, lbar);
-            if (three) tma_load_4d_cg2(dst + patch_plane_bytes, &P.tm_in_lo, P.cb_c0[cb], w0 + P.dw_min, h0 + P.dh_min, n, lbar);
+            tma_load_4d_cg2(dst, &P.tm_in_hi, P.cb_c0[cb], pw0, ph0, n, lbar);
+            if (three) tma_load_4d_cg2(dst + patch_plane_bytes, &P.tm_in_lo, P.cb_c0[cb], pw0, ph0, n, lbar);
           } else {
             mbar_arrive_expect_tx(bar, (uint32_t)nplanes * patch_plane_bytes);
-            tma_load_4d(dst, &P.tm_in_hi, P.cb_c0[cb], w0 + P.dw_min, h0 + P.dh_min, n, bar);
-            if (three) tma_load_4d(dst + patch_plane_bytes, &P.tm_in_lo, P.cb_c0[cb], w0 + P.dw_min, h0 + P.dh_min, n, bar);
+            tma_load_4d(dst, &P.tm_in_hi, P.cb_c0[cb], pw0, ph0, n, bar);
+            if (three) tma_load_4d(dst + patch_plane_bytes, &P.tm_in_lo, P.cb_c0[cb], pw0, ph0, n, bar);
           }
+         }
         }
       }
     }
@@ -1545,6 +1553,8 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
         const uint32_t d1 = tmem_base + kD1Base + (uint32_t)tb * kAccStride;
         int tap = 0, ck = 0, kk = 0;  // tap of this K block (PATCH), position inside the D0 chunk / the ring slot
         int cb = 0;                   // channel block of this K block (PATCH)
+        int cls = 0;                  // parity class of the tap (PATCH with an input stride; one class otherwise)
+        int tap_first = 0, tap_end = PATCH ? P.cls_end[0] : 0;   // taps of the class: [tap_first, tap_end)
         for (int kb = 0; kb < nkb; ++kb, ++g) {
           const bool chunk_first = ck == 0;
           const bool chunk_last = ck == chunk_kb - 1 || kb == nkb - 1;
@@ -1559,7 +1569,7 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
           uint64_t a_hi, a_lo;
           if (PATCH) {
             // K block kb = (channel block, tap): the A operand is the patch shifted by the tap offset
-            if (tap == 0) {
+            if (tap == tap_first) {
               CRDR_EV(if (tr) t0 = clock64();)
               mbar_wait(smem_u32(&patch_full_bar[pb]), patch_par, P.status);
               CRDR_EV(if (tr) t_patch += clock64() - t0;)
@@ -1606,12 +1616,19 @@ conv_tcgen05_kernel(const __grid_constant__ ConvKParams P) {
           const bool slot_last = ++kk == KPS || kb == nkb - 1;
           if (slot_last && elected) umma_done<CG2>(smem_u32(&empty_bar[s]));
           if (PATCH) {
-            if (++tap == ntaps) {  // all taps of the channel block issued: the patch buffer may be refilled
-              tap = 0;
-              ++cb;
+            if (++tap == tap_end) {  // all taps of this patch (channel block, parity class) issued: the buffer may be refilled
               if (elected) umma_done<CG2>(smem_u32(&patch_empty_bar[pb]));
               patch_addr += patch_stage_bytes;
               if (++pb == P.patch_stages) { pb = 0; patch_par ^= 1u; patch_addr = smem_patch; }
+              if (tap == ntaps) {    // last class: next channel block
+                tap = 0;
+                cls = 0;
+                ++cb;
+              } else {
+                ++cls;
+              }
+              tap_first = tap;
+              tap_end = P.cls_end[cls];
             }
           }
           if (chunk_last) {
@@ -1821,10 +1838,10 @@ static std::unordered_map<InKey, CUtensorMap, InKeyHash> g_in_cache;
 // 4-D (C, W, H, N) tensor map over NHWC fp16 planes with a (box_c, pw, ph, 1) box, zero fill out of bounds (loads) /
 // clipping (stores).  swz: 128 (halo patches, 64-channel boxes), 64 (LEAN units, 32-channel boxes) or 0 (linear).
 static int input_tensor_map(const void* ptr, int cs, int w, int h, int n, int pw, int ph, CUtensorMap* out,
-                            int box_c = 64, int swz = 128) {
+                            int box_c = 64, int swz = 128, int estride = 1) {
   int dev = 0;
   cudaGetDevice(&dev);
-  InKey key{ptr, cs, w, h, n, pw, ph, dev, box_c, swz};
+  InKey key{ptr, cs, w, h, n, pw, ph, dev, box_c, swz + 1000 * estride};
   {
     std::lock_guard<std::mutex> lk(g_tm_mutex);
     auto it = g_in_cache.find(key);
@@ -1834,8 +1851,10 @@ static int input_tensor_map(const void* ptr, int cs, int w, int h, int n, int pw
   if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return CRDR_ERR_CUDA; }
   cuuint64_t gdim[4] = {(cuuint64_t)cs, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t gstride[3] = {(cuuint64_t)cs * 2, (cuuint64_t)w * cs * 2, (cuuint64_t)h * w * cs * 2};
-  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)pw, (cuuint32_t)ph, 1u};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // pixel step `estride` (a strided convolution's parity-class patch): the box spans pw * estride pixels, of which
+  // every estride-th is loaded (cuTensorMapEncodeTiled: ceil(boxDim / elementStrides) elements per dimension)
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(pw * estride), (cuuint32_t)(ph * estride), 1u};
+  cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
   CUtensorMap tm;
   const CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                                                     : CU_TENSOR_MAP_SWIZZLE_NONE;
@@ -1890,8 +1909,8 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
         cb_c0[ncb++] = d.in.coff + off + 64 * b;
       }
     }
-    if (d.in_stride != 1 || d.k_pad < ncb * d.ntaps * 64) {
-      set_error("conv2d: k_order=1 needs in_stride == 1 and k_pad >= blocks*taps*64 (in_stride=%d k_pad=%d need %d)",
+    if ((d.in_stride != 1 && d.in_stride != 2) || d.k_pad < ncb * d.ntaps * 64) {
+      set_error("conv2d: k_order=1 needs in_stride 1 or 2 and k_pad >= blocks*taps*64 (in_stride=%d k_pad=%d need %d)",
                 d.in_stride, d.k_pad, ncb * d.ntaps * 64);
       return CRDR_ERR_BAD_SHAPE;
     }
@@ -2084,17 +2103,39 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
   }
   uint32_t patch_total = 0;
   if (use_patch) {
+    // Tap (dh, dw) of a stride-s layer reads pixel (s*b + dh): with dh = s*i + ph (0 <= ph < s) that is pixel (b + i)
+    // of the image sub-sampled at phase ph -- a stride-1 tap on the parity class (ph, pw).  Classes must be contiguous
+    // in the tap list (the packed K order follows the tap list); one halo patch per (channel block, class).
+    const int sdiv = d.in_stride;
+    auto fdiv = [sdiv](int v) { return v >= 0 ? v / sdiv : -((-v + sdiv - 1) / sdiv); };
     int dh_min = 127, dh_max = -127, dw_min = 127, dw_max = -127;
     for (int t = 0; t < d.ntaps; ++t) {
-      dh_min = d.dh[t] < dh_min ? d.dh[t] : dh_min; dh_max = d.dh[t] > dh_max ? d.dh[t] : dh_max;
-      dw_min = d.dw[t] < dw_min ? d.dw[t] : dw_min; dw_max = d.dw[t] > dw_max ? d.dw[t] : dw_max;
+      const int i = fdiv(d.dh[t]), j = fdiv(d.dw[t]);
+      dh_min = i < dh_min ? i : dh_min; dh_max = i > dh_max ? i : dh_max;
+      dw_min = j < dw_min ? j : dw_min; dw_max = j > dw_max ? j : dw_max;
     }
     P.dh_min = dh_min; P.dw_min = dw_min;
     P.ph = kPatchTH + dh_max - dh_min;
     P.pw = kPatchTW + dw_max - dw_min;
     P.ncb = ncb;
+    P.in_mul = sdiv;
     for (int i = 0; i < ncb; ++i) { P.cb_c0[i] = cb_c0[i]; P.cb_ksteps[i] = cb_ksteps[i]; }
-    for (int t = 0; t < d.ntaps; ++t) P.tapoff[t] = (uint32_t)((d.dh[t] - dh_min) * P.pw + (d.dw[t] - dw_min)) * 128u;
+    int ncls = 0, last_id = -1;
+    for (int t = 0; t < d.ntaps; ++t) {
+      const int i = fdiv(d.dh[t]), j = fdiv(d.dw[t]);
+      const int phs = d.dh[t] - sdiv * i, pws = d.dw[t] - sdiv * j;
+      const int id = phs * sdiv + pws;
+      if (id != last_id) {
+        if (id < last_id || ncls >= 4) { set_error("conv2d: strided patch taps must be grouped by parity class in ascending order"); return CRDR_ERR_BAD_SHAPE; }
+        P.cls_h0[ncls] = sdiv * dh_min + phs;
+        P.cls_w0[ncls] = sdiv * dw_min + pws;
+        ++ncls;
+        last_id = id;
+      }
+      P.cls_end[ncls - 1] = t + 1;
+      P.tapoff[t] = (uint32_t)((i - dh_min) * P.pw + (j - dw_min)) * 128u;
+    }
+    P.ncls = ncls;
     P.tiles_h = (d.hb + kPatchTH - 1) / kPatchTH;
     P.tiles_w = (d.wb + kPatchTW - 1) / kPatchTW;
     if (P.ph > 64 || P.pw > 64 || d.in.cs < 64) {
@@ -2110,7 +2151,7 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
       const uint32_t budget = kDynSmemMax - 1024 - res_need - out_need;
       static int pmul_env = -1;
       if (pmul_env < 0) { const char* e = getenv("CRDR_PATCH_TILES"); pmul_env = e ? atoi(e) : 2; }
-      int want = pmul_env * ncb;
+      int want = pmul_env * ncb * P.ncls;
       if (want < 2) want = 2;
       if (want > kMaxPatchStages) want = kMaxPatchStages;
       int ps = want;
@@ -2119,10 +2160,10 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
       P.patch_stages = ps;
     }
     patch_total = (uint32_t)P.patch_stages * pstage;
-    int rc = input_tensor_map(d.in.hi, d.in.cs, d.win, d.hin, d.n, P.pw, P.ph, &P.tm_in_hi);
+    int rc = input_tensor_map(d.in.hi, d.in.cs, d.win, d.hin, d.n, P.pw, P.ph, &P.tm_in_hi, 64, 128, sdiv);
     if (rc) return rc;
     if (three) {
-      rc = input_tensor_map(d.in.lo, d.in.cs, d.win, d.hin, d.n, P.pw, P.ph, &P.tm_in_lo);
+      rc = input_tensor_map(d.in.lo, d.in.cs, d.win, d.hin, d.n, P.pw, P.ph, &P.tm_in_lo, 64, 128, sdiv);
       if (rc) return rc;
     }
   }

@@ -42,8 +42,10 @@ __global__ void __launch_bounds__(256) gauss_kernel(const __grid_constant__ crdr
     // load symbols NCHW (pixel-contiguous) into the tile: s_sym[channel][pixel]
     for (int cc = threadIdx.y; cc < kTile; cc += 8) {
       const int c = tc.c0 + cc, p = tc.p0 + threadIdx.x;
-      if (c < d.c && p < d.hw)
-        s_sym[cc][threadIdx.x] = d.symbols[((int64_t)tc.n * d.c_total + d.nchw_coff + c) * d.hw + p];
+      if (c < d.c && p < d.hw) {
+        const int64_t o = ((int64_t)tc.n * d.c_total + d.nchw_coff + c) * d.hw + p;
+        s_sym[cc][threadIdx.x] = d.symbols ? d.symbols[o] : (int)d.symbols16[o];
+      }
     }
   }
   __syncthreads();
@@ -94,8 +96,15 @@ __global__ void __launch_bounds__(256) gauss_kernel(const __grid_constant__ crdr
     if (c >= d.c || p >= d.hw) continue;
     const int64_t o = ((int64_t)tc.n * d.c_total + d.nchw_coff + c) * d.hw + p;
     if (d.indexes) d.indexes[o] = s_idx[cc][threadIdx.x];
+    if (d.indexes8) d.indexes8[o] = (uint8_t)s_idx[cc][threadIdx.x];   // ntable <= 64
     if (MODE == 0) {
-      if (d.symbols) d.symbols[o] = s_sym[cc][threadIdx.x];
+      const int sym = s_sym[cc][threadIdx.x];
+      if (d.symbols) d.symbols[o] = sym;
+      if (d.symbols16) {
+        const int sat = max(-32768, min(32767, sym));
+        if (sat != sym) atomicOr(status, kFlagSymRange);
+        d.symbols16[o] = (int16_t)sat;
+      }
       if (d.likelihood) d.likelihood[o] = s_lik[cc][threadIdx.x];
     }
   }
@@ -283,6 +292,42 @@ __global__ void __launch_bounds__(256) image_to_patches_kernel(const float* __re
   if (out.lo) *(uint4*)((__half*)out.lo + o) = *(const uint4*)ll;
 }
 
+// uint8 variant of image_to_patches_kernel: ToTensor + Normalize(0.5, 0.5) of the reference data path, in its fp32 order
+__global__ void __launch_bounds__(256) image_u8_to_patches_kernel(const uint8_t* __restrict__ img, int n, int h, int w,
+                                                                  int hp, int wp, crdr_planes out, uint32_t* status) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ho = hp / 2, wo = wp / 2;
+  const int64_t total = (int64_t)n * ho * wo * 16;
+  if (idx >= total) return;
+  const int grp = (int)(idx & 15);
+  const int64_t pix = idx >> 4;
+  const int j = (int)(pix % wo);
+  const int64_t t = pix / wo;
+  const int i = (int)(t % ho);
+  const int b = (int)(t / ho);
+  __align__(16) __half hh[8], ll[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = grp * 8 + e;
+    float v = 0.f;
+    if (k < 75) {
+      const int tap = k / 3, c = k - 3 * tap;
+      const int kh = tap / 5, kw = tap - 5 * kh;
+      const int y = 2 * i + kh - 2, x = 2 * j + kw - 2;
+      if (y >= 0 && y < hp && x >= 0 && x < wp) {
+        const int sy = y < h ? y : 2 * (h - 1) - y;
+        const int sx = x < w ? x : 2 * (w - 1) - x;
+        const float u = (float)img[(((int64_t)b * 3 + c) * h + sy) * w + sx];
+        v = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), 0.5f), 0.5f);   // ToTensor: u / 255; Normalize: (t - 0.5) / 0.5
+      }
+    }
+    split_f16(v, hh[e], ll[e], status);
+  }
+  const int64_t o = pix * out.cs + out.coff + grp * 8;
+  *(uint4*)((__half*)out.hi + o) = *(const uint4*)hh;
+  if (out.lo) *(uint4*)((__half*)out.lo + o) = *(const uint4*)ll;
+}
+
 __global__ void __launch_bounds__(256) planes_to_image_kernel(const float* __restrict__ x, int x_cs, int n, int hp,
                                                               int wp, int h, int w, float* __restrict__ img) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -315,6 +360,24 @@ __global__ void __launch_bounds__(256) phases_to_image_kernel(const float* __res
   img[idx] = fminf(fmaxf(v, -1.f), 1.f);
 }
 
+// uint8 variant: clamp, then the reference's PNG conversion ((x + 1) / 2 * 255 in fp32, truncated by astype(uint8))
+__global__ void __launch_bounds__(256) phases_to_image_u8_kernel(const float* __restrict__ x, int x_cs, int n, int hb,
+                                                                 int wb, int h, int w, uint8_t* __restrict__ img) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)n * 3 * h * w;
+  if (idx >= total) return;
+  const int xx = (int)(idx % w);
+  int64_t t = idx / w;
+  const int yy = (int)(t % h);
+  t /= h;
+  const int c = (int)(t % 3);
+  const int b = (int)(t / 3);
+  float v = x[(((int64_t)b * hb + (yy >> 1)) * wb + (xx >> 1)) * x_cs + ((yy & 1) * 2 + (xx & 1)) * 3 + c];
+  v = fminf(fmaxf(v, -1.f), 1.f);
+  v = __fmul_rn(__fdiv_rn(__fadd_rn(v, 1.0f), 2.0f), 255.0f);
+  img[idx] = (uint8_t)(int)v;   // v in [0, 255]: truncation
+}
+
 // one block per image; fixed summation order -> run-to-run and batch-size invariant
 __global__ void __launch_bounds__(1024) bits_kernel(const float* __restrict__ lik, int64_t per, float* __restrict__ bits) {
   __shared__ double s[1024];
@@ -336,6 +399,16 @@ __global__ void __launch_bounds__(256) max_abs_kernel(const float* __restrict__ 
     m = fmaxf(m, fabsf(x[i]));
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMax((unsigned int*)out, __float_as_uint(m));  // m >= 0: uint order == float order
+}
+
+// gridDim.y = image; per-image maximum through an atomicMax on the (non-negative) float bit pattern
+__global__ void __launch_bounds__(256) max_abs_batch_kernel(const float* __restrict__ x, int64_t per, float* out) {
+  const float* p = x + (int64_t)blockIdx.y * per;
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(p[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax((unsigned int*)out + blockIdx.y, __float_as_uint(m));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -423,6 +496,48 @@ int phases_to_image_launch(const float* x, int x_cs, int n, int hb, int wb, int 
   const int64_t total = (int64_t)n * 3 * h * w;
   phases_to_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, x_cs, n, hb, wb, h, w, img);
   return check_launch("phases_to_image_kernel");
+}
+
+int image_u8_to_patches_launch(const uint8_t* img, int n, int h, int w, int hp, int wp, crdr_planes out, cudaStream_t st) {
+  if (n <= 0 || h <= 0 || w <= 0 || hp < h || wp < w || hp - h >= h || wp - w >= w || (hp & 1) || (wp & 1) ||
+      out.cs % 8 || out.coff % 8 || out.cs < out.coff + 128 || !out.hi || !img) {
+    set_error("image_u8_to_patches: bad shape (h=%d w=%d hp=%d wp=%d cs=%d)", h, w, hp, wp, out.cs);
+    return CRDR_ERR_BAD_SHAPE;
+  }
+  uint32_t* status = device_status_word();
+  if (!status) return CRDR_ERR_CUDA;
+  const int64_t total = (int64_t)n * (hp / 2) * (wp / 2) * 16;
+  image_u8_to_patches_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(img, n, h, w, hp, wp, out, status);
+  return check_launch("image_u8_to_patches_kernel");
+}
+
+int phases_to_image_u8_launch(const float* x, int x_cs, int n, int hb, int wb, int h, int w, uint8_t* img, cudaStream_t st) {
+  if (n <= 0 || h <= 0 || w <= 0 || 2 * hb < h || 2 * wb < w || x_cs < 12 || !img) {
+    set_error("phases_to_image_u8: bad shape");
+    return CRDR_ERR_BAD_SHAPE;
+  }
+  const int64_t total = (int64_t)n * 3 * h * w;
+  phases_to_image_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, x_cs, n, hb, wb, h, w, img);
+  return check_launch("phases_to_image_u8_kernel");
+}
+
+int max_abs_batch_launch(const float* x, int n, int64_t per, float* out, cudaStream_t st) {
+  if (n <= 0 || per <= 0) { set_error("max_abs_batch: bad shape"); return CRDR_ERR_BAD_SHAPE; }
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n, st);
+  if (e != cudaSuccess) { set_error("max_abs_batch: memset failed: %s", cudaGetErrorString(e)); return CRDR_ERR_CUDA; }
+  int bx = (int)((per + 255) / 256);
+  const int cap = (148 * 8 + n - 1) / n;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  max_abs_batch_kernel<<<dim3((unsigned)bx, (unsigned)n), 256, 0, st>>>(x, per, out);
+  return check_launch("max_abs_batch_kernel");
+}
+
+__global__ void status_clear_bits_kernel(uint32_t* status, uint32_t bits) { atomicAnd(status, ~bits); }
+
+int status_clear_bits_launch(uint32_t* status, uint32_t bits, cudaStream_t st) {
+  status_clear_bits_kernel<<<1, 1, 0, st>>>(status, bits);
+  return check_launch("status_clear_bits_kernel");
 }
 
 int bits_launch(const float* lik, int n, int64_t per, float* bits, cudaStream_t st) {

@@ -7,12 +7,20 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <functional>
+#include <mutex>
 #include <cmath>
 #include <cstring>
 #include <limits>
 #include <memory>
 #include <thread>
 #include <vector>
+#ifdef __linux__
+#include <pthread.h>
+#include <sched.h>
+#endif
 
 namespace {
 
@@ -33,9 +41,14 @@ struct EncSym {
   uint32_t rcp_shift;
   uint32_t freq;
 };
+constexpr int kBucketBits = 10;                       // decoder: 1024 buckets of 64 cumulative values per table row
+constexpr int kBuckets = 1 << kBucketBits;
+constexpr int kBucketShift = 16 - kBucketBits;
 struct TableAccel {
   std::vector<EncSym> enc;        // [n_cdf][cdf_stride] (entries past a row's size are unused)
-  std::vector<uint16_t> bucket;   // [n_cdf][256]
+  std::vector<uint16_t> bucket;   // [n_cdf][kBuckets]: first slot whose interval reaches into the bucket
+  std::vector<int32_t> cdf_pad;   // [n_cdf][pad_stride]: the rows followed by 8 sentinels (> any cumulative value), so the
+  int32_t pad_stride = 0;         //   decoder's 8-wide compare may read past a row's end
 };
 // Built by crdr_rans_tables_prepare() and owned by the caller's handle (crdr_cdf_tables::prepared).  There is no
 // cache keyed on table addresses: a rebuilt or reloaded table that lands on a recycled address must never pick up
@@ -43,7 +56,9 @@ struct TableAccel {
 std::shared_ptr<const TableAccel> build_accel(const crdr_cdf_tables* t) {
   auto a = std::make_shared<TableAccel>();
   a->enc.assign((size_t)t->n_cdf * (size_t)t->cdf_stride, EncSym{0, 0, 0, 0, 0});
-  a->bucket.assign((size_t)t->n_cdf * 256, 0);
+  a->bucket.assign((size_t)t->n_cdf * kBuckets, 0);
+  a->pad_stride = t->cdf_stride + 8;
+  a->cdf_pad.assign((size_t)t->n_cdf * (size_t)a->pad_stride, 0x7fffffff);
   for (int32_t r = 0; r < t->n_cdf; ++r) {
     const int32_t* cdf = t->cdfs + (int64_t)r * t->cdf_stride;
     const int32_t size = std::min(t->cdf_sizes[r], t->cdf_stride);
@@ -62,13 +77,16 @@ std::shared_ptr<const TableAccel> build_accel(const crdr_cdf_tables* t) {
         e.bias = start;
       }
     }
-    uint16_t* bk = a->bucket.data() + (size_t)r * 256;
+    uint16_t* bk = a->bucket.data() + (size_t)r * kBuckets;
     int32_t sidx = 0;
-    for (int32_t b = 0; b < 256; ++b) {
-      const int32_t cum = b << 8;
+    for (int32_t b = 0; b < kBuckets; ++b) {
+      const int32_t cum = b << kBucketShift;
       while (sidx + 2 < size && cdf[sidx + 1] <= cum) ++sidx;
       bk[b] = (uint16_t)sidx;
     }
+    // padded copy: entries [0, size-1] are the row (the last one is 2^16 > any cumulative value), sentinels behind it
+    int32_t* cp = a->cdf_pad.data() + (size_t)r * (size_t)a->pad_stride;
+    for (int32_t v = 0; v < size; ++v) cp[v] = cdf[v];
   }
   return a;
 }
@@ -119,23 +137,28 @@ struct Encoder {
   }
 };
 
-int64_t encode_one(const int32_t* symbols, const int32_t* indexes, int64_t n, const TableRef& tr, uint8_t* out,
+template <class SymT, class IdxT>
+int64_t encode_one(const SymT* symbols, const IdxT* indexes, int64_t n, const TableRef& tr, uint8_t* out,
                    int64_t out_cap) {
   Encoder enc;
   const crdr_cdf_tables* t = tr.t;
   const EncSym* esym = tr.accel->enc.data();
-  // a table symbol emits at most one word; an escape adds at most 2 + 8 + 1 nibbles (raw < 2^32) = two more words
-  std::unique_ptr<uint32_t[]> words(new uint32_t[(size_t)(3 * n + 8)]);  // uninitialised on purpose
-  enc.wp = words.get();
+  // a table symbol emits at most one word; an escape adds at most 2 + 8 + 1 nibbles (raw < 2^32) = two more words.
+  // Per-thread grow-only scratch: a fresh multi-megabyte allocation per stream is an mmap / munmap pair, and a dozen
+  // coder threads doing that at once serialise on the process's address-space lock.
+  static thread_local std::vector<uint32_t> scratch;
+  if (scratch.size() < (size_t)(3 * n + 8)) scratch.resize((size_t)(3 * n + 8));
+  uint32_t* const words = scratch.data();
+  enc.wp = words;
   const int32_t n_cdf = t->n_cdf;
   const int32_t* offsets = t->offsets;
   const int32_t* sizes = t->cdf_sizes;
   const int64_t stride = t->cdf_stride;
   for (int64_t i = n - 1; i >= 0; --i) {
-    const int32_t ci = indexes[i];
+    const int32_t ci = (int32_t)indexes[i];
     if ((uint32_t)ci >= (uint32_t)n_cdf) return std::numeric_limits<int64_t>::min();
     const int32_t max_value = sizes[ci] - 2;
-    int32_t value = symbols[i] - offsets[ci];
+    int32_t value = (int32_t)symbols[i] - offsets[ci];
     if (value < 0 || value >= max_value) {
       const uint32_t raw = value < 0 ? (uint32_t)(-2 * (int64_t)value - 1) : (uint32_t)(2 * ((int64_t)value - max_value));
       value = max_value;
@@ -149,7 +172,7 @@ int64_t encode_one(const int32_t* symbols, const int32_t* indexes, int64_t n, co
     }
     enc.put(esym[(int64_t)ci * stride + value]);
   }
-  const int64_t nwords = (int64_t)(enc.wp - words.get());
+  const int64_t nwords = (int64_t)(enc.wp - words);
   const int64_t nbytes = 4 * (nwords + 2);
   if (nbytes > out_cap) return -nbytes;
   uint32_t w0 = (uint32_t)enc.x, w1 = (uint32_t)(enc.x >> 32);
@@ -174,24 +197,65 @@ struct Decoder {
   }
 };
 
-int decode_some(Decoder* d, const int32_t* indexes, int64_t n, const TableRef& tr, int32_t* out) {
+// Slot search: the bucket index gives the first candidate slot s0; the answer is s0 + #{j >= 1 : cdf[s0 + j] <= cum}.
+// With 64 cumulative values per bucket a Gaussian / logistic row has a handful of slots per bucket, so one 8-wide
+// compare (AVX2) or a short scalar walk resolves it; both continue in steps while a whole group compared <= cum.
+#if defined(__x86_64__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) static inline int32_t find_slot_avx2(const int32_t* row, int32_t s, int32_t cum) {
+  const __m256i c = _mm256_set1_epi32(cum);
+  for (;;) {
+    const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(row + s + 1));
+    const int gt = _mm256_movemask_ps(_mm256_castsi256_ps(_mm256_cmpgt_epi32(v, c)));   // bit j: row[s+1+j] > cum
+    if (gt) return s + __builtin_ctz((unsigned)gt);
+    s += 8;
+  }
+}
+#endif
+static inline int32_t find_slot_scalar(const int32_t* row, int32_t s, int32_t cum) {
+  while (row[s + 1] <= cum) ++s;
+  return s;
+}
+
+// returns 0 ok, 1 index out of range
+template <bool AVX2, class IdxT, class OutT>
+#if defined(__x86_64__)
+__attribute__((target("avx2")))
+#endif
+int decode_loop(Decoder* d, const IdxT* indexes, int64_t n, const TableRef& tr, OutT* out) {
   const crdr_cdf_tables* t = tr.t;
   const uint16_t* bucket = tr.accel->bucket.data();
+  const int32_t* cdf_pad = tr.accel->cdf_pad.data();
+  const int64_t pstride = tr.accel->pad_stride;
+  const int32_t n_cdf = t->n_cdf;
+  const int32_t* sizes = t->cdf_sizes;
+  const int32_t* offsets = t->offsets;
+  uint64_t x = d->x;
+  size_t pos = d->pos;
+  const uint32_t* buf = d->buf.data();
+  const size_t nwords = d->buf.size();
   for (int64_t i = 0; i < n; ++i) {
-    const int32_t ci = indexes[i];
-    if (ci < 0 || ci >= t->n_cdf) return 1;
-    const int32_t* cdf = t->cdfs + (int64_t)ci * t->cdf_stride;
-    const int32_t size = t->cdf_sizes[ci];
-    const int32_t max_value = size - 2;
-    const int32_t cum = (int32_t)(d->x & ((1u << kPrecision) - 1));
-    // slot s with cdf[s] <= cum < cdf[s+1] (the tables are increasing): start at the bucket's first slot
-    int32_t s = bucket[(int64_t)ci * 256 + (cum >> 8)];
-    while (s + 2 < size && cdf[s + 1] <= cum) ++s;
-    const uint32_t start = (uint32_t)cdf[s], freq = (uint32_t)(cdf[s + 1] - cdf[s]);
-    d->x = (uint64_t)freq * (d->x >> kPrecision) + (d->x & ((1ull << kPrecision) - 1)) - start;
-    if (d->x < kRansL) d->x = (d->x << 32) | d->next_word();
+    const int32_t ci = (int32_t)indexes[i];
+    if ((uint32_t)ci >= (uint32_t)n_cdf) { d->x = x; d->pos = pos; return 1; }
+    const int32_t* row = cdf_pad + (int64_t)ci * pstride;
+    const int32_t max_value = sizes[ci] - 2;
+    const int32_t cum = (int32_t)(x & ((1u << kPrecision) - 1));
+    int32_t s = bucket[(int64_t)ci * kBuckets + (cum >> kBucketShift)];
+#if defined(__x86_64__)
+    s = AVX2 ? find_slot_avx2(row, s, cum) : find_slot_scalar(row, s, cum);
+#else
+    s = find_slot_scalar(row, s, cum);
+#endif
+    const uint32_t start = (uint32_t)row[s], freq = (uint32_t)(row[s + 1] - row[s]);
+    x = (uint64_t)freq * (x >> kPrecision) + (uint64_t)cum - start;
+    // branch-free renormalisation (the refill is due every few symbols, unpredictably)
+    const bool need = x < kRansL;
+    const uint32_t w = pos < nwords ? buf[pos] : 0u;
+    x = need ? ((x << 32) | w) : x;
+    pos += need;
     int32_t value = s;
-    if (value == max_value) {
+    if (__builtin_expect(value == max_value, 0)) {
+      d->x = x; d->pos = pos;
       int32_t val = (int32_t)d->get_bits();
       int32_t nb = val;
       while (val == kBypassMax) { val = (int32_t)d->get_bits(); nb += val; }
@@ -199,23 +263,169 @@ int decode_some(Decoder* d, const int32_t* indexes, int64_t n, const TableRef& t
       for (int32_t j = 0; j < nb; ++j) raw |= (int32_t)d->get_bits() << (j * kBypassBits);
       value = raw >> 1;
       value = (raw & 1) ? -value - 1 : value + max_value;
+      x = d->x; pos = d->pos;
     }
-    out[i] = value + t->offsets[ci];
+    out[i] = (OutT)(value + offsets[ci]);
   }
+  d->x = x;
+  d->pos = pos;
   return 0;
 }
 
+template <class IdxT, class OutT>
+int decode_some(Decoder* d, const IdxT* indexes, int64_t n, const TableRef& tr, OutT* out) {
+#if defined(__x86_64__)
+  static const bool have_avx2 = __builtin_cpu_supports("avx2");
+  if (have_avx2) return decode_loop<true>(d, indexes, n, tr, out);
+#endif
+  return decode_loop<false>(d, indexes, n, tr, out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Coder threads.  One persistent pool per process, sized and pinned for a one-process-per-GPU job: the CPUs this process
+// may run on are cut into LOCAL_WORLD_SIZE equal slices and the pool lives on the slice of LOCAL_RANK, one worker per
+// CPU (at most kMaxWorkers) -- eight ranks no longer put 8 x 12 freshly spawned threads on 32 cores.  The calling thread
+// works too.  Workers spin for a few microseconds after a job (the codec issues coder calls back to back: z then y,
+// chunk after chunk) and then block on a condition variable; pinned to distinct CPUs, their wake-ups do not pile up on
+// the waker's core.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMaxWorkers = 32;
+
+class Pool {
+ public:
+  static Pool& get() {
+    static Pool p;
+    return p;
+  }
+  int size() const { return (int)workers_.size() + 1; }
+  int first_cpu() const { return first_cpu_; }
+
+  template <class F>
+  void run(int32_t count, int32_t threads, F&& fn) {
+    if (count <= 0) return;
+    int nt = threads > 0 ? std::min(threads, size()) : size();
+    nt = std::max(1, std::min<int>(nt, count));
+    if (nt == 1) { for (int32_t i = 0; i < count; ++i) fn(i); return; }
+    std::lock_guard<std::mutex> serial(run_mutex_);   // one job at a time
+    std::function<void(int32_t)> job = [&](int32_t i) { fn(i); };
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      job_ = &job;
+      count_ = count;
+      helpers_ = nt - 1;
+      next_.store(0, std::memory_order_relaxed);
+      pending_.store(nt - 1, std::memory_order_relaxed);
+      generation_.fetch_add(1, std::memory_order_release);
+    }
+    cv_work_.notify_all();
+    for (int32_t i; (i = next_.fetch_add(1, std::memory_order_relaxed)) < count;) fn(i);
+    // wait for the helpers that picked this generation up
+    for (int spin = 0; pending_.load(std::memory_order_acquire) != 0; ++spin) {
+      if (spin > 2000) {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_done_.wait(lk, [&] { return pending_.load(std::memory_order_acquire) == 0; });
+        break;
+      }
+    }
+    std::lock_guard<std::mutex> lk(m_);
+    job_ = nullptr;
+  }
+
+ private:
+  Pool() {
+    std::vector<int> cpus;
+#ifdef __linux__
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0)
+      for (int c = 0; c < CPU_SETSIZE; ++c)
+        if (CPU_ISSET(c, &set)) cpus.push_back(c);
+#endif
+    if (cpus.empty()) {
+      const int hc = std::max(1u, std::thread::hardware_concurrency());
+      for (int c = 0; c < hc; ++c) cpus.push_back(c);
+    }
+    auto env_int = [](const char* name, int dflt) { const char* e = std::getenv(name); return e && *e ? std::atoi(e) : dflt; };
+    int lw = env_int("LOCAL_WORLD_SIZE", env_int("WORLD_SIZE", 1));
+    int lr = env_int("LOCAL_RANK", env_int("RANK", 0));
+    if (lw < 1) lw = 1;
+    lr = ((lr % lw) + lw) % lw;
+    int per = std::max<int>(1, (int)cpus.size() / lw);
+    int want = env_int("CRDR_CODER_THREADS", per);
+    want = std::max(1, std::min({want, kMaxWorkers, std::max(per, 1)}));
+    const int base = std::min<int>(lr * per, (int)cpus.size() - 1);
+    first_cpu_ = cpus[base];
+    const bool pin = env_int("CRDR_CODER_PIN", 1) != 0 && (int)cpus.size() >= 2;
+    for (int w = 1; w < want; ++w) {   // slot 0 of the slice is left to the calling thread
+      const int cpu = cpus[std::min<int>(base + w, (int)cpus.size() - 1)];
+      workers_.emplace_back([this, cpu, pin] { worker(cpu, pin); });
+    }
+  }
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+      generation_.fetch_add(1, std::memory_order_release);
+    }
+    cv_work_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+
+  void worker(int cpu, bool pin) {
+#ifdef __linux__
+    if (pin) {
+      cpu_set_t set;
+      CPU_ZERO(&set);
+      CPU_SET(cpu, &set);
+      pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+    }
+#endif
+    uint64_t seen = 0;
+    for (;;) {
+      // short spin (back-to-back coder calls), then sleep
+      bool fresh = false;
+      for (int spin = 0; spin < 4000; ++spin) {
+        if (generation_.load(std::memory_order_acquire) != seen) { fresh = true; break; }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      }
+      std::function<void(int32_t)>* job = nullptr;
+      int32_t count = 0;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        if (!fresh) cv_work_.wait(lk, [&] { return generation_.load(std::memory_order_acquire) != seen; });
+        seen = generation_.load(std::memory_order_acquire);
+        if (stop_) return;
+        if (helpers_ <= 0 || job_ == nullptr) continue;   // this job has all the helpers it asked for
+        --helpers_;
+        job = job_;
+        count = count_;
+      }
+      for (int32_t i; (i = next_.fetch_add(1, std::memory_order_relaxed)) < count;) (*job)(i);
+      if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+        std::lock_guard<std::mutex> lk(m_);
+        cv_done_.notify_all();
+      }
+    }
+  }
+
+  std::vector<std::thread> workers_;
+  std::mutex m_, run_mutex_;
+  std::condition_variable cv_work_, cv_done_;
+  std::atomic<uint64_t> generation_{0};
+  std::atomic<int32_t> next_{0};
+  std::atomic<int32_t> pending_{0};
+  std::function<void(int32_t)>* job_ = nullptr;
+  int32_t count_ = 0;
+  int helpers_ = 0;
+  bool stop_ = false;
+  int first_cpu_ = 0;
+};
+
 template <class F>
 void parallel_for(int32_t count, int32_t threads, F&& fn) {
-  int32_t nt = threads > 0 ? threads : (int32_t)std::thread::hardware_concurrency();
-  nt = std::max(1, std::min(nt, count));
-  if (nt == 1) { for (int32_t i = 0; i < count; ++i) fn(i); return; }
-  std::atomic<int32_t> next{0};
-  std::vector<std::thread> pool;
-  pool.reserve(nt);
-  for (int32_t w = 0; w < nt; ++w)
-    pool.emplace_back([&] { for (int32_t i; (i = next.fetch_add(1)) < count;) fn(i); });
-  for (auto& th : pool) th.join();
+  Pool::get().run(count, threads, std::forward<F>(fn));
 }
 
 }  // namespace
@@ -280,6 +490,23 @@ int crdr_rans_encode_batch(int32_t count, const int32_t* const* symbols, const i
   return 0;
 }
 
+int crdr_rans_encode_batch_i16u8(int32_t count, const int16_t* const* symbols, const uint8_t* const* indexes,
+                                 const int64_t* n, const crdr_cdf_tables* t, uint8_t* const* out, const int64_t* out_cap,
+                                 int64_t* lengths, int32_t threads) {
+  const TableRef tr(t);
+  parallel_for(count, threads, [&](int32_t i) { lengths[i] = encode_one(symbols[i], indexes[i], n[i], tr, out[i], out_cap[i]); });
+  for (int32_t i = 0; i < count; ++i)
+    if (lengths[i] < 0) return 1;
+  return 0;
+}
+
+int crdr_rans_pool_info(int32_t* threads, int32_t* first_cpu) {
+  Pool& p = Pool::get();
+  if (threads) *threads = p.size();
+  if (first_cpu) *first_cpu = p.first_cpu();
+  return 0;
+}
+
 void* crdr_rans_decoder_new(void) { return new Decoder(); }
 void crdr_rans_decoder_free(void* dec) { delete static_cast<Decoder*>(dec); }
 
@@ -301,6 +528,16 @@ int crdr_rans_decoder_decode_stream(void* dec, const int32_t* indexes, int64_t n
 
 int crdr_rans_decode_batch(int32_t count, void* const* decoders, const int32_t* const* indexes, const int64_t* n,
                            const crdr_cdf_tables* t, int32_t* const* out, int32_t threads) {
+  std::atomic<int> bad{0};
+  const TableRef tr(t);
+  parallel_for(count, threads, [&](int32_t i) {
+    if (decode_some(static_cast<Decoder*>(decoders[i]), indexes[i], n[i], tr, out[i])) bad.store(1);
+  });
+  return bad.load();
+}
+
+int crdr_rans_decode_batch_u8(int32_t count, void* const* decoders, const uint8_t* const* indexes, const int64_t* n,
+                              const crdr_cdf_tables* t, int32_t* const* out, int32_t threads) {
   std::atomic<int> bad{0};
   const TableRef tr(t);
   parallel_for(count, threads, [&](int32_t i) {

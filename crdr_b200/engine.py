@@ -80,12 +80,23 @@ def split_weight(w2d, device):
 class Phase:
     """One GEMM of a (possibly transposed) convolution: taps, packed weights and output phase."""
 
-    __slots__ = ("dh", "dw", "w_hi", "w_lo", "k_pad", "out_ph", "out_pw")
+    __slots__ = ("dh", "dw", "w_hi", "w_lo", "k_pad", "out_ph", "out_pw", "tmpl")
+
+
+_TILE_N_CACHE = {}
 
 
 def pick_tile_n(cout_pad, m_tiles, three):
     """Largest N tile (multiple of 16, divides cout_pad, <= 256 / 128) that still yields >= 148 CTAs; tiles below
     64 columns (shared-memory-bound MMAs) are used only when the layer itself is that narrow."""
+    key = (cout_pad, min(m_tiles, 4096), three)
+    hit = _TILE_N_CACHE.get(key)
+    if hit is None:
+        hit = _TILE_N_CACHE[key] = _pick_tile_n(cout_pad, m_tiles, three)
+    return hit
+
+
+def _pick_tile_n(cout_pad, m_tiles, three):
     cap = 128 if three else 256  # F16X3 keeps two D0 buffers, D1 and the fp32 total in 512 TMEM columns
     cands = [t for t in range(16, min(cout_pad, cap) + 1, 16) if cout_pad % t == 0]
     good = [t for t in cands if t >= min(64, cands[-1])]
@@ -121,10 +132,12 @@ class ConvOp:
         self.seg_lens = list(seg_lens) if seg_lens else [self.cin]
         assert sum(self.seg_lens) == self.cin
         # "patch": halo-patch engine (input stride 1, >= 64 channels); "gather": per-tap im2col gather (any stride)
+        # A stride-2 convolution runs on the patch engine as four parity classes of stride-1 taps (each class reads the
+        # input sub-sampled by a strided TMA box), so only tiny-Cin layers still need the gather engine.
         in_stride = 1 if transposed else stride
-        default = "patch" if (in_stride == 1 and min(self.seg_lens) >= 8 and self.cin >= 64) else "gather"
+        default = "patch" if (in_stride in (1, 2) and min(self.seg_lens) >= 8 and self.cin >= 64) else "gather"
         self.algo = algo or os.environ.get("CRDR_CONV_ALGO") or default
-        if in_stride != 1 or self.cin < 64:
+        if in_stride not in (1, 2) or self.cin < 64 or (in_stride == 2 and os.environ.get("CRDR_CONV_S2_PATCH", "1") == "0"):
             self.algo = "gather"
         self.phases = []
         s, p = stride, padding
@@ -145,6 +158,10 @@ class ConvOp:
                         blk = torch.nn.functional.pad(blk, (0, self.cin - cin))
                     cols.append(blk)
             assert 0 < len(taps) <= nv.MAX_TAPS
+            if self.algo == "patch" and in_stride > 1:
+                # group the taps by parity class (dh mod s, dw mod s), ascending: the K order the strided patch engine walks
+                order = sorted(range(len(taps)), key=lambda t: ((taps[t][0] % in_stride) * in_stride + taps[t][1] % in_stride, t))
+                taps, cols = [taps[t] for t in order], [cols[t] for t in order]
             phs = Phase()
             phs.dh = [t[0] for t in taps]
             phs.dw = [t[1] for t in taps]
@@ -152,6 +169,22 @@ class ConvOp:
             w2d = self._pack(cols)
             phs.k_pad = w2d.shape[1]
             phs.w_hi, phs.w_lo = split_weight(w2d, device)
+            # launch-descriptor template: everything that does not depend on the call (taps, packed weights, bias).
+            # A launch copies it and fills in the tensors (the per-field ctypes stores were most of the enqueue cost).
+            t = nv.ConvDesc()
+            t.ntaps = len(taps)
+            for i, (a, b) in enumerate(taps):
+                t.dh[i], t.dw[i] = a, b
+            t.w_hi, t.w_lo, t.k_pad = phs.w_hi.data_ptr(), phs.w_lo.data_ptr(), phs.k_pad
+            t.cout_pad, t.cout = self.cout_pad, self.cout
+            t.out_ph, t.out_pw = ph, pw
+            t.bias = self.bias.data_ptr() if self.bias is not None else None
+            t.k_order = 1 if self.algo == "patch" else 0
+            if transposed:
+                t.in_stride, t.out_stride = 1, stride
+            else:
+                t.in_stride, t.out_stride = stride, 1
+            phs.tmpl = t
             self.phases.append(phs)
 
     def _pack(self, cols):
@@ -195,51 +228,47 @@ class ConvOp:
             two_out = precision == nv.PREC_F16X3
         if out is None and want_planes:
             out = Act.empty(x.n, hout, wout, self.cout, two=two_out, device=x.hi.device)
-        d = nv.ConvDesc()
-        d.inp = x.planes(0)
-        d.n, d.hin, d.win = x.n, x.h, x.w
-        d.seg0_off, d.seg0_len = segs[0]
-        d.seg1_off, d.seg1_len = segs[1] if len(segs) > 1 else (0, 0)
-        d.cout_pad, d.cout = self.cout_pad, self.cout
-        d.hout, d.wout = hout, wout
-        d.out = out.planes(out_coff) if out is not None else NULL_PLANES
-        if out_f32 is not None:
-            d.out_f32, d.out_f32_cs, d.out_f32_coff = out_f32.data_ptr(), out_f32.shape[-1], out_f32_coff
-        d.bias = self.bias.data_ptr() if self.bias is not None else None
-        d.relu = int(relu)
-        d.add_vec = add_vec.data_ptr() if add_vec is not None else None
-        d.mode = mode
-        if res is not None:
-            if isinstance(res, Act):
-                d.res = res.planes(res_coff)
-            else:
-                d.res_f32, d.res_f32_cs, d.res_f32_coff = res.data_ptr(), res.shape[-1], res_coff
-        if trunk is not None:
-            d.trunk = trunk.planes(0)
-        d.scale = scale.data_ptr() if scale is not None else None
-        d.shift = shift.data_ptr() if shift is not None else None
-        d.precision, d.engine = precision, engine
-        d.k_order = 1 if self.algo == "patch" else 0
-        if self.algo == "patch" and engine == nv.ENGINE_TCGEN05_NOTMA:
-            d.engine = nv.ENGINE_TCGEN05  # the patch engine has no cp.async variant
+        engine_ = nv.ENGINE_TCGEN05 if (self.algo == "patch" and engine == nv.ENGINE_TCGEN05_NOTMA) else engine  # no cp.async patch variant
         st = nv.stream_handle()
         L = nv.lib()
+        three = precision == nv.PREC_F16X3
+        seg1 = segs[1] if len(segs) > 1 else (0, 0)
         for phs in self.phases:
+            d = nv.ConvDesc.from_buffer_copy(phs.tmpl)
+            d.inp = x.planes(0)
+            d.n, d.hin, d.win = x.n, x.h, x.w
+            d.seg0_off, d.seg0_len = segs[0]
+            d.seg1_off, d.seg1_len = seg1
+            d.hout, d.wout = hout, wout
+            if out is not None:
+                d.out = out.planes(out_coff)
+            if out_f32 is not None:
+                d.out_f32, d.out_f32_cs, d.out_f32_coff = out_f32.data_ptr(), out_f32.shape[-1], out_f32_coff
+            if relu:
+                d.relu = 1
+            if add_vec is not None:
+                d.add_vec = add_vec.data_ptr()
+            if mode:
+                d.mode = mode
+                if isinstance(res, Act):
+                    d.res = res.planes(res_coff)
+                elif res is not None:
+                    d.res_f32, d.res_f32_cs, d.res_f32_coff = res.data_ptr(), res.shape[-1], res_coff
+                if trunk is not None:
+                    d.trunk = trunk.planes(0)
+            if scale is not None:
+                d.scale = scale.data_ptr()
+            if shift is not None:
+                d.shift = shift.data_ptr()
+            d.precision, d.engine = precision, engine_
             if self.transposed:
                 hb = -(-(hout - phs.out_ph) // self.stride)
                 wb = -(-(wout - phs.out_pw) // self.stride)
-                d.in_stride, d.out_stride = 1, self.stride
             else:
                 hb, wb = hout, wout
-                d.in_stride, d.out_stride = self.stride, 1
             d.hb, d.wb = hb, wb
-            d.out_ph, d.out_pw = phs.out_ph, phs.out_pw
-            d.ntaps = len(phs.dh)
-            for i, (a, b) in enumerate(zip(phs.dh, phs.dw)):
-                d.dh[i], d.dw[i] = a, b
-            d.w_hi, d.w_lo, d.k_pad = phs.w_hi.data_ptr(), phs.w_lo.data_ptr(), phs.k_pad
             m_tiles = x.n * (-(-hb // 16)) * (-(-wb // 8)) if self.algo == "patch" else -(-(x.n * hb * wb) // 128)
-            d.tile_n = tile_n or pick_tile_n(self.cout_pad, m_tiles, precision == nv.PREC_F16X3)
+            d.tile_n = tile_n or pick_tile_n(self.cout_pad, m_tiles, three)
             if PROFILE_ON[0]:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()

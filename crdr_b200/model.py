@@ -75,14 +75,19 @@ class CodecEngine:
         s = self.stride
         return -(-h // s) * s, -(-w // s) * s
 
-    def analysis(self, images, q):
-        """images: fp32 NCHW in [-1,1] on the device.  Returns a dict of device tensors (SURVEY 3.1 encode)."""
+    def analysis(self, images, q, compact=False):
+        """images: NCHW on the device, fp32 in [-1,1] or uint8 RGB (normalised on the fly like the reference's
+        ToTensor + Normalize).  Returns a dict of device tensors (SURVEY 3.1 encode); ``compact`` adds the int16 symbol /
+        uint8 index copies for the host coder."""
         L, st = nv.lib(), nv.stream_handle()
         n, _, h, w = images.shape
         hp, wp = self.padded(h, w)
         dev = images.device
         img = Act.empty(n, hp // 2, wp // 2, 128, two=True, device=dev)   # im2col of g_a conv1 fused with the reflect pad
-        nv.check(L.crdr_image_to_patches(images.data_ptr(), n, h, w, hp, wp, img.planes(0), st))
+        if images.dtype == torch.uint8:
+            nv.check(L.crdr_image_u8_to_patches(images.data_ptr(), n, h, w, hp, wp, img.planes(0), st))
+        else:
+            nv.check(L.crdr_image_to_patches(images.data_ptr(), n, h, w, hp, wp, img.planes(0), st))
         y_act, y32 = self.ga.run(img, q)
         z32 = self.ha.run(y_act)
         hz, wz = z32.shape[1:3]
@@ -98,9 +103,13 @@ class CodecEngine:
         nv.check(L.crdr_eb_quantize(C.byref(d), st))
         T = self.charm.new_support(n, y_act.h, y_act.w, dev)
         self.hs.run(zhat, T, self.charm.off_mean, self.charm.off_scale)
-        yhat32, y_sym, y_idx, y_lik = self.charm.encode(T, y32, self.gp)
-        return dict(y32=y32, z32=z32, z_sym=z_sym, z_hat=z_hat, z_lik=z_lik, yhat32=yhat32, y_sym=y_sym, y_idx=y_idx,
-                    y_lik=y_lik, size=(h, w))
+        enc = self.charm.encode(T, y32, self.gp, compact=compact)
+        yhat32, y_sym, y_idx, y_lik = enc[:4]
+        out = dict(y32=y32, z32=z32, z_sym=z_sym, z_hat=z_hat, z_lik=z_lik, yhat32=yhat32, y_sym=y_sym, y_idx=y_idx,
+                   y_lik=y_lik, size=(h, w))
+        if compact:
+            out.update(y_sym16=enc[4], y_idx8=enc[5])
+        return out
 
     def hyper_from_symbols(self, z_sym):
         """z symbols (int32 NCHW, device) -> (support tensor with h_s output, z_hat NCHW)."""
@@ -119,11 +128,16 @@ class CodecEngine:
         self.hs.run(zhat, T, self.charm.off_mean, self.charm.off_scale)
         return T, z_hat
 
-    def synthesis(self, yhat32, q, beta, size):
-        """y_hat fp32 NHWC -> cropped, clamped fp32 NCHW image."""
+    def synthesis(self, yhat32, q, beta, size, out_uint8=False):
+        """y_hat fp32 NHWC -> cropped, clamped NCHW image: fp32 in [-1,1], or uint8 through the reference's PNG
+        conversion (img_utils.py:30-42, truncation)."""
         img = self.gs.run(yhat32, q, beta)  # phase-packed: [n, hp/2, wp/2, 16]
         n, hb, wb, cs = img.shape
         h, w = size
+        if out_uint8:
+            out = torch.empty((n, 3, h, w), dtype=torch.uint8, device=img.device)
+            nv.check(nv.lib().crdr_phases_to_image_u8(img.data_ptr(), cs, n, hb, wb, h, w, out.data_ptr(), nv.stream_handle()))
+            return out
         out = torch.empty((n, 3, h, w), dtype=torch.float32, device=img.device)
         nv.check(nv.lib().crdr_phases_to_image(img.data_ptr(), cs, n, hb, wb, h, w, out.data_ptr(), nv.stream_handle()))
         return out
@@ -151,11 +165,10 @@ class CodecEngine:
         return out
 
     def max_abs(self, x):
+        """Per-image max |x| in one launch."""
         n = x.shape[0]
         out = torch.empty(n, dtype=torch.float32, device=x.device)
-        per = x[0].numel()
-        for i in range(n):
-            nv.check(nv.lib().crdr_max_abs(x.data_ptr() + 4 * per * i, per, out.data_ptr() + 4 * i, nv.stream_handle()))
+        nv.check(nv.lib().crdr_max_abs_batch(x.data_ptr(), n, x[0].numel(), out.data_ptr(), nv.stream_handle()))
         return out
 
     def to_nchw(self, x32):
@@ -166,18 +179,20 @@ class CodecEngine:
 
 
 class _PinnedPool:
-    """Reusable page-locked staging buffers for the device<->host boundary of the coder (symbols, CDF indexes)."""
+    """Reusable page-locked staging buffers for the device<->host boundary of the coder (symbols, CDF indexes).
+    One growable flat byte buffer per tag (views are taken for each shape), so a dataset with many image sizes or a
+    long-running service does not keep pinning new memory."""
 
     def __init__(self):
         self._bufs = {}
 
     def get(self, tag, shape, dtype):
-        key = (tag, tuple(shape), dtype)
-        buf = self._bufs.get(key)
-        if buf is None:
-            buf = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
-            self._bufs[key] = buf
-        return buf
+        nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        buf = self._bufs.get(tag)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 64), dtype=torch.uint8, pin_memory=True)
+            self._bufs[tag] = buf
+        return buf[:nbytes].view(dtype).view(tuple(shape))
 
     def fetch(self, tag, dev_tensor):
         """Asynchronous device -> pinned host copy on the current stream (caller synchronises)."""
@@ -302,7 +317,11 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
         return float(rate_ind)
 
     def _to_device(self, images):
-        return images.to(device=self.device, dtype=torch.float32).contiguous()
+        """fp32 [-1,1] (the reference's API) or uint8 RGB (normalised on the device) -> contiguous device tensor; the copy
+        is asynchronous when the source is page-locked."""
+        dt = torch.uint8 if images.dtype == torch.uint8 else torch.float32
+        nb = images.device.type == "cpu" and images.is_pinned()
+        return images.to(device=self.device, dtype=dt, non_blocking=nb).contiguous()
 
     # -- forward / run_model ---------------------------------------------------------------------
     @torch.no_grad()
@@ -405,19 +424,26 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
         q = self._q(rate_ind)
         x = self._to_device(real_images)
         n, _, h, w = x.shape
-        a = eng.analysis(x, q)
+        a = eng.analysis(x, q, compact=True)
         y_bits, z_bits = eng.bits(a["y_lik"]), eng.bits(a["z_lik"])
         y_max = eng.max_abs(a["yhat32"])
-        # ---- device -> host boundary (the reference moves y, z here; we move symbols and table indexes)
+        # ---- device -> host boundary (the reference moves y, z here; we move int16 symbols and uint8 table indexes)
         pp = self._pinned
-        z_sym, y_sym, y_idx = (pp.fetch(tag + "z_sym", a["z_sym"]), pp.fetch(tag + "y_sym", a["y_sym"]),
-                               pp.fetch(tag + "y_idx", a["y_idx"]))
+        z_sym, y_sym, y_idx = (pp.fetch(tag + "z_sym", a["z_sym"]), pp.fetch(tag + "y_sym16", a["y_sym16"]),
+                               pp.fetch(tag + "y_idx8", a["y_idx8"]))
         y_bits, z_bits, y_max = (pp.fetch(tag + "y_bits", y_bits), pp.fetch(tag + "z_bits", z_bits),
                                  pp.fetch(tag + "y_max", y_max))
+        flags = pp.get(tag + "flags", (1,), torch.int32)
+        nv.check(nv.lib().crdr_status_peek_async(flags.data_ptr(), nv.stream_handle()), counts=False)
         if return_tensors:
             y_hat = eng.to_nchw(a["yhat32"])
         yield self._event()  # the pinned buffers are valid once this event is
         z_sym, y_sym, y_idx = z_sym.numpy(), y_sym.numpy(), y_idx.numpy()
+        if int(flags[0]) & nv.FLAG_SYM_RANGE:
+            # a symbol outside int16 (never seen with sane weights): take the int32 tensors instead, clear the condition
+            y_sym = a["y_sym"].cpu().numpy()
+            y_idx = a["y_idx"].cpu().numpy()
+            nv.check(nv.lib().crdr_status_clear_bits(nv.FLAG_SYM_RANGE, nv.stream_handle()), counts=False)
         y_bits, z_bits, y_max = y_bits.numpy().copy(), z_bits.numpy().copy(), y_max.numpy().copy()
         zc, hz, wz = z_sym.shape[1:]
         zi = _channel_indexes(zc, hz, wz)
@@ -438,11 +464,13 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
 
     @torch.no_grad()
     def compress_batch(self, real_images, rate_ind, return_tensors=False, coder_threads=0):
-        """N images of one shape -> list of N result dicts (same keys as ``compress``)."""
+        """N images of one shape -> list of N result dicts (same keys as ``compress``).  ``real_images``: fp32 NCHW in
+        [-1,1] like the reference, or uint8 NCHW RGB (normalised on the device exactly like ToTensor + Normalize)."""
         if not hasattr(self, "header_handler"):
             raise RuntimeError("call codec_setup() before compress()")
         n = real_images.shape[0]
         with torch.cuda.device(self.engine().device):
+            nv.status_reset()
             res = self._drive([self._compress_gen(f"c{k}_", real_images[lo:hi], rate_ind, return_tensors, coder_threads)
                                for k, (lo, hi) in enumerate(self._chunks(n))])
             nv.status_check()
@@ -454,7 +482,7 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
         assert n == 1, f"In compress mode, batchsize must be 1, but {n}"
         return self.compress_batch(real_images, rate_ind, return_tensors=True)[0]
 
-    def _decompress_gen(self, tag, string_lists, h, w, q, beta, coder_threads):
+    def _decompress_gen(self, tag, string_lists, h, w, q, beta, coder_threads, out_uint8=False):
         eng = self.engine()
         n = len(string_lists)
         hp, wp = eng.padded(h, w)
@@ -472,13 +500,13 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
         hy, wy = T.h, T.w
         y_sym = torch.empty((n, self.yC, hy, wy), dtype=torch.int32, device=dev)
         sc = eng.charm.sc
-        steps = eng.charm.decode_steps(T, eng.gp)
+        steps = eng.charm.decode_steps(T, eng.gp, compact=True)
         try:
             req = next(steps)
             while True:
                 s0, cnt, idx = req
                 c0, c1 = s0 * sc, (s0 + cnt) * sc
-                # device -> host: table indexes of this group (pinned); the event also covers the previous group's
+                # device -> host: uint8 table indexes of this group (pinned); the event also covers the previous group's
                 # host -> device symbol copy, so the pinned symbol buffer below may be reused
                 ix_host = self._pinned.fetch(f"{tag}y_idx_{cnt}", idx[:, c0:c1].contiguous())
                 yield self._event()
@@ -490,13 +518,14 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
                 req = steps.send(y_sym)
         except StopIteration as done:
             yhat32 = done.value
-        img = eng.synthesis(yhat32, q, beta, (h, w))
+        img = eng.synthesis(yhat32, q, beta, (h, w), out_uint8=out_uint8)
         y_hat = eng.to_nchw(yhat32)
         return img, z_hat, y_hat
 
     @torch.no_grad()
-    def decompress_batch(self, string_lists, beta=0.0, coder_threads=0):
-        """Streams of N images with identical size and quality -> (images [N,3,H,W], z_hat, y_hat)."""
+    def decompress_batch(self, string_lists, beta=0.0, coder_threads=0, out_uint8=False):
+        """Streams of N images with identical size and quality -> (images [N,3,H,W], z_hat, y_hat).  ``out_uint8``: the
+        images come back as uint8 RGB through the reference's PNG conversion (truncation) instead of fp32 [-1,1]."""
         if not hasattr(self, "header_handler"):
             raise RuntimeError("call codec_setup() before decompress()")
         for sl in string_lists:
@@ -508,7 +537,8 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
         q = heads[0]["rate_ind"]
         n = len(string_lists)
         with torch.cuda.device(self.engine().device):
-            res = self._drive([self._decompress_gen(f"d{k}_", string_lists[lo:hi], h, w, q, beta, coder_threads)
+            nv.status_reset()
+            res = self._drive([self._decompress_gen(f"d{k}_", string_lists[lo:hi], h, w, q, beta, coder_threads, out_uint8)
                                for k, (lo, hi) in enumerate(self._chunks(n))])
             nv.status_check()
             if len(res) == 1:

@@ -60,6 +60,7 @@ class GaussDesc(C.Structure):
         ("yq_f32", C.c_void_p), ("yq_f32_cs", C.c_int32), ("yq_f32_coff", C.c_int32),
         ("symbols", C.c_void_p), ("indexes", C.c_void_p), ("likelihood", C.c_void_p),
         ("c_total", C.c_int32), ("nchw_coff", C.c_int32),
+        ("symbols16", C.c_void_p), ("indexes8", C.c_void_p),
     ]
 
 
@@ -75,10 +76,12 @@ class EbDesc(C.Structure):
 
 # every symbol include/crdr_b200.h declares (tests check the library exports all of them)
 SM100_SYMBOLS = [
-    "crdr_abi_version", "crdr_last_error", "crdr_status_reset", "crdr_status_read", "crdr_conv2d",
+    "crdr_abi_version", "crdr_last_error", "crdr_status_reset", "crdr_status_read", "crdr_status_peek_async",
+    "crdr_status_clear_bits", "crdr_conv2d",
     "crdr_affine_to_planes", "crdr_image_to_planes", "crdr_image_to_patches", "crdr_planes_to_image", "crdr_phases_to_image", "crdr_nhwc_to_nchw",
     "crdr_gauss_quantize", "crdr_gauss_indexes", "crdr_gauss_dequantize", "crdr_eb_quantize",
-    "crdr_eb_dequantize", "crdr_bits_from_likelihood", "crdr_max_abs",
+    "crdr_eb_dequantize", "crdr_bits_from_likelihood", "crdr_max_abs", "crdr_max_abs_batch",
+    "crdr_image_u8_to_patches", "crdr_phases_to_image_u8",
 ]
 
 _lib = None
@@ -101,6 +104,8 @@ def lib():
         vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
         L.crdr_status_reset.argtypes = [vp]
         L.crdr_status_read.argtypes = [C.POINTER(C.c_uint32), vp]
+        L.crdr_status_peek_async.argtypes = [vp, vp]
+        L.crdr_status_clear_bits.argtypes = [C.c_uint32, vp]
         L.crdr_conv2d.argtypes = [C.POINTER(ConvDesc), vp]
         L.crdr_affine_to_planes.argtypes = [vp, i32, i32, i64, i32, vp, vp, Planes, vp]
         L.crdr_image_to_planes.argtypes = [vp, i32, i32, i32, i32, i32, Planes, vp]
@@ -114,6 +119,11 @@ def lib():
             getattr(L, name).argtypes = [C.POINTER(EbDesc), vp]
         L.crdr_bits_from_likelihood.argtypes = [vp, i32, i64, vp, vp]
         L.crdr_max_abs.argtypes = [vp, i64, vp, vp]
+        L.crdr_max_abs_batch.argtypes = [vp, i32, i64, vp, vp]
+        L.crdr_image_u8_to_patches.argtypes = [vp, i32, i32, i32, i32, i32, Planes, vp]
+        L.crdr_phases_to_image_u8.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp]
+        L.crdr_debug_conv_epilogue.argtypes = [i32, i32]
+        L.crdr_debug_conv_epilogue.restype = None
         assert L.crdr_abi_version() == 1
         _lib = L
     return _lib
@@ -137,6 +147,9 @@ def stream_handle():
 def ptr(t):
     """Device pointer of a tensor (None -> NULL)."""
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+FLAG_OVERFLOW, FLAG_TIMEOUT, FLAG_SYM_RANGE = 1, 2, 4
 
 
 def set_conv_epilogue(enabled=-1, swizzle=-1):

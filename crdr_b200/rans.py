@@ -16,6 +16,7 @@ RANS_SYMBOLS = [
     "crdr_pmf_to_quantized_cdf", "crdr_rans_encode_with_indexes", "crdr_rans_encode_batch",
     "crdr_rans_decoder_new", "crdr_rans_decoder_free", "crdr_rans_decoder_set_stream",
     "crdr_rans_decoder_decode_stream", "crdr_rans_decode_batch",
+    "crdr_rans_encode_batch_i16u8", "crdr_rans_decode_batch_u8", "crdr_rans_pool_info",
 ]
 
 _lib = None
@@ -41,6 +42,9 @@ def lib():
         L.crdr_rans_decoder_set_stream.argtypes = [vp, C.c_char_p, i64]
         L.crdr_rans_decoder_decode_stream.argtypes = [vp, vp, i64, C.POINTER(CdfTables), vp]
         L.crdr_rans_decode_batch.argtypes = [i32, vp, vp, vp, C.POINTER(CdfTables), vp, i32]
+        L.crdr_rans_encode_batch_i16u8.argtypes = [i32, vp, vp, vp, C.POINTER(CdfTables), vp, vp, vp, i32]
+        L.crdr_rans_decode_batch_u8.argtypes = [i32, vp, vp, vp, C.POINTER(CdfTables), vp, i32]
+        L.crdr_rans_pool_info.argtypes = [C.POINTER(i32), C.POINTER(i32)]
         _lib = L
     return _lib
 
@@ -99,11 +103,31 @@ def encode(symbols, indexes, tables):
         cap = -n
 
 
+def pool_info():
+    """(threads, first cpu) of the coder pool of this process."""
+    t, c = C.c_int32(0), C.c_int32(0)
+    lib().crdr_rans_pool_info(C.byref(t), C.byref(c))
+    return t.value, c.value
+
+
+def _compact(symbols_list, indexes_list):
+    return (all(isinstance(s, np.ndarray) and s.dtype == np.int16 for s in symbols_list) and
+            all(isinstance(i, np.ndarray) and i.dtype == np.uint8 for i in indexes_list))
+
+
 def encode_batch(symbols_list, indexes_list, tables, threads=0):
-    """Independent streams coded concurrently on host threads."""
+    """Independent streams coded concurrently on the coder pool.  int32 / int32 arrays, or the compact int16 symbols +
+    uint8 indexes the CUDA kernels write for the coder (no conversion either way)."""
     cnt = len(symbols_list)
-    ss = [_i32(s).reshape(-1) for s in symbols_list]
-    ii = [_i32(i).reshape(-1) for i in indexes_list]
+    compact = _compact(symbols_list, indexes_list)
+    if compact:
+        ss = [np.ascontiguousarray(s).reshape(-1) for s in symbols_list]
+        ii = [np.ascontiguousarray(i).reshape(-1) for i in indexes_list]
+        fn = lib().crdr_rans_encode_batch_i16u8
+    else:
+        ss = [_i32(s).reshape(-1) for s in symbols_list]
+        ii = [_i32(i).reshape(-1) for i in indexes_list]
+        fn = lib().crdr_rans_encode_batch
     caps = [4 * (s.size + 64) for s in ss]
     while True:
         outs = [np.empty(c, dtype=np.uint8) for c in caps]
@@ -111,8 +135,8 @@ def encode_batch(symbols_list, indexes_list, tables, threads=0):
         n = (C.c_int64 * cnt)(*[s.size for s in ss])
         cp = (C.c_int64 * cnt)(*caps)
         lens = (C.c_int64 * cnt)()
-        rc = lib().crdr_rans_encode_batch(cnt, PP(*[s.ctypes.data for s in ss]), PP(*[i.ctypes.data for i in ii]), n,
-                                          C.byref(tables.c), PP(*[o.ctypes.data for o in outs]), cp, lens, threads)
+        rc = fn(cnt, PP(*[s.ctypes.data for s in ss]), PP(*[i.ctypes.data for i in ii]), n,
+                C.byref(tables.c), PP(*[o.ctypes.data for o in outs]), cp, lens, threads)
         if rc == 0:
             return [outs[k][: lens[k]].tobytes() for k in range(cnt)]
         if any(l == -(2 ** 63) for l in lens):
@@ -150,7 +174,8 @@ class Decoder:
 def decode_batch(decoders, indexes_list, tables, threads=0, outs=None):
     """``outs``: optional list of writable contiguous int32 arrays (e.g. views of a pinned buffer) to decode into."""
     cnt = len(decoders)
-    ii = [_i32(i).reshape(-1) for i in indexes_list]
+    u8 = all(isinstance(i, np.ndarray) and i.dtype == np.uint8 for i in indexes_list)
+    ii = [np.ascontiguousarray(i).reshape(-1) for i in indexes_list] if u8 else [_i32(i).reshape(-1) for i in indexes_list]
     if outs is None:
         outs = [np.empty(i.size, dtype=np.int32) for i in ii]
     else:
@@ -158,8 +183,9 @@ def decode_batch(decoders, indexes_list, tables, threads=0, outs=None):
                                         for o, i in zip(outs, ii))
     PP = C.c_void_p * cnt
     n = (C.c_int64 * cnt)(*[i.size for i in ii])
-    rc = lib().crdr_rans_decode_batch(cnt, PP(*[d._h for d in decoders]), PP(*[i.ctypes.data for i in ii]), n,
-                                      C.byref(tables.c), PP(*[o.ctypes.data for o in outs]), threads)
+    fn = lib().crdr_rans_decode_batch_u8 if u8 else lib().crdr_rans_decode_batch
+    rc = fn(cnt, PP(*[d._h for d in decoders]), PP(*[i.ctypes.data for i in ii]), n,
+            C.byref(tables.c), PP(*[o.ctypes.data for o in outs]), threads)
     if rc:
         raise ValueError("rans decode: CDF index out of range")
     return outs

@@ -35,7 +35,7 @@ typedef enum {
   CRDR_ERR_MISALIGNED = 2,
   CRDR_ERR_UNSUPPORTED_ARCH = 3,
   CRDR_ERR_CUDA = 4,
-  CRDR_ERR_DEVICE_FLAG = 5 /* a kernel raised the device status word (fp16 overflow / pipeline timeout) */
+  CRDR_ERR_DEVICE_FLAG = 5 /* a kernel raised the device status word (fp16 overflow / pipeline timeout / int16 symbol range) */
 } crdr_status;
 
 /* Arithmetic of the contraction. */
@@ -125,10 +125,14 @@ int crdr_abi_version(void);
 const char* crdr_last_error(void);
 
 /* Device status word (one per device, lives in device memory owned by the library:
- * bit0 fp16 overflow in an epilogue, bit1 pipeline wait timeout).  `crdr_status_read`
+ * bit0 fp16 overflow in an epilogue, bit1 pipeline wait timeout, bit2 a symbol outside the compact int16 range).  `crdr_status_read`
  * synchronises the stream. */
 int crdr_status_reset(void* stream);
 int crdr_status_read(uint32_t* flags, void* stream);
+/* Asynchronous copy of the status word into caller-owned (page-locked) host memory, no synchronisation; and an
+ * in-stream clear of selected bits (a handled condition must not poison later calls). */
+int crdr_status_peek_async(uint32_t* host_flags, void* stream);
+int crdr_status_clear_bits(uint32_t bits, void* stream);
 
 int crdr_conv2d(const crdr_conv_desc* d, void* stream);
 
@@ -156,6 +160,15 @@ int crdr_planes_to_image(const float* x, int32_t x_cs, int32_t n, int32_t hp, in
  * crop + clamp -> NCHW fp32 (h <= 2*hb, w <= 2*wb). */
 int crdr_phases_to_image(const float* x, int32_t x_cs, int32_t n, int32_t hb, int32_t wb, int32_t h, int32_t w,
                          float* img, void* stream);
+
+/* uint8 image boundary.  Input: NCHW uint8 RGB as PIL / cv2 deliver it; the kernel applies the reference's
+ * ToTensor + Normalize(0.5, 0.5) arithmetic (scripts/compress.py:54-57: (u/255 - 0.5)/0.5 in fp32) before the reflect
+ * pad + im2col of crdr_image_to_patches.  Output: crop + clamp(-1,1) followed by the reference's PNG conversion
+ * (img_utils.py:30-42,66-76: ((x+1)/2*255) in fp32, astype(uint8) = truncation), NCHW uint8. */
+int crdr_image_u8_to_patches(const uint8_t* img, int32_t n, int32_t h, int32_t w, int32_t hp, int32_t wp,
+                             crdr_planes out, void* stream);
+int crdr_phases_to_image_u8(const float* x, int32_t x_cs, int32_t n, int32_t hb, int32_t wb, int32_t h, int32_t w,
+                            uint8_t* img, void* stream);
 
 /* NHWC fp32 [n][hw][cs](coff..coff+c) -> NCHW fp32 [n][c][hw]  (API-facing tensors). */
 int crdr_nhwc_to_nchw(const float* x, int32_t x_cs, int32_t x_coff, int32_t n, int32_t hw, int32_t c,
@@ -188,6 +201,12 @@ typedef struct {
   int32_t* indexes;   /* NCHW, may be NULL */
   float* likelihood;  /* NCHW, may be NULL */
   int32_t c_total, nchw_coff;
+  /* Compact copies for the host range coder (same NCHW order and offsets; a quarter of the PCIe and host-memory
+   * traffic of the int32 tensors the reference moves with .cpu() / .tolist()): symbols as int16 (values outside the
+   * int16 range saturate and raise device status bit 2, the caller then falls back to the int32 tensor), table
+   * indexes as uint8.  crdr_gauss_dequantize reads `symbols16` when `symbols` is NULL.  May be NULL. */
+  int16_t* symbols16;
+  uint8_t* indexes8;
 } crdr_gauss_desc;
 int crdr_gauss_quantize(const crdr_gauss_desc* d, void* stream);
 
@@ -224,6 +243,8 @@ int crdr_bits_from_likelihood(const float* lik, int32_t n, int64_t per, float* b
 
 /* max |x| over `count` floats -> out[0] (header byte, codec_utils.py:88). */
 int crdr_max_abs(const float* x, int64_t count, float* out, void* stream);
+/* out[i] = max |x[i*per .. (i+1)*per)| for n consecutive images in one launch. */
+int crdr_max_abs_batch(const float* x, int32_t n, int64_t per, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,15 @@ int crdr_rans_encode_batch(int32_t count, const int32_t* const* symbols, const i
                            const int64_t* n, const crdr_cdf_tables* t, uint8_t* const* out, const int64_t* out_cap,
                            int64_t* lengths, int32_t threads);
 
+/* Same with the compact arrays the CUDA kernels write for the coder (crdr_gauss_desc.symbols16 / indexes8). */
+int crdr_rans_encode_batch_i16u8(int32_t count, const int16_t* const* symbols, const uint8_t* const* indexes,
+                                 const int64_t* n, const crdr_cdf_tables* t, uint8_t* const* out, const int64_t* out_cap,
+                                 int64_t* lengths, int32_t threads);
+/* Coder thread pool of this process: persistent workers pinned to the LOCAL_RANK-th of LOCAL_WORLD_SIZE equal slices
+ * of the CPUs the process may use (CRDR_CODER_THREADS caps the size, CRDR_CODER_PIN=0 disables pinning).  The
+ * `threads` argument of the batch calls is an upper bound (0 = the whole pool). */
+int crdr_rans_pool_info(int32_t* threads, int32_t* first_cpu);
+
 void* crdr_rans_decoder_new(void);
 void crdr_rans_decoder_free(void* dec);
 /* Copies the stream; subsequent decode_stream calls continue from the same coder state. */
@@ -57,6 +66,10 @@ int crdr_rans_decoder_decode_stream(void* dec, const int32_t* indexes, int64_t n
 /* decoders[i] decodes n[i] symbols with indexes[i] into out[i], concurrently. */
 int crdr_rans_decode_batch(int32_t count, void* const* decoders, const int32_t* const* indexes, const int64_t* n,
                            const crdr_cdf_tables* t, int32_t* const* out, int32_t threads);
+
+/* Same with the uint8 table indexes the CUDA kernels write for the coder (crdr_gauss_desc.indexes8). */
+int crdr_rans_decode_batch_u8(int32_t count, void* const* decoders, const uint8_t* const* indexes, const int64_t* n,
+                              const crdr_cdf_tables* t, int32_t* const* out, int32_t threads);
 
 #ifdef __cplusplus
 }

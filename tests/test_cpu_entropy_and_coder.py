@@ -185,3 +185,26 @@ def test_rebuilt_tables_never_reuse_stale_frequencies():
         assert np.array_equal(out, sym), f"iteration {it}"
         del t
         gc.collect()
+
+
+def test_compact_coder_entry_points_and_pool():
+    """int16 symbols / uint8 indexes (what the CUDA kernels hand to the coder) produce the bytes of the int32 entry
+    points, on the persistent per-rank pool."""
+    from crdr_b200 import rans
+    threads, first_cpu = rans.pool_info()
+    assert threads >= 1 and first_cpu >= 0
+    rng = np.random.default_rng(3)
+    k = 33
+    pmf = np.exp(-0.5 * ((np.arange(k) - 16) / 3.0) ** 2).astype(np.float32)
+    pmf /= pmf.sum()
+    cdf = rans.pmf_to_quantized_cdf(pmf)
+    t = rans.Tables(np.stack([cdf] * 5), [cdf.size] * 5, [-16] * 5)
+    syms = [np.clip(np.rint(rng.normal(0, 6, 3000 + 7 * i)), -300, 300).astype(np.int32) for i in range(9)]
+    idxs = [rng.integers(0, 5, s.size).astype(np.int32) for s in syms]
+    a = rans.encode_batch(syms, idxs, t)
+    b = rans.encode_batch([s.astype(np.int16) for s in syms], [i.astype(np.uint8) for i in idxs], t)
+    assert a == b == [rans.encode(s, i, t) for s, i in zip(syms, idxs)]
+    out = rans.decode_batch([rans.Decoder(s) for s in a], [i.astype(np.uint8) for i in idxs], t)
+    assert all(np.array_equal(o, s) for o, s in zip(out, syms))
+    out = rans.decode_batch([rans.Decoder(s) for s in a], idxs, t, threads=1)
+    assert all(np.array_equal(o, s) for o, s in zip(out, syms))

@@ -339,3 +339,63 @@ def test_compress_script_end_to_end(models, tmp_path):
     want = np.asarray(Image.open(out_dir / "im2.png").convert("RGB"))
     got = ((img[0].cpu() + 1) / 2 * 255).numpy().astype(np.uint8).transpose(1, 2, 0)
     assert got.shape == (70, 100, 3) and np.array_equal(got, want)
+
+
+def test_uint8_image_boundary(models):
+    """uint8 RGB in / out: the device-side ToTensor + Normalize and the PNG conversion reproduce the
+    reference's fp32 arithmetic (scripts/compress.py:54-57, img_utils.py:30-42), so the uint8 entry gives the same
+    bytes as the fp32 entry fed with the reference's own normalisation, and the uint8 output equals the truncated
+    fp32 output."""
+    import fixtures
+    model, _ = models(True)
+    g = torch.Generator().manual_seed(21)
+    u8 = torch.randint(0, 256, (3, 3, 70, 100), generator=g, dtype=torch.uint8)
+    ref_float = (u8.float().div(255) - 0.5) / 0.5          # ToTensor().div(255); Normalize(0.5, 0.5)
+    a = model.compress_batch(u8, 2.0)
+    b = model.compress_batch(ref_float, 2.0)
+    assert [r["string_list"] for r in a] == [r["string_list"] for r in b]
+    strings = [r["string_list"] for r in a]
+    img_u8, _, y1 = model.decompress_batch(strings, beta=3.84, out_uint8=True)
+    img_f, _, y2 = model.decompress_batch(strings, beta=3.84)
+    assert img_u8.dtype == torch.uint8 and img_u8.shape == (3, 3, 70, 100) and torch.equal(y1, y2)
+    want = ((img_f.cpu() + 1.0) / 2.0 * 255.0).numpy().astype(np.uint8)     # torch2npimg
+    assert np.array_equal(img_u8.cpu().numpy(), want)
+
+
+def test_compact_symbol_range_flag():
+    """The coder reads compact int16 symbols / uint8 indexes written next to the int32 tensors.  A symbol outside int16
+    saturates in the compact copy and raises status bit 2 (compress_batch then reads the int32 tensors); the bit can be
+    cleared without touching the others.  (With real weights fp16 activations overflow long before |symbol| > 32767.)"""
+    import ctypes as C
+    from crdr_b200 import native as nv
+    from crdr_b200.engine import Act
+    from crdr_b200.entropy import get_scale_table
+    n, hw, c = 1, 64, 32
+    y = torch.zeros(n, hw, c, device="cuda")
+    y[0, 3, 5], y[0, 9, 31], y[0, 10, 0] = 40000.4, -51000.0, 123.6
+    ms = torch.zeros(n, hw, 2 * c, device="cuda")
+    ms[..., c:] = 2.0
+    table = get_scale_table().cuda()
+    T = Act.zeros(n, 8, 8, c)
+    sym = torch.empty(n, c, hw, dtype=torch.int32, device="cuda")
+    idx = torch.empty_like(sym)
+    sym16 = torch.empty(n, c, hw, dtype=torch.int16, device="cuda")
+    idx8 = torch.empty(n, c, hw, dtype=torch.uint8, device="cuda")
+    d = nv.GaussDesc()
+    d.y, d.y_cs, d.y_coff = y.data_ptr(), c, 0
+    d.mu, d.sigma, d.ms_cs, d.mu_coff, d.sigma_coff = ms.data_ptr(), ms.data_ptr(), 2 * c, 0, c
+    d.n, d.hw, d.c = n, hw, c
+    d.scale_bound, d.scale_table, d.ntable = 0.11, table.data_ptr(), table.numel()
+    d.yq_planes = T.planes(0)
+    d.symbols, d.indexes, d.symbols16, d.indexes8 = sym.data_ptr(), idx.data_ptr(), sym16.data_ptr(), idx8.data_ptr()
+    d.c_total, d.nchw_coff = c, 0
+    nv.status_reset()
+    nv.check(nv.lib().crdr_gauss_quantize(C.byref(d), nv.stream_handle()))
+    flags = C.c_uint32(0)
+    rc = nv.lib().crdr_status_read(C.byref(flags), nv.stream_handle())
+    assert rc == 5 and flags.value == nv.FLAG_SYM_RANGE
+    assert sym[0, 5, 3].item() == 40000 and sym[0, 31, 9].item() == -51000 and sym[0, 0, 10].item() == 124
+    assert sym16[0, 5, 3].item() == 32767 and sym16[0, 31, 9].item() == -32768 and sym16[0, 0, 10].item() == 124
+    assert torch.equal(idx8.int(), idx) and torch.equal(sym16.int().clamp(-32768, 32767), sym.clamp(-32768, 32767))
+    nv.check(nv.lib().crdr_status_clear_bits(nv.FLAG_SYM_RANGE, nv.stream_handle()), counts=False)
+    nv.status_check()

@@ -19,6 +19,10 @@ CASES = [
     ("3x3 96->96 x3 relu_affine", 2, 96, 96, 12, 20, 3, 1, False, X3, "relu_affine"),
     ("5x5s2 192->192 x3", 1, 192, 192, 32, 48, 5, 2, False, X3, "none"),
     ("5x5s2 8->192 x3 odd dims", 1, 8, 192, 30, 42, 5, 2, False, X3, "none"),
+    ("5x5s2 192->192 x3 odd dims n=3", 3, 192, 192, 31, 45, 5, 2, False, X3, "relu_affine"),
+    ("5x5s2 320->256 x3 (h_a)", 2, 320, 256, 32, 48, 5, 2, False, X3, "none"),
+    ("5x5s2 256->192 x3 tiny (h_a)", 1, 256, 192, 8, 12, 5, 2, False, X3, "none"),
+    ("3x3s2 64->64 x1", 1, 64, 64, 20, 20, 3, 2, False, X1, "none"),
     ("1x1 96->192 x3 residual", 1, 96, 192, 16, 24, 1, 1, False, X3, "residual"),
     ("1x1 160->320 x3 gate", 1, 160, 320, 8, 12, 1, 1, False, X3, "gate"),
     ("3x3 128->32 x3 half_tanh", 1, 128, 32, 8, 12, 3, 1, False, X3, "half_tanh"),
