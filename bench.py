@@ -31,6 +31,14 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 H, W, BATCH = 512, 768, 24
+# --workload: BASELINE.json configs.  (height, width, images per rank and step (weak) or per step in total (strong),
+# images per device call, scaling).  The default is configs[1], the configuration the metric is quoted on.
+WORKLOADS = {
+    "kodak24": (512, 768, 24, 24, "weak"),      # configs[1]
+    "kodak1": (512, 768, 1, 1, "weak"),         # configs[0] shape: single-image latency
+    "clic": (1365, 2048, 16, 4, "strong"),      # configs[2]: a fixed list of 16 images sharded round-robin over the ranks
+    "uhd": (2160, 3840, 1, 1, "weak"),          # configs[3]: single-image latency; one image per GPU at N = 8
+}
 SWEEP = [0.25 * i for i in range(17)]
 BETAS = [0.0, 3.84]
 MAC_PER_PX = 1478360  # encode + decode, per padded pixel
@@ -107,7 +115,9 @@ def cpu_codec_sample(images_per_step, steps, warmup):
 def run_reference(args, rank):
     if rank != 0:
         return
-    per_step = 3
+    global H, W
+    H, W = WORKLOADS[args.workload][:2]
+    per_step = 3 if H * W <= 512 * 768 else 1   # bounded sample: about 1 s per Kodak image, 25 s per 4K image on 16 threads
     warm = min(args.warmup, 1)
     steps = min(args.steps, 3)
     v, sec, cores = cpu_codec_sample(per_step, steps, warm)
@@ -115,7 +125,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "MPix/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Kodak-shaped {H}x{W}, {per_step} image per step (bounded sample of the batch-{BATCH} workload), "
+        "config": {"workload": f"{args.workload}: {H}x{W}, {per_step} image per step (bounded sample of the workload), "
                                "quality sweep 0-4, beta in {0,3.84}; calibrated random-init weights"},
         "cpu_baseline": {"value": v, "unit": "MPix/s", "cores": cores, "kind": "port",
                          "sample": f"{steps} timed steps x {per_step} image {H}x{W}: oracle compress()+decompress() incl. host rANS"},
@@ -131,7 +141,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="crdr_b200", choices=["crdr_b200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--batch", type=int, default=None, help="override the workload's images per rank and step")
+    ap.add_argument("--workload", default="kodak24", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
@@ -155,21 +166,33 @@ def main():
     dev = f"cuda:{local}"
     warmup = max(args.warmup, 3)
     steps = args.steps
-    B = args.batch
+    global H, W
+    H, W, per_step, call_batch, scaling = WORKLOADS[args.workload]
+    if args.batch:
+        per_step, call_batch = args.batch, min(args.batch, call_batch if args.workload != "kodak24" else args.batch)
+    if scaling == "strong":
+        B = len(range(rank, per_step, world))        # this rank's share of the fixed image list (round-robin)
+        total_images = per_step
+    else:
+        B = per_step
+        total_images = per_step * world
+    default_cfg = args.workload == "kodak24" and B == BATCH
 
     model, _ = fixtures.build_model(seed=0, calibrated=True, device=dev)
     eng = model.engine()
     # rank-local shard: every rank codes its own `B` images (weak scaling, no data-path collective)
     # uint8 RGB images, the form PIL / cv2 deliver them in and PNGs are written from (normalised on the device)
-    x_f = fixtures.image(B, H, W, seed=100 + rank)
+    x_f = fixtures.image(max(B, 1), H, W, seed=100 + rank)[:B]
     x_host = ((x_f + 1.0) / 2.0 * 255.0).round().clamp(0, 255).to(torch.uint8).pin_memory()
     x_dev = x_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def device_step(i):
         q, beta = SWEEP[i % len(SWEEP)], BETAS[i % 2]
-        a = eng.analysis(x_dev, q)
-        img, _, _ = eng.decode_device(a["z_sym"], a["y_sym"], q, beta, (H, W))
+        img = None
+        for c0 in range(0, B, call_batch):
+            a = eng.analysis(x_dev[c0:c0 + call_batch], q)
+            img, _, _ = eng.decode_device(a["z_sym"], a["y_sym"], q, beta, (H, W))
         return img
 
     def barrier():
@@ -201,14 +224,16 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = t.item() / steps
-    value = world * B * H * W / (ms_step * 1e-3) / 1e6
+    value = total_images * H * W / (ms_step * 1e-3) / 1e6
 
     # ---- end to end through the public API with host buffers
     def e2e_step(i):
         q, beta = SWEEP[i % len(SWEEP)], BETAS[i % 2]
-        outs = model.compress_batch(x_host, q)                       # H2D images, D2H symbols, host rANS encode
-        img, _, _ = model.decompress_batch([o["string_list"] for o in outs], beta=beta, out_uint8=True)  # host rANS decode inside
-        host_img.copy_(img, non_blocking=True)   # result -> the caller's (reused) page-locked buffer
+        outs = None
+        for c0 in range(0, B, call_batch):
+            outs = model.compress_batch(x_host[c0:c0 + call_batch], q)      # H2D images, D2H symbols, host rANS encode
+            img, _, _ = model.decompress_batch([o["string_list"] for o in outs], beta=beta, out_uint8=True)  # host rANS decode inside
+            host_img[c0:c0 + call_batch].copy_(img, non_blocking=True)   # result -> the caller's (reused) page-locked buffer
         torch.cuda.synchronize()
         return outs, host_img
 
@@ -225,8 +250,9 @@ def main():
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * H * W / te.item() / 1e6
-    hy, wy, hz, wz = H // 16, W // 16, H // 64, W // 64
+    e2e_value = total_images * H * W / te.item() / 1e6
+    HP, WP = -(-H // 64) * 64, -(-W // 64) * 64
+    hy, wy, hz, wz = HP // 16, WP // 16, HP // 64, WP // 64
     # encode: uint8 images in; int16 y symbols + uint8 table indexes + int32 z symbols out.
     # decode: int32 z / y symbols in; uint8 table indexes + uint8 images out.
     h2d = B * 3 * H * W + B * (320 * hy * wy + 192 * hz * wz) * 4
@@ -240,17 +266,19 @@ def main():
     eng_mod.PROFILE_ON[0] = False
     conv_ms = sum(p[1].elapsed_time(p[2]) for p in eng_mod.PROFILE)
     conv_launches = len(eng_mod.PROFILE)
-    flops_step = 2.0 * MAC_PER_PX * B * H * W
+    flops_step = 2.0 * MAC_PER_PX * B * HP * WP   # this rank's padded pixels
     tensor_peak, hbm_peak, peak_src = peaks()
     achieved = flops_step / (conv_ms * 1e-3) / 1e12
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "MPix/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f16 (3-term error-compensated split = fp32-class in g_a/h_a/h_s/ChARM; plain f16 in g_s), fp32 accumulate",
             "data": "synthetic",
-            "config": {"workload": f"Kodak-shaped {H}x{W} synthetic uint8 RGB, batch {B} per GPU, quality sweep 0-4 (one q per step), "
+            "config": {"workload": f"{args.workload}: {H}x{W} synthetic uint8 RGB, "
+                                   + (f"{per_step} images per step sharded round-robin over the ranks, " if scaling == "strong"
+                                      else f"batch {B} per GPU, ") + f"{call_batch} per device call, quality sweep 0-4 (one q per step), "
                                    f"beta in {{0,3.84}}; seeded calibrated random-init crdr.yaml weights",
                        "step": "encode (image->symbols+indexes) + decode (symbols->image) of the batch",
                        "l2": "256 MiB memset between steps (inside the timed region); packed weights alone are 0.5 GB > L2",
@@ -263,7 +291,7 @@ def main():
                          "frac": achieved / tensor_peak,
                          # dram__bytes_read+write per conv launch, averaged over the 369 launches of one step of this
                          # workload (ncu capture: profiles/conv_dram_traffic_r01.txt); only valid for the default batch
-                         "traffic": 289.8e6 if (B == BATCH) else None, "peak_source": peak_src,
+                         "traffic": 289.8e6 if default_cfg else None, "peak_source": peak_src,
                          "kernel": "conv_tcgen05_kernel", "launches_per_step": conv_launches, "kernel_ms_per_step": conv_ms,
                          "flops_per_step": flops_step,
                          "note": "algorithmic FLOPs = 2 x 1,478,360 MAC/px x padded px; the F16X3 layers execute 3 fp16 MMAs "
