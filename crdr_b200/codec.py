@@ -13,8 +13,13 @@ import math
 import torch
 import torch.nn.functional as F
 
+import os
+
+from . import engine as engine_mod
 from . import native as nv
 from .engine import Act, ConvOp, NULL_PLANES
+
+FUSE_BC = [os.environ.get("CRDR_FUSE_BC", "1") != "0"]   # fused bottleneck tail (tests flip it to compare the two forms)
 
 X3, X1 = nv.PREC_F16X3, nv.PREC_F16X1
 
@@ -45,17 +50,60 @@ class NetCfg:
 
 class Bottleneck:
     """1x1 -> ReLU -> 3x3 -> ReLU -> 1x1 (+ skip): BaseBlock (elic_layers.py:23-36), NLAMResBlock
-    (cheng_nlam.py:32-47) and BetaCondBaseBlock (elic_interpca_beta_cond_autoencoder.py:42-66)."""
+    (cheng_nlam.py:32-47) and BetaCondBaseBlock (elic_interpca_beta_cond_autoencoder.py:42-66).
+
+    F16X1 blocks whose accumulators fit TMEM (mid <= 128, C <= 256: every g_s block except the 320-channel NLAM) run the
+    3x3 and the last 1x1 as ONE launch (crdr_bottleneck_bc: the mid tensor stays in shared memory); the others as
+    three crdr_conv2d launches.  Both forms produce identical bits (CRDR_FUSE_BC=0 selects the unfused form)."""
 
     def __init__(self, sd, names, cfg):
         self.c1 = Conv(sd, names[0], cfg)
         self.c2 = Conv(sd, names[1], cfg, padding=1)
         self.c3 = Conv(sd, names[2], cfg)
+        self.cfg = cfg
+        mid, cout = self.c2.op.cout, self.c3.op.cout
+        self.fused = (cfg.precision == X1 and cfg.engine == nv.ENGINE_TCGEN05 and self.c2.op.algo == "patch"
+                      and self.c3.op.algo == "patch" and mid % 32 == 0 and 32 <= mid <= 128 and cout % 32 == 0 and cout <= 256
+                      and self.c2.op.cin == mid and self.c3.op.cin == mid)
+        if self.fused:
+            d = nv.BottleneckDesc()
+            p2, p3 = self.c2.op.phases[0], self.c3.op.phases[0]
+            d.mid, d.cout = mid, cout
+            d.w2, d.k2_pad, d.mid_pad = p2.w_hi.data_ptr(), p2.k_pad, self.c2.op.cout_pad
+            d.w3, d.k3_pad, d.cout_pad = p3.w_hi.data_ptr(), p3.k_pad, self.c3.op.cout_pad
+            d.bias2 = self.c2.op.bias.data_ptr() if self.c2.op.bias is not None else None
+            d.bias3 = self.c3.op.bias.data_ptr() if self.c3.op.bias is not None else None
+            d.precision = X1
+            self.tmpl = d
 
     def __call__(self, x, add=(None, None, None), scale=None, shift=None):
         t = self.c1(x, relu=True, add_vec=add[0])
+        if self.fused and FUSE_BC[0]:
+            return self._tail(t, x, add[1], add[2], scale, shift)
         t = self.c2(t, relu=True, add_vec=add[1])
         return self.c3(t, add_vec=add[2], mode=nv.EPI_RESIDUAL, res=x, scale=scale, shift=shift)
+
+    def _tail(self, t, x, add2, add3, scale, shift):
+        out = Act.empty(x.n, x.h, x.w, self.c3.op.cout, two=False, device=x.hi.device)
+        d = nv.BottleneckDesc.from_buffer_copy(self.tmpl)
+        d.inp, d.res, d.out = t.planes(0), x.planes(0), out.planes(0)
+        d.n, d.h, d.w = x.n, x.h, x.w
+        d.add2 = add2.data_ptr() if add2 is not None else None
+        d.add3 = add3.data_ptr() if add3 is not None else None
+        d.scale = scale.data_ptr() if scale is not None else None
+        d.shift = shift.data_ptr() if shift is not None else None
+        st = nv.stream_handle()
+        if engine_mod.PROFILE_ON[0]:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            nv.check(nv.lib().crdr_bottleneck_bc(C.byref(d), st))
+            e1.record()
+            m, mid, cout = x.n * x.h * x.w, self.c2.op.cout, self.c3.op.cout
+            engine_mod.PROFILE.append((2.0 * m * (9 * mid * mid + mid * cout), e0, e1,
+                                       dict(m=m, n=cout, k=9 * mid + mid, taps=10, tile_n=cout, prec=X1, transposed=False, stride=1)))
+        else:
+            nv.check(nv.lib().crdr_bottleneck_bc(C.byref(d), st))
+        return out
 
 
 class Nlam:

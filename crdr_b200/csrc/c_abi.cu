@@ -54,6 +54,7 @@ uint32_t* device_status_word() {
 
 int conv2d_launch(const crdr_conv_desc* d, cudaStream_t stream);
 void conv_set_lean(int enabled, int swizzle);
+int bottleneck_bc_launch(const crdr_bottleneck_desc* d, cudaStream_t stream);
 int gauss_launch(const crdr_gauss_desc* d, int mode, cudaStream_t st);
 int eb_launch(const crdr_eb_desc* d, int dequant, cudaStream_t st);
 int nhwc_to_nchw_launch(const float* x, int x_cs, int x_coff, int n, int hw, int c, float* out, cudaStream_t st);
@@ -143,6 +144,11 @@ void crdr_debug_conv_epilogue(int32_t enabled, int32_t swizzle) { conv_set_lean(
 int crdr_conv2d(const crdr_conv_desc* d, void* stream) {
   if (!d) { set_error("conv2d: null descriptor"); return CRDR_ERR_BAD_SHAPE; }
   return conv2d_launch(d, (cudaStream_t)stream);
+}
+
+int crdr_bottleneck_bc(const crdr_bottleneck_desc* d, void* stream) {
+  if (!d) { set_error("bottleneck: null descriptor"); return CRDR_ERR_BAD_SHAPE; }
+  return bottleneck_bc_launch(d, (cudaStream_t)stream);
 }
 
 int crdr_affine_to_planes(const float* x, int32_t x_cs, int32_t x_coff, int64_t m, int32_t c, const float* scale,

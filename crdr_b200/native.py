@@ -48,6 +48,20 @@ class ConvDesc(C.Structure):
     ]
 
 
+class BottleneckDesc(C.Structure):
+    _fields_ = [
+        ("inp", Planes),
+        ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+        ("mid", C.c_int32), ("cout", C.c_int32),
+        ("w2", C.c_void_p), ("k2_pad", C.c_int32), ("mid_pad", C.c_int32),
+        ("w3", C.c_void_p), ("k3_pad", C.c_int32), ("cout_pad", C.c_int32),
+        ("bias2", C.c_void_p), ("add2", C.c_void_p), ("bias3", C.c_void_p), ("add3", C.c_void_p),
+        ("res", Planes), ("out", Planes),
+        ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("precision", C.c_int32),
+    ]
+
+
 class GaussDesc(C.Structure):
     _fields_ = [
         ("y", C.c_void_p), ("y_cs", C.c_int32), ("y_coff", C.c_int32),
@@ -77,7 +91,7 @@ class EbDesc(C.Structure):
 # every symbol include/crdr_b200.h declares (tests check the library exports all of them)
 SM100_SYMBOLS = [
     "crdr_abi_version", "crdr_last_error", "crdr_status_reset", "crdr_status_read", "crdr_status_peek_async",
-    "crdr_status_clear_bits", "crdr_conv2d",
+    "crdr_status_clear_bits", "crdr_conv2d", "crdr_bottleneck_bc",
     "crdr_affine_to_planes", "crdr_image_to_planes", "crdr_image_to_patches", "crdr_planes_to_image", "crdr_phases_to_image", "crdr_nhwc_to_nchw",
     "crdr_gauss_quantize", "crdr_gauss_indexes", "crdr_gauss_dequantize", "crdr_eb_quantize",
     "crdr_eb_dequantize", "crdr_bits_from_likelihood", "crdr_max_abs", "crdr_max_abs_batch",
@@ -107,6 +121,7 @@ def lib():
         L.crdr_status_peek_async.argtypes = [vp, vp]
         L.crdr_status_clear_bits.argtypes = [C.c_uint32, vp]
         L.crdr_conv2d.argtypes = [C.POINTER(ConvDesc), vp]
+        L.crdr_bottleneck_bc.argtypes = [C.POINTER(BottleneckDesc), vp]
         L.crdr_affine_to_planes.argtypes = [vp, i32, i32, i64, i32, vp, vp, Planes, vp]
         L.crdr_image_to_planes.argtypes = [vp, i32, i32, i32, i32, i32, Planes, vp]
         L.crdr_image_to_patches.argtypes = [vp, i32, i32, i32, i32, i32, Planes, vp]

@@ -136,6 +136,39 @@ int crdr_status_clear_bits(uint32_t bits, void* stream);
 
 int crdr_conv2d(const crdr_conv_desc* d, void* stream);
 
+/*
+ * Fused tail of a residual bottleneck (F16X1 tensors), one launch instead of two crdr_conv2d calls:
+ *     t2  = relu(conv3x3(t1; w2) + bias2) + add2              (never leaves the SM)
+ *     out = (conv1x1(t2; w3) + bias3 + add3 + res) * scale + shift
+ * Replaces the second and third convolution (and the element-wise ops between / after them) of
+ *   BaseBlock.forward (elic_layers.py:23-36), NLAMResBlock.forward (cheng_nlam.py:32-47) and
+ *   BetaCondBaseBlock.forward (elic_interpca_beta_cond_autoencoder.py:52-66; add2 / add3 = proj_2(c) / proj_3(c)).
+ * The result is bit-identical to the two separate launches (same fp16 mid tensor, same K order, same epilogue).
+ * in: t1 [n, h, w, mid] (the first 1x1's output); res / out: [n, h, w, cout] channel ranges of NHWC planes.
+ * w2: packed [mid_pad][k2_pad] in k_order 1 (k = (cb*9 + tap)*64 + ci%64, taps row-major from (-1,-1)), w3: packed
+ * [cout_pad][k3_pad] (k = cb*64 + ci%64) -- the matrices crdr_conv2d takes for the same layers.
+ * Limits: mid % 32 == 0, mid <= 128, cout % 32 == 0, cout <= 256 (512 TMEM columns hold two 3x3 and one 1x1 accumulator).
+ */
+typedef struct {
+  crdr_planes in;   /* t1 */
+  int32_t n, h, w;
+  int32_t mid, cout;
+  const void* w2;
+  int32_t k2_pad, mid_pad;
+  const void* w3;
+  int32_t k3_pad, cout_pad;
+  const float* bias2;
+  const float* add2; /* may be NULL */
+  const float* bias3;
+  const float* add3; /* may be NULL */
+  crdr_planes res;   /* skip connection x */
+  crdr_planes out;
+  const float* scale; /* may be NULL */
+  const float* shift; /* may be NULL */
+  int32_t precision;  /* CRDR_PREC_F16X1 */
+} crdr_bottleneck_desc;
+int crdr_bottleneck_bc(const crdr_bottleneck_desc* d, void* stream);
+
 /* fp32 NHWC [m][c] -> planes, v = x*scale[c] + shift[c] (InterpChAtt on a tensor that has no producing
  * conv: decoder input, elic_interpca_beta_cond_autoencoder.py:153-156).  scale/shift may be NULL. */
 int crdr_affine_to_planes(const float* x, int32_t x_cs, int32_t x_coff, int64_t m, int32_t c,

@@ -97,3 +97,53 @@ def test_fp16_overflow_is_flagged_not_silent():
     with pytest.raises(nv.NativeError, match="overflow"):
         nv.status_check()
     nv.status_reset()
+
+
+BN_CASES = [  # (name, n, h, w, C, mid, beta adds, gain)
+    ("g_s block 256/128 ragged beta gain", 3, 37, 50, 256, 128, True, True),
+    ("g_s block 256/128 single tile", 1, 16, 8, 256, 128, False, False),
+    ("g_s block 256/128 many tiles", 5, 64, 96, 256, 128, True, False),
+    ("192/96 partial channel block", 2, 33, 24, 192, 96, True, True),
+    ("64/32", 1, 20, 20, 64, 32, False, True),
+]
+
+
+@pytest.mark.parametrize("case", BN_CASES, ids=[c[0] for c in BN_CASES])
+def test_fused_bottleneck_tail_is_bit_identical(case):
+    """crdr_bottleneck_bc (3x3 -> ReLU -> 1x1 + skip in one launch, mid tensor in shared memory) against the same block
+    as three crdr_conv2d launches: identical bits, and both within fp16-operand tolerance of a float64 reference."""
+    import torch.nn.functional as F
+    from crdr_b200 import codec, native as nv
+    from crdr_b200.engine import Act
+    _, n, h, w, c, mid, beta, gain = case
+    g = torch.Generator().manual_seed(n * 1000 + h)
+    sd = {"a.weight": torch.randn(mid, c, 1, 1, generator=g) / c ** 0.5, "a.bias": torch.randn(mid, generator=g) * 0.1,
+          "b.weight": torch.randn(mid, mid, 3, 3, generator=g) / (9 * mid) ** 0.5, "b.bias": torch.randn(mid, generator=g) * 0.1,
+          "c.weight": torch.randn(c, mid, 1, 1, generator=g) / mid ** 0.5, "c.bias": torch.randn(c, generator=g) * 0.1}
+    blk = codec.Bottleneck(sd, ["a", "b", "c"], codec.NetCfg("cuda", X1))
+    assert blk.fused
+    x32 = torch.randn(n, c, h, w, generator=g)
+    x = Act.from_nchw(x32.cuda(), two=False)
+    vec = lambda k, s=0.3: (torch.randn(k, generator=g) * s).cuda()
+    add = (vec(mid), vec(mid), vec(c)) if beta else (None, None, None)
+    scale, shift = (vec(c).abs() + 0.5, vec(c)) if gain else (None, None)
+    nv.status_reset()
+    outs = []
+    for fused in (True, False):
+        codec.FUSE_BC[0] = fused
+        try:
+            outs.append(blk(x, add=add, scale=scale, shift=shift).hi.clone())
+        finally:
+            codec.FUSE_BC[0] = True
+    nv.status_check()
+    assert torch.equal(outs[0], outs[1]), f"fused != unfused: {(outs[0].float() - outs[1].float()).abs().max().item():.3e}"
+    xd = x.to_nchw().double().cpu()
+    cw = lambda k: sd[k].double()
+    ad = [a.double().cpu().reshape(1, -1, 1, 1) if a is not None else 0.0 for a in add]
+    t = torch.relu(F.conv2d(xd, cw("a.weight"), cw("a.bias"))) + ad[0]
+    t = torch.relu(F.conv2d(t, cw("b.weight"), cw("b.bias"), padding=1)) + ad[1]
+    ref = F.conv2d(t, cw("c.weight"), cw("c.bias")) + ad[2] + xd
+    if gain:
+        ref = ref * scale.double().cpu().reshape(1, -1, 1, 1) + shift.double().cpu().reshape(1, -1, 1, 1)
+    got = outs[0].float().permute(0, 3, 1, 2).double().cpu()
+    assert (got - ref).abs().max() / ref.abs().max() < 4e-3
