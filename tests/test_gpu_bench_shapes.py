@@ -167,7 +167,7 @@ def _demo_images():
     for n in names:
         arr = np.asarray(Image.open(os.path.join(ROOT, "tests", "golden", n)).convert("RGB"))
         t = torch.from_numpy(arr.copy()).permute(2, 0, 1).float().div(255)        # ToTensor
-        out.append((n, ((t - 0.5) / 0.5).unsqueeze(0)))                            # Normalize(.5, .5); scripts/compress.py:54-57
+        out.append((n, ((t - 0.5) / 0.5).unsqueeze(0).contiguous()))               # Normalize(.5, .5); scripts/compress.py:54-57
     return out
 
 
