@@ -178,7 +178,8 @@ class AnalysisEngine:
         self.block1, self.block2, self.block3 = blk("block1"), blk("block2"), blk("block3")
         self.attn2 = Nlam(_sub(sd, "attn2"), cfg)
         self.attn4 = Nlam(_sub(sd, "attn4"), cfg)
-        self.gains = _gains(sd, 9, device)
+        # ElicEncoder (stage 1, elic_autoencoder.py:33-72) has no InterpChAtt layers: no gains, q is ignored
+        self.gains = _gains(sd, 9, device) if "interp_ca_list.0.weight" in sd else None
         self.out_ch = sd["conv4.weight"].shape[0]
 
     @staticmethod
@@ -189,7 +190,7 @@ class AnalysisEngine:
 
     def run(self, img, q):
         """img: Act (n, H/2, W/2, 128) image patches (crdr_image_to_patches) -> (y planes Act, y fp32 NHWC tensor)."""
-        g = [gn.vectors(q) for gn in self.gains]
+        g = [gn.vectors(q) for gn in self.gains] if self.gains else [(None, None)] * 9
         x = self.conv1(img, scale=g[0][0], shift=g[0][1])
         x = self._blocks(self.block1, x, g[1])
         x = self.conv2(x, scale=g[2][0], shift=g[2][1])
@@ -417,7 +418,7 @@ class SynthesisEngine:
     applied while converting y_hat to planes.  The beta embedding (fourier_cond.py:21-37), its MLP and
     the 27 projections are evaluated once per beta and enter as per-channel epilogue vectors."""
 
-    def __init__(self, sd, max_beta, L, use_pi, include_x, use_tanh, device, precision=X1,
+    def __init__(self, sd, max_beta=0.0, L=0, use_pi=False, include_x=False, use_tanh=False, device="cuda", precision=X1,
                  engine=nv.ENGINE_TCGEN05):
         if use_tanh:
             raise NotImplementedError("use_tanh=True decoders are not lowered (crdr.yaml uses use_tanh: False)")
@@ -430,15 +431,20 @@ class SynthesisEngine:
         self.attn2 = Nlam(_sub(sd, "attn2"), cfg)
         self.conv4p = self._phase_packed(sd["conv4.weight"], sd["conv4.bias"], cfg)
         self.blocks, self.proj = {}, {}
+        # ElicDecoder / ElicInterpCaDecoder (stages 1 / 2: elic_autoencoder.py:75-119, elic_interpca_autoencoder.py:59-97)
+        # have no beta conditioning; ElicDecoder has no InterpChAtt gains either
+        self.has_cond = "mlp.0.weight" in sd
         for b in ("block1", "block2", "block3"):
             self.blocks[b] = [Bottleneck(_sub(sd, f"{b}.block{i}"), ["conv.0", "conv.2", "conv.4"], cfg) for i in range(3)]
-            # beta embedding MLP and the 27 projections are GEMVs evaluated once per beta: host side, results uploaded
-            self.proj[b] = [[(sd[f"{b}.block{i}.proj_{k}.weight"].detach().to(device="cpu", dtype=torch.float32).flatten(1),
-                              sd[f"{b}.block{i}.proj_{k}.bias"].detach().to(device="cpu", dtype=torch.float32))
-                             for k in (1, 2, 3)] for i in range(3)]
-        self.mlp = [(sd[f"mlp.{i}.weight"].detach().to(device="cpu", dtype=torch.float32),
-                     sd[f"mlp.{i}.bias"].detach().to(device="cpu", dtype=torch.float32)) for i in (0, 2)]
-        self.gains = _gains(sd, 9, device)
+            if self.has_cond:
+                # beta embedding MLP and the 27 projections are GEMVs evaluated once per beta: host side, results uploaded
+                self.proj[b] = [[(sd[f"{b}.block{i}.proj_{k}.weight"].detach().to(device="cpu", dtype=torch.float32).flatten(1),
+                                  sd[f"{b}.block{i}.proj_{k}.bias"].detach().to(device="cpu", dtype=torch.float32))
+                                 for k in (1, 2, 3)] for i in range(3)]
+        if self.has_cond:
+            self.mlp = [(sd[f"mlp.{i}.weight"].detach().to(device="cpu", dtype=torch.float32),
+                         sd[f"mlp.{i}.bias"].detach().to(device="cpu", dtype=torch.float32)) for i in (0, 2)]
+        self.gains = _gains(sd, 9, device) if "interp_ca_list.0.weight" in sd else None
         self.max_beta, self.L, self.include_x = float(max_beta), int(L), bool(include_x)
         self.freq = torch.pow(torch.Tensor([2]), torch.arange(L))
         if use_pi:
@@ -469,6 +475,8 @@ class SynthesisEngine:
         return Conv({"w.weight": wc, "w.bias": bc}, "w", cfg, padding=1)
 
     def cond_vectors(self, beta):
+        if not self.has_cond:
+            return {b: [(None, None, None)] * 3 for b in self.blocks}
         beta = float(beta)
         if beta not in self._beta_cache:
             if not (0 <= beta <= self.max_beta):
@@ -494,12 +502,12 @@ class SynthesisEngine:
 
     def run(self, yhat32, q, beta):
         """yhat32: fp32 NHWC [n, h, w, C] -> phase-packed fp32 image [n, 8h, 8w, 16] (see _phase_packed)."""
-        g = [gn.vectors(q) for gn in self.gains]
+        g = [gn.vectors(q) for gn in self.gains] if self.gains else [(None, None)] * 9
         cond = self.cond_vectors(beta)
         n, h, w, c = yhat32.shape
         x = Act.empty(n, h, w, c, two=self.two, device=yhat32.device)
-        nv.check(nv.lib().crdr_affine_to_planes(yhat32.data_ptr(), c, 0, n * h * w, c, g[0][0].data_ptr(),
-                                                g[0][1].data_ptr(), x.planes(0), nv.stream_handle()))
+        nv.check(nv.lib().crdr_affine_to_planes(yhat32.data_ptr(), c, 0, n * h * w, c, nv.ptr(g[0][0]), nv.ptr(g[0][1]),
+                                                x.planes(0), nv.stream_handle()))
         x = self.attn1(x, scale=g[1][0], shift=g[1][1])
         x = self.conv1(x, scale=g[2][0], shift=g[2][1])
         x = self._blocks("block1", x, cond, g[3])

@@ -31,6 +31,28 @@ class MultiRateHeaderHandler:
         return {"img_size": (h, w), "max_sample": m, "rate_ind": q / 16}
 
 
+class HeaderHandler:
+    """Single-rate header of the stage-1 models (codec_utils.py:12-58): <H:u16><W:u16><max|y_hat|:u8>."""
+
+    def __init__(self, use_non_zero_ind=False):
+        if use_non_zero_ind:
+            raise NotImplementedError("use_non_zero_ind headers are not used by any shipped config")
+
+    def encode(self, img_size, y_hat=None, rate_ind=None, max_abs=None):
+        h, w = img_size
+        if not (isinstance(h, int) and isinstance(w, int)):
+            raise AssertionError("img_size must be two ints")
+        if max_abs is None:
+            max_abs = float(y_hat.abs().max())
+        if not (0 <= h <= 65535 and 0 <= w <= 65535):
+            raise OverflowError(f"header field out of range (H={h}, W={w})")
+        return struct.pack("<HHB", h, w, int(max_abs) & 0xFF)
+
+    def decode(self, header):
+        h, w, m = struct.unpack("<HHB", header[:5])
+        return {"img_size": (h, w), "max_sample": m, "rate_ind": None}
+
+
 def save_byte_strings(save_path, string_list):
     with open(save_path, "wb") as f:
         for s in string_list:

@@ -21,7 +21,7 @@ import torch.nn as nn
 from . import native as nv
 from . import rans
 from .codec import GaussianParams
-from .codec_utils import MultiRateHeaderHandler
+from .codec_utils import HeaderHandler, MultiRateHeaderHandler
 from .engine import Act
 from .entropy import EntropyBottleneck, GaussianMeanScaleConditional, get_scale_table
 from .logger import get_root_logger
@@ -81,6 +81,8 @@ class CodecEngine:
         uint8 index copies for the host coder."""
         L, st = nv.lib(), nv.stream_handle()
         n, _, h, w = images.shape
+        if not images.is_contiguous():
+            raise ValueError("analysis() reads the image through a raw pointer: pass a contiguous NCHW tensor")
         hp, wp = self.padded(h, w)
         dev = images.device
         img = Act.empty(n, hp // 2, wp // 2, 128, two=True, device=dev)   # im2col of g_a conv1 fused with the reflect pad
@@ -152,7 +154,7 @@ class CodecEngine:
         """Fill the per-quality / per-beta vector caches on the current stream (before work fans out to side streams)."""
         if q is not None:
             for net in (self.ga, self.gs):
-                for gn in net.gains:
+                for gn in net.gains or ():
                     gn.vectors(q)
         if beta is not None:
             self.gs.cond_vectors(beta)
@@ -276,7 +278,7 @@ class _CodecModelBase(nn.Module):
         return bits, bits / num_pixel
 
     def codec_setup(self):
-        self.header_handler = MultiRateHeaderHandler(use_non_zero_ind=False)
+        self.header_handler = (MultiRateHeaderHandler if self.uses_rate else HeaderHandler)(use_non_zero_ind=False)
         self.entropy_model_z.update(force=True)
         self.entropy_model_y.update_scale_table(get_scale_table(), force=True)
         self.yC, self.zC = self.encoder.latent_ch, self.hyperencoder.latent_ch
@@ -285,13 +287,23 @@ class _CodecModelBase(nn.Module):
         self.invalidate_engine()
 
 
-@MODEL_REGISTRY.register()
-class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
+class _CharmModelCore(_CodecModelBase):
+    """The three ChARM models of the reference share everything but their conditioning inputs:
+    HyperpriorCharmModel (stage 1: none), InterpCaHyperpriorCharmModel (stage 2: quality index q) and
+    BetaCondInterpCaHyperpriorCharmModel (stage 3 / crdr.yaml: q and the realism weight beta).  The core takes
+    (rate_ind, beta) everywhere; the registered classes below restore the reference's public signatures."""
+    uses_rate = True
+    uses_beta = True
+
     def _build_subnets(self):
         sn = self.opt.subnet
-        self.rate_level = sn.encoder.rate_level
-        assert sn.encoder.rate_level == sn.decoder.rate_level
-        self.max_beta = float(sn.decoder.max_beta)
+        if self.uses_rate:
+            self.rate_level = sn.encoder.rate_level
+            assert sn.encoder.rate_level == sn.decoder.rate_level
+            if self.opt.get("batch_rate_ind_sample", False):
+                raise NotImplementedError("batch_rate_ind_sample is not supported yet.")   # interpca_hyperprior_model.py:25-26
+        if self.uses_beta:
+            self.max_beta = float(sn.decoder.max_beta)
         self.encoder = build_subnet(sn.encoder, "encoder")
         self.decoder = build_subnet(sn.decoder, "decoder")
         self.hyperencoder = build_subnet(sn.hyperencoder, "hyperencoder")
@@ -311,6 +323,8 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
 
     @staticmethod
     def _q(rate_ind):
+        if rate_ind is None:
+            return None
         if isinstance(rate_ind, torch.Tensor):
             assert rate_ind.numel() == 1, "one quality index per batch (batch_rate_ind_sample is unsupported upstream)"
             return float(rate_ind.reshape(-1)[0].item())
@@ -452,7 +466,7 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
                                    self.entropy_model_y.coder_tables(), coder_threads)
         out = []
         for i in range(n):
-            header = self.header_handler.encode((h, w), rate_ind=q, max_abs=float(y_max[i]))
+            header = self.header_handler.encode((h, w), rate_ind=q, max_abs=float(y_max[i]))   # q is None for single-rate models
             r = {"string_list": [header, z_strs[i], y_strs[i]],
                  "pred_y_bit": float(y_bits[i]), "pred_y_bpp": float(y_bits[i]) / (h * w),
                  "pred_z_bit": float(z_bits[i]), "pred_z_bpp": float(z_bits[i]) / (h * w)}
@@ -559,10 +573,82 @@ class BetaCondInterpCaHyperpriorCharmModel(_CodecModelBase):
         for idx, data in enumerate(dataloader):
             row = {"idx": idx + 1}
             for q in range(self.rate_level):
-                out = self.run_model(**data, rate_ind=float(q), beta=beta, is_train=False)
+                out = _CharmModelCore.run_model(self, **data, rate_ind=float(q), beta=beta, is_train=False)
                 row[f"bpp_{q + 1}"] = out["bpp"].mean().item()
                 row[f"psnr_{q + 1}"] = calc_psnr(out["real_images"], out["fake_images"], 255)
             rows.append(row)
+            if idx + 1 >= min(len(dataloader), max_sample_size):
+                break
+        return pd.json_normalize(rows)
+
+
+@MODEL_REGISTRY.register()
+class BetaCondInterpCaHyperpriorCharmModel(_CharmModelCore):
+    """config/crdr.yaml, config/crdr_stage_3.yaml (beta_cond_interpca_hyperprior_charm_model.py:13-149): the core's
+    signatures are this model's."""
+
+
+@MODEL_REGISTRY.register()
+class InterpCaHyperpriorCharmModel(_CharmModelCore):
+    """config/crdr_stage_2.yaml: variable rate, no realism conditioning (interpca_hyperprior_charm_model.py:22-146,
+    interpca_hyperprior_model.py:31-62)."""
+    uses_beta = False
+
+    def forward(self, real_images, rate_ind, is_train=True):
+        return super().forward(real_images, rate_ind, None, is_train=is_train)
+
+    def run_model(self, real_images, rate_ind=None, is_train=True):
+        out = super().run_model(real_images, rate_ind=rate_ind, beta=0.0, is_train=is_train)
+        out.pop("beta", None)
+        return out
+
+    def decompress_batch(self, string_lists, coder_threads=0, out_uint8=False):
+        return super().decompress_batch(string_lists, beta=None, coder_threads=coder_threads, out_uint8=out_uint8)
+
+    def decompress(self, string_list):
+        return self.decompress_batch([string_list])
+
+    def validation(self, dataloader, max_sample_size, save_img=False, save_dir="", use_tqdm=False):
+        return super().validation(dataloader, max_sample_size, beta=0.0)
+
+
+@MODEL_REGISTRY.register()
+class HyperpriorCharmModel(_CharmModelCore):
+    """config/crdr_stage_1.yaml: single rate (hyperprior_charm_model.py:21-147, hyperprior_model.py:38-58); the
+    5-byte header carries no quality index."""
+    uses_rate = False
+    uses_beta = False
+
+    def forward(self, real_images, is_train=True):
+        return super().forward(real_images, None, None, is_train=is_train)
+
+    def run_model(self, real_images, is_train=True):
+        out = super().run_model(real_images, rate_ind=0.0, beta=0.0, is_train=is_train)
+        out.pop("beta", None)
+        out.pop("rate_ind", None)
+        return out
+
+    def compress_batch(self, real_images, return_tensors=False, coder_threads=0):
+        return super().compress_batch(real_images, None, return_tensors=return_tensors, coder_threads=coder_threads)
+
+    def compress(self, real_images):
+        n = real_images.shape[0]
+        assert n == 1, f"In compress mode, batchsize must be 1, but {n}"
+        return self.compress_batch(real_images, return_tensors=True)[0]
+
+    def decompress_batch(self, string_lists, coder_threads=0, out_uint8=False):
+        return super().decompress_batch(string_lists, beta=None, coder_threads=coder_threads, out_uint8=out_uint8)
+
+    def decompress(self, string_list):
+        return self.decompress_batch([string_list])
+
+    def validation(self, dataloader, max_sample_size, save_img=False, save_dir="", use_tqdm=False):
+        import pandas as pd
+        from .img_utils import calc_psnr
+        rows = []
+        for idx, data in enumerate(dataloader):
+            out = self.run_model(**data, is_train=False)
+            rows.append({"idx": idx + 1, "bpp": out["bpp"].mean().item(), "psnr": calc_psnr(out["real_images"], out["fake_images"], 255)})
             if idx + 1 >= min(len(dataloader), max_sample_size):
                 break
         return pd.json_normalize(rows)

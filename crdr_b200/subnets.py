@@ -74,6 +74,30 @@ def _gain_list(channels, rate_level, ca_kwargs):
 
 
 @ENCODER_REGISTRY.register()
+class ElicEncoder(nn.Module):
+    """Stage-1 analysis transform without InterpChAtt (elic_autoencoder.py:33-72; config/_base_/model/elic_charm.yaml)."""
+
+    def __init__(self, in_ch=3, out_ch=192, main_ch=192, block_mid_ch=192, num_blocks=3, res_in_res=False):
+        super().__init__()
+        if in_ch != 3 or num_blocks != 3 or res_in_res:
+            raise NotImplementedError("lowered analysis transform expects RGB input, 3 blocks per stage, no res_in_res")
+        m = main_ch
+        self.conv1 = _conv(in_ch, m, 5, 2)
+        self.block1 = _block_group(m, block_mid_ch, num_blocks)
+        self.conv2 = _conv(m, m, 5, 2)
+        self.block2 = _block_group(m, block_mid_ch, num_blocks)
+        self.attn2 = _nlam(m)
+        self.conv3 = _conv(m, m, 5, 2)
+        self.block3 = _block_group(m, block_mid_ch, num_blocks)
+        self.conv4 = _conv(m, out_ch, 5, 2)
+        self.attn4 = _nlam(out_ch)
+        self.num_downscale, self.latent_ch = 4, out_ch
+
+    def lower(self, device, **kw):
+        return codec.AnalysisEngine(dict(self.state_dict()), device, **kw)
+
+
+@ENCODER_REGISTRY.register()
 class ElicInterpCaEncoder(nn.Module):
     def __init__(self, rate_level, in_ch=3, out_ch=192, main_ch=192, block_mid_ch=192, num_blocks=3, ca_kwargs={}):
         super().__init__()
@@ -101,6 +125,44 @@ def _n002_init(module):
     if isinstance(module, (nn.Conv2d, nn.ConvTranspose2d, nn.Linear)):
         module.weight.data.normal_(0.0, 0.02)
         module.bias.data.fill_(0)
+
+
+@DECODER_REGISTRY.register()
+class ElicDecoder(nn.Module):
+    """Stage-1 synthesis transform (elic_autoencoder.py:75-119)."""
+
+    def __init__(self, in_ch=192, out_ch=3, main_ch=192, block_mid_ch=192, num_blocks=3, use_tanh=True,
+                 pixel_shuffle=False, res_in_res=False):
+        super().__init__()
+        if pixel_shuffle or res_in_res or num_blocks != 3 or out_ch != 3:
+            raise NotImplementedError("only the shipped decoder variant (ConvTranspose up-sampling) is lowered")
+        m = main_ch
+        self.attn1 = _nlam(in_ch)
+        self.conv1 = _deconv(in_ch, m)
+        self.block1 = _block_group(m, block_mid_ch, num_blocks)
+        self.conv2 = _deconv(m, m)
+        self.attn2 = _nlam(m)
+        self.block2 = _block_group(m, block_mid_ch, num_blocks)
+        self.conv3 = _deconv(m, m)
+        self.block3 = _block_group(m, block_mid_ch, num_blocks)
+        self.conv4 = _deconv(m, out_ch)
+        self.use_tanh = use_tanh
+
+    def lower(self, device, **kw):
+        return codec.SynthesisEngine(dict(self.state_dict()), use_tanh=self.use_tanh, device=device, **kw)
+
+
+@DECODER_REGISTRY.register()
+class ElicInterpCaDecoder(ElicDecoder):
+    """Stage-2 synthesis transform: ElicDecoder with an InterpChAtt in front of every layer
+    (elic_interpca_autoencoder.py:59-97)."""
+
+    def __init__(self, rate_level, in_ch=192, out_ch=3, main_ch=192, block_mid_ch=192, num_blocks=3, use_tanh=True,
+                 pixel_shuffle=False, ca_kwargs={}):
+        super().__init__(in_ch=in_ch, out_ch=out_ch, main_ch=main_ch, block_mid_ch=block_mid_ch, num_blocks=num_blocks,
+                         use_tanh=use_tanh, pixel_shuffle=pixel_shuffle)
+        self.interp_ca_list = _gain_list([in_ch] * 2 + [main_ch] * 7, rate_level, ca_kwargs)
+        self.rate_level = rate_level
 
 
 @DECODER_REGISTRY.register()

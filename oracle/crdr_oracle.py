@@ -54,6 +54,8 @@ def deconv(sd, name, x, stride=2, pad=2, opad=1):
 
 
 def interp_gain(sd, i, x, q):
+    if f"interp_ca_list.{i}.weight" not in sd:   # stage-1 transforms (ElicEncoder / ElicDecoder) have no InterpChAtt
+        return x
     w, b = sd[f"interp_ca_list.{i}.weight"], sd[f"interp_ca_list.{i}.bias"]
     ind = torch.tensor([q], dtype=torch.float)
     l = torch.floor(ind)
@@ -126,6 +128,8 @@ def h_s(sd, z_hat):
 
 def beta_cond(sd, beta):
     d = sub(sd, "decoder")
+    if "mlp.0.weight" not in d:                  # stage-1 / stage-2 decoders: no beta conditioning
+        return None
     freq = torch.pow(torch.Tensor([2]), torch.arange(CFG["L"]))
     nb = (torch.Tensor([beta]).float() / CFG["max_beta"] - 0.5) * 2
     emb = torch.cat([torch.sin(nb * freq), torch.cos(nb * freq)], dim=0).unsqueeze(0)
@@ -244,7 +248,10 @@ def compress(sd, x, q, eb=None, gc=None):
     a = analysis(sd, x, q, eb, gc)
     z_str = eb.compress(a["z"])[0]
     y_str = gc.compress(a["y"], a["y_idx"], means=a["mu"])[0]
-    header = struct.pack("<HHBB", h, w, int(torch.max(torch.abs(a["y_hat"]))), int(float(q) * 16))
+    if q is None:   # single-rate models: HeaderHandler (codec_utils.py:22-39)
+        header = struct.pack("<HHB", h, w, int(torch.max(torch.abs(a["y_hat"]))))
+    else:
+        header = struct.pack("<HHBB", h, w, int(torch.max(torch.abs(a["y_hat"]))), int(float(q) * 16))
     a.update(string_list=[header, z_str, y_str], pred_y_bit=bits_of(a["y_lik"]), pred_z_bit=bits_of(a["z_lik"]))
     a["pred_y_bpp"], a["pred_z_bpp"] = a["pred_y_bit"] / (h * w), a["pred_z_bit"] / (h * w)
     return a
@@ -254,8 +261,11 @@ def compress(sd, x, q, eb=None, gc=None):
 def decompress(sd, string_list, beta, eb=None, gc=None):
     if eb is None:
         eb, gc = entropy_models(sd)
-    h, w, _, q16 = struct.unpack("<HHBB", string_list[0][:6])
-    q = q16 / 16
+    if len(string_list[0]) == 5:
+        (h, w, _), q = struct.unpack("<HHB", string_list[0][:5]), None
+    else:
+        h, w, _, q16 = struct.unpack("<HHBB", string_list[0][:6])
+        q = q16 / 16
     s = CFG["stride"]
     hz, wz = int(np.ceil(h / s)), int(np.ceil(w / s))
     z_hat = eb.decompress([string_list[1]], (hz, wz))

@@ -7,9 +7,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def crdr_opt(device="cuda:0"):
+def crdr_opt(device="cuda:0", config="crdr.yaml"):
     from crdr_b200.config import BaseConfig
-    return BaseConfig.fromfile(os.path.join(ROOT, "config", "crdr.yaml"), device=device, is_train=False)
+    return BaseConfig.fromfile(os.path.join(ROOT, "config", config), device=device, is_train=False)
 
 
 def calibrate_(sd, seed=0):
@@ -22,18 +22,22 @@ def calibrate_(sd, seed=0):
             v.copy_(torch.exp(math.log(0.05) + u * (math.log(24.0) - math.log(0.05))))
         if k.startswith("context_model.mean_slice_transforms.") and k.endswith("model.4.bias"):
             v.copy_(torch.randn(v.shape, generator=g) * 2.0)
-    sd["encoder.interp_ca_list.8.weight"].add_(30.0)   # softplus(w) ~ 30.5
+    if "encoder.interp_ca_list.8.weight" in sd:
+        sd["encoder.interp_ca_list.8.weight"].add_(30.0)   # softplus(w) ~ 30.5
+    else:   # stage-1 encoder (no InterpChAtt): raise the latent gain through the last gate convolution's trunk instead
+        for k in ("encoder.attn4.trunk_block.2.c3.weight", "encoder.attn4.trunk_block.2.c3.bias"):
+            sd[k].mul_(60.0)
     sd["entropy_model_z.quantiles"][:, 0, 0] = -6.0
     sd["entropy_model_z.quantiles"][:, 0, 2] = 7.0
     sd["entropy_model_z.quantiles"][:, 0, 1] = torch.rand(sd["entropy_model_z.quantiles"].shape[0], generator=g) - 0.5
     return sd
 
 
-def build_model(seed=0, calibrated=True, device="cuda:0"):
+def build_model(seed=0, calibrated=True, device="cuda:0", config="crdr.yaml"):
     """(model, state_dict on CPU).  The model's parameters stay on the CPU; its engine lives on `device`."""
     from crdr_b200.model import build_comp_model
     torch.manual_seed(seed)
-    model = build_comp_model(crdr_opt(device))
+    model = build_comp_model(crdr_opt(device, config))
     if calibrated:
         with torch.no_grad():
             calibrate_(dict(model.state_dict()), seed)

@@ -399,3 +399,37 @@ def test_compact_symbol_range_flag():
     assert torch.equal(idx8.int(), idx) and torch.equal(sym16.int().clamp(-32768, 32767), sym.clamp(-32768, 32767))
     nv.check(nv.lib().crdr_status_clear_bits(nv.FLAG_SYM_RANGE, nv.stream_handle()), counts=False)
     nv.status_check()
+
+
+@pytest.mark.parametrize("stage", [1, 2], ids=["stage1_HyperpriorCharmModel", "stage2_InterpCaHyperpriorCharmModel"])
+def test_stage_model_variants_against_oracle(oracle, stage):
+    """the stage-1 / stage-2 models (config/crdr_stage_{1,2}.yaml) on the same engines, with the
+    reference's signatures (no beta; stage 1: no rate_ind and the 5-byte header).  Encode side, streams, both decoders
+    and eval run_model against the CPU oracle (itself pinned to the reference's classes, test_oracle_vs_reference.py)."""
+    import fixtures
+    from crdr_b200 import native as nv
+    model, sd = fixtures.build_model(seed=3, calibrated=True, config=f"crdr_stage_{stage}.yaml")
+    assert type(model).__name__ == ("HyperpriorCharmModel" if stage == 1 else "InterpCaHyperpriorCharmModel")
+    h, w = 80, 112
+    x = fixtures.image(1, h, w, seed=40 + stage)
+    q = None if stage == 1 else 1.75
+    eb, gc = oracle.entropy_models(sd)
+    o = oracle.compress(sd, x, q, eb, gc)
+    out = model.compress(x) if stage == 1 else model.compress(x, q)
+    a = model.engine().analysis(x.cuda(), q)
+    nv.status_check()
+    assert (a["y_sym"].cpu() == o["y_sym"]).float().mean().item() >= SYMBOL_MATCH
+    assert (a["y_idx"].cpu() == o["y_idx"]).float().mean().item() >= SYMBOL_MATCH
+    assert (a["z_sym"].cpu() == o["z_sym"]).float().mean().item() >= SYMBOL_MATCH
+    assert len(out["string_list"][0]) == (5 if stage == 1 else 6) and out["string_list"][0] == o["string_list"][0]
+    ref_bits = o["pred_y_bit"] + o["pred_z_bit"]
+    assert abs(out["pred_y_bit"] + out["pred_z_bit"] - ref_bits) <= BPP_RTOL * ref_bits + 1e-3
+    img_m, z_hat, y_hat = model.decompress(out["string_list"])
+    assert torch.equal(y_hat, out["y_hat"]) and torch.equal(z_hat, out["z_hat"])
+    img_o, _, y_hat_o, _ = oracle.decompress(sd, o["string_list"], None, eb, gc)
+    assert abs(oracle.psnr_u8(x, img_m.cpu()) - oracle.psnr_u8(x, img_o)) <= PSNR_ATOL
+    if out["string_list"] == o["string_list"]:
+        assert (y_hat.cpu() - y_hat_o).abs().max() <= 1e-4 * max(1.0, float(y_hat_o.abs().max()))
+    rm = model.run_model(x, is_train=False) if stage == 1 else model.run_model(x, rate_ind=q, is_train=False)
+    assert "beta" not in rm and torch.equal(rm["fake_images"], img_m)
+    assert abs(rm["bpp"].item() * h * w - ref_bits) <= BPP_RTOL * ref_bits + 1e-3

@@ -66,3 +66,50 @@ def test_forward_eval_equal(oracle, ref_model):
     assert torch.equal(a["y_hat"], ref["quantized_code"]["y"])
     assert torch.equal(a["y_lik"], ref["q_likelihoods"]["y"])
     assert torch.equal(fake, ref["fake_images"])
+
+
+@pytest.mark.parametrize("stage", [1, 2])
+def test_stage_models_bit_equal_and_same_layout(oracle, stage):
+    """HyperpriorCharmModel (crdr_stage_1.yaml) and InterpCaHyperpriorCharmModel (crdr_stage_2.yaml).
+    The oracle follows the unmodified reference bit for bit, and this package's parameter tree has the reference's
+    state_dict keys, shapes and dtypes in the reference's order."""
+    import fixtures
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "shims"))
+    saved = {k: v for k, v in sys.modules.items() if k == "src" or k.startswith("src.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, REFERENCE)
+    try:
+        import src  # noqa: F401  (the reference's package)
+        from src.models import build_comp_model
+        from src.utils.options import BaseConfig
+        cfg, _, _ = BaseConfig._file2dict_yaml(os.path.join(REFERENCE, "config", f"crdr_stage_{stage}.yaml"))
+        cfg["device"], cfg["is_train"] = "cpu", False
+        torch.manual_seed(4321)
+        ref = build_comp_model(BaseConfig(cfg)).eval()
+        with torch.no_grad():
+            fixtures.calibrate_(dict(ref.state_dict()), 0)
+        ref.codec_setup()
+        sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+        x = torch.rand(1, 3, 70, 96, generator=torch.Generator().manual_seed(9)) * 2 - 1
+        q = None if stage == 1 else 2.5
+        out = ref.compress(x) if stage == 1 else ref.compress(x, rate_ind=q)
+        mine = oracle.compress(sd, x, q)
+        assert mine["string_list"] == out["string_list"]
+        assert torch.equal(mine["y_hat"], out["y_hat"]) and torch.equal(mine["y_lik"], out["y_likelihood"])
+        img_r, z_r, y_r = ref.decompress(out["string_list"])
+        img_o, z_o, y_o, _ = oracle.decompress(sd, mine["string_list"], None)
+        assert torch.equal(img_o, img_r) and torch.equal(y_o, y_r) and torch.equal(z_o, z_r)
+    finally:
+        sys.path.remove(REFERENCE)
+        for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    from crdr_b200.model import build_comp_model as build_mine
+    m = build_mine(fixtures.crdr_opt("cuda:0", f"crdr_stage_{stage}.yaml"))
+    with torch.no_grad():
+        fixtures.calibrate_(dict(m.state_dict()), 0)   # same quantiles as the reference instance -> same table shapes
+    m.codec_setup()
+    got = {k: (tuple(v.shape), v.dtype) for k, v in m.state_dict().items()}
+    want = {k: (tuple(v.shape), v.dtype) for k, v in sd.items()}
+    assert list(got) == list(want) and got == want
