@@ -161,14 +161,16 @@ def _gains(sd, count, device):
 class AnalysisEngine:
     """g_a: ElicInterpCaEncoder.forward (elic_interpca_autoencoder.py:22-56; layers elic_autoencoder.py:42-56).
     Every InterpChAtt that follows a layer is folded into that layer's last epilogue."""
+    PATCH_CH = 80   # channels of the im2col'd image (crdr_image_to_patches): 75 + zero padding to a multiple of 16
 
     def __init__(self, sd, device, precision=X3, engine=nv.ENGINE_TCGEN05):
         cfg = NetCfg(device, precision, engine)
         self.cfg = cfg
         # conv1 (5x5, stride 2, 3 -> C; elic_autoencoder.py:42) runs as a 1x1 convolution over the im2col'd image written
-        # by crdr_image_to_patches: patch channel (kh*5+kw)*3+c, 75 real + 53 zero = 128 = two K blocks on the patch engine
+        # by crdr_image_to_patches: patch channel (kh*5+kw)*3+c, 75 real + 5 zero = 80 channels = one full K block and one
+        # K step of a second (the TMA box of that block zero-fills past channel 80, so the tensor stays 80 wide)
         w1 = sd["conv1.weight"]                                        # (C, 3, 5, 5)
-        wp = torch.zeros(w1.shape[0], 128, 1, 1, dtype=w1.dtype)
+        wp = torch.zeros(w1.shape[0], self.PATCH_CH, 1, 1, dtype=w1.dtype)
         wp[:, :75, 0, 0] = w1.permute(0, 2, 3, 1).reshape(w1.shape[0], 75)
         self.conv1 = Conv({"w.weight": wp, "w.bias": sd["conv1.bias"]}, "w", cfg)
         self.conv2 = Conv(sd, "conv2", cfg, stride=2, padding=2)
@@ -329,7 +331,7 @@ class CharmEngine:
                     out_coff=self.off_y + s * self.sc, out_f32=yhat32, out_f32_coff=s * self.sc)
 
     def gauss_desc(self, gp, T, s, cnt, n, hw, ms, y32=None, yq32=None, sym=None, idx=None, lik=None, sym16=None,
-                   idx8=None):
+                   idx8=None, noise=None, lik_noisy=None):
         """Descriptor covering `cnt` consecutive slices starting at slice s."""
         d = nv.GaussDesc()
         if y32 is not None:
@@ -346,12 +348,17 @@ class CharmEngine:
         d.likelihood = lik.data_ptr() if lik is not None else None
         d.symbols16 = sym16.data_ptr() if sym16 is not None else None
         d.indexes8 = idx8.data_ptr() if idx8 is not None else None
+        d.noise = noise.data_ptr() if noise is not None else None
+        d.likelihood_noisy = lik_noisy.data_ptr() if lik_noisy is not None else None
         d.c_total, d.nchw_coff = self.yc, s * self.sc
         return d
 
-    def encode(self, T, y32, gp, compact=False):
+    def encode(self, T, y32, gp, compact=False, noise=None):
         """Encoder-side pass.  Returns y_hat fp32 NHWC, symbols / indexes int32 NCHW, likelihood fp32 NCHW and, with
-        ``compact``, the int16 symbols / uint8 indexes copies the host range coder reads."""
+        ``compact``, the int16 symbols / uint8 indexes copies the host range coder reads.  ``noise`` (NCHW fp32, uniform
+        in [-1/2, 1/2)) selects the training-mode forward (minnen20_charm_context_model.py:88-141 with is_train=True): the
+        likelihood of y + noise is appended to the result; y_hat / likelihood are then the straight-through forward values
+        and the quantised likelihoods (q_likelihoods)."""
         n, h, w = T.n, T.h, T.w
         dev = T.hi.device
         ms = torch.empty((n, h, w, 2 * self.yc), dtype=torch.float32, device=dev)
@@ -362,15 +369,18 @@ class CharmEngine:
         lik = torch.empty((n, self.yc, h, w), dtype=torch.float32, device=dev)
         sym16 = torch.empty((n, self.yc, h, w), dtype=torch.int16, device=dev) if compact else None
         idx8 = torch.empty((n, self.yc, h, w), dtype=torch.uint8, device=dev) if compact else None
+        lik_noisy = torch.empty((n, self.yc, h, w), dtype=torch.float32, device=dev) if noise is not None else None
         st, L = nv.stream_handle(), nv.lib()
         for grp in self.groups():
             for s in grp:
                 self.params(T, s, ms)
             d = self.gauss_desc(gp, T, grp[0], len(grp), n, h * w, ms, y32=y32, yq32=yq32, sym=sym, idx=idx, lik=lik,
-                                sym16=sym16, idx8=idx8)
+                                sym16=sym16, idx8=idx8, noise=noise, lik_noisy=lik_noisy)
             nv.check(L.crdr_gauss_quantize(C.byref(d), st))
             for s in grp:
                 self.refine(T, s, yq32, yhat32)
+        if noise is not None:
+            return yhat32, sym, idx, lik, lik_noisy
         if compact:
             return yhat32, sym, idx, lik, sym16, idx8
         return yhat32, sym, idx, lik

@@ -63,7 +63,7 @@ int affine_to_planes_launch(const float* x, int x_cs, int x_coff, int64_t m, int
 int image_to_planes_launch(const float* img, int n, int h, int w, int hp, int wp, crdr_planes out, cudaStream_t st);
 int image_to_patches_launch(const float* img, int n, int h, int w, int hp, int wp, crdr_planes out, cudaStream_t st);
 int planes_to_image_launch(const float* x, int x_cs, int n, int hp, int wp, int h, int w, float* img, cudaStream_t st);
-int phases_to_image_launch(const float* x, int x_cs, int n, int hb, int wb, int h, int w, float* img, cudaStream_t st);
+int phases_to_image_launch(const float* x, int x_cs, int n, int hb, int wb, int h, int w, float* img, int clamp, cudaStream_t st);
 int image_u8_to_patches_launch(const uint8_t* img, int n, int h, int w, int hp, int wp, crdr_planes out, cudaStream_t st);
 int phases_to_image_u8_launch(const float* x, int x_cs, int n, int hb, int wb, int h, int w, uint8_t* img, cudaStream_t st);
 int max_abs_batch_launch(const float* x, int n, int64_t per, float* out, cudaStream_t st);
@@ -173,7 +173,12 @@ int crdr_planes_to_image(const float* x, int32_t x_cs, int32_t n, int32_t hp, in
 
 int crdr_phases_to_image(const float* x, int32_t x_cs, int32_t n, int32_t hb, int32_t wb, int32_t h, int32_t w,
                          float* img, void* stream) {
-  return phases_to_image_launch(x, x_cs, n, hb, wb, h, w, img, (cudaStream_t)stream);
+  return phases_to_image_launch(x, x_cs, n, hb, wb, h, w, img, 1, (cudaStream_t)stream);
+}
+
+int crdr_phases_to_image_ex(const float* x, int32_t x_cs, int32_t n, int32_t hb, int32_t wb, int32_t h, int32_t w,
+                            float* img, int32_t clamp, void* stream) {
+  return phases_to_image_launch(x, x_cs, n, hb, wb, h, w, img, clamp, (cudaStream_t)stream);
 }
 
 int crdr_image_u8_to_patches(const uint8_t* img, int32_t n, int32_t h, int32_t w, int32_t hp, int32_t wp, crdr_planes out,

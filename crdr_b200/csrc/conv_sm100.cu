@@ -1796,7 +1796,12 @@ int conv2d_launch(const crdr_conv_desc* dp, cudaStream_t stream) {
       if (want < 2) want = 2;
       if (want > kMaxPatchStages) want = kMaxPatchStages;
       int ps = want;
-      while (ps > 1 && (uint32_t)ps * pstage + 3 * bstage > budget) --ps;
+      // weight slots to keep free: three, but a short-K launch (1x1 layers: one or two slots hold its whole weight tile,
+      // re-streamed per tile from L2) is bound by its patch loads instead -- with three slots reserved the two-plane
+      // 1x1 + skip layers were left with ONE patch stage, i.e. one 64-channel block in flight per SM
+      const int nslots_all = (P.nkb + kSlotKB - 1) / kSlotKB;
+      const uint32_t wres = (uint32_t)(nslots_all + 1 < 3 ? nslots_all + 1 : 3) * bstage;
+      while (ps > 1 && (uint32_t)ps * pstage + wres > budget) --ps;
       if (ps == 1 && pstage + 2 * bstage > budget) ps = 1;
       P.patch_stages = ps;
     }

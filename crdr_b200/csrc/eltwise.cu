@@ -29,15 +29,23 @@ __device__ __forceinline__ float std_cumulative(float x) {
   return 0.5f * erfcf(-0.70710678118654752440f * x);
 }
 
-template <int MODE>
+// TRAIN (MODE 0 only): additionally the likelihood of y + noise (noise: NCHW input, replayable by the oracle).
+template <int MODE, bool TRAIN = false>
 __global__ void __launch_bounds__(256) gauss_kernel(const __grid_constant__ crdr_gauss_desc d, uint32_t* status) {
   __shared__ float s_table[64];
   __shared__ int s_sym[kTile][kTile + 1];
   __shared__ int s_idx[kTile][kTile + 1];
   __shared__ float s_lik[kTile][kTile + 1];
+  __shared__ float s_noise[TRAIN ? kTile : 1][kTile + 1];   // in: noise, out: noisy likelihood
   const TileCoord tc = tile_coord(d.hw);
   const int tid = threadIdx.y * 32 + threadIdx.x;
   if (tid < d.ntable && tid < 64) s_table[tid] = d.scale_table[tid];
+  if (TRAIN) {
+    for (int cc = threadIdx.y; cc < kTile; cc += 8) {
+      const int c = tc.c0 + cc, p = tc.p0 + threadIdx.x;
+      if (c < d.c && p < d.hw) s_noise[cc][threadIdx.x] = d.noise[((int64_t)tc.n * d.c_total + d.nchw_coff + c) * d.hw + p];
+    }
+  }
   if (MODE == 2) {
     // load symbols NCHW (pixel-contiguous) into the tile: s_sym[channel][pixel]
     for (int cc = threadIdx.y; cc < kTile; cc += 8) {
@@ -76,8 +84,15 @@ __global__ void __launch_bounds__(256) gauss_kernel(const __grid_constant__ crdr
     }
     if (MODE != 2) {
       const float sg = fmaxf(d.sigma[m * d.ms_cs + d.sigma_coff + c], d.scale_bound);
-      int idx = d.ntable - 1;
-      for (int k = 0; k < d.ntable - 1; ++k) idx -= (sg <= s_table[k]) ? 1 : 0;
+      // build_indexes: (ntable-1) - #{k < ntable-1 : sg <= table[k]} = #{k < ntable-1 : table[k] < sg}; the table is
+      // strictly ascending, so the count is a lower bound: six branch-free steps instead of 63 compares (same result)
+      const int nt = d.ntable - 1;
+      int idx = 0;
+#pragma unroll
+      for (int step = 32; step > 0; step >>= 1) {
+        const int t = idx + step;
+        if (t <= nt && s_table[t - 1] < sg) idx = t;
+      }
       s_idx[threadIdx.x][pp] = idx;
       if (MODE == 0) {
         const float v = fabsf(yq - mu);
@@ -85,6 +100,13 @@ __global__ void __launch_bounds__(256) gauss_kernel(const __grid_constant__ crdr
         const float lower = std_cumulative((-0.5f - v) / sg);
         s_lik[threadIdx.x][pp] = fmaxf(upper - lower, 1e-9f);
         s_sym[threadIdx.x][pp] = (int)q;
+        if (TRAIN) {
+          // quantize(inputs, "noise") = inputs + noise;  _likelihood: values = |outputs - means|
+          const float vn = fabsf((d.y[m * d.y_cs + d.y_coff + c] + s_noise[threadIdx.x][pp]) - mu);
+          const float un = std_cumulative((0.5f - vn) / sg);
+          const float ln = std_cumulative((-0.5f - vn) / sg);
+          s_noise[threadIdx.x][pp] = fmaxf(un - ln, 1e-9f);
+        }
       }
     }
   }
@@ -106,6 +128,7 @@ __global__ void __launch_bounds__(256) gauss_kernel(const __grid_constant__ crdr
         d.symbols16[o] = (int16_t)sat;
       }
       if (d.likelihood) d.likelihood[o] = s_lik[cc][threadIdx.x];
+      if (TRAIN) d.likelihood_noisy[o] = s_noise[cc][threadIdx.x];
     }
   }
 }
@@ -141,12 +164,29 @@ __device__ __forceinline__ float eb_logits(const float* __restrict__ p, float x)
   return t + p[3];
 }
 
+__device__ __forceinline__ float eb_likelihood(const float* __restrict__ prm, float v) {
+  const float lower = eb_logits(prm, v - 0.5f);
+  const float upper = eb_logits(prm, v + 0.5f);
+  const float sum = lower + upper;
+  const float sgn = sum > 0.f ? -1.f : (sum < 0.f ? 1.f : 0.f);
+  return fmaxf(fabsf(sigmoidf_(sgn * upper) - sigmoidf_(sgn * lower)), 1e-9f);
+}
+
 template <int DEQUANT>
 __global__ void __launch_bounds__(256) eb_kernel(const __grid_constant__ crdr_eb_desc d, uint32_t* status) {
   __shared__ int s_sym[kTile][kTile + 1];
   __shared__ float s_zh[kTile][kTile + 1];
   __shared__ float s_lik[kTile][kTile + 1];
+  __shared__ float s_noise[kTile][kTile + 1];   // training mode: noise in, noisy likelihood out
   const TileCoord tc = tile_coord(d.hw);
+  const bool train = !DEQUANT && d.noise != nullptr;
+  if (train) {
+    for (int cc = threadIdx.y; cc < kTile; cc += 8) {
+      const int c = tc.c0 + cc, p = tc.p0 + threadIdx.x;
+      if (c < d.c && p < d.hw) s_noise[cc][threadIdx.x] = d.noise[((int64_t)tc.n * d.c + c) * d.hw + p];
+    }
+    __syncthreads();
+  }
   if (DEQUANT) {
     for (int cc = threadIdx.y; cc < kTile; cc += 8) {
       const int c = tc.c0 + cc, p = tc.p0 + threadIdx.x;
@@ -174,12 +214,8 @@ __global__ void __launch_bounds__(256) eb_kernel(const __grid_constant__ crdr_eb
     if (!DEQUANT) {
       s_sym[threadIdx.x][pp] = (int)q;
       const float* prm = d.params + (int64_t)c * 58;
-      const float lower = eb_logits(prm, zh - 0.5f);
-      const float upper = eb_logits(prm, zh + 0.5f);
-      const float sum = lower + upper;
-      const float sgn = sum > 0.f ? -1.f : (sum < 0.f ? 1.f : 0.f);
-      const float lik = fabsf(sigmoidf_(sgn * upper) - sigmoidf_(sgn * lower));
-      s_lik[threadIdx.x][pp] = fmaxf(lik, 1e-9f);
+      s_lik[threadIdx.x][pp] = eb_likelihood(prm, zh);
+      if (train) s_noise[threadIdx.x][pp] = eb_likelihood(prm, d.z[m * d.z_cs + c] + s_noise[threadIdx.x][pp]);
     }
   }
   __syncthreads();
@@ -191,6 +227,7 @@ __global__ void __launch_bounds__(256) eb_kernel(const __grid_constant__ crdr_eb
     if (!DEQUANT) {
       if (d.symbols) d.symbols[o] = s_sym[cc][threadIdx.x];
       if (d.likelihood) d.likelihood[o] = s_lik[cc][threadIdx.x];
+      if (train && d.likelihood_noisy) d.likelihood_noisy[o] = s_noise[cc][threadIdx.x];
     }
   }
 }
@@ -259,13 +296,14 @@ __global__ void __launch_bounds__(256) image_to_planes_kernel(const float* __res
 // (output pixel, group of 8 patch channels); patch channel k = (kh * 5 + kw) * 3 + c for k < 75, zero up to 128.
 // The layer then runs as a 1x1 convolution with K = 128 on the patch engine (2 K blocks instead of a 25-tap gather).
 __global__ void __launch_bounds__(256) image_to_patches_kernel(const float* __restrict__ img, int n, int h, int w,
-                                                               int hp, int wp, crdr_planes out, uint32_t* status) {
+                                                               int hp, int wp, crdr_planes out, int ng, uint32_t* status) {
+  // ng groups of 8 channels per pixel (10 .. 16): 75 patch channels + zero padding up to the tensor's channel count
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int ho = hp / 2, wo = wp / 2;
-  const int64_t total = (int64_t)n * ho * wo * 16;
+  const int64_t total = (int64_t)n * ho * wo * ng;
   if (idx >= total) return;
-  const int grp = (int)(idx & 15);
-  const int64_t pix = idx >> 4;
+  const int64_t pix = idx / ng;
+  const int grp = (int)(idx - pix * ng);
   const int j = (int)(pix % wo);
   const int64_t t = pix / wo;
   const int i = (int)(t % ho);
@@ -294,13 +332,14 @@ __global__ void __launch_bounds__(256) image_to_patches_kernel(const float* __re
 
 // uint8 variant of image_to_patches_kernel: ToTensor + Normalize(0.5, 0.5) of the reference data path, in its fp32 order
 __global__ void __launch_bounds__(256) image_u8_to_patches_kernel(const uint8_t* __restrict__ img, int n, int h, int w,
-                                                                  int hp, int wp, crdr_planes out, uint32_t* status) {
+                                                                  int hp, int wp, crdr_planes out, int ng, uint32_t* status) {
+  // ng groups of 8 channels per pixel (10 .. 16): 75 patch channels + zero padding up to the tensor's channel count
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int ho = hp / 2, wo = wp / 2;
-  const int64_t total = (int64_t)n * ho * wo * 16;
+  const int64_t total = (int64_t)n * ho * wo * ng;
   if (idx >= total) return;
-  const int grp = (int)(idx & 15);
-  const int64_t pix = idx >> 4;
+  const int64_t pix = idx / ng;
+  const int grp = (int)(idx - pix * ng);
   const int j = (int)(pix % wo);
   const int64_t t = pix / wo;
   const int i = (int)(t % ho);
@@ -346,7 +385,7 @@ __global__ void __launch_bounds__(256) planes_to_image_kernel(const float* __res
 // Same, for a stride-2 transposed convolution evaluated as ONE stride-1 launch whose output channels are the four
 // output phases: x[(b, y/2, x/2), ((y%2)*2 + x%2)*3 + c]  (pixel shuffle + crop + clamp in one pass).
 __global__ void __launch_bounds__(256) phases_to_image_kernel(const float* __restrict__ x, int x_cs, int n, int hb,
-                                                              int wb, int h, int w, float* __restrict__ img) {
+                                                              int wb, int h, int w, float* __restrict__ img, int clamp) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)n * 3 * h * w;
   if (idx >= total) return;
@@ -357,7 +396,7 @@ __global__ void __launch_bounds__(256) phases_to_image_kernel(const float* __res
   const int c = (int)(t % 3);
   const int b = (int)(t / 3);
   const float v = x[(((int64_t)b * hb + (yy >> 1)) * wb + (xx >> 1)) * x_cs + ((yy & 1) * 2 + (xx & 1)) * 3 + c];
-  img[idx] = fminf(fmaxf(v, -1.f), 1.f);
+  img[idx] = clamp ? fminf(fmaxf(v, -1.f), 1.f) : v;
 }
 
 // uint8 variant: clamp, then the reference's PNG conversion ((x + 1) / 2 * 255 in fp32, truncated by astype(uint8))
@@ -424,7 +463,10 @@ int gauss_launch(const crdr_gauss_desc* d, int mode, cudaStream_t st) {
   uint32_t* status = device_status_word();
   if (!status) return CRDR_ERR_CUDA;
   const dim3 g = tile_grid(d->n, d->hw, d->c), b(32, 8);
-  if (mode == 0) gauss_kernel<0><<<g, b, 0, st>>>(*d, status);
+  if (mode == 0 && (d->noise || d->likelihood_noisy)) {
+    if (!d->noise || !d->likelihood_noisy || !d->y) { set_error("gauss: training mode needs y, noise and likelihood_noisy"); return CRDR_ERR_BAD_SHAPE; }
+    gauss_kernel<0, true><<<g, b, 0, st>>>(*d, status);
+  } else if (mode == 0) gauss_kernel<0><<<g, b, 0, st>>>(*d, status);
   else if (mode == 1) gauss_kernel<1><<<g, b, 0, st>>>(*d, status);
   else gauss_kernel<2><<<g, b, 0, st>>>(*d, status);
   return check_launch("gauss_kernel");
@@ -470,14 +512,15 @@ int image_to_planes_launch(const float* img, int n, int h, int w, int hp, int wp
 
 int image_to_patches_launch(const float* img, int n, int h, int w, int hp, int wp, crdr_planes out, cudaStream_t st) {
   if (n <= 0 || h <= 0 || w <= 0 || hp < h || wp < w || hp - h >= h || wp - w >= w || (hp & 1) || (wp & 1) ||
-      out.cs % 8 || out.coff % 8 || out.cs < out.coff + 128 || !out.hi) {
+      out.cs % 8 || out.coff % 8 || out.cs < out.coff + 80 || !out.hi) {
     set_error("image_to_patches: bad shape (h=%d w=%d hp=%d wp=%d cs=%d)", h, w, hp, wp, out.cs);
     return CRDR_ERR_BAD_SHAPE;
   }
   uint32_t* status = device_status_word();
   if (!status) return CRDR_ERR_CUDA;
-  const int64_t total = (int64_t)n * (hp / 2) * (wp / 2) * 16;
-  image_to_patches_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(img, n, h, w, hp, wp, out, status);
+  const int ng = (out.cs - out.coff) / 8 < 16 ? (out.cs - out.coff) / 8 : 16;
+  const int64_t total = (int64_t)n * (hp / 2) * (wp / 2) * ng;
+  image_to_patches_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(img, n, h, w, hp, wp, out, ng, status);
   return check_launch("image_to_patches_kernel");
 }
 
@@ -488,26 +531,27 @@ int planes_to_image_launch(const float* x, int x_cs, int n, int hp, int wp, int 
   return check_launch("planes_to_image_kernel");
 }
 
-int phases_to_image_launch(const float* x, int x_cs, int n, int hb, int wb, int h, int w, float* img, cudaStream_t st) {
+int phases_to_image_launch(const float* x, int x_cs, int n, int hb, int wb, int h, int w, float* img, int clamp, cudaStream_t st) {
   if (n <= 0 || h <= 0 || w <= 0 || 2 * hb < h || 2 * wb < w || x_cs < 12) {
     set_error("phases_to_image: bad shape");
     return CRDR_ERR_BAD_SHAPE;
   }
   const int64_t total = (int64_t)n * 3 * h * w;
-  phases_to_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, x_cs, n, hb, wb, h, w, img);
+  phases_to_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, x_cs, n, hb, wb, h, w, img, clamp);
   return check_launch("phases_to_image_kernel");
 }
 
 int image_u8_to_patches_launch(const uint8_t* img, int n, int h, int w, int hp, int wp, crdr_planes out, cudaStream_t st) {
   if (n <= 0 || h <= 0 || w <= 0 || hp < h || wp < w || hp - h >= h || wp - w >= w || (hp & 1) || (wp & 1) ||
-      out.cs % 8 || out.coff % 8 || out.cs < out.coff + 128 || !out.hi || !img) {
+      out.cs % 8 || out.coff % 8 || out.cs < out.coff + 80 || !out.hi || !img) {
     set_error("image_u8_to_patches: bad shape (h=%d w=%d hp=%d wp=%d cs=%d)", h, w, hp, wp, out.cs);
     return CRDR_ERR_BAD_SHAPE;
   }
   uint32_t* status = device_status_word();
   if (!status) return CRDR_ERR_CUDA;
-  const int64_t total = (int64_t)n * (hp / 2) * (wp / 2) * 16;
-  image_u8_to_patches_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(img, n, h, w, hp, wp, out, status);
+  const int ng = (out.cs - out.coff) / 8 < 16 ? (out.cs - out.coff) / 8 : 16;
+  const int64_t total = (int64_t)n * (hp / 2) * (wp / 2) * ng;
+  image_u8_to_patches_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(img, n, h, w, hp, wp, out, ng, status);
   return check_launch("image_u8_to_patches_kernel");
 }
 

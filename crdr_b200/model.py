@@ -75,17 +75,18 @@ class CodecEngine:
         s = self.stride
         return -(-h // s) * s, -(-w // s) * s
 
-    def analysis(self, images, q, compact=False):
+    def analysis(self, images, q, compact=False, noise=None):
         """images: NCHW on the device, fp32 in [-1,1] or uint8 RGB (normalised on the fly like the reference's
         ToTensor + Normalize).  Returns a dict of device tensors (SURVEY 3.1 encode); ``compact`` adds the int16 symbol /
-        uint8 index copies for the host coder."""
+        uint8 index copies for the host coder.  ``noise`` = {"y": NCHW fp32, "z": NCHW fp32} (uniform in [-1/2, 1/2))
+        selects the training-mode forward: the likelihoods of y + u / z + u are added as y_lik_noisy / z_lik_noisy."""
         L, st = nv.lib(), nv.stream_handle()
         n, _, h, w = images.shape
         if not images.is_contiguous():
             raise ValueError("analysis() reads the image through a raw pointer: pass a contiguous NCHW tensor")
         hp, wp = self.padded(h, w)
         dev = images.device
-        img = Act.empty(n, hp // 2, wp // 2, 128, two=True, device=dev)   # im2col of g_a conv1 fused with the reflect pad
+        img = Act.empty(n, hp // 2, wp // 2, self.ga.PATCH_CH, two=True, device=dev)   # im2col of g_a conv1 fused with the reflect pad
         if images.dtype == torch.uint8:
             nv.check(L.crdr_image_u8_to_patches(images.data_ptr(), n, h, w, hp, wp, img.planes(0), st))
         else:
@@ -102,14 +103,24 @@ class CodecEngine:
         d.params, d.medians = self.eb_params.data_ptr(), self.eb_medians.data_ptr()
         d.zhat_planes = zhat.planes(0)
         d.symbols, d.zhat_nchw, d.likelihood = z_sym.data_ptr(), z_hat.data_ptr(), z_lik.data_ptr()
+        z_lik_noisy = None
+        if noise is not None:
+            nz, ny = noise["z"], noise["y"]
+            if (tuple(nz.shape) != (n, self.zc, hz, wz) or tuple(ny.shape) != (n, self.charm.yc, y_act.h, y_act.w)
+                    or nz.dtype != torch.float32 or ny.dtype != torch.float32 or not nz.is_contiguous() or not ny.is_contiguous()):
+                raise ValueError("noise must be contiguous fp32 NCHW tensors shaped like z and y")
+            z_lik_noisy = torch.empty((n, self.zc, hz, wz), dtype=torch.float32, device=dev)
+            d.noise, d.likelihood_noisy = nz.data_ptr(), z_lik_noisy.data_ptr()
         nv.check(L.crdr_eb_quantize(C.byref(d), st))
         T = self.charm.new_support(n, y_act.h, y_act.w, dev)
         self.hs.run(zhat, T, self.charm.off_mean, self.charm.off_scale)
-        enc = self.charm.encode(T, y32, self.gp, compact=compact)
+        enc = self.charm.encode(T, y32, self.gp, compact=compact and noise is None, noise=None if noise is None else noise["y"])
         yhat32, y_sym, y_idx, y_lik = enc[:4]
         out = dict(y32=y32, z32=z32, z_sym=z_sym, z_hat=z_hat, z_lik=z_lik, yhat32=yhat32, y_sym=y_sym, y_idx=y_idx,
                    y_lik=y_lik, size=(h, w))
-        if compact:
+        if noise is not None:
+            out.update(y_lik_noisy=enc[4], z_lik_noisy=z_lik_noisy)
+        elif compact:
             out.update(y_sym16=enc[4], y_idx8=enc[5])
         return out
 
@@ -130,9 +141,9 @@ class CodecEngine:
         self.hs.run(zhat, T, self.charm.off_mean, self.charm.off_scale)
         return T, z_hat
 
-    def synthesis(self, yhat32, q, beta, size, out_uint8=False):
+    def synthesis(self, yhat32, q, beta, size, out_uint8=False, clamp=True):
         """y_hat fp32 NHWC -> cropped, clamped NCHW image: fp32 in [-1,1], or uint8 through the reference's PNG
-        conversion (img_utils.py:30-42, truncation)."""
+        conversion (img_utils.py:30-42, truncation).  ``clamp=False``: the raw reconstruction of the training-mode forward."""
         img = self.gs.run(yhat32, q, beta)  # phase-packed: [n, hp/2, wp/2, 16]
         n, hb, wb, cs = img.shape
         h, w = size
@@ -141,7 +152,8 @@ class CodecEngine:
             nv.check(nv.lib().crdr_phases_to_image_u8(img.data_ptr(), cs, n, hb, wb, h, w, out.data_ptr(), nv.stream_handle()))
             return out
         out = torch.empty((n, 3, h, w), dtype=torch.float32, device=img.device)
-        nv.check(nv.lib().crdr_phases_to_image(img.data_ptr(), cs, n, hb, wb, h, w, out.data_ptr(), nv.stream_handle()))
+        nv.check(nv.lib().crdr_phases_to_image_ex(img.data_ptr(), cs, n, hb, wb, h, w, out.data_ptr(), 1 if clamp else 0,
+                                                  nv.stream_handle()))
         return out
 
     def decode_device(self, z_sym, y_sym, q, beta, size):
@@ -338,35 +350,62 @@ class _CharmModelCore(_CodecModelBase):
         return images.to(device=self.device, dtype=dt, non_blocking=nb).contiguous()
 
     # -- forward / run_model ---------------------------------------------------------------------
+    def draw_noise(self, n, h, w, generator=None):
+        """Uniform noise in [-1/2, 1/2) for the training-mode likelihoods, shaped like z and y of n padded h x w images
+        (the reference draws it inside CompressAI's quantize(mode="noise"); here it is an explicit input so a CPU oracle
+        can replay the exact values)."""
+        dev = self.engine().device
+        hy, wy, hz, wz = h // 16, w // 16, h // 64, w // 64
+        mk = lambda c, a, b: torch.rand((n, c, a, b), dtype=torch.float32, device=dev, generator=generator) - 0.5
+        return {"z": mk(self.hyperencoder.latent_ch, hz, wz), "y": mk(self.encoder.latent_ch, hy, wy)}
+
     @torch.no_grad()
-    def forward(self, real_images, rate_ind, beta, is_train=True):
-        if is_train:
-            raise NotImplementedError(
-                "training-mode forward (uniform-noise likelihoods, STE rounding, autograd) is not lowered yet; "
-                "evaluation (is_train=False), compress and decompress run on the CUDA engines")
+    def forward(self, real_images, rate_ind, beta, is_train=True, noise=None):
+        """Forward VALUES of the reference's forward (beta_cond_interpca_hyperprior_charm_model.py:34-78).  Training mode
+        (is_train=True): likelihoods of the noise-perturbed latents (``noise`` = draw_noise(...) or the caller's tensors),
+        straight-through rounded codes, quantised q_likelihoods, unclamped reconstruction.  No autograd graph is built:
+        the backward pass (dgrad / wgrad kernels) is not part of this package yet."""
         eng = self.engine()
         q = self._q(rate_ind)
         x = self._to_device(real_images)
         n, _, h, w = x.shape
         if h % self.stride or w % self.stride:
-            raise ValueError("forward(is_train=False) expects images padded to a multiple of 64 (use run_model)")
-        a = eng.analysis(x, q)
-        fake = eng.synthesis(a["yhat32"], q, beta, (h, w))
+            raise ValueError("forward() expects images padded to a multiple of 64 (use run_model)")
+        if is_train and noise is None:
+            noise = self.draw_noise(n, h, w)
+        a = eng.analysis(x, q, noise=noise if is_train else None)
+        fake = eng.synthesis(a["yhat32"], q, beta, (h, w), clamp=not is_train)
         y, z = eng.to_nchw(a["y32"]), eng.to_nchw(a["z32"])
         y_hat = eng.to_nchw(a["yhat32"])
         nv.status_check()  # a clamped fp16 overflow must surface as an error, never as a silent wrong value
+        lik = {"y": a["y_lik_noisy"], "z": a["z_lik_noisy"]} if is_train else {"y": a["y_lik"], "z": a["z_lik"]}
         return {
             "fake_images": fake,
-            "likelihoods": {"y": a["y_lik"], "z": a["z_lik"]},
+            "likelihoods": lik,
             "latent_code": {"y": y, "z": z},
             "quantized_code": {"y": y_hat, "z": a["z_hat"]},
             "q_likelihoods": {"y": a["y_lik"], "z": a["z_lik"]},
         }
 
     @torch.no_grad()
-    def run_model(self, real_images, rate_ind=None, beta=None, is_train=True):
+    def run_model(self, real_images, rate_ind=None, beta=None, is_train=True, noise=None):
         if is_train:
-            return self.forward(real_images, rate_ind, beta, is_train=True)
+            # beta_cond_interpca_hyperprior_model.py:28-64: one quality index and one beta per batch when not given;
+            # training crops are multiples of 64, so data_preprocess / data_postprocess are identities (base_model.py:35-57)
+            if rate_ind is None and self.uses_rate:
+                rate_ind = self.sample_rate_ind(1)
+            if beta is None and self.uses_beta:
+                beta = self.sample_beta()
+            n, _, h, w = real_images.shape
+            out = _CharmModelCore.forward(self, real_images, rate_ind, beta, is_train=True, noise=noise)
+            num_pixel = h * w
+            eng = self.engine()
+            bpp = (eng.bits(out["likelihoods"]["y"]) + eng.bits(out["likelihoods"]["z"])) / num_pixel
+            qbpp = (eng.bits(out["q_likelihoods"]["y"]) + eng.bits(out["q_likelihoods"]["z"])) / num_pixel
+            return dict(real_images=self._to_device(real_images), fake_images=out["fake_images"],
+                        y_hat=out["quantized_code"]["y"], z_hat=out["quantized_code"]["z"], rate_ind=rate_ind, beta=beta,
+                        y_likelihood=out["likelihoods"]["y"], z_likelihood=out["likelihoods"]["z"], bpp=bpp,
+                        y_q_likelihood=out["q_likelihoods"]["y"], z_q_likelihood=out["q_likelihoods"]["z"], qbpp=qbpp)
         if rate_ind is None:
             raise ValueError('"rate_ind" must be specified if is_train=False')
         if beta is None:
@@ -594,11 +633,11 @@ class InterpCaHyperpriorCharmModel(_CharmModelCore):
     interpca_hyperprior_model.py:31-62)."""
     uses_beta = False
 
-    def forward(self, real_images, rate_ind, is_train=True):
-        return super().forward(real_images, rate_ind, None, is_train=is_train)
+    def forward(self, real_images, rate_ind, is_train=True, noise=None):
+        return super().forward(real_images, rate_ind, None, is_train=is_train, noise=noise)
 
-    def run_model(self, real_images, rate_ind=None, is_train=True):
-        out = super().run_model(real_images, rate_ind=rate_ind, beta=0.0, is_train=is_train)
+    def run_model(self, real_images, rate_ind=None, is_train=True, noise=None):
+        out = super().run_model(real_images, rate_ind=rate_ind, beta=0.0, is_train=is_train, noise=noise)
         out.pop("beta", None)
         return out
 
@@ -619,11 +658,11 @@ class HyperpriorCharmModel(_CharmModelCore):
     uses_rate = False
     uses_beta = False
 
-    def forward(self, real_images, is_train=True):
-        return super().forward(real_images, None, None, is_train=is_train)
+    def forward(self, real_images, is_train=True, noise=None):
+        return super().forward(real_images, None, None, is_train=is_train, noise=noise)
 
-    def run_model(self, real_images, is_train=True):
-        out = super().run_model(real_images, rate_ind=0.0, beta=0.0, is_train=is_train)
+    def run_model(self, real_images, is_train=True, noise=None):
+        out = super().run_model(real_images, rate_ind=0.0, beta=0.0, is_train=is_train, noise=noise)
         out.pop("beta", None)
         out.pop("rate_ind", None)
         return out

@@ -75,6 +75,7 @@ class GaussDesc(C.Structure):
         ("symbols", C.c_void_p), ("indexes", C.c_void_p), ("likelihood", C.c_void_p),
         ("c_total", C.c_int32), ("nchw_coff", C.c_int32),
         ("symbols16", C.c_void_p), ("indexes8", C.c_void_p),
+        ("noise", C.c_void_p), ("likelihood_noisy", C.c_void_p),
     ]
 
 
@@ -85,6 +86,7 @@ class EbDesc(C.Structure):
         ("params", C.c_void_p), ("medians", C.c_void_p),
         ("zhat_planes", Planes),
         ("symbols", C.c_void_p), ("zhat_nchw", C.c_void_p), ("likelihood", C.c_void_p),
+        ("noise", C.c_void_p), ("likelihood_noisy", C.c_void_p),
     ]
 
 
@@ -95,7 +97,7 @@ SM100_SYMBOLS = [
     "crdr_affine_to_planes", "crdr_image_to_planes", "crdr_image_to_patches", "crdr_planes_to_image", "crdr_phases_to_image", "crdr_nhwc_to_nchw",
     "crdr_gauss_quantize", "crdr_gauss_indexes", "crdr_gauss_dequantize", "crdr_eb_quantize",
     "crdr_eb_dequantize", "crdr_bits_from_likelihood", "crdr_max_abs", "crdr_max_abs_batch",
-    "crdr_image_u8_to_patches", "crdr_phases_to_image_u8",
+    "crdr_image_u8_to_patches", "crdr_phases_to_image_u8", "crdr_phases_to_image_ex",
 ]
 
 _lib = None
@@ -137,6 +139,7 @@ def lib():
         L.crdr_max_abs_batch.argtypes = [vp, i32, i64, vp, vp]
         L.crdr_image_u8_to_patches.argtypes = [vp, i32, i32, i32, i32, i32, Planes, vp]
         L.crdr_phases_to_image_u8.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp]
+        L.crdr_phases_to_image_ex.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, i32, vp]
         L.crdr_debug_conv_epilogue.argtypes = [i32, i32]
         L.crdr_debug_conv_epilogue.restype = None
         assert L.crdr_abi_version() == 1

@@ -179,8 +179,8 @@ int crdr_affine_to_planes(const float* x, int32_t x_cs, int32_t x_coff, int64_t 
 int crdr_image_to_planes(const float* img, int32_t n, int32_t h, int32_t w, int32_t hp, int32_t wp,
                          crdr_planes out, void* stream);
 /* Same pre-processing fused with the im2col of the first analysis layer (ElicEncoder.conv1: 5x5, stride 2, padding 2,
- * elic_autoencoder.py:42): output NHWC planes (n, hp/2, wp/2, >=128) whose channel (kh*5+kw)*3+c is the padded image at
- * (2i+kh-2, 2j+kw-2, c) (zero outside), channels 75..127 zero.  conv1 then runs as a 1x1 convolution with K = 128. */
+ * elic_autoencoder.py:42): output NHWC planes (n, hp/2, wp/2, 80..128) whose channel (kh*5+kw)*3+c is the padded image at
+ * (2i+kh-2, 2j+kw-2, c) (zero outside), channels 75.. zero.  conv1 then runs as a 1x1 convolution over these channels. */
 int crdr_image_to_patches(const float* img, int32_t n, int32_t h, int32_t w, int32_t hp, int32_t wp,
                           crdr_planes out, void* stream);
 /* Post-processing: NHWC fp32 (n,hp,wp,cs) first 3 channels -> crop (h,w) -> clamp(-1,1) -> NCHW fp32.
@@ -193,6 +193,10 @@ int crdr_planes_to_image(const float* x, int32_t x_cs, int32_t n, int32_t hp, in
  * crop + clamp -> NCHW fp32 (h <= 2*hb, w <= 2*wb). */
 int crdr_phases_to_image(const float* x, int32_t x_cs, int32_t n, int32_t hb, int32_t wb, int32_t h, int32_t w,
                          float* img, void* stream);
+/* Same with the clamp optional: training-mode forward returns the unclamped reconstruction
+ * (beta_cond_interpca_hyperprior_charm_model.py:54-56 clamps only when not is_train). */
+int crdr_phases_to_image_ex(const float* x, int32_t x_cs, int32_t n, int32_t hb, int32_t wb, int32_t h, int32_t w,
+                            float* img, int32_t clamp, void* stream);
 
 /* uint8 image boundary.  Input: NCHW uint8 RGB as PIL / cv2 deliver it; the kernel applies the reference's
  * ToTensor + Normalize(0.5, 0.5) arithmetic (scripts/compress.py:54-57: (u/255 - 0.5)/0.5 in fp32) before the reflect
@@ -240,6 +244,13 @@ typedef struct {
    * indexes as uint8.  crdr_gauss_dequantize reads `symbols16` when `symbols` is NULL.  May be NULL. */
   int16_t* symbols16;
   uint8_t* indexes8;
+  /* Training-mode likelihood (SteGaussianMeanScaleConditional.forward(is_train=True), ste_gaussian_conditional.py:20-27;
+   * CompressAI GaussianConditional.forward(training=True)): the likelihood of y + u, u ~ U(-1/2, 1/2), under N(mu, sigma).
+   * The noise is an INPUT (NCHW fp32 like `likelihood`) so that a CPU oracle can replay it; the quantised outputs above
+   * are the straight-through forward values (round(y - mu) + mu) and the quantised likelihood (q_likelihoods).  crdr_gauss_quantize
+   * only; both NULL in evaluation mode. */
+  const float* noise;
+  float* likelihood_noisy;
 } crdr_gauss_desc;
 int crdr_gauss_quantize(const crdr_gauss_desc* d, void* stream);
 
@@ -265,6 +276,10 @@ typedef struct {
   int32_t* symbols;
   float* zhat_nchw;
   float* likelihood;
+  /* Training mode (SteEntropyBottleneck.forward(is_train=True), entropy_bottleneck.py:23-30): likelihood of z + u with the
+   * uniform noise u given as an NCHW fp32 input; z_hat stays round(z - median) + median.  crdr_eb_quantize only; may be NULL. */
+  const float* noise;
+  float* likelihood_noisy;
 } crdr_eb_desc;
 int crdr_eb_quantize(const crdr_eb_desc* d, void* stream);
 /* Decoder: symbols (NCHW int32) -> z_hat planes + NCHW fp32. */

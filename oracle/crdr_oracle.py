@@ -275,6 +275,56 @@ def decompress(sd, string_list, beta, eb=None, gc=None):
     return img, z_hat, y_hat, y_sym
 
 
+def eb_likelihood_at(eb, v):
+    """EntropyBottleneck likelihood (lower-bounded) at arbitrary points v [N, C, H, W] (CompressAI EntropyBottleneck.forward
+    after its quantize step: permute to C x 1 x (N H W), _likelihood, likelihood_lower_bound, permute back)."""
+    n, c, h, w = v.shape
+    vals = v.permute(1, 0, 2, 3).contiguous().reshape(c, 1, -1)
+    lik = eb.likelihood_lower_bound(eb._likelihood(vals))
+    return lik.reshape(c, n, h, w).permute(1, 0, 2, 3).contiguous()
+
+
+def ste_round(x):
+    """src/models/subnet/entropy_model/ste_round.py:4-5 (forward value)."""
+    return (torch.round(x) - x) + x
+
+
+@torch.no_grad()
+def forward_train(sd, x, q, beta, noise, eb, gc):
+    """Forward VALUES of model.forward(..., is_train=True) (beta_cond_interpca_hyperprior_charm_model.py:34-78;
+    minnen20_charm_context_model.py:88-141; ste_gaussian_conditional.py:20-27; entropy_bottleneck.py:23-30) with the
+    uniform noise given explicitly: noise = {"z": [N, zc, h/64, w/64], "y": [N, yc, h/16, w/16]} in [-1/2, 1/2).
+    The reference draws the same values inside CompressAI's quantize(mode="noise"): z first (in C x 1 x (N H W) order),
+    then one draw per slice."""
+    S, K = CFG["num_slices"], CFG["max_support"]
+    y = g_a(sd, x, q)
+    z = h_a(sd, y)
+    med = eb._get_medians().reshape(1, -1, 1, 1)
+    z_hat = ste_round(z - med) + med
+    z_lik = eb_likelihood_at(eb, z + noise["z"])
+    hyper = h_s(sd, z_hat)
+    cm = sub(sd, "context_model")
+    hyper_mean, hyper_scale = torch.chunk(hyper, 2, dim=1)
+    y_slices, n_slices = torch.chunk(y, S, dim=1), torch.chunk(noise["y"], S, dim=1)
+    hats, liks, qliks = [], [], []
+    for s in range(S):
+        support = hats[:K]
+        mean_support = torch.cat([hyper_mean] + support, dim=1)
+        scale_support = torch.cat([hyper_scale] + support, dim=1)
+        mu = slice_net(sub(cm, f"mean_slice_transforms.{s}"), mean_support)
+        sigma = slice_net(sub(cm, f"scale_slice_transforms.{s}"), scale_support)
+        liks.append(gc.likelihood_lower_bound(gc._likelihood(y_slices[s] + n_slices[s], sigma, mu)))
+        y_hat_s = ste_round(y_slices[s] - mu) + mu
+        qliks.append(gc(y_slices[s], sigma, means=mu, training=False)[1])
+        lrp = slice_net(sub(cm, f"lrp_slice_transforms.{s}"), torch.cat([mean_support, y_hat_s], dim=1))
+        hats.append(y_hat_s + 0.5 * torch.tanh(lrp))
+    y_hat = torch.cat(hats, dim=1)
+    fake = g_s(sd, y_hat, q, beta)
+    _, z_qlik = eb(z, training=False)
+    return {"fake_images": fake, "likelihoods": {"y": torch.cat(liks, dim=1), "z": z_lik}, "latent_code": {"y": y, "z": z},
+            "quantized_code": {"y": y_hat, "z": z_hat}, "q_likelihoods": {"y": torch.cat(qliks, dim=1), "z": z_qlik}}
+
+
 def to_uint8(img):
     """img_utils.torch2npimg truncation semantics (img_utils.py:30-42)."""
     return ((img + 1.0) / 2.0 * 255.0).numpy().astype(np.uint8)

@@ -77,12 +77,15 @@ def test_no_cpu_fallback(model):
     model.device = "cpu"
     model.invalidate_engine()
     try:
+        if not hasattr(model, "header_handler"):
+            model.codec_setup()
+            model.invalidate_engine()
         with pytest.raises(NativeError):
             model.compress(torch.zeros(1, 3, 64, 64), 0.0)
+        with pytest.raises(NativeError):   # training-mode forward runs on the same engines: no CPU path either
+            model.forward(torch.zeros(1, 3, 64, 64), 0.0, 0.0, is_train=True)
     finally:
         model.device = "cuda:0"
-    with pytest.raises(NotImplementedError):
-        model.forward(torch.zeros(1, 3, 64, 64), 0.0, 0.0, is_train=True)
 
 
 def test_header_and_container_bytes(tmp_path):

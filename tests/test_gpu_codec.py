@@ -243,6 +243,9 @@ def test_eltwise_kernels_against_torch():
     want = cols.permute(0, 2, 1, 3, 4).reshape(2, 75, 32, 32)                                # channel = tap * 3 + c
     gotp = pa.to_nchw()
     assert (gotp[:, :75] - want).abs().max() < 2e-7 and gotp[:, 75:].abs().max() == 0
+    pb = Act.empty(2, 32, 32, 80)      # the width the analysis transform uses: 75 + 5 zero channels
+    nv.check(L.crdr_image_to_patches(img.data_ptr(), 2, 37, 50, 64, 64, pb.planes(0), st))
+    assert torch.equal(pb.to_nchw(), gotp[:, :80])
     # planes -> image: crop + clamp
     x = (torch.randn(2, 16, 24, 4, generator=g) * 2).cuda()
     out = torch.empty(2, 3, 13, 20, device="cuda")
@@ -433,3 +436,44 @@ def test_stage_model_variants_against_oracle(oracle, stage):
     rm = model.run_model(x, is_train=False) if stage == 1 else model.run_model(x, rate_ind=q, is_train=False)
     assert "beta" not in rm and torch.equal(rm["fake_images"], img_m)
     assert abs(rm["bpp"].item() * h * w - ref_bits) <= BPP_RTOL * ref_bits + 1e-3
+
+
+def test_training_mode_forward_values_against_oracle(models, oracle):
+    """SURVEY A10, forward(is_train=True) / run_model(is_train=True): likelihoods of the noise-perturbed latents (the noise
+    is an input, replayed by the oracle, which is itself pinned bit for bit to the reference's forward under a seed --
+    tests/test_oracle_vs_reference.py), straight-through rounded codes, quantised q_likelihoods, unclamped reconstruction,
+    bpp / qbpp of get_rate_summary_dict (hyperprior_model.py:60-78).  Values only: no autograd graph."""
+    import fixtures
+    model, sd = models(True)
+    n, h, w, q, beta = 2, 128, 192, 2.25, 1.28
+    x = fixtures.image(n, h, w, seed=55)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    noise = model.draw_noise(n, h, w, generator=g)
+    assert noise["y"].shape == (n, 320, h // 16, w // 16) and float(noise["y"].min()) >= -0.5 and float(noise["y"].max()) < 0.5
+    eb, gc = oracle.entropy_models(sd)
+    o = oracle.forward_train(sd, x, q, beta, {k: v.cpu() for k, v in noise.items()}, eb, gc)
+    out = model.forward(x, q, beta, is_train=True, noise=noise)
+    for k in ("y", "z"):
+        qc, qo = out["quantized_code"][k].cpu(), o["quantized_code"][k]
+        assert (qc - qo).abs().max() <= 1e-4 * max(1.0, float(qo.abs().max())), k
+        same = (torch.round(qc - qo) == 0)
+        for grp in ("likelihoods", "q_likelihoods"):
+            rel = ((out[grp][k].cpu() - o[grp][k]).abs() / o[grp][k])[same]
+            assert rel.max().item() <= LIK_RTOL, (grp, k, rel.max().item())
+        lc = out["latent_code"][k].cpu()
+        assert (lc - o["latent_code"][k]).abs().max() / o["latent_code"][k].abs().max() < 1e-5
+    # noisy and quantised likelihoods are different quantities
+    assert not torch.equal(out["likelihoods"]["y"], out["q_likelihoods"]["y"])
+    fake, fake_o = out["fake_images"].cpu(), o["fake_images"]
+    assert float(fake.abs().max()) > 1.0 or float(fake_o.abs().max()) <= 1.0    # not clamped
+    assert (fake - fake_o).abs().max().item() <= 0.04                           # F16X1 synthesis: a few grey levels
+    rm = model.run_model(x, rate_ind=q, beta=beta, is_train=True, noise=noise)
+    bits = lambda l: float(-(torch.log(l).sum()) / np.log(2))
+    for key, grp in (("bpp", "likelihoods"), ("qbpp", "q_likelihoods")):
+        want = (bits(o[grp]["y"]) + bits(o[grp]["z"])) / (h * w) / n     # per-image mean of the oracle's totals
+        got = rm[key].mean().item()
+        assert abs(got - want) <= BPP_RTOL * want, (key, got, want)
+    assert rm["rate_ind"] == q and rm["beta"] == beta and torch.equal(rm["fake_images"], out["fake_images"])
+    # sampled conditioning when none is given (one q and one beta per batch)
+    rs = model.run_model(x, is_train=True)
+    assert 0 <= int(rs["rate_ind"].item()) < 5 and 0.0 <= rs["beta"] <= 5.12 and rs["bpp"].shape == (n,)

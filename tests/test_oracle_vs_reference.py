@@ -68,6 +68,29 @@ def test_forward_eval_equal(oracle, ref_model):
     assert torch.equal(fake, ref["fake_images"])
 
 
+def test_forward_train_equal_with_replayed_noise(oracle, ref_model):
+    """Training-mode forward: the oracle, fed with the very noise values the reference draws under a seed
+    (z first, in CompressAI's C x 1 x (N H W) order, then one draw per slice), reproduces the reference's dict."""
+    sd = {k: v.detach().clone() for k, v in ref_model.state_dict().items()}
+    n, h, w = 2, 64, 128
+    x = torch.rand(n, 3, h, w, generator=torch.Generator().manual_seed(13)) * 2 - 1
+    q, beta = 2.25, 1.28
+    torch.manual_seed(77)
+    with torch.no_grad():
+        ref = ref_model.forward(x, q, beta, is_train=True)
+    torch.manual_seed(77)
+    zc, yc, hz, wz, hy, wy = 192, 320, h // 64, w // 64, h // 16, w // 16
+    nz = torch.empty(zc, 1, n * hz * wz).uniform_(-0.5, 0.5).reshape(zc, n, hz, wz).permute(1, 0, 2, 3).contiguous()
+    ny = torch.cat([torch.empty(n, yc // 10, hy, wy).uniform_(-0.5, 0.5) for _ in range(10)], dim=1)
+    eb, gc = oracle.entropy_models(sd)
+    mine = oracle.forward_train(sd, x, q, beta, {"z": nz, "y": ny}, eb, gc)
+    for grp in ("likelihoods", "latent_code", "quantized_code", "q_likelihoods"):
+        for k in ("y", "z"):
+            assert torch.equal(mine[grp][k], ref[grp][k]), (grp, k)
+    assert torch.equal(mine["fake_images"], ref["fake_images"])
+    assert float(ref["fake_images"].abs().max()) > 0 and not torch.equal(ref["likelihoods"]["y"], ref["q_likelihoods"]["y"])
+
+
 @pytest.mark.parametrize("stage", [1, 2])
 def test_stage_models_bit_equal_and_same_layout(oracle, stage):
     """HyperpriorCharmModel (crdr_stage_1.yaml) and InterpCaHyperpriorCharmModel (crdr_stage_2.yaml).
