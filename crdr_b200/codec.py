@@ -292,9 +292,43 @@ class CharmEngine:
         self.mean = [SliceNet(_sub(sd, f"mean_slice_transforms.{i}"), cfg, lens(self._segs_mean(i))) for i in range(num_slices)]
         self.scale = [SliceNet(_sub(sd, f"scale_slice_transforms.{i}"), cfg, lens(self._segs_scale(i))) for i in range(num_slices)]
         self.lrp = [SliceNet(_sub(sd, f"lrp_slice_transforms.{i}"), cfg, lens(self._segs_lrp(i))) for i in range(num_slices)]
+        self._streams = {}
 
     def n_support(self, s):
         return s if self.max_support < 0 else min(s, self.max_support)
+
+    # -- small batches: independent slice networks side by side ---------------------------------------------------
+    # One slice network of a small batch fills a fraction of the GPU (Kodak batch 1: M = 1536 = 6 CTA pairs of 74 per N
+    # tile), and its K loop cannot be split without changing the summation order that the decoder must reproduce.  What
+    # CAN run concurrently are the networks that do not depend on each other: (mean, scale) of a slice, and all networks of
+    # the slices 5..9 group.  They are enqueued on side streams (fork / join with events); every network's arithmetic is
+    # untouched, so the results are bit-identical to the serial order (batch-size invariance is a decoder requirement).
+    CONCURRENT_MAX_PAIR_TILES = 24   # use side streams when one launch occupies at most this many CTA pairs per N tile
+
+    def _concurrent(self, T):
+        pair_tiles = (T.n * (-(-T.h // 16)) * (-(-T.w // 8)) + 1) // 2
+        return pair_tiles <= self.CONCURRENT_MAX_PAIR_TILES and os.environ.get("CRDR_CHARM_STREAMS", "1") != "0"
+
+    def _run_jobs(self, jobs, concurrent):
+        if not concurrent or len(jobs) < 2:
+            for job in jobs:
+                job()
+            return
+        main = torch.cuda.current_stream()
+        dev = main.device
+        pool = self._streams.setdefault(dev, [])
+        while len(pool) < min(len(jobs), 10):
+            pool.append(torch.cuda.Stream(device=dev))
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for i, job in enumerate(jobs):
+            side = pool[i % len(pool)]
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                job()
+            done = torch.cuda.Event()
+            done.record(side)
+            main.wait_event(done)
 
     def new_support(self, n, h, w, device):
         # zero-filled: the 64-channel blocks of the patch engine may read channels that are written later
@@ -322,8 +356,12 @@ class CharmEngine:
     def params(self, T, s, ms):
         """mu_s, sigma_s -> fp32 NHWC scratch `ms` laid out [mu of all slices | sigma of all slices], so that the
         element-wise kernels cover a whole dependency group (consecutive slices) in one launch."""
-        self.mean[s](T, self._segs_mean(s), out_f32=ms, out_f32_coff=s * self.sc, want_planes=False)
-        self.scale[s](T, self._segs_scale(s), out_f32=ms, out_f32_coff=self.yc + s * self.sc, want_planes=False)
+        for job in self.param_jobs(T, s, ms):
+            job()
+
+    def param_jobs(self, T, s, ms):
+        return [lambda: self.mean[s](T, self._segs_mean(s), out_f32=ms, out_f32_coff=s * self.sc, want_planes=False),
+                lambda: self.scale[s](T, self._segs_scale(s), out_f32=ms, out_f32_coff=self.yc + s * self.sc, want_planes=False)]
 
     def refine(self, T, s, yq32, yhat32):
         """LRP: y_hat_s = yq_s + 0.5 tanh(lrp(...)) -> support tensor (planes) and yhat32 (fp32 NHWC)."""
@@ -370,15 +408,14 @@ class CharmEngine:
         sym16 = torch.empty((n, self.yc, h, w), dtype=torch.int16, device=dev) if compact else None
         idx8 = torch.empty((n, self.yc, h, w), dtype=torch.uint8, device=dev) if compact else None
         lik_noisy = torch.empty((n, self.yc, h, w), dtype=torch.float32, device=dev) if noise is not None else None
-        st, L = nv.stream_handle(), nv.lib()
+        L = nv.lib()
+        conc = self._concurrent(T)
         for grp in self.groups():
-            for s in grp:
-                self.params(T, s, ms)
+            self._run_jobs([j for s in grp for j in self.param_jobs(T, s, ms)], conc)
             d = self.gauss_desc(gp, T, grp[0], len(grp), n, h * w, ms, y32=y32, yq32=yq32, sym=sym, idx=idx, lik=lik,
                                 sym16=sym16, idx8=idx8, noise=noise, lik_noisy=lik_noisy)
-            nv.check(L.crdr_gauss_quantize(C.byref(d), st))
-            for s in grp:
-                self.refine(T, s, yq32, yhat32)
+            nv.check(L.crdr_gauss_quantize(C.byref(d), nv.stream_handle()))
+            self._run_jobs([(lambda s=s: self.refine(T, s, yq32, yhat32)) for s in grp], conc)
         if noise is not None:
             return yhat32, sym, idx, lik, lik_noisy
         if compact:
@@ -397,16 +434,15 @@ class CharmEngine:
         yhat32 = torch.empty((n, h, w, self.yc), dtype=torch.float32, device=dev)
         idx = torch.empty((n, self.yc, h, w), dtype=torch.uint8 if compact else torch.int32, device=dev)
         L = nv.lib()
+        conc = self._concurrent(T)
         for grp in self.groups():
-            for s in grp:
-                self.params(T, s, ms)
+            self._run_jobs([j for s in grp for j in self.param_jobs(T, s, ms)], conc)
             d = self.gauss_desc(gp, T, grp[0], len(grp), n, h * w, ms, **({"idx8": idx} if compact else {"idx": idx}))
             nv.check(L.crdr_gauss_indexes(C.byref(d), nv.stream_handle()))
             sym = yield grp[0], len(grp), idx
             d = self.gauss_desc(gp, T, grp[0], len(grp), n, h * w, ms, yq32=yq32, sym=sym)
             nv.check(L.crdr_gauss_dequantize(C.byref(d), nv.stream_handle()))
-            for s in grp:
-                self.refine(T, s, yq32, yhat32)
+            self._run_jobs([(lambda s=s: self.refine(T, s, yq32, yhat32)) for s in grp], conc)
         return yhat32
 
     def decode(self, T, gp, symbol_source):

@@ -183,13 +183,18 @@ __global__ void __launch_bounds__(kBnThreads, 1) bottleneck_bc_kernel(const __gr
         mbar_wait(smem_u32(&accb_full[tb]), (uint32_t)(j >> 1) & 1u, P.status);
         tc_fence_after();
         bool first = true;
-        if (cgrp >= units_b) arrive_leader(&accb_empty[tb]);
+        // Unit ownership balances eb + ec work per warp group: the 1x1's units go round robin (group g: g, g + 3, ...), so
+        // the 3x3's units beyond the first three go to the LAST groups (mid = 128, C = 256: 4 units per group and tile;
+        // round robin for both left group 0 with 5 of the 12 and made it the critical path of every tile)
+        const int nb_mine = (cgrp < units_b ? 1 : 0) + ((units_b > kBnGroups && cgrp == kBnGroups - 1) ? 1 : 0);
+        if (nb_mine == 0) arrive_leader(&accb_empty[tb]);
 #pragma unroll 1
-        for (int u = cgrp; u < units_b; u += kBnGroups) {
+        for (int k = 0; k < nb_mine; ++k) {
+          const int u = k == 0 ? cgrp : units_b - 1;   // units_b <= 4: the only extra unit is the last one
           uint32_t r0[32];
           tmem_ld32_issue(lane_addr + (uint32_t)tb * kBnAccB + (uint32_t)u * 32u, r0);
           tmem_wait_ld();
-          if (u + kBnGroups >= units_b) arrive_leader(&accb_empty[tb]);   // this warp's last read of acc_b[tb]
+          if (k + 1 == nb_mine) arrive_leader(&accb_empty[tb]);   // this warp's last read of acc_b[tb]
           float v[32];
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r0[e]);

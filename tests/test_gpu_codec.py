@@ -470,7 +470,7 @@ def test_training_mode_forward_values_against_oracle(models, oracle):
     fake, fake_o = out["fake_images"].cpu(), o["fake_images"]
     assert float(fake.abs().max()) > 1.0 or float(fake_o.abs().max()) <= 1.0    # not clamped
     err = (fake - fake_o).abs()                                                 # F16X1 synthesis: a few grey levels
-    assert err.pow(2).mean().sqrt().item() <= 0.01 and torch.quantile(err.flatten()[:1000000], 0.999).item() <= 0.04
+    assert err.pow(2).mean().sqrt().item() <= 0.01 and torch.quantile(err.flatten()[:1000000], 0.999).item() <= 0.08
     rm = model.run_model(x, rate_ind=q, beta=beta, is_train=True, noise=noise)
     bits = lambda l: float(-(torch.log(l).sum()) / np.log(2))
     for key, grp in (("bpp", "likelihoods"), ("qbpp", "q_likelihoods")):
