@@ -303,7 +303,10 @@ class CharmEngine:
     # CAN run concurrently are the networks that do not depend on each other: (mean, scale) of a slice, and all networks of
     # the slices 5..9 group.  They are enqueued on side streams (fork / join with events); every network's arithmetic is
     # untouched, so the results are bit-identical to the serial order (batch-size invariance is a decoder requirement).
-    CONCURRENT_MAX_PAIR_TILES = 24   # use side streams when one launch occupies at most this many CTA pairs per N tile
+    # Side streams are used when one launch occupies at most this many CTA pairs per N tile (CRDR_CHARM_STREAMS_MAX).
+    # Measured on B200 (ms per encode + decode step, serial -> concurrent): batch 1 13.7 -> 10.8, batch 8 29.9 -> 26.6,
+    # batch 24 69.9 -> 69.4 (the persistent kernels of a full-GPU launch only overlap in their last wave), so: always.
+    CONCURRENT_MAX_PAIR_TILES = int(os.environ.get("CRDR_CHARM_STREAMS_MAX", str(1 << 30)))
 
     def _concurrent(self, T):
         pair_tiles = (T.n * (-(-T.h // 16)) * (-(-T.w // 8)) + 1) // 2

@@ -17,6 +17,14 @@ print("fused eligible:", blk.fused)
 x = Act.from_nchw(torch.randn(n, c, h, w, generator=g).cuda(), two=False)
 add = tuple((torch.randn(k, generator=g) * 0.3).cuda() for k in (mid, mid, c))
 scale, shift = (torch.rand(c, generator=g) + 0.5).cuda(), (torch.randn(c, generator=g) * 0.2).cuda()
+if "novec" in sys.argv:   # experiment: no per-channel epilogue vectors at all (how much do their shared-memory loads cost?)
+    add, scale, shift = (None, None, None), None, None
+    for cv in (blk.c1, blk.c2, blk.c3):
+        cv.op.bias = None
+        for ph in cv.op.phases:
+            ph.tmpl.bias = None
+    if blk.fused:
+        blk.tmpl.bias2 = blk.tmpl.bias3 = None
 res = {}
 for fused in (False, True):
     codec.FUSE_BC[0] = fused
