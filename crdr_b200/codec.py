@@ -24,6 +24,33 @@ FUSE_BC = [os.environ.get("CRDR_FUSE_BC", "1") != "0"]   # fused bottleneck tail
 X3, X1 = nv.PREC_F16X3, nv.PREC_F16X1
 
 
+_SIDE_STREAMS = {}
+STREAMS_ON = [os.environ.get("CRDR_CHARM_STREAMS", "1") != "0"]
+
+
+def run_concurrent(jobs, enabled=True):
+    """Enqueue independent launch chains (callables) on side streams, fork / join with events on the current stream.
+    Every chain's arithmetic is untouched, so results are bit-identical to running them one after the other."""
+    if not (enabled and STREAMS_ON[0]) or len(jobs) < 2:
+        for job in jobs:
+            job()
+        return
+    main = torch.cuda.current_stream()
+    pool = _SIDE_STREAMS.setdefault(main.device, [])
+    while len(pool) < min(len(jobs), 10):
+        pool.append(torch.cuda.Stream(device=main.device))
+    fork = torch.cuda.Event()
+    fork.record(main)
+    for i, job in enumerate(jobs):
+        side = pool[i % len(pool)]
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            job()
+        done = torch.cuda.Event()
+        done.record(side)
+        main.wait_event(done)
+
+
 def _sub(sd, prefix):
     """state_dict entries below ``prefix.`` with the prefix stripped."""
     p = prefix + "."
@@ -116,13 +143,16 @@ class Nlam:
         self.conv = Conv(sd, "conv", cfg)
 
     def __call__(self, x, scale=None, shift=None, out_f32=None):
-        t = x
-        for b in self.trunk:
-            t = b(t)
-        a = x
-        for b in self.attn:
-            a = b(a)
-        return self.conv(a, mode=nv.EPI_GATE, res=x, trunk=t, scale=scale, shift=shift, out_f32=out_f32)
+        res = {}
+
+        def chain(name, blocks):
+            t = x
+            for b in blocks:
+                t = b(t)
+            res[name] = t
+        # the two branches are independent three-bottleneck chains: side by side (their kernels overlap in the tails)
+        run_concurrent([lambda: chain("t", self.trunk), lambda: chain("a", self.attn)])
+        return self.conv(res["a"], mode=nv.EPI_GATE, res=x, trunk=res["t"], scale=scale, shift=shift, out_f32=out_f32)
 
 
 class InterpGain:
@@ -240,10 +270,11 @@ class HyperSynthesisEngine:
     def run(self, zhat, support, mean_coff, scale_coff, hyper32=None):
         """zhat: Act.  support: Act the outputs are written into.  hyper32: optional fp32 NHWC [.., 2*C]
         receiving cat[mu, std] (the reference's hyper_out) for API / test use."""
-        for branch, coff, f32off in ((self.mu, mean_coff, 0), (self.std, scale_coff, self.out_ch)):
+        def chain(branch, coff, f32off):
             t = branch[0](zhat, relu=True)
             t = branch[1](t, relu=True)
             branch[2](t, out=support, out_coff=coff, out_f32=hyper32, out_f32_coff=f32off)
+        run_concurrent([lambda: chain(self.mu, mean_coff, 0), lambda: chain(self.std, scale_coff, self.out_ch)])
 
 
 class SliceNet:
@@ -292,7 +323,6 @@ class CharmEngine:
         self.mean = [SliceNet(_sub(sd, f"mean_slice_transforms.{i}"), cfg, lens(self._segs_mean(i))) for i in range(num_slices)]
         self.scale = [SliceNet(_sub(sd, f"scale_slice_transforms.{i}"), cfg, lens(self._segs_scale(i))) for i in range(num_slices)]
         self.lrp = [SliceNet(_sub(sd, f"lrp_slice_transforms.{i}"), cfg, lens(self._segs_lrp(i))) for i in range(num_slices)]
-        self._streams = {}
 
     def n_support(self, s):
         return s if self.max_support < 0 else min(s, self.max_support)
@@ -310,28 +340,10 @@ class CharmEngine:
 
     def _concurrent(self, T):
         pair_tiles = (T.n * (-(-T.h // 16)) * (-(-T.w // 8)) + 1) // 2
-        return pair_tiles <= self.CONCURRENT_MAX_PAIR_TILES and os.environ.get("CRDR_CHARM_STREAMS", "1") != "0"
+        return pair_tiles <= self.CONCURRENT_MAX_PAIR_TILES
 
     def _run_jobs(self, jobs, concurrent):
-        if not concurrent or len(jobs) < 2:
-            for job in jobs:
-                job()
-            return
-        main = torch.cuda.current_stream()
-        dev = main.device
-        pool = self._streams.setdefault(dev, [])
-        while len(pool) < min(len(jobs), 10):
-            pool.append(torch.cuda.Stream(device=dev))
-        fork = torch.cuda.Event()
-        fork.record(main)
-        for i, job in enumerate(jobs):
-            side = pool[i % len(pool)]
-            side.wait_event(fork)
-            with torch.cuda.stream(side):
-                job()
-            done = torch.cuda.Event()
-            done.record(side)
-            main.wait_event(done)
+        run_concurrent(jobs, concurrent)
 
     def new_support(self, n, h, w, device):
         # zero-filled: the 64-channel blocks of the patch engine may read channels that are written later

@@ -5,6 +5,8 @@ import json
 import os
 import time
 
+_PROCESS_START = time.time()
+
 
 def rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -49,10 +51,13 @@ def gather_rows(rows, rank, world, scratch_dir=None, timeout_s=600.0):
     os.replace(mine + ".tmp", mine)
     if rank != 0:
         return []
+    # file fallback (no process group): a file left behind by an earlier, crashed run must not be merged -- only files
+    # written after this job started count (all ranks of a job start together on one host)
+    fresh = lambda p: os.path.exists(p) and os.path.getmtime(p) >= _PROCESS_START - 5.0
     out, deadline = [], time.time() + timeout_s
     for r in range(world):
         path = os.path.join(scratch_dir, f"_rows_rank{r}.json")
-        while not os.path.exists(path):
+        while not fresh(path):
             if time.time() > deadline:
                 raise TimeoutError(f"rank {r} never delivered its rows")
             time.sleep(0.05)

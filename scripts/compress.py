@@ -76,12 +76,22 @@ def main():
     model.load_learned_weight(ckpt_path=opt.model_path)
     model.codec_setup()
 
+    # -q / -b: the reference compares them with 0.0 unconditionally (a missing flag is a TypeError there); here a missing
+    # or negative -q is an error for the variable-rate models (their compress() needs rate_ind) and ignored by the
+    # single-rate one, a missing or negative -b means the model's default beta
+    uses_rate = getattr(model, "uses_rate", True)
+    if uses_rate and (opt.quality is None or opt.quality < 0.0):
+        raise SystemExit("compress.py: -q / --quality (0.0 .. rate_level - 1) is required for this model")
+    beta_kw = {"beta": opt.beta} if (getattr(model, "uses_beta", True) and opt.beta is not None and opt.beta >= 0.0) else {}
+    if world > 1 and os.environ.get("MASTER_ADDR") and not torch.distributed.is_initialized():
+        torch.distributed.init_process_group("gloo")   # only for the final gather of the per-image rows
+
     rows = []
-    images = [(p, load_image(p)) for p in mine]
+    images = ((p, load_image(p)) for p in mine)   # lazily: one batch of decoded images in memory at a time
     for group in sharding.same_shape_batches(images, opt.batch):
         x = torch.cat([im for _, im in group], dim=0)
         _, _, H, W = x.shape
-        kwargs = {"rate_ind": opt.quality} if opt.quality >= 0.0 else {}
+        kwargs = {"rate_ind": opt.quality} if uses_rate else {}
         outs = model.compress_batch(x, **kwargs)
         bins = []
         for (path, _), out in zip(group, outs):
@@ -97,8 +107,7 @@ def main():
                 "pred_bpp": out["pred_z_bpp"] + out["pred_y_bpp"], "num_pixel": H * W})
             bins.append(bin_path)
         if opt.decompress:
-            kw = {"beta": opt.beta} if opt.beta >= 0.0 else {}
-            imgs, _, _ = model.decompress_batch([load_byte_strings(b) for b in bins], **kw)
+            imgs, _, _ = model.decompress_batch([load_byte_strings(b) for b in bins], **beta_kw)
             for (path, _), k in zip(group, range(len(group))):
                 img_utils.imwrite(os.path.join(opt.save_dir, os.path.basename(path)), imgs[k:k + 1].cpu())
 
@@ -112,6 +121,8 @@ def main():
         logger.info(f"quality: {opt.quality}, beta: {opt.beta}")
         logger.info(f"num_image: {len(paths)}")
         logger.info(f"avg_bpp: {avg:.4f} [bpp]")
+    if world > 1 and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

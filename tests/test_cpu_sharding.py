@@ -60,3 +60,21 @@ def test_gather_rows_file_fallback(tmp_path):
     out[0] = sharding.gather_rows([{"k": 0}], 0, 2, str(tmp_path))
     th.join()
     assert sorted(r["k"] for r in out[0]) == [0, 1] and out[1] == []
+
+
+def test_stale_rank_files_are_not_merged(tmp_path):
+    """a _rows_rank*.json left by an earlier crashed run must not end up in _bitrates.csv."""
+    import json
+    import os
+    import time
+    import pytest
+    from crdr_b200 import sharding
+    stale = tmp_path / "_rows_rank1.json"
+    stale.write_text(json.dumps([{"img_name": "old.png"}]))
+    old = time.time() - 3600
+    os.utime(stale, (old, old))
+    with pytest.raises(TimeoutError):
+        sharding.gather_rows([{"img_name": "a.png"}], 0, 2, str(tmp_path), timeout_s=0.3)
+    stale.write_text(json.dumps([{"img_name": "b.png"}]))          # a fresh delivery of rank 1
+    rows = sharding.gather_rows([{"img_name": "a.png"}], 0, 2, str(tmp_path), timeout_s=5.0)
+    assert sorted(r["img_name"] for r in rows) == ["a.png", "b.png"]

@@ -104,7 +104,7 @@ BN_CASES = [  # (name, n, h, w, C, mid, beta adds, gain)
     ("g_s block 256/128 single tile", 1, 16, 8, 256, 128, False, False),
     ("g_s block 256/128 many tiles", 5, 64, 96, 256, 128, True, False),
     ("192/96 partial channel block", 2, 33, 24, 192, 96, True, True),
-    ("64/32", 1, 20, 20, 64, 32, False, True),
+    ("128/64", 1, 20, 20, 128, 64, False, True),
 ]
 
 
