@@ -167,6 +167,20 @@ class InterpGain:
         self.levels = self.w.shape[0]
         self._cache = {}
 
+    def vectors_cpu(self, q):
+        """(scale, shift) as CPU fp32 vectors for quality index q."""
+        q = float(q)
+        if not (0.0 <= q <= self.levels - 1):
+            raise AssertionError(f"rate_ind = {q} should be in [0, {self.levels - 1}]")
+        ind = torch.tensor(q, dtype=torch.float32)
+        lo = torch.floor(ind)
+        hi = torch.minimum(lo + 1.0, torch.tensor(float(self.levels - 1)))
+        alpha = hi - ind
+        l, r = int(lo.item()), int(hi.item())
+        w = self.w[l] * alpha + self.w[r] * (1 - alpha)
+        b = self.b[l] * alpha + self.b[r] * (1 - alpha)
+        return F.softplus(w).reshape(-1).contiguous(), b.reshape(-1).contiguous()
+
     def vectors(self, q):
         q = float(q)
         if q not in self._cache:
@@ -186,6 +200,34 @@ class InterpGain:
 
 def _gains(sd, count, device):
     return [InterpGain(sd[f"interp_ca_list.{i}.weight"], sd[f"interp_ca_list.{i}.bias"], device) for i in range(count)]
+
+
+class StaticVectors:
+    """Per-channel epilogue vectors that depend on a call parameter (quality index -> InterpChAtt gains, beta ->
+    conditioning biases) behind FIXED device addresses: the kernels always read one flat device buffer, and selecting
+    another parameter value is one device-to-device copy from that value's cached flat tensor.  Launch sequences (and
+    CUDA graphs of them) are therefore independent of q and beta.  One parameter value is live per engine at a time
+    (stream ordered): a caller that interleaves different q / beta on several streams needs one engine per stream."""
+
+    def __init__(self, sizes, device):
+        self.sizes, self.device = list(sizes), device
+        self.flat = torch.zeros(sum(self.sizes), dtype=torch.float32, device=device)
+        self.views, o = [], 0
+        for n in self.sizes:
+            self.views.append(self.flat[o:o + n])
+            o += n
+        self._cache, self._live = {}, None
+
+    def load(self, key, build):
+        """build() -> list of CPU fp32 vectors (one per view) for `key`; cached on the device per key."""
+        if key != self._live:
+            src = self._cache.get(key)
+            if src is None:
+                src = self._cache[key] = torch.cat([v.reshape(-1).float() for v in build()]).contiguous().to(self.device)
+                assert src.numel() == self.flat.numel()
+            self.flat.copy_(src)
+            self._live = key
+        return self.views
 
 
 class AnalysisEngine:
@@ -212,7 +254,15 @@ class AnalysisEngine:
         self.attn4 = Nlam(_sub(sd, "attn4"), cfg)
         # ElicEncoder (stage 1, elic_autoencoder.py:33-72) has no InterpChAtt layers: no gains, q is ignored
         self.gains = _gains(sd, 9, device) if "interp_ca_list.0.weight" in sd else None
+        self.gain_vecs = StaticVectors([n for gn in self.gains for n in (gn.w.shape[2],) * 2], device) if self.gains else None
         self.out_ch = sd["conv4.weight"].shape[0]
+
+    def gain_pairs(self, q):
+        """[(scale, shift)] * 9 at fixed device addresses, holding the vectors of quality index q."""
+        if not self.gains:
+            return [(None, None)] * 9
+        v = self.gain_vecs.load(float(q), lambda: [t for gn in self.gains for t in gn.vectors_cpu(q)])
+        return [(v[2 * i], v[2 * i + 1]) for i in range(len(self.gains))]
 
     @staticmethod
     def _blocks(blocks, x, g):
@@ -222,7 +272,7 @@ class AnalysisEngine:
 
     def run(self, img, q):
         """img: Act (n, H/2, W/2, 128) image patches (crdr_image_to_patches) -> (y planes Act, y fp32 NHWC tensor)."""
-        g = [gn.vectors(q) for gn in self.gains] if self.gains else [(None, None)] * 9
+        g = self.gain_pairs(q)
         x = self.conv1(img, scale=g[0][0], shift=g[0][1])
         x = self._blocks(self.block1, x, g[1])
         x = self.conv2(x, scale=g[2][0], shift=g[2][1])
@@ -506,6 +556,10 @@ class SynthesisEngine:
             self.mlp = [(sd[f"mlp.{i}.weight"].detach().to(device="cpu", dtype=torch.float32),
                          sd[f"mlp.{i}.bias"].detach().to(device="cpu", dtype=torch.float32)) for i in (0, 2)]
         self.gains = _gains(sd, 9, device) if "interp_ca_list.0.weight" in sd else None
+        self.gain_vecs = StaticVectors([n for gn in self.gains for n in (gn.w.shape[2],) * 2], device) if self.gains else None
+        if self.has_cond:
+            self.cond_vecs = StaticVectors([w.shape[0] for b in ("block1", "block2", "block3") for blk in self.proj[b] for (w, _) in blk],
+                                           device)
         self.max_beta, self.L, self.include_x = float(max_beta), int(L), bool(include_x)
         self.freq = torch.pow(torch.Tensor([2]), torch.arange(L))
         if use_pi:
@@ -535,24 +589,34 @@ class SynthesisEngine:
                             wc[o:o + cout, :, dh + 1, dw + 1] = wf[:, :, i, j].t()
         return Conv({"w.weight": wc, "w.bias": bc}, "w", cfg, padding=1)
 
+    def _cond_cpu(self, beta):
+        """The 27 conditioning bias vectors (block, bottleneck, proj_1..3) for beta, CPU fp32 (fourier_cond.py:21-37,
+        elic_interpca_beta_cond_autoencoder.py:142-152,52-65)."""
+        if not (0 <= beta <= self.max_beta):
+            raise AssertionError(f"beta = {beta} should be in [0, {self.max_beta}]")
+        b = torch.Tensor([beta]).float()
+        nb = (b / self.max_beta - 0.5) * 2
+        emb = torch.cat([torch.sin(nb * self.freq), torch.cos(nb * self.freq)], dim=0)
+        if self.include_x:
+            emb = torch.cat([nb, emb], dim=0)
+        c = emb.unsqueeze(0)
+        c = F.linear(torch.relu(F.linear(c, *self.mlp[0])), *self.mlp[1])  # [1, cond_ch]
+        return [F.linear(c, w, bb).reshape(-1) for b_ in ("block1", "block2", "block3") for blk in self.proj[b_] for (w, bb) in blk]
+
     def cond_vectors(self, beta):
+        """{block: [(add1, add2, add3)] * 3} at fixed device addresses, holding the vectors of `beta`."""
         if not self.has_cond:
             return {b: [(None, None, None)] * 3 for b in self.blocks}
         beta = float(beta)
-        if beta not in self._beta_cache:
-            if not (0 <= beta <= self.max_beta):
-                raise AssertionError(f"beta = {beta} should be in [0, {self.max_beta}]")
-            b = torch.Tensor([beta]).float()
-            nb = (b / self.max_beta - 0.5) * 2
-            emb = torch.cat([torch.sin(nb * self.freq), torch.cos(nb * self.freq)], dim=0)
-            if self.include_x:
-                emb = torch.cat([nb, emb], dim=0)
-            c = emb.unsqueeze(0)
-            c = F.linear(torch.relu(F.linear(c, *self.mlp[0])), *self.mlp[1])  # [1, cond_ch]
-            vec = {b_: [[(F.linear(c, w, bb)).reshape(-1).contiguous().to(self.device) for (w, bb) in blk] for blk in pr]
-                   for b_, pr in self.proj.items()}
-            self._beta_cache[beta] = vec
-        return self._beta_cache[beta]
+        v = self.cond_vecs.load(beta, lambda: self._cond_cpu(beta))
+        return {b_: [tuple(v[(bi * 3 + i) * 3 + k] for k in range(3)) for i in range(3)]
+                for bi, b_ in enumerate(("block1", "block2", "block3"))}
+
+    def gain_pairs(self, q):
+        if not self.gains:
+            return [(None, None)] * 9
+        v = self.gain_vecs.load(float(q), lambda: [t for gn in self.gains for t in gn.vectors_cpu(q)])
+        return [(v[2 * i], v[2 * i + 1]) for i in range(len(self.gains))]
 
     def _blocks(self, name, x, cond, g):
         blks = self.blocks[name]
@@ -563,7 +627,7 @@ class SynthesisEngine:
 
     def run(self, yhat32, q, beta):
         """yhat32: fp32 NHWC [n, h, w, C] -> phase-packed fp32 image [n, 8h, 8w, 16] (see _phase_packed)."""
-        g = [gn.vectors(q) for gn in self.gains] if self.gains else [(None, None)] * 9
+        g = self.gain_pairs(q)
         cond = self.cond_vectors(beta)
         n, h, w, c = yhat32.shape
         x = Act.empty(n, h, w, c, two=self.two, device=yhat32.device)

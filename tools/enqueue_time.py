@@ -7,7 +7,7 @@ import fixtures
 from crdr_b200 import engine as eng_mod
 model, _ = fixtures.build_model(seed=0, calibrated=True)
 eng = model.engine()
-for b in (24, 12):
+for b in [int(a) for a in sys.argv[1:]] or (24, 12):
     x = fixtures.image(b, 512, 768).cuda()
     for _ in range(2):
         a = eng.analysis(x, 1.5); eng.decode_device(a["z_sym"], a["y_sym"], 1.5, 3.84, (512, 768))
