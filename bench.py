@@ -144,7 +144,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="override the workload's images per rank and step")
     ap.add_argument("--workload", default="kodak24", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -261,10 +261,13 @@ def main():
     # ---- roofline of the dominant kernel: one instrumented step (per-launch CUDA events on the launching stream)
     eng_mod.PROFILE.clear()
     eng_mod.PROFILE_ON[0] = True
-    eng.graphs_enabled = False      # per-launch events need eager launches (small workloads replay CUDA graphs otherwise)
+    from crdr_b200 import codec as codec_mod
+    eng.graphs_enabled = False      # per-launch events need eager launches (small workloads replay CUDA graphs otherwise) ...
+    codec_mod.STREAMS_ON[0] = False  # ... one after the other on one stream (concurrent chains would be counted twice)
     device_step(0)
     torch.cuda.synchronize()
     eng.graphs_enabled = type(eng).graphs_enabled
+    codec_mod.STREAMS_ON[0] = True
     eng_mod.PROFILE_ON[0] = False
     conv_ms = sum(p[1].elapsed_time(p[2]) for p in eng_mod.PROFILE)
     conv_launches = len(eng_mod.PROFILE)
