@@ -14,8 +14,9 @@ A step = one encode + decode pass of the batch.
   e2e     : the same metric through the public API (model.compress_batch / decompress_batch) with HOST
             buffers: pinned host images in, .bin byte strings out, bytes in, host images out -- includes the
             host range coder and every host<->device copy.
-  roofline: the dominant kernel (conv_tcgen05_kernel): algorithmic conv FLOPs of a step / summed launch time
-            of that kernel in one instrumented step, against the measured bf16 peak.
+  roofline: the dominant kernels (conv_tcgen05_kernel and the fused bottleneck_bc_kernel): algorithmic conv FLOPs of a
+            step / summed launch time of those kernels in one instrumented (serial, eager) step, against the measured
+            bf16 peak.
   cpu_baseline / --impl reference: the CPU oracle port of the reference path (oracle/) on the host cores.
 """
 import argparse
@@ -36,7 +37,7 @@ H, W, BATCH = 512, 768, 24
 WORKLOADS = {
     "kodak24": (512, 768, 24, 24, "weak"),      # configs[1]
     "kodak1": (512, 768, 1, 1, "weak"),         # configs[0] shape: single-image latency
-    "clic": (1365, 2048, 16, 4, "strong"),      # configs[2]: a fixed list of 16 images sharded round-robin over the ranks
+    "clic": (1365, 2048, 16, 8, "strong"),      # configs[2]: a fixed list of 16 images sharded round-robin over the ranks
     "uhd": (2160, 3840, 1, 1, "weak"),          # configs[3]: single-image latency; one image per GPU at N = 8
 }
 SWEEP = [0.25 * i for i in range(17)]
@@ -294,10 +295,11 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                          "frac": achieved / tensor_peak,
-                         # dram__bytes_read+write per conv launch, averaged over the 369 launches of one step of this
-                         # workload (ncu capture: profiles/conv_dram_traffic_r01.txt); only valid for the default batch
-                         "traffic": 289.8e6 if default_cfg else None, "peak_source": peak_src,
-                         "kernel": "conv_tcgen05_kernel", "launches_per_step": conv_launches, "kernel_ms_per_step": conv_ms,
+                         # dram__bytes_read+write per contraction launch, averaged over the 352 launches of one step of
+                         # this workload (ncu capture: profiles/launches_r02_summary.txt); only valid for the default batch
+                         "traffic": 284.4e6 if default_cfg else None, "peak_source": peak_src,
+                         "kernel": "conv_tcgen05_kernel + bottleneck_bc_kernel (the tcgen05 contraction kernels)",
+                         "launches_per_step": conv_launches, "kernel_ms_per_step": conv_ms,
                          "flops_per_step": flops_step,
                          "note": "algorithmic FLOPs = 2 x 1,478,360 MAC/px x padded px; the F16X3 layers execute 3 fp16 MMAs "
                                  "per algorithmic MAC, so the precision-adjusted ceiling is ~42% of the bf16 peak"},
