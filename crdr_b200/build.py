@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-CU_SOURCES = ["conv_sm100.cu", "bottleneck_sm100.cu", "eltwise.cu", "c_abi.cu"]
+CU_SOURCES = ["conv_sm100.cu", "bottleneck_sm100.cu", "wgrad_sm100.cu", "train_sm100.cu", "eltwise.cu", "c_abi.cu"]
 CU_DEPS = CU_SOURCES + ["common.cuh", "sm100_device.cuh", os.path.join("..", "..", "include", "crdr_b200.h")]
 RANS_SOURCES = ["rans.cpp"]
 RANS_DEPS = RANS_SOURCES + [os.path.join("..", "..", "include", "crdr_rans.h")]

@@ -70,6 +70,19 @@ int max_abs_batch_launch(const float* x, int n, int64_t per, float* out, cudaStr
 int bits_launch(const float* lik, int n, int64_t per, float* bits, cudaStream_t st);
 int status_clear_bits_launch(uint32_t* status, uint32_t bits, cudaStream_t st);
 int max_abs_launch(const float* x, int64_t count, float* out, cudaStream_t st);
+size_t wgrad_workspace_bytes(const crdr_wgrad_desc* d);
+int wgrad_launch(const crdr_wgrad_desc* d, cudaStream_t st);
+int pack_weights_launch(const float* master, const int32_t* map, int64_t count, void* hi, void* lo, cudaStream_t st);
+int epi_bwd_launch(const crdr_epi_bwd_desc* d, cudaStream_t st);
+int colsum_finish_launch(const float* partial, int blocks, int nsums, int which, int c, float* out, float scale, int accumulate,
+                         cudaStream_t st);
+int gate_launch(const crdr_gate_desc* d, int backward, cudaStream_t st);
+int gauss_bwd_launch(const crdr_gauss_bwd_desc* d, cudaStream_t st);
+int mse_bwd_launch(const float* fake, int fake_cs, const float* real, int n, int hb, int wb, int h, int w, float coef, void* g,
+                   int g_cs, cudaStream_t st);
+int adam_launch(float* p, const float* g, float* m, float* v, int64_t count, float lr, float b1, float b2, float eps, int step,
+                const float* gscale_ptr, float gscale, cudaStream_t st);
+int sumsq_launch(const float* x, int64_t count, float* partial1024, float* out, cudaStream_t st);
 
 }  // namespace crdr
 
@@ -211,6 +224,51 @@ int crdr_bits_from_likelihood(const float* lik, int32_t n, int64_t per, float* b
 }
 int crdr_max_abs(const float* x, int64_t count, float* out, void* stream) {
   return max_abs_launch(x, count, out, (cudaStream_t)stream);
+}
+
+/* ---- training step ---- */
+int crdr_conv_dgrad(const crdr_conv_desc* d, void* stream) {
+  if (!d) { set_error("conv_dgrad: null descriptor"); return CRDR_ERR_BAD_SHAPE; }
+  return conv2d_launch(d, (cudaStream_t)stream);
+}
+size_t crdr_conv_wgrad_workspace(const crdr_wgrad_desc* d) { return d ? wgrad_workspace_bytes(d) : 0; }
+int crdr_conv_wgrad(const crdr_wgrad_desc* d, void* stream) {
+  if (!d) { set_error("conv_wgrad: null descriptor"); return CRDR_ERR_BAD_SHAPE; }
+  return wgrad_launch(d, (cudaStream_t)stream);
+}
+int crdr_pack_weights(const float* master, const int32_t* map, int64_t count, void* hi, void* lo, void* stream) {
+  return pack_weights_launch(master, map, count, hi, lo, (cudaStream_t)stream);
+}
+int crdr_epilogue_backward(const crdr_epi_bwd_desc* d, void* stream) {
+  if (!d) { set_error("epilogue_backward: null descriptor"); return CRDR_ERR_BAD_SHAPE; }
+  return epi_bwd_launch(d, (cudaStream_t)stream);
+}
+int crdr_colsum_finish(const float* partial, int32_t blocks, int32_t nsums, int32_t which, int32_t c, float* out, float scale,
+                       int32_t accumulate, void* stream) {
+  return colsum_finish_launch(partial, blocks, nsums, which, c, out, scale, accumulate, (cudaStream_t)stream);
+}
+int crdr_gate_forward(const crdr_gate_desc* d, void* stream) {
+  if (!d) { set_error("gate: null descriptor"); return CRDR_ERR_BAD_SHAPE; }
+  return gate_launch(d, 0, (cudaStream_t)stream);
+}
+int crdr_gate_backward(const crdr_gate_desc* d, void* stream) {
+  if (!d) { set_error("gate: null descriptor"); return CRDR_ERR_BAD_SHAPE; }
+  return gate_launch(d, 1, (cudaStream_t)stream);
+}
+int crdr_gauss_backward(const crdr_gauss_bwd_desc* d, void* stream) {
+  if (!d) { set_error("gauss_backward: null descriptor"); return CRDR_ERR_BAD_SHAPE; }
+  return gauss_bwd_launch(d, (cudaStream_t)stream);
+}
+int crdr_mse_backward(const float* fake, int32_t fake_cs, const float* real, int32_t n, int32_t hb, int32_t wb, int32_t h,
+                      int32_t w, float coef, void* g, int32_t g_cs, void* stream) {
+  return mse_bwd_launch(fake, fake_cs, real, n, hb, wb, h, w, coef, g, g_cs, (cudaStream_t)stream);
+}
+int crdr_adam_step(float* p, const float* g, float* m, float* v, int64_t count, float lr, float beta1, float beta2, float eps,
+                   int32_t step, const float* gscale_ptr, float gscale, void* stream) {
+  return adam_launch(p, g, m, v, count, lr, beta1, beta2, eps, step, gscale_ptr, gscale, (cudaStream_t)stream);
+}
+int crdr_sum_squares(const float* x, int64_t count, float* partial, float* out, void* stream) {
+  return sumsq_launch(x, count, partial, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

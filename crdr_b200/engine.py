@@ -80,7 +80,7 @@ def split_weight(w2d, device):
 class Phase:
     """One GEMM of a (possibly transposed) convolution: taps, packed weights and output phase."""
 
-    __slots__ = ("dh", "dw", "w_hi", "w_lo", "k_pad", "out_ph", "out_pw", "tmpl")
+    __slots__ = ("dh", "dw", "w_hi", "w_lo", "k_pad", "out_ph", "out_pw", "tmpl", "map")
 
 
 _TILE_N_CACHE = {}
@@ -115,7 +115,10 @@ class ConvOp:
     """
 
     def __init__(self, weight, bias, transposed=False, stride=1, padding=0, output_padding=0, cin_pad=None,
-                 device="cuda", seg_lens=None, algo=None):
+                 device="cuda", seg_lens=None, algo=None, index_mode=False, two_planes=True):
+        """index_mode (training, backward.PackedConv): `weight` holds 1 + master element indices instead of values; the
+        phases keep an int32 gather map and uninitialised matrices that crdr_pack_weights fills from the live parameter,
+        and `bias` (if any) is the live fp32 device parameter itself."""
         w = weight.detach().to(torch.float32).cpu()
         self.transposed, self.stride, self.padding, self.output_padding = transposed, stride, padding, output_padding
         if transposed:
@@ -126,8 +129,12 @@ class ConvOp:
         self.cin = cin_pad or cin
         assert self.cin % 8 == 0, "input channels must be padded to a multiple of 8"
         self.cout_pad = round_up(cout, 16)
-        self.bias = None if bias is None else bias.detach().to(device="cpu", dtype=torch.float32).contiguous().to(device)
+        if index_mode:
+            self.bias = bias
+        else:
+            self.bias = None if bias is None else bias.detach().to(device="cpu", dtype=torch.float32).contiguous().to(device)
         self.device = device
+        self.index_mode = index_mode
         # channel ranges the input is read from at launch (ChARM: hyper ++ slices); decides the 64-channel blocking
         self.seg_lens = list(seg_lens) if seg_lens else [self.cin]
         assert sum(self.seg_lens) == self.cin
@@ -168,14 +175,19 @@ class ConvOp:
             phs.out_ph, phs.out_pw = ph, pw
             w2d = self._pack(cols)
             phs.k_pad = w2d.shape[1]
-            phs.w_hi, phs.w_lo = split_weight(w2d, device)
+            if index_mode:
+                phs.map = (w2d.round().to(torch.int32) - 1).contiguous().to(device)
+                phs.w_hi = torch.empty(w2d.shape, dtype=torch.float16, device=device)
+                phs.w_lo = torch.empty(w2d.shape, dtype=torch.float16, device=device) if two_planes else None
+            else:
+                phs.w_hi, phs.w_lo = split_weight(w2d, device)
             # launch-descriptor template: everything that does not depend on the call (taps, packed weights, bias).
             # A launch copies it and fills in the tensors (the per-field ctypes stores were most of the enqueue cost).
             t = nv.ConvDesc()
             t.ntaps = len(taps)
             for i, (a, b) in enumerate(taps):
                 t.dh[i], t.dw[i] = a, b
-            t.w_hi, t.w_lo, t.k_pad = phs.w_hi.data_ptr(), phs.w_lo.data_ptr(), phs.k_pad
+            t.w_hi, t.w_lo, t.k_pad = phs.w_hi.data_ptr(), (phs.w_lo.data_ptr() if phs.w_lo is not None else None), phs.k_pad
             t.cout_pad, t.cout = self.cout_pad, self.cout
             t.out_ph, t.out_pw = ph, pw
             t.bias = self.bias.data_ptr() if self.bias is not None else None

@@ -90,6 +90,54 @@ class EbDesc(C.Structure):
     ]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("s", Planes), ("ca", C.c_int32),
+        ("b", Planes), ("cb", C.c_int32),
+        ("n", C.c_int32), ("hs", C.c_int32), ("ws", C.c_int32), ("hb", C.c_int32), ("wb", C.c_int32), ("stride", C.c_int32),
+        ("ntaps", C.c_int32),
+        ("dh", C.c_int8 * MAX_TAPS), ("dw", C.c_int8 * MAX_TAPS),
+        ("out", C.c_void_p),
+        ("sa", C.c_int64), ("sb", C.c_int64), ("st", C.c_int64),
+        ("scale", C.c_float), ("accumulate", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class EpiBwdDesc(C.Structure):
+    _fields_ = [
+        ("g", Planes), ("out", Planes),
+        ("m", C.c_int64), ("c", C.c_int32), ("relu", C.c_int32),
+        ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("f32_out", C.c_void_p), ("f32_res", C.c_void_p), ("f32_cs", C.c_int32), ("f32_coff", C.c_int32),
+        ("dv", Planes), ("dres", Planes),
+        ("partial", C.c_void_p), ("blocks", C.c_int32),
+    ]
+
+
+class GateDesc(C.Structure):
+    _fields_ = [
+        ("x", Planes), ("t", Planes), ("a", Planes),
+        ("m", C.c_int64), ("c", C.c_int32),
+        ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("out", Planes),
+        ("out_f32", C.c_void_p), ("out_f32_cs", C.c_int32), ("out_f32_coff", C.c_int32),
+        ("g", Planes), ("dx", Planes), ("dt", Planes), ("da", Planes),
+        ("partial", C.c_void_p), ("blocks", C.c_int32),
+    ]
+
+
+class GaussBwdDesc(C.Structure):
+    _fields_ = [
+        ("y", C.c_void_p), ("y_cs", C.c_int32), ("y_coff", C.c_int32),
+        ("noise", C.c_void_p), ("ms", C.c_void_p),
+        ("ms_cs", C.c_int32), ("mu_coff", C.c_int32), ("sigma_coff", C.c_int32),
+        ("n", C.c_int32), ("hw", C.c_int32), ("c", C.c_int32), ("c_total", C.c_int32), ("nchw_coff", C.c_int32),
+        ("scale_bound", C.c_float), ("lik_bound", C.c_float), ("coef", C.c_float),
+        ("gpre", Planes), ("dy", Planes), ("dmu", Planes), ("dsigma", Planes),
+    ]
+
+
 # every symbol include/crdr_b200.h declares (tests check the library exports all of them)
 SM100_SYMBOLS = [
     "crdr_abi_version", "crdr_last_error", "crdr_status_reset", "crdr_status_read", "crdr_status_peek_async",
@@ -98,6 +146,9 @@ SM100_SYMBOLS = [
     "crdr_gauss_quantize", "crdr_gauss_indexes", "crdr_gauss_dequantize", "crdr_eb_quantize",
     "crdr_eb_dequantize", "crdr_bits_from_likelihood", "crdr_max_abs", "crdr_max_abs_batch",
     "crdr_image_u8_to_patches", "crdr_phases_to_image_u8", "crdr_phases_to_image_ex",
+    "crdr_conv_dgrad", "crdr_conv_wgrad_workspace", "crdr_conv_wgrad", "crdr_pack_weights", "crdr_epilogue_backward",
+    "crdr_colsum_finish", "crdr_gate_forward", "crdr_gate_backward", "crdr_gauss_backward", "crdr_mse_backward",
+    "crdr_adam_step", "crdr_sum_squares",
 ]
 
 _lib = None
@@ -140,6 +191,20 @@ def lib():
         L.crdr_image_u8_to_patches.argtypes = [vp, i32, i32, i32, i32, i32, Planes, vp]
         L.crdr_phases_to_image_u8.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp]
         L.crdr_phases_to_image_ex.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, i32, vp]
+        f32 = C.c_float
+        L.crdr_conv_dgrad.argtypes = [C.POINTER(ConvDesc), vp]
+        L.crdr_conv_wgrad_workspace.argtypes = [C.POINTER(WgradDesc)]
+        L.crdr_conv_wgrad_workspace.restype = C.c_size_t
+        L.crdr_conv_wgrad.argtypes = [C.POINTER(WgradDesc), vp]
+        L.crdr_pack_weights.argtypes = [vp, vp, i64, vp, vp, vp]
+        L.crdr_epilogue_backward.argtypes = [C.POINTER(EpiBwdDesc), vp]
+        L.crdr_colsum_finish.argtypes = [vp, i32, i32, i32, i32, vp, f32, i32, vp]
+        L.crdr_gate_forward.argtypes = [C.POINTER(GateDesc), vp]
+        L.crdr_gate_backward.argtypes = [C.POINTER(GateDesc), vp]
+        L.crdr_gauss_backward.argtypes = [C.POINTER(GaussBwdDesc), vp]
+        L.crdr_mse_backward.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, f32, vp, i32, vp]
+        L.crdr_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp, f32, vp]
+        L.crdr_sum_squares.argtypes = [vp, i64, vp, vp, vp]
         L.crdr_debug_conv_epilogue.argtypes = [i32, i32]
         L.crdr_debug_conv_epilogue.restype = None
         assert L.crdr_abi_version() == 1

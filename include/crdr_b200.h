@@ -294,6 +294,116 @@ int crdr_max_abs(const float* x, int64_t count, float* out, void* stream);
 /* out[i] = max |x[i*per .. (i+1)*per)| for n consecutive images in one launch. */
 int crdr_max_abs_batch(const float* x, int32_t n, int64_t per, float* out, void* stream);
 
+/* =====================================================================================================================
+ * Training step (backward).  The reference's backward is torch.autograd behind `l_total.backward()`
+ * (rate_distortion_trainer.py:84) followed by clip_grad_norm_ / Adam (:85-87); the entry points below are the
+ * contractions and element-wise steps that autograd would dispatch for this model.  Activation gradients are single
+ * fp16 planes multiplied by the caller's loss scale; parameter gradients are fp32 in the parameter's own layout.
+ * ===================================================================================================================== */
+
+/* dgrad: the gradient w.r.t. a convolution's input is itself a convolution of the output gradient with the transposed
+ * (and, for stride 1, flipped) weights -- the same kernel and descriptor as crdr_conv2d, fed with matrices packed by
+ * crdr_pack_weights through a dgrad index map (torch: conv backward-data at every nn.Conv2d / nn.ConvTranspose2d). */
+int crdr_conv_dgrad(const crdr_conv_desc* d, void* stream);
+
+/* wgrad:  G[t][a][b] = sum over pixels p = (n, h, w) of the small grid   S[p][a] * B[n, h*stride + dh[t], w*stride + dw[t]][b]
+ *         out[t*st + a*sa + b*sb] (+)= scale * G[t][a][b]
+ * nn.Conv2d:          S = dY, B = X (input), stride = conv stride      -> weight.grad [co][ci][kh][kw]
+ * nn.ConvTranspose2d: S = X (input), B = dY, stride = deconv stride    -> weight.grad [ci][co][kh][kw]
+ * S / B: channel ranges [coff, coff + ca|cb) of NHWC fp16 planes (hi plane only).  Deterministic (fixed-order split-K). */
+typedef struct {
+  crdr_planes s;
+  int32_t ca;
+  crdr_planes b;
+  int32_t cb;
+  int32_t n, hs, ws, hb, wb, stride;
+  int32_t ntaps;
+  int8_t dh[CRDR_MAX_TAPS], dw[CRDR_MAX_TAPS];
+  float* out;
+  int64_t sa, sb, st;
+  float scale;
+  int32_t accumulate;
+  void* workspace;        /* device scratch for the split-K partial sums */
+  size_t workspace_bytes; /* >= crdr_conv_wgrad_workspace(d) for full parallelism; smaller values reduce the split count */
+} crdr_wgrad_desc;
+size_t crdr_conv_wgrad_workspace(const crdr_wgrad_desc* d);
+int crdr_conv_wgrad(const crdr_wgrad_desc* d, void* stream);
+
+/* packed[i] = split_fp16(master[map[i]]) (map[i] < 0: zero): re-packs a parameter into a K-major tensor-core matrix
+ * (forward, dgrad or phase-packed form) after every optimiser step.  lo may be NULL (single-plane matrices). */
+int crdr_pack_weights(const float* master, const int32_t* map, int64_t count, void* hi, void* lo, void* stream);
+
+/* Backward of the fused convolution epilogue  out = ([relu](acc + bias) [+ res | res + 0.5 tanh(.)]) * scale + shift:
+ *   g1 = g * scale;  dres += g1;  dv = relu ? g1 * (out > 0) : (half-tanh ? g1 * 0.5 * (1 - (2 (f32_out - f32_res))^2) : g1)
+ * and per-channel sums over the pixels, written per row block to partial[blocks][3][c]:
+ *   0: sum dv (bias.grad)   1: sum g (InterpChAtt bias path)   2: sum g * (out - shift) / scale (InterpChAtt weight path) */
+typedef struct {
+  crdr_planes g;
+  crdr_planes out;
+  int64_t m;
+  int32_t c;
+  int32_t relu;
+  const float* scale;
+  const float* shift;
+  const float* f32_out; /* half-tanh (LRP): the layer's fp32 result and its residual operand, NHWC */
+  const float* f32_res;
+  int32_t f32_cs, f32_coff;
+  crdr_planes dv;       /* may have hi == NULL (sums only) */
+  crdr_planes dres;     /* may have hi == NULL */
+  float* partial;       /* may be NULL */
+  int32_t blocks;       /* row blocks = grid size (1..4096) */
+} crdr_epi_bwd_desc;
+int crdr_epilogue_backward(const crdr_epi_bwd_desc* d, void* stream);
+/* out[c] (+)= scale * sum_b partial[b][which][c], blocks in ascending order */
+int crdr_colsum_finish(const float* partial, int32_t blocks, int32_t nsums, int32_t which, int32_t c, float* out, float scale,
+                       int32_t accumulate, void* stream);
+
+/* ChengNLAM gate as its own step (training keeps the logits): out = (x + t * sigmoid(a)) * scale + shift (cheng_nlam.py:23-29).
+ * Backward: dx += g * scale; dt = g * scale * sig; da = g * scale * t * sig * (1 - sig); partial[blocks][2][c]: sum g | sum g * pre */
+typedef struct {
+  crdr_planes x, t, a;
+  int64_t m;
+  int32_t c;
+  const float* scale;
+  const float* shift;
+  crdr_planes out;    /* forward */
+  float* out_f32;
+  int32_t out_f32_cs, out_f32_coff;
+  crdr_planes g, dx, dt, da; /* backward */
+  float* partial;
+  int32_t blocks;
+} crdr_gate_desc;
+int crdr_gate_forward(const crdr_gate_desc* d, void* stream);
+int crdr_gate_backward(const crdr_gate_desc* d, void* stream);
+
+/* Rate term of one slice group: loss += -coef * ln max(L(y + noise; mu, sigma), lik_bound)  (GaussianConditional._likelihood +
+ * LowerBound; ste_gaussian_conditional.py:20-27, minnen20_charm_context_model.py:118).  dy = dL/dy + gpre (the
+ * straight-through path of the quantised slice), dmu, dsigma. */
+typedef struct {
+  const float* y;
+  int32_t y_cs, y_coff;
+  const float* noise; /* NCHW [n][c_total][hw], this group's channels start at nchw_coff */
+  const float* ms;    /* NHWC fp32: mu at mu_coff, sigma at sigma_coff */
+  int32_t ms_cs, mu_coff, sigma_coff;
+  int32_t n, hw, c, c_total, nchw_coff;
+  float scale_bound, lik_bound, coef;
+  crdr_planes gpre;   /* may have hi == NULL */
+  crdr_planes dy, dmu, dsigma;
+} crdr_gauss_bwd_desc;
+int crdr_gauss_backward(const crdr_gauss_bwd_desc* d, void* stream);
+
+/* Gradient of coef/2 * sum (fake - real)^2 on the phase-packed output of the last up-convolution (distortion_loss.py:40-46):
+ * fake [n, hb, wb, >=16] fp32 (channel (ph*2+pw)*3 + c), real [n, 3, h, w] fp32 -> g [n, hb, wb, g_cs] fp16. */
+int crdr_mse_backward(const float* fake, int32_t fake_cs, const float* real, int32_t n, int32_t hb, int32_t wb, int32_t h,
+                      int32_t w, float coef, void* g, int32_t g_cs, void* stream);
+
+/* torch.optim.Adam step on flat fp32 buffers; the gradient is multiplied by gscale (* gscale_ptr[0] when given: the
+ * clip coefficient computed on the device).  step >= 1. */
+int crdr_adam_step(float* p, const float* g, float* m, float* v, int64_t count, float lr, float beta1, float beta2, float eps,
+                   int32_t step, const float* gscale_ptr, float gscale, void* stream);
+/* out[0] = sum x^2 (fixed order); partial: 1024 floats of scratch. */
+int crdr_sum_squares(const float* x, int64_t count, float* partial, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,330 @@
+"""GPU parity of the training-step primitives (through the C ABI) against torch.autograd on the same operands:
+wgrad (crdr_conv_wgrad), dgrad (crdr_conv_dgrad with device-packed matrices), the epilogue / gate / rate / MSE backward
+kernels, fused Adam and the gradient norm.  Tolerances are stated per test: fp16 operands are exact in the references
+(they are built from the same fp16 values), so what is compared is fp32 accumulation order only."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _act(x_nchw, two=False):
+    from crdr_b200.engine import Act
+    return Act.from_nchw(x_nchw.to(DEV), two=two)
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+WGRAD_CASES = [
+    # (n, hin, win, cin, cout, k, stride, pad, transposed)
+    (2, 32, 24, 96, 96, 3, 1, 1, False),
+    (3, 16, 16, 192, 96, 1, 1, 0, False),
+    (2, 32, 32, 192, 192, 5, 2, 2, False),
+    (2, 16, 24, 320, 256, 5, 2, 2, True),
+    (8, 4, 4, 192, 320, 5, 2, 2, True),       # z-sized grid: K blocks span several images
+    (2, 16, 16, 480, 224, 5, 1, 2, False),    # ChARM first layer: 2 M tiles, 8 boxes of N
+    (1, 20, 12, 32, 16, 3, 1, 1, False),      # narrow channels (boxes zero-filled past the tensor), ragged grid
+    (2, 16, 16, 192, 320, 3, 1, 1, True),     # h_s conv3: stride-1 transposed convolution
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_wgrad_matches_autograd(case):
+    from crdr_b200 import backward as bw
+    n, hin, win, cin, cout, k, stride, pad, transposed = case
+    g = torch.Generator().manual_seed(sum(case[:5]))
+    x = (torch.randn(n, cin, hin, win, generator=g)).half().float()
+    if transposed:
+        w = torch.randn(cin, cout, k, k, generator=g) * 0.05
+        ref_fwd = lambda xx, ww: F.conv_transpose2d(xx, ww, stride=stride, padding=pad, output_padding=stride - 1)
+    else:
+        w = torch.randn(cout, cin, k, k, generator=g) * 0.05
+        ref_fwd = lambda xx, ww: F.conv2d(xx, ww, stride=stride, padding=pad)
+    xd = x.to(DEV).double()
+    wd = w.to(DEV).double().requires_grad_(True)
+    y = ref_fwd(xd, wd)
+    dy = (torch.randn(y.shape, generator=g)).half().float()
+    y.backward(dy.to(DEV).double())
+    ref = wd.grad.float()
+
+    xa, dya = _act(x), _act(dy)
+    out = torch.zeros_like(ref)
+    taps = [(i - pad, j - pad) for i in range(k) for j in range(k)]
+    if transposed:   # S = X (small grid), B = dY; dW[ci][co][t]
+        bw.wgrad(xa, 0, cin, dya, 0, cout, taps, stride, out, cout * k * k, k * k, 1, scale=0.5)
+    else:            # S = dY, B = X; dW[co][ci][t]
+        bw.wgrad(dya, 0, cout, xa, 0, cin, taps, stride, out, cin * k * k, k * k, 1, scale=0.5)
+    torch.cuda.synchronize()
+    err = _rel(out * 2.0, ref)
+    assert err < 2e-5, (case, err)      # fp32 accumulation of exact fp16 products vs fp64
+    # accumulate flag and channel sub-ranges
+    out2 = ref.clone()
+    if not transposed and cin >= 64:
+        half = (cin // 2) // 8 * 8
+        sub = torch.zeros(cout, cin - half, k, k, device=DEV)
+        bw.wgrad(dya, 0, cout, xa, half, cin - half, taps, stride, sub, (cin - half) * k * k, k * k, 1)
+        torch.cuda.synchronize()
+        assert _rel(sub, ref[:, half:]) < 2e-5
+    if transposed:
+        bw.wgrad(xa, 0, cin, dya, 0, cout, taps, stride, out2, cout * k * k, k * k, 1, accumulate=True)
+    else:
+        bw.wgrad(dya, 0, cout, xa, 0, cin, taps, stride, out2, cin * k * k, k * k, 1, accumulate=True)
+    torch.cuda.synchronize()
+    assert _rel(out2, 2 * ref) < 2e-5
+
+
+DGRAD_CASES = [
+    (2, 32, 24, 96, 96, 3, 1, 1, False),
+    (2, 16, 16, 192, 96, 1, 1, 0, False),
+    (2, 32, 32, 192, 192, 5, 2, 2, False),
+    (2, 16, 24, 320, 256, 5, 2, 2, True),
+    (2, 16, 16, 480, 224, 5, 1, 2, False),
+    (2, 16, 16, 192, 320, 3, 1, 1, True),
+    (1, 24, 16, 256, 16, 3, 1, 1, False),     # the phase-packed last layer's adjoint: 16 input channels (gather engine)
+]
+
+
+@pytest.mark.parametrize("case", DGRAD_CASES)
+def test_dgrad_matches_autograd(case):
+    from crdr_b200 import backward as bw
+    from crdr_b200 import native as nv
+    n, hin, win, cin, cout, k, stride, pad, transposed = case
+    g = torch.Generator().manual_seed(7 + sum(case[:5]))
+    if transposed:
+        w = (torch.randn(cin, cout, k, k, generator=g) * 0.05).half().float()
+        ref_fwd = lambda xx, ww: F.conv_transpose2d(xx, ww, stride=stride, padding=pad, output_padding=stride - 1)
+    else:
+        w = (torch.randn(cout, cin, k, k, generator=g) * 0.05).half().float()
+        ref_fwd = lambda xx, ww: F.conv2d(xx, ww, stride=stride, padding=pad)
+    xd = torch.zeros(n, cin, hin, win, device=DEV, dtype=torch.float64, requires_grad=True)
+    y = ref_fwd(xd, w.to(DEV).double())
+    dy = torch.randn(y.shape, generator=g).half().float()
+    y.backward(dy.to(DEV).double())
+    ref = xd.grad.float()
+
+    master = w.to(DEV).contiguous()
+    ds = bw.DgradSet(master, transposed, stride, pad, k, [(0, cin)])     # > 320 input channels: two chunks
+    ds.repack()
+    dya = _act(dy)
+    from crdr_b200.engine import Act
+    out = Act.zeros(n, hin, win, cin, two=False, device=DEV)
+    ds.run(dya, out, accumulate=False)
+    torch.cuda.synchronize()
+    got = out.to_nchw()
+    # fp16 result of an fp32 accumulation: half an ulp of fp16 relative to each value, measured against the tensor's scale
+    err = _rel(got, ref)
+    assert err < 1.5e-3, (case, err)
+    # accumulate into an existing gradient through the residual epilogue (in place)
+    ds.run(dya, out)
+    torch.cuda.synchronize()
+    assert _rel(out.to_nchw(), 2 * ref) < 3e-3
+    nv.status_check()
+
+
+def test_pack_weights_matches_host_packing():
+    """Device gather through the index map == the host-side packing of the same values (forward matrices, both planes)."""
+    from crdr_b200 import backward as bw
+    from crdr_b200.engine import ConvOp
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(224, 352, 5, 5, generator=g) * 0.03
+    host = ConvOp(w, None, padding=2, device=DEV, seg_lens=[320, 32])
+    pc = bw.PackedConv(w.to(DEV), lambda t: t, two_planes=True, padding=2, seg_lens=[320, 32])
+    pc.repack()
+    torch.cuda.synchronize()
+    for a, b in zip(host.phases, pc.op.phases):
+        assert torch.equal(a.w_hi, b.w_hi) and torch.equal(a.w_lo, b.w_lo)
+
+
+def test_epilogue_backward_kernels():
+    from crdr_b200 import native as nv
+    from crdr_b200.engine import Act
+    g = torch.Generator().manual_seed(11)
+    n, h, w, c = 2, 12, 20, 96
+    m = n * h * w
+    L = nv.lib()
+    st = nv.stream_handle()
+    # --- relu + bias sums ------------------------------------------------------------------------------------
+    pre = torch.randn(n, c, h, w, generator=g)
+    out = _act(torch.relu(pre), two=True)
+    grad = torch.randn(n, c, h, w, generator=g).half().float()
+    ga = _act(grad)
+    dv = Act.empty(n, h, w, c, two=False, device=DEV)
+    blocks = 7
+    partial = torch.zeros(blocks * 3 * c, device=DEV)
+    d = nv.EpiBwdDesc()
+    d.g, d.out, d.dv = ga.planes(0), out.planes(0), dv.planes(0)
+    d.m, d.c, d.relu, d.partial, d.blocks = m, c, 1, partial.data_ptr(), blocks
+    nv.check(L.crdr_epilogue_backward(C.byref(d), st))
+    dbias = torch.zeros(c, device=DEV)
+    nv.check(L.crdr_colsum_finish(partial.data_ptr(), blocks, 3, 0, c, dbias.data_ptr(), 0.25, 0, st))
+    torch.cuda.synchronize()
+    ref = (grad * (out.to_nchw().cpu() > 0)).half().float()
+    assert torch.equal(dv.to_nchw().cpu(), ref)
+    assert _rel(dbias.cpu(), 0.25 * ref.sum((0, 2, 3))) < 1e-5
+    # --- residual + affine: dres accumulation, scale / shift sums -------------------------------------------
+    scale = (torch.rand(c, generator=g) + 0.5).to(DEV)
+    shift = torch.randn(c, generator=g).to(DEV)
+    v = torch.randn(n, c, h, w, generator=g)
+    o = _act(v * scale.cpu().view(1, -1, 1, 1) + shift.cpu().view(1, -1, 1, 1), two=True)
+    dres = _act(torch.randn(n, c, h, w, generator=g).half().float())
+    dres0 = dres.to_nchw().cpu()
+    d = nv.EpiBwdDesc()
+    d.g, d.out, d.dv, d.dres = ga.planes(0), o.planes(0), dv.planes(0), dres.planes(0)
+    d.m, d.c, d.scale, d.shift, d.partial, d.blocks = m, c, scale.data_ptr(), shift.data_ptr(), partial.data_ptr(), blocks
+    nv.check(L.crdr_epilogue_backward(C.byref(d), st))
+    sums = torch.zeros(3, c, device=DEV)
+    for k in range(3):
+        nv.check(L.crdr_colsum_finish(partial.data_ptr(), blocks, 3, k, c, sums[k].data_ptr(), 1.0, 0, st))
+    torch.cuda.synchronize()
+    g1 = grad * scale.cpu().view(1, -1, 1, 1)
+    assert torch.equal(dv.to_nchw().cpu(), g1.half().float())
+    assert _rel(dres.to_nchw().cpu(), dres0 + g1) < 1e-3
+    assert _rel(sums[0].cpu(), g1.sum((0, 2, 3))) < 1e-3
+    assert _rel(sums[1].cpu(), grad.sum((0, 2, 3))) < 1e-5
+    assert _rel(sums[2].cpu(), (grad * o.to_nchw().cpu().sub(shift.cpu().view(1, -1, 1, 1)).div(scale.cpu().view(1, -1, 1, 1))).sum((0, 2, 3))) < 1e-4
+    nv.status_check()
+
+
+def test_gate_forward_backward():
+    from crdr_b200 import native as nv
+    from crdr_b200.engine import Act
+    g = torch.Generator().manual_seed(5)
+    n, h, w, c = 2, 8, 12, 320
+    m = n * h * w
+    x, t, a = (torch.randn(n, c, h, w, generator=g, requires_grad=True) for _ in range(3))
+    scale = (torch.rand(c, generator=g) + 0.5).requires_grad_(True)
+    shift = torch.randn(c, generator=g).requires_grad_(True)
+    xa, ta, aa = _act(x.detach(), True), _act(t.detach(), True), _act(a.detach(), True)
+    xr, tr, ar = (p.to_nchw().cpu().requires_grad_(True) for p in (xa, ta, aa))
+    ref = (xr + tr * torch.sigmoid(ar)) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    grad = torch.randn(n, c, h, w, generator=g).half().float()
+    ref.backward(grad)
+    out = Act.empty(n, h, w, c, two=True, device=DEV)
+    o32 = torch.empty(n, h, w, c, device=DEV)
+    sc, sh = scale.detach().to(DEV), shift.detach().to(DEV)
+    d = nv.GateDesc()
+    d.x, d.t, d.a, d.out = xa.planes(0), ta.planes(0), aa.planes(0), out.planes(0)
+    d.m, d.c, d.scale, d.shift, d.blocks = m, c, sc.data_ptr(), sh.data_ptr(), 16
+    d.out_f32, d.out_f32_cs, d.out_f32_coff = o32.data_ptr(), c, 0
+    L, st = nv.lib(), nv.stream_handle()
+    nv.check(L.crdr_gate_forward(C.byref(d), st))
+    torch.cuda.synchronize()
+    assert _rel(o32.permute(0, 3, 1, 2).cpu(), ref.detach()) < 1e-6
+    assert _rel(out.to_nchw().cpu(), ref.detach()) < 1e-6
+    ga = _act(grad)
+    dx = Act.zeros(n, h, w, c, two=False, device=DEV)
+    dt, da = Act.empty(n, h, w, c, two=False, device=DEV), Act.empty(n, h, w, c, two=False, device=DEV)
+    partial = torch.zeros(16 * 2 * c, device=DEV)
+    d.g, d.dx, d.dt, d.da, d.partial = ga.planes(0), dx.planes(0), dt.planes(0), da.planes(0), partial.data_ptr()
+    nv.check(L.crdr_gate_backward(C.byref(d), st))
+    sums = torch.zeros(2, c, device=DEV)
+    for k in range(2):
+        nv.check(L.crdr_colsum_finish(partial.data_ptr(), 16, 2, k, c, sums[k].data_ptr(), 1.0, 0, st))
+    torch.cuda.synchronize()
+    assert _rel(dx.to_nchw().cpu(), xr.grad) < 1e-3
+    assert _rel(dt.to_nchw().cpu(), tr.grad) < 1e-3
+    assert _rel(da.to_nchw().cpu(), ar.grad) < 1e-3
+    assert _rel(sums[0].cpu(), shift.grad) < 1e-5
+    assert _rel(sums[1].cpu(), scale.grad) < 1e-4
+    nv.status_check()
+
+
+def test_gauss_backward_matches_autograd(oracle):
+    """Rate-term gradients vs autograd through the oracle's GaussianConditional (likelihood of y + noise, lower bounds)."""
+    from crdr_b200 import native as nv
+    from crdr_b200.engine import Act
+    from compressai.entropy_models import GaussianConditional
+    g = torch.Generator().manual_seed(9)
+    n, h, w, c, ctot, coff = 2, 6, 10, 32, 96, 32
+    gc = GaussianConditional(None, scale_bound=0.11)
+    y = (torch.randn(n, c, h, w, generator=g) * 3).requires_grad_(True)
+    mu = torch.randn(n, c, h, w, generator=g).requires_grad_(True)
+    sigma = torch.exp(torch.randn(n, c, h, w, generator=g) * 1.5 - 1.0).requires_grad_(True)   # some below the 0.11 bound
+    noise = torch.rand(n, ctot, h, w, generator=g) - 0.5
+    lik = gc.likelihood_lower_bound(gc._likelihood(y + noise[:, coff:coff + c], sigma, mu))
+    coef = 37.5
+    (-coef * torch.log(lik)).sum().backward()
+    nhwc = lambda t: t.detach().permute(0, 2, 3, 1).contiguous()
+    y32 = torch.zeros(n, h, w, ctot, device=DEV)
+    y32[..., coff:coff + c] = nhwc(y).to(DEV)
+    ms = torch.zeros(n, h, w, 2 * ctot, device=DEV)
+    ms[..., coff:coff + c] = nhwc(mu).to(DEV)
+    ms[..., ctot + coff:ctot + coff + c] = nhwc(sigma).to(DEV)
+    gpre_t = torch.randn(n, c, h, w, generator=g).half().float()
+    gpre = _act(gpre_t)
+    dy, dms = Act.zeros(n, h, w, ctot, two=False, device=DEV), Act.zeros(n, h, w, 2 * ctot, two=False, device=DEV)
+    nz = noise.to(DEV).contiguous()
+    d = nv.GaussBwdDesc()
+    d.y, d.y_cs, d.y_coff = y32.data_ptr(), ctot, coff
+    d.noise, d.ms, d.ms_cs, d.mu_coff, d.sigma_coff = nz.data_ptr(), ms.data_ptr(), 2 * ctot, coff, ctot + coff
+    d.n, d.hw, d.c, d.c_total, d.nchw_coff = n, h * w, c, ctot, coff
+    d.scale_bound, d.lik_bound, d.coef = 0.11, 1e-9, coef
+    d.gpre, d.dy = gpre.planes(0), dy.planes(coff)
+    d.dmu, d.dsigma = dms.planes(coff), dms.planes(ctot + coff)
+    nv.check(nv.lib().crdr_gauss_backward(C.byref(d), nv.stream_handle()))
+    torch.cuda.synchronize()
+    got_dy = dy.to_nchw().cpu()[:, coff:coff + c]
+    got_dmu = dms.to_nchw().cpu()[:, coff:coff + c]
+    got_ds = dms.to_nchw().cpu()[:, ctot + coff:ctot + coff + c]
+    assert _rel(got_dy, y.grad + gpre_t) < 2e-3
+    assert _rel(got_dmu, mu.grad) < 2e-3
+    assert _rel(got_ds, sigma.grad) < 2e-3
+    nv.status_check()
+
+
+def test_mse_backward_adam_and_norm():
+    from crdr_b200 import native as nv
+    L, st = nv.lib(), nv.stream_handle()
+    g = torch.Generator().manual_seed(13)
+    n, H, W = 2, 20, 24
+    real = torch.rand(n, 3, H, W, generator=g) * 2 - 1
+    fake = (torch.rand(n, 3, H, W, generator=g) * 2 - 1).requires_grad_(True)
+    loss = 150.0 * F.mse_loss((real + 1) / 2, (fake + 1) / 2)
+    loss.backward()
+    S = 4096.0
+    hb, wb = H // 2, W // 2
+    packed = torch.zeros(n, hb, wb, 16)
+    for ph in range(2):
+        for pw in range(2):
+            packed[..., (ph * 2 + pw) * 3:(ph * 2 + pw) * 3 + 3] = fake.detach()[:, :, ph::2, pw::2].permute(0, 2, 3, 1)
+    gp = torch.empty(n, hb, wb, 16, dtype=torch.float16, device=DEV)
+    coef = S * 150.0 * 2.0 * 0.25 / (n * 3 * H * W)
+    packed_d, real_d = packed.to(DEV), real.to(DEV).contiguous()
+    nv.check(L.crdr_mse_backward(packed_d.data_ptr(), 16, real_d.data_ptr(), n, hb, wb, H, W, coef, gp.data_ptr(), 16, st))
+    torch.cuda.synchronize()
+    got = torch.zeros(n, 3, H, W)
+    for ph in range(2):
+        for pw in range(2):
+            got[:, :, ph::2, pw::2] = gp.cpu().float()[..., (ph * 2 + pw) * 3:(ph * 2 + pw) * 3 + 3].permute(0, 3, 1, 2)
+    assert _rel(got / S, fake.grad) < 1e-3
+    assert float(gp[..., 12:].abs().max()) == 0.0
+    # Adam + squared norm vs torch.optim.Adam / clip_grad_norm_
+    count = 100_003
+    p0 = torch.randn(count, generator=g)
+    grads = [torch.randn(count, generator=g) for _ in range(3)]
+    pt = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([pt], lr=1e-3)
+    p = p0.to(DEV).clone()
+    m, v = torch.zeros(count, device=DEV), torch.zeros(count, device=DEV)
+    partial, nrm = torch.zeros(1024, device=DEV), torch.zeros(1, device=DEV)
+    for i, gr in enumerate(grads):
+        pt.grad = gr.clone()
+        total = torch.nn.utils.clip_grad_norm_([pt], 1.0)
+        opt.step()
+        gd = gr.to(DEV)
+        nv.check(L.crdr_sum_squares(gd.data_ptr(), count, partial.data_ptr(), nrm.data_ptr(), st))
+        torch.cuda.synchronize()
+        assert abs(math.sqrt(float(nrm)) - float(total)) / float(total) < 1e-5
+        clip = min(1.0, 1.0 / (math.sqrt(float(nrm)) + 1e-6))
+        nv.check(L.crdr_adam_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), count, 1e-3, 0.9, 0.999, 1e-8, i + 1,
+                                  None, clip, st))
+    torch.cuda.synchronize()
+    assert float((p.cpu() - pt.detach()).abs().max()) < 2e-6
