@@ -65,12 +65,13 @@ def index_weight(shape):
 class PackedConv:
     """A ConvOp whose matrices are gathered on the device from a master fp32 parameter (``repack``)."""
 
-    def __init__(self, master, weight_of_index, two_planes, **conv_kwargs):
+    def __init__(self, master, weight_of_index, two_planes, bias=None, **conv_kwargs):
         """master: fp32 device parameter (any shape).  weight_of_index(idx) -> the tensor ConvOp takes as `weight`,
-        computed from the index tensor by pure indexing ops (permute / flip / slice / zero padding)."""
+        computed from the index tensor by pure indexing ops (permute / flip / slice / zero padding).  bias: the live
+        fp32 device vector the launches read (or None)."""
         self.master = master
         w = weight_of_index(index_weight(tuple(master.shape)))
-        self.op = ConvOp(w, None, device=master.device, index_mode=True, two_planes=two_planes, **conv_kwargs)
+        self.op = ConvOp(w, bias, device=master.device, index_mode=True, two_planes=two_planes, **conv_kwargs)
 
     def repack(self):
         L, st = nv.lib(), nv.stream_handle()
@@ -119,10 +120,12 @@ class DgradSet:
         for pc, _, _ in self.parts:
             pc.repack()
 
-    def run(self, dv, grad, accumulate=True):
-        """dv: Act (fp16 gradient of the convolution result); grad: Act the input gradient is accumulated into."""
+    def run(self, dv, grad, accumulate=True, dv_coff=0, dv_c=None):
+        """dv: Act (fp16 gradient of the convolution result; channels [dv_coff, dv_coff + dv_c) when it is a range of a
+        wider tensor); grad: Act the input gradient is accumulated into."""
+        segs = None if dv_c is None else [(dv_coff, dv_c)]
         for pc, coff, cnt in self.parts:
             if accumulate:
-                pc.op(dv, out=grad, out_coff=coff, precision=nv.PREC_F16X1, mode=nv.EPI_RESIDUAL, res=grad, res_coff=coff)
+                pc.op(dv, segs=segs, out=grad, out_coff=coff, precision=nv.PREC_F16X1, mode=nv.EPI_RESIDUAL, res=grad, res_coff=coff)
             else:
-                pc.op(dv, out=grad, out_coff=coff, precision=nv.PREC_F16X1)
+                pc.op(dv, segs=segs, out=grad, out_coff=coff, precision=nv.PREC_F16X1)

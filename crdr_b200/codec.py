@@ -58,21 +58,33 @@ def _sub(sd, prefix):
 
 
 class Conv:
-    """ConvOp + the launch-time defaults (precision / engine) shared by a whole sub-network."""
+    """ConvOp + the launch-time defaults (precision / engine) shared by a whole sub-network.
 
-    def __init__(self, sd, name, cfg, **kw):
-        self.op = ConvOp(sd[name + ".weight"], sd[name + ".bias"], device=cfg.device, **kw)
-        self.cfg = cfg
+    ``transform`` / ``bias_transform`` map the checkpoint tensors to the tensors the ConvOp takes (g_a conv1 as a 1x1
+    convolution over im2col patches, the phase-packed last up-convolution); they are pure indexing ops, so in training
+    mode (``cfg.train``: a train.TrainContext) the same function applied to an index tensor yields the gather map that
+    re-packs the live parameter on the device after every optimiser step (backward.PackedConv)."""
 
-    def __call__(self, x, **kw):
+    def __init__(self, sd, name, cfg, transform=None, bias_transform=None, **kw):
+        self.cfg, self.name, self.kw = cfg, name, kw
+        w, b = sd[name + ".weight"], sd.get(name + ".bias")
+        if cfg.train is None:
+            self.op = ConvOp(transform(w) if transform else w, bias_transform(b) if bias_transform else b, device=cfg.device, **kw)
+        else:
+            cfg.train.adopt(self, w, b, transform, bias_transform, two_planes=cfg.precision == X3, **kw)
+
+    def __call__(self, x, bwd_res=None, no_input_grad=False, **kw):
         kw.setdefault("precision", self.cfg.precision)
         kw.setdefault("engine", self.cfg.engine)
-        return self.op(x, **kw)
+        out = self.op(x, **kw)
+        if self.cfg.train is not None and self.cfg.train.tape is not None:
+            self.cfg.train.tape.append(("conv", self, x, kw, out, bwd_res, no_input_grad))
+        return out
 
 
 class NetCfg:
-    def __init__(self, device, precision, engine=nv.ENGINE_TCGEN05):
-        self.device, self.precision, self.engine = device, precision, engine
+    def __init__(self, device, precision, engine=nv.ENGINE_TCGEN05, train=None):
+        self.device, self.precision, self.engine, self.train = device, precision, engine, train
 
 
 class Bottleneck:
@@ -89,7 +101,7 @@ class Bottleneck:
         self.c3 = Conv(sd, names[2], cfg)
         self.cfg = cfg
         mid, cout = self.c2.op.cout, self.c3.op.cout
-        self.fused = (cfg.precision == X1 and cfg.engine == nv.ENGINE_TCGEN05 and self.c2.op.algo == "patch"
+        self.fused = (cfg.train is None and cfg.precision == X1 and cfg.engine == nv.ENGINE_TCGEN05 and self.c2.op.algo == "patch"
                       and self.c3.op.algo == "patch" and mid % 32 == 0 and 32 <= mid <= 128 and cout % 32 == 0 and cout <= 256
                       and self.c2.op.cin == mid and self.c3.op.cin == mid)
         if self.fused:
@@ -152,7 +164,22 @@ class Nlam:
             res[name] = t
         # the two branches are independent three-bottleneck chains: side by side (their kernels overlap in the tails)
         run_concurrent([lambda: chain("t", self.trunk), lambda: chain("a", self.attn)])
-        return self.conv(res["a"], mode=nv.EPI_GATE, res=x, trunk=res["t"], scale=scale, shift=shift, out_f32=out_f32)
+        train = self.conv.cfg.train
+        if train is None:
+            return self.conv(res["a"], mode=nv.EPI_GATE, res=x, trunk=res["t"], scale=scale, shift=shift, out_f32=out_f32)
+        # training: the gate is its own step so that the logits survive for the backward (crdr_gate_forward / _backward)
+        a = self.conv(res["a"])
+        out = Act.empty(x.n, x.h, x.w, x.c, two=x.lo is not None, device=x.hi.device)
+        d = nv.GateDesc()
+        d.x, d.t, d.a, d.out = x.planes(0), res["t"].planes(0), a.planes(0), out.planes(0)
+        d.m, d.c, d.scale, d.shift = x.pixels, x.c, nv.ptr(scale), nv.ptr(shift)
+        d.blocks = max(1, min(1024, x.pixels // 64))
+        if out_f32 is not None:
+            d.out_f32, d.out_f32_cs, d.out_f32_coff = out_f32.data_ptr(), out_f32.shape[-1], 0
+        nv.check(nv.lib().crdr_gate_forward(C.byref(d), nv.stream_handle()))
+        if train.tape is not None:
+            train.tape.append(("gate", x, res["t"], a, out, scale, shift))
+        return out
 
 
 class InterpGain:
@@ -235,16 +262,13 @@ class AnalysisEngine:
     Every InterpChAtt that follows a layer is folded into that layer's last epilogue."""
     PATCH_CH = 80   # channels of the im2col'd image (crdr_image_to_patches): 75 + zero padding to a multiple of 16
 
-    def __init__(self, sd, device, precision=X3, engine=nv.ENGINE_TCGEN05):
-        cfg = NetCfg(device, precision, engine)
+    def __init__(self, sd, device, precision=X3, engine=nv.ENGINE_TCGEN05, train=None):
+        cfg = NetCfg(device, precision, engine, train)
         self.cfg = cfg
         # conv1 (5x5, stride 2, 3 -> C; elic_autoencoder.py:42) runs as a 1x1 convolution over the im2col'd image written
         # by crdr_image_to_patches: patch channel (kh*5+kw)*3+c, 75 real + 5 zero = 80 channels = one full K block and one
         # K step of a second (the TMA box of that block zero-fills past channel 80, so the tensor stays 80 wide)
-        w1 = sd["conv1.weight"]                                        # (C, 3, 5, 5)
-        wp = torch.zeros(w1.shape[0], self.PATCH_CH, 1, 1, dtype=w1.dtype)
-        wp[:, :75, 0, 0] = w1.permute(0, 2, 3, 1).reshape(w1.shape[0], 75)
-        self.conv1 = Conv({"w.weight": wp, "w.bias": sd["conv1.bias"]}, "w", cfg)
+        self.conv1 = Conv(sd, "conv1", cfg, transform=self._patch_weight)
         self.conv2 = Conv(sd, "conv2", cfg, stride=2, padding=2)
         self.conv3 = Conv(sd, "conv3", cfg, stride=2, padding=2)
         self.conv4 = Conv(sd, "conv4", cfg, stride=2, padding=2)
@@ -257,11 +281,21 @@ class AnalysisEngine:
         self.gain_vecs = StaticVectors([n for gn in self.gains for n in (gn.w.shape[2],) * 2], device) if self.gains else None
         self.out_ch = sd["conv4.weight"].shape[0]
 
+    @classmethod
+    def _patch_weight(cls, w1):
+        """(C, 3, 5, 5) -> (C, 80, 1, 1) over the patch channels (kh*5+kw)*3+c."""
+        wp = torch.zeros(w1.shape[0], cls.PATCH_CH, 1, 1, dtype=w1.dtype)
+        wp[:, :75, 0, 0] = w1.permute(0, 2, 3, 1).reshape(w1.shape[0], 75)
+        return wp
+
     def gain_pairs(self, q):
         """[(scale, shift)] * 9 at fixed device addresses, holding the vectors of quality index q."""
         if not self.gains:
             return [(None, None)] * 9
-        v = self.gain_vecs.load(float(q), lambda: [t for gn in self.gains for t in gn.vectors_cpu(q)])
+        if self.cfg.train is not None:
+            v = self.cfg.train.live_gains(self, "encoder", q)
+        else:
+            v = self.gain_vecs.load(float(q), lambda: [t for gn in self.gains for t in gn.vectors_cpu(q)])
         return [(v[2 * i], v[2 * i + 1]) for i in range(len(self.gains))]
 
     @staticmethod
@@ -273,7 +307,7 @@ class AnalysisEngine:
     def run(self, img, q):
         """img: Act (n, H/2, W/2, 128) image patches (crdr_image_to_patches) -> (y planes Act, y fp32 NHWC tensor)."""
         g = self.gain_pairs(q)
-        x = self.conv1(img, scale=g[0][0], shift=g[0][1])
+        x = self.conv1(img, scale=g[0][0], shift=g[0][1], no_input_grad=True)
         x = self._blocks(self.block1, x, g[1])
         x = self.conv2(x, scale=g[2][0], shift=g[2][1])
         x = self._blocks(self.block2, x, g[3])
@@ -289,8 +323,8 @@ class AnalysisEngine:
 class HyperAnalysisEngine:
     """h_a: Minnen20HyperEncoder.forward (minnen20_hyperprior.py:9-27)."""
 
-    def __init__(self, sd, device, precision=X3, engine=nv.ENGINE_TCGEN05):
-        cfg = NetCfg(device, precision, engine)
+    def __init__(self, sd, device, precision=X3, engine=nv.ENGINE_TCGEN05, train=None):
+        cfg = NetCfg(device, precision, engine, train)
         self.conv1 = Conv(sd, "conv1", cfg, padding=1)
         self.conv2 = Conv(sd, "conv2", cfg, stride=2, padding=2)
         self.conv3 = Conv(sd, "conv3", cfg, stride=2, padding=2)
@@ -309,8 +343,8 @@ class HyperSynthesisEngine:
     """h_s: Minnen20HyperDecoder.forward (minnen20_hyperprior.py:30-58); the two branches write their
     320 channels straight into the ChARM support tensor (no torch.cat)."""
 
-    def __init__(self, sd, device, precision=X3, engine=nv.ENGINE_TCGEN05):
-        cfg = NetCfg(device, precision, engine)
+    def __init__(self, sd, device, precision=X3, engine=nv.ENGINE_TCGEN05, train=None):
+        cfg = NetCfg(device, precision, engine, train)
         mk = lambda p: [Conv(sd, f"{p}.conv1", cfg, transposed=True, stride=2, padding=2, output_padding=1),
                         Conv(sd, f"{p}.conv2", cfg, transposed=True, stride=2, padding=2, output_padding=1),
                         Conv(sd, f"{p}.conv3", cfg, transposed=True, stride=1, padding=1)]
@@ -335,10 +369,10 @@ class SliceNet:
         self.c2 = Conv(sd, "model.2", cfg, padding=2)
         self.c3 = Conv(sd, "model.4", cfg, padding=1)
 
-    def __call__(self, x, segs, **last):
+    def __call__(self, x, segs, bwd_res=None, **last):
         t = self.c1(x, segs=segs, relu=True)
         t = self.c2(t, relu=True)
-        return self.c3(t, **last)
+        return self.c3(t, bwd_res=bwd_res, **last)
 
 
 class GaussianParams:
@@ -359,8 +393,8 @@ class CharmEngine:
     """
 
     def __init__(self, sd, num_slices, slice_ch, hyper_ch, max_support, device, precision=X3,
-                 engine=nv.ENGINE_TCGEN05):
-        cfg = NetCfg(device, precision, engine)
+                 engine=nv.ENGINE_TCGEN05, train=None):
+        cfg = NetCfg(device, precision, engine, train)
         self.cfg = cfg
         self.S, self.sc, self.hc = num_slices, slice_ch, hyper_ch
         self.max_support = max_support
@@ -431,7 +465,8 @@ class CharmEngine:
     def refine(self, T, s, yq32, yhat32):
         """LRP: y_hat_s = yq_s + 0.5 tanh(lrp(...)) -> support tensor (planes) and yhat32 (fp32 NHWC)."""
         self.lrp[s](T, self._segs_lrp(s), mode=nv.EPI_HALF_TANH, res=yq32, res_coff=s * self.sc, out=T,
-                    out_coff=self.off_y + s * self.sc, out_f32=yhat32, out_f32_coff=s * self.sc)
+                    out_coff=self.off_y + s * self.sc, out_f32=yhat32, out_f32_coff=s * self.sc,
+                    bwd_res=(T, self.off_tmp + s * self.sc))   # backward: the quantised slice's planes live in the scratch slot
 
     def gauss_desc(self, gp, T, s, cnt, n, hw, ms, y32=None, yq32=None, sym=None, idx=None, lik=None, sym16=None,
                    idx8=None, noise=None, lik_noisy=None):
@@ -480,6 +515,8 @@ class CharmEngine:
             d = self.gauss_desc(gp, T, grp[0], len(grp), n, h * w, ms, y32=y32, yq32=yq32, sym=sym, idx=idx, lik=lik,
                                 sym16=sym16, idx8=idx8, noise=noise, lik_noisy=lik_noisy)
             nv.check(L.crdr_gauss_quantize(C.byref(d), nv.stream_handle()))
+            if self.cfg.train is not None and self.cfg.train.tape is not None:
+                self.cfg.train.tape.append(("gauss", grp[0], len(grp), T, y32, ms, noise))
             self._run_jobs([(lambda s=s: self.refine(T, s, yq32, yhat32)) for s in grp], conc)
         if noise is not None:
             return yhat32, sym, idx, lik, lik_noisy
@@ -530,17 +567,17 @@ class SynthesisEngine:
     the 27 projections are evaluated once per beta and enter as per-channel epilogue vectors."""
 
     def __init__(self, sd, max_beta=0.0, L=0, use_pi=False, include_x=False, use_tanh=False, device="cuda", precision=X1,
-                 engine=nv.ENGINE_TCGEN05):
+                 engine=nv.ENGINE_TCGEN05, train=None):
         if use_tanh:
             raise NotImplementedError("use_tanh=True decoders are not lowered (crdr.yaml uses use_tanh: False)")
-        cfg = NetCfg(device, precision, engine)
+        cfg = NetCfg(device, precision, engine, train)
         self.cfg, self.device = cfg, device
         self.two = precision == X3
         up = lambda name: Conv(sd, name, cfg, transposed=True, stride=2, padding=2, output_padding=1)
         self.attn1 = Nlam(_sub(sd, "attn1"), cfg)
         self.conv1, self.conv2, self.conv3 = up("conv1"), up("conv2"), up("conv3")
         self.attn2 = Nlam(_sub(sd, "attn2"), cfg)
-        self.conv4p = self._phase_packed(sd["conv4.weight"], sd["conv4.bias"], cfg)
+        self.conv4p = Conv(sd, "conv4", cfg, transform=self._phase_weight, bias_transform=self._phase_bias, padding=1)
         self.blocks, self.proj = {}, {}
         # ElicDecoder / ElicInterpCaDecoder (stages 1 / 2: elic_autoencoder.py:75-119, elic_interpca_autoencoder.py:59-97)
         # have no beta conditioning; ElicDecoder has no InterpChAtt gains either
@@ -568,7 +605,7 @@ class SynthesisEngine:
         self.in_ch = sd["conv1.weight"].shape[0]
 
     @staticmethod
-    def _phase_packed(w, b, cfg):
+    def _phase_weight(w):
         """The last up-convolution (ConvTranspose2d 5x5, stride 2, padding 2, output_padding 1, Cout = 3) as ONE
         stride-1 3x3 convolution with 4 phases x 3 = 12 (padded to 16) output channels: out[2a+ph, 2b+pw, c] uses the
         taps kh = ph + 2 - 2*dh, kw = pw + 2 - 2*dw (dh, dw in -1..1).  2.8x fewer (tiny-N) MMAs than four phase
@@ -576,18 +613,22 @@ class SynthesisEngine:
         cin, cout, kh, kw = w.shape
         assert (kh, kw) == (5, 5) and cout * 4 <= 16
         wc = torch.zeros(16, cin, 3, 3, dtype=torch.float32)
-        bc = torch.zeros(16, dtype=torch.float32)
-        wf, bf = w.detach().float().cpu(), b.detach().float().cpu()
+        wf = w.detach().float().cpu()
         for ph in range(2):
             for pw in range(2):
                 o = (ph * 2 + pw) * cout
-                bc[o:o + cout] = bf
                 for dh in (-1, 0, 1):
                     for dw in (-1, 0, 1):
                         i, j = ph + 2 - 2 * dh, pw + 2 - 2 * dw
                         if 0 <= i < 5 and 0 <= j < 5:
                             wc[o:o + cout, :, dh + 1, dw + 1] = wf[:, :, i, j].t()
-        return Conv({"w.weight": wc, "w.bias": bc}, "w", cfg, padding=1)
+        return wc
+
+    @staticmethod
+    def _phase_bias(b):
+        bc = torch.zeros(16, dtype=torch.float32, device=b.device)
+        bc[:4 * b.numel()] = b.detach().float().repeat(4)
+        return bc
 
     def _cond_cpu(self, beta):
         """The 27 conditioning bias vectors (block, bottleneck, proj_1..3) for beta, CPU fp32 (fourier_cond.py:21-37,
@@ -615,7 +656,10 @@ class SynthesisEngine:
     def gain_pairs(self, q):
         if not self.gains:
             return [(None, None)] * 9
-        v = self.gain_vecs.load(float(q), lambda: [t for gn in self.gains for t in gn.vectors_cpu(q)])
+        if self.cfg.train is not None:
+            v = self.cfg.train.live_gains(self, "decoder", q)
+        else:
+            v = self.gain_vecs.load(float(q), lambda: [t for gn in self.gains for t in gn.vectors_cpu(q)])
         return [(v[2 * i], v[2 * i + 1]) for i in range(len(self.gains))]
 
     def _blocks(self, name, x, cond, g):
@@ -633,6 +677,8 @@ class SynthesisEngine:
         x = Act.empty(n, h, w, c, two=self.two, device=yhat32.device)
         nv.check(nv.lib().crdr_affine_to_planes(yhat32.data_ptr(), c, 0, n * h * w, c, nv.ptr(g[0][0]), nv.ptr(g[0][1]),
                                                 x.planes(0), nv.stream_handle()))
+        if self.cfg.train is not None and self.cfg.train.tape is not None:
+            self.cfg.train.tape.append(("affine_in", x, g[0][0], g[0][1], yhat32))
         x = self.attn1(x, scale=g[1][0], shift=g[1][1])
         x = self.conv1(x, scale=g[2][0], shift=g[2][1])
         x = self._blocks("block1", x, cond, g[3])

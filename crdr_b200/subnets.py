@@ -93,8 +93,8 @@ class ElicEncoder(nn.Module):
         self.attn4 = _nlam(out_ch)
         self.num_downscale, self.latent_ch = 4, out_ch
 
-    def lower(self, device, **kw):
-        return codec.AnalysisEngine(dict(self.state_dict()), device, **kw)
+    def lower(self, device, sd=None, **kw):
+        return codec.AnalysisEngine((sd if sd is not None else dict(self.state_dict())), device, **kw)
 
 
 @ENCODER_REGISTRY.register()
@@ -116,8 +116,8 @@ class ElicInterpCaEncoder(nn.Module):
         self.interp_ca_list = _gain_list([m] * 7 + [out_ch] * 2, rate_level, ca_kwargs)
         self.num_downscale, self.latent_ch, self.rate_level = 4, out_ch, rate_level
 
-    def lower(self, device, **kw):
-        return codec.AnalysisEngine(dict(self.state_dict()), device, **kw)
+    def lower(self, device, sd=None, **kw):
+        return codec.AnalysisEngine((sd if sd is not None else dict(self.state_dict())), device, **kw)
 
 
 def _n002_init(module):
@@ -148,8 +148,8 @@ class ElicDecoder(nn.Module):
         self.conv4 = _deconv(m, out_ch)
         self.use_tanh = use_tanh
 
-    def lower(self, device, **kw):
-        return codec.SynthesisEngine(dict(self.state_dict()), use_tanh=self.use_tanh, device=device, **kw)
+    def lower(self, device, sd=None, **kw):
+        return codec.SynthesisEngine((sd if sd is not None else dict(self.state_dict())), use_tanh=self.use_tanh, device=device, **kw)
 
 
 @DECODER_REGISTRY.register()
@@ -191,8 +191,8 @@ class ElicInterpCaBetaCondDecoder(nn.Module):
         self.hparams = dict(max_beta=max_beta, L=L, use_pi=use_pi, include_x=include_x, use_tanh=use_tanh)
         self.max_beta, self.rate_level = max_beta, rate_level
 
-    def lower(self, device, **kw):
-        return codec.SynthesisEngine(dict(self.state_dict()), device=device, **self.hparams, **kw)
+    def lower(self, device, sd=None, **kw):
+        return codec.SynthesisEngine((sd if sd is not None else dict(self.state_dict())), device=device, **self.hparams, **kw)
 
 
 @HYPERENCODER_REGISTRY.register()
@@ -204,8 +204,8 @@ class Minnen20HyperEncoder(nn.Module):
         self.conv3 = _conv(256, bottleneck_z, 5, 2)
         self.num_downscale, self.latent_ch = 2, bottleneck_z
 
-    def lower(self, device, **kw):
-        return codec.HyperAnalysisEngine(dict(self.state_dict()), device, **kw)
+    def lower(self, device, sd=None, **kw):
+        return codec.HyperAnalysisEngine((sd if sd is not None else dict(self.state_dict())), device, **kw)
 
 
 @HYPERDECODER_REGISTRY.register()
@@ -218,8 +218,8 @@ class Minnen20HyperDecoder(nn.Module):
         self.hd_mu, self.hd_std = branch(), branch()
         self.out_ch = hyper_out_ch
 
-    def lower(self, device, **kw):
-        return codec.HyperSynthesisEngine(dict(self.state_dict()), device, **kw)
+    def lower(self, device, sd=None, **kw):
+        return codec.HyperSynthesisEngine((sd if sd is not None else dict(self.state_dict())), device, **kw)
 
 
 def _slice_net(cin, cout):
@@ -247,6 +247,6 @@ class Minnen20CharmContextModel(nn.Module):
             self.scale_slice_transforms.append(_slice_net(sup + hc, sc))
             self.lrp_slice_transforms.append(_slice_net(sup + hc + sc, sc))
 
-    def lower(self, device, **kw):
-        return codec.CharmEngine(dict(self.state_dict()), self.num_slices, self.slice_ch, self.hyper_ch,
+    def lower(self, device, sd=None, **kw):
+        return codec.CharmEngine((sd if sd is not None else dict(self.state_dict())), self.num_slices, self.slice_ch, self.hyper_ch,
                                  self.max_support_slices, device, **kw)

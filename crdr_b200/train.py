@@ -1,0 +1,604 @@
+"""Training step of the ChARM codec models on the CUDA engines: forward (training mode) + backward + optimiser.
+
+What it replaces in the reference: ``RateDistortionTrainer.optimize_parameters`` (rate_distortion_trainer.py:57-101):
+``run_model(is_train=True)`` -> rate + distortion losses -> ``l_total.backward()`` -> ``clip_grad_norm_`` ->
+``g_optimizer.step()`` -> aux optimiser.  The reference delegates the backward to torch.autograd; here it is an explicit
+reverse sweep over the tape of launches the forward recorded:
+
+  conv record   -> crdr_epilogue_backward (ReLU mask / gain / skip / LRP tanh, per-channel sums), crdr_conv_wgrad (tcgen05),
+                   crdr_conv_dgrad (the forward kernel over device-packed adjoint matrices, accumulating in place)
+  gate record   -> crdr_gate_backward                 (ChengNLAM, cheng_nlam.py:23-29)
+  gauss record  -> crdr_gauss_backward                (rate term + straight-through path, ste_gaussian_conditional.py:20-27)
+  loss roots    -> crdr_mse_backward (distortion_loss.py:40-46) and the rate coefficient (rate_loss.py:84-110)
+
+Activation gradients are fp16 planes under a power-of-two loss scale; parameter gradients, Adam moments and the master
+weights are fp32 in one flat buffer each (one fused Adam launch, one NCCL all-reduce per bucket for data parallelism).
+The factorised prior over z (18 k elements per Kodak image, 58 parameters per channel) is differentiated with torch
+autograd on the device: it is 0.003 % of the step's arithmetic and not worth a kernel.
+
+Scope: the models without beta conditioning (stage 1 / stage 2: crdr_stage_1.yaml, crdr_stage_2.yaml = BASELINE config
+5) with rate + MSE losses.  LPIPS needs pretrained AlexNet weights that are not available offline and is left out.
+"""
+import ctypes as C
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import backward as bw
+from . import native as nv
+from .engine import Act
+
+AUX_SUFFIX = "quantiles"
+
+
+class TrainContext:
+    """Owns the flat fp32 parameter / gradient buffers and everything the engines need in training mode."""
+
+    def __init__(self, model, device):
+        self.device = torch.device(device)
+        self.tape = None
+        self.convs = []
+        named = list(model.named_parameters())
+        main = [(k, p) for k, p in named if not k.endswith(AUX_SUFFIX)]
+        aux = [(k, p) for k, p in named if k.endswith(AUX_SUFFIX)]
+        self.names = [k for k, _ in main + aux]
+        sizes = [p.numel() for _, p in main + aux]
+        self.n_main = sum(p.numel() for _, p in main)
+        total = sum(sizes)
+        # every view starts on a 16-byte boundary (vector loads of biases / gains)
+        self.offsets, o = [], 0
+        for s in sizes:
+            self.offsets.append(o)
+            o += (s + 3) // 4 * 4
+        self.total = o
+        self.n_main_padded = self.offsets[len(main)] if aux else o
+        self.flat_p = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        self.flat_g = torch.zeros_like(self.flat_p)
+        self.params, self.grads = {}, {}
+        for (k, p), off in zip(main + aux, self.offsets):
+            v = self.flat_p[off:off + p.numel()].view(p.shape)
+            v.copy_(p.detach().to(self.device, torch.float32))
+            self.params[k] = v
+            self.grads[k] = self.flat_g[off:off + p.numel()].view(p.shape)
+        self.buffers = {k: b.detach().to(self.device) for k, b in model.named_buffers()}
+        self._grad_by_ptr = {self.params[k].data_ptr(): self.grads[k] for k in self.names}
+        self.live = {}          # sub-network name -> live state dict (views of flat_p)
+        self.gain_state = {}    # "encoder" / "decoder" -> (engine, l, r, alpha, lerped weights)
+        self.gain_grad = {}
+        self._gain_by_ptr = {}
+
+    def live_sd(self, prefix):
+        p = prefix + "."
+        sd = {k[len(p):]: v for k, v in self.params.items() if k.startswith(p)}
+        sd.update({k[len(p):]: v for k, v in self.buffers.items() if k.startswith(p)})
+        self.live[prefix] = sd
+        return sd
+
+    def grad_view(self, master):
+        return self._grad_by_ptr[master.data_ptr()]
+
+    # ---- engines call these ------------------------------------------------------------------------------------
+    def adopt(self, conv, w, b, transform, bias_transform, two_planes, **kw):
+        conv.master, conv.bias_master, conv.bias_transform, conv.packed_transform = w, b, bias_transform, transform
+        conv.bias_buf = bias_transform(b) if (bias_transform and b is not None) else None
+        bias = conv.bias_buf if conv.bias_buf is not None else b
+        conv.packed = bw.PackedConv(w, transform or (lambda t: t), two_planes, bias=bias, **kw)
+        conv.op = conv.packed.op
+        conv.wmap = None
+        if transform is not None:
+            conv.wmap = (transform(bw.index_weight(tuple(w.shape))).round().to(torch.int64) - 1).reshape(-1).to(self.device)
+        conv.dgrad = None
+        self.convs.append(conv)
+
+    def repack(self):
+        """After an optimiser step: re-pack every forward / adjoint matrix and refresh the derived bias vectors."""
+        for conv in self.convs:
+            conv.packed.repack()
+            if conv.dgrad is not None:
+                conv.dgrad.repack()
+            if conv.bias_buf is not None:
+                conv.bias_buf.copy_(conv.bias_transform(conv.bias_master))
+
+    def live_gains(self, engine, which, q):
+        """InterpChAtt vectors (interp_channel_attention.py:54-73) from the live parameters, written behind the fixed
+        addresses the launches read."""
+        sd = self.live[which]
+        levels = engine.gains[0].levels
+        q = float(q)
+        if not (0.0 <= q <= levels - 1):
+            raise AssertionError(f"rate_ind = {q} should be in [0, {levels - 1}]")
+        l = int(math.floor(q))
+        r = min(l + 1, levels - 1)
+        alpha = float(r) - q
+        vecs, lerped = [], []
+        for i in range(len(engine.gains)):
+            W, B = sd[f"interp_ca_list.{i}.weight"], sd[f"interp_ca_list.{i}.bias"]
+            w = (W[l] * alpha + W[r] * (1 - alpha)).reshape(-1)
+            b = (B[l] * alpha + B[r] * (1 - alpha)).reshape(-1)
+            lerped.append(w)
+            vecs += [F.softplus(w), b]
+        flat = engine.gain_vecs.flat
+        flat.copy_(torch.cat(vecs))
+        engine.gain_vecs._live = None
+        views = engine.gain_vecs.views
+        if which not in self.gain_grad:
+            self.gain_grad[which] = torch.zeros_like(flat)
+            o = 0
+            for i, n in enumerate(engine.gain_vecs.sizes):
+                self._gain_by_ptr[views[i].data_ptr()] = (which, o, n)
+                o += n
+        self.gain_state[which] = (engine, l, r, alpha, lerped)
+        return views
+
+    def gain_grad_slot(self, vec):
+        which, o, n = self._gain_by_ptr[vec.data_ptr()]
+        return self.gain_grad[which][o:o + n]
+
+    def finish_gain_grads(self, inv_scale):
+        """d(scale), d(shift) sums -> interp_ca_list.{i}.weight / .bias gradients (softplus and the level lerp)."""
+        for which, (engine, l, r, alpha, lerped) in self.gain_state.items():
+            gg = self.gain_grad[which]
+            o = 0
+            for i in range(len(engine.gains)):
+                n = engine.gain_vecs.sizes[2 * i]
+                dscale, dshift = gg[o:o + n] * inv_scale, gg[o + n:o + 2 * n] * inv_scale
+                o += 2 * n
+                dw = dscale * torch.sigmoid(lerped[i])
+                gW = self.grads[f"{which}.interp_ca_list.{i}.weight"]
+                gB = self.grads[f"{which}.interp_ca_list.{i}.bias"]
+                shape = gW[l].shape
+                gW[l] += alpha * dw.view(shape)
+                gB[l] += alpha * dshift.view(shape)
+                if r != l or alpha != 1.0:
+                    gW[r] += (1 - alpha) * dw.view(shape)
+                    gB[r] += (1 - alpha) * dshift.view(shape)
+            gg.zero_()
+
+
+def _eb_likelihood(sd, v):
+    """CompressAI EntropyBottleneck._likelihood on points v [C, 1, K] with the live parameters (autograd on the device)."""
+    def logits(x):
+        h = x
+        for i in range(5):
+            h = torch.matmul(F.softplus(sd[f"_matrix{i}"]), h) + sd[f"_bias{i}"]
+            if i < 4:
+                h = h + torch.tanh(sd[f"_factor{i}"]) * torch.tanh(h)
+        return h
+    lower, upper = logits(v - 0.5), logits(v + 0.5)
+    sign = (-torch.sign(lower + upper)).detach()
+    return torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))
+
+
+class CodecTrainer:
+    """One data-parallel replica of the rate-distortion training step (stage 1 / stage 2 models)."""
+
+    def __init__(self, model, device="cuda:0", lr=1e-4, betas=(0.9, 0.999), eps=1e-8, clip_max_norm=None,
+                 lambda_mse=150.0, rate_lambda_a=(3.6, 1.8, 0.8, 0.4, 0.1), rate_lambda_b=2.0 ** -6,
+                 target_rate=(0.08, 0.16, 0.36, 0.72, 1.2), aux_lr=1e-3, loss_scale=None, process_group=None):
+        if getattr(model, "uses_beta", False):
+            raise NotImplementedError("the beta-conditioned (stage 3) model's backward is not lowered: train stage 1 / 2 models")
+        self.model, self.device = model, torch.device(device)
+        self.ctx = ctx = TrainContext(model, device)
+        X3, X1 = nv.PREC_F16X3, nv.PREC_F16X1
+        with torch.cuda.device(self.device):
+            self.ga = model.encoder.lower(device, sd=ctx.live_sd("encoder"), precision=X3, train=ctx)
+            self.ha = model.hyperencoder.lower(device, sd=ctx.live_sd("hyperencoder"), precision=X3, train=ctx)
+            self.hs = model.hyperdecoder.lower(device, sd=ctx.live_sd("hyperdecoder"), precision=X3, train=ctx)
+            self.charm = model.context_model.lower(device, sd=ctx.live_sd("context_model"), precision=X3, train=ctx)
+            self.gs = model.decoder.lower(device, sd=ctx.live_sd("decoder"), precision=X1, train=ctx)
+        if self.gs.has_cond:
+            raise NotImplementedError("beta conditioning is not part of the lowered training step")
+        self.eb_sd = ctx.live_sd("entropy_model_z")
+        from .codec import GaussianParams
+        from .entropy import get_scale_table
+        table = model.entropy_model_y.scale_table
+        self.gp = GaussianParams(table if table.numel() else get_scale_table(), float(model.entropy_model_y.scale_bound.item()), device)
+        self.zc = model.entropy_model_z.channels
+        self.uses_rate = bool(getattr(model, "uses_rate", False))
+        self.lr, self.betas, self.eps, self.clip = lr, betas, eps, clip_max_norm
+        self.aux_lr = aux_lr
+        self.lambda_mse = float(lambda_mse)
+        self.lambda_a, self.lambda_b, self.target = list(rate_lambda_a), rate_lambda_b, list(target_rate)
+        self.loss_scale = None if loss_scale is None else float(loss_scale)   # None: from the batch's pixel count
+        self._auto_scale = loss_scale is None
+        self.m = torch.zeros_like(ctx.flat_p)
+        self.v = torch.zeros_like(ctx.flat_p)
+        self.step_count = 0
+        self.pg = process_group
+        self._sumsq = torch.zeros(1024 + 1, dtype=torch.float32, device=self.device)
+        ctx.repack()
+        self._grads = {}     # activation storage pointer -> gradient Act of the current step
+        self._keep = []
+
+    # ------------------------------------------------------------------ forward (training mode, taped)
+    def _eb_kernel_params(self):
+        sd, c = self.eb_sd, self.zc
+        cols = []
+        for i in range(5):
+            cols.append(F.softplus(sd[f"_matrix{i}"]).reshape(c, -1))
+            cols.append(sd[f"_bias{i}"].reshape(c, -1))
+            if i < 4:
+                cols.append(torch.tanh(sd[f"_factor{i}"]).reshape(c, -1))
+        return torch.cat(cols, dim=1).contiguous(), sd["quantiles"][:, 0, 1].contiguous()
+
+    def forward(self, images, q, noise):
+        """images: [n, 3, h, w] fp32 device tensor (h, w multiples of 64); noise = {"y", "z"} uniform in [-1/2, 1/2).
+        Returns the dict of device tensors of the training-mode forward and leaves the tape for backward()."""
+        ctx, L, st = self.ctx, nv.lib(), nv.stream_handle()
+        ctx.tape = []
+        self._grads, self._keep = {}, []
+        n, _, h, w = images.shape
+        assert h % 64 == 0 and w % 64 == 0 and images.is_contiguous() and images.dtype == torch.float32
+        dev = images.device
+        img = Act.empty(n, h // 2, w // 2, self.ga.PATCH_CH, two=True, device=dev)
+        nv.check(L.crdr_image_to_patches(images.data_ptr(), n, h, w, h, w, img.planes(0), st))
+        y_act, y32 = self.ga.run(img, q)
+        z32 = self.ha.run(y_act)
+        hz, wz = z32.shape[1:3]
+        zhat = Act.empty(n, hz, wz, self.zc, two=True, device=dev)
+        z_sym = torch.empty((n, self.zc, hz, wz), dtype=torch.int32, device=dev)
+        z_hat = torch.empty((n, self.zc, hz, wz), dtype=torch.float32, device=dev)
+        z_lik = torch.empty((n, self.zc, hz, wz), dtype=torch.float32, device=dev)
+        z_lik_noisy = torch.empty((n, self.zc, hz, wz), dtype=torch.float32, device=dev)
+        eb_params, eb_medians = self._eb_kernel_params()
+        d = nv.EbDesc()
+        d.z, d.z_cs, d.n, d.hw, d.c = z32.data_ptr(), self.zc, n, hz * wz, self.zc
+        d.params, d.medians = eb_params.data_ptr(), eb_medians.data_ptr()
+        d.zhat_planes = zhat.planes(0)
+        d.symbols, d.zhat_nchw, d.likelihood = z_sym.data_ptr(), z_hat.data_ptr(), z_lik.data_ptr()
+        d.noise, d.likelihood_noisy = noise["z"].data_ptr(), z_lik_noisy.data_ptr()
+        nv.check(L.crdr_eb_quantize(C.byref(d), st))
+        self._keep += [eb_params, eb_medians]
+        ctx.tape.append(("eb", z32, zhat, noise["z"]))
+        T = self.charm.new_support(n, y_act.h, y_act.w, dev)
+        self.hs.run(zhat, T, self.charm.off_mean, self.charm.off_scale)
+        self._y_act, self._T, self._zhat = y_act, T, zhat
+        yhat32, y_sym, y_idx, y_lik, y_lik_noisy = self.charm.encode(T, y32, self.gp, noise=noise["y"])
+        fake_packed = self.gs.run(yhat32, q, 0.0)
+        fake = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
+        nv.check(L.crdr_phases_to_image_ex(fake_packed.data_ptr(), fake_packed.shape[-1], n, h // 2, w // 2, h, w, fake.data_ptr(), 0, st))
+        return dict(fake_images=fake, fake_packed=fake_packed, y32=y32, z32=z32, yhat32=yhat32, z_hat=z_hat, y_lik=y_lik, y_sym=y_sym,
+                    z_lik=z_lik, y_lik_noisy=y_lik_noisy, z_lik_noisy=z_lik_noisy, T=T, y_act=y_act, size=(h, w))
+
+    # ------------------------------------------------------------------ losses (values, for logging and the rate switch)
+    def _bits(self, lik):
+        n = lik.shape[0]
+        out = torch.empty(n, dtype=torch.float32, device=lik.device)
+        nv.check(nv.lib().crdr_bits_from_likelihood(lik.data_ptr(), n, lik[0].numel(), out.data_ptr(), nv.stream_handle()))
+        return out
+
+    def losses(self, images, out, q):
+        """rate_distortion_trainer.py:70-76 with HificVariableRateLoss (rate_loss.py:84-175) and MSELoss (0_1 scale)."""
+        h, w = out["size"]
+        bpp = (self._bits(out["y_lik_noisy"]) + self._bits(out["z_lik_noisy"])) / (h * w)
+        qbpp = (self._bits(out["y_lik"]) + self._bits(out["z_lik"])) / (h * w)
+        lvl = int(q) if self.uses_rate else 0
+        lam_a = self.lambda_a[lvl] if isinstance(self.lambda_a, (list, tuple)) else self.lambda_a
+        lam_b = self.lambda_b[lvl] if isinstance(self.lambda_b, (list, tuple)) else self.lambda_b
+        tgt = self.target[lvl] if isinstance(self.target, (list, tuple)) else self.target
+        rate_w = lam_a if float(qbpp.mean().item()) > tgt else lam_b
+        mse = torch.mean(((images + 1) / 2 - (out["fake_images"] + 1) / 2) ** 2)
+        return dict(rate=rate_w * bpp.mean(), distortion=self.lambda_mse * mse, bpp=bpp.mean(), qbpp=qbpp.mean(), rate_weight=rate_w)
+
+    # ------------------------------------------------------------------ backward
+    def _grad(self, key, like=None, shape=None):
+        """Gradient Act (fp16, zero-initialised on first use) of the tensor whose storage starts at `key`."""
+        g = self._grads.get(key)
+        if g is None:
+            n, h, w, c = shape if shape is not None else (like.n, like.h, like.w, like.c)
+            g = self._grads[key] = Act.zeros(n, h, w, c, two=False, device=self.device)
+        return g
+
+    def _partial(self, blocks, nsums, c):
+        return bw.workspace(1 << 24, self.device)[: blocks * nsums * c * 4].view(torch.float32)
+
+    def backward(self, images, out, rate_weight):
+        """Reverse sweep over the tape; fills ctx.flat_g (unscaled fp32 gradients of mean-reduced losses)."""
+        ctx, L, st = self.ctx, nv.lib(), nv.stream_handle()
+        n = images.shape[0]
+        h, w = out["size"]
+        if self._auto_scale:
+            # the loss roots carry 1 / (n h w): keep the activation gradients in fp16's normal range whatever the batch
+            self.loss_scale = 2.0 ** math.floor(math.log2(max(2.0, n * h * w / 2.0)))
+        S = self.loss_scale
+        inv = 1.0 / S
+        ctx.flat_g.zero_()
+        # ---- loss roots --------------------------------------------------------------------------------------------
+        fp = out["fake_packed"]
+        g_img = self._grad(fp.data_ptr(), shape=(n, h // 2, w // 2, 16))
+        coef_mse = S * self.lambda_mse * 2.0 * 0.25 / (n * 3 * h * w)
+        nv.check(L.crdr_mse_backward(fp.data_ptr(), fp.shape[-1], images.data_ptr(), n, h // 2, w // 2, h, w, coef_mse,
+                                     g_img.hi.data_ptr(), 16, st))
+        self._rate_coef = S * rate_weight / (math.log(2.0) * n * h * w)   # d(rate_w * mean bpp) / d(-ln L) per element
+        tape, ctx.tape = ctx.tape, None
+        for rec in reversed(tape):
+            kind = rec[0]
+            if kind == "conv":
+                self._conv_backward(*rec[1:])
+            elif kind == "gate":
+                self._gate_backward(*rec[1:])
+            elif kind == "affine_in":
+                self._affine_in_backward(*rec[1:])
+            elif kind == "gauss":
+                self._gauss_backward(*rec[1:])
+            elif kind == "eb":
+                self._eb_backward(*rec[1:])
+        ctx.finish_gain_grads(inv)
+        nv.status_check()
+
+    def _sums_to(self, partial, blocks, nsums, which, c, target, accumulate=True, scale=None):
+        nv.check(nv.lib().crdr_colsum_finish(partial.data_ptr(), blocks, nsums, which, c, target.data_ptr(),
+                                             (1.0 / self.loss_scale) if scale is None else scale, 1 if accumulate else 0,
+                                             nv.stream_handle()))
+
+    def _conv_backward(self, conv, x, kw, out, bwd_res, no_input_grad):
+        ctx, L, st = self.ctx, nv.lib(), nv.stream_handle()
+        op = conv.op
+        out_f32 = kw.get("out_f32")
+        if out is not None and kw.get("want_planes", True):
+            G, gcoff = self._grads.get(out.hi.data_ptr()), kw.get("out_coff", 0)
+        else:
+            G, gcoff = self._grads.get(out_f32.data_ptr()), kw.get("out_f32_coff", 0)
+        if G is None:
+            return          # nothing downstream depends on this output
+        cout = op.cout_pad if conv.wmap is not None else op.cout
+        relu, mode = bool(kw.get("relu")), kw.get("mode", nv.EPI_NONE)
+        scale, shift = kw.get("scale"), kw.get("shift")
+        affine = scale is not None or shift is not None
+        tanh = mode == nv.EPI_HALF_TANH
+        need_dv = relu or affine or tanh
+        ho, wo = G.h, G.w
+        m = G.n * ho * wo
+        blocks = max(1, min(512, m // 64))
+        partial = self._partial(blocks, 3, cout)
+        d = nv.EpiBwdDesc()
+        d.g = nv.Planes(G.hi.data_ptr(), None, G.c, gcoff)
+        d.m, d.c, d.relu = m, cout, 1 if relu else 0
+        if relu or affine:
+            d.out = out.planes(kw.get("out_coff", 0))
+        d.scale, d.shift = nv.ptr(scale), nv.ptr(shift)
+        if tanh:
+            res32 = kw["res"]
+            d.f32_out, d.f32_res = out_f32.data_ptr(), res32.data_ptr()
+            d.f32_cs, d.f32_coff = out_f32.shape[-1], kw.get("out_f32_coff", 0)
+            assert res32.shape[-1] == out_f32.shape[-1] and kw.get("res_coff", 0) == kw.get("out_f32_coff", 0)
+        if need_dv:
+            dv = Act.empty(G.n, ho, wo, cout, two=False, device=self.device)
+            d.dv = dv.planes(0)
+            dv_coff = 0
+        else:
+            dv, dv_coff = G, gcoff
+        if mode == nv.EPI_RESIDUAL:
+            res = kw["res"]
+            Gr = self._grad(res.hi.data_ptr(), like=res)
+            d.dres = nv.Planes(Gr.hi.data_ptr(), None, Gr.c, kw.get("res_coff", 0))
+        elif tanh:
+            Tres, coff = bwd_res
+            Gr = self._grad(Tres.hi.data_ptr(), like=Tres)
+            d.dres = nv.Planes(Gr.hi.data_ptr(), None, Gr.c, coff)
+        d.partial, d.blocks = partial.data_ptr(), blocks
+        nv.check(L.crdr_epilogue_backward(C.byref(d), st))
+        # bias / gain sums
+        if conv.bias_master is not None:
+            if conv.bias_buf is not None:      # derived bias vector (phase-packed last layer): fold the phases back
+                tmp = torch.zeros(cout, dtype=torch.float32, device=self.device)
+                self._sums_to(partial, blocks, 3, 0, cout, tmp, accumulate=False)
+                nb = conv.bias_master.numel()
+                ctx.grad_view(conv.bias_master).add_(tmp[: 4 * nb].view(4, nb).sum(0))
+            else:
+                self._sums_to(partial, blocks, 3, 0, op.cout, ctx.grad_view(conv.bias_master))
+        if affine:
+            if shift is not None:
+                self._sums_to(partial, blocks, 3, 1, op.cout, ctx.gain_grad_slot(shift), scale=1.0)
+            if scale is not None:
+                self._sums_to(partial, blocks, 3, 2, op.cout, ctx.gain_grad_slot(scale), scale=1.0)
+        # wgrad
+        segs = kw.get("segs") or [(0, op.cin)]
+        k2 = op.kh * op.kw
+        taps = [(i - op.padding, j - op.padding) for i in range(op.kh) for j in range(op.kw)]
+        if conv.wmap is not None:
+            # transformed weight (im2col'd first layer, phase-packed last layer): gradient in the ConvOp's layout, then
+            # scattered to the parameter through the transform's index map
+            tmp = torch.empty((op.cout_pad, op.cin, op.kh, op.kw), dtype=torch.float32, device=self.device)
+            bw.wgrad(dv, dv_coff, op.cout_pad, x, 0, op.cin, taps, 1, tmp, op.cin * k2, k2, 1, scale=1.0 / self.loss_scale)
+            valid = conv.wmap >= 0
+            ctx.grad_view(conv.master).view(-1).index_add_(0, conv.wmap[valid], tmp.view(-1)[valid])
+        else:
+            gw = ctx.grad_view(conv.master).view(-1)
+            start = 0
+            for off, ln in segs:
+                real = min(ln, op.cin_real - start)
+                if real > 0:
+                    if op.transposed:   # parameter [ci, co, kh, kw]:  S = x (a = ci), B = dv (b = co)
+                        bw.wgrad(x, off, real, dv, dv_coff, op.cout, taps, op.stride, gw[start * op.cout * k2:], op.cout * k2, k2, 1,
+                                 scale=1.0 / self.loss_scale, accumulate=True)
+                    else:               # parameter [co, ci, kh, kw]:  S = dv (a = co), B = x (b = ci)
+                        bw.wgrad(dv, dv_coff, op.cout, x, off, real, taps, op.stride, gw[start * k2:], op.cin_real * k2, k2, 1,
+                                 scale=1.0 / self.loss_scale, accumulate=True)
+                start += ln
+        # dgrad
+        if no_input_grad:
+            return
+        if conv.dgrad is None:
+            assert conv.wmap is None or conv.name == "conv4", "only the last layer has a transformed weight and an input gradient"
+            if conv.wmap is not None:
+                # adjoint of the phase-packed 3x3 convolution [16, cin, 3, 3] built from the parameter through both maps
+                tf = conv.packed_transform
+                fn, dkw = bw.dgrad_spec(False, 1, op.padding, op.kh)
+                conv.dgrad = _SingleDgrad(bw.PackedConv(conv.master, lambda wi: fn(tf(wi)), two_planes=False, **dkw))
+            else:
+                conv.dgrad = bw.DgradSet(conv.master, op.transposed, op.stride, op.padding, op.kh, segs, cin_real=op.cin_real)
+            conv.dgrad.repack()
+        Gx = self._grad(x.hi.data_ptr(), like=x)
+        if need_dv:
+            conv.dgrad.run(dv, Gx)
+        else:
+            conv.dgrad.run(G, Gx, dv_coff=gcoff, dv_c=cout)
+
+    def _gate_backward(self, x, t, a, out, scale, shift):
+        G = self._grads.get(out.hi.data_ptr())
+        if G is None:
+            return
+        ctx, L, st = self.ctx, nv.lib(), nv.stream_handle()
+        Gx, Gt, Ga = self._grad(x.hi.data_ptr(), like=x), self._grad(t.hi.data_ptr(), like=t), self._grad(a.hi.data_ptr(), like=a)
+        blocks = max(1, min(512, x.pixels // 64))
+        partial = self._partial(blocks, 2, x.c)
+        d = nv.GateDesc()
+        d.x, d.t, d.a = x.planes(0), t.planes(0), a.planes(0)
+        d.m, d.c, d.scale, d.shift = x.pixels, x.c, nv.ptr(scale), nv.ptr(shift)
+        d.g, d.dx, d.dt, d.da = G.planes(0), Gx.planes(0), Gt.planes(0), Ga.planes(0)
+        d.partial, d.blocks = partial.data_ptr(), blocks
+        nv.check(L.crdr_gate_backward(C.byref(d), st))
+        if shift is not None:
+            self._sums_to(partial, blocks, 2, 0, x.c, ctx.gain_grad_slot(shift), scale=1.0)
+        if scale is not None:
+            self._sums_to(partial, blocks, 2, 1, x.c, ctx.gain_grad_slot(scale), scale=1.0)
+
+    def _affine_in_backward(self, x, scale, shift, yhat32):
+        """g_s input: x = y_hat * scale + shift (the first InterpChAtt of the decoder) -> d(y_hat) into the support
+        tensor's gradient (y_hat channels)."""
+        G = self._grads.get(x.hi.data_ptr())
+        if G is None:
+            return
+        T = self._T
+        GT = self._grad(T.hi.data_ptr(), like=T)
+        affine = scale is not None
+        m = x.pixels
+        blocks = max(1, min(512, m // 64))
+        partial = self._partial(blocks, 3, x.c)
+        d = nv.EpiBwdDesc()
+        d.g, d.m, d.c = G.planes(0), m, x.c
+        if affine:
+            d.out, d.scale, d.shift = x.planes(0), nv.ptr(scale), nv.ptr(shift)
+        d.dres = nv.Planes(GT.hi.data_ptr(), None, GT.c, self.charm.off_y)
+        d.partial, d.blocks = partial.data_ptr(), blocks
+        nv.check(nv.lib().crdr_epilogue_backward(C.byref(d), nv.stream_handle()))
+        if affine:
+            self._sums_to(partial, blocks, 3, 1, x.c, self.ctx.gain_grad_slot(shift), scale=1.0)
+            self._sums_to(partial, blocks, 3, 2, x.c, self.ctx.gain_grad_slot(scale), scale=1.0)
+
+    def _gauss_backward(self, s0, cnt, T, y32, ms, noise):
+        ch = self.charm
+        GT = self._grad(T.hi.data_ptr(), like=T)
+        Gy = self._grad(self._y_act.hi.data_ptr(), like=self._y_act)
+        n, hgt, wid = T.n, T.h, T.w
+        Gms = self._grad(ms.data_ptr(), shape=(n, hgt, wid, ms.shape[-1]))
+        d = nv.GaussBwdDesc()
+        d.y, d.y_cs, d.y_coff = y32.data_ptr(), ch.yc, s0 * ch.sc
+        d.noise, d.ms = noise.data_ptr(), ms.data_ptr()
+        d.ms_cs, d.mu_coff, d.sigma_coff = ms.shape[-1], s0 * ch.sc, ch.yc + s0 * ch.sc
+        d.n, d.hw, d.c, d.c_total, d.nchw_coff = n, hgt * wid, ch.sc * cnt, ch.yc, s0 * ch.sc
+        d.scale_bound, d.lik_bound, d.coef = self.gp.bound, 1e-9, self._rate_coef
+        d.gpre = nv.Planes(GT.hi.data_ptr(), None, GT.c, ch.off_tmp + s0 * ch.sc)
+        d.dy = nv.Planes(Gy.hi.data_ptr(), None, Gy.c, s0 * ch.sc)
+        d.dmu = nv.Planes(Gms.hi.data_ptr(), None, Gms.c, s0 * ch.sc)
+        d.dsigma = nv.Planes(Gms.hi.data_ptr(), None, Gms.c, ch.yc + s0 * ch.sc)
+        nv.check(nv.lib().crdr_gauss_backward(C.byref(d), nv.stream_handle()))
+
+    def _eb_backward(self, z32, zhat, noise_z):
+        """z path: straight-through z_hat (entropy_bottleneck.py:23-30) + the rate term of the factorised prior."""
+        ctx = self.ctx
+        S = self.loss_scale
+        n, hz, wz, c = z32.shape
+        names = [k for k in self.eb_sd if k.startswith(("_matrix", "_bias", "_factor"))]
+        leaves = {k: self.eb_sd[k].detach().requires_grad_(True) for k in names}
+        with torch.enable_grad():
+            z = z32.detach().permute(0, 3, 1, 2).contiguous().requires_grad_(True)     # NCHW
+            v = (z + noise_z).permute(1, 0, 2, 3).reshape(c, 1, -1)
+            lik = _eb_likelihood(leaves, v)
+            lik = lik + (torch.clamp(lik, min=1e-9) - lik).detach()       # LowerBound: every (negative) gradient passes
+            loss = -(self._rate_coef / S) * torch.log(lik).sum()
+            grads = torch.autograd.grad(loss, [z] + [leaves[k] for k in names])
+        for k, g in zip(names, grads[1:]):
+            ctx.grads["entropy_model_z." + k].add_(g)
+        dz = grads[0].permute(0, 2, 3, 1) * S                              # NHWC, loss-scaled
+        Gzh = self._grads.get(zhat.hi.data_ptr())
+        if Gzh is not None:
+            dz = dz + Gzh.hi.float()
+        Gz = self._grad(z32.data_ptr(), shape=(n, hz, wz, c))
+        Gz.hi.copy_(dz.clamp(-65504.0, 65504.0).half())
+
+    # ------------------------------------------------------------------ the step
+    def aux_step(self):
+        """BaseModel.aux_loss (base_model.py:65-76) + its own Adam (rate_distortion_trainer.py:96-100); 576 parameters."""
+        sd = self.eb_sd
+        qv = sd["quantiles"].detach().requires_grad_(True)
+        with torch.enable_grad():
+            h = qv
+            for i in range(5):
+                h = torch.matmul(F.softplus(sd[f"_matrix{i}"].detach()), h) + sd[f"_bias{i}"].detach()
+                if i < 4:
+                    h = h + torch.tanh(sd[f"_factor{i}"].detach()) * torch.tanh(h)
+            loss = torch.abs(h - self.ctx.buffers["entropy_model_z.target"]).sum()
+            (g,) = torch.autograd.grad(loss, [qv])
+        self.ctx.grads["entropy_model_z.quantiles"].copy_(g)
+        return loss.detach()
+
+    def all_reduce_grads(self, bucket_bytes=64 << 20):
+        """Data parallelism: average the flat gradient buffer over the ranks in fixed-size buckets (NCCL over NVLink;
+        SURVEY 8e: 127.7 M parameters = 510.9 MB per step).  A no-op for a single process."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.pg) == 1:
+            return 0
+        world = dist.get_world_size(self.pg)
+        g = self.ctx.flat_g
+        per = bucket_bytes // 4
+        handles = []
+        for o in range(0, g.numel(), per):
+            handles.append(dist.all_reduce(g[o:o + per], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        for hnd in handles:
+            hnd.wait()
+        g.mul_(1.0 / world)
+        return len(handles)
+
+    def optimizer_step(self):
+        ctx, L, st = self.ctx, nv.lib(), nv.stream_handle()
+        self.step_count += 1
+        clip_ptr = None
+        if self.clip:
+            nv.check(L.crdr_sum_squares(ctx.flat_g.data_ptr(), ctx.n_main_padded, self._sumsq.data_ptr(), self._sumsq[1024:].data_ptr(), st))
+            coef = torch.clamp(self.clip / (torch.sqrt(self._sumsq[1024]) + 1e-6), max=1.0).reshape(1)
+            self._keep.append(coef)
+            clip_ptr = coef.data_ptr()
+        nv.check(L.crdr_adam_step(ctx.flat_p.data_ptr(), ctx.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), ctx.n_main_padded,
+                                  self.lr, self.betas[0], self.betas[1], self.eps, self.step_count, clip_ptr, 1.0, st))
+        if ctx.total > ctx.n_main_padded:   # aux parameters (quantiles): their own learning rate, no clipping
+            o, cnt = ctx.n_main_padded, ctx.total - ctx.n_main_padded
+            nv.check(L.crdr_adam_step(ctx.flat_p[o:].data_ptr(), ctx.flat_g[o:].data_ptr(), self.m[o:].data_ptr(), self.v[o:].data_ptr(),
+                                      cnt, self.aux_lr, self.betas[0], self.betas[1], self.eps, self.step_count, None, 1.0, st))
+        ctx.repack()
+
+    def train_step(self, images, q=None, noise=None, generator=None):
+        """One optimisation step on a batch of [-1, 1] crops (device fp32 NCHW).  Returns the loss dict (device scalars)."""
+        n, _, h, w = images.shape
+        if q is None:
+            q = float(torch.randint(self.model.rate_level, (1,)).item()) if self.uses_rate else 0.0
+        if noise is None:
+            mk = lambda c, a, b: torch.rand((n, c, a, b), dtype=torch.float32, device=self.device, generator=generator) - 0.5
+            noise = {"z": mk(self.zc, h // 64, w // 64), "y": mk(self.charm.yc, h // 16, w // 16)}
+        out = self.forward(images, q, noise)
+        ld = self.losses(images, out, q)
+        self.backward(images, out, ld["rate_weight"])
+        ld["aux"] = self.aux_step()
+        self.all_reduce_grads()
+        self.optimizer_step()
+        return ld
+
+    def sync_to_model(self):
+        """Copy the trained parameters back into the nn.Module (checkpointing: state_dict layout of the reference)."""
+        with torch.no_grad():
+            for k, p in self.model.named_parameters():
+                p.copy_(self.ctx.params[k].to(p.device))
+
+
+class _SingleDgrad:
+    def __init__(self, pc):
+        self.pc = pc
+
+    def repack(self):
+        self.pc.repack()
+
+    def run(self, dv, grad, accumulate=True, dv_coff=0, dv_c=None):
+        segs = None if dv_c is None else [(dv_coff, dv_c)]
+        self.pc.op(dv, segs=segs, out=grad, out_coff=0, precision=nv.PREC_F16X1, mode=nv.EPI_RESIDUAL, res=grad, res_coff=0)

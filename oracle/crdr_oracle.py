@@ -285,17 +285,20 @@ def eb_likelihood_at(eb, v):
 
 
 def ste_round(x):
-    """src/models/subnet/entropy_model/ste_round.py:4-5 (forward value)."""
-    return (torch.round(x) - x) + x
+    """src/models/subnet/entropy_model/ste_round.py:4-5 (straight-through: the rounding residual carries no gradient)."""
+    return (torch.round(x) - x).detach() + x
 
 
 @torch.no_grad()
-def forward_train(sd, x, q, beta, noise, eb, gc):
+def forward_train(sd, x, q, beta, noise, eb, gc, forced_y_symbols=None):
     """Forward VALUES of model.forward(..., is_train=True) (beta_cond_interpca_hyperprior_charm_model.py:34-78;
     minnen20_charm_context_model.py:88-141; ste_gaussian_conditional.py:20-27; entropy_bottleneck.py:23-30) with the
     uniform noise given explicitly: noise = {"z": [N, zc, h/64, w/64], "y": [N, yc, h/16, w/16]} in [-1/2, 1/2).
     The reference draws the same values inside CompressAI's quantize(mode="noise"): z first (in C x 1 x (N H W) order),
-    then one draw per slice."""
+    then one draw per slice.
+    forced_y_symbols (tests only): integer rounding decisions round(y - mu) [N, yc, h/16, w/16] to use instead of this
+    function's own torch.round -- an fp32-rounding-level difference in mu can flip a tie, and a flipped symbol changes
+    every later slice; forcing the decisions lets a gradient comparison isolate the backward arithmetic."""
     S, K = CFG["num_slices"], CFG["max_support"]
     y = g_a(sd, x, q)
     z = h_a(sd, y)
@@ -314,7 +317,11 @@ def forward_train(sd, x, q, beta, noise, eb, gc):
         mu = slice_net(sub(cm, f"mean_slice_transforms.{s}"), mean_support)
         sigma = slice_net(sub(cm, f"scale_slice_transforms.{s}"), scale_support)
         liks.append(gc.likelihood_lower_bound(gc._likelihood(y_slices[s] + n_slices[s], sigma, mu)))
-        y_hat_s = ste_round(y_slices[s] - mu) + mu
+        if forced_y_symbols is None:
+            y_hat_s = ste_round(y_slices[s] - mu) + mu
+        else:
+            r = y_slices[s] - mu
+            y_hat_s = (forced_y_symbols[:, s * CFG["slice_ch"]:(s + 1) * CFG["slice_ch"]].to(r.dtype) - r).detach() + r + mu
         qliks.append(gc(y_slices[s], sigma, means=mu, training=False)[1])
         lrp = slice_net(sub(cm, f"lrp_slice_transforms.{s}"), torch.cat([mean_support, y_hat_s], dim=1))
         hats.append(y_hat_s + 0.5 * torch.tanh(lrp))

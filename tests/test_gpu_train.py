@@ -328,3 +328,108 @@ def test_mse_backward_adam_and_norm():
                                   None, clip, st))
     torch.cuda.synchronize()
     assert float((p.cpu() - pt.detach()).abs().max()) < 2e-6
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The whole training step against autograd through the oracle (= the reference's forward, pinned in
+# tests/test_oracle_vs_reference.py): same weights, same crops, same noise, same losses.
+# ----------------------------------------------------------------------------------------------------------------------
+def _oracle_grads(oracle, sd, x, q, noise, rate_w, lam_mse, forced=None):
+    """Autograd gradients of rate_w * mean(bpp) + lam_mse * MSE_01 through oracle.forward_train (CPU fp32)."""
+    sdr = {k: (v.detach().clone().float().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    eb, gc = oracle.entropy_models(sdr)
+    for p in eb.parameters():
+        p.requires_grad_(True)
+    fwd = oracle.forward_train.__wrapped__          # the undecorated function (forward_train itself runs under no_grad)
+    with torch.enable_grad():
+        out = fwd(sdr, x, q, None, noise, eb, gc, forced_y_symbols=forced)
+        n, _, h, w = x.shape
+        bits = lambda lik: (-torch.log2(lik)).sum((1, 2, 3))
+        bpp = (bits(out["likelihoods"]["y"]) + bits(out["likelihoods"]["z"])) / (h * w)
+        mse = torch.mean(((x + 1) / 2 - (out["fake_images"] + 1) / 2) ** 2)
+        loss = rate_w * bpp.mean() + lam_mse * mse
+        loss.backward()
+    grads = {k: v.grad for k, v in sdr.items() if v.is_floating_point() and v.grad is not None}
+    for k, p in eb.named_parameters():
+        if p.grad is not None and k != "quantiles":
+            grads["entropy_model_z." + k] = p.grad
+    return out, grads, float(loss)
+
+
+@pytest.mark.parametrize("q", [2.0, 0.5])
+def test_training_step_gradients_match_oracle_autograd(oracle, q):
+    import fixtures
+    from crdr_b200.train import CodecTrainer
+    model, sd = fixtures.build_model(seed=5, calibrated=True, config="crdr_stage_2.yaml")
+    tr = CodecTrainer(model, device=DEV)
+    n, h, w = 2, 128, 128
+    x = fixtures.image(n, h, w, seed=21)
+    g = torch.Generator().manual_seed(77)
+    noise = {"z": torch.rand(n, 192, h // 64, w // 64, generator=g) - 0.5, "y": torch.rand(n, 320, h // 16, w // 16, generator=g) - 0.5}
+    rate_w = 0.8
+    xd = x.to(DEV).contiguous()
+    nd = {k: v.to(DEV).contiguous() for k, v in noise.items()}
+    out = tr.forward(xd, q, nd)
+    ld = tr.losses(xd, out, q)
+    # The oracle replays the CUDA path's rounding decisions (the integer symbols): one tie broken the other way changes the
+    # support of every later slice, which would make this a comparison of two different forwards rather than of the
+    # backward arithmetic.  Without forcing, the two forwards differ in <= 1e-3 of the symbols (checked below).
+    free_out = oracle.forward_train(sd, x, q, None, noise, *oracle.entropy_models(sd))
+    flips = (free_out["quantized_code"]["y"] - out["yhat32"].permute(0, 3, 1, 2).cpu()).abs() > 0.5
+    assert float(flips.float().mean()) < 1e-3
+    ref_out, ref, ref_loss = _oracle_grads(oracle, sd, x, q, noise, rate_w, 150.0, forced=out["y_sym"].cpu())
+    # forward values first (training-mode parity is tested in test_gpu_codec.py; here: the taped engines agree too)
+    assert _rel(out["fake_images"].cpu(), ref_out["fake_images"].detach()) < 2e-3
+    assert abs(float(ld["rate"] + ld["distortion"]) - ref_loss) / ref_loss < 1e-3 or ld["rate_weight"] != rate_w
+    tr.backward(xd, out, rate_w)
+    torch.cuda.synchronize()
+    got = {k: v.detach().cpu() for k, v in tr.ctx.grads.items()}
+    worst = []
+    for k, gr in ref.items():
+        if k.endswith("quantiles") or k not in got:
+            continue
+        a, b = got[k].reshape(-1).double(), gr.reshape(-1).double()
+        nb = float(b.norm())
+        if nb == 0.0:
+            assert float(a.norm()) == 0.0, k
+            continue
+        worst.append((float((a - b).norm()) / nb, k, nb))
+    worst.sort(reverse=True)
+    report = "\n".join(f"{e:.3e}  |g|={nb:.3e}  {k}" for e, k, nb in worst[:25])
+    print(report)
+    missing = [k for k in ref if k not in got and not k.endswith("quantiles")]
+    assert not missing, missing
+    # fp16 activation gradients (11-bit significand) accumulated through ~100 layers: a few 1e-3 per tensor in L2
+    errs = torch.tensor([e for e, _, _ in worst])
+    assert float(errs.median()) < 5e-3, report
+    assert float(errs.max()) < 5e-2, report
+
+
+def test_training_steps_reduce_the_loss_and_keep_engines_in_sync():
+    """A few optimiser steps on a fixed batch: the loss goes down, the re-packed matrices follow the parameters (the
+    taped forward of the updated trainer equals a fresh model built from its synced parameters)."""
+    import fixtures
+    from crdr_b200.train import CodecTrainer
+    model, _ = fixtures.build_model(seed=6, calibrated=False, config="crdr_stage_2.yaml")
+    tr = CodecTrainer(model, device=DEV, lr=1e-4, clip_max_norm=1.0)
+    n, h, w = 2, 128, 128
+    x = fixtures.image(n, h, w, seed=22).to(DEV).contiguous()
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    first = last = None
+    for it in range(6):
+        ld = tr.train_step(x, q=2.0, generator=gen)
+        total = float(ld["rate"] + ld["distortion"])
+        first = total if first is None else first
+        last = total
+    assert math.isfinite(last) and last < first, (first, last)
+    tr.sync_to_model()
+    model.codec_setup()
+    xc = x.cpu()
+    a = model.run_model(xc, rate_ind=2.0, is_train=False)
+    g2 = torch.Generator(device=DEV).manual_seed(9)
+    mk = lambda c, aa, bb: torch.rand((n, c, aa, bb), dtype=torch.float32, device=DEV, generator=g2) - 0.5
+    out = tr.forward(x, 2.0, {"z": mk(192, h // 64, w // 64), "y": mk(320, h // 16, w // 16)})
+    torch.cuda.synchronize()
+    # evaluation-mode reconstruction of the synced model (clamped) vs the trainer's training-mode forward (unclamped):
+    # same weights, same quantised latents up to straight-through rounding
+    assert _rel(out["fake_images"].clamp(-1, 1).cpu(), a["fake_images"].cpu()) < 2e-2

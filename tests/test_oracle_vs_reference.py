@@ -91,6 +91,51 @@ def test_forward_train_equal_with_replayed_noise(oracle, ref_model):
     assert float(ref["fake_images"].abs().max()) > 0 and not torch.equal(ref["likelihoods"]["y"], ref["q_likelihoods"]["y"])
 
 
+def test_training_gradients_equal_reference_autograd(oracle, ref_model):
+    """The gradients the GPU training step is checked against (tests/test_gpu_train.py) are autograd through the oracle's
+    forward_train; here they are pinned to autograd through the UNMODIFIED reference model (same seed -> same noise):
+    rate + MSE loss, every parameter's gradient."""
+    sd = {k: v.detach().clone() for k, v in ref_model.state_dict().items()}
+    n, h, w = 1, 64, 64
+    x = torch.rand(n, 3, h, w, generator=torch.Generator().manual_seed(14)) * 2 - 1
+    q, beta = 1.5, 2.56
+
+    def loss_of(out):
+        bits = lambda lik: (-torch.log2(lik)).sum((1, 2, 3))
+        bpp = (bits(out["likelihoods"]["y"]) + bits(out["likelihoods"]["z"])) / (h * w)
+        return 0.8 * bpp.mean() + 150.0 * torch.mean(((x + 1) / 2 - (out["fake_images"] + 1) / 2) ** 2)
+
+    ref_model.zero_grad()
+    torch.manual_seed(78)
+    loss_of(ref_model.forward(x, q, beta, is_train=True)).backward()
+    ref = {k: p.grad.detach().clone() for k, p in ref_model.named_parameters() if p.grad is not None}
+    ref_model.zero_grad()
+
+    torch.manual_seed(78)
+    zc, yc, hz, wz, hy, wy = 192, 320, h // 64, w // 64, h // 16, w // 16
+    nz = torch.empty(zc, 1, n * hz * wz).uniform_(-0.5, 0.5).reshape(zc, n, hz, wz).permute(1, 0, 2, 3).contiguous()
+    ny = torch.cat([torch.empty(n, yc // 10, hy, wy).uniform_(-0.5, 0.5) for _ in range(10)], dim=1)
+    sdr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    eb, gc = oracle.entropy_models(sdr)
+    for p in eb.parameters():
+        p.requires_grad_(True)
+    with torch.enable_grad():
+        loss_of(oracle.forward_train.__wrapped__(sdr, x, q, beta, {"z": nz, "y": ny}, eb, gc)).backward()
+    mine = {k: v.grad for k, v in sdr.items() if v.is_floating_point() and v.grad is not None}
+    for k, p in eb.named_parameters():
+        if p.grad is not None:
+            mine["entropy_model_z." + k] = p.grad
+    checked = 0
+    for k, g in ref.items():
+        if k.endswith("quantiles"):
+            continue          # aux parameter: no gradient from the main loss in either implementation
+        assert k in mine, k
+        den = float(g.abs().max())
+        assert float((mine[k] - g).abs().max()) <= 1e-5 * max(den, 1e-12) + 1e-12, (k, float((mine[k] - g).abs().max()), den)
+        checked += 1
+    assert checked > 580
+
+
 @pytest.mark.parametrize("stage", [1, 2])
 def test_stage_models_bit_equal_and_same_layout(oracle, stage):
     """HyperpriorCharmModel (crdr_stage_1.yaml) and InterpCaHyperpriorCharmModel (crdr_stage_2.yaml).
