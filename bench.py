@@ -39,7 +39,9 @@ WORKLOADS = {
     "kodak1": (512, 768, 1, 1, "weak"),         # configs[0] shape: single-image latency
     "clic": (1365, 2048, 16, 8, "strong"),      # configs[2]: a fixed list of 16 images sharded round-robin over the ranks
     "uhd": (2160, 3840, 1, 1, "weak"),          # configs[3]: single-image latency; one image per GPU at N = 8
+    "train": (256, 256, 8, 8, "weak"),          # configs[4]: crdr_stage_2 training step, 8 crops per GPU, gradient all-reduce
 }
+TRAIN_MAC_PER_PX = 1090930   # one forward pass per pixel; forward + dgrad + wgrad = 3 x
 SWEEP = [0.25 * i for i in range(17)]
 BETAS = [0.0, 3.84]
 MAC_PER_PX = 1478360  # encode + decode, per padded pixel
@@ -113,8 +115,152 @@ def cpu_codec_sample(images_per_step, steps, warmup):
     return images_per_step * H * W / sec / 1e6, sec, cores
 
 
+def cpu_train_sample(crops, steps, warmup):
+    """Times the reference algorithm's training step (oracle forward_train + torch.autograd backward, CPU fp32, all host
+    threads) on `crops` 256 x 256 crops: rate + MSE losses of crdr_stage_2.yaml, gradients of every parameter."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import crdr_oracle as orc
+    import make_state
+    import fixtures
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = make_state.random_state_dict(seed=0, calibrated=False, config="crdr_stage_2.yaml")
+    h = w = 256
+    x = fixtures.image(crops, h, w, seed=7)
+    g = torch.Generator().manual_seed(1)
+    times = []
+    for s in range(warmup + steps):
+        noise = {"z": torch.rand(crops, 192, h // 64, w // 64, generator=g) - 0.5, "y": torch.rand(crops, 320, h // 16, w // 16, generator=g) - 0.5}
+        t0 = time.perf_counter()
+        sdr = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+        eb, gc = orc.entropy_models(sdr)
+        with torch.enable_grad():
+            out = orc.forward_train.__wrapped__(sdr, x, float(s % 5), None, noise, eb, gc)
+            bits = lambda lik: (-torch.log2(lik)).sum((1, 2, 3))
+            bpp = (bits(out["likelihoods"]["y"]) + bits(out["likelihoods"]["z"])) / (h * w)
+            (0.8 * bpp.mean() + 150.0 * torch.mean(((x + 1) / 2 - (out["fake_images"] + 1) / 2) ** 2)).backward()
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return crops * h * w / sec / 1e6, sec, cores
+
+
+TRAIN_METRIC = "training MPix/s (crdr_stage_2 step: forward + backward + gradient all-reduce + Adam, device-timed)"
+
+
+def run_train(args, rank, world, local):
+    """BASELINE configs[4]: one optimisation step of the stage-2 model on 8 crops of 256 x 256 per GPU."""
+    import torch
+    import torch.distributed as dist
+    import fixtures
+    from crdr_b200 import native as nv
+    from crdr_b200 import engine as eng_mod
+    from crdr_b200.train import CodecTrainer
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = f"cuda:{local}"
+    h, w, B = 256, 256, args.batch or 8
+    warmup, steps = max(args.warmup, 3), args.steps
+    model, _ = fixtures.build_model(seed=0, calibrated=False, device=dev, config="crdr_stage_2.yaml")
+    tr = CodecTrainer(model, device=dev, lr=1e-4, clip_max_norm=1.0)
+    crops = [fixtures.image(B, h, w, seed=1000 + 17 * rank + i).pin_memory() for i in range(4)]
+    crops_dev = [c.to(dev) for c in crops]
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        tr.train_step(crops_dev[i % 4], q=float(i % 5), generator=gen)
+        flush.zero_()
+    nv.status_check()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = eng_mod.LAUNCH_COUNT[0]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(steps):
+        ld = tr.train_step(crops_dev[i % 4], q=float(i % 5), generator=gen)
+        flush.zero_()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = (eng_mod.LAUNCH_COUNT[0] - l0) // max(steps, 1)
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / steps
+    value = world * B * h * w / (ms_step * 1e-3) / 1e6
+    # end to end: crops from page-locked host memory every step, the loss scalars read back
+    loss_host = torch.empty(2, dtype=torch.float32, pin_memory=True)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.e2e_steps):
+        xd = crops[i % 4].to(dev, non_blocking=True)
+        ld = tr.train_step(xd, q=float(i % 5), generator=gen)
+        loss_host.copy_(torch.stack([ld["rate"], ld["distortion"]]), non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    flops_step = 3 * 2.0 * TRAIN_MAC_PER_PX * B * h * w
+    tensor_peak, hbm_peak, peak_src = peaks()
+    achieved = flops_step / (ms_step * 1e-3) / 1e12
+    if rank == 0:
+        line = {
+            "metric": TRAIN_METRIC, "value": value, "unit": "MPix/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 planes (3-term split forward in g_a/h_a/h_s/ChARM), fp16 activation gradients under a loss scale, fp32 "
+                     "accumulate / parameters / gradients / Adam",
+            "data": "synthetic",
+            "config": {"workload": f"train: crdr_stage_2.yaml (InterpCaHyperpriorCharmModel), {B} crops {h}x{w} per GPU, rate (HiFiC "
+                                   "variable-rate switch) + MSE losses (LPIPS left out: no pretrained weights offline), clip 1.0, Adam 1e-4; "
+                                   "seeded random-init weights, one quality level per step",
+                       "step": "training-mode forward (taped) + backward (wgrad / dgrad / element-wise kernels) + gradient "
+                               "all-reduce (NCCL, N > 1) + fused Adam + re-packing of the tensor-core matrices",
+                       "l2": "256 MiB memset between steps (inside the timed region)", "e2e_steps": args.e2e_steps},
+            "e2e": {"value": world * B * h * w / te.item() / 1e6, "unit": "MPix/s", "h2d_bytes_per_step": B * 3 * h * w * 4,
+                    "d2h_bytes_per_step": 8 + 4, "s_per_step": te.item()},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "whole step (launch-bound at this batch size)",
+                         "flops_per_step": flops_step,
+                         "note": "algorithmic FLOPs = 3 x 2 x 1,090,930 MAC/px (forward + dgrad + wgrad) x pixels"},
+            "losses": {k: float(v) for k, v in ld.items()},
+        }
+        if not args.no_cpu_baseline:
+            v, sec, cores = cpu_train_sample(1, 1, 1)
+            line["cpu_baseline"] = {"value": v, "unit": "MPix/s", "cores": cores, "kind": "port",
+                                    "sample": f"1 warm-up + 1 timed step on 1 crop {h}x{w}: oracle forward_train + torch.autograd backward, {sec:.1f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args, rank):
     if rank != 0:
+        return
+    if args.workload == "train":
+        warm, steps = min(args.warmup, 1), min(args.steps, 3)
+        v, sec, cores = cpu_train_sample(1, steps, warm)
+        print(json.dumps({
+            "impl": "reference", "metric": TRAIN_METRIC, "value": v, "unit": "MPix/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "train: crdr_stage_2.yaml, 1 crop 256x256 per step (bounded sample), rate + MSE losses"},
+            "cpu_baseline": {"value": v, "unit": "MPix/s", "cores": cores, "kind": "port",
+                             "sample": f"{steps} timed steps x 1 crop 256x256: oracle forward_train + torch.autograd backward"},
+            "e2e": {"value": v, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
         return
     global H, W
     H, W = WORKLOADS[args.workload][:2]
@@ -161,6 +307,8 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU implementation (use --impl reference)")
+    if args.workload == "train":
+        return run_train(args, rank, world, local)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

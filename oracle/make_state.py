@@ -16,8 +16,13 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def random_state_dict(seed=0, calibrated=True):
+def random_state_dict(seed=0, calibrated=True, config="crdr.yaml"):
     layout = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_layout_crdr.json")))
+    if config == "crdr_stage_2.yaml":
+        # InterpCaHyperpriorCharmModel = the crdr.yaml model without the decoder's beta conditioning (MLP + 27 projections)
+        layout = {k: v for k, v in layout.items() if not (k.startswith("decoder.mlp.") or ".proj_" in k)}
+    elif config != "crdr.yaml":
+        raise ValueError(config)
     g = torch.Generator().manual_seed(seed)
     sd = {}
     for key, (shape, dtype) in layout.items():
