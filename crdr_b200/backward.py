@@ -27,9 +27,11 @@ def workspace(nbytes, device):
     return buf
 
 
-def wgrad(s, s_coff, ca, b, b_coff, cb, taps, stride, out, sa, sb, st, scale=1.0, accumulate=False):
+def wgrad(s, s_coff, ca, b, b_coff, cb, taps, stride, out, sa, sb, st, scale=1.0, accumulate=False, ws=None):
     """out[t*st + a*sa + b*sb] (+)= scale * sum_p S[p][a] * B[p*stride + tap_t][b].
-    s, b: Act (hi planes are read); out: fp32 device tensor (the parameter gradient, in the parameter's layout)."""
+    s, b: Act (hi planes are read); out: fp32 device tensor (the parameter gradient, in the parameter's layout).
+    ws: scratch tensor of the calling stream (default: the shared per-device workspace); a smaller one than the kernel
+    would like only lowers the split-K count."""
     assert s.n == b.n
     d = nv.WgradDesc()
     d.s = nv.Planes(s.hi.data_ptr(), None, s.c, s_coff)
@@ -47,8 +49,9 @@ def wgrad(s, s_coff, ca, b, b_coff, cb, taps, stride, out, sa, sb, st, scale=1.0
     need = L.crdr_conv_wgrad_workspace(C.byref(d))
     if need == 0:
         raise nv.NativeError(f"crdr_conv_wgrad_workspace: {L.crdr_last_error().decode()}")
-    ws = workspace(need, s.hi.device)
-    d.workspace, d.workspace_bytes = ws.data_ptr(), need
+    if ws is None:
+        ws = workspace(need, s.hi.device)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), min(need, ws.numel() * ws.element_size())
     nv.check(L.crdr_conv_wgrad(C.byref(d), nv.stream_handle()))
 
 
@@ -78,6 +81,26 @@ class PackedConv:
         for phs in self.op.phases:
             nv.check(L.crdr_pack_weights(self.master.data_ptr(), phs.map.data_ptr(), phs.map.numel(), phs.w_hi.data_ptr(),
                                          nv.ptr(phs.w_lo), st))
+
+
+class PackTable:
+    """Device-resident job table for crdr_pack_weights_multi: every matrix of a set of PackedConvs in one launch."""
+
+    def __init__(self, packed_convs, device):
+        import numpy as np
+        jobs = [(pc.master.data_ptr(), phs.map.data_ptr(), phs.map.numel(), phs.w_hi.data_ptr(),
+                 phs.w_lo.data_ptr() if phs.w_lo is not None else 0) for pc in packed_convs for phs in pc.op.phases]
+        self.count = len(jobs)
+        arr = (nv.PackJob * self.count)()
+        for i, (m, mp, cnt, hi, lo) in enumerate(jobs):
+            arr[i].master, arr[i].map, arr[i].count, arr[i].hi, arr[i].lo = m, mp, cnt, hi, lo or None
+        raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+        self.table = torch.from_numpy(raw).to(device)
+        self.keep = list(packed_convs)
+
+    def run(self):
+        if self.count:
+            nv.check(nv.lib().crdr_pack_weights_multi(self.table.data_ptr(), self.count, nv.stream_handle()))
 
 
 def dgrad_spec(transposed, stride, padding, kh):
@@ -119,6 +142,9 @@ class DgradSet:
     def repack(self):
         for pc, _, _ in self.parts:
             pc.repack()
+
+    def packed(self):
+        return [pc for pc, _, _ in self.parts]
 
     def run(self, dv, grad, accumulate=True, dv_coff=0, dv_c=None):
         """dv: Act (fp16 gradient of the convolution result; channels [dv_coff, dv_coff + dv_c) when it is a range of a

@@ -73,6 +73,7 @@ int max_abs_launch(const float* x, int64_t count, float* out, cudaStream_t st);
 size_t wgrad_workspace_bytes(const crdr_wgrad_desc* d);
 int wgrad_launch(const crdr_wgrad_desc* d, cudaStream_t st);
 int pack_weights_launch(const float* master, const int32_t* map, int64_t count, void* hi, void* lo, cudaStream_t st);
+int pack_weights_multi_launch(const crdr_pack_job* jobs, int njobs, cudaStream_t st);
 int epi_bwd_launch(const crdr_epi_bwd_desc* d, cudaStream_t st);
 int colsum_finish_launch(const float* partial, int blocks, int nsums, int which, int c, float* out, float scale, int accumulate,
                          cudaStream_t st);
@@ -81,7 +82,7 @@ int gauss_bwd_launch(const crdr_gauss_bwd_desc* d, cudaStream_t st);
 int mse_bwd_launch(const float* fake, int fake_cs, const float* real, int n, int hb, int wb, int h, int w, float coef, void* g,
                    int g_cs, cudaStream_t st);
 int adam_launch(float* p, const float* g, float* m, float* v, int64_t count, float lr, float b1, float b2, float eps, int step,
-                const float* gscale_ptr, float gscale, cudaStream_t st);
+                const float* gscale_ptr, float gscale, const float* hyper, cudaStream_t st);
 int sumsq_launch(const float* x, int64_t count, float* partial1024, float* out, cudaStream_t st);
 
 }  // namespace crdr
@@ -239,6 +240,9 @@ int crdr_conv_wgrad(const crdr_wgrad_desc* d, void* stream) {
 int crdr_pack_weights(const float* master, const int32_t* map, int64_t count, void* hi, void* lo, void* stream) {
   return pack_weights_launch(master, map, count, hi, lo, (cudaStream_t)stream);
 }
+int crdr_pack_weights_multi(const crdr_pack_job* jobs, int32_t njobs, void* stream) {
+  return pack_weights_multi_launch(jobs, njobs, (cudaStream_t)stream);
+}
 int crdr_epilogue_backward(const crdr_epi_bwd_desc* d, void* stream) {
   if (!d) { set_error("epilogue_backward: null descriptor"); return CRDR_ERR_BAD_SHAPE; }
   return epi_bwd_launch(d, (cudaStream_t)stream);
@@ -264,8 +268,8 @@ int crdr_mse_backward(const float* fake, int32_t fake_cs, const float* real, int
   return mse_bwd_launch(fake, fake_cs, real, n, hb, wb, h, w, coef, g, g_cs, (cudaStream_t)stream);
 }
 int crdr_adam_step(float* p, const float* g, float* m, float* v, int64_t count, float lr, float beta1, float beta2, float eps,
-                   int32_t step, const float* gscale_ptr, float gscale, void* stream) {
-  return adam_launch(p, g, m, v, count, lr, beta1, beta2, eps, step, gscale_ptr, gscale, (cudaStream_t)stream);
+                   int32_t step, const float* gscale_ptr, float gscale, const float* hyper, void* stream) {
+  return adam_launch(p, g, m, v, count, lr, beta1, beta2, eps, step, gscale_ptr, gscale, hyper, (cudaStream_t)stream);
 }
 int crdr_sum_squares(const float* x, int64_t count, float* partial, float* out, void* stream) {
   return sumsq_launch(x, count, partial, out, (cudaStream_t)stream);

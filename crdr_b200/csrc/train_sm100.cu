@@ -30,6 +30,30 @@ int pack_weights_launch(const float* master, const int32_t* map, int64_t count, 
   return check_launch("pack_weights_kernel");
 }
 
+// All matrices of a model in ONE launch: blockIdx.y selects the job (a device-resident table built once, the pointers are
+// stable), blockIdx.x strides over its elements.
+__global__ void pack_weights_multi_kernel(const crdr_pack_job* __restrict__ jobs) {
+  const crdr_pack_job j = jobs[blockIdx.y];
+  const float* __restrict__ master = j.master;
+  const int32_t* __restrict__ map = j.map;
+  __half* __restrict__ hi = (__half*)j.hi;
+  __half* __restrict__ lo = (__half*)j.lo;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < j.count; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t m = map[i];
+    float v = m >= 0 ? master[m] : 0.0f;
+    v = fminf(fmaxf(v, -65504.0f), 65504.0f);
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    if (lo) lo[i] = __float2half_rn((v - __half2float(h)) * kLoScale);
+  }
+}
+
+int pack_weights_multi_launch(const crdr_pack_job* jobs, int njobs, cudaStream_t st) {
+  if (!jobs || njobs <= 0 || njobs > 65535) { set_error("pack_weights_multi: bad job table"); return CRDR_ERR_BAD_SHAPE; }
+  pack_weights_multi_kernel<<<dim3(32, (unsigned)njobs), 256, 0, st>>>(jobs);
+  return check_launch("pack_weights_multi_kernel");
+}
+
 // ----------------------------------------------------------------------------------------------
 // 8-channel vector helpers on fp16 planes
 // ----------------------------------------------------------------------------------------------
@@ -191,20 +215,29 @@ int epi_bwd_launch(const crdr_epi_bwd_desc* dp, cudaStream_t st) {
   return check_launch("epi_bwd_kernel");
 }
 
-// out[c] (+)= scale * sum over blocks (ascending) of partial[b][which][c]
-__global__ void colsum_finish_kernel(const float* __restrict__ partial, int blocks, int nsums, int which, int c, float* out,
-                                     float scale, int accumulate) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
+// out[c] (+)= scale * sum over blocks of partial[b][which][c].  Block (32, 8): lane x owns a channel, the 8 rows take
+// interleaved subsets of the row blocks and are combined through shared memory in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ partial, int blocks, int nsums, int which, int c,
+                                                            float* out, float scale, int accumulate) {
+  __shared__ float s_red[8][32];
+  const int ch = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int b = 0; b < blocks; ++b) s += partial[((int64_t)b * nsums + which) * c + ch];
-  out[ch] = accumulate ? fmaf(s, scale, out[ch]) : s * scale;
+  if (ch < c)
+    for (int b = threadIdx.y; b < blocks; b += 8) s += partial[((int64_t)b * nsums + which) * c + ch];
+  s_red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && ch < c) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += s_red[y][threadIdx.x];
+    out[ch] = accumulate ? fmaf(t, scale, out[ch]) : t * scale;
+  }
 }
 
 int colsum_finish_launch(const float* partial, int blocks, int nsums, int which, int c, float* out, float scale, int accumulate,
                          cudaStream_t st) {
   if (!partial || !out || blocks < 1 || c < 1 || which < 0 || which >= nsums) { set_error("colsum_finish: bad arguments"); return CRDR_ERR_BAD_SHAPE; }
-  colsum_finish_kernel<<<(c + 127) / 128, 128, 0, st>>>(partial, blocks, nsums, which, c, out, scale, accumulate);
+  colsum_finish_kernel<<<(c + 31) / 32, dim3(32, 8), 0, st>>>(partial, blocks, nsums, which, c, out, scale, accumulate);
   return check_launch("colsum_finish_kernel");
 }
 
@@ -303,6 +336,7 @@ int gate_launch(const crdr_gate_desc* dp, int backward, cudaStream_t st) {
 // ----------------------------------------------------------------------------------------------
 __global__ void gauss_bwd_kernel(const crdr_gauss_bwd_desc d, uint32_t* status) {
   const int64_t total = (int64_t)d.n * d.hw * d.c;
+  const float coef = d.coef_scale ? d.coef * d.coef_scale[0] : d.coef;   // device-resident rate weight (graph replay)
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int ch = (int)(i % d.c);
     const int64_t pix = i / d.c;
@@ -316,7 +350,7 @@ __global__ void gauss_bwd_kernel(const crdr_gauss_bwd_desc d, uint32_t* status) 
     const float v = fabsf(x);
     const float up = (0.5f - v) / s, lo = (-0.5f - v) / s;
     const float L = 0.5f * erfcf(-0.70710678118654752f * up) - 0.5f * erfcf(-0.70710678118654752f * lo);
-    const float gL = -d.coef / fmaxf(L, d.lik_bound);      // LowerBound passes every negative gradient
+    const float gL = -coef / fmaxf(L, d.lik_bound);        // LowerBound passes every negative gradient
     const float pu = 0.3989422804014327f * expf(-0.5f * up * up), pl = 0.3989422804014327f * expf(-0.5f * lo * lo);
     const float dLdv = -(pu - pl) / s;
     const float dLds = -(up * pu - lo * pl) / s;
@@ -394,8 +428,9 @@ int mse_bwd_launch(const float* fake, int fake_cs, const float* real, int n, int
 // ----------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             int64_t count, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
-                            const float* __restrict__ gscale_ptr, float gscale) {
+                            const float* __restrict__ gscale_ptr, float gscale, const float* __restrict__ hyper) {
   const float gs = gscale_ptr ? gscale * gscale_ptr[0] : gscale;
+  if (hyper) { lr = hyper[0]; bc1 = hyper[1]; bc2_sqrt = hyper[2]; }   // device-resident schedule (graph replay)
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = g[i] * gs;
     const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
@@ -408,12 +443,13 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 
 int adam_launch(float* p, const float* g, float* m, float* v, int64_t count, float lr, float b1, float b2, float eps, int step,
-                const float* gscale_ptr, float gscale, cudaStream_t st) {
-  if (!p || !g || !m || !v || count <= 0 || step < 1) { set_error("adam: bad arguments"); return CRDR_ERR_BAD_SHAPE; }
+                const float* gscale_ptr, float gscale, const float* hyper, cudaStream_t st) {
+  if (!p || !g || !m || !v || count <= 0 || (step < 1 && !hyper)) { set_error("adam: bad arguments"); return CRDR_ERR_BAD_SHAPE; }
+  if (step < 1) step = 1;
   const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
   int64_t blocks = (count + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, count, lr, b1, b2, eps, bc1, sqrtf(bc2), gscale_ptr, gscale);
+  adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, count, lr, b1, b2, eps, bc1, sqrtf(bc2), gscale_ptr, gscale, hyper);
   return check_launch("adam_kernel");
 }
 

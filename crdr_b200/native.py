@@ -104,6 +104,10 @@ class WgradDesc(C.Structure):
     ]
 
 
+class PackJob(C.Structure):
+    _fields_ = [("master", C.c_void_p), ("map", C.c_void_p), ("count", C.c_int64), ("hi", C.c_void_p), ("lo", C.c_void_p)]
+
+
 class EpiBwdDesc(C.Structure):
     _fields_ = [
         ("g", Planes), ("out", Planes),
@@ -135,6 +139,7 @@ class GaussBwdDesc(C.Structure):
         ("n", C.c_int32), ("hw", C.c_int32), ("c", C.c_int32), ("c_total", C.c_int32), ("nchw_coff", C.c_int32),
         ("scale_bound", C.c_float), ("lik_bound", C.c_float), ("coef", C.c_float),
         ("gpre", Planes), ("dy", Planes), ("dmu", Planes), ("dsigma", Planes),
+        ("coef_scale", C.c_void_p),
     ]
 
 
@@ -146,7 +151,7 @@ SM100_SYMBOLS = [
     "crdr_gauss_quantize", "crdr_gauss_indexes", "crdr_gauss_dequantize", "crdr_eb_quantize",
     "crdr_eb_dequantize", "crdr_bits_from_likelihood", "crdr_max_abs", "crdr_max_abs_batch",
     "crdr_image_u8_to_patches", "crdr_phases_to_image_u8", "crdr_phases_to_image_ex",
-    "crdr_conv_dgrad", "crdr_conv_wgrad_workspace", "crdr_conv_wgrad", "crdr_pack_weights", "crdr_epilogue_backward",
+    "crdr_conv_dgrad", "crdr_conv_wgrad_workspace", "crdr_conv_wgrad", "crdr_pack_weights", "crdr_pack_weights_multi", "crdr_epilogue_backward",
     "crdr_colsum_finish", "crdr_gate_forward", "crdr_gate_backward", "crdr_gauss_backward", "crdr_mse_backward",
     "crdr_adam_step", "crdr_sum_squares",
 ]
@@ -197,13 +202,14 @@ def lib():
         L.crdr_conv_wgrad_workspace.restype = C.c_size_t
         L.crdr_conv_wgrad.argtypes = [C.POINTER(WgradDesc), vp]
         L.crdr_pack_weights.argtypes = [vp, vp, i64, vp, vp, vp]
+        L.crdr_pack_weights_multi.argtypes = [vp, i32, vp]
         L.crdr_epilogue_backward.argtypes = [C.POINTER(EpiBwdDesc), vp]
         L.crdr_colsum_finish.argtypes = [vp, i32, i32, i32, i32, vp, f32, i32, vp]
         L.crdr_gate_forward.argtypes = [C.POINTER(GateDesc), vp]
         L.crdr_gate_backward.argtypes = [C.POINTER(GateDesc), vp]
         L.crdr_gauss_backward.argtypes = [C.POINTER(GaussBwdDesc), vp]
         L.crdr_mse_backward.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, f32, vp, i32, vp]
-        L.crdr_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp, f32, vp]
+        L.crdr_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp, f32, vp, vp]
         L.crdr_sum_squares.argtypes = [vp, i64, vp, vp, vp]
         L.crdr_debug_conv_epilogue.argtypes = [i32, i32]
         L.crdr_debug_conv_epilogue.restype = None

@@ -63,6 +63,7 @@ class TrainContext:
             self.grads[k] = self.flat_g[off:off + p.numel()].view(p.shape)
         self.buffers = {k: b.detach().to(self.device) for k, b in model.named_buffers()}
         self._grad_by_ptr = {self.params[k].data_ptr(): self.grads[k] for k in self.names}
+        self._pack_table = None
         self.live = {}          # sub-network name -> live state dict (views of flat_p)
         self.gain_state = {}    # "encoder" / "decoder" -> (engine, l, r, alpha, lerped weights)
         self.gain_grad = {}
@@ -87,16 +88,25 @@ class TrainContext:
         conv.op = conv.packed.op
         conv.wmap = None
         if transform is not None:
-            conv.wmap = (transform(bw.index_weight(tuple(w.shape))).round().to(torch.int64) - 1).reshape(-1).to(self.device)
+            conv.wmap = (transform(bw.index_weight(tuple(w.shape))).round().to(torch.int64) - 1).reshape(-1)
+            conv.wmap_src = torch.nonzero(conv.wmap >= 0).reshape(-1).to(self.device)      # positions in the ConvOp's layout
+            conv.wmap_dst = conv.wmap[conv.wmap >= 0].to(self.device)                      # ... and in the parameter
+            conv.wmap = conv.wmap.to(self.device)
         conv.dgrad = None
         self.convs.append(conv)
 
     def repack(self):
-        """After an optimiser step: re-pack every forward / adjoint matrix and refresh the derived bias vectors."""
+        """After an optimiser step: re-pack every forward / adjoint matrix (one launch over a device-resident job table,
+        rebuilt whenever a backward pass has created new adjoint matrices) and refresh the derived bias vectors."""
+        packed = []
         for conv in self.convs:
-            conv.packed.repack()
+            packed.append(conv.packed)
             if conv.dgrad is not None:
-                conv.dgrad.repack()
+                packed += conv.dgrad.packed()
+        if self._pack_table is None or self._pack_table.count != sum(len(pc.op.phases) for pc in packed):
+            self._pack_table = bw.PackTable(packed, self.device)
+        self._pack_table.run()
+        for conv in self.convs:
             if conv.bias_buf is not None:
                 conv.bias_buf.copy_(conv.bias_transform(conv.bias_master))
 
@@ -207,9 +217,26 @@ class CodecTrainer:
         self.step_count = 0
         self.pg = process_group
         self._sumsq = torch.zeros(1024 + 1, dtype=torch.float32, device=self.device)
+        # everything a captured step reads that changes from step to step lives in device memory: the HiFiC rate weight,
+        # the learning rates and Adam's bias corrections
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self._rate_w = torch.zeros(1, **f32)
+        self._lr = torch.tensor([lr, aux_lr], **f32)
+        self._step_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._hyper = torch.zeros(2, 4, **f32)           # rows: main / aux; columns: lr, 1 - b1^t, sqrt(1 - b2^t), unused
+        self._clip_coef = torch.ones(1, **f32)
         ctx.repack()
         self._grads = {}     # activation storage pointer -> gradient Act of the current step
         self._keep = []
+        self._warm, self._graphs, self._pool = set(), {}, None
+        self.use_graphs = True
+        bw.workspace(256 << 20, self.device)   # split-K partial sums / column sums: sized once (no growth inside a capture)
+        # parameter-gradient work (wgrad + split-K reduction, bias / gain column sums) hangs off the critical chain
+        # epilogue-backward -> dgrad -> next layer: it runs on side streams with their own scratch and joins at the end
+        self.side_streams = int(__import__("os").environ.get("CRDR_TRAIN_SIDE_STREAMS", "4"))
+        self._sides = [(torch.cuda.Stream(device=self.device), torch.empty(64 << 20, dtype=torch.uint8, device=self.device))
+                       for _ in range(self.side_streams)]
+        self._side_next, self._side_used = 0, set()
 
     # ------------------------------------------------------------------ forward (training mode, taped)
     def _eb_kernel_params(self):
@@ -268,18 +295,26 @@ class CodecTrainer:
         nv.check(nv.lib().crdr_bits_from_likelihood(lik.data_ptr(), n, lik[0].numel(), out.data_ptr(), nv.stream_handle()))
         return out
 
-    def losses(self, images, out, q):
-        """rate_distortion_trainer.py:70-76 with HificVariableRateLoss (rate_loss.py:84-175) and MSELoss (0_1 scale)."""
+    def _losses_device(self, images, out, q):
+        """rate_distortion_trainer.py:70-76 with HificVariableRateLoss (rate_loss.py:84-175) and MSELoss (0_1 scale), all
+        on the device: the rate weight (lambda_A if the quantised bpp exceeds the target else lambda_B) is decided by a
+        torch.where and left in self._rate_w for the backward kernels, so a step needs no host round trip."""
         h, w = out["size"]
         bpp = (self._bits(out["y_lik_noisy"]) + self._bits(out["z_lik_noisy"])) / (h * w)
         qbpp = (self._bits(out["y_lik"]) + self._bits(out["z_lik"])) / (h * w)
         lvl = int(q) if self.uses_rate else 0
-        lam_a = self.lambda_a[lvl] if isinstance(self.lambda_a, (list, tuple)) else self.lambda_a
-        lam_b = self.lambda_b[lvl] if isinstance(self.lambda_b, (list, tuple)) else self.lambda_b
-        tgt = self.target[lvl] if isinstance(self.target, (list, tuple)) else self.target
-        rate_w = lam_a if float(qbpp.mean().item()) > tgt else lam_b
+        pick = lambda v: float(v[lvl]) if isinstance(v, (list, tuple)) else float(v)
+        lam_a, lam_b, tgt = pick(self.lambda_a), pick(self.lambda_b), pick(self.target)
+        rate_w = torch.where(qbpp.mean() > tgt, torch.full_like(self._rate_w, lam_a), torch.full_like(self._rate_w, lam_b))
+        self._rate_w.copy_(rate_w)
         mse = torch.mean(((images + 1) / 2 - (out["fake_images"] + 1) / 2) ** 2)
-        return dict(rate=rate_w * bpp.mean(), distortion=self.lambda_mse * mse, bpp=bpp.mean(), qbpp=qbpp.mean(), rate_weight=rate_w)
+        return dict(rate=(rate_w * bpp.mean()).reshape(()), distortion=self.lambda_mse * mse, bpp=bpp.mean(), qbpp=qbpp.mean(),
+                    rate_weight=rate_w.reshape(()))
+
+    def losses(self, images, out, q):
+        ld = self._losses_device(images, out, q)
+        ld["rate_weight"] = float(ld["rate_weight"].item())
+        return ld
 
     # ------------------------------------------------------------------ backward
     def _grad(self, key, like=None, shape=None):
@@ -291,10 +326,54 @@ class CodecTrainer:
         return g
 
     def _partial(self, blocks, nsums, c):
-        return bw.workspace(1 << 24, self.device)[: blocks * nsums * c * 4].view(torch.float32)
+        """Per-record scratch for the per-block column sums, alive until the step ends (side streams read it later)."""
+        t = torch.empty(blocks * nsums * c, dtype=torch.float32, device=self.device)
+        self._keep.append(t)
+        return t
 
-    def backward(self, images, out, rate_weight):
-        """Reverse sweep over the tape; fills ctx.flat_g (unscaled fp32 gradients of mean-reduced losses)."""
+    class _Side:
+        """with trainer._side() as ws: ... -- enqueue on the next side stream (forked from the current stream here)."""
+
+        def __init__(self, tr):
+            self.tr = tr
+
+        def __enter__(self):
+            tr = self.tr
+            if not tr._sides:
+                return None
+            self.main = torch.cuda.current_stream()
+            i = tr._side_next
+            tr._side_next = (i + 1) % len(tr._sides)
+            stream, ws = tr._sides[i]
+            ev = torch.cuda.Event()
+            ev.record(self.main)
+            stream.wait_event(ev)
+            tr._side_used.add(i)
+            self.ctx = torch.cuda.stream(stream)
+            self.ctx.__enter__()
+            return ws
+
+        def __exit__(self, *exc):
+            if self.tr._sides:
+                self.ctx.__exit__(*exc)
+            return False
+
+    def _side(self):
+        return CodecTrainer._Side(self)
+
+    def _join_sides(self):
+        main = torch.cuda.current_stream()
+        for i in sorted(self._side_used):
+            ev = torch.cuda.Event()
+            ev.record(self._sides[i][0])
+            main.wait_event(ev)
+        self._side_used.clear()
+
+    def backward(self, images, out, rate_weight=None):
+        """Reverse sweep over the tape; fills ctx.flat_g (unscaled fp32 gradients of mean-reduced losses).  rate_weight:
+        a float overrides the device-resident weight the last losses() call decided."""
+        if rate_weight is not None:
+            self._rate_w.fill_(float(rate_weight))
         ctx, L, st = self.ctx, nv.lib(), nv.stream_handle()
         n = images.shape[0]
         h, w = out["size"]
@@ -310,7 +389,7 @@ class CodecTrainer:
         coef_mse = S * self.lambda_mse * 2.0 * 0.25 / (n * 3 * h * w)
         nv.check(L.crdr_mse_backward(fp.data_ptr(), fp.shape[-1], images.data_ptr(), n, h // 2, w // 2, h, w, coef_mse,
                                      g_img.hi.data_ptr(), 16, st))
-        self._rate_coef = S * rate_weight / (math.log(2.0) * n * h * w)   # d(rate_w * mean bpp) / d(-ln L) per element
+        self._rate_coef = S / (math.log(2.0) * n * h * w)   # d(mean bpp) / d(-ln L) per element; x the device-resident rate weight
         tape, ctx.tape = ctx.tape, None
         for rec in reversed(tape):
             kind = rec[0]
@@ -324,8 +403,8 @@ class CodecTrainer:
                 self._gauss_backward(*rec[1:])
             elif kind == "eb":
                 self._eb_backward(*rec[1:])
+        self._join_sides()
         ctx.finish_gain_grads(inv)
-        nv.status_check()
 
     def _sums_to(self, partial, blocks, nsums, which, c, target, accumulate=True, scale=None):
         nv.check(nv.lib().crdr_colsum_finish(partial.data_ptr(), blocks, nsums, which, c, target.data_ptr(),
@@ -379,7 +458,33 @@ class CodecTrainer:
             d.dres = nv.Planes(Gr.hi.data_ptr(), None, Gr.c, coff)
         d.partial, d.blocks = partial.data_ptr(), blocks
         nv.check(L.crdr_epilogue_backward(C.byref(d), st))
-        # bias / gain sums
+        segs = kw.get("segs") or [(0, op.cin)]
+        if need_dv:
+            self._keep.append(dv)       # read by the side stream after this function returns
+        with self._side() as ws:
+            self._param_grads(conv, op, x, kw, dv, dv_coff, cout, partial, blocks, scale, shift, affine, ws)
+        # dgrad
+        if no_input_grad:
+            return
+        if conv.dgrad is None:
+            assert conv.wmap is None or conv.name == "conv4", "only the last layer has a transformed weight and an input gradient"
+            if conv.wmap is not None:
+                # adjoint of the phase-packed 3x3 convolution [16, cin, 3, 3] built from the parameter through both maps
+                tf = conv.packed_transform
+                fn, dkw = bw.dgrad_spec(False, 1, op.padding, op.kh)
+                conv.dgrad = _SingleDgrad(bw.PackedConv(conv.master, lambda wi: fn(tf(wi)), two_planes=False, **dkw))
+            else:
+                conv.dgrad = bw.DgradSet(conv.master, op.transposed, op.stride, op.padding, op.kh, segs, cin_real=op.cin_real)
+            conv.dgrad.repack()
+        Gx = self._grad(x.hi.data_ptr(), like=x)
+        if need_dv:
+            conv.dgrad.run(dv, Gx)
+        else:
+            conv.dgrad.run(G, Gx, dv_coff=gcoff, dv_c=cout)
+
+    def _param_grads(self, conv, op, x, kw, dv, dv_coff, cout, partial, blocks, scale, shift, affine, ws):
+        """Bias / gain column sums and the weight gradient of one convolution record (side stream)."""
+        ctx = self.ctx
         if conv.bias_master is not None:
             if conv.bias_buf is not None:      # derived bias vector (phase-packed last layer): fold the phases back
                 tmp = torch.zeros(cout, dtype=torch.float32, device=self.device)
@@ -401,9 +506,8 @@ class CodecTrainer:
             # transformed weight (im2col'd first layer, phase-packed last layer): gradient in the ConvOp's layout, then
             # scattered to the parameter through the transform's index map
             tmp = torch.empty((op.cout_pad, op.cin, op.kh, op.kw), dtype=torch.float32, device=self.device)
-            bw.wgrad(dv, dv_coff, op.cout_pad, x, 0, op.cin, taps, 1, tmp, op.cin * k2, k2, 1, scale=1.0 / self.loss_scale)
-            valid = conv.wmap >= 0
-            ctx.grad_view(conv.master).view(-1).index_add_(0, conv.wmap[valid], tmp.view(-1)[valid])
+            bw.wgrad(dv, dv_coff, op.cout_pad, x, 0, op.cin, taps, 1, tmp, op.cin * k2, k2, 1, scale=1.0 / self.loss_scale, ws=ws)
+            ctx.grad_view(conv.master).view(-1).index_add_(0, conv.wmap_dst, tmp.view(-1)[conv.wmap_src])
         else:
             gw = ctx.grad_view(conv.master).view(-1)
             start = 0
@@ -412,29 +516,11 @@ class CodecTrainer:
                 if real > 0:
                     if op.transposed:   # parameter [ci, co, kh, kw]:  S = x (a = ci), B = dv (b = co)
                         bw.wgrad(x, off, real, dv, dv_coff, op.cout, taps, op.stride, gw[start * op.cout * k2:], op.cout * k2, k2, 1,
-                                 scale=1.0 / self.loss_scale, accumulate=True)
+                                 scale=1.0 / self.loss_scale, accumulate=True, ws=ws)
                     else:               # parameter [co, ci, kh, kw]:  S = dv (a = co), B = x (b = ci)
                         bw.wgrad(dv, dv_coff, op.cout, x, off, real, taps, op.stride, gw[start * k2:], op.cin_real * k2, k2, 1,
-                                 scale=1.0 / self.loss_scale, accumulate=True)
+                                 scale=1.0 / self.loss_scale, accumulate=True, ws=ws)
                 start += ln
-        # dgrad
-        if no_input_grad:
-            return
-        if conv.dgrad is None:
-            assert conv.wmap is None or conv.name == "conv4", "only the last layer has a transformed weight and an input gradient"
-            if conv.wmap is not None:
-                # adjoint of the phase-packed 3x3 convolution [16, cin, 3, 3] built from the parameter through both maps
-                tf = conv.packed_transform
-                fn, dkw = bw.dgrad_spec(False, 1, op.padding, op.kh)
-                conv.dgrad = _SingleDgrad(bw.PackedConv(conv.master, lambda wi: fn(tf(wi)), two_planes=False, **dkw))
-            else:
-                conv.dgrad = bw.DgradSet(conv.master, op.transposed, op.stride, op.padding, op.kh, segs, cin_real=op.cin_real)
-            conv.dgrad.repack()
-        Gx = self._grad(x.hi.data_ptr(), like=x)
-        if need_dv:
-            conv.dgrad.run(dv, Gx)
-        else:
-            conv.dgrad.run(G, Gx, dv_coff=gcoff, dv_c=cout)
 
     def _gate_backward(self, x, t, a, out, scale, shift):
         G = self._grads.get(out.hi.data_ptr())
@@ -490,6 +576,7 @@ class CodecTrainer:
         d.ms_cs, d.mu_coff, d.sigma_coff = ms.shape[-1], s0 * ch.sc, ch.yc + s0 * ch.sc
         d.n, d.hw, d.c, d.c_total, d.nchw_coff = n, hgt * wid, ch.sc * cnt, ch.yc, s0 * ch.sc
         d.scale_bound, d.lik_bound, d.coef = self.gp.bound, 1e-9, self._rate_coef
+        d.coef_scale = self._rate_w.data_ptr()
         d.gpre = nv.Planes(GT.hi.data_ptr(), None, GT.c, ch.off_tmp + s0 * ch.sc)
         d.dy = nv.Planes(Gy.hi.data_ptr(), None, Gy.c, s0 * ch.sc)
         d.dmu = nv.Planes(Gms.hi.data_ptr(), None, Gms.c, s0 * ch.sc)
@@ -508,7 +595,7 @@ class CodecTrainer:
             v = (z + noise_z).permute(1, 0, 2, 3).reshape(c, 1, -1)
             lik = _eb_likelihood(leaves, v)
             lik = lik + (torch.clamp(lik, min=1e-9) - lik).detach()       # LowerBound: every (negative) gradient passes
-            loss = -(self._rate_coef / S) * torch.log(lik).sum()
+            loss = -(self._rate_coef / S) * self._rate_w[0] * torch.log(lik).sum()
             grads = torch.autograd.grad(loss, [z] + [leaves[k] for k in names])
         for k, g in zip(names, grads[1:]):
             ctx.grads["entropy_model_z." + k].add_(g)
@@ -552,37 +639,97 @@ class CodecTrainer:
         g.mul_(1.0 / world)
         return len(handles)
 
+    def set_lr(self, lr=None, aux_lr=None):
+        """Scheduler hook (MultiStepLR of crdr_stage_2.yaml): the rates live on the device."""
+        if lr is not None:
+            self.lr = lr
+            self._lr[0] = lr
+        if aux_lr is not None:
+            self.aux_lr = aux_lr
+            self._lr[1] = aux_lr
+
     def optimizer_step(self):
         ctx, L, st = self.ctx, nv.lib(), nv.stream_handle()
         self.step_count += 1
+        self._step_dev += 1
+        b1, b2 = self.betas
+        bc = torch.stack([1.0 - b1 ** self._step_dev, torch.sqrt(1.0 - b2 ** self._step_dev)], dim=1).to(torch.float32)   # [1, 2]
+        self._hyper[:, 0] = self._lr
+        self._hyper[:, 1:3] = bc
         clip_ptr = None
         if self.clip:
             nv.check(L.crdr_sum_squares(ctx.flat_g.data_ptr(), ctx.n_main_padded, self._sumsq.data_ptr(), self._sumsq[1024:].data_ptr(), st))
-            coef = torch.clamp(self.clip / (torch.sqrt(self._sumsq[1024]) + 1e-6), max=1.0).reshape(1)
-            self._keep.append(coef)
-            clip_ptr = coef.data_ptr()
+            self._clip_coef.copy_(torch.clamp(self.clip / (torch.sqrt(self._sumsq[1024]) + 1e-6), max=1.0).reshape(1))
+            clip_ptr = self._clip_coef.data_ptr()
         nv.check(L.crdr_adam_step(ctx.flat_p.data_ptr(), ctx.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), ctx.n_main_padded,
-                                  self.lr, self.betas[0], self.betas[1], self.eps, self.step_count, clip_ptr, 1.0, st))
+                                  self.lr, b1, b2, self.eps, 0, clip_ptr, 1.0, self._hyper[0].data_ptr(), st))
         if ctx.total > ctx.n_main_padded:   # aux parameters (quantiles): their own learning rate, no clipping
             o, cnt = ctx.n_main_padded, ctx.total - ctx.n_main_padded
             nv.check(L.crdr_adam_step(ctx.flat_p[o:].data_ptr(), ctx.flat_g[o:].data_ptr(), self.m[o:].data_ptr(), self.v[o:].data_ptr(),
-                                      cnt, self.aux_lr, self.betas[0], self.betas[1], self.eps, self.step_count, None, 1.0, st))
+                                      cnt, self.aux_lr, b1, b2, self.eps, 0, None, 1.0, self._hyper[1].data_ptr(), st))
         ctx.repack()
 
+    def _core_a(self, images, q, noise):
+        """Forward + losses + backward + aux gradient: capture-safe (no host synchronisation)."""
+        out = self.forward(images, q, noise)
+        ld = self._losses_device(images, out, q)
+        self.backward(images, out)
+        ld["aux"] = self.aux_step()
+        return ld
+
+    def _distributed(self):
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.pg) > 1
+
     def train_step(self, images, q=None, noise=None, generator=None):
-        """One optimisation step on a batch of [-1, 1] crops (device fp32 NCHW).  Returns the loss dict (device scalars)."""
+        """One optimisation step on a batch of [-1, 1] crops (device fp32 NCHW).  Returns the loss dict (device scalars;
+        overwritten by the next step of the same shape and quality level when CUDA graphs are on).
+
+        The step is ~1 900 small launches whose host enqueue (47 ms) costs several times their device time, so from the
+        second call of a (shape, quality level) on, the step replays two captured CUDA graphs: A = forward + losses +
+        backward, B = clip + Adam + re-packing, with the NCCL gradient all-reduce between them on the same stream."""
         n, _, h, w = images.shape
         if q is None:
             q = float(torch.randint(self.model.rate_level, (1,)).item()) if self.uses_rate else 0.0
         if noise is None:
             mk = lambda c, a, b: torch.rand((n, c, a, b), dtype=torch.float32, device=self.device, generator=generator) - 0.5
             noise = {"z": mk(self.zc, h // 64, w // 64), "y": mk(self.charm.yc, h // 16, w // 16)}
-        out = self.forward(images, q, noise)
-        ld = self.losses(images, out, q)
-        self.backward(images, out, ld["rate_weight"])
-        ld["aux"] = self.aux_step()
+        key = (n, h, w, float(q))
+        if not self.use_graphs or key not in self._warm:
+            # eager: also the warm-up that builds the adjoint matrices, tensor maps and kernel attributes before a capture
+            ld = self._core_a(images, q, noise)
+            self.all_reduce_grads()
+            self.optimizer_step()
+            nv.status_check()
+            self._warm.add(key)
+            return ld
+        hit = self._graphs.get(key)
+        if hit is None:
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()
+            st_in = dict(x=torch.empty_like(images), z=torch.empty_like(noise["z"]), y=torch.empty_like(noise["y"]))
+            st_in["x"].copy_(images); st_in["z"].copy_(noise["z"]); st_in["y"].copy_(noise["y"])
+            torch.cuda.current_stream().synchronize()
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            l0 = nv.LAUNCH_COUNT[0]
+            with torch.cuda.graph(ga, pool=self._pool):
+                ld = self._core_a(st_in["x"], q, {"z": st_in["z"], "y": st_in["y"]})
+            la = nv.LAUNCH_COUNT[0] - l0
+            count = self.step_count
+            with torch.cuda.graph(gb, pool=self._pool):
+                self.optimizer_step()
+            self.step_count = count        # the capture itself executes nothing
+            hit = self._graphs[key] = (ga, gb, st_in, ld, la, nv.LAUNCH_COUNT[0] - l0 - la)
+        ga, gb, st_in, ld, la, lb = hit
+        st_in["x"].copy_(images, non_blocking=True)
+        st_in["z"].copy_(noise["z"], non_blocking=True)
+        st_in["y"].copy_(noise["y"], non_blocking=True)
+        ga.replay()
         self.all_reduce_grads()
-        self.optimizer_step()
+        gb.replay()
+        self.step_count += 1
+        nv.LAUNCH_COUNT[0] += la + lb
+        nv.status_check()
         return ld
 
     def sync_to_model(self):
@@ -595,6 +742,9 @@ class CodecTrainer:
 class _SingleDgrad:
     def __init__(self, pc):
         self.pc = pc
+
+    def packed(self):
+        return [self.pc]
 
     def repack(self):
         self.pc.repack()

@@ -332,6 +332,15 @@ int crdr_conv_wgrad(const crdr_wgrad_desc* d, void* stream);
 /* packed[i] = split_fp16(master[map[i]]) (map[i] < 0: zero): re-packs a parameter into a K-major tensor-core matrix
  * (forward, dgrad or phase-packed form) after every optimiser step.  lo may be NULL (single-plane matrices). */
 int crdr_pack_weights(const float* master, const int32_t* map, int64_t count, void* hi, void* lo, void* stream);
+/* The same for a whole table of matrices in one launch; `jobs` is DEVICE memory (njobs entries, <= 65535). */
+typedef struct {
+  const float* master;
+  const int32_t* map;
+  int64_t count;
+  void* hi;
+  void* lo;
+} crdr_pack_job;
+int crdr_pack_weights_multi(const crdr_pack_job* jobs, int32_t njobs, void* stream);
 
 /* Backward of the fused convolution epilogue  out = ([relu](acc + bias) [+ res | res + 0.5 tanh(.)]) * scale + shift:
  *   g1 = g * scale;  dres += g1;  dv = relu ? g1 * (out > 0) : (half-tanh ? g1 * 0.5 * (1 - (2 (f32_out - f32_res))^2) : g1)
@@ -389,6 +398,7 @@ typedef struct {
   float scale_bound, lik_bound, coef;
   crdr_planes gpre;   /* may have hi == NULL */
   crdr_planes dy, dmu, dsigma;
+  const float* coef_scale; /* optional device scalar multiplied into coef (the HiFiC rate weight decided on the device) */
 } crdr_gauss_bwd_desc;
 int crdr_gauss_backward(const crdr_gauss_bwd_desc* d, void* stream);
 
@@ -398,9 +408,10 @@ int crdr_mse_backward(const float* fake, int32_t fake_cs, const float* real, int
                       int32_t w, float coef, void* g, int32_t g_cs, void* stream);
 
 /* torch.optim.Adam step on flat fp32 buffers; the gradient is multiplied by gscale (* gscale_ptr[0] when given: the
- * clip coefficient computed on the device).  step >= 1. */
+ * clip coefficient computed on the device).  step >= 1, or `hyper` = device float[3] {lr, 1 - beta1^step, sqrt(1 - beta2^step)}
+ * overriding lr / step (a CUDA-graph replay reads the schedule from device memory). */
 int crdr_adam_step(float* p, const float* g, float* m, float* v, int64_t count, float lr, float beta1, float beta2, float eps,
-                   int32_t step, const float* gscale_ptr, float gscale, void* stream);
+                   int32_t step, const float* gscale_ptr, float gscale, const float* hyper, void* stream);
 /* out[0] = sum x^2 (fixed order); partial: 1024 floats of scratch. */
 int crdr_sum_squares(const float* x, int64_t count, float* partial, float* out, void* stream);
 

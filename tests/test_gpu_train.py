@@ -325,7 +325,7 @@ def test_mse_backward_adam_and_norm():
         assert abs(math.sqrt(float(nrm)) - float(total)) / float(total) < 1e-5
         clip = min(1.0, 1.0 / (math.sqrt(float(nrm)) + 1e-6))
         nv.check(L.crdr_adam_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), count, 1e-3, 0.9, 0.999, 1e-8, i + 1,
-                                  None, clip, st))
+                                  None, clip, None, st))
     torch.cuda.synchronize()
     assert float((p.cpu() - pt.detach()).abs().max()) < 2e-6
 
