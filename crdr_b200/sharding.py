@@ -1,6 +1,11 @@
 """Image-level sharding across GPUs: images are independent units, so rank r of W simply takes items
 r, r+W, ... of the sorted list; there is no collective on the data path.  Per-image result rows are merged on
-rank 0 -- through torch.distributed when a process group exists, else through per-rank JSON files."""
+rank 0 -- through torch.distributed when a process group exists, else through per-rank JSON files.
+
+Training (third row) is data parallel: identical replicas, rank-local crops, and three small exchanges per
+step -- the quality level drawn by rank 0 (the reference draws one per batch), the quantised-bpp mean behind the HiFiC
+rate switch, and the bucketed mean all-reduce of the flat gradient buffer (NCCL over NVLink on the GPUs; the same code
+runs over gloo in the CPU tests)."""
 import json
 import os
 import time
@@ -65,3 +70,44 @@ def gather_rows(rows, rank, world, scratch_dir=None, timeout_s=600.0):
             out.extend(json.load(f))
         os.remove(path)
     return out
+
+
+def _group_world(group=None):
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return None, 1
+    return dist, dist.get_world_size(group)
+
+
+def allreduce_mean_flat(flat, bucket_bytes=64 << 20, group=None):
+    """In-place mean over the ranks of a flat (1-D, contiguous) gradient buffer, in fixed-size buckets so that the
+    first buckets are on the wire while the later ones are still being enqueued.  Returns the number of buckets
+    (0: single process, nothing done)."""
+    dist, world = _group_world(group)
+    if world == 1:
+        return 0
+    assert flat.dim() == 1 and flat.is_contiguous()
+    per = max(1, bucket_bytes // flat.element_size())
+    handles = [dist.all_reduce(flat[o:o + per], op=dist.ReduceOp.SUM, group=group, async_op=True)
+               for o in range(0, flat.numel(), per)]
+    for h in handles:
+        h.wait()
+    flat.mul_(1.0 / world)
+    return len(handles)
+
+
+def allreduce_mean_scalar(t, group=None):
+    """Mean over the ranks of a small tensor, in place and without a host round trip (the HiFiC rate switch's qbpp)."""
+    dist, world = _group_world(group)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        t.mul_(1.0 / world)
+    return t
+
+
+def broadcast_from_rank0(t, group=None):
+    """Rank 0's tensor on every rank (the per-step quality level / beta the reference draws once per batch)."""
+    dist, world = _group_world(group)
+    if world > 1:
+        dist.broadcast(t, src=0, group=group)
+    return t

@@ -221,6 +221,8 @@ class CodecTrainer:
         # the learning rates and Adam's bias corrections
         f32 = dict(dtype=torch.float32, device=self.device)
         self._rate_w = torch.zeros(1, **f32)
+        self._qbpp = torch.zeros(1, **f32)
+        self._level = 0
         self._lr = torch.tensor([lr, aux_lr], **f32)
         self._step_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._hyper = torch.zeros(2, 4, **f32)           # rows: main / aux; columns: lr, 1 - b1^t, sqrt(1 - b2^t), unused
@@ -295,24 +297,35 @@ class CodecTrainer:
         nv.check(nv.lib().crdr_bits_from_likelihood(lik.data_ptr(), n, lik[0].numel(), out.data_ptr(), nv.stream_handle()))
         return out
 
-    def _losses_device(self, images, out, q):
+    def _losses_device(self, images, out, q, decide=True):
         """rate_distortion_trainer.py:70-76 with HificVariableRateLoss (rate_loss.py:84-175) and MSELoss (0_1 scale), all
         on the device: the rate weight (lambda_A if the quantised bpp exceeds the target else lambda_B) is decided by a
         torch.where and left in self._rate_w for the backward kernels, so a step needs no host round trip."""
         h, w = out["size"]
         bpp = (self._bits(out["y_lik_noisy"]) + self._bits(out["z_lik_noisy"])) / (h * w)
         qbpp = (self._bits(out["y_lik"]) + self._bits(out["z_lik"])) / (h * w)
-        lvl = int(q) if self.uses_rate else 0
-        pick = lambda v: float(v[lvl]) if isinstance(v, (list, tuple)) else float(v)
-        lam_a, lam_b, tgt = pick(self.lambda_a), pick(self.lambda_b), pick(self.target)
-        rate_w = torch.where(qbpp.mean() > tgt, torch.full_like(self._rate_w, lam_a), torch.full_like(self._rate_w, lam_b))
-        self._rate_w.copy_(rate_w)
+        self._qbpp.copy_(qbpp.mean().reshape(1))
+        self._level = int(q) if self.uses_rate else 0
+        if decide:
+            self._decide_rate()
         mse = torch.mean(((images + 1) / 2 - (out["fake_images"] + 1) / 2) ** 2)
-        return dict(rate=(rate_w * bpp.mean()).reshape(()), distortion=self.lambda_mse * mse, bpp=bpp.mean(), qbpp=qbpp.mean(),
-                    rate_weight=rate_w.reshape(()))
+        return dict(bpp_mean=bpp.mean(), distortion=self.lambda_mse * mse, bpp=bpp.mean(), qbpp=qbpp.mean())
+
+    def _decide_rate(self):
+        """HiFiC rate switch on the mean quantised bpp of the GLOBAL batch (all ranks), on the device."""
+        from .sharding import allreduce_mean_scalar
+        allreduce_mean_scalar(self._qbpp, self.pg)
+        pick = lambda v: float(v[self._level]) if isinstance(v, (list, tuple)) else float(v)
+        lam_a, lam_b, tgt = pick(self.lambda_a), pick(self.lambda_b), pick(self.target)
+        self._rate_w.copy_(torch.where(self._qbpp > tgt, torch.full_like(self._rate_w, lam_a), torch.full_like(self._rate_w, lam_b)))
+
+    def _finish_losses(self, ld):
+        ld["rate_weight"] = self._rate_w.reshape(())
+        ld["rate"] = ld["rate_weight"] * ld.pop("bpp_mean")
+        return ld
 
     def losses(self, images, out, q):
-        ld = self._losses_device(images, out, q)
+        ld = self._finish_losses(self._losses_device(images, out, q))
         ld["rate_weight"] = float(ld["rate_weight"].item())
         return ld
 
@@ -625,19 +638,8 @@ class CodecTrainer:
     def all_reduce_grads(self, bucket_bytes=64 << 20):
         """Data parallelism: average the flat gradient buffer over the ranks in fixed-size buckets (NCCL over NVLink;
         SURVEY 8e: 127.7 M parameters = 510.9 MB per step).  A no-op for a single process."""
-        import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.pg) == 1:
-            return 0
-        world = dist.get_world_size(self.pg)
-        g = self.ctx.flat_g
-        per = bucket_bytes // 4
-        handles = []
-        for o in range(0, g.numel(), per):
-            handles.append(dist.all_reduce(g[o:o + per], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
-        for hnd in handles:
-            hnd.wait()
-        g.mul_(1.0 / world)
-        return len(handles)
+        from .sharding import allreduce_mean_flat
+        return allreduce_mean_flat(self.ctx.flat_g, bucket_bytes, self.pg)
 
     def set_lr(self, lr=None, aux_lr=None):
         """Scheduler hook (MultiStepLR of crdr_stage_2.yaml): the rates live on the device."""
@@ -669,40 +671,42 @@ class CodecTrainer:
                                       cnt, self.aux_lr, b1, b2, self.eps, 0, None, 1.0, self._hyper[1].data_ptr(), st))
         ctx.repack()
 
-    def _core_a(self, images, q, noise):
-        """Forward + losses + backward + aux gradient: capture-safe (no host synchronisation)."""
-        out = self.forward(images, q, noise)
-        ld = self._losses_device(images, out, q)
-        self.backward(images, out)
-        ld["aux"] = self.aux_step()
-        return ld
+    def _core_forward(self, images, q, noise):
+        """Training-mode forward + loss values: capture-safe (no host synchronisation, no collective)."""
+        self._out = self.forward(images, q, noise)
+        return self._losses_device(images, self._out, q, decide=False)
 
-    def _distributed(self):
-        import torch.distributed as dist
-        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.pg) > 1
+    def _core_backward(self, images):
+        self.backward(images, self._out)
+        return self.aux_step()
 
     def train_step(self, images, q=None, noise=None, generator=None):
         """One optimisation step on a batch of [-1, 1] crops (device fp32 NCHW).  Returns the loss dict (device scalars;
         overwritten by the next step of the same shape and quality level when CUDA graphs are on).
 
         The step is ~1 900 small launches whose host enqueue (47 ms) costs several times their device time, so from the
-        second call of a (shape, quality level) on, the step replays two captured CUDA graphs: A = forward + losses +
-        backward, B = clip + Adam + re-packing, with the NCCL gradient all-reduce between them on the same stream."""
+        second call of a (shape, quality level) on, the step replays three captured CUDA graphs -- F = forward + loss
+        values, B = backward, O = clip + Adam + re-packing -- with the two data-parallel exchanges (the qbpp mean of the
+        rate switch, the gradient all-reduce) between them on the same stream."""
+        from .sharding import broadcast_from_rank0
         n, _, h, w = images.shape
         if q is None:
-            q = float(torch.randint(self.model.rate_level, (1,)).item()) if self.uses_rate else 0.0
+            qt = torch.randint(self.model.rate_level, (1,)).to(self.device, torch.float32) if self.uses_rate else torch.zeros(1, device=self.device)
+            q = float(broadcast_from_rank0(qt, self.pg).item())      # one level per (global) batch, like the reference
         if noise is None:
             mk = lambda c, a, b: torch.rand((n, c, a, b), dtype=torch.float32, device=self.device, generator=generator) - 0.5
             noise = {"z": mk(self.zc, h // 64, w // 64), "y": mk(self.charm.yc, h // 16, w // 16)}
         key = (n, h, w, float(q))
         if not self.use_graphs or key not in self._warm:
             # eager: also the warm-up that builds the adjoint matrices, tensor maps and kernel attributes before a capture
-            ld = self._core_a(images, q, noise)
+            ld = self._core_forward(images, q, noise)
+            self._decide_rate()
+            ld["aux"] = self._core_backward(images)
             self.all_reduce_grads()
             self.optimizer_step()
             nv.status_check()
             self._warm.add(key)
-            return ld
+            return self._finish_losses(ld)
         hit = self._graphs.get(key)
         if hit is None:
             if self._pool is None:
@@ -710,27 +714,31 @@ class CodecTrainer:
             st_in = dict(x=torch.empty_like(images), z=torch.empty_like(noise["z"]), y=torch.empty_like(noise["y"]))
             st_in["x"].copy_(images); st_in["z"].copy_(noise["z"]); st_in["y"].copy_(noise["y"])
             torch.cuda.current_stream().synchronize()
-            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            l0 = nv.LAUNCH_COUNT[0]
-            with torch.cuda.graph(ga, pool=self._pool):
-                ld = self._core_a(st_in["x"], q, {"z": st_in["z"], "y": st_in["y"]})
-            la = nv.LAUNCH_COUNT[0] - l0
-            count = self.step_count
+            gf, gb, go = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            counts, l0 = [], nv.LAUNCH_COUNT[0]
+            with torch.cuda.graph(gf, pool=self._pool):
+                ld = self._core_forward(st_in["x"], q, {"z": st_in["z"], "y": st_in["y"]})
             with torch.cuda.graph(gb, pool=self._pool):
+                ld["aux"] = self._core_backward(st_in["x"])
+            count = self.step_count
+            with torch.cuda.graph(go, pool=self._pool):
                 self.optimizer_step()
             self.step_count = count        # the capture itself executes nothing
-            hit = self._graphs[key] = (ga, gb, st_in, ld, la, nv.LAUNCH_COUNT[0] - l0 - la)
-        ga, gb, st_in, ld, la, lb = hit
+            hit = self._graphs[key] = (gf, gb, go, st_in, ld, nv.LAUNCH_COUNT[0] - l0, int(q) if self.uses_rate else 0)
+        gf, gb, go, st_in, ld, launches, level = hit
         st_in["x"].copy_(images, non_blocking=True)
         st_in["z"].copy_(noise["z"], non_blocking=True)
         st_in["y"].copy_(noise["y"], non_blocking=True)
-        ga.replay()
-        self.all_reduce_grads()
+        gf.replay()
+        self._level = level
+        self._decide_rate()
         gb.replay()
+        self.all_reduce_grads()
+        go.replay()
         self.step_count += 1
-        nv.LAUNCH_COUNT[0] += la + lb
+        nv.LAUNCH_COUNT[0] += launches
         nv.status_check()
-        return ld
+        return self._finish_losses(dict(ld))
 
     def sync_to_model(self):
         """Copy the trained parameters back into the nn.Module (checkpointing: state_dict layout of the reference)."""

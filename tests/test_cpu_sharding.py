@@ -39,6 +39,42 @@ def test_shard_and_gather_world2(tmp_path):
     assert (tmp_path / "ok").exists()
 
 
+def _train_worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from crdr_b200 import sharding
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # flat gradient buffer: several buckets, the last one partial
+    n = 100_003
+    g = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    buckets = sharding.allreduce_mean_flat(g, bucket_bytes=64 * 1024)
+    want = torch.arange(n, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
+    assert buckets == -(-n * 4 // (64 * 1024)) and torch.allclose(g, want, rtol=1e-6)
+    q = torch.tensor([3.0 if rank == 0 else -1.0])
+    assert sharding.broadcast_from_rank0(q).item() == 3.0
+    qbpp = torch.tensor([0.1 * (rank + 1)])
+    assert abs(sharding.allreduce_mean_scalar(qbpp).item() - 0.1 * (world + 1) / 2) < 1e-7
+    if rank == 0:
+        open(os.path.join(tmp, "ok_train"), "w").write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_training_exchanges_world2(tmp_path):
+    """The data-parallel exchanges of the training step over gloo: bucketed gradient mean, the rank-0
+    quality level, the qbpp mean of the rate switch."""
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_train_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok_train").exists()
+
+
+def test_training_exchanges_single_process_are_noops():
+    from crdr_b200 import sharding
+    g = torch.ones(10)
+    assert sharding.allreduce_mean_flat(g) == 0 and torch.equal(g, torch.ones(10))
+    assert sharding.broadcast_from_rank0(torch.tensor([2.0])).item() == 2.0
+
+
 def test_shard_partition_properties():
     from crdr_b200 import sharding
     items = list(range(23))
