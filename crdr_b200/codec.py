@@ -648,8 +648,11 @@ class SynthesisEngine:
         """{block: [(add1, add2, add3)] * 3} at fixed device addresses, holding the vectors of `beta`."""
         if not self.has_cond:
             return {b: [(None, None, None)] * 3 for b in self.blocks}
-        beta = float(beta)
-        v = self.cond_vecs.load(beta, lambda: self._cond_cpu(beta))
+        if self.cfg.train is not None:
+            v = self.cfg.train.live_cond(self, beta)
+        else:
+            beta = float(beta)
+            v = self.cond_vecs.load(beta, lambda: self._cond_cpu(beta))
         return {b_: [tuple(v[(bi * 3 + i) * 3 + k] for k in range(3)) for i in range(3)]
                 for bi, b_ in enumerate(("block1", "block2", "block3"))}
 

@@ -156,15 +156,20 @@ __global__ void __launch_bounds__(256) epi_bwd_kernel(const crdr_epi_bwd_desc d,
     if (live) {
       const F8 sc = load_vec8(d.scale, c0, 1.0f), sh = load_vec8(d.shift, c0, 0.0f);
       const bool affine = d.scale != nullptr || d.shift != nullptr;
+      // ReLU followed by a per-channel bias (beta conditioning): the unit was clipped iff the stored value IS the bias
+      F8 zero_level = load_vec8(d.add_vec, c0, 0.0f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) zero_level.v[e] = __half2float(__float2half_rn(zero_level.v[e]));
       for (int64_t r = r0 + threadIdx.y; r < r1; r += kBwRowsPerBlockY) {
         const F8 g = load_h8(reinterpret_cast<const __half*>(d.g.hi) + r * d.g.cs + d.g.coff + c0);
         F8 g1 = g, dv;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[1][e] += g.v[e];
         if (affine) {
           const F8 o = load_planes8(d.out, r, c0);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const float pre = (o.v[e] - sh.v[e]) / sc.v[e];
-            acc[1][e] += g.v[e];
             acc[2][e] = fmaf(g.v[e], pre, acc[2][e]);
             g1.v[e] = g.v[e] * sc.v[e];
           }
@@ -172,8 +177,13 @@ __global__ void __launch_bounds__(256) epi_bwd_kernel(const crdr_epi_bwd_desc d,
         dv = g1;
         if (d.relu) {
           const F8 o = load_h8(reinterpret_cast<const __half*>(d.out.hi) + r * d.out.cs + d.out.coff + c0);
+          if (d.add_vec) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) dv.v[e] = o.v[e] > 0.f ? g1.v[e] : 0.f;
+            for (int e = 0; e < 8; ++e) dv.v[e] = o.v[e] != zero_level.v[e] ? g1.v[e] : 0.f;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dv.v[e] = o.v[e] > 0.f ? g1.v[e] : 0.f;
+          }
         } else if (d.f32_out) {
           // half-tanh (LRP): out = res + 0.5 tanh(v)  =>  dv = g * 0.5 * (1 - tanh^2),  tanh = 2 (out - res)
           const float* po = d.f32_out + r * d.f32_cs + d.f32_coff + c0;

@@ -116,6 +116,7 @@ class EpiBwdDesc(C.Structure):
         ("f32_out", C.c_void_p), ("f32_res", C.c_void_p), ("f32_cs", C.c_int32), ("f32_coff", C.c_int32),
         ("dv", Planes), ("dres", Planes),
         ("partial", C.c_void_p), ("blocks", C.c_int32),
+        ("add_vec", C.c_void_p),
     ]
 
 

@@ -16,8 +16,10 @@ weights are fp32 in one flat buffer each (one fused Adam launch, one NCCL all-re
 The factorised prior over z (18 k elements per Kodak image, 58 parameters per channel) is differentiated with torch
 autograd on the device: it is 0.003 % of the step's arithmetic and not worth a kernel.
 
-Scope: the models without beta conditioning (stage 1 / stage 2: crdr_stage_1.yaml, crdr_stage_2.yaml = BASELINE config
-5) with rate + MSE losses.  LPIPS needs pretrained AlexNet weights that are not available offline and is left out.
+Scope: every ChARM model of the reference (stage 1, stage 2 = BASELINE config 5, and the beta-conditioned crdr.yaml model)
+with the rate + MSE losses.  Not lowered: LPIPS (pretrained AlexNet weights are not available offline) and the stage-3 GAN
+terms (discriminators), i.e. the beta * (perceptual + adversarial) part of
+multirate_hr_rgan_beta_cond_rate_distortion_trainer.py:62-66.
 """
 import ctypes as C
 import math
@@ -68,6 +70,7 @@ class TrainContext:
         self.gain_state = {}    # "encoder" / "decoder" -> (engine, l, r, alpha, lerped weights)
         self.gain_grad = {}
         self._gain_by_ptr = {}
+        self.cond_grad, self.cond_state = None, None
 
     def live_sd(self, prefix):
         p = prefix + "."
@@ -141,6 +144,52 @@ class TrainContext:
         self.gain_state[which] = (engine, l, r, alpha, lerped)
         return views
 
+    def live_cond(self, engine, beta):
+        """The 27 conditioning bias vectors (fourier_cond.py:21-37 embedding -> MLP -> proj_1..3 of every BetaCondBaseBlock,
+        elic_interpca_beta_cond_autoencoder.py:52-65,142-152) from the live parameters, under autograd: the forward copies
+        their values behind the fixed addresses the launches read, the backward feeds the per-channel gradient sums the
+        epilogue-backward kernels produce into torch.autograd.grad (a handful of GEMVs).  beta: device scalar tensor."""
+        sd = self.live["decoder"]
+        names = [k for k in sd if k.startswith("mlp.") or ".proj_" in k]
+        leaves = {k: sd[k].detach().requires_grad_(True) for k in names}
+        with torch.enable_grad():
+            nb = (beta.reshape(1) / engine.max_beta - 0.5) * 2
+            if getattr(engine, "_freq_dev", None) is None:
+                engine._freq_dev = engine.freq.to(self.device)     # first (eager) step: no host copies inside a capture
+            freq = engine._freq_dev
+            emb = torch.cat([torch.sin(nb * freq), torch.cos(nb * freq)], dim=0)
+            if engine.include_x:
+                emb = torch.cat([nb, emb], dim=0)
+            c = F.linear(torch.relu(F.linear(emb.unsqueeze(0), leaves["mlp.0.weight"], leaves["mlp.0.bias"])),
+                         leaves["mlp.2.weight"], leaves["mlp.2.bias"])
+            vecs = [F.linear(c, leaves[f"{b}.block{i}.proj_{k}.weight"].flatten(1), leaves[f"{b}.block{i}.proj_{k}.bias"]).reshape(-1)
+                    for b in ("block1", "block2", "block3") for i in range(3) for k in (1, 2, 3)]
+            flat_vec = torch.cat(vecs)
+        flat = engine.cond_vecs.flat
+        flat.copy_(flat_vec.detach())
+        engine.cond_vecs._live = None
+        views = engine.cond_vecs.views
+        if self.cond_grad is None:
+            self.cond_grad = torch.zeros_like(flat)
+            o = 0
+            for i, n in enumerate(engine.cond_vecs.sizes):
+                self._gain_by_ptr[views[i].data_ptr()] = ("cond", o, n)
+                o += n
+            self.gain_grad["cond"] = self.cond_grad
+        self.cond_state = (names, leaves, flat_vec)
+        return views
+
+    def finish_cond_grads(self, inv_scale):
+        if self.cond_state is None:
+            return
+        names, leaves, flat_vec = self.cond_state
+        grads = torch.autograd.grad(flat_vec, [leaves[k] for k in names], grad_outputs=self.cond_grad * inv_scale, allow_unused=True)
+        for k, g in zip(names, grads):
+            if g is not None:
+                self.grads["decoder." + k].add_(g)
+        self.cond_grad.zero_()
+        self.cond_state = None
+
     def gain_grad_slot(self, vec):
         which, o, n = self._gain_by_ptr[vec.data_ptr()]
         return self.gain_grad[which][o:o + n]
@@ -186,8 +235,6 @@ class CodecTrainer:
     def __init__(self, model, device="cuda:0", lr=1e-4, betas=(0.9, 0.999), eps=1e-8, clip_max_norm=None,
                  lambda_mse=150.0, rate_lambda_a=(3.6, 1.8, 0.8, 0.4, 0.1), rate_lambda_b=2.0 ** -6,
                  target_rate=(0.08, 0.16, 0.36, 0.72, 1.2), aux_lr=1e-3, loss_scale=None, process_group=None):
-        if getattr(model, "uses_beta", False):
-            raise NotImplementedError("the beta-conditioned (stage 3) model's backward is not lowered: train stage 1 / 2 models")
         self.model, self.device = model, torch.device(device)
         self.ctx = ctx = TrainContext(model, device)
         X3, X1 = nv.PREC_F16X3, nv.PREC_F16X1
@@ -197,8 +244,8 @@ class CodecTrainer:
             self.hs = model.hyperdecoder.lower(device, sd=ctx.live_sd("hyperdecoder"), precision=X3, train=ctx)
             self.charm = model.context_model.lower(device, sd=ctx.live_sd("context_model"), precision=X3, train=ctx)
             self.gs = model.decoder.lower(device, sd=ctx.live_sd("decoder"), precision=X1, train=ctx)
-        if self.gs.has_cond:
-            raise NotImplementedError("beta conditioning is not part of the lowered training step")
+        self.uses_beta = bool(self.gs.has_cond)
+        self._beta = torch.zeros(1, dtype=torch.float32, device=self.device)   # device-resident (graph replays read it)
         self.eb_sd = ctx.live_sd("entropy_model_z")
         from .codec import GaussianParams
         from .entropy import get_scale_table
@@ -251,10 +298,13 @@ class CodecTrainer:
                 cols.append(torch.tanh(sd[f"_factor{i}"]).reshape(c, -1))
         return torch.cat(cols, dim=1).contiguous(), sd["quantiles"][:, 0, 1].contiguous()
 
-    def forward(self, images, q, noise):
-        """images: [n, 3, h, w] fp32 device tensor (h, w multiples of 64); noise = {"y", "z"} uniform in [-1/2, 1/2).
+    def forward(self, images, q, noise, beta=None):
+        """images: [n, 3, h, w] fp32 device tensor (h, w multiples of 64); noise = {"y", "z"} uniform in [-1/2, 1/2);
+        beta: realism weight of the beta-conditioned decoder (float: stored in the device scalar; None: keep it).
         Returns the dict of device tensors of the training-mode forward and leaves the tape for backward()."""
         ctx, L, st = self.ctx, nv.lib(), nv.stream_handle()
+        if beta is not None:
+            self._beta.fill_(float(beta))
         ctx.tape = []
         self._grads, self._keep = {}, []
         n, _, h, w = images.shape
@@ -284,7 +334,7 @@ class CodecTrainer:
         self.hs.run(zhat, T, self.charm.off_mean, self.charm.off_scale)
         self._y_act, self._T, self._zhat = y_act, T, zhat
         yhat32, y_sym, y_idx, y_lik, y_lik_noisy = self.charm.encode(T, y32, self.gp, noise=noise["y"])
-        fake_packed = self.gs.run(yhat32, q, 0.0)
+        fake_packed = self.gs.run(yhat32, q, self._beta)
         fake = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
         nv.check(L.crdr_phases_to_image_ex(fake_packed.data_ptr(), fake_packed.shape[-1], n, h // 2, w // 2, h, w, fake.data_ptr(), 0, st))
         return dict(fake_images=fake, fake_packed=fake_packed, y32=y32, z32=z32, yhat32=yhat32, z_hat=z_hat, y_lik=y_lik, y_sym=y_sym,
@@ -418,6 +468,7 @@ class CodecTrainer:
                 self._eb_backward(*rec[1:])
         self._join_sides()
         ctx.finish_gain_grads(inv)
+        ctx.finish_cond_grads(inv)
 
     def _sums_to(self, partial, blocks, nsums, which, c, target, accumulate=True, scale=None):
         nv.check(nv.lib().crdr_colsum_finish(partial.data_ptr(), blocks, nsums, which, c, target.data_ptr(),
@@ -437,7 +488,9 @@ class CodecTrainer:
         cout = op.cout_pad if conv.wmap is not None else op.cout
         relu, mode = bool(kw.get("relu")), kw.get("mode", nv.EPI_NONE)
         scale, shift = kw.get("scale"), kw.get("shift")
+        add_vec = kw.get("add_vec")
         affine = scale is not None or shift is not None
+        assert not (add_vec is not None and relu and affine), "ReLU + conditioning bias + gain in one epilogue is not used by the path"
         tanh = mode == nv.EPI_HALF_TANH
         need_dv = relu or affine or tanh
         ho, wo = G.h, G.w
@@ -450,6 +503,8 @@ class CodecTrainer:
         if relu or affine:
             d.out = out.planes(kw.get("out_coff", 0))
         d.scale, d.shift = nv.ptr(scale), nv.ptr(shift)
+        if add_vec is not None and relu:
+            d.add_vec = add_vec.data_ptr()
         if tanh:
             res32 = kw["res"]
             d.f32_out, d.f32_res = out_f32.data_ptr(), res32.data_ptr()
@@ -476,6 +531,8 @@ class CodecTrainer:
             self._keep.append(dv)       # read by the side stream after this function returns
         with self._side() as ws:
             self._param_grads(conv, op, x, kw, dv, dv_coff, cout, partial, blocks, scale, shift, affine, ws)
+            if add_vec is not None:     # conditioning bias: after the ReLU (sum of g) or, without one, like the bias (sum of dv)
+                self._sums_to(partial, blocks, 3, 1 if relu else 0, op.cout, ctx.gain_grad_slot(add_vec), scale=1.0)
         # dgrad
         if no_input_grad:
             return
@@ -673,14 +730,14 @@ class CodecTrainer:
 
     def _core_forward(self, images, q, noise):
         """Training-mode forward + loss values: capture-safe (no host synchronisation, no collective)."""
-        self._out = self.forward(images, q, noise)
+        self._out = self.forward(images, q, noise)      # beta: the device scalar set by train_step
         return self._losses_device(images, self._out, q, decide=False)
 
     def _core_backward(self, images):
         self.backward(images, self._out)
         return self.aux_step()
 
-    def train_step(self, images, q=None, noise=None, generator=None):
+    def train_step(self, images, q=None, noise=None, generator=None, beta=None):
         """One optimisation step on a batch of [-1, 1] crops (device fp32 NCHW).  Returns the loss dict (device scalars;
         overwritten by the next step of the same shape and quality level when CUDA graphs are on).
 
@@ -693,6 +750,12 @@ class CodecTrainer:
         if q is None:
             qt = torch.randint(self.model.rate_level, (1,)).to(self.device, torch.float32) if self.uses_rate else torch.zeros(1, device=self.device)
             q = float(broadcast_from_rank0(qt, self.pg).item())      # one level per (global) batch, like the reference
+        if self.uses_beta:
+            if beta is None:    # beta_cond_interpca_hyperprior_model.py:43-45: max_beta * randint(0, 101) / 100, one per batch
+                bt = torch.randint(0, 101, (1,)).to(self.device, torch.float32) * (self.gs.max_beta / 100.0)
+                self._beta.copy_(broadcast_from_rank0(bt, self.pg))
+            else:
+                self._beta.fill_(float(beta))
         if noise is None:
             mk = lambda c, a, b: torch.rand((n, c, a, b), dtype=torch.float32, device=self.device, generator=generator) - 0.5
             noise = {"z": mk(self.zc, h // 64, w // 64), "y": mk(self.charm.yc, h // 16, w // 16)}

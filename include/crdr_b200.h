@@ -345,7 +345,7 @@ int crdr_pack_weights_multi(const crdr_pack_job* jobs, int32_t njobs, void* stre
 /* Backward of the fused convolution epilogue  out = ([relu](acc + bias) [+ res | res + 0.5 tanh(.)]) * scale + shift:
  *   g1 = g * scale;  dres += g1;  dv = relu ? g1 * (out > 0) : (half-tanh ? g1 * 0.5 * (1 - (2 (f32_out - f32_res))^2) : g1)
  * and per-channel sums over the pixels, written per row block to partial[blocks][3][c]:
- *   0: sum dv (bias.grad)   1: sum g (InterpChAtt bias path)   2: sum g * (out - shift) / scale (InterpChAtt weight path) */
+ *   0: sum dv (bias.grad)   1: sum g (InterpChAtt bias path; always computed)   2: sum g * (out - shift) / scale (InterpChAtt weight path) */
 typedef struct {
   crdr_planes g;
   crdr_planes out;
@@ -361,6 +361,8 @@ typedef struct {
   crdr_planes dres;     /* may have hi == NULL */
   float* partial;       /* may be NULL */
   int32_t blocks;       /* row blocks = grid size (1..4096) */
+  const float* add_vec; /* forward added this per-channel vector AFTER the ReLU (beta conditioning, single-plane tensors): the
+                           mask is out != fp16(add_vec) instead of out > 0; its gradient is sum 1 (no gain) or sum 0 (no ReLU) */
 } crdr_epi_bwd_desc;
 int crdr_epilogue_backward(const crdr_epi_bwd_desc* d, void* stream);
 /* out[c] (+)= scale * sum_b partial[b][which][c], blocks in ascending order */

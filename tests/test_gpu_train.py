@@ -334,7 +334,7 @@ def test_mse_backward_adam_and_norm():
 # The whole training step against autograd through the oracle (= the reference's forward, pinned in
 # tests/test_oracle_vs_reference.py): same weights, same crops, same noise, same losses.
 # ----------------------------------------------------------------------------------------------------------------------
-def _oracle_grads(oracle, sd, x, q, noise, rate_w, lam_mse, forced=None):
+def _oracle_grads(oracle, sd, x, q, noise, rate_w, lam_mse, forced=None, beta=None):
     """Autograd gradients of rate_w * mean(bpp) + lam_mse * MSE_01 through oracle.forward_train (CPU fp32)."""
     sdr = {k: (v.detach().clone().float().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
     eb, gc = oracle.entropy_models(sdr)
@@ -342,7 +342,7 @@ def _oracle_grads(oracle, sd, x, q, noise, rate_w, lam_mse, forced=None):
         p.requires_grad_(True)
     fwd = oracle.forward_train.__wrapped__          # the undecorated function (forward_train itself runs under no_grad)
     with torch.enable_grad():
-        out = fwd(sdr, x, q, None, noise, eb, gc, forced_y_symbols=forced)
+        out = fwd(sdr, x, q, beta, noise, eb, gc, forced_y_symbols=forced)
         n, _, h, w = x.shape
         bits = lambda lik: (-torch.log2(lik)).sum((1, 2, 3))
         bpp = (bits(out["likelihoods"]["y"]) + bits(out["likelihoods"]["z"])) / (h * w)
@@ -356,11 +356,12 @@ def _oracle_grads(oracle, sd, x, q, noise, rate_w, lam_mse, forced=None):
     return out, grads, float(loss)
 
 
-@pytest.mark.parametrize("q", [2.0, 0.5])
-def test_training_step_gradients_match_oracle_autograd(oracle, q):
+@pytest.mark.parametrize("config,q,beta", [("crdr_stage_2.yaml", 2.0, None), ("crdr_stage_2.yaml", 0.5, None), ("crdr.yaml", 1.5, 2.56)],
+                         ids=["stage2_q2", "stage2_q0.5", "beta_cond_q1.5"])
+def test_training_step_gradients_match_oracle_autograd(oracle, config, q, beta):
     import fixtures
     from crdr_b200.train import CodecTrainer
-    model, sd = fixtures.build_model(seed=5, calibrated=True, config="crdr_stage_2.yaml")
+    model, sd = fixtures.build_model(seed=5, calibrated=True, config=config)
     tr = CodecTrainer(model, device=DEV)
     n, h, w = 2, 128, 128
     x = fixtures.image(n, h, w, seed=21)
@@ -369,15 +370,15 @@ def test_training_step_gradients_match_oracle_autograd(oracle, q):
     rate_w = 0.8
     xd = x.to(DEV).contiguous()
     nd = {k: v.to(DEV).contiguous() for k, v in noise.items()}
-    out = tr.forward(xd, q, nd)
+    out = tr.forward(xd, q, nd, beta=beta)
     ld = tr.losses(xd, out, q)
     # The oracle replays the CUDA path's rounding decisions (the integer symbols): one tie broken the other way changes the
     # support of every later slice, which would make this a comparison of two different forwards rather than of the
     # backward arithmetic.  Without forcing, the two forwards differ in <= 1e-3 of the symbols (checked below).
-    free_out = oracle.forward_train(sd, x, q, None, noise, *oracle.entropy_models(sd))
+    free_out = oracle.forward_train(sd, x, q, beta, noise, *oracle.entropy_models(sd))
     flips = (free_out["quantized_code"]["y"] - out["yhat32"].permute(0, 3, 1, 2).cpu()).abs() > 0.5
     assert float(flips.float().mean()) < 1e-3
-    ref_out, ref, ref_loss = _oracle_grads(oracle, sd, x, q, noise, rate_w, 150.0, forced=out["y_sym"].cpu())
+    ref_out, ref, ref_loss = _oracle_grads(oracle, sd, x, q, noise, rate_w, 150.0, forced=out["y_sym"].cpu(), beta=beta)
     # forward values first (training-mode parity is tested in test_gpu_codec.py; here: the taped engines agree too)
     assert _rel(out["fake_images"].cpu(), ref_out["fake_images"].detach()) < 2e-3
     assert abs(float(ld["rate"] + ld["distortion"]) - ref_loss) / ref_loss < 1e-3 or ld["rate_weight"] != rate_w
@@ -405,19 +406,22 @@ def test_training_step_gradients_match_oracle_autograd(oracle, q):
     assert float(errs.max()) < 5e-2, report
 
 
-def test_training_steps_reduce_the_loss_and_keep_engines_in_sync():
-    """A few optimiser steps on a fixed batch: the loss goes down, the re-packed matrices follow the parameters (the
-    taped forward of the updated trainer equals a fresh model built from its synced parameters)."""
+@pytest.mark.parametrize("config", ["crdr_stage_2.yaml", "crdr.yaml"])
+def test_training_steps_reduce_the_loss_and_keep_engines_in_sync(config):
+    """A few optimiser steps on a fixed batch (eager warm-up, then CUDA-graph replays): the loss goes down, the re-packed
+    matrices follow the parameters (the taped forward of the updated trainer equals a fresh model built from its synced
+    parameters)."""
     import fixtures
     from crdr_b200.train import CodecTrainer
-    model, _ = fixtures.build_model(seed=6, calibrated=False, config="crdr_stage_2.yaml")
+    model, _ = fixtures.build_model(seed=6, calibrated=False, config=config)
     tr = CodecTrainer(model, device=DEV, lr=1e-4, clip_max_norm=1.0)
+    beta = 2.56 if config == "crdr.yaml" else None
     n, h, w = 2, 128, 128
     x = fixtures.image(n, h, w, seed=22).to(DEV).contiguous()
     gen = torch.Generator(device=DEV).manual_seed(5)
     first = last = None
     for it in range(6):
-        ld = tr.train_step(x, q=2.0, generator=gen)
+        ld = tr.train_step(x, q=2.0, generator=gen, beta=beta)
         total = float(ld["rate"] + ld["distortion"])
         first = total if first is None else first
         last = total
@@ -425,7 +429,7 @@ def test_training_steps_reduce_the_loss_and_keep_engines_in_sync():
     tr.sync_to_model()
     model.codec_setup()
     xc = x.cpu()
-    a = model.run_model(xc, rate_ind=2.0, is_train=False)
+    a = model.run_model(xc, rate_ind=2.0, beta=beta, is_train=False) if beta is not None else model.run_model(xc, rate_ind=2.0, is_train=False)
     g2 = torch.Generator(device=DEV).manual_seed(9)
     mk = lambda c, aa, bb: torch.rand((n, c, aa, bb), dtype=torch.float32, device=DEV, generator=g2) - 0.5
     out = tr.forward(x, 2.0, {"z": mk(192, h // 64, w // 64), "y": mk(320, h // 16, w // 16)})
