@@ -50,7 +50,7 @@ __global__ void pack_weights_multi_kernel(const crdr_pack_job* __restrict__ jobs
 
 int pack_weights_multi_launch(const crdr_pack_job* jobs, int njobs, cudaStream_t st) {
   if (!jobs || njobs <= 0 || njobs > 65535) { set_error("pack_weights_multi: bad job table"); return CRDR_ERR_BAD_SHAPE; }
-  pack_weights_multi_kernel<<<dim3(32, (unsigned)njobs), 256, 0, st>>>(jobs);
+  pack_weights_multi_kernel<<<dim3(96, (unsigned)njobs), 256, 0, st>>>(jobs);
   return check_launch("pack_weights_multi_kernel");
 }
 

@@ -256,7 +256,8 @@ class CodecTrainer:
         self.lr, self.betas, self.eps, self.clip = lr, betas, eps, clip_max_norm
         self.aux_lr = aux_lr
         self.lambda_mse = float(lambda_mse)
-        self.lambda_a, self.lambda_b, self.target = list(rate_lambda_a), rate_lambda_b, list(target_rate)
+        as_cfg = lambda v: list(v) if isinstance(v, (list, tuple)) else float(v)     # per quality level, or one value
+        self.lambda_a, self.lambda_b, self.target = as_cfg(rate_lambda_a), as_cfg(rate_lambda_b), as_cfg(target_rate)
         self.loss_scale = None if loss_scale is None else float(loss_scale)   # None: from the batch's pixel count
         self._auto_scale = loss_scale is None
         self.m = torch.zeros_like(ctx.flat_p)
@@ -495,7 +496,7 @@ class CodecTrainer:
         need_dv = relu or affine or tanh
         ho, wo = G.h, G.w
         m = G.n * ho * wo
-        blocks = max(1, min(512, m // 64))
+        blocks = max(1, min(2048, m // 32))
         partial = self._partial(blocks, 3, cout)
         d = nv.EpiBwdDesc()
         d.g = nv.Planes(G.hi.data_ptr(), None, G.c, gcoff)

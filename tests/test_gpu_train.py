@@ -414,18 +414,20 @@ def test_training_steps_reduce_the_loss_and_keep_engines_in_sync(config):
     import fixtures
     from crdr_b200.train import CodecTrainer
     model, _ = fixtures.build_model(seed=6, calibrated=False, config=config)
-    tr = CodecTrainer(model, device=DEV, lr=1e-4, clip_max_norm=1.0)
+    # constant rate weight and fixed noise: with the HiFiC switch (lambda 0.8 <-> 2^-6 whenever the quantised bpp crosses the
+    # target) and fresh noise the loss of consecutive steps is not comparable (tools/train_loss_curve.py)
+    tr = CodecTrainer(model, device=DEV, lr=1e-4, clip_max_norm=1.0, rate_lambda_a=2.0 ** -6, rate_lambda_b=2.0 ** -6)
     beta = 2.56 if config == "crdr.yaml" else None
     n, h, w = 2, 128, 128
     x = fixtures.image(n, h, w, seed=22).to(DEV).contiguous()
     gen = torch.Generator(device=DEV).manual_seed(5)
-    first = last = None
-    for it in range(6):
-        ld = tr.train_step(x, q=2.0, generator=gen, beta=beta)
-        total = float(ld["rate"] + ld["distortion"])
-        first = total if first is None else first
-        last = total
-    assert math.isfinite(last) and last < first, (first, last)
+    mk0 = lambda c, aa, bb: torch.rand((n, c, aa, bb), dtype=torch.float32, device=DEV, generator=gen) - 0.5
+    noise = {"z": mk0(192, h // 64, w // 64), "y": mk0(320, h // 16, w // 16)}
+    totals = []
+    for it in range(8):      # step 0 eager (warm-up), step 1 captures the graphs, 2.. replay them
+        ld = tr.train_step(x, q=2.0, noise=noise, beta=beta)
+        totals.append(float(ld["rate"] + ld["distortion"]))
+    assert all(math.isfinite(t) for t in totals) and min(totals[-3:]) < totals[0] and totals[-1] < totals[1], totals
     tr.sync_to_model()
     model.codec_setup()
     xc = x.cpu()
