@@ -48,6 +48,11 @@ struct alignas(64) WgParams {
   uint32_t tmem_cols;
   int8_t dh[CRDR_MAX_TAPS], dw[CRDR_MAX_TAPS];
   uint32_t* status;
+  // splits == 1: the epilogue writes the parameter gradient itself (no workspace round trip, no reduction launch)
+  float* out;
+  int64_t sa, sb, st;
+  int32_t ca, cb, accumulate;
+  float scale;
 };
 
 // MN-major SWIZZLE_128B operand: `lbo` bytes between 64-element atoms along M / N, `sbo` bytes between 8-row K groups
@@ -149,16 +154,40 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     mbar_wait(smem_u32(&acc_full), 0u, P.status);
     tc_fence_after();
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    float* dst = P.ws + (((int64_t)split * P.ntaps + tap) * P.a_pad + (at * 128 + row)) * (int64_t)P.b_pad + (int64_t)bt * 64 * nb;
-    for (int c0 = 0; c0 < 64 * nb; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32_issue(lane_addr + (uint32_t)c0, r);
-      tmem_wait_ld();
-      float4* o = reinterpret_cast<float4*>(dst + c0);
+    if (P.splits == 1) {
+      // direct: out[t*st + a*sa + b*sb] (+)= scale * G   (one writer per element: deterministic)
+      const int a = at * 128 + row;
+      const int b0 = bt * 64 * nb;
+      float* dst = P.out + (int64_t)a * P.sa + (int64_t)tap * P.st;
+      for (int c0 = 0; c0 < 64 * nb; c0 += 32) {
+        if (b0 + c0 >= P.cb) break;           // warp-uniform: the rest of this N tile is padding
+        uint32_t r[32];
+        tmem_ld32_issue(lane_addr + (uint32_t)c0, r);
+        tmem_wait_ld();
+        if (a < P.ca) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                           __uint_as_float(r[4 * j + 3]));
+          for (int j = 0; j < 32; ++j) {
+            const int b = b0 + c0 + j;
+            if (b < P.cb) {
+              float* o = dst + (int64_t)b * P.sb;
+              const float v = __uint_as_float(r[j]) * P.scale;
+              *o = P.accumulate ? *o + v : v;
+            }
+          }
+        }
+      }
+    } else {
+      float* dst = P.ws + (((int64_t)split * P.ntaps + tap) * P.a_pad + (at * 128 + row)) * (int64_t)P.b_pad + (int64_t)bt * 64 * nb;
+      for (int c0 = 0; c0 < 64 * nb; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32_issue(lane_addr + (uint32_t)c0, r);
+        tmem_wait_ld();
+        float4* o = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                             __uint_as_float(r[4 * j + 3]));
+      }
     }
   }
   tc_fence_before();
@@ -235,6 +264,9 @@ static int wgrad_plan(const crdr_wgrad_desc& d, size_t ws_bytes, WgPlan* pl) {
   pl->b_tiles = (nb_total + pl->nb - 1) / pl->nb;
   pl->nb = (nb_total + pl->b_tiles - 1) / pl->b_tiles;
   pl->b_pad = pl->b_tiles * pl->nb * 64;
+  // The K loop is bound by the L2 -> shared-memory traffic of its operand boxes (no reuse across taps yet), which does not
+  // depend on the split count, so what matters is keeping every SM loading: two waves of CTAs.  (One wave of longer CTAs was
+  // tried: 26 -> 70 us per launch on the training step's shapes.)
   const int64_t tiles = (int64_t)d.ntaps * pl->a_tiles * pl->b_tiles;
   int64_t splits = (2 * 148 + tiles - 1) / tiles;
   const int64_t by_k = pl->kb_total / 8 > 0 ? pl->kb_total / 8 : 1;
@@ -281,6 +313,7 @@ int wgrad_launch(const crdr_wgrad_desc* dp, cudaStream_t stream) {
   P.kw_blocks = pl.kw_blocks; P.kh_blocks = pl.kh_blocks;
   P.bw = pl.bw; P.bh = pl.bh; P.bn = pl.bn; P.stride = d.stride;
   P.kb_total = pl.kb_total; P.splits = pl.splits;
+  P.out = d.out; P.sa = d.sa; P.sb = d.sb; P.st = d.st; P.ca = d.ca; P.cb = d.cb; P.accumulate = d.accumulate; P.scale = d.scale;
   for (int t = 0; t < d.ntaps; ++t) { P.dh[t] = d.dh[t]; P.dw[t] = d.dw[t]; }
   const uint32_t stage_bytes = (uint32_t)(2 + pl.nb) * kWgBox;
   int stages = (int)((kWgSmemMax - 2048u) / stage_bytes);
@@ -303,7 +336,7 @@ int wgrad_launch(const crdr_wgrad_desc* dp, cudaStream_t stream) {
   dim3 grid((unsigned)(d.ntaps * pl.a_tiles * pl.b_tiles), (unsigned)pl.splits);
   wgrad_kernel<<<grid, kWgThreads, smem, stream>>>(P);
   rc = check_launch("wgrad_kernel");
-  if (rc) return rc;
+  if (rc || pl.splits == 1) return rc;
   const int64_t total = (int64_t)d.ca * d.cb * d.ntaps;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
