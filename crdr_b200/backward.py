@@ -115,6 +115,14 @@ def dgrad_spec(transposed, stride, padding, kh):
     return (lambda w: w), dict(stride=stride, padding=padding)
 
 
+def _pad_axis(w, axis, pad):
+    if pad == 0:
+        return w
+    shape = list(w.shape)
+    shape[axis] = pad
+    return torch.cat([w, torch.zeros(shape, dtype=w.dtype)], dim=axis)
+
+
 MAX_DGRAD_COUT = 320   # per-CTA epilogue parameter cache of the convolution kernel (kMaxCout)
 
 
@@ -122,9 +130,13 @@ class DgradSet:
     """dL/d(in) of one forward convolution: one PackedConv per (input channel range, <= 320-channel chunk), each
     accumulating in place (residual epilogue) into the matching channel range of the input's gradient tensor."""
 
-    def __init__(self, master, transposed, stride, padding, kh, segs, cin_real=None):
-        """segs: [(channel offset in the input tensor, length)] in the forward's logical input-channel order."""
-        fn, kw = dgrad_spec(transposed, stride, padding, kh)
+    def __init__(self, master, transposed, stride, padding, kh, segs, cin_real=None, pre=None):
+        """segs: [(channel offset in the input tensor, length)] in the forward's logical input-channel order.
+        pre: optional transform parameter -> the forward ConvOp's weight (pure indexing ops), applied before slicing."""
+        fn0, kw = dgrad_spec(transposed, stride, padding, kh)
+        fn = fn0 if pre is None else None
+        if pre is not None:
+            assert not transposed, "transformed weights are plain convolutions on this path"
         self.parts = []
         start = 0
         for off, ln in segs:
@@ -132,10 +144,15 @@ class DgradSet:
             for c0 in range(0, real, MAX_DGRAD_COUT):
                 cnt = min(MAX_DGRAD_COUT, real - c0)
                 lo, hi = start + c0, start + c0 + cnt
+                pad = (-cnt) % 8      # e.g. the 3 image channels of the discriminator's first layer live in 8-channel planes
                 if transposed:   # master [ci, co, kh, kw]
-                    sl = (lambda w, lo=lo, hi=hi: fn(w[lo:hi]))
-                else:            # master [co, ci, kh, kw]
-                    sl = (lambda w, lo=lo, hi=hi: fn(w[:, lo:hi]))
+                    sl = (lambda w, lo=lo, hi=hi, pad=pad: _pad_axis(fn(w[lo:hi]), 0, pad))
+                else:            # master [co, ci, kh, kw]; the adjoint's weight has the input channels on axis 0 (plain
+                    #              convolution, stride 1) or on axis 1 (transposed convolution of a strided forward)
+                    if pre is None:
+                        sl = (lambda w, lo=lo, hi=hi, pad=pad, ax=(0 if stride == 1 else 1): _pad_axis(fn(w[:, lo:hi]), ax, pad))
+                    else:
+                        sl = (lambda w, lo=lo, hi=hi, pad=pad, ax=(0 if stride == 1 else 1): _pad_axis(fn0(pre(w)[:, lo:hi]), ax, pad))
                 self.parts.append((PackedConv(master, sl, two_planes=False, **kw), off + c0, cnt))
             start += ln
 

@@ -694,3 +694,62 @@ class SynthesisEngine:
         img = torch.empty((n, x.h, x.w, 16), dtype=torch.float32, device=yhat32.device)
         self.conv4p(x, out_f32=img, want_planes=False)
         return img
+
+
+class DiscriminatorEngine:
+    """CLIC21GVAEDiscriminator.forward (clic21_gvae_discriminator.py:27-50, norm_type none): 3x3 convolutions with
+    LeakyReLU(0.2) between them on single-plane fp16 tensors.  The image enters as 8-channel NHWC planes
+    (crdr_image_to_planes: 3 channels + zero padding); layers wider than 256 output channels run as two launches over
+    output-channel halves (the kernel's per-CTA parameter cache holds 320); the 1-channel head is padded to 8 channels
+    (channel 0 is the logit map)."""
+    SLOPE = 0.2
+
+    def __init__(self, sd, strides, device, precision=X1, engine=nv.ENGINE_TCGEN05, train=None):
+        cfg = NetCfg(device, precision, engine, train)
+        self.cfg = cfg
+        self.layers = []
+        names = sorted((k[:-len(".weight")] for k in sd if k.endswith(".weight")), key=lambda k: int(k.split(".")[1]))
+        assert len(names) == len(strides)
+        for i, (name, stride) in enumerate(zip(names, strides)):
+            cout, cin = sd[name + ".weight"].shape[:2]
+            last = i == len(names) - 1
+            kw = dict(stride=stride, padding=1, cin_pad=8 if cin < 8 else None)
+            if last:
+                parts = [(Conv(sd, name, cfg, transform=self._pad_head, bias_transform=self._pad_head_bias, **kw), 0, 8)]
+                width = 8
+            elif cout > 256:
+                half = cout // 2
+                parts = [(Conv(sd, name, cfg, transform=(lambda w, a=a: w[a:a + half]), bias_transform=(lambda b, a=a: b[a:a + half]), **kw),
+                          a, half) for a in (0, half)]
+                width = cout
+            else:
+                parts = [(Conv(sd, name, cfg, **kw), 0, cout)]
+                width = cout
+            self.layers.append((parts, width, stride, not last))
+
+    @staticmethod
+    def _pad_head(w):
+        out = torch.zeros((8,) + tuple(w.shape[1:]), dtype=torch.float32)
+        out[:w.shape[0]] = w.detach().float().cpu()
+        return out
+
+    @staticmethod
+    def _pad_head_bias(b):
+        out = torch.zeros(8, dtype=torch.float32, device=b.device)
+        out[:b.numel()] = b.detach().float()
+        return out
+
+    def run(self, x, no_input_grad=False):
+        """x: Act [n, h, w, 8] (single plane).  Returns the logits as an Act [n, h/16, w/16, 8] (channel 0)."""
+        train = self.cfg.train
+        for li, (parts, width, stride, act) in enumerate(self.layers):
+            ho, wo = parts[0][0].op.out_hw(x.h, x.w)
+            out = Act.empty(x.n, ho, wo, width, two=False, device=x.hi.device)
+            for conv, coff, cnt in parts:
+                conv(x, out=out, out_coff=coff, no_input_grad=(no_input_grad and li == 0))
+            if act:
+                nv.check(nv.lib().crdr_leaky_relu(out.planes(0), out.pixels, width, self.SLOPE, nv.stream_handle()))
+                if train is not None and train.tape is not None:
+                    train.tape.append(("lrelu", out, self.SLOPE))
+            x = out
+        return x

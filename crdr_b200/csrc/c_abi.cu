@@ -84,6 +84,8 @@ int mse_bwd_launch(const float* fake, int fake_cs, const float* real, int n, int
 int adam_launch(float* p, const float* g, float* m, float* v, int64_t count, float lr, float b1, float b2, float eps, int step,
                 const float* gscale_ptr, float gscale, const float* hyper, cudaStream_t st);
 int sumsq_launch(const float* x, int64_t count, float* partial1024, float* out, cudaStream_t st);
+int leaky_relu_launch(crdr_planes x, int64_t m, int c, float slope, cudaStream_t st);
+int planes_grad_to_phases_launch(const void* g8, int g8_cs, int n, int hb, int wb, float scale, void* g, int g_cs, cudaStream_t st);
 
 }  // namespace crdr
 
@@ -270,6 +272,13 @@ int crdr_mse_backward(const float* fake, int32_t fake_cs, const float* real, int
 int crdr_adam_step(float* p, const float* g, float* m, float* v, int64_t count, float lr, float beta1, float beta2, float eps,
                    int32_t step, const float* gscale_ptr, float gscale, const float* hyper, void* stream) {
   return adam_launch(p, g, m, v, count, lr, beta1, beta2, eps, step, gscale_ptr, gscale, hyper, (cudaStream_t)stream);
+}
+int crdr_leaky_relu(crdr_planes x, int64_t m, int32_t c, float slope, void* stream) {
+  return leaky_relu_launch(x, m, c, slope, (cudaStream_t)stream);
+}
+int crdr_planes_grad_to_phases(const void* g8, int32_t g8_cs, int32_t n, int32_t hb, int32_t wb, float scale, void* g,
+                               int32_t g_cs, void* stream) {
+  return planes_grad_to_phases_launch(g8, g8_cs, n, hb, wb, scale, g, g_cs, (cudaStream_t)stream);
 }
 int crdr_sum_squares(const float* x, int64_t count, float* partial, float* out, void* stream) {
   return sumsq_launch(x, count, partial, out, (cudaStream_t)stream);

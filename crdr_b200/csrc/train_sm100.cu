@@ -180,6 +180,9 @@ __global__ void __launch_bounds__(256) epi_bwd_kernel(const crdr_epi_bwd_desc d,
           if (d.add_vec) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) dv.v[e] = o.v[e] != zero_level.v[e] ? g1.v[e] : 0.f;
+          } else if (d.leaky_slope != 0.f) {   // LeakyReLU (discriminator): the stored output has the sign of the input
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dv.v[e] = o.v[e] > 0.f ? g1.v[e] : d.leaky_slope * g1.v[e];
           } else {
 #pragma unroll
             for (int e = 0; e < 8; ++e) dv.v[e] = o.v[e] > 0.f ? g1.v[e] : 0.f;
@@ -223,6 +226,65 @@ int epi_bwd_launch(const crdr_epi_bwd_desc* dp, cudaStream_t st) {
   if (!status) return CRDR_ERR_CUDA;
   epi_bwd_kernel<<<d.blocks, dim3(32, 8), 0, st>>>(d, status);
   return check_launch("epi_bwd_kernel");
+}
+
+// LeakyReLU in place on a single fp16 plane (CLIC21GVAEDiscriminator, clic21_gvae_discriminator.py:12-25)
+__global__ void leaky_relu_kernel(__half* __restrict__ x, int64_t m, int c, int cs, int coff, float slope) {
+  const int groups = c >> 3;
+  const int64_t total = m * groups;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / groups;
+    const int c0 = (int)(i % groups) * 8;
+    __half* p = x + r * cs + coff + c0;
+    F8 v = load_h8(p);
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = v.v[2 * k] > 0.f ? v.v[2 * k] : slope * v.v[2 * k];
+      const float b = v.v[2 * k + 1] > 0.f ? v.v[2 * k + 1] : slope * v.v[2 * k + 1];
+      const __half2 h = __floats2half2_rn(a, b);
+      w[k] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+int leaky_relu_launch(crdr_planes x, int64_t m, int c, float slope, cudaStream_t st) {
+  if (!x.hi || x.lo || m <= 0 || c <= 0 || c % 8 || x.cs % 8 || x.coff % 8) { set_error("leaky_relu: single fp16 plane, channels / stride / offset multiples of 8"); return CRDR_ERR_BAD_SHAPE; }
+  int64_t blocks = (m * (c >> 3) + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  leaky_relu_kernel<<<(unsigned)blocks, 256, 0, st>>>(const_cast<__half*>(reinterpret_cast<const __half*>(x.hi)), m, c, x.cs, x.coff, slope);
+  return check_launch("leaky_relu_kernel");
+}
+
+// Gradient w.r.t. an image held as 8-channel NHWC planes (the discriminator's input) added into the phase-packed gradient
+// of the last up-convolution's output:  g[n, a, b, (ph*2+pw)*3 + c] += scale * g8[n, 2a+ph, 2b+pw, c]
+__global__ void planes_grad_to_phases_kernel(const __half* __restrict__ g8, int g8_cs, int n, int hb, int wb, float scale,
+                                             __half* __restrict__ g, int g_cs, uint32_t* status) {
+  const int64_t total = (int64_t)n * hb * wb * 12;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % 12);
+    const int64_t pix = i / 12;
+    const int b = (int)(pix % wb);
+    const int a = (int)((pix / wb) % hb);
+    const int64_t img = pix / ((int64_t)wb * hb);
+    const int phase = ch / 3, c = ch % 3;
+    const int64_t src = ((img * (2 * hb) + 2 * a + (phase >> 1)) * (2 * wb) + 2 * b + (phase & 1)) * g8_cs + c;
+    float v = __half2float(g[pix * g_cs + ch]) + scale * __half2float(g8[src]);
+    if (!(fabsf(v) <= 65504.f)) { atomicOr(status, kFlagOverflow); v = fminf(fmaxf(v, -65504.f), 65504.f); }
+    g[pix * g_cs + ch] = __float2half_rn(v);
+  }
+}
+
+int planes_grad_to_phases_launch(const void* g8, int g8_cs, int n, int hb, int wb, float scale, void* g, int g_cs, cudaStream_t st) {
+  if (!g8 || !g || n <= 0 || hb <= 0 || wb <= 0 || g8_cs < 3 || g_cs < 12) { set_error("planes_grad_to_phases: bad arguments"); return CRDR_ERR_BAD_SHAPE; }
+  uint32_t* status = device_status_word();
+  if (!status) return CRDR_ERR_CUDA;
+  const int64_t total = (int64_t)n * hb * wb * 12;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  planes_grad_to_phases_kernel<<<(unsigned)blocks, 256, 0, st>>>((const __half*)g8, g8_cs, n, hb, wb, scale, (__half*)g, g_cs, status);
+  return check_launch("planes_grad_to_phases_kernel");
 }
 
 // out[c] (+)= scale * sum over blocks of partial[b][which][c].  Block (32, 8): lane x owns a channel, the 8 rows take

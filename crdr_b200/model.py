@@ -489,7 +489,7 @@ class _CharmModelCore(_CodecModelBase):
     # chunks' next segments.  (Two host threads on two streams were tried first: the chunks' full-GPU persistent kernels
     # interleave one for one, both chunks reach the host coder at the same moment and nothing overlaps.)
     # Results are per image and independent of the chunking (deterministic kernels, one rANS stream per image).
-    pipeline_chunks = 2
+    pipeline_chunks = int(os.environ.get("CRDR_PIPELINE_CHUNKS", "2"))
     pipeline_min_images = 8
     pipeline_weights = None  # optional relative chunk sizes, e.g. (2, 1)
 

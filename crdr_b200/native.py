@@ -117,6 +117,7 @@ class EpiBwdDesc(C.Structure):
         ("dv", Planes), ("dres", Planes),
         ("partial", C.c_void_p), ("blocks", C.c_int32),
         ("add_vec", C.c_void_p),
+        ("leaky_slope", C.c_float),
     ]
 
 
@@ -154,7 +155,7 @@ SM100_SYMBOLS = [
     "crdr_image_u8_to_patches", "crdr_phases_to_image_u8", "crdr_phases_to_image_ex",
     "crdr_conv_dgrad", "crdr_conv_wgrad_workspace", "crdr_conv_wgrad", "crdr_pack_weights", "crdr_pack_weights_multi", "crdr_epilogue_backward",
     "crdr_colsum_finish", "crdr_gate_forward", "crdr_gate_backward", "crdr_gauss_backward", "crdr_mse_backward",
-    "crdr_adam_step", "crdr_sum_squares",
+    "crdr_adam_step", "crdr_sum_squares", "crdr_leaky_relu", "crdr_planes_grad_to_phases",
 ]
 
 _lib = None
@@ -212,6 +213,8 @@ def lib():
         L.crdr_mse_backward.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, f32, vp, i32, vp]
         L.crdr_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp, f32, vp, vp]
         L.crdr_sum_squares.argtypes = [vp, i64, vp, vp, vp]
+        L.crdr_leaky_relu.argtypes = [Planes, i64, i32, f32, vp]
+        L.crdr_planes_grad_to_phases.argtypes = [vp, i32, i32, i32, i32, f32, vp, i32, vp]
         L.crdr_debug_conv_epilogue.argtypes = [i32, i32]
         L.crdr_debug_conv_epilogue.restype = None
         assert L.crdr_abi_version() == 1

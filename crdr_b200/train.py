@@ -66,6 +66,7 @@ class TrainContext:
         self.buffers = {k: b.detach().to(self.device) for k, b in model.named_buffers()}
         self._grad_by_ptr = {self.params[k].data_ptr(): self.grads[k] for k in self.names}
         self._pack_table = None
+        self.param_grads = True
         self.live = {}          # sub-network name -> live state dict (views of flat_p)
         self.gain_state = {}    # "encoder" / "decoder" -> (engine, l, r, alpha, lerped weights)
         self.gain_grad = {}
@@ -95,6 +96,10 @@ class TrainContext:
             conv.wmap_src = torch.nonzero(conv.wmap >= 0).reshape(-1).to(self.device)      # positions in the ConvOp's layout
             conv.wmap_dst = conv.wmap[conv.wmap >= 0].to(self.device)                      # ... and in the parameter
             conv.wmap = conv.wmap.to(self.device)
+        if conv.bias_buf is not None:
+            bidx = bias_transform(torch.arange(b.numel(), dtype=torch.float32) + 1.0).round().to(torch.int64).reshape(-1) - 1
+            conv.bmap_src = torch.nonzero(bidx >= 0).reshape(-1).to(self.device)
+            conv.bmap_dst = bidx[bidx >= 0].to(self.device)
         conv.dgrad = None
         self.convs.append(conv)
 
@@ -436,9 +441,10 @@ class CodecTrainer:
             main.wait_event(ev)
         self._side_used.clear()
 
-    def backward(self, images, out, rate_weight=None):
+    def backward(self, images, out, rate_weight=None, image_grad=None, image_grad_scale=1.0):
         """Reverse sweep over the tape; fills ctx.flat_g (unscaled fp32 gradients of mean-reduced losses).  rate_weight:
-        a float overrides the device-resident weight the last losses() call decided."""
+        a float overrides the device-resident weight the last losses() call decided.  image_grad: an extra loss-scaled
+        gradient w.r.t. the reconstruction as 8-channel NHWC planes (the adversarial term's path through a discriminator)."""
         if rate_weight is not None:
             self._rate_w.fill_(float(rate_weight))
         ctx, L, st = self.ctx, nv.lib(), nv.stream_handle()
@@ -456,6 +462,9 @@ class CodecTrainer:
         coef_mse = S * self.lambda_mse * 2.0 * 0.25 / (n * 3 * h * w)
         nv.check(L.crdr_mse_backward(fp.data_ptr(), fp.shape[-1], images.data_ptr(), n, h // 2, w // 2, h, w, coef_mse,
                                      g_img.hi.data_ptr(), 16, st))
+        if image_grad is not None:
+            nv.check(L.crdr_planes_grad_to_phases(image_grad.hi.data_ptr(), image_grad.c, n, h // 2, w // 2, image_grad_scale,
+                                                  g_img.hi.data_ptr(), 16, st))
         self._rate_coef = S / (math.log(2.0) * n * h * w)   # d(mean bpp) / d(-ln L) per element; x the device-resident rate weight
         tape, ctx.tape = ctx.tape, None
         for rec in reversed(tape):
@@ -470,6 +479,8 @@ class CodecTrainer:
                 self._gauss_backward(*rec[1:])
             elif kind == "eb":
                 self._eb_backward(*rec[1:])
+            elif kind == "lrelu":
+                self._lrelu_backward(*rec[1:])
         self._join_sides()
         ctx.finish_gain_grads(inv)
         ctx.finish_cond_grads(inv)
@@ -480,7 +491,7 @@ class CodecTrainer:
                                              nv.stream_handle()))
 
     def _conv_backward(self, conv, x, kw, out, bwd_res, no_input_grad):
-        ctx, L, st = self.ctx, nv.lib(), nv.stream_handle()
+        ctx, L, st = conv.cfg.train, nv.lib(), nv.stream_handle()
         op = conv.op
         out_f32 = kw.get("out_f32")
         if out is not None and kw.get("want_planes", True):
@@ -489,7 +500,7 @@ class CodecTrainer:
             G, gcoff = self._grads.get(out_f32.data_ptr()), kw.get("out_f32_coff", 0)
         if G is None:
             return          # nothing downstream depends on this output
-        cout = op.cout_pad if conv.wmap is not None else op.cout
+        cout = op.cout
         relu, mode = bool(kw.get("relu")), kw.get("mode", nv.EPI_NONE)
         scale, shift = kw.get("scale"), kw.get("shift")
         add_vec = kw.get("add_vec")
@@ -541,14 +552,10 @@ class CodecTrainer:
         if no_input_grad:
             return
         if conv.dgrad is None:
-            assert conv.wmap is None or conv.name == "conv4", "only the last layer has a transformed weight and an input gradient"
-            if conv.wmap is not None:
-                # adjoint of the phase-packed 3x3 convolution [16, cin, 3, 3] built from the parameter through both maps
-                tf = conv.packed_transform
-                fn, dkw = bw.dgrad_spec(False, 1, op.padding, op.kh)
-                conv.dgrad = _SingleDgrad(bw.PackedConv(conv.master, lambda wi: fn(tf(wi)), two_planes=False, **dkw))
-            else:
-                conv.dgrad = bw.DgradSet(conv.master, op.transposed, op.stride, op.padding, op.kh, segs, cin_real=op.cin_real)
+            # (a convolution whose matrix is a transform of the parameter -- phase-packed last layer, output-channel halves /
+            # padded head of the discriminator -- gets its adjoint from the parameter through both index maps)
+            conv.dgrad = bw.DgradSet(conv.master, op.transposed, op.stride, op.padding, op.kh, segs, cin_real=op.cin_real,
+                                     pre=conv.packed_transform)
             conv.dgrad.repack()
         Gx = self._grad(x.hi.data_ptr(), like=x)
         if need_dv:
@@ -558,13 +565,14 @@ class CodecTrainer:
 
     def _param_grads(self, conv, op, x, kw, dv, dv_coff, cout, partial, blocks, scale, shift, affine, ws):
         """Bias / gain column sums and the weight gradient of one convolution record (side stream)."""
-        ctx = self.ctx
+        ctx = conv.cfg.train
+        if not ctx.param_grads:
+            return          # this network's parameters are frozen in this sweep (discriminator during the generator step)
         if conv.bias_master is not None:
-            if conv.bias_buf is not None:      # derived bias vector (phase-packed last layer): fold the phases back
+            if conv.bias_buf is not None:      # derived bias vector (phase-packed / sliced / padded): scatter through its index map
                 tmp = torch.zeros(cout, dtype=torch.float32, device=self.device)
                 self._sums_to(partial, blocks, 3, 0, cout, tmp, accumulate=False)
-                nb = conv.bias_master.numel()
-                ctx.grad_view(conv.bias_master).add_(tmp[: 4 * nb].view(4, nb).sum(0))
+                ctx.grad_view(conv.bias_master).view(-1).index_add_(0, conv.bmap_dst, tmp[conv.bmap_src])
             else:
                 self._sums_to(partial, blocks, 3, 0, op.cout, ctx.grad_view(conv.bias_master))
         if affine:
@@ -579,8 +587,8 @@ class CodecTrainer:
         if conv.wmap is not None:
             # transformed weight (im2col'd first layer, phase-packed last layer): gradient in the ConvOp's layout, then
             # scattered to the parameter through the transform's index map
-            tmp = torch.empty((op.cout_pad, op.cin, op.kh, op.kw), dtype=torch.float32, device=self.device)
-            bw.wgrad(dv, dv_coff, op.cout_pad, x, 0, op.cin, taps, 1, tmp, op.cin * k2, k2, 1, scale=1.0 / self.loss_scale, ws=ws)
+            tmp = torch.empty((op.cout, op.cin, op.kh, op.kw), dtype=torch.float32, device=self.device)
+            bw.wgrad(dv, dv_coff, op.cout, x, 0, op.cin, taps, op.stride, tmp, op.cin * k2, k2, 1, scale=1.0 / self.loss_scale, ws=ws)
             ctx.grad_view(conv.master).view(-1).index_add_(0, conv.wmap_dst, tmp.view(-1)[conv.wmap_src])
         else:
             gw = ctx.grad_view(conv.master).view(-1)
@@ -595,6 +603,17 @@ class CodecTrainer:
                         bw.wgrad(dv, dv_coff, op.cout, x, off, real, taps, op.stride, gw[start * k2:], op.cin_real * k2, k2, 1,
                                  scale=1.0 / self.loss_scale, accumulate=True, ws=ws)
                 start += ln
+
+    def _lrelu_backward(self, out, slope):
+        """LeakyReLU between two convolutions: the gradient of its output is rescaled in place (the convolution records that
+        wrote `out` come next in the reverse sweep and read it as the gradient of their result)."""
+        G = self._grads.get(out.hi.data_ptr())
+        if G is None:
+            return
+        d = nv.EpiBwdDesc()
+        d.g, d.out, d.dv = G.planes(0), out.planes(0), G.planes(0)
+        d.m, d.c, d.relu, d.leaky_slope, d.blocks = out.pixels, out.c, 1, slope, max(1, min(2048, out.pixels // 32))
+        nv.check(nv.lib().crdr_epilogue_backward(C.byref(d), nv.stream_handle()))
 
     def _gate_backward(self, x, t, a, out, scale, shift):
         G = self._grads.get(out.hi.data_ptr())
@@ -814,16 +833,151 @@ class CodecTrainer:
                 p.copy_(self.ctx.params[k].to(p.device))
 
 
-class _SingleDgrad:
-    def __init__(self, pc):
-        self.pc = pc
+class GanCodecTrainer(CodecTrainer):
+    """Stage 3 of the reference (MultirateBetaCondHrrGanRateDistortionTrainer.optimize_parameters,
+    multirate_hr_rgan_beta_cond_rate_distortion_trainer.py:13-114) on the CUDA engines, without the LPIPS term (no pretrained
+    AlexNet weights offline):
 
-    def packed(self):
-        return [self.pc]
+      G step:  l = distortion + rate + beta * adv,   adv = lambda_gan / 2 * (BCE(D(rel) - D(fake), 0) + BCE(D(fake) - D(rel), 1))
+               where `rel` is the reconstruction at the next higher quality level (no gradient; the real image at the top
+               level) and D = sub-discriminator int(q); the discriminator's parameters are frozen, its input gradient is
+               added to the MSE gradient of the reconstruction.
+      D step:  0.5 * BCE(D(real) - D(fake).detach(), 1) + 0.5 * BCE(D(fake.detach()) - D(real).detach(), 0), Adam on the
+               active sub-discriminator only (parameters without a gradient are skipped by torch.optim.Adam).
 
-    def repack(self):
-        self.pc.repack()
+    The discriminator runs through the same tape / reverse-sweep machinery as the codec (3x3 convolutions, LeakyReLU,
+    tcgen05 wgrad, dgrad); the logit maps are 16 x 16 per crop, so the BCE terms are evaluated with torch on the device."""
 
-    def run(self, dv, grad, accumulate=True, dv_coff=0, dv_c=None):
-        segs = None if dv_c is None else [(dv_coff, dv_c)]
-        self.pc.op(dv, segs=segs, out=grad, out_coff=0, precision=nv.PREC_F16X1, mode=nv.EPI_RESIDUAL, res=grad, res_coff=0)
+    def __init__(self, model, discriminator, device="cuda:0", lambda_gan=0.000390625, d_lr=1e-4, relative_score_rate_delta=1,
+                 **kw):
+        kw.setdefault("target_rate", (0.0,) * 5)
+        kw.setdefault("rate_lambda_a", (3.4, 1.3, 0.4, 0.12, 0.05))
+        super().__init__(model, device=device, **kw)
+        self.use_graphs = False            # the two-network step is enqueued eagerly
+        self.discriminator = discriminator
+        self.dctx = TrainContext(discriminator, device)
+        subs = len(discriminator.subD_list)
+        with torch.cuda.device(self.device):
+            self.D = [discriminator.subD_list[k].lower(device, sd=self.dctx.live_sd(f"subD_list.{k}"), train=self.dctx) for k in range(subs)]
+        self.dctx.repack()
+        # flat-buffer segment of every sub-discriminator (named_parameters order: subD_list.0.*, subD_list.1.*, ...)
+        self._dseg = []
+        for k in range(subs):
+            idx = [i for i, n in enumerate(self.dctx.names) if n.startswith(f"subD_list.{k}.")]
+            lo = self.dctx.offsets[idx[0]]
+            hi = self.dctx.offsets[idx[-1] + 1] if idx[-1] + 1 < len(self.dctx.offsets) else self.dctx.total
+            self._dseg.append((lo, hi))
+        self.dm, self.dv = torch.zeros_like(self.dctx.flat_p), torch.zeros_like(self.dctx.flat_p)
+        self.d_steps = [0] * subs
+        self.lambda_gan, self.d_lr, self.delta = float(lambda_gan), float(d_lr), int(relative_score_rate_delta)
+
+    # ------------------------------------------------------------------ discriminator passes
+    def d_forward(self, k, images, tape=True, input_grad=False):
+        """Sub-discriminator k on [n, 3, h, w] fp32 device images.  Returns (logit map [n, h/16, w/16] fp32, tape, logits Act,
+        input planes Act)."""
+        n, _, h, w = images.shape
+        x = Act.empty(n, h, w, 8, two=False, device=self.device)
+        nv.check(nv.lib().crdr_image_to_planes(images.data_ptr(), n, h, w, h, w, x.planes(0), nv.stream_handle()))
+        self.dctx.tape = [] if tape else None
+        logits = self.D[k].run(x, no_input_grad=not input_grad)
+        rec, self.dctx.tape = self.dctx.tape, None
+        return logits.hi[..., 0].float(), rec, logits, x
+
+    def d_backward(self, tape, logits, dpred, param_grads=True):
+        """Reverse sweep of one discriminator pass from d(loss)/d(logit map) (unscaled fp32 [n, h', w']).  The pass uses
+        its own power-of-two loss scale, chosen so that the root gradient sits at 2^6 in fp16 (the adversarial term is
+        1e-4 of the MSE term: under the codec's scale its gradients would live in fp16's subnormals); returns that scale."""
+        peak = float(dpred.abs().max().item())
+        scale = 2.0 ** math.floor(math.log2(64.0 / peak)) if peak > 0 else 1.0
+        G = self._grad(logits.hi.data_ptr(), like=logits)
+        G.hi.zero_()
+        G.hi[..., 0] = (dpred * scale).half()
+        saved, self.loss_scale = self.loss_scale, scale
+        self.dctx.param_grads = param_grads
+        try:
+            for rec in reversed(tape):
+                if rec[0] == "conv":
+                    self._conv_backward(*rec[1:])
+                elif rec[0] == "lrelu":
+                    self._lrelu_backward(*rec[1:])
+            self._join_sides()
+        finally:
+            self.dctx.param_grads = True
+            self.loss_scale = saved
+        return scale
+
+    @staticmethod
+    def _bce(x, target):
+        return F.binary_cross_entropy_with_logits(x, torch.full_like(x, target))
+
+    # ------------------------------------------------------------------ the step
+    def train_step(self, images, q=None, noise=None, generator=None, beta=None):
+        from .sharding import broadcast_from_rank0
+        n, _, h, w = images.shape
+        if q is None:
+            qt = torch.randint(self.model.rate_level, (1,)).to(self.device, torch.float32)
+            q = float(broadcast_from_rank0(qt, self.pg).item())
+        if beta is None:
+            bt = torch.randint(0, 101, (1,)).to(self.device, torch.float32) * (self.gs.max_beta / 100.0)
+            beta = float(broadcast_from_rank0(bt, self.pg).item())
+        if noise is None:
+            mk = lambda c, a, b: torch.rand((n, c, a, b), dtype=torch.float32, device=self.device, generator=generator) - 0.5
+            noise = {"z": mk(self.zc, h // 64, w // 64), "y": mk(self.charm.yc, h // 16, w // 16)}
+        k = int(q)
+        if self._auto_scale:
+            self.loss_scale = 2.0 ** math.floor(math.log2(max(2.0, n * h * w / 2.0)))
+        # ---- relative-score image: the reconstruction one quality level up (no gradient), or the real image at the top level
+        if q + self.delta > self.model.rate_level - 1:
+            rel = images
+        else:
+            noise_rel = {kk: torch.rand_like(v) - 0.5 for kk, v in noise.items()}
+            rel = self.forward(images, q + self.delta, noise_rel, beta=beta)["fake_images"]
+            self.ctx.tape = None
+        # ================================================================== train G
+        out = self.forward(images, q, noise, beta=beta)
+        fake = out["fake_images"]
+        ld = self._losses_device(images, out, q)
+        real_d, _, _, _ = self.d_forward(k, rel, tape=False)
+        fake_g, dtape, dlogits, dplanes = self.d_forward(k, fake, tape=True, input_grad=True)
+        with torch.enable_grad():
+            fg = fake_g.detach().requires_grad_(True)
+            adv = self.lambda_gan * 0.5 * (self._bce(real_d - fg, 0.0) + self._bce(fg - real_d, 1.0))
+            (dfg,) = torch.autograd.grad(beta * adv, [fg])
+        self.dctx.flat_g.zero_()
+        d_scale = self.d_backward(dtape, dlogits, dfg, param_grads=False)
+        g_in = self._grads[dplanes.hi.data_ptr()]          # d(beta * adv) / d(fake image) as 8-channel planes, x d_scale
+        self.backward(images, out, image_grad=g_in, image_grad_scale=self.loss_scale / d_scale)
+        ld["aux"] = self.aux_step()
+        self.all_reduce_grads()
+        self.optimizer_step()
+        ld = self._finish_losses(ld)
+        ld["adv"] = adv.detach()
+        # ================================================================== train D
+        # (gradient buffers are keyed by the storage address of the activation they belong to: the generator step's
+        # activations are released now, so its entries must go before new tensors can land on the same addresses)
+        self._grads, self._keep = {}, []
+        self.dctx.flat_g.zero_()
+        fake_d, ftape, flogits, _ = self.d_forward(k, fake, tape=True)
+        real_p, rtape, rlogits, _ = self.d_forward(k, images, tape=True)
+        with torch.enable_grad():
+            rp, fp = real_p.detach().requires_grad_(True), fake_d.detach().requires_grad_(True)
+            l_d_real = 0.5 * self._bce(rp - fp.detach(), 1.0)
+            l_d_fake = 0.5 * self._bce(fp - rp.detach(), 0.0)
+            drp, dfp = torch.autograd.grad(l_d_real + l_d_fake, [rp, fp])
+        self.d_backward(rtape, rlogits, drp)
+        self.d_backward(ftape, flogits, dfp)
+        from .sharding import allreduce_mean_flat
+        allreduce_mean_flat(self.dctx.flat_g, 64 << 20, self.pg)
+        self.d_optimizer_step(k)
+        nv.status_check()
+        ld.update(d_real=l_d_real.detach(), d_fake=l_d_fake.detach(), out_d_real=real_p.mean(), out_d_fake=fake_d.mean())
+        return ld
+
+    def d_optimizer_step(self, k):
+        lo, hi = self._dseg[k]
+        self.d_steps[k] += 1
+        c = self.dctx
+        nv.check(nv.lib().crdr_adam_step(c.flat_p[lo:].data_ptr(), c.flat_g[lo:].data_ptr(), self.dm[lo:].data_ptr(), self.dv[lo:].data_ptr(),
+                                         hi - lo, self.d_lr, self.betas[0], self.betas[1], self.eps, self.d_steps[k], None, 1.0, None,
+                                         nv.stream_handle()))
+        c.repack()

@@ -363,6 +363,7 @@ typedef struct {
   int32_t blocks;       /* row blocks = grid size (1..4096) */
   const float* add_vec; /* forward added this per-channel vector AFTER the ReLU (beta conditioning, single-plane tensors): the
                            mask is out != fp16(add_vec) instead of out > 0; its gradient is sum 1 (no gain) or sum 0 (no ReLU) */
+  float leaky_slope;    /* with relu = 1: LeakyReLU of this negative slope (0: plain ReLU) */
 } crdr_epi_bwd_desc;
 int crdr_epilogue_backward(const crdr_epi_bwd_desc* d, void* stream);
 /* out[c] (+)= scale * sum_b partial[b][which][c], blocks in ascending order */
@@ -408,6 +409,14 @@ int crdr_gauss_backward(const crdr_gauss_bwd_desc* d, void* stream);
  * fake [n, hb, wb, >=16] fp32 (channel (ph*2+pw)*3 + c), real [n, 3, h, w] fp32 -> g [n, hb, wb, g_cs] fp16. */
 int crdr_mse_backward(const float* fake, int32_t fake_cs, const float* real, int32_t n, int32_t hb, int32_t wb, int32_t h,
                       int32_t w, float coef, void* g, int32_t g_cs, void* stream);
+
+/* nn.LeakyReLU(slope) in place on channels [coff, coff + c) of a single fp16 plane (clic21_gvae_discriminator.py:12-25;
+ * its backward is crdr_epilogue_backward with relu = 1 and leaky_slope). */
+int crdr_leaky_relu(crdr_planes x, int64_t m, int32_t c, float slope, void* stream);
+/* g[n, a, b, (ph*2+pw)*3 + c] += scale * g8[n, 2a+ph, 2b+pw, c]: the gradient a discriminator sends back to the image
+ * (8-channel NHWC fp16 planes, 3 used) added to the phase-packed gradient of the reconstruction (see crdr_mse_backward). */
+int crdr_planes_grad_to_phases(const void* g8, int32_t g8_cs, int32_t n, int32_t hb, int32_t wb, float scale, void* g,
+                               int32_t g_cs, void* stream);
 
 /* torch.optim.Adam step on flat fp32 buffers; the gradient is multiplied by gscale (* gscale_ptr[0] when given: the
  * clip coefficient computed on the device).  step >= 1, or `hyper` = device float[3] {lr, 1 - beta1^step, sqrt(1 - beta2^step)}

@@ -332,6 +332,18 @@ def forward_train(sd, x, q, beta, noise, eb, gc, forced_y_symbols=None):
             "quantized_code": {"y": y_hat, "z": z_hat}, "q_likelihoods": {"y": torch.cat(qliks, dim=1), "z": z_qlik}}
 
 
+def discriminator(sd, x, slope=0.2):
+    """CLIC21GVAEDiscriminator.forward with norm_type none (src/models/discriminator/clic21_gvae_discriminator.py:27-50):
+    sd = state dict of ONE sub-discriminator (keys model.{0,2,...}.weight / .bias); strides 1, 2, 1, 2, ..., head 1."""
+    idx = sorted(int(k.split(".")[1]) for k in sd if k.endswith(".weight"))
+    for n, i in enumerate(idx):
+        last = n == len(idx) - 1
+        x = F.conv2d(x, sd[f"model.{i}.weight"], sd[f"model.{i}.bias"], stride=1 if (last or n % 2 == 0) else 2, padding=1)
+        if not last:
+            x = F.leaky_relu(x, slope)
+    return x
+
+
 def to_uint8(img):
     """img_utils.torch2npimg truncation semantics (img_utils.py:30-42)."""
     return ((img + 1.0) / 2.0 * 255.0).numpy().astype(np.uint8)

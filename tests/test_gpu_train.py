@@ -439,3 +439,71 @@ def test_training_steps_reduce_the_loss_and_keep_engines_in_sync(config):
     # evaluation-mode reconstruction of the synced model (clamped) vs the trainer's training-mode forward (unclamped):
     # same weights, same quantised latents up to straight-through rounding
     assert _rel(out["fake_images"].clamp(-1, 1).cpu(), a["fake_images"].cpu()) < 2e-2
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Stage 3: discriminators and the GAN step
+# ----------------------------------------------------------------------------------------------------------------------
+def _gan_trainer(seed=8):
+    import fixtures
+    from crdr_b200.discriminator import build_discriminator
+    from crdr_b200.train import GanCodecTrainer
+    model, _ = fixtures.build_model(seed=seed, calibrated=False, config="crdr.yaml")
+    torch.manual_seed(seed + 1)
+    disc = build_discriminator(dict(type="ModuleListDiscriminator", _subd_type="CLIC21GVAEDiscriminator", _num_subd=5, in_ch=3,
+                                    out_ch=1, main_ch=64, norm_type="none"))
+    return GanCodecTrainer(model, disc, device=DEV, lr=1e-4, clip_max_norm=1.0), disc
+
+
+def test_discriminator_forward_and_gradients_match_autograd(oracle):
+    import fixtures
+    tr, disc = _gan_trainer()
+    k = 3
+    sub = {n: p.detach().clone() for n, p in disc.subD_list[k].state_dict().items()}
+    x = fixtures.image(2, 64, 96, seed=31)
+    # reference: the oracle's functional discriminator (bit-equal to the reference module, tests/test_oracle_vs_reference.py)
+    subr = {n: v.clone().requires_grad_(True) for n, v in sub.items()}
+    xr = x.clone().requires_grad_(True)
+    pred_ref = oracle.discriminator(subr, xr)
+    loss = F.binary_cross_entropy_with_logits(pred_ref, torch.ones_like(pred_ref))
+    loss.backward()
+    pred, tape, logits, planes = tr.d_forward(k, x.to(DEV).contiguous(), tape=True, input_grad=True)
+    torch.cuda.synchronize()
+    assert _rel(pred.cpu(), pred_ref.detach()[:, 0]) < 1e-2          # fp16 activations through 9 layers
+    p = pred.detach().requires_grad_(True)
+    (dp,) = torch.autograd.grad(F.binary_cross_entropy_with_logits(p, torch.ones_like(p)), [p])
+    tr.dctx.flat_g.zero_()
+    d_scale = tr.d_backward(tape, logits, dp)
+    torch.cuda.synchronize()
+    errs = []
+    for n, v in subr.items():
+        got = tr.dctx.grads[f"subD_list.{k}.{n}"].cpu()
+        errs.append((float((got - v.grad).norm() / v.grad.norm()), n))
+    assert max(errs)[0] < 3e-2, sorted(errs, reverse=True)[:6]
+    other = [n for n in tr.dctx.grads if not n.startswith(f"subD_list.{k}.")]
+    assert all(float(tr.dctx.grads[n].abs().max()) == 0.0 for n in other)           # the other sub-discriminators are untouched
+    gin = tr._grads[planes.hi.data_ptr()].to_nchw().cpu()[:, :3] / d_scale
+    # the fp16 forward flips the sign of ~1e-3 of the near-zero LeakyReLU inputs relative to the fp32 reference (slope 1 <-> 0.2),
+    # which bounds the agreement of everything that flows back through all eight of them at a few per cent (the number does
+    # not move with the loss scale)
+    assert float((gin - xr.grad).norm() / xr.grad.norm()) < 5e-2
+    from crdr_b200 import native as nv
+    nv.status_check()
+
+
+def test_stage3_gan_step_runs_and_updates_the_right_parameters():
+    import fixtures
+    tr, disc = _gan_trainer(seed=10)
+    n, h, w = 2, 128, 128
+    x = fixtures.image(n, h, w, seed=23).to(DEV).contiguous()
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    p0 = tr.ctx.flat_p.clone()
+    d0 = tr.dctx.flat_p.clone()
+    for q in (1.0, 4.0):          # q = 1: relative score against the reconstruction at level 2; q = 4 (top level): against the real image
+        ld = tr.train_step(x, q=q, beta=2.56, generator=gen)
+        for key in ("rate", "distortion", "adv", "d_real", "d_fake", "aux"):
+            assert math.isfinite(float(ld[key])), (key, ld)
+        assert 0.3 < float(ld["d_real"]) < 0.4 and 0.3 < float(ld["d_fake"]) < 0.4     # ~ ln(2) / 2 for an untrained discriminator
+    assert float((tr.ctx.flat_p - p0).abs().max()) > 0
+    changed = [k for k, (lo, hi) in enumerate(tr._dseg) if float((tr.dctx.flat_p[lo:hi] - d0[lo:hi]).abs().max()) > 0]
+    assert changed == [1, 4], changed

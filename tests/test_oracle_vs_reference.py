@@ -91,6 +91,26 @@ def test_forward_train_equal_with_replayed_noise(oracle, ref_model):
     assert float(ref["fake_images"].abs().max()) > 0 and not torch.equal(ref["likelihoods"]["y"], ref["q_likelihoods"]["y"])
 
 
+def test_discriminator_equals_reference_and_same_layout(oracle, ref_model):
+    """ModuleListDiscriminator of CLIC21GVAEDiscriminators (config/crdr_stage_3.yaml:13-21).  The oracle's
+    functional forward equals the unmodified reference module bit for bit, and this package's parameter tree has the
+    reference's state_dict keys and shapes."""
+    from src.models.discriminator import build_discriminator as build_ref     # ref_model's fixture put the reference on sys.path
+    opt = dict(type="ModuleListDiscriminator", _subd_type="CLIC21GVAEDiscriminator", _num_subd=5, in_ch=3, out_ch=1, main_ch=64,
+               norm_type="none")
+    torch.manual_seed(99)
+    ref = build_ref(dict(opt)).eval()
+    x = torch.rand(2, 3, 64, 96, generator=torch.Generator().manual_seed(5)) * 2 - 1
+    for q in (0.0, 2.0, 3.7):
+        with torch.no_grad():
+            want = ref(x, rate_ind=q)
+        sub = {k[len(f"subD_list.{int(q)}."):]: v for k, v in ref.state_dict().items() if k.startswith(f"subD_list.{int(q)}.")}
+        assert torch.equal(oracle.discriminator(sub, x), want)
+    from crdr_b200.discriminator import build_discriminator as build_mine
+    mine = build_mine(dict(opt))
+    assert [(k, tuple(v.shape)) for k, v in mine.state_dict().items()] == [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]
+
+
 def test_training_gradients_equal_reference_autograd(oracle, ref_model):
     """The gradients the GPU training step is checked against (tests/test_gpu_train.py) are autograd through the oracle's
     forward_train; here they are pinned to autograd through the UNMODIFIED reference model (same seed -> same noise):
