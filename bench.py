@@ -40,6 +40,7 @@ WORKLOADS = {
     "clic": (1365, 2048, 16, 8, "strong"),      # configs[2]: a fixed list of 16 images sharded round-robin over the ranks
     "uhd": (2160, 3840, 1, 1, "weak"),          # configs[3]: single-image latency; one image per GPU at N = 8
     "train": (256, 256, 8, 8, "weak"),          # configs[4]: crdr_stage_2 training step, 8 crops per GPU, gradient all-reduce
+    "train_gan": (256, 256, 8, 8, "weak"),      # the stage-3 step (crdr.yaml + 5 discriminators, generator + discriminator update)
 }
 TRAIN_MAC_PER_PX = 1090930   # one forward pass per pixel; forward + dgrad + wgrad = 3 x
 SWEEP = [0.25 * i for i in range(17)]
@@ -163,8 +164,19 @@ def run_train(args, rank, world, local):
     dev = f"cuda:{local}"
     h, w, B = 256, 256, args.batch or 8
     warmup, steps = max(args.warmup, 3), args.steps
-    model, _ = fixtures.build_model(seed=0, calibrated=False, device=dev, config="crdr_stage_2.yaml")
-    tr = CodecTrainer(model, device=dev, lr=1e-4, clip_max_norm=1.0)
+    gan = args.workload == "train_gan"
+    if gan:
+        from crdr_b200.discriminator import build_discriminator
+        from crdr_b200.train import GanCodecTrainer
+        model, _ = fixtures.build_model(seed=0, calibrated=False, device=dev, config="crdr.yaml")
+        torch.manual_seed(1)
+        disc = build_discriminator(dict(type="ModuleListDiscriminator", _subd_type="CLIC21GVAEDiscriminator", _num_subd=5, in_ch=3,
+                                        out_ch=1, main_ch=64, norm_type="none"))
+        tr = GanCodecTrainer(model, disc, device=dev, lr=1e-4, clip_max_norm=1.0)
+    else:
+        model, _ = fixtures.build_model(seed=0, calibrated=False, device=dev, config="crdr_stage_2.yaml")
+        tr = CodecTrainer(model, device=dev, lr=1e-4, clip_max_norm=1.0)
+    step_kw = dict(beta=2.56) if gan else {}
     crops = [fixtures.image(B, h, w, seed=1000 + 17 * rank + i).pin_memory() for i in range(4)]
     crops_dev = [c.to(dev) for c in crops]
     gen = torch.Generator(device=dev).manual_seed(rank)
@@ -177,7 +189,7 @@ def run_train(args, rank, world, local):
         torch.cuda.synchronize()
 
     for i in range(warmup):
-        tr.train_step(crops_dev[i % 4], q=float(i % 5), generator=gen)
+        tr.train_step(crops_dev[i % 4], q=float(i % 5), generator=gen, **step_kw)
         flush.zero_()
     nv.status_check()
     sampler = ClockSampler(local)
@@ -188,7 +200,7 @@ def run_train(args, rank, world, local):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(steps):
-        ld = tr.train_step(crops_dev[i % 4], q=float(i % 5), generator=gen)
+        ld = tr.train_step(crops_dev[i % 4], q=float(i % 5), generator=gen, **step_kw)
         flush.zero_()
     ev1.record()
     barrier()
@@ -205,26 +217,34 @@ def run_train(args, rank, world, local):
     t0 = time.perf_counter()
     for i in range(args.e2e_steps):
         xd = crops[i % 4].to(dev, non_blocking=True)
-        ld = tr.train_step(xd, q=float(i % 5), generator=gen)
+        ld = tr.train_step(xd, q=float(i % 5), generator=gen, **step_kw)
         loss_host.copy_(torch.stack([ld["rate"], ld["distortion"]]), non_blocking=True)
         torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / args.e2e_steps
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    # stage 3: + the no-gradient forward one level up (4 of 5 levels), + 5 discriminator passes (94 kMAC/px each) of which one
+    # has an input-gradient pass and two have parameter-gradient passes
     flops_step = 3 * 2.0 * TRAIN_MAC_PER_PX * B * h * w
+    if gan:
+        flops_step += (0.8 * 2.0 * TRAIN_MAC_PER_PX + 2.0 * 94000 * (5 + 1 + 2 + 2)) * B * h * w
     tensor_peak, hbm_peak, peak_src = peaks()
     achieved = flops_step / (ms_step * 1e-3) / 1e12
     if rank == 0:
         line = {
-            "metric": TRAIN_METRIC, "value": value, "unit": "MPix/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "metric": TRAIN_METRIC if not gan else TRAIN_METRIC.replace("crdr_stage_2 step", "crdr_stage_3 step without LPIPS, generator + discriminator update"),
+            "value": value, "unit": "MPix/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 planes (3-term split forward in g_a/h_a/h_s/ChARM), fp16 activation gradients under a loss scale, fp32 "
                      "accumulate / parameters / gradients / Adam",
             "data": "synthetic",
-            "config": {"workload": f"train: crdr_stage_2.yaml (InterpCaHyperpriorCharmModel), {B} crops {h}x{w} per GPU, rate (HiFiC "
-                                   "variable-rate switch) + MSE losses (LPIPS left out: no pretrained weights offline), clip 1.0, Adam 1e-4; "
-                                   "seeded random-init weights, one quality level per step",
+            "config": {"workload": (f"train_gan: crdr.yaml model + ModuleListDiscriminator (5 x CLIC21GVAEDiscriminator), {B} crops {h}x{w} per GPU, "
+                                    "rate + MSE + beta * relativistic adversarial loss (LPIPS left out), generator and discriminator Adam steps, "
+                                    "eager launches (no CUDA graphs)" if gan else
+                                    f"train: crdr_stage_2.yaml (InterpCaHyperpriorCharmModel), {B} crops {h}x{w} per GPU, rate (HiFiC "
+                                    "variable-rate switch) + MSE losses (LPIPS left out: no pretrained weights offline), clip 1.0, Adam 1e-4; "
+                                    "seeded random-init weights, one quality level per step"),
                        "step": "training-mode forward (taped) + backward (wgrad / dgrad / element-wise kernels) + gradient "
                                "all-reduce (NCCL, N > 1) + fused Adam + re-packing of the tensor-core matrices",
                        "l2": "256 MiB memset between steps (inside the timed region)", "e2e_steps": args.e2e_steps},
@@ -250,7 +270,7 @@ def run_train(args, rank, world, local):
 def run_reference(args, rank):
     if rank != 0:
         return
-    if args.workload == "train":
+    if args.workload in ("train", "train_gan"):
         warm, steps = min(args.warmup, 1), min(args.steps, 3)
         v, sec, cores = cpu_train_sample(1, steps, warm)
         print(json.dumps({
@@ -307,7 +327,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU implementation (use --impl reference)")
-    if args.workload == "train":
+    if args.workload in ("train", "train_gan"):
         return run_train(args, rank, world, local)
     torch.cuda.set_device(local)
     if world > 1:
