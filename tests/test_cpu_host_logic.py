@@ -230,3 +230,71 @@ def test_chunk_split_and_pipeline_scheduler(model):
             assert log[i - 1] == ("sync", f"{rec[1]}{rec[2]}")
     hosts = [r[1:] for r in log if r[0] == "host"]
     assert hosts == [("a", 0), ("b", 0), ("a", 1), ("b", 1), ("b", 2)]
+
+
+def test_trainer_plugins_and_loss_config():
+    """The reference's trainer / discriminator registry names resolve (src/trainer/__init__.py:9-26,
+    src/models/discriminator/__init__.py:15-30) and the loss / optimiser sections of the stage-2 / stage-3 yaml files map
+    onto the lowered step's settings."""
+    import src  # noqa: F401
+    from crdr_b200.config import BaseConfig
+    from crdr_b200.registry import DISCRIMINATOR_REGISTRY, TRAINER_REGISTRY
+    from crdr_b200.trainers import _loss_kwargs
+    from src.models.discriminator import build_discriminator
+    from src.trainer import build_trainer  # noqa: F401
+    assert {"RateDistortionTrainer", "MultirateBetaCondHrrGanRateDistortionTrainer"} <= set(TRAINER_REGISTRY.keys())
+    assert {"CLIC21GVAEDiscriminator", "ModuleListDiscriminator"} <= set(DISCRIMINATOR_REGISTRY.keys())
+    o2 = BaseConfig.fromfile(os.path.join(ROOT, "config", "crdr_stage_2.yaml"), device="cpu", is_train=True)
+    k2 = _loss_kwargs(o2)
+    assert k2["rate_lambda_a"] == [3.6, 1.8, 0.8, 0.4, 0.1] and k2["rate_lambda_b"] == 2.0 ** -6 and k2["lambda_mse"] == 150.0
+    assert k2["clip_max_norm"] == 1.0 and k2["lr"] == 1e-4 and k2["aux_lr"] == 1e-3
+    o3 = BaseConfig.fromfile(os.path.join(ROOT, "config", "crdr_stage_3.yaml"), device="cpu", is_train=True)
+    assert o3["trainer"]["type"] == "MultirateBetaCondHrrGanRateDistortionTrainer" and _loss_kwargs(o3)["target_rate"] == [0.0] * 5
+    d = build_discriminator(dict(o3["discriminator"]))
+    assert len(d.subD_list) == 5 and sum(p.numel() for p in d.subD_list[0].parameters()) == 4689985    # SURVEY 8e
+
+
+def test_weight_index_maps_reproduce_host_packing():
+    """Training re-packs every tensor-core matrix on the device by a gather through an index map (crdr_pack_weights).  The
+    maps come from pushing an index tensor through the host packing code; here the gather is emulated with torch indexing
+    and must reproduce the host-packed matrices for every kind of convolution of the path: plain / strided / transposed,
+    two input ranges, the im2col'd first layer, the phase-packed last layer, and their dgrad adjoints (value check against
+    an explicit transposed / flipped weight)."""
+    import torch
+    from crdr_b200 import backward as bw
+    from crdr_b200.codec import AnalysisEngine, SynthesisEngine
+    from crdr_b200.engine import ConvOp, LO_SCALE
+
+    def emulate(pc):
+        flat = pc.master.reshape(-1)
+        for phs in pc.op.phases:
+            idx = phs.map.long()
+            v = torch.where(idx >= 0, flat[idx.clamp_min(0)], torch.zeros(()))
+            hi = v.half()
+            yield hi, ((v - hi.float()) * LO_SCALE).half()
+
+    g = torch.Generator().manual_seed(0)
+    cases = [
+        (torch.randn(96, 192, 1, 1, generator=g), None, {}),
+        (torch.randn(192, 192, 5, 5, generator=g) * 0.1, None, dict(stride=2, padding=2)),
+        (torch.randn(320, 256, 5, 5, generator=g) * 0.1, None, dict(transposed=True, stride=2, padding=2, output_padding=1)),
+        (torch.randn(224, 352, 5, 5, generator=g) * 0.1, None, dict(padding=2, seg_lens=[320, 32])),
+        (torch.randn(192, 3, 5, 5, generator=g), AnalysisEngine._patch_weight, {}),
+        (torch.randn(256, 3, 5, 5, generator=g), SynthesisEngine._phase_weight, dict(padding=1)),
+    ]
+    for w, tf, kw in cases:
+        host = ConvOp(tf(w) if tf else w, None, device="cpu", **kw)
+        pc = bw.PackedConv(w, tf or (lambda t: t), two_planes=True, **kw)
+        for phs, (hi, lo) in zip(host.phases, emulate(pc)):
+            assert torch.equal(phs.w_hi, hi) and torch.equal(phs.w_lo, lo)
+    # adjoints: the dgrad matrices of a 3x3 stride-1 convolution hold the transposed, flipped weights
+    w = torch.randn(96, 64, 3, 3, generator=g)
+    ds = bw.DgradSet(w, False, 1, 1, 3, [(0, 64)])
+    host = ConvOp(w.permute(1, 0, 2, 3).flip(2, 3).contiguous(), None, device="cpu", padding=1)
+    (pc, coff, cnt), = ds.parts
+    assert (coff, cnt) == (0, 64)
+    for phs, (hi, _) in zip(host.phases, emulate(pc)):
+        assert torch.equal(phs.w_hi, hi)
+    # more than 320 input channels: two chunks, written to consecutive channel ranges of the input gradient
+    ds = bw.DgradSet(torch.randn(224, 480, 5, 5, generator=g), False, 1, 2, 5, [(320, 320), (960, 160)])
+    assert [(c, n) for _, c, n in ds.parts] == [(320, 320), (960, 160)]

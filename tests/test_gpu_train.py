@@ -4,6 +4,7 @@ kernels, fused Adam and the gradient norm.  Tolerances are stated per test: fp16
 (they are built from the same fp16 values), so what is compared is fp32 accumulation order only."""
 import ctypes as C
 import math
+import os
 
 import pytest
 import torch
@@ -507,3 +508,27 @@ def test_stage3_gan_step_runs_and_updates_the_right_parameters():
     assert float((tr.ctx.flat_p - p0).abs().max()) > 0
     changed = [k for k, (lo, hi) in enumerate(tr._dseg) if float((tr.dctx.flat_p[lo:hi] - d0[lo:hi]).abs().max()) > 0]
     assert changed == [1, 4], changed
+
+
+@pytest.mark.parametrize("config", ["crdr_stage_2.yaml", "crdr_stage_3.yaml"])
+def test_train_script_drop_in(tmp_path, config):
+    """scripts/train.py (the reference's config -> build_trainer -> train_loop flow, reference scripts/train.py:16-28) for a
+    few iterations on synthetic crops; the checkpoint it writes has the reference layout and loads into a fresh model."""
+    import subprocess
+    import sys
+    import fixtures
+    from conftest import ROOT
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    cmd = [sys.executable, os.path.join(ROOT, "scripts", "train.py"), os.path.join(ROOT, "config", config), "-d", DEV, "--total_iter", "3",
+           "--batch_size", "2", "--patch_size", "128", "--exp", "t"]
+    r = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    path = tmp_path / "checkpoint" / "t" / "model" / "comp_model_iter3.pth.tar"
+    assert path.exists(), r.stdout[-500:]
+    ckpt = torch.load(path, map_location="cpu")
+    assert ckpt["iter"] == 3
+    from crdr_b200.model import build_comp_model
+    fresh = build_comp_model(fixtures.crdr_opt(DEV, "crdr_stage_2.yaml" if config == "crdr_stage_2.yaml" else "crdr.yaml"))
+    assert [k for k in ckpt["comp_model"] if "entropy_model" not in k] == [k for k in fresh.state_dict() if "entropy_model" not in k]
+    fresh.load_learned_weight(str(path))
+    assert all(torch.isfinite(v).all() for v in ckpt["comp_model"].values() if v.is_floating_point())
