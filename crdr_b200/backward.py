@@ -14,7 +14,7 @@ import ctypes as C
 import torch
 
 from . import native as nv
-from .engine import Act, ConvOp
+from .engine import ConvOp
 
 _WORKSPACE = {}
 

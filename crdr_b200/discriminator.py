@@ -1,12 +1,11 @@
 """Discriminators of the stage-3 (GAN) training under the reference's registry names: parameter trees with the reference's
 state_dict keys (clic21_gvae_discriminator.py:12-50, module_list_discriminator.py:13-29); the arithmetic runs in the
 lowered engine (``codec.DiscriminatorEngine``).  Only ``norm_type: none`` (what config/crdr_stage_3.yaml uses) is lowered."""
-import torch
 import torch.nn as nn
 
 from . import codec
 from .registry import DISCRIMINATOR_REGISTRY
-from .subnets import _conv, _indexed
+from .subnets import _indexed
 
 
 @DISCRIMINATOR_REGISTRY.register()

@@ -96,10 +96,13 @@ def pick_tile_n(cout_pad, m_tiles, three):
     return hit
 
 
+MIN_TILE_N = int(os.environ.get("CRDR_MIN_TILE_N", "64"))
+
+
 def _pick_tile_n(cout_pad, m_tiles, three):
     cap = 128 if three else 256  # F16X3 keeps two D0 buffers, D1 and the fp32 total in 512 TMEM columns
     cands = [t for t in range(16, min(cout_pad, cap) + 1, 16) if cout_pad % t == 0]
-    good = [t for t in cands if t >= min(64, cands[-1])]
+    good = [t for t in cands if t >= min(MIN_TILE_N, cands[-1])]
     best = good[0]
     for t in good:
         if m_tiles * (cout_pad // t) >= 148:

@@ -23,6 +23,7 @@ multirate_hr_rgan_beta_cond_rate_distortion_trainer.py:62-66.
 """
 import ctypes as C
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -243,7 +244,7 @@ class CodecTrainer:
         self.model, self.device = model, torch.device(device)
         # programmatic dependent launch between consecutive convolutions: the next launch's prologue overlaps the previous
         # one's tail; neutral for the full-GPU inference launches, -3.7 % on the small launches of a training step
-        __import__("os").environ.setdefault("CRDR_CONV_PDL", "1")
+        os.environ.setdefault("CRDR_CONV_PDL", "1")
         self.ctx = ctx = TrainContext(model, device)
         X3, X1 = nv.PREC_F16X3, nv.PREC_F16X1
         with torch.cuda.device(self.device):
@@ -291,7 +292,7 @@ class CodecTrainer:
         bw.workspace(256 << 20, self.device)   # split-K partial sums / column sums: sized once (no growth inside a capture)
         # parameter-gradient work (wgrad + split-K reduction, bias / gain column sums) hangs off the critical chain
         # epilogue-backward -> dgrad -> next layer: it runs on side streams with their own scratch and joins at the end
-        self.side_streams = int(__import__("os").environ.get("CRDR_TRAIN_SIDE_STREAMS", "4"))
+        self.side_streams = int(os.environ.get("CRDR_TRAIN_SIDE_STREAMS", "4"))
         self._sides = [(torch.cuda.Stream(device=self.device), torch.empty(64 << 20, dtype=torch.uint8, device=self.device))
                        for _ in range(self.side_streams)]
         self._side_next, self._side_used = 0, set()
