@@ -491,7 +491,8 @@ class _CharmModelCore(_CodecModelBase):
     # Results are per image and independent of the chunking (deterministic kernels, one rANS stream per image).
     pipeline_chunks = int(os.environ.get("CRDR_PIPELINE_CHUNKS", "2"))
     pipeline_min_images = 8
-    pipeline_weights = None  # optional relative chunk sizes, e.g. (2, 1)
+    pipeline_weights = (tuple(float(v) for v in os.environ["CRDR_PIPELINE_WEIGHTS"].split(","))
+                        if os.environ.get("CRDR_PIPELINE_WEIGHTS") else None)  # optional relative chunk sizes, e.g. (2, 1)
 
     def _chunks(self, n):
         k = self.pipeline_chunks if n >= self.pipeline_min_images else 1

@@ -1,6 +1,11 @@
 #!/bin/bash
-# e2e of the default workload for several pipeline depths, with all host cores and confined to 4 cores (the share of one
-# rank on an 8-GPU box with 32 hardware threads)
+# e2e of the default workload for several pipeline shapes
 p() { python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$1', round(d['value'],1), 'MPix/s device', round(d['e2e']['value'],1), 'e2e', round(d['e2e']['s_per_step']*1e3,1), 'ms')"; }
-for c in 2 3 4; do CRDR_PIPELINE_CHUNKS=$c timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 6 2>/dev/null | p "all cores, chunks $c:"; done
-for c in 2 3 4 6; do CRDR_CODER_THREADS=4 CRDR_PIPELINE_CHUNKS=$c taskset -c 0-3 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 6 2>/dev/null | p "4 cores, chunks $c:"; done
+run() { CRDR_PIPELINE_CHUNKS=$1 CRDR_PIPELINE_WEIGHTS=$2 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 8 2>/dev/null | p "chunks $1 weights [$2]:"; }
+run 1 ""
+run 2 ""
+run 2 "1,2"
+run 2 "2,1"
+run 2 "3,2"
+run 3 "2,2,1"
+run 3 "1,2,2"
