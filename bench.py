@@ -190,7 +190,8 @@ def run_train(args, rank, world, local):
 
     # every quality level is stepped three times before anything is timed: the first step of a (shape, level) is the eager
     # warm-up that builds the adjoint matrices, the second captures the CUDA graphs, from the third on the step is a replay
-    for i in range(max(warmup, 15)):
+    warmup = max(warmup, 15)
+    for i in range(warmup):
         tr.train_step(crops_dev[i % 4], q=float(i % 5), generator=gen, **step_kw)
         flush.zero_()
     nv.status_check()

@@ -398,6 +398,21 @@ class CodecTrainer:
             g = self._grads[key] = Act.zeros(n, h, w, c, two=False, device=self.device)
         return g
 
+    @staticmethod
+    def _initial_scale(n, h, w):
+        """The loss roots carry 1 / (n h w): a power of two proportional to the pixel count keeps the activation gradients
+        in fp16's normal range whatever the batch.  Measured (tools/activation_range.py, profiles/activation_range_r02.txt):
+        with n h w / 2 the largest gradient of a step is 2^10 (default-init weights) to 2^13 (calibrated stage-2 weights) and
+        saturates for the calibrated beta-conditioned model, hence n h w / 16; an overflow lowers the scale further."""
+        return 2.0 ** math.floor(math.log2(max(2.0, n * h * w / 16.0)))
+
+    def _on_overflow(self):
+        """fp16 overflow in a backward kernel (gradients were clamped, the device flag is already cleared): lower the loss
+        scale and drop the captured graphs, which have the old scale baked into their launch parameters."""
+        self.loss_scale = max(1.0, self.loss_scale / 8.0)
+        self._graphs.clear()
+        self._warm.clear()
+
     def _partial(self, blocks, nsums, c):
         """Per-record scratch for the per-block column sums, alive until the step ends (side streams read it later)."""
         t = torch.empty(blocks * nsums * c, dtype=torch.float32, device=self.device)
@@ -451,9 +466,8 @@ class CodecTrainer:
         ctx, L, st = self.ctx, nv.lib(), nv.stream_handle()
         n = images.shape[0]
         h, w = out["size"]
-        if self._auto_scale:
-            # the loss roots carry 1 / (n h w): keep the activation gradients in fp16's normal range whatever the batch
-            self.loss_scale = 2.0 ** math.floor(math.log2(max(2.0, n * h * w / 2.0)))
+        if self.loss_scale is None:
+            self.loss_scale = self._initial_scale(n, h, w)
         S = self.loss_scale
         inv = 1.0 / S
         ctx.flat_g.zero_()
@@ -786,12 +800,19 @@ class CodecTrainer:
         key = (n, h, w, float(q))
         if not self.use_graphs or key not in self._warm:
             # eager: also the warm-up that builds the adjoint matrices, tensor maps and kernel attributes before a capture
-            ld = self._core_forward(images, q, noise)
-            self._decide_rate()
-            ld["aux"] = self._core_backward(images)
+            for attempt in range(4):
+                ld = self._core_forward(images, q, noise)
+                self._decide_rate()
+                ld["aux"] = self._core_backward(images)
+                try:
+                    nv.status_check()       # before the update: a step whose gradients were clamped is redone
+                    break
+                except nv.NativeError as e:
+                    if "overflow" not in str(e) or attempt == 3:
+                        raise
+                    self._on_overflow()
             self.all_reduce_grads()
             self.optimizer_step()
-            nv.status_check()
             self._warm.add(key)
             return self._finish_losses(ld)
         hit = self._graphs.get(key)
@@ -824,7 +845,12 @@ class CodecTrainer:
         go.replay()
         self.step_count += 1
         nv.LAUNCH_COUNT[0] += launches
-        nv.status_check()
+        try:
+            nv.status_check()
+        except nv.NativeError as e:
+            if "overflow" not in str(e):
+                raise
+            self._on_overflow()             # this update used clamped gradients (finite); the next steps run at a lower scale
         return self._finish_losses(dict(ld))
 
     def sync_to_model(self):
@@ -925,8 +951,8 @@ class GanCodecTrainer(CodecTrainer):
             mk = lambda c, a, b: torch.rand((n, c, a, b), dtype=torch.float32, device=self.device, generator=generator) - 0.5
             noise = {"z": mk(self.zc, h // 64, w // 64), "y": mk(self.charm.yc, h // 16, w // 16)}
         k = int(q)
-        if self._auto_scale:
-            self.loss_scale = 2.0 ** math.floor(math.log2(max(2.0, n * h * w / 2.0)))
+        if self.loss_scale is None:
+            self.loss_scale = self._initial_scale(n, h, w)
         # ---- relative-score image: the reconstruction one quality level up (no gradient), or the real image at the top level
         if q + self.delta > self.model.rate_level - 1:
             rel = images

@@ -532,3 +532,20 @@ def test_train_script_drop_in(tmp_path, config):
     assert [k for k in ckpt["comp_model"] if "entropy_model" not in k] == [k for k in fresh.state_dict() if "entropy_model" not in k]
     fresh.load_learned_weight(str(path))
     assert all(torch.isfinite(v).all() for v in ckpt["comp_model"].values() if v.is_floating_point())
+
+
+def test_loss_scale_backs_off_on_fp16_overflow():
+    """A loss scale that overflows fp16 in the backward kernels raises the device status flag; the step is redone at a lower
+    scale instead of applying clamped gradients, and the parameters stay finite."""
+    import fixtures
+    from crdr_b200.train import CodecTrainer
+    model, _ = fixtures.build_model(seed=6, calibrated=True, config="crdr_stage_2.yaml")
+    tr = CodecTrainer(model, device=DEV, loss_scale=2.0 ** 26)
+    x = fixtures.image(2, 128, 128, seed=22).to(DEV).contiguous()
+    ld = tr.train_step(x, q=2.0)
+    assert tr.loss_scale < 2.0 ** 26 and math.isfinite(float(ld["rate"] + ld["distortion"]))
+    assert bool(torch.isfinite(tr.ctx.flat_p).all()) and bool(torch.isfinite(tr.ctx.flat_g).all())
+    first = tr.loss_scale
+    tr.train_step(x, q=2.0)
+    tr.train_step(x, q=2.0)       # graph replay at the settled scale
+    assert tr.loss_scale == first
