@@ -494,8 +494,10 @@ class _CharmModelCore(_CodecModelBase):
     pipeline_weights = (tuple(float(v) for v in os.environ["CRDR_PIPELINE_WEIGHTS"].split(","))
                         if os.environ.get("CRDR_PIPELINE_WEIGHTS") else None)  # optional relative chunk sizes, e.g. (2, 1)
 
-    def _chunks(self, n):
-        k = self.pipeline_chunks if n >= self.pipeline_min_images else 1
+    pipeline_chunks_compress = int(os.environ.get("CRDR_PIPELINE_CHUNKS_COMPRESS", "0"))   # 0: pipeline_chunks
+
+    def _chunks(self, n, chunks=None):
+        k = (chunks or self.pipeline_chunks) if n >= self.pipeline_min_images else 1
         k = max(1, min(k, n))
         w = list(self.pipeline_weights) if self.pipeline_weights and len(self.pipeline_weights) == k else [1] * k
         tot, acc, edges = float(sum(w)), 0.0, [0]
@@ -585,7 +587,7 @@ class _CharmModelCore(_CodecModelBase):
         with torch.cuda.device(self.engine().device):
             nv.status_reset()
             res = self._drive([self._compress_gen(f"c{k}_", real_images[lo:hi], rate_ind, return_tensors, coder_threads)
-                               for k, (lo, hi) in enumerate(self._chunks(n))])
+                               for k, (lo, hi) in enumerate(self._chunks(n, self.pipeline_chunks_compress))])
             nv.status_check()
         return [r for chunk in res for r in chunk]
 

@@ -343,7 +343,9 @@ class CodecTrainer:
         T = self.charm.new_support(n, y_act.h, y_act.w, dev)
         self.hs.run(zhat, T, self.charm.off_mean, self.charm.off_scale)
         self._y_act, self._T, self._zhat = y_act, T, zhat
+        self._out_y_sym = None
         yhat32, y_sym, y_idx, y_lik, y_lik_noisy = self.charm.encode(T, y32, self.gp, noise=noise["y"])
+        self._out_y_sym = y_sym      # the integer rounding decisions of this forward (tests replay them in the oracle)
         fake_packed = self.gs.run(yhat32, q, self._beta)
         fake = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
         nv.check(L.crdr_phases_to_image_ex(fake_packed.data_ptr(), fake_packed.shape[-1], n, h // 2, w // 2, h, w, fake.data_ptr(), 0, st))
@@ -938,6 +940,27 @@ class GanCodecTrainer(CodecTrainer):
         return F.binary_cross_entropy_with_logits(x, torch.full_like(x, target))
 
     # ------------------------------------------------------------------ the step
+    def generator_backward(self, images, q, noise, beta, rel):
+        """Forward + losses + backward of the generator step (parameters of the discriminator frozen): fills ctx.flat_g with
+        the gradient of distortion + rate + beta * adv.  rel: the relative-score images (no gradient)."""
+        k = int(q)
+        if self.loss_scale is None:
+            self.loss_scale = self._initial_scale(images.shape[0], images.shape[2], images.shape[3])
+        out = self.forward(images, q, noise, beta=beta)
+        fake = out["fake_images"]
+        ld = self._losses_device(images, out, q)
+        real_d, _, _, _ = self.d_forward(k, rel, tape=False)
+        fake_g, dtape, dlogits, dplanes = self.d_forward(k, fake, tape=True, input_grad=True)
+        with torch.enable_grad():
+            fg = fake_g.detach().requires_grad_(True)
+            adv = self.lambda_gan * 0.5 * (self._bce(real_d - fg, 0.0) + self._bce(fg - real_d, 1.0))
+            (dfg,) = torch.autograd.grad(beta * adv, [fg])
+        self.dctx.flat_g.zero_()
+        d_scale = self.d_backward(dtape, dlogits, dfg, param_grads=False)
+        g_in = self._grads[dplanes.hi.data_ptr()]          # d(beta * adv) / d(fake image) as 8-channel planes, x d_scale
+        self.backward(images, out, image_grad=g_in, image_grad_scale=self.loss_scale / d_scale)
+        return ld, adv, fake
+
     def train_step(self, images, q=None, noise=None, generator=None, beta=None):
         from .sharding import broadcast_from_rank0
         n, _, h, w = images.shape
@@ -961,19 +984,7 @@ class GanCodecTrainer(CodecTrainer):
             rel = self.forward(images, q + self.delta, noise_rel, beta=beta)["fake_images"]
             self.ctx.tape = None
         # ================================================================== train G
-        out = self.forward(images, q, noise, beta=beta)
-        fake = out["fake_images"]
-        ld = self._losses_device(images, out, q)
-        real_d, _, _, _ = self.d_forward(k, rel, tape=False)
-        fake_g, dtape, dlogits, dplanes = self.d_forward(k, fake, tape=True, input_grad=True)
-        with torch.enable_grad():
-            fg = fake_g.detach().requires_grad_(True)
-            adv = self.lambda_gan * 0.5 * (self._bce(real_d - fg, 0.0) + self._bce(fg - real_d, 1.0))
-            (dfg,) = torch.autograd.grad(beta * adv, [fg])
-        self.dctx.flat_g.zero_()
-        d_scale = self.d_backward(dtape, dlogits, dfg, param_grads=False)
-        g_in = self._grads[dplanes.hi.data_ptr()]          # d(beta * adv) / d(fake image) as 8-channel planes, x d_scale
-        self.backward(images, out, image_grad=g_in, image_grad_scale=self.loss_scale / d_scale)
+        ld, adv, fake = self.generator_backward(images, q, noise, beta, rel)
         ld["aux"] = self.aux_step()
         self.all_reduce_grads()
         self.optimizer_step()

@@ -549,3 +549,49 @@ def test_loss_scale_backs_off_on_fp16_overflow():
     tr.train_step(x, q=2.0)
     tr.train_step(x, q=2.0)       # graph replay at the settled scale
     assert tr.loss_scale == first
+
+
+def test_generator_step_gradients_with_adversarial_term_match_autograd(oracle):
+    """Generator step of stage 3 at the top quality level (relative score against the real image): the gradient of
+    distortion + rate + beta * adv w.r.t. every codec parameter vs autograd through the oracle's codec AND discriminator.
+    lambda_gan is raised from the config's 3.9e-4 to 50 so that the adversarial path (discriminator dgrad -> reconstruction
+    gradient -> g_s ...) carries a third of the decoder's gradient instead of 1e-5 of it."""
+    import fixtures
+    tr, disc = _gan_trainer(seed=12)
+    tr.lambda_gan = 50.0
+    model_sd = {k: v.detach().clone() for k, v in tr.model.state_dict().items()}
+    n, h, w, q, beta, k = 2, 128, 128, 4.0, 2.56, 4
+    x = fixtures.image(n, h, w, seed=24)
+    g = torch.Generator().manual_seed(78)
+    noise = {"z": torch.rand(n, 192, h // 64, w // 64, generator=g) - 0.5, "y": torch.rand(n, 320, h // 16, w // 16, generator=g) - 0.5}
+    xd = x.to(DEV).contiguous()
+    ld, adv, fake = tr.generator_backward(xd, q, {kk: v.to(DEV).contiguous() for kk, v in noise.items()}, beta, xd)
+    torch.cuda.synchronize()
+    rate_w = float(tr._rate_w)
+    # reference
+    sdr = {kk: (v.clone().float().requires_grad_(True) if v.is_floating_point() else v) for kk, v in model_sd.items()}
+    eb, gc = oracle.entropy_models(sdr)
+    for p in eb.parameters():
+        p.requires_grad_(True)
+    dsub = {kk: v.detach().clone() for kk, v in disc.subD_list[k].state_dict().items()}
+    with torch.enable_grad():
+        out = oracle.forward_train.__wrapped__(sdr, x, q, beta, noise, eb, gc, forced_y_symbols=tr._out_y_sym.cpu())
+        bits = lambda lik: (-torch.log2(lik)).sum((1, 2, 3))
+        bpp = (bits(out["likelihoods"]["y"]) + bits(out["likelihoods"]["z"])) / (h * w)
+        mse = torch.mean(((x + 1) / 2 - (out["fake_images"] + 1) / 2) ** 2)
+        real_d = oracle.discriminator(dsub, x).detach()
+        fake_g = oracle.discriminator(dsub, out["fake_images"])
+        bce = lambda t, y: F.binary_cross_entropy_with_logits(t, torch.full_like(t, y))
+        adv_ref = 50.0 * 0.5 * (bce(real_d - fake_g, 0.0) + bce(fake_g - real_d, 1.0))
+        (rate_w * bpp.mean() + 150.0 * mse + beta * adv_ref).backward()
+    assert abs(float(adv) - float(adv_ref)) / float(adv_ref) < 2e-3
+    errs = []
+    for kk, v in sdr.items():
+        if not v.is_floating_point() or v.grad is None or kk.endswith("quantiles") or float(v.grad.norm()) == 0.0:
+            continue
+        got = tr.ctx.grads[kk].cpu()
+        errs.append((float((got - v.grad).norm() / v.grad.norm()), kk))
+    errs.sort(reverse=True)
+    dec = [e for e, kk in errs if kk.startswith("decoder.")]
+    assert len(dec) > 100 and max(dec) < 5e-2 and sorted(dec)[len(dec) // 2] < 1e-2, errs[:8]
+    assert errs[0][0] < 8e-2, errs[:8]
