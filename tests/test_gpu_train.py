@@ -357,14 +357,17 @@ def _oracle_grads(oracle, sd, x, q, noise, rate_w, lam_mse, forced=None, beta=No
     return out, grads, float(loss)
 
 
-@pytest.mark.parametrize("config,q,beta", [("crdr_stage_2.yaml", 2.0, None), ("crdr_stage_2.yaml", 0.5, None), ("crdr.yaml", 1.5, 2.56)],
-                         ids=["stage2_q2", "stage2_q0.5", "beta_cond_q1.5"])
-def test_training_step_gradients_match_oracle_autograd(oracle, config, q, beta):
+@pytest.mark.parametrize("config,q,beta,shape", [("crdr_stage_2.yaml", 2.0, None, (2, 128, 128)), ("crdr_stage_2.yaml", 0.5, None, (2, 128, 128)),
+                                                 ("crdr.yaml", 1.5, 2.56, (2, 128, 128)), ("crdr_stage_2.yaml", 3.0, None, (3, 192, 320))],
+                         ids=["stage2_q2", "stage2_q0.5", "beta_cond_q1.5", "stage2_ragged_3x192x320"])
+def test_training_step_gradients_match_oracle_autograd(oracle, config, q, beta, shape):
+    """(the last case: a batch and crop whose pixel grids are not powers of two -- 12 x 20 latents, 3 x 5 hyper-latents --
+    so the wgrad kernel's pixel blocks run past the tensors and rely on the TMA zero fill)"""
     import fixtures
     from crdr_b200.train import CodecTrainer
     model, sd = fixtures.build_model(seed=5, calibrated=True, config=config)
     tr = CodecTrainer(model, device=DEV)
-    n, h, w = 2, 128, 128
+    n, h, w = shape
     x = fixtures.image(n, h, w, seed=21)
     g = torch.Generator().manual_seed(77)
     noise = {"z": torch.rand(n, 192, h // 64, w // 64, generator=g) - 0.5, "y": torch.rand(n, 320, h // 16, w // 16, generator=g) - 0.5}
