@@ -164,8 +164,8 @@ class EntropyBottleneck(_CoderTables):
 
 @ENTROPYMODEL_REGISTRY.register()
 class SteEntropyBottleneck(EntropyBottleneck):
-    """Reference name (entropy_bottleneck.py:18-30); evaluation behaviour is identical, the STE / noise
-    training path is not lowered yet."""
+    """Reference name (entropy_bottleneck.py:18-30); evaluation behaviour is identical.  The noise likelihood / STE code of
+    training mode are values of crdr_eb_quantize with a noise tensor; their gradients are taken in train.CodecTrainer."""
 
 
 @ENTROPYMODEL_REGISTRY.register()

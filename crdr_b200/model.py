@@ -422,8 +422,9 @@ class _CharmModelCore(_CodecModelBase):
     def forward(self, real_images, rate_ind, beta, is_train=True, noise=None):
         """Forward VALUES of the reference's forward (beta_cond_interpca_hyperprior_charm_model.py:34-78).  Training mode
         (is_train=True): likelihoods of the noise-perturbed latents (``noise`` = draw_noise(...) or the caller's tensors),
-        straight-through rounded codes, quantised q_likelihoods, unclamped reconstruction.  No autograd graph is built:
-        the backward pass (dgrad / wgrad kernels) is not part of this package yet."""
+        straight-through rounded codes, quantised q_likelihoods, unclamped reconstruction.  No autograd graph is built
+        here: the optimisation step (this forward on taped engines + the backward kernels + Adam) is train.CodecTrainer /
+        trainers.RateDistortionTrainer, which keep their own device copy of the parameters."""
         eng = self.engine()
         q = self._q(rate_ind)
         x = self._to_device(real_images)
