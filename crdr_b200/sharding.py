@@ -96,6 +96,28 @@ def allreduce_mean_flat(flat, bucket_bytes=64 << 20, group=None):
     return len(handles)
 
 
+def allreduce_sum_async(flat, ranges, bucket_bytes=64 << 20, group=None):
+    """Start the bucketed sum over the ranks of the element ranges [(lo, hi), ...] of a flat buffer and return the work
+    handles: the collective runs on the backend's own stream, ordered after what the current stream has enqueued so far,
+    so kernels launched afterwards (the rest of the backward pass) overlap it.  [] for a single process."""
+    dist, world = _group_world(group)
+    if world == 1:
+        return []
+    per = max(1, bucket_bytes // flat.element_size())
+    return [dist.all_reduce(flat[o:min(o + per, hi)], op=dist.ReduceOp.SUM, group=group, async_op=True)
+            for lo, hi in ranges for o in range(lo, hi, per)]
+
+
+def allreduce_finish_mean(handles, flat, group=None):
+    """Wait for the handles of allreduce_sum_async (together covering the whole buffer) and turn the sums into means."""
+    dist, world = _group_world(group)
+    if world == 1:
+        return
+    for h in handles:
+        h.wait()
+    flat.mul_(1.0 / world)
+
+
 def allreduce_mean_scalar(t, group=None):
     """Mean over the ranks of a small tensor, in place and without a host round trip (the HiFiC rate switch's qbpp)."""
     dist, world = _group_world(group)

@@ -200,9 +200,11 @@ class TrainContext:
         which, o, n = self._gain_by_ptr[vec.data_ptr()]
         return self.gain_grad[which][o:o + n]
 
-    def finish_gain_grads(self, inv_scale):
+    def finish_gain_grads(self, inv_scale, which_sets=("encoder", "decoder")):
         """d(scale), d(shift) sums -> interp_ca_list.{i}.weight / .bias gradients (softplus and the level lerp)."""
         for which, (engine, l, r, alpha, lerped) in self.gain_state.items():
+            if which not in which_sets:
+                continue
             gg = self.gain_grad[which]
             o = 0
             for i in range(len(engine.gains)):
@@ -288,6 +290,16 @@ class CodecTrainer:
         self._grads = {}     # activation storage pointer -> gradient Act of the current step
         self._keep = []
         self._warm, self._graphs, self._pool = set(), {}, None
+        # flat-buffer ranges whose gradients are final after phase 1 of the backward (decoder.*, context_model.*) and the rest
+        early = [i for i, k in enumerate(ctx.names) if k.startswith(("decoder.", "context_model."))]
+        ends = ctx.offsets[1:] + [ctx.total]
+        self._early_ranges, self._late_ranges, pos = [], [], 0
+        for i in range(len(ctx.names)):
+            target = self._early_ranges if i in set(early) else self._late_ranges
+            if target and target[-1][1] == ctx.offsets[i]:
+                target[-1] = (target[-1][0], ends[i])
+            else:
+                target.append((ctx.offsets[i], ends[i]))
         self.use_graphs = True
         bw.workspace(256 << 20, self.device)   # split-K partial sums / column sums: sized once (no growth inside a capture)
         # parameter-gradient work (wgrad + split-K reduction, bias / gain column sums) hangs off the critical chain
@@ -459,10 +471,14 @@ class CodecTrainer:
             main.wait_event(ev)
         self._side_used.clear()
 
-    def backward(self, images, out, rate_weight=None, image_grad=None, image_grad_scale=1.0):
+    def backward(self, images, out, rate_weight=None, image_grad=None, image_grad_scale=1.0, phase=None):
         """Reverse sweep over the tape; fills ctx.flat_g (unscaled fp32 gradients of mean-reduced losses).  rate_weight:
         a float overrides the device-resident weight the last losses() call decided.  image_grad: an extra loss-scaled
-        gradient w.r.t. the reconstruction as 8-channel NHWC planes (the adversarial term's path through a discriminator)."""
+        gradient w.r.t. the reconstruction as 8-channel NHWC planes (the adversarial term's path through a discriminator).
+        phase: None = the whole sweep; 1 = loss roots, g_s and ChARM (afterwards the gradients of `decoder.*` and
+        `context_model.*`, 90 % of the parameters, are final: their all-reduce can start); 2 = h_s, the factorised prior, h_a, g_a."""
+        if phase == 2:
+            return self._sweep(self._pending, ("encoder",), 1.0 / self.loss_scale)
         if rate_weight is not None:
             self._rate_w.fill_(float(rate_weight))
         ctx, L, st = self.ctx, nv.lib(), nv.stream_handle()
@@ -484,7 +500,17 @@ class CodecTrainer:
                                                   g_img.hi.data_ptr(), 16, st))
         self._rate_coef = S / (math.log(2.0) * n * h * w)   # d(mean bpp) / d(-ln L) per element; x the device-resident rate weight
         tape, ctx.tape = ctx.tape, None
-        for rec in reversed(tape):
+        recs = list(reversed(tape))
+        if phase is None:
+            return self._sweep(recs, ("encoder", "decoder"), inv)
+        hs_cfg = self.hs.mu[0].cfg
+        cut = next((i for i, r in enumerate(recs) if r[0] == "conv" and r[1].cfg is hs_cfg), len(recs))
+        self._pending = recs[cut:]
+        self._sweep(recs[:cut], ("decoder",), inv)
+
+    def _sweep(self, recs, gain_sets, inv):
+        ctx = self.ctx
+        for rec in recs:
             kind = rec[0]
             if kind == "conv":
                 self._conv_backward(*rec[1:])
@@ -499,8 +525,9 @@ class CodecTrainer:
             elif kind == "lrelu":
                 self._lrelu_backward(*rec[1:])
         self._join_sides()
-        ctx.finish_gain_grads(inv)
-        ctx.finish_cond_grads(inv)
+        ctx.finish_gain_grads(inv, gain_sets)
+        if "decoder" in gain_sets:
+            ctx.finish_cond_grads(inv)
 
     def _sums_to(self, partial, blocks, nsums, which, c, target, accumulate=True, scale=None):
         nv.check(nv.lib().crdr_colsum_finish(partial.data_ptr(), blocks, nsums, which, c, target.data_ptr(),
@@ -773,18 +800,19 @@ class CodecTrainer:
         self._out = self.forward(images, q, noise)      # beta: the device scalar set by train_step
         return self._losses_device(images, self._out, q, decide=False)
 
-    def _core_backward(self, images):
-        self.backward(images, self._out)
-        return self.aux_step()
+    def _core_backward(self, images, phase=None):
+        self.backward(images, self._out, phase=phase)
+        return self.aux_step() if phase in (None, 2) else None
 
     def train_step(self, images, q=None, noise=None, generator=None, beta=None):
         """One optimisation step on a batch of [-1, 1] crops (device fp32 NCHW).  Returns the loss dict (device scalars;
         overwritten by the next step of the same shape and quality level when CUDA graphs are on).
 
         The step is ~1 900 small launches whose host enqueue (47 ms) costs several times their device time, so from the
-        second call of a (shape, quality level) on, the step replays three captured CUDA graphs -- F = forward + loss
-        values, B = backward, O = clip + Adam + re-packing -- with the two data-parallel exchanges (the qbpp mean of the
-        rate switch, the gradient all-reduce) between them on the same stream."""
+        second call of a (shape, quality level) on, the step replays four captured CUDA graphs -- F = forward + loss
+        values, B1 = backward of g_s and ChARM, B2 = backward of h_s / h_a / g_a, O = clip + Adam + re-packing -- with the
+        data-parallel exchanges between them: the qbpp mean of the rate switch after F, the all-reduce of the decoder and
+        context-model gradients (90 % of the 510 MB) started after B1 so that it overlaps B2, the rest after B2."""
         from .sharding import broadcast_from_rank0
         n, _, h, w = images.shape
         if q is None:
@@ -824,26 +852,32 @@ class CodecTrainer:
             st_in = dict(x=torch.empty_like(images), z=torch.empty_like(noise["z"]), y=torch.empty_like(noise["y"]))
             st_in["x"].copy_(images); st_in["z"].copy_(noise["z"]); st_in["y"].copy_(noise["y"])
             torch.cuda.current_stream().synchronize()
-            gf, gb, go = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            gf, gb, gb2, go = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             counts, l0 = [], nv.LAUNCH_COUNT[0]
             with torch.cuda.graph(gf, pool=self._pool):
                 ld = self._core_forward(st_in["x"], q, {"z": st_in["z"], "y": st_in["y"]})
             with torch.cuda.graph(gb, pool=self._pool):
-                ld["aux"] = self._core_backward(st_in["x"])
+                self._core_backward(st_in["x"], phase=1)
+            with torch.cuda.graph(gb2, pool=self._pool):
+                ld["aux"] = self._core_backward(st_in["x"], phase=2)
             count = self.step_count
             with torch.cuda.graph(go, pool=self._pool):
                 self.optimizer_step()
             self.step_count = count        # the capture itself executes nothing
-            hit = self._graphs[key] = (gf, gb, go, st_in, ld, nv.LAUNCH_COUNT[0] - l0, int(q) if self.uses_rate else 0)
-        gf, gb, go, st_in, ld, launches, level = hit
+            hit = self._graphs[key] = (gf, gb, gb2, go, st_in, ld, nv.LAUNCH_COUNT[0] - l0, int(q) if self.uses_rate else 0)
+        gf, gb, gb2, go, st_in, ld, launches, level = hit
         st_in["x"].copy_(images, non_blocking=True)
         st_in["z"].copy_(noise["z"], non_blocking=True)
         st_in["y"].copy_(noise["y"], non_blocking=True)
         gf.replay()
         self._level = level
         self._decide_rate()
-        gb.replay()
-        self.all_reduce_grads()
+        from .sharding import allreduce_finish_mean, allreduce_sum_async
+        gb.replay()                 # loss roots, g_s, ChARM: decoder.* and context_model.* gradients are final ...
+        handles = allreduce_sum_async(self.ctx.flat_g, self._early_ranges, 64 << 20, self.pg)   # ... and travel while ...
+        gb2.replay()                # ... h_s, the factorised prior, h_a and g_a run
+        handles += allreduce_sum_async(self.ctx.flat_g, self._late_ranges, 64 << 20, self.pg)
+        allreduce_finish_mean(handles, self.ctx.flat_g, self.pg)
         go.replay()
         self.step_count += 1
         nv.LAUNCH_COUNT[0] += launches

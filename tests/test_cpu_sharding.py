@@ -50,6 +50,12 @@ def _train_worker(rank, world, port, tmp):
     buckets = sharding.allreduce_mean_flat(g, bucket_bytes=64 * 1024)
     want = torch.arange(n, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
     assert buckets == -(-n * 4 // (64 * 1024)) and torch.allclose(g, want, rtol=1e-6)
+    # the two-phase form the training step uses: some ranges start early (overlapping the rest of the backward), the rest later
+    g2 = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    early = sharding.allreduce_sum_async(g2, [(1000, 40_000), (60_000, n)], bucket_bytes=64 * 1024)
+    late = sharding.allreduce_sum_async(g2, [(0, 1000), (40_000, 60_000)], bucket_bytes=64 * 1024)
+    sharding.allreduce_finish_mean(early + late, g2)
+    assert torch.allclose(g2, want, rtol=1e-6)
     q = torch.tensor([3.0 if rank == 0 else -1.0])
     assert sharding.broadcast_from_rank0(q).item() == 3.0
     qbpp = torch.tensor([0.1 * (rank + 1)])
