@@ -17,8 +17,8 @@ The factorised prior over z (18 k elements per Kodak image, 58 parameters per ch
 autograd on the device: it is 0.003 % of the step's arithmetic and not worth a kernel.
 
 Scope: every ChARM model of the reference (stage 1, stage 2 = BASELINE config 5, and the beta-conditioned crdr.yaml model)
-with the rate + MSE losses.  Not lowered: LPIPS (pretrained AlexNet weights are not available offline) and the stage-3 GAN
-terms (discriminators), i.e. the beta * (perceptual + adversarial) part of
+with the rate + MSE losses (+ the weight-free stand-in of the LPIPS term: pretrained AlexNet weights are not available
+offline); GanCodecTrainer below adds the stage-3 discriminators and the beta * (perceptual + adversarial) terms of
 multirate_hr_rgan_beta_cond_rate_distortion_trainer.py:62-66.
 """
 import ctypes as C
@@ -242,7 +242,8 @@ class CodecTrainer:
 
     def __init__(self, model, device="cuda:0", lr=1e-4, betas=(0.9, 0.999), eps=1e-8, clip_max_norm=None,
                  lambda_mse=150.0, rate_lambda_a=(3.6, 1.8, 0.8, 0.4, 0.1), rate_lambda_b=2.0 ** -6,
-                 target_rate=(0.08, 0.16, 0.36, 0.72, 1.2), aux_lr=1e-3, loss_scale=None, process_group=None):
+                 target_rate=(0.08, 0.16, 0.36, 0.72, 1.2), aux_lr=1e-3, loss_scale=None, process_group=None,
+                 perceptual_weight=0.0):
         self.model, self.device = model, torch.device(device)
         # programmatic dependent launch between consecutive convolutions: the next launch's prologue overlaps the previous
         # one's tail; neutral for the full-GPU inference launches, -3.7 % on the small launches of a training step
@@ -267,6 +268,11 @@ class CodecTrainer:
         self.lr, self.betas, self.eps, self.clip = lr, betas, eps, clip_max_norm
         self.aux_lr = aux_lr
         self.lambda_mse = float(lambda_mse)
+        # LPIPSLoss (perceptual_loss.py:11-31) needs pretrained AlexNet weights that are not available offline.  What can be
+        # lowered is the weight-free stand-in the oracle stack uses in its place (oracle/shims/lpips.py: the per-image mean
+        # squared difference on the [-1, 1] scale), i.e. a second squared-error term of this weight (0: term absent).
+        self.perceptual_weight = float(perceptual_weight)
+        self._perceptual_factor = 1.0      # stage 3 multiplies the perceptual term by beta
         as_cfg = lambda v: list(v) if isinstance(v, (list, tuple)) else float(v)     # per quality level, or one value
         self.lambda_a, self.lambda_b, self.target = as_cfg(rate_lambda_a), as_cfg(rate_lambda_b), as_cfg(target_rate)
         self.loss_scale = None if loss_scale is None else float(loss_scale)   # None: from the batch's pixel count
@@ -383,7 +389,10 @@ class CodecTrainer:
         if decide:
             self._decide_rate()
         mse = torch.mean(((images + 1) / 2 - (out["fake_images"] + 1) / 2) ** 2)
-        return dict(bpp_mean=bpp.mean(), distortion=self.lambda_mse * mse, bpp=bpp.mean(), qbpp=qbpp.mean())
+        ld = dict(bpp_mean=bpp.mean(), distortion=self.lambda_mse * mse, bpp=bpp.mean(), qbpp=qbpp.mean())
+        if self.perceptual_weight:
+            ld["perceptual"] = self.perceptual_weight * 4.0 * mse      # mean (x - y)^2 on [-1, 1] = 4 x the 0..1 MSE
+        return ld
 
     def _decide_rate(self):
         """HiFiC rate switch on the mean quantised bpp of the GLOBAL batch (all ranks), on the device."""
@@ -492,7 +501,7 @@ class CodecTrainer:
         # ---- loss roots --------------------------------------------------------------------------------------------
         fp = out["fake_packed"]
         g_img = self._grad(fp.data_ptr(), shape=(n, h // 2, w // 2, 16))
-        coef_mse = S * self.lambda_mse * 2.0 * 0.25 / (n * 3 * h * w)
+        coef_mse = S * (self.lambda_mse * 2.0 * 0.25 + self.perceptual_weight * self._perceptual_factor * 2.0) / (n * 3 * h * w)
         nv.check(L.crdr_mse_backward(fp.data_ptr(), fp.shape[-1], images.data_ptr(), n, h // 2, w // 2, h, w, coef_mse,
                                      g_img.hi.data_ptr(), 16, st))
         if image_grad is not None:
@@ -983,6 +992,7 @@ class GanCodecTrainer(CodecTrainer):
         out = self.forward(images, q, noise, beta=beta)
         fake = out["fake_images"]
         ld = self._losses_device(images, out, q)
+        self._perceptual_factor = float(beta)          # l_total = dist + rate + beta * (perceptual + adv)
         real_d, _, _, _ = self.d_forward(k, rel, tape=False)
         fake_g, dtape, dlogits, dplanes = self.d_forward(k, fake, tape=True, input_grad=True)
         with torch.enable_grad():

@@ -40,7 +40,11 @@ def _loss_kwargs(opt):
     if g["type"] != "Adam":
         raise NotImplementedError("only Adam is lowered")
     as_list = lambda v: list(v) if isinstance(v, (list, tuple)) else float(v)
+    percep = loss.get("perceptual_loss")
+    if percep and (percep["type"] != "LPIPSLoss" or percep.get("range_norm", False)):
+        raise NotImplementedError("only LPIPSLoss on [-1, 1] inputs is mapped (to its weight-free stand-in)")
     return dict(lr=float(g["lr"]), clip_max_norm=optim.get("clip_max_norm"), lambda_mse=float(dist["loss_weight"]),
+                perceptual_weight=float(percep["loss_weight"]) if percep else 0.0,
                 rate_lambda_a=as_list(rate["lambda_A"]), rate_lambda_b=as_list(rate["lambda_B"]), target_rate=as_list(rate["target_rate"]),
                 aux_lr=float(optim.get("aux_optimizer", {}).get("lr", 1e-3)))
 
@@ -52,7 +56,8 @@ class _TrainerBase:
         if opt.get("pretrained_weight_path") and os.path.exists(opt["pretrained_weight_path"]):
             self.comp_model.load_learned_weight(opt["pretrained_weight_path"])
         if opt["loss"].get("perceptual_loss"):
-            self.logger.warning("perceptual_loss (LPIPS) is not lowered on this path: training proceeds without it")
+            self.logger.warning("perceptual_loss: LPIPS needs pretrained AlexNet weights that are not available here; the weight-free "
+                                "stand-in of the oracle stack (per-image mean squared difference, oracle/shims/lpips.py) is used")
         self.milestones = list(opt["optim"].get("g_scheduler", {}).get("milestones", []))
         self.gamma = float(opt["optim"].get("g_scheduler", {}).get("gamma", 0.1))
         self.base_lr = float(opt["optim"]["g_optimizer"]["lr"])

@@ -247,7 +247,7 @@ def test_trainer_plugins_and_loss_config():
     o2 = BaseConfig.fromfile(os.path.join(ROOT, "config", "crdr_stage_2.yaml"), device="cpu", is_train=True)
     k2 = _loss_kwargs(o2)
     assert k2["rate_lambda_a"] == [3.6, 1.8, 0.8, 0.4, 0.1] and k2["rate_lambda_b"] == 2.0 ** -6 and k2["lambda_mse"] == 150.0
-    assert k2["clip_max_norm"] == 1.0 and k2["lr"] == 1e-4 and k2["aux_lr"] == 1e-3
+    assert k2["clip_max_norm"] == 1.0 and k2["lr"] == 1e-4 and k2["aux_lr"] == 1e-3 and k2["perceptual_weight"] == 1.0
     o3 = BaseConfig.fromfile(os.path.join(ROOT, "config", "crdr_stage_3.yaml"), device="cpu", is_train=True)
     assert o3["trainer"]["type"] == "MultirateBetaCondHrrGanRateDistortionTrainer" and _loss_kwargs(o3)["target_rate"] == [0.0] * 5
     d = build_discriminator(dict(o3["discriminator"]))

@@ -335,7 +335,7 @@ def test_mse_backward_adam_and_norm():
 # The whole training step against autograd through the oracle (= the reference's forward, pinned in
 # tests/test_oracle_vs_reference.py): same weights, same crops, same noise, same losses.
 # ----------------------------------------------------------------------------------------------------------------------
-def _oracle_grads(oracle, sd, x, q, noise, rate_w, lam_mse, forced=None, beta=None):
+def _oracle_grads(oracle, sd, x, q, noise, rate_w, lam_mse, forced=None, beta=None, percep=0.0):
     """Autograd gradients of rate_w * mean(bpp) + lam_mse * MSE_01 through oracle.forward_train (CPU fp32)."""
     sdr = {k: (v.detach().clone().float().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
     eb, gc = oracle.entropy_models(sdr)
@@ -349,6 +349,9 @@ def _oracle_grads(oracle, sd, x, q, noise, rate_w, lam_mse, forced=None, beta=No
         bpp = (bits(out["likelihoods"]["y"]) + bits(out["likelihoods"]["z"])) / (h * w)
         mse = torch.mean(((x + 1) / 2 - (out["fake_images"] + 1) / 2) ** 2)
         loss = rate_w * bpp.mean() + lam_mse * mse
+        if percep:
+            import lpips          # the oracle stack's weight-free stand-in (oracle/shims/lpips.py), as LPIPSLoss calls it
+            loss = loss + percep * torch.mean(lpips.LPIPS(net="alex")(x, out["fake_images"]))
         loss.backward()
     grads = {k: v.grad for k, v in sdr.items() if v.is_floating_point() and v.grad is not None}
     for k, p in eb.named_parameters():
@@ -366,7 +369,8 @@ def test_training_step_gradients_match_oracle_autograd(oracle, config, q, beta, 
     import fixtures
     from crdr_b200.train import CodecTrainer
     model, sd = fixtures.build_model(seed=5, calibrated=True, config=config)
-    tr = CodecTrainer(model, device=DEV)
+    percep = 1.0 if shape[0] == 3 else 0.0       # one case carries crdr_stage_2.yaml's perceptual term (stand-in, see train.py)
+    tr = CodecTrainer(model, device=DEV, perceptual_weight=percep)
     n, h, w = shape
     x = fixtures.image(n, h, w, seed=21)
     g = torch.Generator().manual_seed(77)
@@ -382,10 +386,10 @@ def test_training_step_gradients_match_oracle_autograd(oracle, config, q, beta, 
     free_out = oracle.forward_train(sd, x, q, beta, noise, *oracle.entropy_models(sd))
     flips = (free_out["quantized_code"]["y"] - out["yhat32"].permute(0, 3, 1, 2).cpu()).abs() > 0.5
     assert float(flips.float().mean()) < 1e-3
-    ref_out, ref, ref_loss = _oracle_grads(oracle, sd, x, q, noise, rate_w, 150.0, forced=out["y_sym"].cpu(), beta=beta)
+    ref_out, ref, ref_loss = _oracle_grads(oracle, sd, x, q, noise, rate_w, 150.0, forced=out["y_sym"].cpu(), beta=beta, percep=percep)
     # forward values first (training-mode parity is tested in test_gpu_codec.py; here: the taped engines agree too)
     assert _rel(out["fake_images"].cpu(), ref_out["fake_images"].detach()) < 2e-3
-    assert abs(float(ld["rate"] + ld["distortion"]) - ref_loss) / ref_loss < 1e-3 or ld["rate_weight"] != rate_w
+    assert abs(float(ld["rate"] + ld["distortion"] + ld.get("perceptual", 0.0)) - ref_loss) / ref_loss < 1e-3 or ld["rate_weight"] != rate_w
     tr.backward(xd, out, rate_w)
     torch.cuda.synchronize()
     got = {k: v.detach().cpu() for k, v in tr.ctx.grads.items()}
