@@ -502,7 +502,10 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
                             int64_t count, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
                             const float* __restrict__ gscale_ptr, float gscale, const float* __restrict__ hyper) {
   const float gs = gscale_ptr ? gscale * gscale_ptr[0] : gscale;
-  if (hyper) { lr = hyper[0]; bc1 = hyper[1]; bc2_sqrt = hyper[2]; }   // device-resident schedule (graph replay)
+  if (hyper) {   // device-resident schedule (graph replay); hyper[3] != 0: this step is skipped (non-finite / huge loss)
+    if (hyper[3] != 0.f) return;
+    lr = hyper[0]; bc1 = hyper[1]; bc2_sqrt = hyper[2];
+  }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = g[i] * gs;
     const float mi = fmaf(b1, m[i], (1.f - b1) * gi);

@@ -288,6 +288,8 @@ class CodecTrainer:
         self._rate_w = torch.zeros(1, **f32)
         self._qbpp = torch.zeros(1, **f32)
         self._level = 0
+        self._loss_vals = torch.zeros(2, **f32)          # mean bpp | weighted distortion (+ perceptual) of the current step
+        self._skip = torch.zeros(1, **f32)               # 1: loss is nan / inf / > 10000 -> no update (base_trainer.py:228-238)
         self._lr = torch.tensor([lr, aux_lr], **f32)
         self._step_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._hyper = torch.zeros(2, 4, **f32)           # rows: main / aux; columns: lr, 1 - b1^t, sqrt(1 - b2^t), unused
@@ -392,6 +394,9 @@ class CodecTrainer:
         ld = dict(bpp_mean=bpp.mean(), distortion=self.lambda_mse * mse, bpp=bpp.mean(), qbpp=qbpp.mean())
         if self.perceptual_weight:
             ld["perceptual"] = self.perceptual_weight * 4.0 * mse      # mean (x - y)^2 on [-1, 1] = 4 x the 0..1 MSE
+        self._loss_vals.copy_(torch.stack([bpp.mean(), ld["distortion"] + ld.get("perceptual", 0.0)]))
+        if decide:
+            self._decide_skip()
         return ld
 
     def _decide_rate(self):
@@ -402,7 +407,22 @@ class CodecTrainer:
         lam_a, lam_b, tgt = pick(self.lambda_a), pick(self.lambda_b), pick(self.target)
         self._rate_w.copy_(torch.where(self._qbpp > tgt, torch.full_like(self._rate_w, lam_a), torch.full_like(self._rate_w, lam_b)))
 
+    def _decide_skip(self):
+        """check_loss_nan_inf (base_trainer.py:228-238) on the device, after the rate weight is known: a nan / inf / > 10000
+        total loss makes the optimiser kernels of this step no-ops (on every rank: the flag is max-reduced)."""
+        total = self._rate_w * self._loss_vals[0] + self._loss_vals[1]
+        bad = (~torch.isfinite(total)) | (total > 10000.0)
+        self._skip.copy_(bad.to(torch.float32))
+        if self._distributed():
+            import torch.distributed as dist
+            dist.all_reduce(self._skip, op=dist.ReduceOp.MAX, group=self.pg)
+
+    def _distributed(self):
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.pg) > 1
+
     def _finish_losses(self, ld):
+        ld["skipped"] = self._skip.reshape(())
         ld["rate_weight"] = self._rate_w.reshape(())
         ld["rate"] = ld["rate_weight"] * ld.pop("bpp_mean")
         return ld
@@ -786,11 +806,12 @@ class CodecTrainer:
     def optimizer_step(self):
         ctx, L, st = self.ctx, nv.lib(), nv.stream_handle()
         self.step_count += 1
-        self._step_dev += 1
+        self._step_dev += 1.0 - self._skip.to(torch.float64)     # a skipped step does not advance Adam's bias correction
         b1, b2 = self.betas
         bc = torch.stack([1.0 - b1 ** self._step_dev, torch.sqrt(1.0 - b2 ** self._step_dev)], dim=1).to(torch.float32)   # [1, 2]
         self._hyper[:, 0] = self._lr
         self._hyper[:, 1:3] = bc
+        self._hyper[:, 3] = self._skip
         clip_ptr = None
         if self.clip:
             nv.check(L.crdr_sum_squares(ctx.flat_g.data_ptr(), ctx.n_main_padded, self._sumsq.data_ptr(), self._sumsq[1024:].data_ptr(), st))
@@ -842,6 +863,7 @@ class CodecTrainer:
             for attempt in range(4):
                 ld = self._core_forward(images, q, noise)
                 self._decide_rate()
+                self._decide_skip()
                 ld["aux"] = self._core_backward(images)
                 try:
                     nv.status_check()       # before the update: a step whose gradients were clamped is redone
@@ -881,6 +903,7 @@ class CodecTrainer:
         gf.replay()
         self._level = level
         self._decide_rate()
+        self._decide_skip()
         from .sharding import allreduce_finish_mean, allreduce_sum_async
         gb.replay()                 # loss roots, g_s, ChARM: decoder.* and context_model.* gradients are final ...
         handles = allreduce_sum_async(self.ctx.flat_g, self._early_ranges, 64 << 20, self.pg)   # ... and travel while ...
@@ -1029,6 +1052,9 @@ class GanCodecTrainer(CodecTrainer):
             self.ctx.tape = None
         # ================================================================== train G
         ld, adv, fake = self.generator_backward(images, q, noise, beta, rel)
+        if float(self._skip.item()) > 0:      # nan / inf / huge loss: the reference returns before any update (trainer :68-71)
+            nv.status_check()
+            return self._finish_losses(ld)
         ld["aux"] = self.aux_step()
         self.all_reduce_grads()
         self.optimizer_step()

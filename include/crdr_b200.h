@@ -419,8 +419,9 @@ int crdr_planes_grad_to_phases(const void* g8, int32_t g8_cs, int32_t n, int32_t
                                int32_t g_cs, void* stream);
 
 /* torch.optim.Adam step on flat fp32 buffers; the gradient is multiplied by gscale (* gscale_ptr[0] when given: the
- * clip coefficient computed on the device).  step >= 1, or `hyper` = device float[3] {lr, 1 - beta1^step, sqrt(1 - beta2^step)}
- * overriding lr / step (a CUDA-graph replay reads the schedule from device memory). */
+ * clip coefficient computed on the device).  step >= 1, or `hyper` = device float[4] {lr, 1 - beta1^step, sqrt(1 - beta2^step),
+ * skip} overriding lr / step (a CUDA-graph replay reads the schedule from device memory); skip != 0 leaves everything
+ * untouched (the reference skips the update when the loss is nan / inf / huge, base_trainer.py:228-238). */
 int crdr_adam_step(float* p, const float* g, float* m, float* v, int64_t count, float lr, float beta1, float beta2, float eps,
                    int32_t step, const float* gscale_ptr, float gscale, const float* hyper, void* stream);
 /* out[0] = sum x^2 (fixed order); partial: 1024 floats of scratch. */

@@ -602,3 +602,23 @@ def test_generator_step_gradients_with_adversarial_term_match_autograd(oracle):
     dec = [e for e, kk in errs if kk.startswith("decoder.")]
     assert len(dec) > 100 and max(dec) < 5e-2 and sorted(dec)[len(dec) // 2] < 1e-2, errs[:8]
     assert errs[0][0] < 8e-2, errs[:8]
+
+
+def test_huge_loss_skips_the_update():
+    """check_loss_nan_inf (base_trainer.py:228-238): a total loss above 10000 leaves parameters and Adam state untouched, in the
+    eager step and in the graph replay; a normal step afterwards updates again."""
+    import fixtures
+    from crdr_b200.train import CodecTrainer
+    model, _ = fixtures.build_model(seed=6, calibrated=False, config="crdr_stage_2.yaml")
+    tr = CodecTrainer(model, device=DEV, lr=1e-4, clip_max_norm=1.0)
+    x = fixtures.image(2, 128, 128, seed=22).to(DEV).contiguous()
+    p0 = tr.ctx.flat_p.clone()
+    tr.lambda_mse = 1e7
+    for _ in range(3):                       # eager, capture, replay
+        ld = tr.train_step(x, q=2.0)
+        assert float(ld["skipped"]) == 1.0
+    assert torch.equal(tr.ctx.flat_p, p0) and float(tr.m.abs().max()) == 0.0 and float(tr._step_dev) == 0.0
+    tr.lambda_mse = 150.0
+    tr._graphs.clear(); tr._warm.clear()     # the loss weight is baked into the captured launch parameters
+    ld = tr.train_step(x, q=2.0)
+    assert float(ld["skipped"]) == 0.0 and not torch.equal(tr.ctx.flat_p, p0) and float(tr._step_dev) == 1.0
