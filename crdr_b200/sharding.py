@@ -24,6 +24,17 @@ def shard(items, rank, world):
     return list(items[rank::world])
 
 
+def shard_balanced(items, sizes, rank, world, stride=64):
+    """"sort by padded area for balance".  items with their (height, width): sorted by padded area (descending),
+    then shape, then name; rank r takes positions r, r+W, ... of that order, so every rank gets the same mix of large and
+    small images and same-shaped images stay adjacent (they are batched into one launch).  Deterministic on every rank."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    pad = lambda v: -(-v // stride) * stride
+    order = sorted(range(len(items)), key=lambda i: (-pad(sizes[i][0]) * pad(sizes[i][1]), sizes[i], str(items[i])))
+    return [items[i] for i in order[rank::world]]
+
+
 def same_shape_batches(named_images, batch):
     """Group consecutive (name, tensor[1,3,H,W]) pairs of identical shape into lists of at most `batch`."""
     group = []

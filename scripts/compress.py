@@ -70,7 +70,12 @@ def main():
         opt.device = f"cuda:{int(os.environ.get('LOCAL_RANK', rank))}"
     os.makedirs(opt.save_dir, exist_ok=True)
     paths = sorted(glob(os.path.join(opt.img_dir, "*.png")))
-    mine = sharding.shard(paths, rank, world)
+    from PIL import Image
+    sizes = []
+    for p in paths:                     # header read only: balances the ranks by padded area and keeps equal shapes adjacent
+        with Image.open(p) as im:
+            sizes.append((im.height, im.width))
+    mine = sharding.shard_balanced(paths, sizes, rank, world)
 
     model = build_comp_model(opt)
     model.load_learned_weight(ckpt_path=opt.model_path)

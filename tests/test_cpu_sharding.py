@@ -93,6 +93,26 @@ def test_shard_partition_properties():
     assert [[n for n, _ in g] for g in groups] == [["a", "b"], ["c"], ["d"], ["e"]]
 
 
+def test_shard_balanced_by_padded_area():
+    from crdr_b200 import sharding
+    names = [f"i{k:02d}.png" for k in range(12)]
+    sizes = [(2160, 3840)] * 2 + [(1365, 2048)] * 4 + [(512, 768)] * 6
+    import random
+    perm = list(range(12))
+    random.Random(3).shuffle(perm)
+    names_p, sizes_p = [names[i] for i in perm], [sizes[i] for i in perm]
+    pad = lambda v: -(-v // 64) * 64
+    area = {n: pad(s[0]) * pad(s[1]) for n, s in zip(names, sizes)}
+    for world in (1, 2, 4):
+        parts = [sharding.shard_balanced(names_p, sizes_p, r, world) for r in range(world)]
+        assert sorted(x for p in parts for x in p) == names                     # a partition
+        loads = [sum(area[n] for n in p) for p in parts]
+        assert max(loads) - min(loads) <= max(area.values())                    # balanced to within one image
+        for p in parts:                                                         # equal shapes adjacent on every rank
+            shapes = [sizes[names.index(n)] for n in p]
+            assert shapes == sorted(shapes, key=lambda s: -pad(s[0]) * pad(s[1]))
+
+
 def test_gather_rows_file_fallback(tmp_path):
     from crdr_b200 import sharding
     import threading
