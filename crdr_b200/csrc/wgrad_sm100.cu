@@ -16,6 +16,12 @@
 // blocks); partial sums go to an fp32 workspace and wgrad_reduce_kernel adds the splits in a fixed order (deterministic,
 // no atomics) while scattering into the parameter's own layout.
 //
+// HALO form (stride 1, several taps, enough pixels): one CTA = (group of <= 8 taps, M tile, 64-channel block of B); a K block
+// is an 8 x 8 pixel tile whose halo patch (one TMA box, zero filled outside the image) serves every tap of the group: the B
+// operand of a tap is the same patch seen from a shifted start row with the 8-row K groups one PATCH row apart (the 128B
+// swizzle is a function of the absolute shared-memory address, so any 128-byte start row works), and every tap accumulates
+// into its own 64 TMEM columns.  L2 -> shared-memory traffic per MAC drops 5.6x against one tap per CTA.
+//
 // Warp roles: 0 TMA producer, 1 TMEM allocation + MMA issue, 2-5 epilogue (TMEM -> workspace).
 #include <cstdlib>
 #include <cstring>
@@ -53,6 +59,13 @@ struct alignas(64) WgParams {
   int64_t sa, sb, st;
   int32_t ca, cb, accumulate;
   float scale;
+  // HALO variant (stride 1, several taps): one CTA = (tap group, M tile, 64-channel block of B); a K block is an 8 x 8 pixel
+  // tile whose halo patch (box (64, pw, ph, 1), zero filled outside the image) serves every tap of the group from shared
+  // memory, each tap accumulating into its own 64 TMEM columns
+  CUtensorMap tm_patch;
+  int32_t ph, pw, dh_min, dw_min, group_taps, ngroups, b_blocks;
+  uint32_t patch_bytes;
+  uint32_t tapoff[CRDR_MAX_TAPS];
 };
 
 // MN-major SWIZZLE_128B operand: `lbo` bytes between 64-element atoms along M / N, `sbo` bytes between 8-row K groups
@@ -65,6 +78,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t 
   return d;
 }
 
+template <bool HALO>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_constant__ WgParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full[kWgMaxStages], empty[kWgMaxStages];
@@ -74,15 +88,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int tile = (int)blockIdx.x;
-  const int bt = tile % P.b_tiles;
-  const int at = (tile / P.b_tiles) % P.a_tiles;
-  const int tap = tile / (P.b_tiles * P.a_tiles);
+  const int nbt = HALO ? P.b_blocks : P.b_tiles;
+  const int bt = tile % nbt;
+  const int at = (tile / nbt) % P.a_tiles;
+  const int tap = tile / (nbt * P.a_tiles);                       // HALO: the tap GROUP
+  const int tap0 = HALO ? tap * P.group_taps : tap;
+  const int gtaps = HALO ? min(P.group_taps, P.ntaps - tap0) : 1;
   const int split = (int)blockIdx.y;
   const int kb0 = (int)(((int64_t)split * P.kb_total) / P.splits);
   const int kb1 = (int)(((int64_t)(split + 1) * P.kb_total) / P.splits);
   const int nkb = kb1 - kb0;
-  const int nb = P.nb;
-  const uint32_t stage_bytes = (uint32_t)(2 + nb) * kWgBox;
+  const int nb = HALO ? 1 : P.nb;
+  const uint32_t stage_bytes = HALO ? 2u * kWgBox + P.patch_bytes : (uint32_t)(2 + nb) * kWgBox;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
   if (threadIdx.x == 0) {
@@ -101,8 +118,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       prefetch_tmap(&P.tm_s);
-      prefetch_tmap(&P.tm_b);
-      const int dh = P.dh[tap], dw = P.dw[tap];
+      prefetch_tmap(HALO ? &P.tm_patch : &P.tm_b);
+      const int dh = HALO ? P.dh_min : P.dh[tap], dw = HALO ? P.dw_min : P.dw[tap];
       int s = 0;
       uint32_t par = 1u;
       for (int i = 0; i < nkb; ++i) {
@@ -113,13 +130,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
         const int nn = t / P.kh_blocks;
         mbar_wait(smem_u32(&empty[s]), par, P.status);
         const uint32_t bar = smem_u32(&full[s]);
-        mbar_arrive_expect_tx(bar, stage_bytes);
+        // bytes the TMA actually delivers (the patch slot is rounded up to the swizzle atom, the box is not)
+        mbar_arrive_expect_tx(bar, HALO ? 2u * kWgBox + (uint32_t)(P.ph * P.pw) * 128u : stage_bytes);
         const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
         const int w0 = ww * P.bw, h0 = hh * P.bh, n0 = nn * P.bn;
         tma_load_4d(dst, &P.tm_s, at * 128, w0, h0, n0, bar);
         tma_load_4d(dst + kWgBox, &P.tm_s, at * 128 + 64, w0, h0, n0, bar);
-        for (int j = 0; j < nb; ++j)
-          tma_load_4d(dst + (uint32_t)(2 + j) * kWgBox, &P.tm_b, (bt * nb + j) * 64, w0 * P.stride + dw, h0 * P.stride + dh, n0, bar);
+        if (HALO) {
+          tma_load_4d(dst + 2u * kWgBox, &P.tm_patch, bt * 64, w0 + dw, h0 + dh, n0, bar);
+        } else {
+          for (int j = 0; j < nb; ++j)
+            tma_load_4d(dst + (uint32_t)(2 + j) * kWgBox, &P.tm_b, (bt * nb + j) * 64, w0 * P.stride + dw, h0 * P.stride + dh, n0, bar);
+        }
         if (++s == P.stages) { s = 0; par ^= 1u; }
       }
     }
@@ -128,6 +150,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     const bool elected = elect_one();
     const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)((64 * nb) >> 3) << 17) | ((128u >> 4) << 24);
     const uint64_t desc0 = umma_desc_mn_sw128(0u, kWgBox, 1024u);
+    // HALO: the B operand of a tap is the patch seen from a shifted start row; its 8-row K groups (one tile row of 8 pixels)
+    // are one PATCH row apart.  As for the K-major operands of the convolution kernel, the 128B swizzle is a function of the
+    // absolute shared-memory address, so any 128-byte start row of the 1024-byte aligned patch works.
+    const uint64_t desc_p = umma_desc_mn_sw128(0u, kWgBox, (uint32_t)P.pw * 128u);
+    const uint32_t krow = (uint32_t)P.pw * 256u;                  // two tile rows of the patch = one K16 step
     int s = 0;
     uint32_t par = 0u;
     for (int i = 0; i < nkb; ++i) {
@@ -137,9 +164,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
       const uint64_t a = desc0 + (uint64_t)(st >> 4);
       const uint64_t b = desc0 + (uint64_t)((st + 2u * kWgBox) >> 4);
       if (elected) {
+        if (HALO) {
+          for (int j = 0; j < gtaps; ++j) {
+            const uint32_t pb = st + 2u * kWgBox + P.tapoff[tap0 + j];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // 64 pixels = 4 x K16; 16 K rows = 2048 bytes
-          umma_f16(tmem_base, a + (uint64_t)(k * 128), b + (uint64_t)(k * 128), idesc, (i > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tmem_base + (uint32_t)j * 64u, a + (uint64_t)(k * 128), desc_p + (uint64_t)((pb + (uint32_t)k * krow) >> 4), idesc,
+                       (i > 0 || k > 0) ? 1u : 0u);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // 64 pixels = 4 x K16; 16 K rows = 2048 bytes
+            umma_f16(tmem_base, a + (uint64_t)(k * 128), b + (uint64_t)(k * 128), idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
         umma_commit(smem_u32(&empty[s]));
       }
       __syncwarp();
@@ -153,7 +190,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     const int row = q * 32 + lane;
     mbar_wait(smem_u32(&acc_full), 0u, P.status);
     tc_fence_after();
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int tj = 0; tj < gtaps; ++tj) {
+    const int tap = tap0 + tj;                                      // (shadows the group index: from here on the real tap)
+    const uint32_t lane_addr = lane_base + (HALO ? (uint32_t)tj * 64u : 0u);
     if (P.splits == 1) {
       // direct: out[t*st + a*sa + b*sb] (+)= scale * G   (one writer per element: deterministic)
       const int a = at * 128 + row;
@@ -189,6 +229,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
                              __uint_as_float(r[4 * j + 3]));
       }
     }
+    }   // taps of the group
   }
   tc_fence_before();
   __syncthreads();
@@ -239,13 +280,58 @@ static int pow2_le(int x) { int p = 1; while (p * 2 <= x) p *= 2; return p; }
 struct WgPlan {
   int bw, bh, bn, kw_blocks, kh_blocks, kn_blocks, kb_total;
   int a_tiles, b_tiles, nb, a_pad, b_pad, splits;
+  int halo, ph, pw, dh_min, dw_min, group_taps, ngroups, b_blocks;
 };
+
+static int g_wgrad_halo = -1;   // CRDR_WGRAD_HALO (default 1): 0 forces the one-tap-per-CTA form (bisecting / comparison)
 
 static int wgrad_plan(const crdr_wgrad_desc& d, size_t ws_bytes, WgPlan* pl) {
   if (d.n <= 0 || d.hs <= 0 || d.ws <= 0 || d.hb <= 0 || d.wb <= 0 || d.ca <= 0 || d.cb <= 0 || d.ntaps < 1 ||
       d.ntaps > CRDR_MAX_TAPS || d.stride < 1 || d.stride > 4) {
     set_error("wgrad: bad shape (n=%d hs=%d ws=%d ca=%d cb=%d ntaps=%d stride=%d)", d.n, d.hs, d.ws, d.ca, d.cb, d.ntaps, d.stride);
     return CRDR_ERR_BAD_SHAPE;
+  }
+  if (g_wgrad_halo < 0) { const char* e = getenv("CRDR_WGRAD_HALO"); g_wgrad_halo = e ? atoi(e) : 1; }
+  int dh0 = 127, dh1 = -127, dw0 = 127, dw1 = -127;
+  for (int t = 0; t < d.ntaps; ++t) {
+    dh0 = d.dh[t] < dh0 ? d.dh[t] : dh0; dh1 = d.dh[t] > dh1 ? d.dh[t] : dh1;
+    dw0 = d.dw[t] < dw0 ? d.dw[t] : dw0; dw1 = d.dw[t] > dw1 ? d.dw[t] : dw1;
+  }
+  // Measured (tools/wgrad_bench.py, profiles/wgrad_bench_r02.txt): with >= 128 pixel blocks the halo form is 1.9x faster
+  // (3x3 128->128 on 131 072 pixels: 119 -> 63 us, 615 TFLOP/s; 914 TFLOP/s at eight times the pixels); on the 16 x 16 latent
+  // grids of a training crop (32 pixel blocks) a launch is fixed cost + partial-sum traffic and the wide one-tap tiles win.
+  const int64_t halo_kb = (int64_t)((d.ws + 7) / 8) * ((d.hs + 7) / 8) * d.n;
+  pl->halo = g_wgrad_halo && d.stride == 1 && d.ntaps > 1 && d.hs >= 8 && d.ws >= 8 && dh1 - dh0 <= 8 && dw1 - dw0 <= 8 &&
+             (halo_kb >= 128 || g_wgrad_halo > 1);
+  if (pl->halo) {
+    pl->ph = 8 + dh1 - dh0; pl->pw = 8 + dw1 - dw0; pl->dh_min = dh0; pl->dw_min = dw0;
+    pl->ngroups = (d.ntaps + 7) / 8;
+    pl->group_taps = (d.ntaps + pl->ngroups - 1) / pl->ngroups;
+    pl->ngroups = (d.ntaps + pl->group_taps - 1) / pl->group_taps;
+    pl->bw = 8; pl->bh = 8; pl->bn = 1;
+    pl->kw_blocks = (d.ws + 7) / 8; pl->kh_blocks = (d.hs + 7) / 8; pl->kn_blocks = d.n;
+    const int64_t kbh = (int64_t)pl->kw_blocks * pl->kh_blocks * pl->kn_blocks;
+    if (kbh > (1 << 30)) { set_error("wgrad: too many pixel blocks"); return CRDR_ERR_BAD_SHAPE; }
+    pl->kb_total = (int)kbh;
+    pl->a_tiles = (d.ca + 127) / 128;
+    pl->a_pad = pl->a_tiles * 128;
+    pl->b_blocks = (d.cb + 63) / 64;
+    pl->b_tiles = pl->b_blocks; pl->nb = 1;
+    pl->b_pad = pl->b_blocks * 64;
+    const int64_t tiles = (int64_t)pl->ngroups * pl->a_tiles * pl->b_blocks;
+    static int waves_x2 = -1;   // CRDR_WGRAD_HALO_WAVES2: CTAs per launch in half waves of 148 (tuning knob)
+    if (waves_x2 < 0) { const char* e = getenv("CRDR_WGRAD_HALO_WAVES2"); waves_x2 = e ? atoi(e) : 2; }
+    int64_t splits = (waves_x2 * 74 + tiles - 1) / tiles;
+    const int64_t by_k = pl->kb_total / 4 > 0 ? pl->kb_total / 4 : 1;
+    if (splits > by_k) splits = by_k;
+    if (splits > 128) splits = 128;
+    const int64_t per = (int64_t)d.ntaps * pl->a_pad * pl->b_pad * 4;
+    if (ws_bytes) {
+      if ((int64_t)ws_bytes < per) { set_error("wgrad: workspace too small (%zu < %lld bytes)", ws_bytes, (long long)per); return CRDR_ERR_BAD_SHAPE; }
+      if (splits * per > (int64_t)ws_bytes) splits = (int64_t)ws_bytes / per;
+    }
+    pl->splits = (int)splits;
+    return CRDR_OK;
   }
   pl->bw = pow2_le(d.ws < 8 ? d.ws : 8);
   pl->bh = pow2_le(d.hs < 64 / pl->bw ? d.hs : 64 / pl->bw);
@@ -305,7 +391,8 @@ int wgrad_launch(const crdr_wgrad_desc* dp, cudaStream_t stream) {
   const __half* sp = reinterpret_cast<const __half*>(d.s.hi) + d.s.coff;
   const __half* bp = reinterpret_cast<const __half*>(d.b.hi) + d.b.coff;
   rc = nhwc_box_map(sp, d.ca, d.s.cs, d.ws, d.hs, d.n, pl.bw, pl.bh, pl.bn, 1, &P.tm_s);
-  if (!rc) rc = nhwc_box_map(bp, d.cb, d.b.cs, d.wb, d.hb, d.n, pl.bw, pl.bh, pl.bn, d.stride, &P.tm_b);
+  if (!rc && !pl.halo) rc = nhwc_box_map(bp, d.cb, d.b.cs, d.wb, d.hb, d.n, pl.bw, pl.bh, pl.bn, d.stride, &P.tm_b);
+  if (!rc && pl.halo) rc = nhwc_box_map(bp, d.cb, d.b.cs, d.wb, d.hb, d.n, pl.pw, pl.ph, 1, 1, &P.tm_patch);
   if (rc) return rc;
   P.ws = reinterpret_cast<float*>(d.workspace);
   P.ntaps = d.ntaps; P.a_tiles = pl.a_tiles; P.b_tiles = pl.b_tiles; P.nb = pl.nb;
@@ -315,12 +402,19 @@ int wgrad_launch(const crdr_wgrad_desc* dp, cudaStream_t stream) {
   P.kb_total = pl.kb_total; P.splits = pl.splits;
   P.out = d.out; P.sa = d.sa; P.sb = d.sb; P.st = d.st; P.ca = d.ca; P.cb = d.cb; P.accumulate = d.accumulate; P.scale = d.scale;
   for (int t = 0; t < d.ntaps; ++t) { P.dh[t] = d.dh[t]; P.dw[t] = d.dw[t]; }
-  const uint32_t stage_bytes = (uint32_t)(2 + pl.nb) * kWgBox;
+  if (pl.halo) {
+    P.ph = pl.ph; P.pw = pl.pw; P.dh_min = pl.dh_min; P.dw_min = pl.dw_min;
+    P.group_taps = pl.group_taps; P.ngroups = pl.ngroups; P.b_blocks = pl.b_blocks;
+    P.patch_bytes = ((uint32_t)(pl.ph * pl.pw) * 128u + 1023u) & ~1023u;
+    for (int t = 0; t < d.ntaps; ++t)
+      P.tapoff[t] = (uint32_t)((d.dh[t] - pl.dh_min) * pl.pw + (d.dw[t] - pl.dw_min)) * 128u;
+  }
+  const uint32_t stage_bytes = pl.halo ? 2u * kWgBox + P.patch_bytes : (uint32_t)(2 + pl.nb) * kWgBox;
   int stages = (int)((kWgSmemMax - 2048u) / stage_bytes);
   if (stages > kWgMaxStages) stages = kWgMaxStages;
   P.stages = stages;
-  const int ncols = 64 * pl.nb;
-  P.tmem_cols = ncols <= 64 ? 64u : ncols <= 128 ? 128u : 256u;
+  const int ncols = pl.halo ? 64 * pl.group_taps : 64 * pl.nb;
+  P.tmem_cols = ncols <= 64 ? 64u : ncols <= 128 ? 128u : ncols <= 256 ? 256u : 512u;
   const uint32_t smem = 1024u + (uint32_t)stages * stage_bytes;
 
   static std::mutex mu;
@@ -328,13 +422,19 @@ int wgrad_launch(const crdr_wgrad_desc* dp, cudaStream_t stream) {
   {
     std::lock_guard<std::mutex> lk(mu);
     if (!attr_done) {
-      cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmemMax);
+      cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmemMax);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmemMax);
       if (e != cudaSuccess) { set_error("wgrad: cannot opt in to large shared memory: %s", cudaGetErrorString(e)); return CRDR_ERR_UNSUPPORTED_ARCH; }
       attr_done = true;
     }
   }
-  dim3 grid((unsigned)(d.ntaps * pl.a_tiles * pl.b_tiles), (unsigned)pl.splits);
-  wgrad_kernel<<<grid, kWgThreads, smem, stream>>>(P);
+  if (pl.halo) {
+    dim3 grid((unsigned)(pl.ngroups * pl.a_tiles * pl.b_blocks), (unsigned)pl.splits);
+    wgrad_kernel<true><<<grid, kWgThreads, smem, stream>>>(P);
+  } else {
+    dim3 grid((unsigned)(d.ntaps * pl.a_tiles * pl.b_tiles), (unsigned)pl.splits);
+    wgrad_kernel<false><<<grid, kWgThreads, smem, stream>>>(P);
+  }
   rc = check_launch("wgrad_kernel");
   if (rc || pl.splits == 1) return rc;
   const int64_t total = (int64_t)d.ca * d.cb * d.ntaps;
