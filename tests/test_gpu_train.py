@@ -34,6 +34,9 @@ WGRAD_CASES = [
     (2, 16, 16, 480, 224, 5, 1, 2, False),    # ChARM first layer: 2 M tiles, 8 boxes of N
     (1, 20, 12, 32, 16, 3, 1, 1, False),      # narrow channels (boxes zero-filled past the tensor), ragged grid
     (2, 16, 16, 192, 320, 3, 1, 1, True),     # h_s conv3: stride-1 transposed convolution
+    (2, 100, 44, 64, 96, 3, 1, 1, False),     # halo form (>= 128 pixel blocks) on a grid that is ragged in both directions
+    (2, 64, 64, 96, 64, 5, 1, 2, False),      # halo form, 25 taps in four groups
+    (2, 64, 72, 160, 96, 3, 1, 1, True),      # halo form, transposed stride-1 convolution, two M tiles
 ]
 
 
