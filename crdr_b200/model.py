@@ -493,14 +493,20 @@ class _CharmModelCore(_CodecModelBase):
     pipeline_chunks = int(os.environ.get("CRDR_PIPELINE_CHUNKS", "2"))
     pipeline_min_images = 8
     pipeline_weights = (tuple(float(v) for v in os.environ["CRDR_PIPELINE_WEIGHTS"].split(","))
-                        if os.environ.get("CRDR_PIPELINE_WEIGHTS") else None)  # optional relative chunk sizes, e.g. (2, 1)
+                        if os.environ.get("CRDR_PIPELINE_WEIGHTS") else (2.0, 1.0))
+    # relative chunk sizes of decompress_batch: a smaller LAST chunk shortens the pipeline drain (the synthesis transform of
+    # the last chunk runs after the last host decode); measured 88.4 vs 89.2 and 91.2 vs 95.9 ms per 24-image step on two boxes
 
     pipeline_chunks_compress = int(os.environ.get("CRDR_PIPELINE_CHUNKS_COMPRESS", "0"))   # 0: pipeline_chunks
 
-    def _chunks(self, n, chunks=None):
+    pipeline_weights_compress = (tuple(float(v) for v in os.environ["CRDR_PIPELINE_WEIGHTS_COMPRESS"].split(","))
+                                 if os.environ.get("CRDR_PIPELINE_WEIGHTS_COMPRESS") else (1.0, 1.0))
+
+    def _chunks(self, n, chunks=None, weights=None):
         k = (chunks or self.pipeline_chunks) if n >= self.pipeline_min_images else 1
         k = max(1, min(k, n))
-        w = list(self.pipeline_weights) if self.pipeline_weights and len(self.pipeline_weights) == k else [1] * k
+        weights = weights or self.pipeline_weights
+        w = list(weights) if weights and len(weights) == k else [1] * k
         tot, acc, edges = float(sum(w)), 0.0, [0]
         for wi in w:
             acc += wi
@@ -588,7 +594,7 @@ class _CharmModelCore(_CodecModelBase):
         with torch.cuda.device(self.engine().device):
             nv.status_reset()
             res = self._drive([self._compress_gen(f"c{k}_", real_images[lo:hi], rate_ind, return_tensors, coder_threads)
-                               for k, (lo, hi) in enumerate(self._chunks(n, self.pipeline_chunks_compress))])
+                               for k, (lo, hi) in enumerate(self._chunks(n, self.pipeline_chunks_compress, self.pipeline_weights_compress))])
             nv.status_check()
         return [r for chunk in res for r in chunk]
 
