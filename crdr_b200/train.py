@@ -272,7 +272,7 @@ class CodecTrainer:
         # lowered is the weight-free stand-in the oracle stack uses in its place (oracle/shims/lpips.py: the per-image mean
         # squared difference on the [-1, 1] scale), i.e. a second squared-error term of this weight (0: term absent).
         self.perceptual_weight = float(perceptual_weight)
-        self._perceptual_factor = 1.0      # stage 3 multiplies the perceptual term by beta
+        self._pfac = torch.ones(1, dtype=torch.float32, device=torch.device(device))   # stage 3: beta (device-resident)
         as_cfg = lambda v: list(v) if isinstance(v, (list, tuple)) else float(v)     # per quality level, or one value
         self.lambda_a, self.lambda_b, self.target = as_cfg(rate_lambda_a), as_cfg(rate_lambda_b), as_cfg(target_rate)
         self.loss_scale = None if loss_scale is None else float(loss_scale)   # None: from the batch's pixel count
@@ -393,7 +393,7 @@ class CodecTrainer:
         mse = torch.mean(((images + 1) / 2 - (out["fake_images"] + 1) / 2) ** 2)
         ld = dict(bpp_mean=bpp.mean(), distortion=self.lambda_mse * mse, bpp=bpp.mean(), qbpp=qbpp.mean())
         if self.perceptual_weight:
-            ld["perceptual"] = self.perceptual_weight * 4.0 * mse      # mean (x - y)^2 on [-1, 1] = 4 x the 0..1 MSE
+            ld["perceptual"] = (self._pfac * (self.perceptual_weight * 4.0) * mse).reshape(())   # mean (x - y)^2 on [-1, 1] = 4 x the 0..1 MSE
         self._loss_vals.copy_(torch.stack([bpp.mean(), ld["distortion"] + ld.get("perceptual", 0.0)]))
         if decide:
             self._decide_skip()
@@ -521,9 +521,13 @@ class CodecTrainer:
         # ---- loss roots --------------------------------------------------------------------------------------------
         fp = out["fake_packed"]
         g_img = self._grad(fp.data_ptr(), shape=(n, h // 2, w // 2, 16))
-        coef_mse = S * (self.lambda_mse * 2.0 * 0.25 + self.perceptual_weight * self._perceptual_factor * 2.0) / (n * 3 * h * w)
+        coef_mse = S * self.lambda_mse * 2.0 * 0.25 / (n * 3 * h * w)
         nv.check(L.crdr_mse_backward(fp.data_ptr(), fp.shape[-1], images.data_ptr(), n, h // 2, w // 2, h, w, coef_mse,
                                      g_img.hi.data_ptr(), 16, st))
+        if self.perceptual_weight:
+            # the stand-in perceptual term is a second squared error: the same gradient direction, rescaled on the device
+            # (its weight is multiplied by the device-resident beta in stage 3)
+            g_img.hi.mul_((1.0 + self._pfac * (self.perceptual_weight * 2.0 / (self.lambda_mse * 0.5))).to(torch.float16))
         if image_grad is not None:
             nv.check(L.crdr_planes_grad_to_phases(image_grad.hi.data_ptr(), image_grad.c, n, h // 2, w // 2, image_grad_scale,
                                                   g_img.hi.data_ptr(), 16, st))
@@ -948,7 +952,6 @@ class GanCodecTrainer(CodecTrainer):
         kw.setdefault("target_rate", (0.0,) * 5)
         kw.setdefault("rate_lambda_a", (3.4, 1.3, 0.4, 0.12, 0.05))
         super().__init__(model, device=device, **kw)
-        self.use_graphs = False            # the two-network step is enqueued eagerly
         self.discriminator = discriminator
         self.dctx = TrainContext(discriminator, device)
         subs = len(discriminator.subD_list)
@@ -965,6 +968,9 @@ class GanCodecTrainer(CodecTrainer):
         self.dm, self.dv = torch.zeros_like(self.dctx.flat_p), torch.zeros_like(self.dctx.flat_p)
         self.d_steps = [0] * subs
         self.lambda_gan, self.d_lr, self.delta = float(lambda_gan), float(d_lr), int(relative_score_rate_delta)
+        self._dstep_dev = torch.zeros(subs, dtype=torch.float64, device=self.device)
+        self._dhyper = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self.use_gan_graphs = True
 
     # ------------------------------------------------------------------ discriminator passes
     def d_forward(self, k, images, tape=True, input_grad=False):
@@ -978,15 +984,16 @@ class GanCodecTrainer(CodecTrainer):
         rec, self.dctx.tape = self.dctx.tape, None
         return logits.hi[..., 0].float(), rec, logits, x
 
-    def d_backward(self, tape, logits, dpred, param_grads=True):
+    def d_backward(self, tape, logits, dpred, param_grads=True, peak_bound=None):
         """Reverse sweep of one discriminator pass from d(loss)/d(logit map) (unscaled fp32 [n, h', w']).  The pass uses
         its own power-of-two loss scale, chosen so that the root gradient sits at 2^6 in fp16 (the adversarial term is
-        1e-4 of the MSE term: under the codec's scale its gradients would live in fp16's subnormals); returns that scale."""
-        peak = float(dpred.abs().max().item())
+        1e-4 of the MSE term: under the codec's scale its gradients would live in fp16's subnormals); returns that scale.
+        peak_bound: an analytic bound of max |dpred| (no host round trip: needed inside a CUDA-graph capture)."""
+        peak = float(dpred.abs().max().item()) if peak_bound is None else float(peak_bound)
         scale = 2.0 ** math.floor(math.log2(64.0 / peak)) if peak > 0 else 1.0
         G = self._grad(logits.hi.data_ptr(), like=logits)
         G.hi.zero_()
-        G.hi[..., 0] = (dpred * scale).half()
+        G.hi[..., 0] = (dpred * scale).clamp(-65504.0, 65504.0).half()
         saved, self.loss_scale = self.loss_scale, scale
         self.dctx.param_grads = param_grads
         try:
@@ -1006,58 +1013,47 @@ class GanCodecTrainer(CodecTrainer):
         return F.binary_cross_entropy_with_logits(x, torch.full_like(x, target))
 
     # ------------------------------------------------------------------ the step
-    def generator_backward(self, images, q, noise, beta, rel):
+    def generator_backward(self, images, q, noise, beta, rel, bounded=False):
         """Forward + losses + backward of the generator step (parameters of the discriminator frozen): fills ctx.flat_g with
-        the gradient of distortion + rate + beta * adv.  rel: the relative-score images (no gradient)."""
+        the gradient of distortion + rate + beta * (perceptual stand-in + adv).  rel: the relative-score images (no gradient).
+        beta: float (stored in the device scalar) or None (keep the device scalar).  bounded: size the discriminator pass's loss
+        scale from an analytic bound instead of the measured peak (capture-safe)."""
         k = int(q)
         if self.loss_scale is None:
             self.loss_scale = self._initial_scale(images.shape[0], images.shape[2], images.shape[3])
         out = self.forward(images, q, noise, beta=beta)
+        self._pfac.copy_(self._beta)                     # l_total = dist + rate + beta * (perceptual + adv)
         fake = out["fake_images"]
         ld = self._losses_device(images, out, q)
-        self._perceptual_factor = float(beta)          # l_total = dist + rate + beta * (perceptual + adv)
         real_d, _, _, _ = self.d_forward(k, rel, tape=False)
         fake_g, dtape, dlogits, dplanes = self.d_forward(k, fake, tape=True, input_grad=True)
         with torch.enable_grad():
             fg = fake_g.detach().requires_grad_(True)
             adv = self.lambda_gan * 0.5 * (self._bce(real_d - fg, 0.0) + self._bce(fg - real_d, 1.0))
-            (dfg,) = torch.autograd.grad(beta * adv, [fg])
+            (dfg,) = torch.autograd.grad(self._beta[0] * adv, [fg])
         self.dctx.flat_g.zero_()
-        d_scale = self.d_backward(dtape, dlogits, dfg, param_grads=False)
+        # |d(beta adv)/d logit| <= beta_max * lambda_gan / (number of logits): each BCE term's derivative is a sigmoid / count
+        bound = self.gs.max_beta * self.lambda_gan / fake_g.numel() if bounded else None
+        d_scale = self.d_backward(dtape, dlogits, dfg, param_grads=False, peak_bound=bound)
         g_in = self._grads[dplanes.hi.data_ptr()]          # d(beta * adv) / d(fake image) as 8-channel planes, x d_scale
         self.backward(images, out, image_grad=g_in, image_grad_scale=self.loss_scale / d_scale)
         return ld, adv, fake
 
-    def train_step(self, images, q=None, noise=None, generator=None, beta=None):
-        from .sharding import broadcast_from_rank0
-        n, _, h, w = images.shape
-        if q is None:
-            qt = torch.randint(self.model.rate_level, (1,)).to(self.device, torch.float32)
-            q = float(broadcast_from_rank0(qt, self.pg).item())
-        if beta is None:
-            bt = torch.randint(0, 101, (1,)).to(self.device, torch.float32) * (self.gs.max_beta / 100.0)
-            beta = float(broadcast_from_rank0(bt, self.pg).item())
-        if noise is None:
-            mk = lambda c, a, b: torch.rand((n, c, a, b), dtype=torch.float32, device=self.device, generator=generator) - 0.5
-            noise = {"z": mk(self.zc, h // 64, w // 64), "y": mk(self.charm.yc, h // 16, w // 16)}
+    def _gan_core(self, images, q, noise, noise_rel, bounded):
+        """The whole stage-3 step on device-resident scalars (beta, rate weight, skip flag, Adam schedules): no host round
+        trip, so it can be enqueued eagerly or captured into one CUDA graph."""
         k = int(q)
-        if self.loss_scale is None:
-            self.loss_scale = self._initial_scale(n, h, w)
         # ---- relative-score image: the reconstruction one quality level up (no gradient), or the real image at the top level
         if q + self.delta > self.model.rate_level - 1:
             rel = images
         else:
-            noise_rel = {kk: torch.rand_like(v) - 0.5 for kk, v in noise.items()}
-            rel = self.forward(images, q + self.delta, noise_rel, beta=beta)["fake_images"]
+            rel = self.forward(images, q + self.delta, noise_rel, beta=None)["fake_images"]
             self.ctx.tape = None
         # ================================================================== train G
-        ld, adv, fake = self.generator_backward(images, q, noise, beta, rel)
-        if float(self._skip.item()) > 0:      # nan / inf / huge loss: the reference returns before any update (trainer :68-71)
-            nv.status_check()
-            return self._finish_losses(ld)
+        ld, adv, fake = self.generator_backward(images, q, noise, None, rel, bounded=bounded)
         ld["aux"] = self.aux_step()
         self.all_reduce_grads()
-        self.optimizer_step()
+        self.optimizer_step()               # honours the skip flag (nan / inf / huge loss: the reference returns before any update)
         ld = self._finish_losses(ld)
         ld["adv"] = adv.detach()
         # ================================================================== train D
@@ -1072,20 +1068,76 @@ class GanCodecTrainer(CodecTrainer):
             l_d_real = 0.5 * self._bce(rp - fp.detach(), 1.0)
             l_d_fake = 0.5 * self._bce(fp - rp.detach(), 0.0)
             drp, dfp = torch.autograd.grad(l_d_real + l_d_fake, [rp, fp])
-        self.d_backward(rtape, rlogits, drp)
-        self.d_backward(ftape, flogits, dfp)
+        bound = 0.5 / real_p.numel() if bounded else None
+        self.d_backward(rtape, rlogits, drp, peak_bound=bound)
+        self.d_backward(ftape, flogits, dfp, peak_bound=bound)
         from .sharding import allreduce_mean_flat
         allreduce_mean_flat(self.dctx.flat_g, 64 << 20, self.pg)
         self.d_optimizer_step(k)
-        nv.status_check()
         ld.update(d_real=l_d_real.detach(), d_fake=l_d_fake.detach(), out_d_real=real_p.mean(), out_d_fake=fake_d.mean())
         return ld
 
+    def train_step(self, images, q=None, noise=None, generator=None, beta=None):
+        """One generator + discriminator update.  Like CodecTrainer.train_step, the first call of a (shape, quality level)
+        is enqueued eagerly (it also builds the adjoint matrices of the codec and of sub-discriminator int(q)), the second
+        captures the whole step into ONE CUDA graph and from then on the step is a replay (single process; under
+        torch.distributed the collectives keep the step eager)."""
+        from .sharding import broadcast_from_rank0
+        n, _, h, w = images.shape
+        if q is None:
+            qt = torch.randint(self.model.rate_level, (1,)).to(self.device, torch.float32)
+            q = float(broadcast_from_rank0(qt, self.pg).item())
+        if beta is None:
+            bt = torch.randint(0, 101, (1,)).to(self.device, torch.float32) * (self.gs.max_beta / 100.0)
+            self._beta.copy_(broadcast_from_rank0(bt, self.pg))
+        else:
+            self._beta.fill_(float(beta))
+        mk = lambda c, a, b: torch.rand((n, c, a, b), dtype=torch.float32, device=self.device, generator=generator) - 0.5
+        if noise is None:
+            noise = {"z": mk(self.zc, h // 64, w // 64), "y": mk(self.charm.yc, h // 16, w // 16)}
+        noise_rel = {"z": mk(self.zc, h // 64, w // 64), "y": mk(self.charm.yc, h // 16, w // 16)}
+        if self.loss_scale is None:
+            self.loss_scale = self._initial_scale(n, h, w)
+        key = (n, h, w, float(q))
+        if not self.use_gan_graphs or self._distributed() or key not in self._warm:
+            ld = self._gan_core(images, q, noise, noise_rel, bounded=False)
+            nv.status_check()
+            self._warm.add(key)
+            return ld
+        hit = self._graphs.get(key)
+        if hit is None:
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()
+            st_in = dict(x=images.clone(), z=noise["z"].clone(), y=noise["y"].clone(), rz=noise_rel["z"].clone(), ry=noise_rel["y"].clone())
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            count, dcount, l0 = self.step_count, list(self.d_steps), nv.LAUNCH_COUNT[0]
+            with torch.cuda.graph(g, pool=self._pool):
+                ld = self._gan_core(st_in["x"], q, {"z": st_in["z"], "y": st_in["y"]}, {"z": st_in["rz"], "y": st_in["ry"]}, bounded=True)
+            self.step_count, self.d_steps = count, dcount          # the capture itself executes nothing
+            hit = self._graphs[key] = (g, st_in, ld, nv.LAUNCH_COUNT[0] - l0, int(q))
+        g, st_in, ld, launches, k = hit
+        for name, src in (("x", images), ("z", noise["z"]), ("y", noise["y"]), ("rz", noise_rel["z"]), ("ry", noise_rel["y"])):
+            st_in[name].copy_(src, non_blocking=True)
+        g.replay()
+        self.step_count += 1
+        self.d_steps[k] += 1
+        nv.LAUNCH_COUNT[0] += launches
+        nv.status_check()
+        return dict(ld)
+
     def d_optimizer_step(self, k):
+        """Adam on the active sub-discriminator's segment; step count, learning rate and the skip flag are device resident."""
         lo, hi = self._dseg[k]
         self.d_steps[k] += 1
         c = self.dctx
+        b1, b2 = self.betas
+        self._dstep_dev[k] += 1.0 - self._skip[0].to(torch.float64)
+        t = self._dstep_dev[k]
+        self._dhyper[0:1].fill_(self.d_lr)      # (a Python scalar assigned to an element would be a host copy: not capturable)
+        self._dhyper[1] = (1.0 - b1 ** t).to(torch.float32)
+        self._dhyper[2] = torch.sqrt(1.0 - b2 ** t).to(torch.float32)
+        self._dhyper[3] = self._skip[0]
         nv.check(nv.lib().crdr_adam_step(c.flat_p[lo:].data_ptr(), c.flat_g[lo:].data_ptr(), self.dm[lo:].data_ptr(), self.dv[lo:].data_ptr(),
-                                         hi - lo, self.d_lr, self.betas[0], self.betas[1], self.eps, self.d_steps[k], None, 1.0, None,
-                                         nv.stream_handle()))
+                                         hi - lo, self.d_lr, b1, b2, self.eps, 0, None, 1.0, self._dhyper.data_ptr(), nv.stream_handle()))
         c.repack()

@@ -625,3 +625,33 @@ def test_huge_loss_skips_the_update():
     tr._graphs.clear(); tr._warm.clear()     # the loss weight is baked into the captured launch parameters
     ld = tr.train_step(x, q=2.0)
     assert float(ld["skipped"]) == 0.0 and not torch.equal(tr.ctx.flat_p, p0) and float(tr._step_dev) == 1.0
+
+
+def test_stage3_graph_replay_matches_eager_steps():
+    """The stage-3 step captured into one CUDA graph (device-resident beta / rate weight / skip flag / Adam schedules,
+    analytic loss-scale bounds for the discriminator passes) against the same steps enqueued eagerly: same inputs, same
+    noise; the parameters of the codec and of the active sub-discriminator agree to a fraction of one Adam step."""
+    import fixtures
+    x = fixtures.image(2, 128, 128, seed=25).to(DEV).contiguous()
+    results = []
+    for graphs in (False, True):
+        tr, _ = _gan_trainer(seed=14)
+        tr.use_gan_graphs = graphs
+        gen = torch.Generator(device=DEV).manual_seed(11)
+        for it in range(4):
+            ld = tr.train_step(x, q=1.0, beta=1.28 * (it + 1), generator=gen)
+            assert math.isfinite(float(ld["rate"] + ld["distortion"] + ld["adv"]))
+        assert (len(tr._graphs) == 1) == graphs
+        results.append((tr.ctx.flat_p.clone(), tr.dctx.flat_p.clone(), tr.step_count, list(tr.d_steps)))
+    (pa, da, sa, dsa), (pb, db, sb, dsb) = results
+    assert sa == sb == 4 and dsa == dsb == [0, 4, 0, 0, 0]
+    lr = 1e-4
+    assert float((pa - pb).abs().max()) < 0.5 * lr
+    # discriminator: its passes run under a different loss scale in the captured step (analytic bound instead of the measured
+    # peak), and Adam's first updates are lr * sign(gradient) whatever the magnitude, so parameters whose gradient is
+    # rounding noise may move the other way: a handful of elements, by at most a few steps
+    dd = (da - db).abs()
+    assert float(dd.max()) < 4 * lr and float((dd > 0.5 * lr).float().mean()) < 1e-3, (float(dd.max()), float((dd > 0.5 * lr).float().mean()))
+    # ... and both moved by several steps' worth
+    tr0, _ = _gan_trainer(seed=14)
+    assert float((pa - tr0.ctx.flat_p).abs().max()) > 2 * lr and float((da - tr0.dctx.flat_p).abs().max()) > 2 * lr
