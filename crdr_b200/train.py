@@ -276,7 +276,6 @@ class CodecTrainer:
         as_cfg = lambda v: list(v) if isinstance(v, (list, tuple)) else float(v)     # per quality level, or one value
         self.lambda_a, self.lambda_b, self.target = as_cfg(rate_lambda_a), as_cfg(rate_lambda_b), as_cfg(target_rate)
         self.loss_scale = None if loss_scale is None else float(loss_scale)   # None: from the batch's pixel count
-        self._auto_scale = loss_scale is None
         self.m = torch.zeros_like(ctx.flat_p)
         self.v = torch.zeros_like(ctx.flat_p)
         self.step_count = 0
@@ -934,10 +933,10 @@ class CodecTrainer:
 
 class GanCodecTrainer(CodecTrainer):
     """Stage 3 of the reference (MultirateBetaCondHrrGanRateDistortionTrainer.optimize_parameters,
-    multirate_hr_rgan_beta_cond_rate_distortion_trainer.py:13-114) on the CUDA engines, without the LPIPS term (no pretrained
-    AlexNet weights offline):
+    multirate_hr_rgan_beta_cond_rate_distortion_trainer.py:13-114) on the CUDA engines (LPIPS as its weight-free stand-in):
 
-      G step:  l = distortion + rate + beta * adv,   adv = lambda_gan / 2 * (BCE(D(rel) - D(fake), 0) + BCE(D(fake) - D(rel), 1))
+      G step:  l = distortion + rate + beta * (perceptual + adv),
+               adv = lambda_gan / 2 * (BCE(D(rel) - D(fake), 0) + BCE(D(fake) - D(rel), 1))
                where `rel` is the reconstruction at the next higher quality level (no gradient; the real image at the top
                level) and D = sub-discriminator int(q); the discriminator's parameters are frozen, its input gradient is
                added to the MSE gradient of the reconstruction.
