@@ -520,7 +520,7 @@ def test_stage3_gan_step_runs_and_updates_the_right_parameters():
     assert changed == [1, 4], changed
 
 
-@pytest.mark.parametrize("config", ["crdr_stage_2.yaml", "crdr_stage_3.yaml"])
+@pytest.mark.parametrize("config", ["crdr_stage_1.yaml", "crdr_stage_2.yaml", "crdr_stage_3.yaml"])
 def test_train_script_drop_in(tmp_path, config):
     """scripts/train.py (the reference's config -> build_trainer -> train_loop flow, reference scripts/train.py:16-28) for a
     few iterations on synthetic crops; the checkpoint it writes has the reference layout and loads into a fresh model."""
@@ -538,7 +538,7 @@ def test_train_script_drop_in(tmp_path, config):
     ckpt = torch.load(path, map_location="cpu")
     assert ckpt["iter"] == 3
     from crdr_b200.model import build_comp_model
-    fresh = build_comp_model(fixtures.crdr_opt(DEV, "crdr_stage_2.yaml" if config == "crdr_stage_2.yaml" else "crdr.yaml"))
+    fresh = build_comp_model(fixtures.crdr_opt(DEV, "crdr.yaml" if config == "crdr_stage_3.yaml" else config))
     assert [k for k in ckpt["comp_model"] if "entropy_model" not in k] == [k for k in fresh.state_dict() if "entropy_model" not in k]
     fresh.load_learned_weight(str(path))
     assert all(torch.isfinite(v).all() for v in ckpt["comp_model"].values() if v.is_floating_point())
