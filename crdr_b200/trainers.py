@@ -89,6 +89,15 @@ class _TrainerBase:
             if itr % save_step == 0:
                 self.save(itr)
 
+    def validation(self, dataloader, max_sample_size=1 << 30, **kw):
+        """base_trainer.py:162-169: evaluate the current parameters with the model's own validation() (evaluation-mode
+        forward on the inference engines, one row of bpp / PSNR per image and quality level).  dataloader: a sequence of
+        data_dicts {"real_images": [1, 3, H, W]}."""
+        self.step_impl.sync_to_model()
+        self.comp_model.invalidate_engine()
+        self.comp_model.codec_setup()
+        return self.comp_model.validation(dataloader, max_sample_size, **kw)
+
     def _synthetic(self):
         g = torch.Generator().manual_seed(0)
         n, s = int(self.opt.get("batch_size", 8)), int(self.opt.get("patch_size", 256))

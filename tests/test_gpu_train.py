@@ -655,3 +655,23 @@ def test_stage3_graph_replay_matches_eager_steps():
     # ... and both moved by several steps' worth
     tr0, _ = _gan_trainer(seed=14)
     assert float((pa - tr0.ctx.flat_p).abs().max()) > 2 * lr and float((da - tr0.dctx.flat_p).abs().max()) > 2 * lr
+
+
+def test_trainer_plugin_step_and_validation():
+    """The registry-built trainer (reference names / step interface): a few optimize_parameters calls, then validation()
+    of the updated parameters through the model's evaluation path."""
+    import fixtures
+    import src  # noqa: F401
+    from conftest import ROOT
+    from crdr_b200.config import BaseConfig
+    from src.trainer import build_trainer
+    opt = BaseConfig.fromfile(os.path.join(ROOT, "config", "crdr_stage_2.yaml"), device=DEV, is_train=True)
+    opt["pretrained_weight_path"] = None
+    trainer = build_trainer(opt)
+    assert type(trainer).__name__ == "RateDistortionTrainer"
+    x = fixtures.image(2, 128, 128, seed=30)
+    for it in range(1, 4):
+        log = trainer.optimize_parameters(it, {"real_images": x})
+        assert math.isfinite(float(log["rate"] + log["distortion"] + log["perceptual"]))
+    df = trainer.validation([{"real_images": fixtures.image(1, 128, 192, seed=31)}], max_sample_size=1)
+    assert len(df) == 1 and all(math.isfinite(float(df[f"psnr_{q}"][0])) and float(df[f"bpp_{q}"][0]) > 0 for q in range(1, 6))
