@@ -924,6 +924,27 @@ class CodecTrainer:
             self._on_overflow()             # this update used clamped gradients (finite); the next steps run at a lower scale
         return self._finish_losses(dict(ld))
 
+    def training_state(self):
+        """Everything needed to resume (base_trainer.save with keep_training_state: model parameters + optimiser state):
+        CPU tensors keyed by parameter name, Adam step count, loss scale."""
+        c = self.ctx
+        take = lambda flat: {k: flat[o:o + c.params[k].numel()].view(c.params[k].shape).detach().cpu().clone()
+                             for k, o in zip(c.names, c.offsets)}
+        return {"params": take(c.flat_p), "exp_avg": take(self.m), "exp_avg_sq": take(self.v), "step": int(round(float(self._step_dev))),
+                "step_count": self.step_count, "loss_scale": self.loss_scale, "lr": self.lr, "aux_lr": self.aux_lr}
+
+    def load_training_state(self, state):
+        c = self.ctx
+        for src, flat in ((state["params"], c.flat_p), (state["exp_avg"], self.m), (state["exp_avg_sq"], self.v)):
+            for k, o in zip(c.names, c.offsets):
+                flat[o:o + c.params[k].numel()].view(c.params[k].shape).copy_(src[k].to(self.device))
+        self._step_dev.fill_(float(state["step"]))
+        self.step_count, self.loss_scale = int(state["step_count"]), state["loss_scale"]
+        self.set_lr(state["lr"], state["aux_lr"])
+        self._graphs.clear()
+        self._warm.clear()
+        c.repack()
+
     def sync_to_model(self):
         """Copy the trained parameters back into the nn.Module (checkpointing: state_dict layout of the reference)."""
         with torch.no_grad():

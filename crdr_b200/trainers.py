@@ -110,7 +110,16 @@ class _TrainerBase:
         os.makedirs(root, exist_ok=True)
         path = os.path.join(root, f"comp_model_iter{current_iter}.pth.tar")
         torch.save({"iter": current_iter, "comp_model": self.comp_model.state_dict()}, path)
+        if self.opt.get("keep_training_state", False):      # rate_distortion_trainer.py:104-117: optimiser state next to the model
+            torch.save({"iter": current_iter, "training_state": self.step_impl.training_state()},
+                       os.path.join(root, f"training_state_iter{current_iter}.pth.tar"))
         return path
+
+    def load_checkpoint(self, exp, itr):
+        """Resume (base_trainer.py:102-108): parameters, Adam moments, step count and loss scale of `training_state_iter{itr}`."""
+        root = os.path.join(self.opt.get("ckpt_root", "./checkpoint"), str(exp), "model")
+        state = torch.load(os.path.join(root, f"training_state_iter{itr}.pth.tar"), map_location="cpu")
+        self.step_impl.load_training_state(state["training_state"])
 
 
 @TRAINER_REGISTRY.register()

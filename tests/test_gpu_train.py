@@ -675,3 +675,34 @@ def test_trainer_plugin_step_and_validation():
         assert math.isfinite(float(log["rate"] + log["distortion"] + log["perceptual"]))
     df = trainer.validation([{"real_images": fixtures.image(1, 128, 192, seed=31)}], max_sample_size=1)
     assert len(df) == 1 and all(math.isfinite(float(df[f"psnr_{q}"][0])) and float(df[f"bpp_{q}"][0]) > 0 for q in range(1, 6))
+
+
+def test_training_state_resume_is_bit_identical():
+    """Resume from training_state(): two steps + save + two steps in a fresh trainer == four steps straight."""
+    import fixtures
+    from crdr_b200.train import CodecTrainer
+    x = fixtures.image(2, 128, 128, seed=33).to(DEV).contiguous()
+
+    def noise(i):
+        g = torch.Generator(device=DEV).manual_seed(100 + i)
+        mk = lambda c, a, b: torch.rand((2, c, a, b), dtype=torch.float32, device=DEV, generator=g) - 0.5
+        return {"z": mk(192, 2, 2), "y": mk(320, 8, 8)}
+
+    def fresh():
+        model, _ = fixtures.build_model(seed=6, calibrated=False, config="crdr_stage_2.yaml")
+        return CodecTrainer(model, device=DEV, lr=1e-4, clip_max_norm=1.0)
+
+    a = fresh()
+    for i in range(4):
+        a.train_step(x, q=float(i % 2), noise=noise(i))
+    b = fresh()
+    for i in range(2):
+        b.train_step(x, q=float(i % 2), noise=noise(i))
+    state = b.training_state()
+    c = fresh()
+    c.load_training_state(state)
+    for i in range(2, 4):
+        c.train_step(x, q=float(i % 2), noise=noise(i))
+    torch.cuda.synchronize()
+    assert torch.equal(a.ctx.flat_p, c.ctx.flat_p) and torch.equal(a.m, c.m) and torch.equal(a.v, c.v)
+    assert a.step_count == c.step_count == 4
