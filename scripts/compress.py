@@ -92,7 +92,29 @@ def main():
         torch.distributed.init_process_group("gloo")   # only for the final gather of the per-image rows
 
     rows = []
-    images = ((p, load_image(p)) for p in mine)   # lazily: one batch of decoded images in memory at a time
+    # PNG decode ahead of the device (a few images in flight) and PNG encode behind it on host threads:
+    # neither PIL's decoder nor cv2.imwrite holds the GIL while it works
+    from collections import deque
+    from concurrent.futures import ThreadPoolExecutor
+    io_threads = max(2, min(8, (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))))
+    pool = ThreadPoolExecutor(max_workers=io_threads)
+    pending_writes = []
+
+    def prefetched(paths_, depth):
+        q = deque()
+        it = iter(paths_)
+        for p_ in it:
+            q.append((p_, pool.submit(load_image, p_)))
+            if len(q) >= depth:
+                break
+        while q:
+            p_, fut = q.popleft()
+            nxt = next(it, None)
+            if nxt is not None:
+                q.append((nxt, pool.submit(load_image, nxt)))
+            yield p_, fut.result()
+
+    images = prefetched(mine, max(2, 2 * int(opt.batch)))
     for group in sharding.same_shape_batches(images, opt.batch):
         x = torch.cat([im for _, im in group], dim=0)
         _, _, H, W = x.shape
@@ -113,8 +135,13 @@ def main():
             bins.append(bin_path)
         if opt.decompress:
             imgs, _, _ = model.decompress_batch([load_byte_strings(b) for b in bins], **beta_kw)
+            host = imgs.cpu()
             for (path, _), k in zip(group, range(len(group))):
-                img_utils.imwrite(os.path.join(opt.save_dir, os.path.basename(path)), imgs[k:k + 1].cpu())
+                pending_writes.append(pool.submit(img_utils.imwrite, os.path.join(opt.save_dir, os.path.basename(path)), host[k:k + 1]))
+            pending_writes = [f for f in pending_writes if not f.done() or f.result() is not None]
+    for f in pending_writes:
+        f.result()
+    pool.shutdown()
 
     rows = sharding.gather_rows(rows, rank, world, opt.save_dir)
     if rank == 0:
