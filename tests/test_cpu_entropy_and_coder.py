@@ -208,3 +208,43 @@ def test_compact_coder_entry_points_and_pool():
     assert all(np.array_equal(o, s) for o, s in zip(out, syms))
     out = rans.decode_batch([rans.Decoder(s) for s in a], idxs, t, threads=1)
     assert all(np.array_equal(o, s) for o, s in zip(out, syms))
+
+
+def test_interleaved_streams_match_single_stream_and_oracle(product_gc, oracle):
+    """More equal-length streams than coder threads: each thread codes bundles of up to four streams side by side
+    (rans.cpp encode_many / decode_loop<K>).  Bytes and symbols must equal the one-stream-at-a-time coder and the oracle
+    coder, for every bundle size, with escapes on both sides, peaked rows (the decoder's pure-bucket shortcut) and wide
+    rows (the slot search), and across split decode calls that continue from the saved coder state."""
+    from crdr_b200 import rans
+    from compressai import ans
+    T = product_gc.coder_tables()
+    rng = np.random.default_rng(17)
+    table = np.asarray(product_gc.scale_table, dtype=np.float64)
+    n = 6001
+    for count in (2, 3, 4, 5, 7, 9):
+        idxs = [np.minimum(rng.integers(0, 64, n), rng.integers(0, 64, n)).astype(np.int32) for _ in range(count)]
+        syms = [np.rint(rng.standard_normal(n) * table[i] * 1.5).astype(np.int32) for i in idxs]
+        for s in syms:                                   # escapes, both signs, different lengths
+            pos = rng.integers(0, n, 40)
+            s[pos] = rng.integers(-70000, 70000, 40)
+        single = [rans.encode(s, i, T) for s, i in zip(syms, idxs)]
+        if count == 3:
+            enc = ans.RansEncoder()
+            assert single == [enc.encode_with_indexes(s, i, T.cdfs, T.sizes, T.offsets) for s, i in zip(syms, idxs)]
+        for th in (1, 2):
+            assert rans.encode_batch(syms, idxs, T, threads=th) == single
+            clipped = [np.clip(s, -32768, 32767) for s in syms]
+            assert rans.encode_batch([s.astype(np.int16) for s in clipped], [i.astype(np.uint8) for i in idxs], T, threads=th) == \
+                [rans.encode(s, i, T) for s, i in zip(clipped, idxs)]
+            decs = [rans.Decoder(s) for s in single]
+            cut = 2345
+            a = rans.decode_batch(decs, [i[:cut] for i in idxs], T, threads=th)
+            b = rans.decode_batch(decs, [i[cut:].astype(np.uint8) for i in idxs], T, threads=th)
+            assert all(np.array_equal(np.concatenate([x, y]), s) for x, y, s in zip(a, b, syms))
+    # a bad table index in one stream of a bundle is reported, not decoded
+    bad = [i.copy() for i in idxs[:4]]
+    bad[2][100] = 64
+    with pytest.raises(ValueError):
+        rans.encode_batch(syms[:4], bad, T, threads=1)
+    with pytest.raises(ValueError):
+        rans.decode_batch([rans.Decoder(s) for s in single[:4]], bad, T, threads=1)
