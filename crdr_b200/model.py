@@ -71,6 +71,7 @@ class CodecEngine:
         self.zc = model.entropy_model_z.channels
         self.stride = 64
         self._graphs = OrderedDict()   # CUDA graphs of the device-only launch sequences of small calls (LRU)
+        self.decode_graph_sets = OrderedDict()   # model._DecodeGraphs per decompress chunk shape (LRU)
 
     # ------------------------------------------------------------------ device-side stages
     def padded(self, h, w):
@@ -272,6 +273,96 @@ class _PinnedPool:
         buf = self.get(tag, dev_tensor.shape, dev_tensor.dtype)
         buf.copy_(dev_tensor, non_blocking=True)
         return buf
+
+
+class _DecodeGraphs:
+    """CUDA graphs of the device segments of ONE pipelined decompress chunk (n images of one size).
+
+    The decoder alternates between the host coder and the device, group of slices after group: with eager
+    launches the Python enqueue of a segment (~12 launches on forked side streams, 0.8 ms) and the host decode (0.8 ms) add
+    up on one thread while the device waits (profiles/e2e_timeline_r02.txt: the scheduler never waited for the device).  Here
+    every segment -- [host -> device copy of the decoded symbols, dequantise, LRP refinement, (mean, scale) networks of the
+    next group, CDF indexes, device -> host copy of the indexes] -- is one graph replay; the first segment also holds h_s and
+    the last one g_s.  The pinned staging buffers are owned by the set (fixed addresses inside the memcpy nodes), all segments
+    share one memory pool and are replayed in capture order, and the per-quality / per-beta vectors stay behind their fixed
+    device addresses (StaticVectors), so one set serves every q and beta.  Same launch sequence, same arithmetic: the
+    output is bit-identical to the eager path."""
+
+    def __init__(self, model, eng, n, h, w, out_uint8, q, beta):
+        self.n = n
+        dev = eng.device
+        hp, wp = eng.padded(h, w)
+        hz, wz = hp // model.model_stride, wp // model.model_stride
+        sc, yC = eng.charm.sc, model.yC
+        self.groups = eng.charm.groups()
+        pin = lambda shape, dtype: torch.empty(shape, dtype=dtype, pin_memory=True)
+        self.z_host = pin((n, model.zC, hz, wz), torch.int32)
+        hy, wy = 4 * hz, 4 * wz
+        self.ix_host = [pin((n, len(g) * sc, hy, wy), torch.uint8) for g in self.groups]
+        self.sym_host = [pin((n, len(g) * sc, hy, wy), torch.int32) for g in self.groups]
+        # the coder side: persistent decoder objects and marshalled calls on the pinned buffers
+        zi = _channel_indexes(model.zC, hz, wz)
+        self.z_dec = [rans.Decoder() for _ in range(n)]
+        self.y_dec = [rans.Decoder() for _ in range(n)]
+        zv = self.z_host.numpy().reshape(n, -1)
+        self.z_plan = rans.DecodePlan(self.z_dec, [zi] * n, [zv[i] for i in range(n)])
+        self.y_plans = []
+        for ix, sy in zip(self.ix_host, self.sym_host):
+            iv, sv = ix.numpy().reshape(n, -1), sy.numpy().reshape(n, -1)
+            self.y_plans.append(rans.DecodePlan(self.y_dec, [iv[i] for i in range(n)], [sv[i] for i in range(n)]))
+        # capture (nothing executes): the generator of the slice loop runs across the captures
+        eng.prepare(q=q, beta=beta)
+        torch.cuda.current_stream().synchronize()
+        self.pool = torch.cuda.graph_pool_handle()
+        self.segments = []
+        st = {}
+
+        def capture(fn):
+            g = torch.cuda.CUDAGraph()
+            l0 = nv.LAUNCH_COUNT[0]
+            with torch.cuda.graph(g, pool=self.pool):
+                fn()
+            self.segments.append((g, nv.LAUNCH_COUNT[0] - l0))
+
+        def fetch_indexes(k, req):
+            s0, cnt, idx = req
+            assert s0 == self.groups[k][0] and cnt == len(self.groups[k])
+            self.ix_host[k].copy_(idx[:, s0 * sc:(s0 + cnt) * sc].contiguous(), non_blocking=True)
+
+        def first():
+            st["z_sym"] = self.z_host.to(dev, non_blocking=True)
+            st["T"], st["z_hat"] = eng.hyper_from_symbols(st["z_sym"])
+            st["y_sym"] = torch.empty((n, yC, st["T"].h, st["T"].w), dtype=torch.int32, device=dev)
+            st["steps"] = eng.charm.decode_steps(st["T"], eng.gp, compact=True)
+            fetch_indexes(0, next(st["steps"]))
+
+        def middle(k):   # symbols of group k-1 in, indexes of group k out
+            g = self.groups[k - 1]
+            st["y_sym"][:, g[0] * sc:(g[-1] + 1) * sc].copy_(self.sym_host[k - 1], non_blocking=True)
+            fetch_indexes(k, st["steps"].send(st["y_sym"]))
+
+        def last():
+            g = self.groups[-1]
+            st["y_sym"][:, g[0] * sc:(g[-1] + 1) * sc].copy_(self.sym_host[-1], non_blocking=True)
+            try:
+                st["steps"].send(st["y_sym"])
+                raise RuntimeError("decode_steps yielded past the last slice group")
+            except StopIteration as done:
+                yhat32 = done.value
+            st["img"] = eng.synthesis(yhat32, q, beta, (h, w), out_uint8=out_uint8)
+            st["y_hat"] = eng.to_nchw(yhat32)
+
+        capture(first)
+        for k in range(1, len(self.groups)):
+            capture(lambda k=k: middle(k))
+        capture(last)
+        self.img, self.z_hat, self.y_hat = st["img"], st["z_hat"], st["y_hat"]
+        self._keep = st   # tensors of the shared pool that later segments read
+
+    def replay(self, k):
+        g, launches = self.segments[k]
+        g.replay()
+        nv.LAUNCH_COUNT[0] += launches
 
 
 def _channel_indexes(c, h, w):
@@ -500,7 +591,10 @@ class _CharmModelCore(_CodecModelBase):
     pipeline_chunks_compress = int(os.environ.get("CRDR_PIPELINE_CHUNKS_COMPRESS", "0"))   # 0: pipeline_chunks
 
     pipeline_weights_compress = (tuple(float(v) for v in os.environ["CRDR_PIPELINE_WEIGHTS_COMPRESS"].split(","))
-                                 if os.environ.get("CRDR_PIPELINE_WEIGHTS_COMPRESS") else (1.0, 1.0))
+                                 if os.environ.get("CRDR_PIPELINE_WEIGHTS_COMPRESS") else (3.0, 1.0))
+    # compress_batch: what stays exposed is the host encode of the LAST chunk, and one image's stream is one sequential coder
+    # pass whatever the chunk size -- a short last chunk only shortens the device span that precedes it.  Measured
+    # (tools/e2e_pipeline_sweep.py, 24 x 512x768, ms per call): one chunk 48.6, 1:1 46.9, 2:1 46.0, 3:1 44.4, 1:1:1 47.6
 
     def _chunks(self, n, chunks=None, weights=None):
         k = (chunks or self.pipeline_chunks) if n >= self.pipeline_min_images else 1
@@ -644,6 +738,36 @@ class _CharmModelCore(_CodecModelBase):
         y_hat = eng.to_nchw(yhat32)
         return img, z_hat, y_hat
 
+    # CUDA graphs of the decode segments (class _DecodeGraphs): a chunk shape is coded eagerly the first time it is seen
+    # (that call also loads every kernel the sequence uses) and captured right after; later calls replay.
+    DECODE_GRAPH_MAX_PIXELS = int(os.environ.get("CRDR_DECODE_GRAPH_MAX_PIXELS", str(32 * 512 * 768)))
+    DECODE_GRAPH_CACHE = 6
+    decode_graphs_enabled = os.environ.get("CRDR_DECODE_GRAPHS", "1") != "0"
+
+    def _decode_graph_key(self, tag, n, h, w, out_uint8):
+        eng = self.engine()
+        hp, wp = eng.padded(h, w)
+        if not (self.decode_graphs_enabled and eng.graphs_enabled and n * hp * wp <= self.DECODE_GRAPH_MAX_PIXELS):
+            return None
+        return (tag, n, h, w, bool(out_uint8))
+
+    def _decompress_gen_graphed(self, gs, string_lists, q, beta, coder_threads):
+        """_decompress_gen with every device segment replayed from the chunk's graph set (same results)."""
+        eng = self.engine()
+        zt, yt = self.entropy_model_z.coder_tables(), self.entropy_model_y.coder_tables()
+        eng.prepare(q=q, beta=beta)
+        for d, sl in zip(gs.z_dec, string_lists):
+            d.set_stream(sl[1])
+        gs.z_plan.run(zt, coder_threads)
+        gs.replay(0)
+        for d, sl in zip(gs.y_dec, string_lists):
+            d.set_stream(sl[2])
+        for k, plan in enumerate(gs.y_plans):
+            yield self._event()      # the indexes of group k are in pinned memory once this event is
+            plan.run(yt, coder_threads)
+            gs.replay(k + 1)
+        return gs.img, gs.z_hat, gs.y_hat
+
     @torch.no_grad()
     def decompress_batch(self, string_lists, beta=0.0, coder_threads=0, out_uint8=False):
         """Streams of N images with identical size and quality -> (images [N,3,H,W], z_hat, y_hat).  ``out_uint8``: the
@@ -660,12 +784,27 @@ class _CharmModelCore(_CodecModelBase):
         n = len(string_lists)
         with torch.cuda.device(self.engine().device):
             nv.status_reset()
-            res = self._drive([self._decompress_gen(f"d{k}_", string_lists[lo:hi], h, w, q, beta, coder_threads, out_uint8)
-                               for k, (lo, hi) in enumerate(self._chunks(n))])
+            sets = self.engine().decode_graph_sets   # owned by the engine: they hold its weight pointers
+            gens, fresh = [], []
+            for k, (lo, hi) in enumerate(self._chunks(n)):
+                key = self._decode_graph_key(f"d{k}_", hi - lo, h, w, out_uint8)
+                gs = sets.get(key) if key is not None else None
+                if gs is not None:
+                    sets.move_to_end(key)
+                    gens.append(self._decompress_gen_graphed(gs, string_lists[lo:hi], q, beta, coder_threads))
+                else:
+                    if key is not None:
+                        fresh.append((key, hi - lo))
+                    gens.append(self._decompress_gen(f"d{k}_", string_lists[lo:hi], h, w, q, beta, coder_threads, out_uint8))
+            res = self._drive(gens)
             nv.status_check()
-            if len(res) == 1:
-                return res[0]
-            return tuple(torch.cat([r[j] for r in res], dim=0) for j in range(3))
+            # graph-owned outputs are overwritten by the next call on the same chunk shape: hand out copies
+            out = tuple(torch.cat([r[j] for r in res], dim=0) if len(res) > 1 else res[0][j].clone() for j in range(3))
+            for key, cnt in fresh:
+                sets[key] = _DecodeGraphs(self, self.engine(), cnt, h, w, out_uint8, q, beta)
+                while len(sets) > self.DECODE_GRAPH_CACHE:
+                    sets.popitem(last=False)
+            return out
 
     @torch.no_grad()
     def decompress(self, string_list, beta=0.0):

@@ -189,3 +189,26 @@ def decode_batch(decoders, indexes_list, tables, threads=0, outs=None):
     if rc:
         raise ValueError("rans decode: CDF index out of range")
     return outs
+
+
+class DecodePlan:
+    """A decode_batch call with fixed buffers (pinned index / symbol arrays that a caller reuses call after call):
+    the pointer arrays are marshalled once, ``run`` is one foreign call."""
+
+    def __init__(self, decoders, indexes_list, outs):
+        cnt = len(decoders)
+        assert cnt == len(indexes_list) == len(outs) and cnt > 0
+        u8 = all(i.dtype == np.uint8 for i in indexes_list)
+        assert u8 or all(i.dtype == np.int32 for i in indexes_list)
+        assert all(i.flags.c_contiguous and o.flags.c_contiguous and o.dtype == np.int32 and o.size == i.size
+                   for i, o in zip(indexes_list, outs))
+        self._keep = (decoders, indexes_list, outs)
+        PP = C.c_void_p * cnt
+        self._args = (cnt, PP(*[d._h for d in decoders]), PP(*[i.ctypes.data for i in indexes_list]),
+                      (C.c_int64 * cnt)(*[i.size for i in indexes_list]))
+        self._out = PP(*[o.ctypes.data for o in outs])
+        self._fn = lib().crdr_rans_decode_batch_u8 if u8 else lib().crdr_rans_decode_batch
+
+    def run(self, tables, threads=0):
+        if self._fn(*self._args, C.byref(tables.c), self._out, threads):
+            raise ValueError("rans decode: CDF index out of range")

@@ -28,8 +28,19 @@ def dec(*a, **k):
     mark("decode>"); r = _dec(*a, **k); mark("decode<"); return r
 def chk(*a, **k):
     mark("sync>"); r = _chk(*a, **k); mark("sync<"); return r
+_plan_run = rans.DecodePlan.run
+def plan_run(self, *a, **k):
+    mark("decode>"); r = _plan_run(self, *a, **k); mark("decode<"); return r
+rans.DecodePlan.run = plan_run
 rans.encode_batch, rans.decode_batch, nv.status_check = enc, dec, chk
 M.rans.encode_batch, M.rans.decode_batch, M.nv.status_check = enc, dec, chk
+# the scheduler's waits for a chunk's device -> host copy (model.py _drive): host idle = device (or copy) on the critical path
+class _Ev:
+    def __init__(self, ev): self.ev = ev
+    def synchronize(self):
+        mark("wait>"); self.ev.synchronize(); mark("wait<")
+_event = M._CharmModelCore._event
+M._CharmModelCore._event = staticmethod(lambda: _Ev(_event()))
 _an = model.engine().analysis
 def an(*a, **k):
     mark("analysis-enqueue>"); r = _an(*a, **k); mark("analysis-enqueue<"); return r
