@@ -192,9 +192,11 @@ def test_chunk_split_and_pipeline_scheduler(model):
     exactly once, and generators are resumed round-robin, each only after its own event has been synchronised."""
     cls = type(model)
     assert model._chunks(3) == [(0, 3)]                                     # below pipeline_min_images: one chunk
-    # compress_batch: equal chunks; decompress_batch: 2:1 (a short last chunk shortens the pipeline drain)
-    eq = model.pipeline_weights_compress
-    assert model._chunks(24, None, eq) == [(0, 12), (12, 24)] and model._chunks(9, None, eq) == [(0, 4), (4, 9)]
+    # compress_batch: 3:1 (a short last chunk shortens the device span before the exposed last host encode);
+    # decompress_batch: 2:1 (a short last chunk shortens the pipeline drain)
+    wc = model.pipeline_weights_compress
+    assert model._chunks(24, None, wc) == [(0, 18), (18, 24)] and model._chunks(9, None, wc) == [(0, 7), (7, 9)]
+    assert model._chunks(24, None, (1.0, 1.0)) == [(0, 12), (12, 24)] and model._chunks(9, None, (1.0, 1.0)) == [(0, 4), (4, 9)]
     assert model._chunks(24) == [(0, 16), (16, 24)] and model._chunks(9) == [(0, 6), (6, 9)]
     saved = model.pipeline_weights
     model.pipeline_chunks, model.pipeline_weights = 3, (3, 2, 1)
