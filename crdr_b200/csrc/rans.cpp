@@ -127,20 +127,29 @@ struct Encoder {
   uint64_t x = kRansL;
   uint32_t* wp = nullptr;  // next free word, emission order (the stream stores the words reversed)
 
-  // branch-free renormalisation: the low word is always stored, the pointer only advances when it was due
-  inline void renorm(uint64_t x_max) {
-    const uint64_t emit = (uint64_t)(x >= x_max);
-    *wp = (uint32_t)x;
-    wp += emit;
-    x >>= (emit << 5);   // shift instead of ?: (which compiles to an unpredictable jump)
+  // Renormalisation.  JUMP (one stream per thread): a jump -- at the codec's rates (about a bit per symbol) a word is due
+  // every few dozen symbols, the jump predicts well and compare + shift stay off the serial chain x -> x' (multiply-high,
+  // shift, multiply, add).  !JUMP (interleaved streams): branch free -- the low word is always stored, the pointer only
+  // advances when it was due, the state shifts by 0 or 32 (a ?: compiles to a jump).
+  template <bool JUMP>
+  __attribute__((always_inline)) inline void renorm(uint64_t x_max) {
+    if (JUMP) {
+      if (__builtin_expect(x >= x_max, 0)) { *wp++ = (uint32_t)x; x >>= 32; }
+    } else {
+      const uint64_t emit = (uint64_t)(x >= x_max);
+      *wp = (uint32_t)x;
+      wp += emit;
+      x >>= (emit << 5);
+    }
   }
-  inline void put(const EncSym& e) {
-    renorm(((kRansL >> kPrecision) << 32) * (uint64_t)e.freq);
+  template <bool JUMP>
+  __attribute__((always_inline)) inline void put(const EncSym& e) {
+    renorm<JUMP>(((kRansL >> kPrecision) << 32) * (uint64_t)e.freq);
     const uint64_t q = (uint64_t)(((unsigned __int128)x * e.rcp_freq) >> 64) >> e.rcp_shift;   // == x / freq
     x = x + e.bias + q * e.cmpl_freq;
   }
-  inline void put_bits(uint32_t val) {
-    renorm(((kRansL >> 16) << 32) * (uint64_t)(1u << (16 - kBypassBits)));
+  __attribute__((always_inline)) inline void put_bits(uint32_t val) {
+    renorm<false>(((kRansL >> 16) << 32) * (uint64_t)(1u << (16 - kBypassBits)));
     x = (x << kBypassBits) | val;
   }
 };
@@ -157,7 +166,7 @@ struct EncTables {
 };
 
 // One symbol into one stream's state; false on an index out of range.
-template <class SymT, class IdxT>
+template <bool JUMP, class SymT, class IdxT>
 __attribute__((always_inline)) inline bool encode_symbol(Encoder& enc, SymT symbol, IdxT index, const EncTables& T) {
   const int32_t ci = (int32_t)index;
   if (__builtin_expect((uint32_t)ci >= (uint32_t)T.n_cdf, 0)) return false;
@@ -174,7 +183,7 @@ __attribute__((always_inline)) inline bool encode_symbol(Encoder& enc, SymT symb
     enc.put_bits((uint32_t)rem);
     for (int32_t r = 0; r < full; ++r) enc.put_bits((uint32_t)kBypassMax);
   }
-  enc.put(T.esym[(int64_t)ci * T.stride + value]);
+  enc.put<JUMP>(T.esym[(int64_t)ci * T.stride + value]);
   return true;
 }
 
@@ -182,9 +191,13 @@ constexpr int kMaxInterleave = 4;
 
 // K streams of n symbols each, side by side in one thread (their state-update chains overlap in the out-of-order
 // core); lengths[k] = bytes written, -(bytes needed) when out_cap[k] is too small, INT64_MIN on a bad index.
-template <int K, class SymT, class IdxT>
-void encode_many(const SymT* const* symbols, const IdxT* const* indexes, int64_t n, const TableRef& tr, uint8_t* const* out,
-                 const int64_t* out_cap, int64_t* lengths) {
+// (BMI2: the variable shifts on the chain become one-cycle shrx / shlx; every x86-64 server core since 2013 has it)
+template <bool BMI2, int K, class SymT, class IdxT>
+#if defined(__x86_64__)
+__attribute__((target(BMI2 ? "bmi2" : "sse2")))
+#endif
+void encode_many_impl(const SymT* const* symbols, const IdxT* const* indexes, int64_t n, const TableRef& tr, uint8_t* const* out,
+                      const int64_t* out_cap, int64_t* lengths) {
   const EncTables T(tr);
   // a table symbol emits at most one word; an escape adds at most 2 + 8 + 1 nibbles (raw < 2^32) = two more words.
   // Per-thread grow-only scratch: a fresh multi-megabyte allocation per stream is an mmap / munmap pair, and a dozen
@@ -203,7 +216,7 @@ void encode_many(const SymT* const* symbols, const IdxT* const* indexes, int64_t
   bool ok = true;
   for (int64_t i = n - 1; i >= 0 && ok; --i) {
 #pragma GCC unroll 8
-    for (int k = 0; k < K; ++k) ok &= encode_symbol(enc[k], sy[k][i], ix[k][i], T);
+    for (int k = 0; k < K; ++k) ok &= encode_symbol<K == 1>(enc[k], sy[k][i], ix[k][i], T);
   }
   for (int k = 0; k < K; ++k) {
     if (!ok) { lengths[k] = std::numeric_limits<int64_t>::min(); continue; }
@@ -219,6 +232,16 @@ void encode_many(const SymT* const* symbols, const IdxT* const* indexes, int64_t
     for (int64_t j = nwords; j-- > 0; pos += 4) std::memcpy(o + pos, &words[(size_t)j], 4);
     lengths[k] = nbytes;
   }
+}
+
+template <int K, class SymT, class IdxT>
+void encode_many(const SymT* const* symbols, const IdxT* const* indexes, int64_t n, const TableRef& tr, uint8_t* const* out,
+                 const int64_t* out_cap, int64_t* lengths) {
+#if defined(__x86_64__)
+  static const bool have_bmi2 = __builtin_cpu_supports("bmi2");
+  if (have_bmi2) return encode_many_impl<true, K>(symbols, indexes, n, tr, out, out_cap, lengths);
+#endif
+  return encode_many_impl<false, K>(symbols, indexes, n, tr, out, out_cap, lengths);
 }
 
 template <class SymT, class IdxT>
@@ -383,8 +406,9 @@ int decode_some(Decoder* const* d, const IdxT* const* indexes, int64_t n, const 
 }
 
 // How many equal-length streams one thread should code side by side: K interleaved streams cost about
-// 1 + step (K - 1) single-stream times (measured: decoder 0.4 -- its chain is latency bound; encoder 0.75 -- it is
-// nearly throughput bound already), and the job ends with its last round of bundles.
+// 1 + step (K - 1) single-stream times (measured: decoder 0.4 -- its chain is latency bound; encoder 1.0 -- with the
+// renormalisation jump its single-stream loop is throughput bound already, so it never interleaves unless
+// CRDR_CODER_INTERLEAVE forces it), and the job ends with its last round of bundles.
 int pick_interleave(int32_t count, int nt, double step) {
   static const int forced = [] { const char* e = std::getenv("CRDR_CODER_INTERLEAVE"); return e && *e ? std::atoi(e) : 0; }();
   if (forced >= 1) return std::min(forced, kMaxInterleave);
@@ -566,7 +590,7 @@ int encode_batch_impl(int32_t count, const SymT* const* symbols, const IdxT* con
   if (count <= 0) return 0;
   if (!t) return 1;
   const TableRef tr(t);
-  const int K = equal_lengths(count, n) ? pick_interleave(count, effective_threads(count, threads), 0.75) : 1;
+  const int K = equal_lengths(count, n) ? pick_interleave(count, effective_threads(count, threads), 1.0) : 1;
   const int32_t bundles = (count + K - 1) / K;
   parallel_for(bundles, threads, [&](int32_t b) {
     const int32_t lo = b * K, m = std::min<int32_t>(K, count - lo);
