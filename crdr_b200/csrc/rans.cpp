@@ -148,8 +148,9 @@ struct Encoder {
     const uint64_t q = (uint64_t)(((unsigned __int128)x * e.rcp_freq) >> 64) >> e.rcp_shift;   // == x / freq
     x = x + e.bias + q * e.cmpl_freq;
   }
+  template <bool JUMP>
   __attribute__((always_inline)) inline void put_bits(uint32_t val) {
-    renorm<false>(((kRansL >> 16) << 32) * (uint64_t)(1u << (16 - kBypassBits)));
+    renorm<JUMP>(((kRansL >> 16) << 32) * (uint64_t)(1u << (16 - kBypassBits)));
     x = (x << kBypassBits) | val;
   }
 };
@@ -178,10 +179,10 @@ __attribute__((always_inline)) inline bool encode_symbol(Encoder& enc, SymT symb
     int32_t nb = 0;
     while (nb < 8 && (raw >> (nb * kBypassBits)) != 0) ++nb;
     // forward order is: [run of 15s][remainder][nibble 0 .. nibble nb-1]; feed it reversed
-    for (int32_t j = nb - 1; j >= 0; --j) enc.put_bits((raw >> (j * kBypassBits)) & kBypassMax);
+    for (int32_t j = nb - 1; j >= 0; --j) enc.put_bits<JUMP>((raw >> (j * kBypassBits)) & kBypassMax);
     int32_t full = nb / kBypassMax, rem = nb % kBypassMax;
-    enc.put_bits((uint32_t)rem);
-    for (int32_t r = 0; r < full; ++r) enc.put_bits((uint32_t)kBypassMax);
+    enc.put_bits<JUMP>((uint32_t)rem);
+    for (int32_t r = 0; r < full; ++r) enc.put_bits<JUMP>((uint32_t)kBypassMax);
   }
   enc.put<JUMP>(T.esym[(int64_t)ci * T.stride + value]);
   return true;
@@ -263,7 +264,7 @@ struct Decoder {
 // compare (AVX2) or a short scalar walk resolves it; both continue in steps while a whole group compared <= cum.
 #if defined(__x86_64__)
 #include <immintrin.h>
-__attribute__((target("avx2"))) static inline int32_t find_slot_avx2(const int32_t* row, int32_t s, int32_t cum) {
+__attribute__((target("avx2,bmi2"))) static inline int32_t find_slot_avx2(const int32_t* row, int32_t s, int32_t cum) {
   const __m256i c = _mm256_set1_epi32(cum);
   for (;;) {
     const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(row + s + 1));
@@ -321,7 +322,7 @@ struct DecTables {
 // returns false on an index out of range
 template <bool AVX2, bool RENORM_JUMP, class IdxT, class OutT>
 #if defined(__x86_64__)
-__attribute__((target("avx2"), always_inline))
+__attribute__((target("avx2,bmi2"), always_inline))
 #else
 __attribute__((always_inline))
 #endif
@@ -375,7 +376,7 @@ inline bool decode_symbol(DecState& st, const DecTables& T, IdxT index, OutT* ou
 // K streams of equal length side by side in one thread: their serial chains overlap in the out-of-order core
 template <bool AVX2, int K, class IdxT, class OutT>
 #if defined(__x86_64__)
-__attribute__((target("avx2")))
+__attribute__((target("avx2,bmi2")))
 #endif
 int decode_loop(Decoder* const* d, const IdxT* const* indexes, int64_t n, const TableRef& tr, OutT* const* out) {
   const DecTables T(tr);
@@ -399,7 +400,7 @@ done:
 template <int K, class IdxT, class OutT>
 int decode_some(Decoder* const* d, const IdxT* const* indexes, int64_t n, const TableRef& tr, OutT* const* out) {
 #if defined(__x86_64__)
-  static const bool have_avx2 = __builtin_cpu_supports("avx2");
+  static const bool have_avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
   if (have_avx2) return decode_loop<true, K>(d, indexes, n, tr, out);
 #endif
   return decode_loop<false, K>(d, indexes, n, tr, out);

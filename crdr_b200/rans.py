@@ -151,7 +151,9 @@ class Decoder:
             self.set_stream(stream)
 
     def set_stream(self, stream):
-        if lib().crdr_rans_decoder_set_stream(self._h, bytes(stream), len(stream)):
+        if not isinstance(stream, bytes):
+            stream = bytes(stream)
+        if lib().crdr_rans_decoder_set_stream(self._h, stream, len(stream)):
             raise ValueError("rans decoder: stream shorter than 8 bytes")
 
     def decode_stream(self, indexes, tables, out=None):
