@@ -412,11 +412,13 @@ def main():
     # the caller's result buffer: allocated once like any serving loop would (cudaHostAlloc of 113 MB costs 60-90 ms)
     host_img = torch.empty((B, 3, H, W), dtype=torch.uint8, pin_memory=True)
 
-    e2e_step(0)
+    E2E_WARMUP = 3   # untimed: decompress_batch captures the CUDA graphs of a chunk shape at the end of its second call
+    for i in range(E2E_WARMUP):
+        e2e_step(i)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.e2e_steps):
-        outs, host = e2e_step(1 + i)
+        outs, host = e2e_step(E2E_WARMUP + i)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / args.e2e_steps
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)

@@ -72,6 +72,7 @@ class CodecEngine:
         self.stride = 64
         self._graphs = OrderedDict()   # CUDA graphs of the device-only launch sequences of small calls (LRU)
         self.decode_graph_sets = OrderedDict()   # model._DecodeGraphs per decompress chunk shape (LRU)
+        self.decode_graph_seen = OrderedDict()   # eager calls per chunk shape that has no set yet
 
     # ------------------------------------------------------------------ device-side stages
     def padded(self, h, w):
@@ -738,9 +739,11 @@ class _CharmModelCore(_CodecModelBase):
         y_hat = eng.to_nchw(yhat32)
         return img, z_hat, y_hat
 
-    # CUDA graphs of the decode segments (class _DecodeGraphs): a chunk shape is coded eagerly the first time it is seen
-    # (that call also loads every kernel the sequence uses) and captured right after; later calls replay.
+    # CUDA graphs of the decode segments (class _DecodeGraphs): a chunk shape is coded eagerly the first
+    # DECODE_GRAPH_AFTER times it is seen (those calls also load every kernel the sequence uses) and captured at the end of
+    # the last of them; later calls replay.  A data set whose image sizes never repeat therefore never pays for a capture.
     DECODE_GRAPH_MAX_PIXELS = int(os.environ.get("CRDR_DECODE_GRAPH_MAX_PIXELS", str(32 * 512 * 768)))
+    DECODE_GRAPH_AFTER = int(os.environ.get("CRDR_DECODE_GRAPH_AFTER", "2"))
     DECODE_GRAPH_CACHE = 6
     decode_graphs_enabled = os.environ.get("CRDR_DECODE_GRAPHS", "1") != "0"
 
@@ -794,13 +797,19 @@ class _CharmModelCore(_CodecModelBase):
                     gens.append(self._decompress_gen_graphed(gs, string_lists[lo:hi], q, beta, coder_threads))
                 else:
                     if key is not None:
-                        fresh.append((key, hi - lo))
+                        seen = self.engine().decode_graph_seen
+                        seen[key] = seen.pop(key, 0) + 1
+                        while len(seen) > 64:
+                            seen.popitem(last=False)
+                        if seen[key] >= self.DECODE_GRAPH_AFTER:
+                            fresh.append((key, hi - lo))
                     gens.append(self._decompress_gen(f"d{k}_", string_lists[lo:hi], h, w, q, beta, coder_threads, out_uint8))
             res = self._drive(gens)
             nv.status_check()
             # graph-owned outputs are overwritten by the next call on the same chunk shape: hand out copies
             out = tuple(torch.cat([r[j] for r in res], dim=0) if len(res) > 1 else res[0][j].clone() for j in range(3))
             for key, cnt in fresh:
+                self.engine().decode_graph_seen.pop(key, None)
                 sets[key] = _DecodeGraphs(self, self.engine(), cnt, h, w, out_uint8, q, beta)
                 while len(sets) > self.DECODE_GRAPH_CACHE:
                     sets.popitem(last=False)

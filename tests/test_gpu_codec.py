@@ -211,19 +211,20 @@ def test_chunk_pipelining_is_transparent(models):
 
 
 def test_decode_graph_replay_is_transparent(models):
-    """decompress_batch codes a chunk shape eagerly the first time and replays CUDA graphs of its device segments from the
-    second call on (model._DecodeGraphs).  Replays must return the bits of the eager path for every (q, beta), also when q and
+    """decompress_batch codes a chunk shape eagerly the first two times and replays CUDA graphs of its device segments from
+    the third call on (model._DecodeGraphs).  Replays must return the bits of the eager path for every (q, beta), also when q and
     beta change between replays of the same set, for float and uint8 images, and after the set was captured at another q."""
     import fixtures
     model, _ = models(True)
     x = fixtures.image(9, 128, 192, seed=91)
-    cases = [(1.5, 2.0), (0.0, 0.0), (4.0, 3.84), (1.5, 2.0)]
+    cases = [(1.5, 2.0), (0.0, 0.0), (4.0, 3.84), (1.5, 2.0), (0.0, 3.84)]
     streams = {q: [o["string_list"] for o in model.compress_batch(x, q)] for q in {c[0] for c in cases}}
     eng = model.engine()
 
     def run(enabled, out_uint8):
         model.decode_graphs_enabled = enabled
         eng.decode_graph_sets.clear()
+        eng.decode_graph_seen.clear()
         got = []
         for q, beta in cases:
             img, z_hat, y_hat = model.decompress_batch(streams[q], beta=beta, out_uint8=out_uint8)
@@ -234,7 +235,7 @@ def test_decode_graph_replay_is_transparent(models):
         for out_uint8 in (False, True):
             eager = run(False, out_uint8)
             assert len(eng.decode_graph_sets) == 0
-            replay = run(True, out_uint8)                      # call 1 eager + capture, calls 2-4 replay
+            replay = run(True, out_uint8)                      # calls 1-2 eager (capture after the second), calls 3-5 replay
             assert len(eng.decode_graph_sets) == 2             # one set per pipelined chunk
             for a, b in zip(eager, replay):
                 assert all(torch.equal(u, v) for u, v in zip(a, b))

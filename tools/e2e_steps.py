@@ -11,13 +11,13 @@ import os
 model.pipeline_chunks = int(os.environ.get('CHUNKS', '2'))
 if os.environ.get('WEIGHTS'):
     model.pipeline_weights = tuple(float(v) for v in os.environ['WEIGHTS'].split(','))
-x = fixtures.image(24, 512, 768, seed=100).pin_memory()
+x = (fixtures.image(24, 512, 768, seed=100) * 127.5 + 127.5).clamp(0, 255).to(torch.uint8).pin_memory()   # uint8 RGB like bench.py
 host = None
 def T(): torch.cuda.synchronize(); return time.perf_counter()
-for i in range(6):
+for i in range(8):
     q, beta = SWEEP[i % 5], BETAS[i % 2]
     t0 = T(); outs = model.compress_batch(x, q); t1 = T()
-    img, _, _ = model.decompress_batch([o["string_list"] for o in outs], beta=beta); t2 = T()
+    img, _, _ = model.decompress_batch([o["string_list"] for o in outs], beta=beta, out_uint8=True); t2 = T()
     if host is None:
         host = torch.empty(img.shape, dtype=img.dtype, pin_memory=True)
     t3 = T(); host.copy_(img, non_blocking=True); t4 = T()
