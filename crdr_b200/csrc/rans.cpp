@@ -254,7 +254,9 @@ int64_t encode_one(const SymT* symbols, const IdxT* indexes, int64_t n, const Ta
 }
 
 struct Decoder {
-  std::vector<uint32_t> buf;
+  std::vector<uint32_t> buf;          // private copy of the stream (crdr_rans_decoder_set_stream) ...
+  const uint32_t* words = nullptr;    // ... or the caller's bytes (crdr_rans_decoder_set_stream_view); either way the words
+  size_t nwords = 0;
   size_t pos = 0;
   uint64_t x = 0;
 };
@@ -302,8 +304,8 @@ struct DecState {
     return (raw & 1) ? -value - 1 : value + max_value;
   }
 };
-inline DecState load_state(const Decoder* d) { return DecState{d->x, d->pos, d->buf.data(), d->buf.size()}; }
-inline void store_state(Decoder* d, const DecState& st) { d->x = st.x; d->pos = std::min(st.pos, d->buf.size()); }
+inline DecState load_state(const Decoder* d) { return DecState{d->x, d->pos, d->words, d->nwords}; }
+inline void store_state(Decoder* d, const DecState& st) { d->x = st.x; d->pos = std::min(st.pos, d->nwords); }
 
 struct DecTables {
   const uint64_t* bucket;
@@ -710,7 +712,21 @@ int crdr_rans_decoder_set_stream(void* dec, const uint8_t* stream, int64_t nbyte
   if (!d || nbytes < 8) return 1;
   d->buf.assign((size_t)((nbytes + 3) / 4), 0u);
   std::memcpy(d->buf.data(), stream, (size_t)nbytes);
+  d->words = d->buf.data();
+  d->nwords = d->buf.size();
   d->x = (uint64_t)d->buf[0] | ((uint64_t)d->buf[1] << 32);
+  d->pos = 2;
+  return 0;
+}
+
+int crdr_rans_decoder_set_stream_view(void* dec, const uint8_t* stream, int64_t nbytes) {
+  Decoder* d = static_cast<Decoder*>(dec);
+  if (!d || !stream || nbytes < 8) return 1;
+  if (nbytes % 4 != 0 || ((uintptr_t)stream & 3) != 0) return crdr_rans_decoder_set_stream(dec, stream, nbytes);
+  d->buf.clear();
+  d->words = reinterpret_cast<const uint32_t*>(stream);
+  d->nwords = (size_t)(nbytes / 4);
+  d->x = (uint64_t)d->words[0] | ((uint64_t)d->words[1] << 32);
   d->pos = 2;
   return 0;
 }

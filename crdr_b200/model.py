@@ -321,7 +321,8 @@ class _DecodeGraphs:
         def capture(fn):
             g = torch.cuda.CUDAGraph()
             l0 = nv.LAUNCH_COUNT[0]
-            with torch.cuda.graph(g, pool=self.pool):
+            # thread_local: other host threads (PNG workers of compress.py, NCCL's watchdog) keep making CUDA calls
+            with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
                 fn()
             self.segments.append((g, nv.LAUNCH_COUNT[0] - l0))
 

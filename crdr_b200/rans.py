@@ -14,7 +14,7 @@ class CdfTables(C.Structure):
 RANS_SYMBOLS = [
     "crdr_rans_tables_prepare", "crdr_rans_tables_free",
     "crdr_pmf_to_quantized_cdf", "crdr_rans_encode_with_indexes", "crdr_rans_encode_batch",
-    "crdr_rans_decoder_new", "crdr_rans_decoder_free", "crdr_rans_decoder_set_stream",
+    "crdr_rans_decoder_new", "crdr_rans_decoder_free", "crdr_rans_decoder_set_stream", "crdr_rans_decoder_set_stream_view",
     "crdr_rans_decoder_decode_stream", "crdr_rans_decode_batch",
     "crdr_rans_encode_batch_i16u8", "crdr_rans_decode_batch_u8", "crdr_rans_pool_info",
 ]
@@ -40,6 +40,7 @@ def lib():
         L.crdr_rans_decoder_new.restype = vp
         L.crdr_rans_decoder_free.argtypes = [vp]
         L.crdr_rans_decoder_set_stream.argtypes = [vp, C.c_char_p, i64]
+        L.crdr_rans_decoder_set_stream_view.argtypes = [vp, C.c_char_p, i64]
         L.crdr_rans_decoder_decode_stream.argtypes = [vp, vp, i64, C.POINTER(CdfTables), vp]
         L.crdr_rans_decode_batch.argtypes = [i32, vp, vp, vp, C.POINTER(CdfTables), vp, i32]
         L.crdr_rans_encode_batch_i16u8.argtypes = [i32, vp, vp, vp, C.POINTER(CdfTables), vp, vp, vp, i32]
@@ -153,7 +154,8 @@ class Decoder:
     def set_stream(self, stream):
         if not isinstance(stream, bytes):
             stream = bytes(stream)
-        if lib().crdr_rans_decoder_set_stream(self._h, stream, len(stream)):
+        self._stream = stream   # the decoder reads these bytes in place (immutable, kept alive here)
+        if lib().crdr_rans_decoder_set_stream_view(self._h, stream, len(stream)):
             raise ValueError("rans decoder: stream shorter than 8 bytes")
 
     def decode_stream(self, indexes, tables, out=None):

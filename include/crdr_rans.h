@@ -61,6 +61,10 @@ void* crdr_rans_decoder_new(void);
 void crdr_rans_decoder_free(void* dec);
 /* Copies the stream; subsequent decode_stream calls continue from the same coder state. */
 int crdr_rans_decoder_set_stream(void* dec, const uint8_t* stream, int64_t nbytes);
+/* Same without the copy: the decoder reads the caller's bytes, which must stay valid and unchanged until the next
+ * set_stream* call on this decoder or its release (the Python front-end keeps a reference to the bytes object).
+ * Streams whose length is not a multiple of 4 or whose address is not 4-byte aligned are copied as above. */
+int crdr_rans_decoder_set_stream_view(void* dec, const uint8_t* stream, int64_t nbytes);
 int crdr_rans_decoder_decode_stream(void* dec, const int32_t* indexes, int64_t n, const crdr_cdf_tables* t,
                                     int32_t* out);
 /* decoders[i] decodes n[i] symbols with indexes[i] into out[i], concurrently. */

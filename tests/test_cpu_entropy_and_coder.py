@@ -248,3 +248,27 @@ def test_interleaved_streams_match_single_stream_and_oracle(product_gc, oracle):
         rans.encode_batch(syms[:4], bad, T, threads=1)
     with pytest.raises(ValueError):
         rans.decode_batch([rans.Decoder(s) for s in single[:4]], bad, T, threads=1)
+
+
+def test_decode_plan_and_stream_views(product_gc):
+    """rans.DecodePlan (pre-marshalled decode_batch call on fixed buffers, persistent decoders re-armed with set_stream)
+    and the zero-copy stream view of the decoder return what decode_batch returns, call after call."""
+    from crdr_b200 import rans
+    T = product_gc.coder_tables()
+    rng = np.random.default_rng(23)
+    n, cnt = 3000, 5
+    decs = [rans.Decoder() for _ in range(cnt)]
+    ix_buf = [np.zeros(n, np.uint8) for _ in range(cnt)]
+    out_buf = [np.zeros(n, np.int32) for _ in range(cnt)]
+    plan = rans.DecodePlan(decs, ix_buf, out_buf)
+    for rep in range(3):
+        idxs = [rng.integers(0, 64, n).astype(np.uint8) for _ in range(cnt)]
+        syms = [rng.integers(-40, 40, n).astype(np.int32) for _ in range(cnt)]
+        streams = rans.encode_batch(syms, [i.astype(np.int32) for i in idxs], T)
+        for d, s, b, i in zip(decs, streams, ix_buf, idxs):
+            d.set_stream(s if rep != 1 else bytearray(s))      # bytes are read in place; other buffers are converted first
+            b[:] = i
+        plan.run(T, threads=2 if rep else 0)
+        assert all(np.array_equal(o, s) for o, s in zip(out_buf, syms))
+    with pytest.raises(ValueError):
+        rans.Decoder(b"\x00" * 7)
