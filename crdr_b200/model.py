@@ -598,6 +598,28 @@ class _CharmModelCore(_CodecModelBase):
     # pass whatever the chunk size -- a short last chunk only shortens the device span that precedes it.  Measured
     # (tools/e2e_pipeline_sweep.py, 24 x 512x768, ms per call): one chunk 48.6, 1:1 46.9, 2:1 46.0, 3:1 44.4, 1:1:1 47.6
 
+    # Few coder threads (one process per GPU on a slice of the host: 4 cores per rank at N = 8): the host coder, not the
+    # device, paces the pipeline, so the chunks are cut for the coder -- several rounds of streams per chunk hide behind the
+    # next chunk's device span.  Measured on one GPU confined to 4 cores (`CRDR_CODER_THREADS=4 taskset -c 0-3 python
+    # tools/e2e_pipeline_sweep.py`, ms per 24-image call): compress 3:1 50.1, 2:1 45.5, 1:1 48.7, 3:2:1 45.5, 1:1:1 48.3;
+    # decompress 2:1 42.7, 1:1 38.2, 1:1:1 36.2, 1:1:1:1 41.1.  Applies when neither the environment nor the instance
+    # sets a pipeline shape.
+    pipeline_few_threads = int(os.environ.get("CRDR_PIPELINE_FEW_THREADS", "12"))
+    pipeline_weights_few = (1.0, 1.0, 1.0)
+    pipeline_weights_compress_few = (2.0, 1.0)
+
+    def _pipeline_shape(self, compress):
+        """(chunk count, weights) of compress_batch / decompress_batch."""
+        names = ("pipeline_chunks", "pipeline_weights", "pipeline_chunks_compress", "pipeline_weights_compress")
+        envs = ("CRDR_PIPELINE_CHUNKS", "CRDR_PIPELINE_WEIGHTS", "CRDR_PIPELINE_CHUNKS_COMPRESS", "CRDR_PIPELINE_WEIGHTS_COMPRESS")
+        explicit = any(k in self.__dict__ for k in names) or any(os.environ.get(e) for e in envs)
+        if not explicit and rans.pool_info()[0] < self.pipeline_few_threads:
+            w = self.pipeline_weights_compress_few if compress else self.pipeline_weights_few
+            return len(w), w
+        if compress:
+            return (self.pipeline_chunks_compress or self.pipeline_chunks), self.pipeline_weights_compress
+        return self.pipeline_chunks, self.pipeline_weights
+
     def _chunks(self, n, chunks=None, weights=None):
         k = (chunks or self.pipeline_chunks) if n >= self.pipeline_min_images else 1
         k = max(1, min(k, n))
@@ -690,7 +712,7 @@ class _CharmModelCore(_CodecModelBase):
         with torch.cuda.device(self.engine().device):
             nv.status_reset()
             res = self._drive([self._compress_gen(f"c{k}_", real_images[lo:hi], rate_ind, return_tensors, coder_threads)
-                               for k, (lo, hi) in enumerate(self._chunks(n, self.pipeline_chunks_compress, self.pipeline_weights_compress))])
+                               for k, (lo, hi) in enumerate(self._chunks(n, *self._pipeline_shape(compress=True)))])
             nv.status_check()
         return [r for chunk in res for r in chunk]
 
@@ -790,7 +812,7 @@ class _CharmModelCore(_CodecModelBase):
             nv.status_reset()
             sets = self.engine().decode_graph_sets   # owned by the engine: they hold its weight pointers
             gens, fresh = [], []
-            for k, (lo, hi) in enumerate(self._chunks(n)):
+            for k, (lo, hi) in enumerate(self._chunks(n, *self._pipeline_shape(compress=False))):
                 key = self._decode_graph_key(f"d{k}_", hi - lo, h, w, out_uint8)
                 gs = sets.get(key) if key is not None else None
                 if gs is not None:

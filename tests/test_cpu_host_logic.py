@@ -198,6 +198,20 @@ def test_chunk_split_and_pipeline_scheduler(model):
     assert model._chunks(24, None, wc) == [(0, 18), (18, 24)] and model._chunks(9, None, wc) == [(0, 7), (7, 9)]
     assert model._chunks(24, None, (1.0, 1.0)) == [(0, 12), (12, 24)] and model._chunks(9, None, (1.0, 1.0)) == [(0, 4), (4, 9)]
     assert model._chunks(24) == [(0, 16), (16, 24)] and model._chunks(9) == [(0, 6), (6, 9)]
+    # the shape the codec calls use: the defaults above with enough coder threads, the few-thread profile (coder paced:
+    # compress 2:1, decompress 1:1:1) on a small slice of the host, and never when the instance sets a shape itself
+    saved_few = cls.pipeline_few_threads
+    try:
+        cls.pipeline_few_threads = 0
+        assert model._pipeline_shape(True) == (2, wc) and model._pipeline_shape(False) == (2, model.pipeline_weights)
+        cls.pipeline_few_threads = 10 ** 6
+        assert model._pipeline_shape(True) == (2, (2.0, 1.0)) and model._pipeline_shape(False) == (3, (1.0, 1.0, 1.0))
+        assert model._chunks(24, *model._pipeline_shape(False)) == [(0, 8), (8, 16), (16, 24)]
+        model.pipeline_chunks = 2
+        assert model._pipeline_shape(False) == (2, model.pipeline_weights)
+        del model.pipeline_chunks
+    finally:
+        cls.pipeline_few_threads = saved_few
     saved = model.pipeline_weights
     model.pipeline_chunks, model.pipeline_weights = 3, (3, 2, 1)
     try:

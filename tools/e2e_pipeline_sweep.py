@@ -23,13 +23,13 @@ def timed(fn, reps=5, warm=2):
 outs = model.compress_batch(x, 1.5)
 streams = [o["string_list"] for o in outs]
 print("decompress_batch (24 x 512x768, uint8 out): chunks / weights -> median, min ms")
-for weights in [(2, 1), (1, 1), (3, 1), (3, 2), (5, 3), (3, 2, 1), (2, 2, 1), (2, 1, 1), (4, 2, 1)]:
+for weights in [(2, 1), (1, 1), (3, 2), (3, 2, 1), (2, 2, 1), (1, 1, 1), (4, 2, 1), (1, 1, 1, 1)]:
     model.pipeline_chunks, model.pipeline_weights = len(weights), tuple(float(w) for w in weights)
     _, med, mn = timed(lambda: model.decompress_batch(streams, beta=3.84, out_uint8=True))
     print(f"  {str(weights):16s} {med:6.1f} {mn:6.1f}", flush=True)
     model.engine().decode_graph_sets.clear()
 print("compress_batch: chunks / weights -> median, min ms")
-for weights in [(1, 1), (2, 1), (3, 1), (4, 1), (5, 1), (7, 1), (11, 1), (6, 1, 1), (8, 3, 1)]:
+for weights in [(1, 1), (2, 1), (3, 1), (4, 1), (1, 1, 1), (2, 2, 1), (3, 2, 1), (1, 1, 1, 1), (3, 3, 2, 1), (6, 1, 1)]:
     model.pipeline_chunks_compress, model.pipeline_weights_compress = len(weights), tuple(float(w) for w in weights)
     _, med, mn = timed(lambda: model.compress_batch(x, 1.5))
     print(f"  {str(weights):16s} {med:6.1f} {mn:6.1f}", flush=True)
