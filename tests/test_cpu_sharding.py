@@ -140,3 +140,42 @@ def test_stale_rank_files_are_not_merged(tmp_path):
     stale.write_text(json.dumps([{"img_name": "b.png"}]))          # a fresh delivery of rank 1
     rows = sharding.gather_rows([{"img_name": "a.png"}], 0, 2, str(tmp_path), timeout_s=5.0)
     assert sorted(r["img_name"] for r in rows) == ["a.png", "b.png"]
+
+
+def test_coder_pool_takes_the_ranks_slice_of_the_host():
+    """One process per GPU: the coder pool of rank r lives on the r-th of LOCAL_WORLD_SIZE equal slices of the CPUs the
+    process may use (rans.cpp Pool), interleaves streams when they outnumber its threads, and still returns the bytes of a
+    single-threaded run."""
+    import subprocess
+    import sys
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if ncpu < 4:
+        pytest.skip("needs at least 4 CPUs")
+    code = r"""
+import sys, hashlib, numpy as np
+sys.path.insert(0, %r)
+from crdr_b200 import rans
+pmf = np.exp(-0.5 * ((np.arange(41) - 20) / 4.0) ** 2).astype(np.float32); pmf /= pmf.sum()
+cdf = rans.pmf_to_quantized_cdf(pmf)
+t = rans.Tables(np.stack([cdf] * 3), [cdf.size] * 3, [-20] * 3)
+rng = np.random.default_rng(5)
+syms = [np.rint(rng.normal(0, 5, 4000)).astype(np.int32) for _ in range(11)]
+idxs = [rng.integers(0, 3, 4000).astype(np.int32) for _ in range(11)]
+out = rans.encode_batch(syms, idxs, t)
+back = rans.decode_batch([rans.Decoder(s) for s in out], idxs, t)
+assert all(np.array_equal(a, b) for a, b in zip(back, syms))
+print(rans.pool_info()[0], rans.pool_info()[1], hashlib.sha1(b"".join(out)).hexdigest())
+""" % ROOT
+    cpus = sorted(os.sched_getaffinity(0))
+    lines = []
+    for env in ({}, {"LOCAL_WORLD_SIZE": "4", "LOCAL_RANK": "1"}, {"LOCAL_WORLD_SIZE": "2", "LOCAL_RANK": "1", "CRDR_CODER_THREADS": "1"}):
+        e = {k: v for k, v in os.environ.items() if k not in ("LOCAL_WORLD_SIZE", "LOCAL_RANK", "WORLD_SIZE", "RANK", "CRDR_CODER_THREADS")}
+        e.update(env)
+        r = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        lines.append(r.stdout.split())
+    (t0, c0, h0), (t1, c1, h1), (t2, c2, h2) = lines
+    assert int(t0) == min(ncpu, 32) and int(c0) == cpus[0]
+    assert int(t1) == ncpu // 4 and int(c1) == cpus[ncpu // 4]            # second slice of four
+    assert int(t2) == 1 and int(c2) == cpus[ncpu // 2]
+    assert h0 == h1 == h2                                                  # same bytes whatever the pool
