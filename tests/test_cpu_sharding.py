@@ -148,6 +148,7 @@ def test_coder_pool_takes_the_ranks_slice_of_the_host():
     single-threaded run."""
     import subprocess
     import sys
+    import pytest
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if ncpu < 4:
         pytest.skip("needs at least 4 CPUs")
